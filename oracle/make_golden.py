@@ -1,0 +1,170 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN source files.
+
+Runs only in the build container (needs /root/reference and numba); the fixtures it writes are
+committed so that neither the tests nor the GPU box ever read /root/reference.
+
+How the reference is run:
+  * one subprocess per configuration, because numba freezes the configure_me globals;
+  * a generated configure_me.py and a 15-line ``pyfftw`` shim (scipy.fft, complex128, normalised
+    inverse -- pyFFTW's default) are placed ahead of /root/reference/src on sys.path;
+  * density.py, fourier_utils.py, potential.py, integrate.py, cosmology.py are imported UNMODIFIED;
+  * numba.set_num_threads(1): the reference's threaded deposit is a data race;
+  * fgrid[0,0,0] = 0: the reference leaves the DC entry uninitialised; the harness
+    owns fgrid (pmesh.py:54,61), so pinning it is not a change to the reference;
+  * the loop body is pmesh.py:56-63 restated verbatim (pmesh.py itself imports h5py/matplotlib).
+
+Usage:  python oracle/make_golden.py            (writes tests/golden/)
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import textwrap
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SRC = "/root/reference/src"
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+CONFIGURE_ME = """\
+N_PARTS = {N_PARTS}
+N_CELLS = {N_CELLS}
+BOX_SIZE = 100
+N_CPU = 1
+RANDOM_SEED = 38
+STEPS = {STEPS}
+N_SAVE_FILES = 100
+N_PLOTS = 100
+PLOT_STEPS = False
+PLOT_PROJECTIONS = False
+PLOT_GRF = False
+SAVE_DATA = False
+SAVE_DENSITY = False
+PRINT_STATUS = False
+RESTART = False
+RESTART_FROM_N = 0
+POWER = 1.00
+LCDM_TRANSFER_FUNCTION = True
+OMEGA_M0 = 0.31
+OMEGA_B0 = 0.04
+OMEGA_K0 = 0.00
+OMEGA_LAMBDA0 = 0.69
+H0 = 0.68
+A_INIT = {A_INIT}
+A_END = 1.00
+"""
+
+PYFFTW_SHIM = """\
+# Stand-in for pyFFTW (not installable here): same constructor/call shape as potential.py:20,27 uses.
+import scipy.fft
+class FFTW:
+    def __init__(self, input_array, output_array, direction='FFTW_FORWARD', axes=(0,), threads=1, **kw):
+        self.i, self.o, self.d, self.axes, self.t = input_array, output_array, direction, axes, threads
+    def __call__(self):
+        fn = scipy.fft.fftn if self.d == 'FFTW_FORWARD' else scipy.fft.ifftn
+        self.o[...] = fn(self.i, axes=self.axes, workers=self.t)
+        return self.o
+"""
+
+WORKER = """\
+import sys, json
+import numpy as np
+import numba as nb
+nb.set_num_threads(1)
+case = json.loads(sys.argv[1])
+sys.path.insert(0, {repo!r})
+from oracle.oracle import lattice_ic          # input generator only (no oracle arithmetic used)
+from density import density                   # /root/reference/src/density.py
+from fourier_utils import fourier_grid        # /root/reference/src/fourier_utils.py
+from integrate import advance_time            # /root/reference/src/integrate.py
+from potential import potential               # /root/reference/src/potential.py
+from configure_me import N_CELLS, N_PARTS, A_INIT, A_END, STEPS
+
+rs = np.random.RandomState(case['seed'])
+if case['kind'] == 'lattice':
+    pos, vel = lattice_ic(N_PARTS, N_CELLS, seed=case['seed'], jitter=2.0, vel_rms=case['vel_rms'])
+    mass = (N_CELLS / N_PARTS) ** 3           # pmesh.py:28
+else:  # clustered: half the particles in a 1-cell-sigma Gaussian blob, half uniform
+    n = case['np']
+    blob = rs.normal(N_CELLS / 2 + 0.3, 1.0, size=(3, n // 2))
+    uni = rs.uniform(0, N_CELLS, size=(3, n - n // 2))
+    pos = (np.concatenate([blob, uni], axis=1) % N_CELLS).astype(np.float32)
+    pos = np.ascontiguousarray(pos[:, rs.permutation(n)])
+    vel = (case['vel_rms'] * rs.standard_normal(pos.shape)).astype(np.float32)
+    mass = 8.0
+# Edge cases the path must reproduce (SURVEY Q4 and the periodic-wrap list of section 4).
+Nc = np.float32(N_CELLS)
+special = np.array([
+    [Nc,                     5.25,                   7.5],      # pos == N_CELLS: cell 0, d = Nc (Q4)
+    [0.0,                    0.0,                    0.0],      # exact origin
+    [np.nextafter(Nc, np.float32(0)), Nc - 0.5,      0.25],     # last cell, wraps to plane 0
+    [1e-8,                   N_CELLS / 2,            Nc - 1],   # tiny offset; z in last plane
+    [3.0,                    Nc,                     Nc],       # two axes at == N_CELLS
+    [N_CELLS / 2 + 0.5,      N_CELLS / 2 + 0.5,      N_CELLS / 2 + 0.5],  # cell centre weights 1/8
+], dtype=np.float32).T
+k = special.shape[1]
+pos[:, :k] = special
+pos = np.ascontiguousarray(pos); vel = np.ascontiguousarray(vel)
+
+out = dict(pos0=pos.copy(), vel0=vel.copy(), mass=np.float64(mass), n_cells=np.int64(N_CELLS),
+           n_parts=np.int64(N_PARTS), steps_cfg=np.int64(STEPS))
+fgrid = fourier_grid()
+fgrid[0, 0, 0] = 0.0                          # SURVEY Q5
+out['fgrid_shape'] = np.array(fgrid.shape); out['fgrid_dtype'] = np.array(str(fgrid.dtype))
+if N_CELLS <= 32:
+    out['fgrid'] = fgrid
+da = (A_END - A_INIT) / STEPS                 # pmesh.py:30
+a_current = case.get('a_start', A_INIT)
+a_list = []
+for s in range(case['nsteps']):               # pmesh.py:56-63
+    a_list.append(a_current)
+    rho = density(pos, mass)
+    if s in case['keep_mesh']:
+        out['rho_%d' % s] = rho.copy()
+        out['phi_%d' % s] = potential(rho, fgrid, a_current)
+    pos, vel = advance_time(rho, pos, vel, fgrid, a_current, da)
+    a_current += da
+    out['pos_%d' % (s + 1)] = pos.copy()
+    out['vel_%d' % (s + 1)] = vel.copy()
+out['a_list'] = np.array(a_list, dtype=np.float64); out['da'] = np.float64(da)
+# loop trip count of pmesh.py:56 for this STEPS (SURVEY Q10)
+a, n = A_INIT, 0
+while a < A_END - da:
+    a += da; n += 1
+out['trip_count'] = np.int64(n)
+np.savez_compressed(case['out'], **out)
+print('wrote', case['out'], 'rho.min', float(rho.min()), 'trip', n)
+"""
+
+CASES = [
+    dict(name="g16_free10", N_PARTS=16, N_CELLS=32, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
+         vel_rms=0.05, nsteps=10, keep_mesh=[0, 9]),
+    dict(name="g32_step2", N_PARTS=32, N_CELLS=64, STEPS=1000, A_INIT=0.01, kind="lattice", seed=7,
+         vel_rms=0.5, nsteps=2, keep_mesh=[0], a_start=0.5),
+    dict(name="g12_nonpow2", N_PARTS=12, N_CELLS=20, STEPS=10, A_INIT=0.01, kind="lattice", seed=3,
+         vel_rms=0.02, nsteps=3, keep_mesh=[0, 2]),
+    dict(name="clustered32", N_PARTS=16, N_CELLS=32, STEPS=500, A_INIT=0.01, kind="clustered", seed=11,
+         np=20000, vel_rms=0.3, nsteps=2, keep_mesh=[0, 1], a_start=0.9),
+]
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    for case in CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            with open(os.path.join(tmp, "configure_me.py"), "w") as fh:
+                fh.write(CONFIGURE_ME.format(**case))
+            with open(os.path.join(tmp, "pyfftw.py"), "w") as fh:
+                fh.write(PYFFTW_SHIM)
+            with open(os.path.join(tmp, "worker.py"), "w") as fh:
+                fh.write(textwrap.dedent(WORKER.format(repo=REPO)))
+            arg = dict(case, out=os.path.join(GOLDEN, case["name"] + ".npz"))
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([tmp, REF_SRC]), NUMBA_NUM_THREADS="1",
+                       NUMBA_CACHE_DIR=os.path.join(tmp, "nbcache"))
+            subprocess.run([sys.executable, os.path.join(tmp, "worker.py"), json.dumps(arg)],
+                           check=True, env=env, cwd=tmp)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,112 @@
+"""The oracle (oracle/pm_oracle.c + oracle/oracle.py) against fixtures produced by the
+reference's own source files (oracle/make_golden.py).  Bar: BIT-EXACT on every array -- the
+oracle restates the same arithmetic in the same order and precision."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+CASES = ["g16_free10", "g32_step2", "g12_nonpow2", "clustered32"]
+
+
+def _load(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = O.Config(N_CELLS=int(g["n_cells"]), N_PARTS=int(g["n_parts"]), STEPS=int(g["steps_cfg"]))
+    return g, cfg
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_reference_bit_exact(golden_dir, name):
+    g, cfg = _load(golden_dir, name)
+    pos, vel, mass, da = g["pos0"].copy(), g["vel0"].copy(), float(g["mass"]), float(g["da"])
+    fg = O.fourier_grid(cfg)
+    assert fg.dtype == np.float32 and tuple(g["fgrid_shape"]) == fg.shape
+    if "fgrid" in g:
+        assert np.array_equal(fg, g["fgrid"])
+    for s, a in enumerate(g["a_list"]):
+        rho = O.density(pos, mass, cfg)
+        if f"rho_{s}" in g:
+            assert np.array_equal(rho, g[f"rho_{s}"]), f"density step {s}"
+            assert np.array_equal(O.potential(rho, fg, a, cfg), g[f"phi_{s}"]), f"potential step {s}"
+        p2, v2 = O.advance_time(rho, pos, vel, fg, a, da, cfg)
+        assert p2 is pos and v2 is vel  # in place + returned, like integrate.py:25
+        assert np.array_equal(pos, g[f"pos_{s + 1}"]), f"positions step {s}"
+        assert np.array_equal(vel, g[f"vel_{s + 1}"]), f"velocities step {s}"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_loop_trip_count(golden_dir, name):
+    g, cfg = _load(golden_dir, name)
+    assert O.loop_trip_count(cfg) == int(g["trip_count"])
+
+
+def test_trip_counts_of_survey_q10():
+    # pmesh.py:30,56,63 -- 10/99/999/500/1999 iterations for STEPS = 10/100/1000/500/2000
+    for steps, want in [(10, 10), (100, 99), (1000, 999), (500, 500), (2000, 1999)]:
+        assert O.loop_trip_count(O.Config(STEPS=steps)) == want
+
+
+def test_q4_fixture_has_negative_mass_event(golden_dir):
+    g, _ = _load(golden_dir, "g16_free10")
+    assert g["rho_0"].min() < -1000.0  # the pos == N_CELLS particle deposits -(Nc-1)*m*...
+
+
+def test_mass_conservation_and_cell_centre_weights():
+    cfg = O.Config(N_CELLS=16, N_PARTS=8)
+    pos = np.array([[4.5], [7.5], [9.5]], dtype=np.float32)
+    rho = O.density(pos, 8.0, cfg)
+    assert rho.sum() == 8.0
+    assert np.all(rho[9:11, 7:9, 4:6] == 1.0)          # [z, y, x]; eight corners get m/8
+    pos = np.array([[4.25], [7.0], [15.5]], dtype=np.float32)
+    rho = O.density(pos, 1.0, cfg)
+    assert rho[15, 7, 4] == 0.375 and rho[15, 7, 5] == 0.125
+    assert rho[0, 7, 4] == 0.375 and rho[0, 7, 5] == 0.125   # wraps into plane 0 (density.py:33-35)
+
+
+def test_uniform_lattice_gives_zero_kick():
+    cfg = O.Config(N_CELLS=16, N_PARTS=16)
+    pos, vel = O.lattice_ic(16, 16, jitter=0.0)
+    rho = O.density(pos, 1.0, cfg)
+    assert np.all(rho == 1.0)
+    O.advance_time(rho, pos, vel, O.fourier_grid(cfg), 0.5, 0.01, cfg)
+    assert np.all(vel == 0.0)
+
+
+def test_single_mode_potential():
+    # phi = -3*Om/(8a) / sin^2(pi m / Nc) * rho for rho = cos(2 pi m x / Nc)  (fourier_utils.py:15, potential.py:15)
+    cfg = O.Config(N_CELLS=32)
+    m, a = 3, 0.25
+    x = np.arange(32)
+    rho = np.broadcast_to(np.cos(2 * np.pi * m * x / 32).astype(np.float32), (32, 32, 32)).copy()
+    phi = O.potential(rho, O.fourier_grid(cfg), a, cfg)
+    want = -3 * cfg.OMEGA_M0 / 8 / a / np.sin(np.pi * m / 32) ** 2 * rho
+    assert np.abs(phi - want).max() < 2e-5 * np.abs(want).max()
+
+
+def test_sort_order_is_stable_and_keys_match_definition():
+    cfg = O.Config(N_CELLS=8, N_PARTS=4)
+    pos, _ = O.lattice_ic(4, 8, seed=1)
+    pos[:, 0] = 8.0   # Q4: key 0
+    keys = O.cell_keys(pos, cfg)
+    c = np.floor(pos).astype(np.int64) % 8
+    assert np.array_equal(keys, (c[2] * 8 + c[1]) * 8 + c[0]) and keys[0] == 0
+    order = O.sort_order(pos, cfg)
+    ks = keys[order]
+    assert np.all(np.diff(ks) >= 0)
+    same = np.diff(ks) == 0
+    assert np.all(np.diff(order)[same] > 0)
+
+
+def test_threaded_oracle_matches_serial_to_rounding():
+    cfg1 = O.Config(N_CELLS=32, N_PARTS=16, N_CPU=1)
+    cfg4 = O.Config(N_CELLS=32, N_PARTS=16, N_CPU=4)
+    pos, vel = O.lattice_ic(16, 32, seed=5, vel_rms=0.1)
+    r1, r4 = O.density(pos, 8.0, cfg1), O.density(pos, 8.0, cfg4)
+    assert np.linalg.norm(r1 - r4) <= 1e-6 * np.linalg.norm(r1)
+    fg = O.fourier_grid(cfg1)
+    p1, v1, p4, v4 = pos.copy(), vel.copy(), pos.copy(), vel.copy()
+    O.advance_time(r1, p1, v1, fg, 0.3, 0.001, cfg1)
+    O.advance_time(r1, p4, v4, fg, 0.3, 0.001, cfg4)
+    assert np.array_equal(p1, p4) and np.array_equal(v1, v4)
