@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the full particle-mesh step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one body of the reference loop src/pmesh.py:60-61 (CIC deposit + FFT Poisson solve
++ force gather/kick/drift) over all particles.  Workload at N=1: BASELINE.json configs[1],
+256^3 particles on a 512^3 mesh (the README benchmark config), IC-like synthetic particles
+(lattice + seeded uniform(-2,2) jitter).
+
+Our arm prints ONE JSON line with
+  value      particle-steps/s, state resident in HBM, K steps timed with CUDA events on the
+             launching stream (max over ranks);
+  e2e        the same metric through the host-buffer C-ABI call pm_step_host(): every step
+             uploads positions+velocities from pinned host memory and downloads the results;
+  roofline   the dominant hand-written kernel, timed live with CUDA events inside the timed
+             region (pm_plan_profile_*), against MEASURED_PEAKS.json hbm_gbs;
+  roofline_step  the whole step against B_step = 60*Np + 64*Nc^3 bytes;
+  stages     per-stage mean milliseconds of the same timed steps;
+  cpu_baseline   the CPU oracle port (oracle/) on this box's host cores, bounded sample.
+
+--impl reference times the reference's CPU implementation of the same step: the reference is
+pure Python + numba + pyFFTW and cannot travel to the GPU box (no /root/reference there, pyFFTW
+not installable), so the arm runs the oracle *port* (oracle/pm_oracle.c + scipy.fft, which
+tests/test_oracle_golden.py pins bit-for-bit to the reference's own code) with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "particle-steps/sec"
+UNIT = "particle-steps/s"
+
+
+def measured_hbm_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_particles_torch(n_parts, n_cells, device, seed=38):
+    """Lattice (zeldovich.py:79-83: row-0 coordinate slowest, +0.5) + uniform(-2,2) jitter
+    (zeldovich.py:89-91) wrapped to [0, Nc); zero initial velocities.  Generated on the host with
+    torch's CPU generator (deterministic), float32."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    res = n_cells / n_parts
+    ax = torch.arange(n_parts, dtype=torch.float64) * res + 0.5
+    npart = n_parts ** 3
+    pos = torch.empty((3, npart), dtype=torch.float32)
+    idx = torch.arange(npart, dtype=torch.int64)
+    comps = (idx // (n_parts * n_parts), (idx // n_parts) % n_parts, idx % n_parts)
+    for d in range(3):
+        jit = (torch.rand(npart, generator=g, dtype=torch.float64) * 4.0 - 2.0)
+        pos[d] = torch.remainder(ax[comps[d]] + jit, float(n_cells)).to(torch.float32)
+    pos.clamp_(max=float(n_cells))
+    vel = torch.zeros((3, npart), dtype=torch.float32)
+    return pos, vel
+
+
+def cfg_namespace(n_parts, n_cells, steps_cfg=1000):
+    return types.SimpleNamespace(N_PARTS=n_parts, N_CELLS=n_cells, N_CPU=1, STEPS=steps_cfg,
+                                 OMEGA_M0=0.31, OMEGA_K0=0.0, OMEGA_LAMBDA0=0.69, H0=0.68,
+                                 A_INIT=0.01, A_END=1.0)
+
+
+def b_step_bytes(npart, n_cells):
+    return 60 * npart + 64 * n_cells ** 3
+
+
+# algorithmic bytes per launch of each hand-written stage (DESIGN.md "Kernels")
+def stage_alg_bytes(npart, n_cells):
+    m = n_cells ** 3
+    return {
+        "keys": 12 * npart + 8 * npart,              # read x,y,z; write key + index
+        "rows": 4 * npart + 4 * n_cells ** 2,        # read sorted keys; write row offsets
+        "deposit": 12 * npart + 4 * m,               # SURVEY 8d deposit row
+        "green": 8 * m,                              # read + write half spectrum
+        "gather_kick_drift": 48 * npart + 4 * m,     # SURVEY 8d gather row
+        "sort": 4 * 16 * npart + 4 * npart,          # 4 radix passes over (key,index) r+w + histogram read
+        "fft_r2c": 24 * m, "fft_c2r": 24 * m,
+    }
+
+
+OWN_STAGES = ("keys", "rows", "deposit", "green", "gather_kick_drift")
+
+
+def cpu_baseline_sample(n_parts, n_cells, pos_h, vel_h, threads, nsteps=1):
+    """The oracle port on this box's host cores; returns (particle-steps/s, seconds)."""
+    from oracle import oracle as O
+    cfg = O.Config(N_CELLS=n_cells, N_PARTS=n_parts, N_CPU=threads)
+    fg = O.fourier_grid(cfg)
+    a, da = 0.01, 0.99 / 1000
+    mass = (n_cells / n_parts) ** 3
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        O.step(pos_h, vel_h, fg, a, da, cfg, mass=mass)
+        a += da
+    dt = time.perf_counter() - t0
+    return pos_h.shape[1] * nsteps / dt, dt
+
+
+# ------------------------------------------------------------------------------------------------
+# arms
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: oracle port, all host threads, same config/metric.  Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = O.max_threads()
+    n_parts, n_cells = args.n_parts, args.n_cells
+    pos, vel = make_particles_torch(n_parts, n_cells, "cpu")
+    pos_h, vel_h = pos.numpy(), vel.numpy()
+    npart = pos_h.shape[1]
+    # bounded: each step is the full workload; the number of steps is capped by a time budget
+    _, t_first = cpu_baseline_sample(n_parts, n_cells, pos_h, vel_h, threads, 1)   # warm-up step
+    budget = args.reference_budget_s
+    k = max(1, min(args.steps, int(budget / max(t_first, 1e-3))))
+    rate, dt = cpu_baseline_sample(n_parts, n_cells, pos_h, vel_h, threads, k)
+    sample = f"{k} full steps of {n_parts}^3 on {n_cells}^3 after 1 warm-up step (requested {args.steps}; capped by a {budget:.0f} s budget)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": k, "warmup": 1, "requested_steps": args.steps, "ms_per_step": 1e3 * dt / k,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": rate / 4.7e6,
+        "dtype": "f64 (complex128 FFT, float32 state)", "data": "synthetic",
+        "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step",
+                   "n_parts": n_parts, "n_cells": n_cells},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of the reference's numba+pyFFTW step (C + scipy.fft complex128); the "
+                "reference itself cannot run on this box (no /root/reference, no pyFFTW)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import cosmological_particle_mesh_simulation_b200 as pm
+    rt = pm._runtime
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product arm)")
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
+
+    n_parts, n_cells = args.n_parts, args.n_cells
+    cfg = cfg_namespace(n_parts, n_cells)
+    pm.set_config(cfg)
+    npart = n_parts ** 3
+    mass = (n_cells / n_parts) ** 3
+    pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
+    pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
+    plan = rt.get_plan(n_cells, npart, dev)
+    sched = pm.loop_scale_factors(cfg)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    step_i = 0
+    for _ in range(W):
+        a, da = sched[step_i % len(sched)]
+        pm.step(pos, vel, a, da, mass=mass)
+        step_i += 1
+    barrier()
+
+    # ---- timed region: K resident steps, CUDA events on the launching stream ----
+    sampler = ClockSampler(dev)
+    sampler.start()
+    time.sleep(0.3)
+    rt.check(rt.lib().pm_plan_profile_begin(plan.handle, K), "profile_begin")
+    launches0 = pm.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        a, da = sched[step_i % len(sched)]
+        pm.step(pos, vel, a, da, mass=mass)
+        step_i += 1
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = pm.launch_count() - launches0
+    import ctypes
+    import numpy as np
+    nst = len(rt.STAGE_NAMES)
+    buf = np.zeros((K, nst), dtype=np.float32)
+    nrec = ctypes.c_int(0)
+    rt.check(rt.lib().pm_plan_profile_read(plan.handle, buf.ctypes.data, ctypes.byref(nrec)), "profile_read")
+    rt.check(rt.lib().pm_plan_profile_begin(plan.handle, 0), "profile_end")
+    clocks = sampler.stop()
+    stage_ms = {n: float(buf[:nrec.value, i].mean()) for i, n in enumerate(rt.STAGE_NAMES)}
+
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = npart * world * K / (ms_total * 1e-3)   # replicas until the slab path lands
+
+    # ---- e2e: host-buffer C-ABI call, pinned host memory, copies inside the timed region ----
+    ph, vh = pos.cpu().pin_memory(), vel.cpu().pin_memory()
+    ke = max(3, min(K, 10))
+    for _ in range(2):
+        a, da = sched[step_i % len(sched)]
+        pm.step_host(ph, vh, a, da, mass=mass, device=dev)
+        step_i += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        a, da = sched[step_i % len(sched)]
+        pm.step_host(ph, vh, a, da, mass=mass, device=dev)
+        step_i += 1
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = npart * world * ke / e2e_s
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_hbm_peak()
+    alg = stage_alg_bytes(npart, n_cells)
+    dominant = max(OWN_STAGES, key=lambda n: stage_ms[n])
+    ach = alg[dominant] / (stage_ms[dominant] * 1e-3) / 1e9
+    bstep = b_step_bytes(npart, n_cells)
+    ach_step = bstep / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "traffic.json")   # dram bytes per launch from ncu --set full
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dominant)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if world == 1 else "weak", "vs_baseline": value / 4.7e6,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step "
+                               "(CIC deposit + FFT Poisson + gather/kick/drift), BASELINE configs[1]",
+                   "n_parts": n_parts, "n_cells": n_cells, "particles": "lattice + uniform(-2,2) jitter, seed 38",
+                   "l2": "inputs larger than L2 (201 MB particles rows, 537 MB meshes vs 126 MB L2)",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab path pending)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * npart,
+                "d2h_bytes_per_step": 24 * npart, "steps": ke,
+                "api": "pm_step_host (pinned host pos+vel in, pos+vel out; density stays on device, "
+                       "as with the reference defaults SAVE_DENSITY=False, PLOT_*=False)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg[dominant], "ms_per_launch": stage_ms[dominant]},
+        "roofline_step": {"bound": "hbm", "achieved": ach_step, "peak": peak, "unit": "GB/s",
+                          "frac": ach_step / peak, "algorithmic_bytes_per_step": bstep,
+                          "formula": "60*Np + 64*Nc^3 (SURVEY 8d)"},
+        "stages_ms": stage_ms,
+        "stage_frac_of_peak": {n: alg[n] / (stage_ms[n] * 1e-3) / 1e9 / peak for n in stage_ms if stage_ms[n] > 0},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        threads = O.max_threads()
+        pc, vc = pos_h.numpy().copy(), vel_h.numpy().copy()
+        rate, dt = cpu_baseline_sample(n_parts, n_cells, pc, vc, threads, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"1 full step of {n_parts}^3 on {n_cells}^3 ({dt:.1f} s), oracle port "
+                                          "(C particle loops + scipy.fft complex128)"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-parts", type=int, default=256)
+    ap.add_argument("--n-cells", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-budget-s", type=float, default=90.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

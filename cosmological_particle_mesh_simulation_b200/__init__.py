@@ -1,0 +1,25 @@
+"""B200-native particle-mesh timestep: a drop-in for the per-step loop of
+grkooij/Cosmological-Particle-Mesh-Simulation (reference: src/pmesh.py:56-63).
+
+The module names and call signatures mirror the reference's flat source tree:
+
+    density.density(positions, mass)                       src/density.py:8
+    fourier_utils.fourier_grid()                           src/fourier_utils.py:5
+    potential.potential(density, fgrid, a)                 src/potential.py:7
+    integrate.advance_time(density, positions, velocities, fgrid, a, da)   src/integrate.py:9
+    integrate.integrate(positions, velocities, a_val, f_a1, da, potentials) src/integrate.py:16
+    cosmology.f(a, cosmology)                              src/cosmology.py:20
+    configure_me.*                                         src/configure_me.py:7-40
+
+All arithmetic runs in libpmstep.so (hand-written sm_100a CUDA + cuFFT) through the C ABI of
+include/pmstep.h.  CUDA tensors in -> CUDA tensors out (state stays in HBM); NumPy arrays in ->
+NumPy arrays out (uploaded, computed on the GPU, downloaded).  There is no CPU fallback.
+"""
+from . import configure_me, cosmology  # noqa: F401
+from ._runtime import PMStepError, set_config, config, launch_count, release_plans  # noqa: F401
+from .density import density  # noqa: F401
+from .fourier_utils import fourier_grid, FourierGrid  # noqa: F401
+from .potential import potential  # noqa: F401
+from .integrate import advance_time, integrate  # noqa: F401
+from .cosmology import f  # noqa: F401
+from .pmesh import step, step_host, simulator, loop_scale_factors  # noqa: F401

@@ -1,0 +1,216 @@
+"""Runtime glue between the Python drop-in modules and libpmstep.so (include/pmstep.h).
+
+PyTorch is used for device memory, streams and (multi-GPU) torch.distributed only; every
+computation of the particle-mesh step happens inside the C-ABI library.  There is NO CPU
+fallback: if the library is missing or no CUDA device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import importlib
+import os
+import sys
+import threading
+
+import numpy as np
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libpmstep.so")
+
+_lib = None
+_lock = threading.Lock()
+
+
+class PMStepError(RuntimeError):
+    """A libpmstep.so entry point returned non-zero."""
+
+    def __init__(self, code, where=""):
+        self.code = int(code)
+        msg = lib().pm_error_string(self.code).decode() if _lib is not None else "?"
+        super().__init__(f"{where}: libpmstep error {self.code}: {msg}")
+
+
+def lib():
+    """Load libpmstep.so (once).  Raises if it has not been built -- run
+    ``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C <pkg>/csrc``."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: the CUDA extension is not built and there is no CPU "
+                f"fallback.  Build it with `make -C {os.path.join(_PKG_DIR, 'csrc')}`.")
+        L = ctypes.CDLL(LIB_PATH)
+        i32, i64, f64, vp, sz = (ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p,
+                                 ctypes.c_size_t)
+        sig = {
+            "pm_version": (ctypes.c_char_p, []),
+            "pm_error_string": (ctypes.c_char_p, [i32]),
+            "pm_last_cufft_status": (i32, []),
+            "pm_launch_count": (ctypes.c_uint64, []),
+            "pm_plan_workspace_bytes": (sz, [i32, i64]),
+            "pm_plan_create": (i32, [ctypes.POINTER(vp), i32, i64, i32]),
+            "pm_plan_destroy": (i32, [vp]),
+            "pm_plan_n_cells": (i32, [vp]),
+            "pm_plan_np_capacity": (i64, [vp]),
+            "pm_fourier_grid": (i32, [vp, vp, vp]),
+            "pm_cell_keys": (i32, [vp, vp, i64, vp, vp]),
+            "pm_sort_by_cell": (i32, [vp, vp, i64, vp, vp, vp]),
+            "pm_deposit_cic": (i32, [vp, vp, i64, f64, vp, vp]),
+            "pm_poisson": (i32, [vp, vp, f64, f64, vp, vp]),
+            "pm_gather_kick_drift": (i32, [vp, vp, vp, i64, vp, f64, f64, f64, vp, vp]),
+            "pm_step": (i32, [vp, vp, vp, i64, f64, f64, f64, f64, f64, vp, vp]),
+            "pm_step_host": (i32, [vp, vp, vp, i64, f64, f64, f64, f64, f64, vp]),
+            "pm_plan_profile_begin": (i32, [vp, i32]),
+            "pm_plan_profile_read": (i32, [vp, vp, ctypes.POINTER(i32)]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)  # AttributeError here = header/library mismatch, fail loudly
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = (
+    "pm_version", "pm_error_string", "pm_last_cufft_status", "pm_launch_count",
+    "pm_plan_workspace_bytes", "pm_plan_create", "pm_plan_destroy", "pm_plan_n_cells",
+    "pm_plan_np_capacity", "pm_fourier_grid", "pm_cell_keys", "pm_sort_by_cell", "pm_deposit_cic",
+    "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_plan_profile_begin",
+    "pm_plan_profile_read",
+)
+
+STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")
+
+
+def check(rc, where):
+    if rc != 0:
+        raise PMStepError(rc, where)
+
+
+def launch_count() -> int:
+    return int(lib().pm_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# configuration: which configure_me is read
+# ---------------------------------------------------------------------------------------------
+_config_override = None
+
+
+def set_config(cfg):
+    """Use `cfg` (module or any object with the configure_me attribute names) instead of the
+    configure_me module.  Pass None to go back to module lookup."""
+    global _config_override
+    _config_override = cfg
+
+
+def config():
+    """The configure_me the drop-in modules read, at call time: an explicit set_config() object,
+    else a top-level module named ``configure_me`` (the reference's own file when these modules
+    are dropped into its source tree), else this package's configure_me.py."""
+    if _config_override is not None:
+        return _config_override
+    mod = sys.modules.get("configure_me")
+    if mod is None:
+        try:
+            mod = importlib.import_module("configure_me")
+        except ImportError:
+            mod = importlib.import_module(__package__ + ".configure_me" if __package__ else "configure_me")
+    return mod
+
+
+# ---------------------------------------------------------------------------------------------
+# plans
+# ---------------------------------------------------------------------------------------------
+class Plan:
+    """Owns one pm_plan* (cuFFT plans, Green's table, all per-step scratch) on one device."""
+
+    def __init__(self, n_cells: int, np_capacity: int, device: int):
+        self.n_cells, self.np_capacity, self.device = int(n_cells), int(np_capacity), int(device)
+        h = ctypes.c_void_p()
+        check(lib().pm_plan_create(ctypes.byref(h), self.n_cells, self.np_capacity, self.device),
+              f"pm_plan_create(n_cells={n_cells}, np={np_capacity}, device={device})")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().pm_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_plans: dict = {}
+
+
+def get_plan(n_cells: int, np_needed: int, device: int) -> Plan:
+    """Cached plan for (n_cells, device) whose particle capacity covers np_needed."""
+    key = (int(n_cells), int(device))
+    plan = _plans.get(key)
+    if plan is None or plan.np_capacity < np_needed or plan.handle is None:
+        if plan is not None:
+            torch.cuda.synchronize(device)
+            plan.close()
+        plan = Plan(n_cells, max(int(np_needed), 1), device)
+        _plans[key] = plan
+    return plan
+
+
+def release_plans():
+    for plan in _plans.values():
+        plan.close()
+    _plans.clear()
+
+
+# ---------------------------------------------------------------------------------------------
+# tensors
+# ---------------------------------------------------------------------------------------------
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: the B200 particle-mesh step has no CPU fallback")
+
+
+def current_device() -> int:
+    require_cuda()
+    return torch.cuda.current_device()
+
+
+def stream_ptr(device: int) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def is_host(x) -> bool:
+    return isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
+
+
+def as_host_f32(x, shape=None):
+    """A C-contiguous float32 NumPy view/copy of a NumPy array or CPU tensor."""
+    a = x.numpy() if isinstance(x, torch.Tensor) else x
+    if a.dtype != np.float32 or not a.flags.c_contiguous:
+        raise TypeError("expected a C-contiguous float32 array (reference dtypes, SURVEY Q13)")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {tuple(a.shape)}")
+    return a
+
+
+def check_dev_f32(t: torch.Tensor, shape=None, name="tensor"):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TypeError(f"{name}: expected a CUDA tensor")
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise TypeError(f"{name}: expected contiguous float32")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+def to_device(x, device: int) -> torch.Tensor:
+    a = as_host_f32(x)
+    return torch.from_numpy(a).to(f"cuda:{device}", non_blocking=False)

@@ -1,0 +1,398 @@
+// pm_api.cu -- the extern "C" surface declared in include/pmstep.h.
+#include <new>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pm_internal.cuh"
+
+unsigned long long g_pm_launches = 0;
+int g_pm_last_cufft = 0;
+
+namespace {
+
+const size_t kAlign = 512;
+inline size_t align_up(size_t v) { return (v + kAlign - 1) / kAlign * kAlign; }
+
+int key_bits_for(int nc)
+{
+    const uint64_t m = (uint64_t)nc * nc * nc;
+    int b = 1;
+    while (((uint64_t)1 << b) < m) ++b;
+    return b;
+}
+
+// Sizes of every workspace segment, in the order they are carved.
+struct Layout {
+    size_t keys, order, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2,
+        pos_stage, vel_stage, total;
+};
+
+bool config_ok(int nc, int64_t np)
+{
+    if (nc < 4 || nc > 1625) return false;  // nc^3 < 2^32: 32-bit cell keys and mesh offsets
+    if (np < 0 || np > (int64_t)0xfffffff0u) return false;
+    return true;
+}
+
+int make_fft_plans(int nc, cufftHandle *r2c, cufftHandle *c2r, size_t *work)
+{
+    size_t w1 = 0, w2 = 0;
+    PM_CUFFT(cufftCreate(r2c));
+    PM_CUFFT(cufftCreate(c2r));
+    PM_CUFFT(cufftSetAutoAllocation(*r2c, 0));
+    PM_CUFFT(cufftSetAutoAllocation(*c2r, 0));
+    PM_CUFFT(cufftMakePlan3d(*r2c, nc, nc, nc, CUFFT_R2C, &w1));
+    PM_CUFFT(cufftMakePlan3d(*c2r, nc, nc, nc, CUFFT_C2R, &w2));
+    *work = w1 > w2 ? w1 : w2;
+    return PM_OK;
+}
+
+int compute_layout(int nc, int64_t np, size_t fft_work, Layout *L)
+{
+    const size_t m = (size_t)nc * nc * nc;
+    const size_t npad = (size_t)((np + 3) / 4 * 4);
+    L->keys = align_up(npad * 4);
+    L->order = align_up(npad * 4);
+    L->keys_sorted = align_up(npad * 4);
+    L->order_sorted = align_up(npad * 4);
+    L->cub = align_up(pm_sort_temp_bytes(np > 0 ? np : 1, key_bits_for(nc)));
+    L->row_start = align_up(((size_t)nc * nc + 1) * 4);
+    L->mesh = align_up(m * 4);
+    L->mesh2 = align_up(m * 4);
+    L->spec = align_up((size_t)nc * nc * (nc / 2 + 1) * sizeof(float2));
+    L->fft = align_up(fft_work);
+    L->sin2 = align_up((size_t)nc * 4);
+    L->pos_stage = align_up(3 * npad * 4);
+    L->vel_stage = align_up(3 * npad * 4);
+    L->total = L->keys + L->order + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
+               L->mesh + L->mesh2 + L->spec + L->fft + L->sin2 + L->pos_stage + L->vel_stage;
+    return PM_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    int enter(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return PM_ERR_NO_DEVICE;
+        if (dev >= 0 && dev != prev) {
+            cudaError_t e = cudaSetDevice(dev);
+            if (e != cudaSuccess) return (int)e;
+            active = true;
+        }
+        return PM_OK;
+    }
+    ~DeviceGuard()
+    {
+        if (active) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char *pm_version(void) { return "pmstep 0.1 (sm_100a; cuFFT R2C/C2R + hand-written particle/Green kernels)"; }
+
+const char *pm_error_string(int code)
+{
+    switch (code) {
+        case PM_OK: return "ok";
+        case PM_ERR_INVALID: return "invalid argument";
+        case PM_ERR_UNSUPPORTED: return "unsupported configuration";
+        case PM_ERR_NOMEM: return "workspace allocation failed";
+        case PM_ERR_CUFFT: return "cuFFT error (see pm_last_cufft_status)";
+        case PM_ERR_NO_DEVICE: return "no usable CUDA device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int pm_last_cufft_status(void) { return g_pm_last_cufft; }
+uint64_t pm_launch_count(void) { return g_pm_launches; }
+
+size_t pm_plan_workspace_bytes(int n_cells, int64_t np_capacity)
+{
+    if (!config_ok(n_cells, np_capacity)) return 0;
+    cufftHandle a, b;
+    size_t work = 0;
+    if (make_fft_plans(n_cells, &a, &b, &work) != PM_OK) return 0;
+    cufftDestroy(a);
+    cufftDestroy(b);
+    Layout L;
+    compute_layout(n_cells, np_capacity, work, &L);
+    return L.total;
+}
+
+int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
+{
+    if (!out) return PM_ERR_INVALID;
+    *out = nullptr;
+    if (!config_ok(n_cells, np_capacity)) return PM_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return PM_ERR_NO_DEVICE;
+    }
+    DeviceGuard guard;
+    int rc = guard.enter(device);
+    if (rc != PM_OK) return rc;
+
+    pm_plan *p = new (std::nothrow) pm_plan();
+    if (!p) return PM_ERR_NOMEM;
+    memset(p, 0, sizeof(*p));
+    p->nc = n_cells;
+    p->np_cap = np_capacity;
+    p->key_bits = key_bits_for(n_cells);
+    cudaGetDevice(&p->device);
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
+
+    size_t work = 0;
+    rc = make_fft_plans(n_cells, &p->r2c, &p->c2r, &work);
+    if (rc != PM_OK) {
+        pm_plan_destroy(p);
+        return rc;
+    }
+    p->have_fft = true;
+    Layout L;
+    compute_layout(n_cells, np_capacity, work, &L);
+    p->ws_bytes = L.total;
+    if (cudaMalloc((void **)&p->ws, L.total) != cudaSuccess) {
+        cudaGetLastError();
+        pm_plan_destroy(p);
+        return PM_ERR_NOMEM;
+    }
+    char *c = p->ws;
+    p->keys = (uint32_t *)c;          c += L.keys;
+    p->order = (uint32_t *)c;         c += L.order;
+    p->keys_sorted = (uint32_t *)c;   c += L.keys_sorted;
+    p->order_sorted = (uint32_t *)c;  c += L.order_sorted;
+    p->cub_tmp = c;                   c += L.cub;
+    p->cub_bytes = L.cub;
+    p->row_start = (uint32_t *)c;     c += L.row_start;
+    p->mesh = (float *)c;             c += L.mesh;
+    p->mesh2 = (float *)c;            c += L.mesh2;
+    p->spec = (float2 *)c;            c += L.spec;
+    p->fft_work = c;                  c += L.fft;
+    p->fft_work_bytes = L.fft;
+    p->sin2 = (float *)c;             c += L.sin2;
+    p->pos_stage = (float *)c;        c += L.pos_stage;
+    p->vel_stage = (float *)c;        c += L.vel_stage;
+
+    if (cufftSetWorkArea(p->r2c, p->fft_work) != CUFFT_SUCCESS ||
+        cufftSetWorkArea(p->c2r, p->fft_work) != CUFFT_SUCCESS) {
+        pm_plan_destroy(p);
+        return PM_ERR_CUFFT;
+    }
+    rc = pm_k_sin2_table(p);
+    if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);
+    if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking);
+    if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking);
+    if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_a, cudaEventDisableTiming);
+    if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_b, cudaEventDisableTiming);
+    if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_c, cudaEventDisableTiming);
+    if (rc != PM_OK) {
+        pm_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return PM_OK;
+}
+
+int pm_plan_destroy(pm_plan *p)
+{
+    if (!p) return PM_OK;
+    DeviceGuard guard;
+    guard.enter(p->device);
+    if (p->have_fft) {
+        cufftDestroy(p->r2c);
+        cufftDestroy(p->c2r);
+    }
+    if (p->ev_a) cudaEventDestroy(p->ev_a);
+    if (p->ev_b) cudaEventDestroy(p->ev_b);
+    if (p->ev_c) cudaEventDestroy(p->ev_c);
+    if (p->s_main) cudaStreamDestroy(p->s_main);
+    if (p->s_up) cudaStreamDestroy(p->s_up);
+    if (p->s_down) cudaStreamDestroy(p->s_down);
+    if (p->ws) cudaFree(p->ws);
+    if (p->prof_ev) {
+        for (int i = 0; i < p->prof_cap * (PM_NUM_STAGES + 1); ++i) cudaEventDestroy(p->prof_ev[i]);
+        free(p->prof_ev);
+    }
+    delete p;
+    return PM_OK;
+}
+
+int pm_plan_n_cells(const pm_plan *p) { return p ? p->nc : 0; }
+int64_t pm_plan_np_capacity(const pm_plan *p) { return p ? p->np_cap : 0; }
+
+#define PM_ARGS(cond)                     \
+    do {                                  \
+        if (!(cond)) return PM_ERR_INVALID; \
+    } while (0)
+#define PM_TRY(expr)                      \
+    do {                                  \
+        int rc_ = (expr);                 \
+        if (rc_ != PM_OK) return rc_;     \
+    } while (0)
+
+int pm_fourier_grid(pm_plan *p, float *fgrid_d, pm_stream_t stream)
+{
+    PM_ARGS(p && fgrid_d);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return pm_k_fourier_grid(p, fgrid_d, pm_cu(stream));
+}
+
+int pm_cell_keys(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_d, pm_stream_t stream)
+{
+    PM_ARGS(p && pos_d && keys_d && np >= 0 && np <= p->np_cap);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return pm_k_cell_keys(p, pos_d, np, keys_d, nullptr, pm_cu(stream));
+}
+
+int pm_sort_by_cell(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_sorted_d,
+                    uint32_t *order_d, pm_stream_t stream)
+{
+    PM_ARGS(p && pos_d && np >= 0 && np <= p->np_cap);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    cudaStream_t st = pm_cu(stream);
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, p->order, st));
+    PM_TRY(pm_k_sort(p, np, st));
+    if (keys_sorted_d)
+        PM_CUDA(cudaMemcpyAsync(keys_sorted_d, p->keys_sorted, (size_t)np * 4,
+                                cudaMemcpyDeviceToDevice, st));
+    if (order_d)
+        PM_CUDA(cudaMemcpyAsync(order_d, p->order_sorted, (size_t)np * 4, cudaMemcpyDeviceToDevice, st));
+    return PM_OK;
+}
+
+int pm_deposit_cic(pm_plan *p, const float *pos_d, int64_t np, double mass, float *rho_d,
+                   pm_stream_t stream)
+{
+    PM_ARGS(p && pos_d && rho_d && np >= 0 && np <= p->np_cap);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    cudaStream_t st = pm_cu(stream);
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, p->order, st));
+    PM_TRY(pm_k_sort(p, np, st));
+    PM_TRY(pm_k_row_offsets(p, np, st));
+    return pm_k_deposit(p, pos_d, np, mass, rho_d, st);
+}
+
+int pm_poisson(pm_plan *p, const float *rho_d, double a, double omega_m0, float *phi_d,
+               pm_stream_t stream)
+{
+    PM_ARGS(p && rho_d && phi_d && a != 0.0);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return pm_k_poisson(p, rho_d, a, omega_m0, phi_d, pm_cu(stream));
+}
+
+int pm_gather_kick_drift(pm_plan *p, float *pos_d, float *vel_d, int64_t np, const float *phi_d,
+                         double a_val, double f_a1, double da, float *acc_d, pm_stream_t stream)
+{
+    PM_ARGS(p && pos_d && vel_d && phi_d && np >= 0);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return pm_k_gather_kick_drift(p, pos_d, vel_d, np, phi_d, a_val, f_a1, da, acc_d, pm_cu(stream));
+}
+
+int pm_step(pm_plan *p, float *pos_d, float *vel_d, int64_t np, double mass, double a, double da,
+            double f_a1, double omega_m0, float *rho_d, pm_stream_t stream)
+{
+    PM_ARGS(p && pos_d && vel_d && np >= 0 && np <= p->np_cap && a != 0.0);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    cudaStream_t st = pm_cu(stream);
+    float *rho = rho_d ? rho_d : p->mesh;
+    pm_prof_mark(p, 0, st);
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, p->order, st));
+    pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
+    PM_TRY(pm_k_sort(p, np, st));
+    pm_prof_mark(p, PM_STAGE_SORT + 1, st);
+    PM_TRY(pm_k_row_offsets(p, np, st));
+    pm_prof_mark(p, PM_STAGE_ROWS + 1, st);
+    PM_TRY(pm_k_deposit(p, pos_d, np, mass, rho, st));
+    pm_prof_mark(p, PM_STAGE_DEPOSIT + 1, st);
+    PM_TRY(pm_k_poisson(p, rho, a, omega_m0, p->mesh2, st));  // marks R2C, GREEN, C2R itself
+    PM_TRY(pm_k_gather_kick_drift(p, pos_d, vel_d, np, p->mesh2, a, f_a1, da, nullptr, st));
+    pm_prof_mark(p, PM_STAGE_GATHER + 1, st);
+    if (p->prof_ev && p->prof_n < p->prof_cap) ++p->prof_n;
+    return PM_OK;
+}
+
+int pm_plan_profile_begin(pm_plan *p, int max_steps)
+{
+    PM_ARGS(p && max_steps >= 0 && max_steps <= 4096);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    if (p->prof_ev) {
+        for (int i = 0; i < p->prof_cap * (PM_NUM_STAGES + 1); ++i) cudaEventDestroy(p->prof_ev[i]);
+        free(p->prof_ev);
+        p->prof_ev = nullptr;
+    }
+    p->prof_cap = p->prof_n = 0;
+    if (max_steps == 0) return PM_OK;
+    const int n = max_steps * (PM_NUM_STAGES + 1);
+    p->prof_ev = (cudaEvent_t *)calloc(n, sizeof(cudaEvent_t));
+    if (!p->prof_ev) return PM_ERR_NOMEM;
+    for (int i = 0; i < n; ++i) PM_CUDA(cudaEventCreate(&p->prof_ev[i]));
+    p->prof_cap = max_steps;
+    return PM_OK;
+}
+
+int pm_plan_profile_read(pm_plan *p, float *ms, int *n_steps)
+{
+    PM_ARGS(p && ms && n_steps);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    *n_steps = p->prof_n;
+    for (int s = 0; s < p->prof_n; ++s) {
+        cudaEvent_t *e = p->prof_ev + (size_t)s * (PM_NUM_STAGES + 1);
+        PM_CUDA(cudaEventSynchronize(e[PM_NUM_STAGES]));
+        for (int k = 0; k < PM_NUM_STAGES; ++k)
+            PM_CUDA(cudaEventElapsedTime(&ms[s * PM_NUM_STAGES + k], e[k], e[k + 1]));
+    }
+    p->prof_n = 0;
+    return PM_OK;
+}
+
+int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass, double a,
+                 double da, double f_a1, double omega_m0, float *rho_h)
+{
+    PM_ARGS(p && pos_h && vel_h && np >= 0 && np <= p->np_cap && a != 0.0);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    const size_t pbytes = (size_t)np * 3 * sizeof(float);
+    const size_t mbytes = (size_t)p->nc * p->nc * p->nc * sizeof(float);
+    // positions feed the deposit at once; velocities are not needed until the gather, so their
+    // upload (s_up) and the density download (s_down) overlap the deposit and the Poisson solve.
+    PM_CUDA(cudaMemcpyAsync(p->pos_stage, pos_h, pbytes, cudaMemcpyHostToDevice, p->s_main));
+    PM_CUDA(cudaMemcpyAsync(p->vel_stage, vel_h, pbytes, cudaMemcpyHostToDevice, p->s_up));
+    PM_CUDA(cudaEventRecord(p->ev_a, p->s_up));
+    PM_TRY(pm_k_cell_keys(p, p->pos_stage, np, p->keys, p->order, p->s_main));
+    PM_TRY(pm_k_sort(p, np, p->s_main));
+    PM_TRY(pm_k_row_offsets(p, np, p->s_main));
+    PM_TRY(pm_k_deposit(p, p->pos_stage, np, mass, p->mesh, p->s_main));
+    if (rho_h) {
+        PM_CUDA(cudaEventRecord(p->ev_b, p->s_main));
+        PM_CUDA(cudaStreamWaitEvent(p->s_down, p->ev_b, 0));
+        PM_CUDA(cudaMemcpyAsync(rho_h, p->mesh, mbytes, cudaMemcpyDeviceToHost, p->s_down));
+    }
+    PM_TRY(pm_k_poisson(p, p->mesh, a, omega_m0, p->mesh2, p->s_main));
+    PM_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_a, 0));
+    PM_TRY(pm_k_gather_kick_drift(p, p->pos_stage, p->vel_stage, np, p->mesh2, a, f_a1, da, nullptr,
+                                  p->s_main));
+    PM_CUDA(cudaEventRecord(p->ev_c, p->s_main));
+    PM_CUDA(cudaMemcpyAsync(pos_h, p->pos_stage, pbytes, cudaMemcpyDeviceToHost, p->s_main));
+    PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
+    PM_CUDA(cudaMemcpyAsync(vel_h, p->vel_stage, pbytes, cudaMemcpyDeviceToHost, p->s_up));
+    PM_CUDA(cudaStreamSynchronize(p->s_main));
+    PM_CUDA(cudaStreamSynchronize(p->s_up));
+    PM_CUDA(cudaStreamSynchronize(p->s_down));
+    return PM_OK;
+}
+
+}  // extern "C"

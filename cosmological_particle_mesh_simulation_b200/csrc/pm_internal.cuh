@@ -1,0 +1,101 @@
+// pm_internal.cuh -- shared declarations of libpmstep.so (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+
+#include "pmstep.h"
+
+// Every kernel launch of this library goes through PM_LAUNCH so that pm_launch_count() is an
+// honest count (bench.py reports it as gpu_launches).
+extern unsigned long long g_pm_launches;
+#define PM_LAUNCH(kernel, grid, block, smem, stream, ...)              \
+    do {                                                               \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);    \
+        ++g_pm_launches;                                               \
+    } while (0)
+
+#define PM_CUDA(expr)                                   \
+    do {                                                \
+        cudaError_t e_ = (expr);                        \
+        if (e_ != cudaSuccess) return (int)e_;          \
+    } while (0)
+
+#define PM_CHECK_LAUNCH()                               \
+    do {                                                \
+        cudaError_t e_ = cudaPeekAtLastError();         \
+        if (e_ != cudaSuccess) return (int)e_;          \
+    } while (0)
+
+extern int g_pm_last_cufft;
+#define PM_CUFFT(expr)                                  \
+    do {                                                \
+        cufftResult r_ = (expr);                        \
+        if (r_ != CUFFT_SUCCESS) {                      \
+            g_pm_last_cufft = (int)r_;                  \
+            return PM_ERR_CUFFT;                        \
+        }                                               \
+    } while (0)
+
+struct pm_plan {
+    int nc;           // N_CELLS
+    int64_t np_cap;   // particle capacity
+    int device;
+    int sm_count;
+    int key_bits;     // ceil(log2(nc^3))
+
+    char *ws;         // one workspace allocation; everything below points into it
+    size_t ws_bytes;
+
+    // deposit scratch
+    uint32_t *keys, *order, *keys_sorted, *order_sorted;
+    void *cub_tmp;
+    size_t cub_bytes;
+    uint32_t *row_start;  // nc*nc + 1 offsets into the sorted particle list
+
+    // Poisson scratch
+    float *mesh;          // nc^3: rho when the caller does not keep it
+    float *mesh2;         // nc^3: phi
+    float2 *spec;         // nc*nc*(nc/2+1) half spectrum
+    void *fft_work;
+    size_t fft_work_bytes;
+    float *sin2;          // sin^2(pi i / nc), i < nc
+    cufftHandle r2c, c2r;
+    bool have_fft;
+
+    // device residence for the host-buffer entry point
+    float *pos_stage, *vel_stage;
+    cudaStream_t s_main, s_up, s_down;
+    cudaEvent_t ev_a, ev_b, ev_c;
+
+    // optional per-stage timing of pm_step (pm_plan_profile_begin/read)
+    cudaEvent_t *prof_ev;   // prof_cap * (PM_NUM_STAGES + 1) events
+    int prof_cap, prof_n;
+};
+
+// Record the boundary event `k` (0 = before the first stage) of the step being profiled.
+static inline void pm_prof_mark(pm_plan *p, int k, cudaStream_t st)
+{
+    if (p->prof_ev && p->prof_n < p->prof_cap)
+        cudaEventRecord(p->prof_ev[(size_t)p->prof_n * (PM_NUM_STAGES + 1) + k], st);
+}
+
+static inline cudaStream_t pm_cu(pm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// pm_particles.cu
+size_t pm_sort_temp_bytes(int64_t np, int key_bits);
+int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, uint32_t *keys, uint32_t *order,
+                   cudaStream_t st);
+int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st);
+int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st);
+int pm_k_deposit(pm_plan *p, const float *pos, int64_t np, double mass, float *rho,
+                 cudaStream_t st);
+int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const float *phi,
+                           double a_val, double f_a1, double da, float *acc, cudaStream_t st);
+
+// pm_poisson.cu
+int pm_k_sin2_table(pm_plan *p);
+int pm_k_fourier_grid(pm_plan *p, float *fgrid, cudaStream_t st);
+int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
+                 cudaStream_t st);

@@ -1,0 +1,359 @@
+// pm_particles.cu -- particle-side kernels of the PM step: cell keys, sort, row offsets,
+// deterministic CIC deposit, fused force gather + kick + drift.
+//
+// Compiled with --fmad=false: the reference's numba/LLVM code never contracts a*b+c, and the
+// gather/kick/drift arithmetic below is written to be bit-identical to it given the same phi
+// (reference: src/integrate.py:27-97).  The explicit __f*_rn / __d*_rn intrinsics make the
+// rounding points visible (and keep them if the flag is ever lost).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "pm_internal.cuh"
+
+// --------------------------------------------------------------------------------------------
+// int(floor(x)) mod Nc with Python's sign convention (src/density.py:19-21, integrate.py:20).
+// Positions live in [0, Nc] (integrate.py:95 wraps them; the float32 store can round up to
+// exactly Nc -- SURVEY Q4 -- which must map to cell 0 while the offset d = x - cell stays Nc).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pm_cell(float x, int nc)
+{
+    int c = (int)floorf(x);
+    if ((unsigned)c >= (unsigned)nc) {
+        if (c == nc) {
+            c = 0;
+        } else {
+            c %= nc;
+            if (c < 0) c += nc;
+        }
+    }
+    return c;
+}
+
+// --------------------------------------------------------------------------------------------
+// Cell keys: key = (z_c*Nc + y_c)*Nc + x_c            (src/density.py:19-21,37)
+// VEC: one thread takes 4 consecutive particles of each SoA row with 128-bit loads.
+// --------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_cell_keys(const float *__restrict__ px,
+                                                   const float *__restrict__ py,
+                                                   const float *__restrict__ pz, int64_t np, int nc,
+                                                   uint32_t *__restrict__ keys,
+                                                   uint32_t *__restrict__ order)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        int64_t i = t * 4;
+        if (i >= np) return;
+        float4 x = *reinterpret_cast<const float4 *>(px + i);
+        float4 y = *reinterpret_cast<const float4 *>(py + i);
+        float4 z = *reinterpret_cast<const float4 *>(pz + i);
+        uint4 k;
+        k.x = ((uint32_t)pm_cell(z.x, nc) * nc + pm_cell(y.x, nc)) * nc + pm_cell(x.x, nc);
+        k.y = ((uint32_t)pm_cell(z.y, nc) * nc + pm_cell(y.y, nc)) * nc + pm_cell(x.y, nc);
+        k.z = ((uint32_t)pm_cell(z.z, nc) * nc + pm_cell(y.z, nc)) * nc + pm_cell(x.z, nc);
+        k.w = ((uint32_t)pm_cell(z.w, nc) * nc + pm_cell(y.w, nc)) * nc + pm_cell(x.w, nc);
+        *reinterpret_cast<uint4 *>(keys + i) = k;
+        if (order) {
+            uint32_t b = (uint32_t)i;
+            *reinterpret_cast<uint4 *>(order + i) = make_uint4(b, b + 1, b + 2, b + 3);
+        }
+    } else {
+        if (t >= np) return;
+        keys[t] = ((uint32_t)pm_cell(pz[t], nc) * nc + pm_cell(py[t], nc)) * nc + pm_cell(px[t], nc);
+        if (order) order[t] = (uint32_t)t;
+    }
+}
+
+int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, uint32_t *keys, uint32_t *order,
+                   cudaStream_t st)
+{
+    if (np == 0) return PM_OK;
+    const float *px = pos, *py = pos + np, *pz = pos + 2 * np;
+    bool vec = (np % 4 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)keys % 16 == 0) &&
+               (!order || (uintptr_t)order % 16 == 0);
+    if (vec) {
+        int64_t nthr = np / 4;
+        PM_LAUNCH(k_cell_keys<true>, (unsigned)((nthr + 255) / 256), 256, 0, st, px, py, pz, np,
+                  p->nc, keys, order);
+    } else {
+        PM_LAUNCH(k_cell_keys<false>, (unsigned)((np + 255) / 256), 256, 0, st, px, py, pz, np,
+                  p->nc, keys, order);
+    }
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (key, original index) on the low key_bits bits.
+// --------------------------------------------------------------------------------------------
+size_t pm_sort_temp_bytes(int64_t np, int key_bits)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, np, 0, key_bits);
+    return bytes;
+}
+
+int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st)
+{
+    if (np == 0) return PM_OK;
+    size_t bytes = p->cub_bytes;
+    PM_CUDA(cub::DeviceRadixSort::SortPairs(p->cub_tmp, bytes, (const uint32_t *)p->keys,
+                                            p->keys_sorted, (const uint32_t *)p->order,
+                                            p->order_sorted, np, 0, p->key_bits, st));
+    return PM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// row_start[r] = first sorted particle whose mesh row (z_c*Nc + y_c) is >= r, r in [0, Nc^2].
+// One thread per boundary j in [0, np]; it fills every row that starts at j (empty rows too).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_offsets(const uint32_t *__restrict__ keys_sorted,
+                                                     int64_t np, int nc,
+                                                     uint32_t *__restrict__ row_start)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > np) return;
+    int64_t nrows = (int64_t)nc * nc;
+    int64_t prev = (j == 0) ? -1 : (int64_t)(keys_sorted[j - 1] / (uint32_t)nc);
+    int64_t cur = (j == np) ? nrows : (int64_t)(keys_sorted[j] / (uint32_t)nc);
+    for (int64_t r = prev + 1; r <= cur; ++r) row_start[r] = (uint32_t)j;
+}
+
+int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st)
+{
+    PM_LAUNCH(k_row_offsets, (unsigned)((np + 1 + 255) / 256), 256, 0, st, p->keys_sorted, np,
+              p->nc, p->row_start);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// CIC deposit (src/density.py:7-48), deterministic and atomic-free.
+//
+// One warp owns one output mesh row (Z, y) held as float64 in shared memory.  The row receives
+// mass from the particles of four source rows, visited in a fixed order:
+//     (Z, y) * t_z t_y,   (Z, y-1) * t_z d_y,   (Z-1, y) * d_z t_y,   (Z-1, y-1) * d_z d_y
+// Each source row is a contiguous, x-sorted run of the cell-sorted particle list.  The warp walks
+// it 32 particles at a time: every lane forms its two x-contributions exactly as the reference
+// does (mass*{t,d}_x*{t,d}_y*{t,d}_z left to right in float64, density.py:37-47), a warp-segmented
+// inclusive scan adds up lanes that share a cell, and the last lane of each cell run adds the run
+// totals to bins x_c and x_c+1 in two conflict-free phases.  The summation tree is fixed by the
+// sort order, so the result is bit-reproducible run to run; it differs from the reference's
+// sequential float32 "+=" only by rounding (float64 accumulation, one rounding at the end).
+// Every cell of rho is written exactly once, zeros included -- no memset pass.
+// --------------------------------------------------------------------------------------------
+template <int RY>
+__global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restrict__ px,
+                                                          const float *__restrict__ py,
+                                                          const float *__restrict__ pz,
+                                                          const uint32_t *__restrict__ order,
+                                                          const uint32_t *__restrict__ row_start,
+                                                          int nc, double mass,
+                                                          float *__restrict__ rho)
+{
+    extern __shared__ double s_rows[];
+    const unsigned full = 0xffffffffu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Z = blockIdx.y;
+    const int y = blockIdx.x * RY + warp;
+    if (y >= nc) return;  // warp-uniform; no block-wide barrier is used below
+    double *row = s_rows + (size_t)warp * nc;
+    for (int x = lane; x < nc; x += 32) row[x] = 0.0;
+    __syncwarp();
+
+    const int Zm = (Z == 0) ? nc - 1 : Z - 1;
+    const int ym = (y == 0) ? nc - 1 : y - 1;
+#pragma unroll 1
+    for (int src = 0; src < 4; ++src) {
+        const int zs = (src & 2) ? Zm : Z;
+        const int ys = (src & 1) ? ym : y;
+        const uint32_t r = (uint32_t)zs * nc + ys;
+        const uint32_t beg = row_start[r], end = row_start[r + 1];
+        for (uint32_t base = beg; base < end; base += 32) {
+            const uint32_t j = base + lane;
+            const bool valid = j < end;
+            int xc = -1 - lane;  // distinct dummy cells: idle lanes never join a run
+            double v0 = 0.0, v1 = 0.0;
+            if (valid) {
+                const uint32_t i = order[j];
+                const float x = px[i], yy = py[i], zz = pz[i];
+                xc = pm_cell(x, nc);
+                const double d_x = (double)x - (double)xc;      // density.py:24-26 (float64)
+                const double d_y = (double)yy - (double)ys;     // particle's y cell is ys by sort
+                const double d_z = (double)zz - (double)zs;
+                const double t_x = 1.0 - d_x;
+                const double w_y = (src & 1) ? d_y : 1.0 - d_y;
+                const double w_z = (src & 2) ? d_z : 1.0 - d_z;
+                v0 = __dmul_rn(__dmul_rn(__dmul_rn(mass, t_x), w_y), w_z);
+                v1 = __dmul_rn(__dmul_rn(__dmul_rn(mass, d_x), w_y), w_z);
+            }
+            // warp-segmented inclusive scan over runs of equal x cell
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double o0 = __shfl_up_sync(full, v0, d);
+                const double o1 = __shfl_up_sync(full, v1, d);
+                const int oc = __shfl_up_sync(full, xc, d);
+                if (lane >= d && oc == xc) {
+                    v0 += o0;
+                    v1 += o1;
+                }
+            }
+            const int nxt = __shfl_down_sync(full, xc, 1);
+            const bool tail = valid && (lane == 31 || nxt != xc);
+            if (tail) row[xc] += v0;
+            __syncwarp();
+            if (tail) row[(xc + 1 == nc) ? 0 : xc + 1] += v1;
+            __syncwarp();
+        }
+    }
+    float *out = rho + ((size_t)Z * nc + y) * nc;
+    for (int x = lane; x < nc; x += 32) out[x] = (float)row[x];
+}
+
+static const int PM_DEPOSIT_RY = 8;
+
+int pm_k_deposit(pm_plan *p, const float *pos, int64_t np, double mass, float *rho, cudaStream_t st)
+{
+    const int nc = p->nc;
+    size_t smem = (size_t)PM_DEPOSIT_RY * nc * sizeof(double);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        PM_CUDA(cudaFuncSetAttribute(k_deposit_rows<PM_DEPOSIT_RY>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    dim3 grid((nc + PM_DEPOSIT_RY - 1) / PM_DEPOSIT_RY, nc);
+    PM_LAUNCH(k_deposit_rows<PM_DEPOSIT_RY>, grid, PM_DEPOSIT_RY * 32, smem, st, pos, pos + np,
+              pos + 2 * np, p->order_sorted, p->row_start, nc, mass, rho);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Fused force gather + kick + drift (src/integrate.py:15-97), one thread per particle.
+//
+// Per particle: cell and CIC weights from the PRE-step position for all three directions
+// (integrate.py:20-24), 32 distinct phi loads (the 8 corners and their +-1 neighbours
+// along each axis), then per direction
+//     g_p  = (sum_c g_c * t_c) / 2          float32 products/sums left to right (integrate.py:92)
+//     v   += da*f_a1*g_p                    float64, stored float32          (integrate.py:94)
+//     x    = (x + da*v/(a+da)^2*f_a1) % Nc  float64 with the stored v, stored float32 (:95)
+// The weight table t[8,Np], the int64 cell table and its six per-direction copies that the
+// reference materialises never exist here.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double pm_pymod(double a, double n)
+{
+    // Python float %: fmod then lift negatives by n.  Fast exact paths for the usual ranges.
+    if (a >= 0.0) {
+        if (a < n) return a;
+        if (a < 2.0 * n) return a - n;  // exact (Sterbenz)
+        return fmod(a, n);
+    }
+    double r = (a >= -n) ? a : fmod(a, n);
+    return (r < 0.0) ? __dadd_rn(r, n) : fabs(r);
+}
+
+template <int DIR>
+__device__ __forceinline__ float pm_gp(const float (&v)[4][4][4], const float (&t)[8])
+{
+    // corner (oz,oy,ox): g = -phi[c+o+e_DIR] + phi[c+o-e_DIR]        (integrate.py:84-91)
+#define PM_G(oz, oy, ox)                                                                   \
+    __fsub_rn(v[1 + oz - (DIR == 2)][1 + oy - (DIR == 1)][1 + ox - (DIR == 0)],            \
+              v[1 + oz + (DIR == 2)][1 + oy + (DIR == 1)][1 + ox + (DIR == 0)])
+    float s = __fmul_rn(PM_G(0, 0, 0), t[0]);           // g    * ttt
+    s = __fadd_rn(s, __fmul_rn(PM_G(0, 0, 1), t[1]));   // g_x  * dtt
+    s = __fadd_rn(s, __fmul_rn(PM_G(0, 1, 0), t[2]));   // g_y  * tdt
+    s = __fadd_rn(s, __fmul_rn(PM_G(1, 0, 0), t[3]));   // g_z  * ttd
+    s = __fadd_rn(s, __fmul_rn(PM_G(0, 1, 1), t[4]));   // g_xy * ddt
+    s = __fadd_rn(s, __fmul_rn(PM_G(1, 0, 1), t[5]));   // g_xz * dtd
+    s = __fadd_rn(s, __fmul_rn(PM_G(1, 1, 0), t[6]));   // g_yz * tdd
+    s = __fadd_rn(s, __fmul_rn(PM_G(1, 1, 1), t[7]));   // g_xyz* ddd
+#undef PM_G
+    return s;
+}
+
+__device__ __forceinline__ void pm_push(float &x, float &vel, float s, double k_kick, double da,
+                                        double aa, double f_a1, int nc, float *acc_out)
+{
+    const double g_p = (double)s / 2.0;
+    if (acc_out) *acc_out = (float)g_p;
+    vel = (float)__dadd_rn((double)vel, __dmul_rn(k_kick, g_p));
+    const double step = __dmul_rn(__ddiv_rn(__dmul_rn(da, (double)vel), aa), f_a1);
+    x = (float)pm_pymod(__dadd_rn((double)x, step), (double)nc);
+}
+
+__global__ void __launch_bounds__(256) k_gather_kick_drift(float *__restrict__ pos,
+                                                           float *__restrict__ vel, int64_t np,
+                                                           const float *__restrict__ phi, int nc,
+                                                           double k_kick, double da, double aa,
+                                                           double f_a1, float *__restrict__ acc)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= np) return;
+    float x = pos[i], y = pos[np + i], z = pos[2 * np + i];
+    float vx = vel[i], vy = vel[np + i], vz = vel[2 * np + i];
+
+    const int xc = pm_cell(x, nc), yc = pm_cell(y, nc), zc = pm_cell(z, nc);
+    // weights (integrate.py:36-51): float64 products left to right, stored float32
+    const double d_x = (double)x - (double)xc, d_y = (double)y - (double)yc,
+                 d_z = (double)z - (double)zc;
+    const double t_x = 1.0 - d_x, t_y = 1.0 - d_y, t_z = 1.0 - d_z;
+    float t[8];
+    t[0] = (float)__dmul_rn(__dmul_rn(t_x, t_y), t_z);
+    t[1] = (float)__dmul_rn(__dmul_rn(d_x, t_y), t_z);
+    t[2] = (float)__dmul_rn(__dmul_rn(t_x, d_y), t_z);
+    t[3] = (float)__dmul_rn(__dmul_rn(t_x, t_y), d_z);
+    t[4] = (float)__dmul_rn(__dmul_rn(d_x, d_y), t_z);
+    t[5] = (float)__dmul_rn(__dmul_rn(d_x, t_y), d_z);
+    t[6] = (float)__dmul_rn(__dmul_rn(t_x, d_y), d_z);
+    t[7] = (float)__dmul_rn(__dmul_rn(d_x, d_y), d_z);
+
+    // periodic neighbour indices c-1, c, c+1, c+2 (integrate.py:64-65,77-82)
+    uint32_t xo[4], yo[4], zo[4];
+    {
+        const int n = nc;
+        int a1 = xc + 1 == n ? 0 : xc + 1;
+        xo[0] = xc == 0 ? n - 1 : xc - 1; xo[1] = xc; xo[2] = a1; xo[3] = a1 + 1 == n ? 0 : a1 + 1;
+        int b1 = yc + 1 == n ? 0 : yc + 1;
+        yo[0] = yc == 0 ? n - 1 : yc - 1; yo[1] = yc; yo[2] = b1; yo[3] = b1 + 1 == n ? 0 : b1 + 1;
+        int c1 = zc + 1 == n ? 0 : zc + 1;
+        zo[0] = zc == 0 ? n - 1 : zc - 1; zo[1] = zc; zo[2] = c1; zo[3] = c1 + 1 == n ? 0 : c1 + 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            yo[k] *= (uint32_t)n;
+            zo[k] *= (uint32_t)n * (uint32_t)n;
+        }
+    }
+    // the 32 cells with at most one "outer" (0 or 3) coordinate
+    float v[4][4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int outer = (a == 0 || a == 3) + (b == 0 || b == 3) + (c == 0 || c == 3);
+                v[a][b][c] = (outer <= 1) ? __ldg(phi + (zo[a] + yo[b] + xo[c])) : 0.0f;
+            }
+
+    const float sx = pm_gp<0>(v, t), sy = pm_gp<1>(v, t), sz = pm_gp<2>(v, t);
+    pm_push(x, vx, sx, k_kick, da, aa, f_a1, nc, acc ? acc + i : nullptr);
+    pm_push(y, vy, sy, k_kick, da, aa, f_a1, nc, acc ? acc + np + i : nullptr);
+    pm_push(z, vz, sz, k_kick, da, aa, f_a1, nc, acc ? acc + 2 * np + i : nullptr);
+
+    pos[i] = x; pos[np + i] = y; pos[2 * np + i] = z;
+    vel[i] = vx; vel[np + i] = vy; vel[2 * np + i] = vz;
+}
+
+int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const float *phi,
+                           double a_val, double f_a1, double da, float *acc, cudaStream_t st)
+{
+    if (np == 0) return PM_OK;
+    // host scalars evaluated exactly as integrate.py:94-95 does: da*f_a1, (a_val+da)**2
+    const double k_kick = da * f_a1;
+    const double aa = (a_val + da) * (a_val + da);
+    PM_LAUNCH(k_gather_kick_drift, (unsigned)((np + 255) / 256), 256, 0, st, pos, vel, np, phi,
+              p->nc, k_kick, da, aa, f_a1, acc);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}

@@ -1,0 +1,97 @@
+// pm_poisson.cu -- Poisson solve of the PM step: cuFFT R2C -> fused Green's kernel -> cuFFT C2R.
+//
+// Reference: src/potential.py:7-29 (complex128 c2c transforms of the real density, a separate
+// elementwise multiply by the float32[Nc^3] table of src/fourier_utils.py:5-16, real part kept).
+// Here the density is real, so only the Nc*Nc*(Nc/2+1) half spectrum exists, the table is never
+// materialised (three float32 sin^2 values per mode from an Nc-entry table), and the constant
+// -3*Omega_m/(8a), the 1/Nc^3 of the inverse transform (pyFFTW normalises, cuFFT does not) and
+// the zeroed DC mode are folded into the same pass over the spectrum.
+#include <math.h>
+
+#include "pm_internal.cuh"
+
+// sin^2(k_i/2), k_i = 2*pi*fftfreq(Nc)[i]   (src/fourier_utils.py:8-15).  sin^2 is even and
+// pi-periodic, so sin^2(pi*i/Nc) covers the negative frequencies too.  Evaluated in float64 on
+// the host and rounded once to float32 (the reference rounds k to float32 first; the difference
+// is below 2e-7 relative per mode).
+int pm_k_sin2_table(pm_plan *p)
+{
+    const int nc = p->nc;
+    float *h = (float *)malloc(sizeof(float) * nc);
+    if (!h) return PM_ERR_NOMEM;
+    for (int i = 0; i < nc; ++i) {
+        double s = sin(M_PI * (double)i / (double)nc);
+        h[i] = (float)(s * s);
+    }
+    cudaError_t e = cudaMemcpy(p->sin2, h, sizeof(float) * nc, cudaMemcpyHostToDevice);
+    free(h);
+    return (int)e;
+}
+
+// G(z,y,x) = 1 / ((s[z] + s[y]) + s[x]) in float32, 0 at DC -- the table fourier_grid() returns.
+__device__ __forceinline__ float pm_green(float sz, float sy, float sx)
+{
+    const float ksq = __fadd_rn(__fadd_rn(sz, sy), sx);
+    return ksq != 0.0f ? __fdiv_rn(1.0f, ksq) : 0.0f;
+}
+
+__global__ void __launch_bounds__(256) k_fourier_grid(const float *__restrict__ sin2, int nc,
+                                                      float *__restrict__ fgrid)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, z = blockIdx.z;
+    if (x >= nc) return;
+    fgrid[((size_t)z * nc + y) * nc + x] = pm_green(sin2[z], sin2[y], sin2[x]);
+}
+
+int pm_k_fourier_grid(pm_plan *p, float *fgrid, cudaStream_t st)
+{
+    dim3 grid((p->nc + 255) / 256, p->nc, p->nc);
+    PM_LAUNCH(k_fourier_grid, grid, 256, 0, st, p->sin2, p->nc, fgrid);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// phi_k = (-3*Omega_m/8/a / Nc^3) * G(k) * rho_k on the half spectrum [z][y][x <= Nc/2], in place.
+// One CTA per (z, y) row; the x-row of sin^2 sits in shared memory; float2 (8-byte) accesses.
+__global__ void __launch_bounds__(256) k_green_multiply(float2 *__restrict__ spec,
+                                                        const float *__restrict__ sin2, int nc,
+                                                        int nxh, double scale)
+{
+    extern __shared__ float s_sin2[];
+    for (int i = threadIdx.x; i < nxh; i += blockDim.x) s_sin2[i] = sin2[i];
+    __syncthreads();
+    const int rows = nc * nc;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int z = r / nc, y = r - z * nc;
+        const float sz = sin2[z], sy = sin2[y];
+        float2 *row = spec + (size_t)r * nxh;
+        for (int x = threadIdx.x; x < nxh; x += blockDim.x) {
+            const double g = scale * (double)pm_green(sz, sy, s_sin2[x]);
+            float2 c = row[x];
+            c.x = (float)(g * (double)c.x);
+            c.y = (float)(g * (double)c.y);
+            row[x] = c;
+        }
+    }
+}
+
+int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
+                 cudaStream_t st)
+{
+    const int nc = p->nc, nxh = nc / 2 + 1;
+    PM_CUFFT(cufftSetStream(p->r2c, st));
+    PM_CUFFT(cufftSetStream(p->c2r, st));
+    PM_CUFFT(cufftExecR2C(p->r2c, const_cast<float *>(rho), reinterpret_cast<cufftComplex *>(p->spec)));
+    pm_prof_mark(p, PM_STAGE_R2C + 1, st);
+    const double m = (double)nc * (double)nc * (double)nc;
+    const double scale = -3 * omega_m0 / 8 / a / m;  // potential.py:15, plus the IFFT's 1/Nc^3
+    int rows = nc * nc;
+    int grid = rows < p->sm_count * 8 ? rows : p->sm_count * 8;
+    PM_LAUNCH(k_green_multiply, grid, 256, nxh * sizeof(float), st, p->spec, p->sin2, nc, nxh, scale);
+    PM_CHECK_LAUNCH();
+    pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
+    PM_CUFFT(cufftExecC2R(p->c2r, reinterpret_cast<cufftComplex *>(p->spec), phi));
+    pm_prof_mark(p, PM_STAGE_C2R + 1, st);
+    return PM_OK;
+}

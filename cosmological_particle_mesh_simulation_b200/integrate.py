@@ -1,0 +1,72 @@
+"""advance_time / integrate -- force interpolation and leapfrog kick + drift
+(reference: src/integrate.py:9-97).
+
+B200 path: pm_gather_kick_drift, one fused kernel (csrc/pm_particles.cu): CIC weights from the
+pre-step position, central-difference force at the 8 corners, kick, drift with periodic wrap.
+positions and velocities are updated IN PLACE and returned, like the reference."""
+try:
+    from . import _runtime as rt
+    from .cosmology import f
+    from .potential import _potential_device
+    from .fourier_utils import FourierGrid
+except ImportError:
+    import _runtime as rt
+    from cosmology import f
+    from potential import _potential_device
+    from fourier_utils import FourierGrid
+import numpy as np
+import torch
+
+
+def _integrate_device(positions, velocities, a_val, f_a1, da, potentials, acc=None):
+    n = potentials.shape[0]
+    rt.check_dev_f32(potentials, (n, n, n), "potentials")
+    rt.check_dev_f32(positions, name="positions")
+    rt.check_dev_f32(velocities, tuple(positions.shape), "velocities")
+    if positions.dim() != 2 or positions.shape[0] != 3:
+        raise ValueError("positions must have shape (3, Np)")
+    dev = positions.device.index
+    npart = positions.shape[1]
+    plan = rt.get_plan(n, 1, dev)
+    if acc is not None:
+        rt.check_dev_f32(acc, (3, npart), "acc")
+    with torch.cuda.device(dev):
+        rt.check(rt.lib().pm_gather_kick_drift(
+            plan.handle, positions.data_ptr(), velocities.data_ptr(), npart, potentials.data_ptr(),
+            float(a_val), float(f_a1), float(da), acc.data_ptr() if acc is not None else None,
+            rt.stream_ptr(dev)), "pm_gather_kick_drift")
+    return positions, velocities
+
+
+def _copy_back(dst, src_dev):
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src_dev)
+    else:
+        np.copyto(dst, src_dev.cpu().numpy())
+
+
+def integrate(positions, velocities, a_val, f_a1, da, potentials):
+    """src/integrate.py:15-25."""
+    if rt.is_host(positions):
+        dev = rt.current_device()
+        p, v = rt.to_device(positions, dev), rt.to_device(velocities, dev)
+        phi = rt.to_device(potentials, dev) if rt.is_host(potentials) else potentials
+        _integrate_device(p, v, a_val, f_a1, da, phi)
+        _copy_back(positions, p)
+        _copy_back(velocities, v)
+        return positions, velocities
+    return _integrate_device(positions, velocities, a_val, f_a1, da, potentials)
+
+
+def advance_time(density, positions, velocities, fgrid, a, da):
+    """src/integrate.py:9-13, including the argument order of the f() call (H0 lands in the
+    Omega_m slot of src/cosmology.py:23)."""
+    cfg = rt.config()
+    fa1 = f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])
+    if rt.is_host(positions):
+        dev = rt.current_device()
+        rho = rt.to_device(density, dev) if rt.is_host(density) else density
+        phi = _potential_device(rho, fgrid, a)
+        return integrate(positions, velocities, a, fa1, da, phi)
+    phi = _potential_device(density, fgrid, a)
+    return _integrate_device(positions, velocities, a, fa1, da, phi)

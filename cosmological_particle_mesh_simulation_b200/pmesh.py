@@ -1,0 +1,88 @@
+"""The per-timestep loop (reference: src/pmesh.py:56-63) as single C-ABI calls.
+
+`step` is one loop body on device-resident state (pm_step), `step_host` the same for state kept
+in host memory (pm_step_host, uploads/downloads overlapped with compute), `simulator` the
+`while a_current < A_END - da` loop itself with the reference's predicate kept verbatim
+(SURVEY Q10).  Initial conditions, snapshots and plots are outside this package's scope: the
+caller supplies positions/velocities and an optional per-step callback."""
+try:
+    from . import _runtime as rt
+    from .cosmology import f
+except ImportError:
+    import _runtime as rt
+    from cosmology import f
+import torch
+
+
+def _fa1(a, da, cfg):
+    return f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])  # src/integrate.py:12
+
+
+def step(positions, velocities, a, da, mass=None, rho_out=None):
+    """rho = density(pos, mass); pos, vel = advance_time(rho, pos, vel, fgrid, a, da) on CUDA
+    tensors, in place.  rho_out (optional float32[Nc,Nc,Nc] CUDA tensor) receives the density."""
+    cfg = rt.config()
+    n = int(cfg.N_CELLS)
+    if mass is None:
+        mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3  # src/pmesh.py:28
+    rt.check_dev_f32(positions, name="positions")
+    rt.check_dev_f32(velocities, tuple(positions.shape), "velocities")
+    dev = positions.device.index
+    npart = positions.shape[1]
+    if rho_out is not None:
+        rt.check_dev_f32(rho_out, (n, n, n), "rho_out")
+    plan = rt.get_plan(n, npart, dev)
+    with torch.cuda.device(dev):
+        rt.check(rt.lib().pm_step(plan.handle, positions.data_ptr(), velocities.data_ptr(), npart,
+                                  float(mass), float(a), float(da), float(_fa1(a, da, cfg)),
+                                  float(cfg.OMEGA_M0),
+                                  rho_out.data_ptr() if rho_out is not None else None,
+                                  rt.stream_ptr(dev)), "pm_step")
+    return positions, velocities
+
+
+def step_host(positions, velocities, a, da, mass=None, rho_out=None, device=None):
+    """Same loop body for host-resident state: NumPy arrays or CPU tensors (pinned = fast),
+    updated in place.  Returns after the results are back in host memory."""
+    cfg = rt.config()
+    n = int(cfg.N_CELLS)
+    if mass is None:
+        mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3
+    p = rt.as_host_f32(positions)
+    v = rt.as_host_f32(velocities, p.shape)
+    r = rt.as_host_f32(rho_out, (n, n, n)) if rho_out is not None else None
+    dev = rt.current_device() if device is None else int(device)
+    plan = rt.get_plan(n, p.shape[1], dev)
+    rt.check(rt.lib().pm_step_host(plan.handle, p.ctypes.data, v.ctypes.data, p.shape[1],
+                                   float(mass), float(a), float(da), float(_fa1(a, da, cfg)),
+                                   float(cfg.OMEGA_M0), r.ctypes.data if r is not None else None),
+             "pm_step_host")
+    return positions, velocities
+
+
+def loop_scale_factors(cfg=None):
+    """The (a_current, da) pairs the loop of src/pmesh.py:30,56,63 visits, predicate verbatim."""
+    cfg = cfg or rt.config()
+    da = (cfg.A_END - cfg.A_INIT) / cfg.STEPS
+    a_current = cfg.A_INIT
+    out = []
+    while a_current < cfg.A_END - da:
+        out.append((a_current, da))
+        a_current += da
+    return out
+
+
+def simulator(positions, velocities, on_step=None, max_steps=None):
+    """Run the loop of src/pmesh.py:56-63 on CUDA tensors.  on_step(i, a_current, rho, positions,
+    velocities) is called after each step with the PRE-step density and POST-step particles,
+    the pairing the reference's save_file sees (src/pmesh.py:60-67)."""
+    cfg = rt.config()
+    n = int(cfg.N_CELLS)
+    rho = torch.empty((n, n, n), dtype=torch.float32, device=positions.device) if on_step else None
+    for i, (a_current, da) in enumerate(loop_scale_factors(cfg)):
+        if max_steps is not None and i >= max_steps:
+            break
+        step(positions, velocities, a_current, da, rho_out=rho)
+        if on_step:
+            on_step(i, a_current + da, rho, positions, velocities)
+    return positions, velocities

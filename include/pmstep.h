@@ -1,0 +1,164 @@
+/*
+ * pmstep.h -- C ABI of libpmstep.so: a B200 (sm_100a) particle-mesh timestep.
+ *
+ * This is the drop-in boundary for the per-timestep loop of
+ * grkooij/Cosmological-Particle-Mesh-Simulation (reference: src/pmesh.py:56-63).  The reference
+ * has no FFI layer of its own (it is Python calling numba-jitted functions and pyFFTW), so each
+ * entry point below replaces one reference *callable* and cites it; INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every pointer is a raw address, every size explicit;
+ *   - "_d" pointers are device memory of the plan's device, "_h" pointers are host memory;
+ *   - particle arrays are SoA float32[3][np], row 0 = x (zeldovich.py:12-13); meshes are
+ *     float32[Nc][Nc][Nc] indexed [z][y][x], x contiguous (density.py:11,37);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all device
+ *     entry points are asynchronous on that stream and never synchronise, the *_host entry
+ *     points return after their results are in host memory;
+ *   - return value: 0 on success, a positive cudaError_t, or one of the negative PM_ERR_* codes;
+ *     nothing throws, nothing prints;
+ *   - no allocation after pm_plan_create(): all scratch lives in the plan's workspace, whose
+ *     size pm_plan_workspace_bytes() reports in advance;
+ *   - there is no CPU fallback: without a CUDA device every entry point fails with
+ *     PM_ERR_NO_DEVICE or the cudaError_t it hit.
+ */
+#ifndef PMSTEP_H
+#define PMSTEP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* The library is built with -fvisibility=hidden; only these entry points are exported. */
+#if defined(__GNUC__)
+#define PM_API __attribute__((visibility("default")))
+#else
+#define PM_API
+#endif
+
+#define PM_OK 0
+#define PM_ERR_INVALID (-1)     /* bad argument (NULL pointer, size out of range, np > capacity) */
+#define PM_ERR_UNSUPPORTED (-2) /* configuration outside what this build handles            */
+#define PM_ERR_NOMEM (-3)       /* workspace allocation failed                              */
+#define PM_ERR_CUFFT (-4)       /* cuFFT returned an error (pm_last_cufft_status())         */
+#define PM_ERR_NO_DEVICE (-5)   /* no usable CUDA device                                    */
+
+typedef struct pm_plan pm_plan; /* opaque */
+typedef void *pm_stream_t;      /* cudaStream_t */
+
+/* Library identification; counts kernels launched by this library in this process (bench.py's
+ * gpu_launches). */
+PM_API const char *pm_version(void);
+PM_API const char *pm_error_string(int code);
+PM_API int pm_last_cufft_status(void);
+PM_API uint64_t pm_launch_count(void);
+
+/*
+ * Plan = everything fourier_grid() stands for in the reference (src/fourier_utils.py:5-16,
+ * called once at src/pmesh.py:54) plus the scratch the reference re-allocates every step
+ * (potential.py:19,26; integrate.py:33,61-62): cuFFT R2C/C2R plans, the sin^2(pi i/Nc) table of
+ * the Green's function, sort buffers, row offsets, the half-spectrum and one mesh.
+ *
+ *   n_cells      N_CELLS  (configure_me.py:8), 4 <= n_cells and n_cells^3 < 2^32
+ *   np_capacity  largest particle count later calls may pass (N_PARTS^3, configure_me.py:7)
+ *   device       CUDA device ordinal, or -1 for the current device
+ */
+PM_API size_t pm_plan_workspace_bytes(int n_cells, int64_t np_capacity);
+PM_API int pm_plan_create(pm_plan **plan, int n_cells, int64_t np_capacity, int device);
+PM_API int pm_plan_destroy(pm_plan *plan);
+PM_API int pm_plan_n_cells(const pm_plan *plan);
+PM_API int64_t pm_plan_np_capacity(const pm_plan *plan);
+
+/*
+ * fourier_grid() made explicit (src/fourier_utils.py:5-16): writes the float32[Nc^3] table
+ * 1/(sin^2(kz/2)+sin^2(ky/2)+sin^2(kx/2)) with the DC entry set to 0 (the reference leaves it
+ * uninitialised).  Only for inspection/parity -- the solver never materialises this table.
+ */
+PM_API int pm_fourier_grid(pm_plan *plan, float *fgrid_d, pm_stream_t stream);
+
+/*
+ * Cell key of every particle: key = (z_c*Nc + y_c)*Nc + x_c with c = int(floor(pos)) mod Nc
+ * (src/density.py:19-21,37).  keys_d: uint32[np].
+ */
+PM_API int pm_cell_keys(pm_plan *plan, const float *pos_d, int64_t np, uint32_t *keys_d,
+                 pm_stream_t stream);
+
+/*
+ * Stable radix sort of the particles by cell key.  keys_sorted_d, order_d: uint32[np];
+ * order_d[j] = original index of the j-th particle in cell order.  Either output may be NULL.
+ */
+PM_API int pm_sort_by_cell(pm_plan *plan, const float *pos_d, int64_t np, uint32_t *keys_sorted_d,
+                    uint32_t *order_d, pm_stream_t stream);
+
+/*
+ * density(positions, mass) (src/density.py:7-48; called at src/pmesh.py:60): cloud-in-cell
+ * deposit.  keys -> sort -> deterministic warp-segmented scatter; every cell of rho_d is written
+ * exactly once (no memset, no atomics).  pos_d is not modified.
+ */
+PM_API int pm_deposit_cic(pm_plan *plan, const float *pos_d, int64_t np, double mass, float *rho_d,
+                   pm_stream_t stream);
+
+/*
+ * potential(density, fgrid, a) (src/potential.py:7-29; called at src/integrate.py:11):
+ * phi = IFFT( -3*omega_m0/(8a) * G(k) * FFT(rho) ), G from pm_fourier_grid, inverse normalised
+ * by 1/Nc^3.  cuFFT R2C -> fused Green's kernel on the half spectrum -> cuFFT C2R, float32.
+ * rho_d is not modified; phi_d may alias rho_d.
+ */
+PM_API int pm_poisson(pm_plan *plan, const float *rho_d, double a, double omega_m0, float *phi_d,
+               pm_stream_t stream);
+
+/*
+ * integrate(positions, velocities, a_val, f_a1, da, potentials) (src/integrate.py:15-97):
+ * CIC force gather (central difference of phi at the 8 corners), kick and drift with periodic
+ * wrap, fused in one kernel; pos_d and vel_d are updated in place.  f_a1 is the host scalar
+ * f(a+da, ...) of src/integrate.py:12 / src/cosmology.py:20-27.  acc_d (optional, float32[3][np])
+ * receives g_p of src/integrate.py:92.
+ */
+PM_API int pm_gather_kick_drift(pm_plan *plan, float *pos_d, float *vel_d, int64_t np,
+                         const float *phi_d, double a_val, double f_a1, double da, float *acc_d,
+                         pm_stream_t stream);
+
+/*
+ * One body of the loop src/pmesh.py:60-61 on device-resident state:
+ *   rho = density(pos, mass); pos, vel = advance_time(rho, pos, vel, fgrid, a, da)
+ * rho_d (optional) receives the pre-step density (what the reference keeps for save/plot,
+ * src/pmesh.py:67-73); when NULL the deposit lands in the plan's own mesh.
+ */
+PM_API int pm_step(pm_plan *plan, float *pos_d, float *vel_d, int64_t np, double mass, double a,
+            double da, double f_a1, double omega_m0, float *rho_d, pm_stream_t stream);
+
+/*
+ * The same loop body for a caller that keeps its state in host memory like the reference does
+ * (NumPy arrays): uploads pos_h/vel_h, runs pm_step, downloads the updated pos_h/vel_h (and
+ * rho_h when not NULL).  Pinned host buffers make the copies asynchronous and overlapped;
+ * pageable ones work but are slower.  Returns after the results are in host memory.
+ */
+PM_API int pm_step_host(pm_plan *plan, float *pos_h, float *vel_h, int64_t np, double mass, double a,
+                 double da, double f_a1, double omega_m0, float *rho_h);
+
+/*
+ * Per-stage device timing of pm_step (bench.py's live roofline).  pm_plan_profile_begin arms a
+ * ring of CUDA events for up to max_steps calls of pm_step (0 disarms it); each armed call records
+ * an event on the caller's stream between stages -- no synchronisation, no extra kernels.
+ * pm_plan_profile_read synchronises on the last event and writes ms[step][PM_NUM_STAGES]
+ * (row-major) for the *n_steps calls recorded since begin.
+ */
+#define PM_STAGE_KEYS 0    /* cell keys                         (own kernel)            */
+#define PM_STAGE_SORT 1    /* radix sort by cell                (cub)                   */
+#define PM_STAGE_ROWS 2    /* row offsets                       (own kernel)            */
+#define PM_STAGE_DEPOSIT 3 /* warp-segmented CIC scatter        (own kernel)            */
+#define PM_STAGE_R2C 4     /* forward FFT                       (cuFFT)                 */
+#define PM_STAGE_GREEN 5   /* Green's function on half spectrum (own kernel)            */
+#define PM_STAGE_C2R 6     /* inverse FFT                       (cuFFT)                 */
+#define PM_STAGE_GATHER 7  /* force gather + kick + drift       (own kernel)            */
+#define PM_NUM_STAGES 8
+PM_API int pm_plan_profile_begin(pm_plan *plan, int max_steps);
+PM_API int pm_plan_profile_read(pm_plan *plan, float *ms, int *n_steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMSTEP_H */

@@ -27,9 +27,13 @@
 #include <omp.h>
 #endif
 
-/* Python's integer %: result has the sign of the divisor (density.py:19, integrate.py:20,65). */
+/* Python's integer %: result has the sign of the divisor (density.py:19, integrate.py:20,65).
+ * numba compiles N_CELLS in as a constant, so for a power-of-two mesh its % is a single AND;
+ * the same shortcut here (two's-complement AND == Python % for a power-of-two divisor) keeps the
+ * timing build comparable.  Values are identical either way. */
 static inline int64_t pymod_i64(int64_t a, int64_t n)
 {
+    if ((n & (n - 1)) == 0) return a & (n - 1);
     int64_t r = a % n;
     return (r < 0) ? r + n : r;
 }
@@ -82,7 +86,7 @@ void pmo_density(const float *positions, int64_t np, int nc, double mass, float 
     double d_z = (double)pz[i] - (double)z_c;                                         \
     double t_x = 1 - d_x, t_y = 1 - d_y, t_z = 1 - d_z;                               \
     /* density.py:33-35 */                                                            \
-    int64_t X = (x_c + 1) % n, Y = (y_c + 1) % n, Z = (z_c + 1) % n;                  \
+    int64_t X = pymod_i64(x_c + 1, n), Y = pymod_i64(y_c + 1, n), Z = pymod_i64(z_c + 1, n); \
     /* density.py:37-47, products left to right in float64, "+=" rounds to float32 */ \
     ADD(grid[(z_c * n + y_c) * n + x_c], mass * t_x * t_y * t_z);                     \
     ADD(grid[(z_c * n + y_c) * n + X], mass * d_x * t_y * t_z);                       \
@@ -178,11 +182,19 @@ static void pmo_sweep_one_direction(const int64_t *cc, float *pos_d, float *vel_
     /* integrate.py:61-65: two full copies of the cell table, one row rewritten in each */
     int64_t *cc_n = (int64_t *)malloc(sizeof(int64_t) * 3 * (size_t)np);
     int64_t *cc_p = (int64_t *)malloc(sizeof(int64_t) * 3 * (size_t)np);
-    memcpy(cc_n, cc, sizeof(int64_t) * 3 * (size_t)np);
-    memcpy(cc_p, cc, sizeof(int64_t) * 3 * (size_t)np);
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 1 ? nthreads : 1) schedule(static)
+#endif
+    for (int64_t i = 0; i < 3 * np; ++i) {
+        cc_n[i] = cc[i];
+        cc_p[i] = cc[i];
+    }
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads > 1 ? nthreads : 1) schedule(static)
+#endif
     for (int64_t i = 0; i < np; ++i) {
         cc_n[direction * np + i] = cc[direction * np + i] - 1;
-        cc_p[direction * np + i] = (cc[direction * np + i] + 1) % n;
+        cc_p[direction * np + i] = pymod_i64(cc[direction * np + i] + 1, n);
     }
 
 #define PHI(zz, yy, xx) phi[(wrapneg(zz, n) * n + wrapneg(yy, n)) * n + wrapneg(xx, n)]
@@ -193,8 +205,8 @@ static void pmo_sweep_one_direction(const int64_t *cc, float *pos_d, float *vel_
         /* integrate.py:69-82 */
         int64_t x = cc_p[i], y = cc_p[np + i], z = cc_p[2 * np + i];
         int64_t x2 = cc_n[i], y2 = cc_n[np + i], z2 = cc_n[2 * np + i];
-        int64_t X = (x + 1) % n, Y = (y + 1) % n, Z = (z + 1) % n;
-        int64_t X2 = (x2 + 1) % n, Y2 = (y2 + 1) % n, Z2 = (z2 + 1) % n;
+        int64_t X = pymod_i64(x + 1, n), Y = pymod_i64(y + 1, n), Z = pymod_i64(z + 1, n);
+        int64_t X2 = pymod_i64(x2 + 1, n), Y2 = pymod_i64(y2 + 1, n), Z2 = pymod_i64(z2 + 1, n);
         /* integrate.py:84-91, float32 */
         float g = -PHI(z, y, x) + PHI(z2, y2, x2);
         float g_x = -PHI(z, y, X) + PHI(z2, y2, X2);

@@ -1,0 +1,130 @@
+"""CPU-side checks (no GPU needed): the C-ABI library loads and exports every symbol that
+include/pmstep.h declares, fails loudly without a device, and the host-side mirror of the
+reference interface (configure_me names, f(), loop predicate, flat-module drop-in) is right."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "cosmological_particle_mesh_simulation_b200")
+HEADER = os.path.join(REPO, "include", "pmstep.h")
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    so = os.path.join(PKG, "libpmstep.so")
+    if not os.path.exists(so):
+        sys.path.insert(0, REPO)
+        import __graft_entry__ as g
+        g.build()
+    assert os.path.exists(so)
+    return so
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    return re.findall(r"PM_API\s+[\w\s\*]+?\b(pm_\w+)\s*\(", text)
+
+
+def test_header_declares_the_documented_surface():
+    syms = declared_symbols()
+    for must in ["pm_plan_create", "pm_plan_destroy", "pm_cell_keys", "pm_sort_by_cell", "pm_deposit_cic",
+                 "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_fourier_grid"]:
+        assert must in syms
+    assert len(syms) == len(set(syms))
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(libpath)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in pmstep.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(declared_symbols()) == {s for s in exported if s.startswith("pm_")}
+    # python binding table and header agree
+    from cosmological_particle_mesh_simulation_b200 import _runtime as rt
+    assert set(rt.EXPORTED_SYMBOLS) == set(declared_symbols())
+
+
+def test_built_for_sm_100a_only(libpath):
+    out = subprocess.run(["cuobjdump", "--list-elf", libpath], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_device(libpath):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import cosmological_particle_mesh_simulation_b200 as pm
+    lib = pm._runtime.lib()
+    assert b"pmstep" in lib.pm_version()
+    h = ctypes.c_void_p()
+    assert lib.pm_plan_create(ctypes.byref(h), 32, 1000, -1) == -5      # PM_ERR_NO_DEVICE
+    assert lib.pm_plan_create(ctypes.byref(h), 2000, 1000, -1) == -2    # PM_ERR_UNSUPPORTED
+    assert lib.pm_step(None, None, None, 0, 1.0, 0.1, 0.1, 1.0, 0.3, None, None) == -1  # PM_ERR_INVALID
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.density(np.zeros((3, 8), np.float32), 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pm.fourier_grid()
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(PKG):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, fn)).read()
+                assert "oracle" not in text.lower().replace("# oracle", ""), f"{fn} mentions the oracle"
+    for fn in ["bench.py"]:
+        pass  # bench.py may use the oracle only in its cpu_baseline / --impl reference legs
+
+
+def test_configure_me_names_and_defaults_match_reference():
+    from cosmological_particle_mesh_simulation_b200 import configure_me as cm
+    want = dict(N_PARTS=256, N_CELLS=512, BOX_SIZE=100, N_CPU=16, RANDOM_SEED=38, STEPS=1000,
+                N_SAVE_FILES=100, N_PLOTS=100, PLOT_STEPS=False, PLOT_PROJECTIONS=False, PLOT_GRF=False,
+                SAVE_DATA=True, SAVE_DENSITY=False, PRINT_STATUS=True, RESTART=False, RESTART_FROM_N=0,
+                POWER=1.00, LCDM_TRANSFER_FUNCTION=True, OMEGA_M0=0.31, OMEGA_B0=0.04, OMEGA_K0=0.00,
+                OMEGA_LAMBDA0=0.69, H0=0.68, A_INIT=0.01, A_END=1.00)   # configure_me.py:7-40
+    for k, v in want.items():
+        assert getattr(cm, k) == v, k
+
+
+def test_f_matches_oracle_bitwise_and_loop_predicate():
+    import cosmological_particle_mesh_simulation_b200 as pm
+    for a in np.linspace(0.01, 1.0, 57):
+        assert pm.f(float(a), [0.68, 0.69, 0.0]) == float(O.f(float(a), [0.68, 0.69, 0.0]))
+    for steps, want in [(10, 10), (100, 99), (1000, 999), (500, 500), (2000, 1999)]:
+        cfg = types.SimpleNamespace(A_INIT=0.01, A_END=1.00, STEPS=steps)
+        sched = pm.loop_scale_factors(cfg)
+        assert len(sched) == want == O.loop_trip_count(O.Config(STEPS=steps))
+        assert sched[0] == (0.01, (1.00 - 0.01) / steps)
+
+
+def test_config_lookup_order():
+    import cosmological_particle_mesh_simulation_b200 as pm
+    pm.set_config(types.SimpleNamespace(N_CELLS=48))
+    assert pm.config().N_CELLS == 48
+    pm.set_config(None)
+    assert pm.config().N_CELLS == 512 or "configure_me" in sys.modules
+
+
+def test_flat_module_drop_in_layout():
+    """The reference imports `from density import density` etc. from a flat directory
+    (pmesh.py:5-16); putting the package directory on sys.path must satisfy those imports."""
+    code = ("import sys; sys.path.insert(0, %r);"
+            "from density import density; from integrate import advance_time, integrate;"
+            "from fourier_utils import fourier_grid; from potential import potential;"
+            "from cosmology import f, H, Dt; import configure_me;"
+            "print(configure_me.N_CELLS, density.__name__, advance_time.__name__)") % PKG
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["512", "density", "advance_time"]

@@ -1,0 +1,339 @@
+"""Parity of the CUDA path (through the C ABI of include/pmstep.h, via the Python drop-in modules)
+against the CPU oracle and the golden fixtures.  Run on the B200 box:  pytest -m gpu
+
+Bars (BASELINE.json north_star):
+  * cell keys, sort order: BIT-EXACT;
+  * gather+kick+drift given the same phi: BIT-EXACT positions and velocities (the kernel repeats
+    the reference's float32/float64 rounding points);
+  * density, potential, accelerations, positions, velocities: relative L2 <= 1e-5 per step over a
+    10-step free-running horizon;
+  * P(k) within 0.1 % after a full 64^3/128^3 run.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 1e-5  # north_star tolerance
+
+
+@pytest.fixture(scope="module")
+def pm():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import cosmological_particle_mesh_simulation_b200 as pm
+    yield pm
+    pm.set_config(None)
+    pm.release_plans()
+
+
+def cfg_ns(cfg: O.Config):
+    return types.SimpleNamespace(**cfg.__dict__)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def rel_l2_periodic(a, b, n):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = (a - b + n / 2) % n - n / 2
+    return np.linalg.norm(d) / np.linalg.norm(b)
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def load_case(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = O.Config(N_CELLS=int(g["n_cells"]), N_PARTS=int(g["n_parts"]), STEPS=int(g["steps_cfg"]))
+    return g, cfg
+
+
+CASES = ["g16_free10", "g32_step2", "g12_nonpow2", "clustered32"]
+
+
+# ----------------------------------------------------------------------------- keys and sort
+@pytest.mark.parametrize("name", CASES)
+def test_cell_keys_and_sort_order_bit_exact(pm, golden_dir, name):
+    import ctypes
+    g, cfg = load_case(golden_dir, name)
+    pm.set_config(cfg_ns(cfg))
+    rt = pm._runtime
+    for key in ["pos0", "pos_1", "pos_2"]:
+        pos = g[key]
+        npart = pos.shape[1]
+        plan = rt.get_plan(cfg.N_CELLS, npart, 0)
+        p = dev(pos)
+        keys = torch.empty(npart, dtype=torch.int32, device="cuda")
+        ks = torch.empty_like(keys)
+        order = torch.empty_like(keys)
+        rt.check(rt.lib().pm_cell_keys(plan.handle, p.data_ptr(), npart, keys.data_ptr(), None), "keys")
+        rt.check(rt.lib().pm_sort_by_cell(plan.handle, p.data_ptr(), npart, ks.data_ptr(),
+                                          order.data_ptr(), None), "sort")
+        torch.cuda.synchronize()
+        want_keys = O.cell_keys(pos, cfg)
+        want_order = O.sort_order(pos, cfg)
+        assert np.array_equal(keys.cpu().numpy().astype(np.int64), want_keys)
+        assert np.array_equal(order.cpu().numpy().astype(np.int64), want_order)
+        assert np.array_equal(ks.cpu().numpy().astype(np.int64), want_keys[want_order])
+
+
+# ----------------------------------------------------------------------------- deposit
+@pytest.mark.parametrize("name", CASES)
+def test_density_matches_golden_and_is_deterministic(pm, golden_dir, name):
+    g, cfg = load_case(golden_dir, name)
+    pm.set_config(cfg_ns(cfg))
+    pos = dev(g["pos0"])
+    rho = pm.density(pos, float(g["mass"]))
+    assert rho.shape == (cfg.N_CELLS,) * 3 and rho.dtype == torch.float32 and rho.is_cuda
+    got = rho.cpu().numpy()
+    assert rel_l2(got, g["rho_0"]) <= REL_L2
+    # far tighter in practice: float64 accumulation vs the reference's float32 running sum
+    assert rel_l2(got, g["rho_0"]) <= 2e-7
+    for _ in range(3):
+        assert torch.equal(pm.density(pos, float(g["mass"])), rho)   # bit-reproducible
+    # NumPy in -> NumPy out, same values (drop-in signature of density.py:8)
+    host = pm.density(g["pos0"], float(g["mass"]))
+    assert isinstance(host, np.ndarray) and np.array_equal(host, got)
+
+
+def test_density_single_particle_weights_and_wrap(pm):
+    cfg = O.Config(N_CELLS=16, N_PARTS=8)
+    pm.set_config(cfg_ns(cfg))
+    rho = pm.density(dev(np.array([[4.25], [7.0], [15.5]], dtype=np.float32)), 1.0).cpu().numpy()
+    assert rho[15, 7, 4] == 0.375 and rho[15, 7, 5] == 0.125
+    assert rho[0, 7, 4] == 0.375 and rho[0, 7, 5] == 0.125      # density.py:33-35
+    assert rho.sum() == 1.0
+    # Q4: x == N_CELLS deposits -(Nc-1)*m and +Nc*m
+    rho = pm.density(dev(np.array([[16.0], [3.0], [2.0]], dtype=np.float32)), 1.0).cpu().numpy()
+    assert rho[2, 3, 0] == -15.0 and rho[2, 3, 1] == 16.0
+    # empty particle set -> all zeros written (no memset relied upon)
+    rho = pm.density(torch.empty((3, 0), dtype=torch.float32, device="cuda"), 1.0)
+    assert float(rho.abs().max()) == 0.0
+
+
+def test_density_ragged_sizes(pm):
+    # particle counts that are not multiples of 4/32 and unaligned row starts (scalar key path)
+    cfg = O.Config(N_CELLS=24, N_PARTS=8)
+    pm.set_config(cfg_ns(cfg))
+    rs = np.random.RandomState(0)
+    for npart in [1, 2, 3, 5, 31, 33, 1001]:
+        pos = rs.uniform(0, 24, size=(3, npart)).astype(np.float32)
+        got = pm.density(dev(pos), 2.5).cpu().numpy()
+        assert rel_l2(got, O.density(pos, 2.5, cfg)) <= 2e-7
+
+
+# ----------------------------------------------------------------------------- Poisson
+@pytest.mark.parametrize("name", CASES)
+def test_fourier_grid_and_potential(pm, golden_dir, name):
+    g, cfg = load_case(golden_dir, name)
+    pm.set_config(cfg_ns(cfg))
+    fg = pm.fourier_grid()
+    table = fg.to_array().cpu().numpy()
+    want = O.fourier_grid(cfg)
+    assert table.shape == want.shape and table[0, 0, 0] == 0.0
+    assert np.abs(table - want).max() <= 1e-6 * np.abs(want).max()
+    for s in range(10):
+        if f"rho_{s}" not in g:
+            continue
+        a = float(g["a_list"][s])
+        phi = pm.potential(dev(g[f"rho_{s}"]), fg, a).cpu().numpy()
+        ref = g[f"phi_{s}"].astype(np.float64)
+        # DC of the Green's table is 0 on both sides; compare phi - mean anyway
+        assert rel_l2(phi - phi.mean(dtype=np.float64), ref - ref.mean()) <= REL_L2
+
+
+def test_single_mode_potential(pm):
+    cfg = O.Config(N_CELLS=32)
+    pm.set_config(cfg_ns(cfg))
+    m, a = 3, 0.25
+    x = np.arange(32)
+    rho = np.broadcast_to(np.cos(2 * np.pi * m * x / 32).astype(np.float32), (32, 32, 32)).copy()
+    phi = pm.potential(dev(rho), pm.fourier_grid(), a).cpu().numpy()
+    want = -3 * cfg.OMEGA_M0 / 8 / a / np.sin(np.pi * m / 32) ** 2 * rho
+    assert np.abs(phi - want).max() < 2e-5 * np.abs(want).max()
+
+
+# ----------------------------------------------------------------------------- gather/kick/drift
+@pytest.mark.parametrize("name", CASES)
+def test_integrate_bit_exact_given_reference_phi(pm, golden_dir, name):
+    g, cfg = load_case(golden_dir, name)
+    pm.set_config(cfg_ns(cfg))
+    da = float(g["da"])
+    s = 0
+    a = float(g["a_list"][s])
+    f_a1 = float(O.f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0]))
+    pos, vel = dev(g["pos0"]), dev(g["vel0"])
+    p2, v2 = pm.integrate(pos, vel, a, f_a1, da, dev(g[f"phi_{s}"]))
+    assert p2 is pos and v2 is vel
+    assert np.array_equal(vel.cpu().numpy(), g["vel_1"])
+    assert np.array_equal(pos.cpu().numpy(), g["pos_1"])
+    # accelerations (g_p of integrate.py:92) against the oracle
+    npart = g["pos0"].shape[1]
+    acc_ref = np.zeros((3, npart))
+    po, vo = g["pos0"].copy(), g["vel0"].copy()
+    O.integrate(po, vo, a, f_a1, da, g[f"phi_{s}"], cfg, acc=acc_ref)
+    acc = torch.zeros((3, npart), dtype=torch.float32, device="cuda")
+    import importlib
+    mod = importlib.import_module("cosmological_particle_mesh_simulation_b200.integrate")
+    mod._integrate_device(dev(g["pos0"]), dev(g["vel0"]), a, f_a1, da, dev(g[f"phi_{s}"]), acc=acc)
+    assert np.array_equal(acc.cpu().numpy(), acc_ref.astype(np.float32))
+
+
+def test_uniform_lattice_zero_kick(pm):
+    cfg = O.Config(N_CELLS=16, N_PARTS=16)
+    pm.set_config(cfg_ns(cfg))
+    pos, vel = O.lattice_ic(16, 16, jitter=0.0)
+    p, v = dev(pos), dev(vel)
+    rho = pm.density(p, 1.0)
+    assert torch.all(rho == 1.0)
+    pm.advance_time(rho, p, v, pm.fourier_grid(), 0.5, 0.01)
+    assert float(v.abs().max()) <= 1e-6     # phi is constant up to float32 FFT rounding
+
+
+# ----------------------------------------------------------------------------- whole step
+@pytest.mark.parametrize("name", CASES)
+def test_free_running_steps_against_golden(pm, golden_dir, name):
+    g, cfg = load_case(golden_dir, name)
+    pm.set_config(cfg_ns(cfg))
+    n = cfg.N_CELLS
+    pos, vel = dev(g["pos0"]), dev(g["vel0"])
+    fg = pm.fourier_grid()
+    da = float(g["da"])
+    for s, a in enumerate(g["a_list"]):
+        rho = pm.density(pos, float(g["mass"]))
+        if f"rho_{s}" in g:
+            assert rel_l2(rho.cpu().numpy(), g[f"rho_{s}"]) <= REL_L2, f"density step {s}"
+        pm.advance_time(rho, pos, vel, fg, float(a), da)
+        assert rel_l2_periodic(pos.cpu().numpy(), g[f"pos_{s + 1}"], n) <= REL_L2, f"positions step {s}"
+        assert rel_l2(vel.cpu().numpy(), g[f"vel_{s + 1}"]) <= REL_L2, f"velocities step {s}"
+
+
+@pytest.mark.parametrize("name", ["g16_free10", "clustered32"])
+def test_fused_step_and_host_step_equal_the_composed_calls(pm, golden_dir, name):
+    g, cfg = load_case(golden_dir, name)
+    pm.set_config(cfg_ns(cfg))
+    da, a, mass = float(g["da"]), float(g["a_list"][0]), float(g["mass"])
+    pos, vel = dev(g["pos0"]), dev(g["vel0"])
+    rho = pm.density(pos, mass)
+    pm.advance_time(rho, pos, vel, pm.fourier_grid(), a, da)
+    p2, v2 = dev(g["pos0"]), dev(g["vel0"])
+    rho2 = torch.empty_like(rho)
+    pm.step(p2, v2, a, da, mass=mass, rho_out=rho2)
+    assert torch.equal(rho2, rho) and torch.equal(p2, pos) and torch.equal(v2, vel)
+    p3, v3 = dev(g["pos0"]), dev(g["vel0"])
+    pm.step(p3, v3, a, da, mass=mass)                      # density kept in the plan's mesh
+    assert torch.equal(p3, pos) and torch.equal(v3, vel)
+    ph = torch.from_numpy(g["pos0"].copy()).pin_memory()
+    vh = torch.from_numpy(g["vel0"].copy()).pin_memory()
+    rh = torch.empty(rho.shape, dtype=torch.float32).pin_memory()
+    pm.step_host(ph, vh, a, da, mass=mass, rho_out=rh)
+    assert torch.equal(ph, pos.cpu()) and torch.equal(vh, vel.cpu()) and torch.equal(rh, rho.cpu())
+    pn, vn = g["pos0"].copy(), g["vel0"].copy()            # pageable NumPy buffers
+    pm.step_host(pn, vn, a, da, mass=mass)
+    assert np.array_equal(pn, pos.cpu().numpy()) and np.array_equal(vn, vel.cpu().numpy())
+
+
+def test_numpy_drop_in_signatures(pm, golden_dir):
+    """The reference's loop body (pmesh.py:60-61) on NumPy arrays, unchanged call shapes."""
+    g, cfg = load_case(golden_dir, "g12_nonpow2")
+    pm.set_config(cfg_ns(cfg))
+    pos, vel = g["pos0"].copy(), g["vel0"].copy()
+    fg = pm.fourier_grid()
+    rho = pm.density(pos, float(g["mass"]))
+    p2, v2 = pm.advance_time(rho, pos, vel, fg, float(g["a_list"][0]), float(g["da"]))
+    assert p2 is pos and v2 is vel and isinstance(rho, np.ndarray)
+    assert rel_l2_periodic(pos, g["pos_1"], cfg.N_CELLS) <= REL_L2
+    assert rel_l2(vel, g["vel_1"]) <= REL_L2
+
+
+def test_errors_are_loud(pm):
+    cfg = O.Config(N_CELLS=16, N_PARTS=8)
+    pm.set_config(cfg_ns(cfg))
+    with pytest.raises(TypeError):
+        pm.density(torch.zeros((3, 8), dtype=torch.float64, device="cuda"), 1.0)
+    with pytest.raises(TypeError):
+        pm.potential(torch.zeros((16, 16, 16), device="cuda"), np.zeros((16, 16, 16), np.float32), 0.5)
+    with pytest.raises(pm.PMStepError):
+        pm._runtime.Plan(2000, 10, 0)       # n_cells^3 >= 2^32 is outside this build
+
+
+# ----------------------------------------------------------------------------- full-size properties
+def test_full_size_properties_256_on_512(pm):
+    """BASELINE config 2 (256^3 on 512^3): too big for the oracle in a test, so check
+    size-independent properties: mass conservation, run-to-run determinism, sortedness,
+    momentum-free uniform lattice, and every particle inside [0, Nc] after a step."""
+    cfg = O.Config(N_CELLS=512, N_PARTS=256)
+    pm.set_config(cfg_ns(cfg))
+    rt = pm._runtime
+    pos_h, vel_h = O.lattice_ic(256, 512, seed=38)
+    npart = pos_h.shape[1]
+    pos, vel = dev(pos_h), dev(vel_h)
+    rho = pm.density(pos, 8.0)
+    total = float(rho.sum(dtype=torch.float64))
+    assert abs(total - 8.0 * npart) <= 1e-6 * 8.0 * npart
+    assert torch.equal(pm.density(pos, 8.0), rho)
+    plan = rt.get_plan(512, npart, 0)
+    ks = torch.empty(npart, dtype=torch.int32, device="cuda")
+    order = torch.empty_like(ks)
+    rt.check(rt.lib().pm_sort_by_cell(plan.handle, pos.data_ptr(), npart, ks.data_ptr(),
+                                      order.data_ptr(), None), "sort")
+    assert bool((ks[1:] >= ks[:-1]).all())
+    assert torch.equal(torch.sort(order.long()).values, torch.arange(npart, device="cuda"))
+    # spot-check 100k random particles' keys and a z-slab of the density against the oracle
+    sel = np.random.RandomState(1).choice(npart, 100000, replace=False)
+    keys = torch.empty(npart, dtype=torch.int32, device="cuda")
+    rt.check(rt.lib().pm_cell_keys(plan.handle, pos.data_ptr(), npart, keys.data_ptr(), None), "keys")
+    assert np.array_equal(keys.cpu().numpy()[sel].astype(np.int64),
+                          O.cell_keys(np.ascontiguousarray(pos_h[:, sel]), cfg))
+    p1, v1 = pos.clone(), vel.clone()
+    pm.step(p1, v1, 0.01, 0.00099)
+    assert float(p1.min()) >= 0.0 and float(p1.max()) <= 512.0
+    assert torch.isfinite(v1).all()
+    p2, v2 = pos.clone(), vel.clone()
+    pm.step(p2, v2, 0.01, 0.00099)
+    assert torch.equal(p1, p2) and torch.equal(v1, v2)
+    # uniform lattice: rho == mass everywhere, no kick
+    pl, vl = O.lattice_ic(256, 512, jitter=0.0)
+    pl, vl = dev(pl), dev(vl)
+    rho = pm.density(pl, 8.0)
+    assert bool((rho == 1.0).all())     # offset-0.5 lattice: every cell gets 8 * (m/8) / 8 = 1
+    pm.step(pl, vl, 0.5, 0.001)
+    assert float(vl.abs().max()) <= 1e-5
+
+
+def test_full_run_power_spectrum_64_on_128(pm):
+    """BASELINE config 1 (64^3 on 128^3, STEPS=100 -> 99 iterations): free-running CUDA path vs
+    the oracle from identical initial conditions; P(k) of the final density within 0.1 %."""
+    cfg = O.Config(N_CELLS=128, N_PARTS=64, STEPS=100, N_CPU=O.max_threads())
+    pm.set_config(cfg_ns(cfg))
+    pos_h, vel_h = O.lattice_ic(64, 128, seed=38, vel_rms=0.02)
+    pos, vel = dev(pos_h), dev(vel_h)
+    fg_o = O.fourier_grid(cfg)
+    cfg1 = O.Config(**{**cfg.__dict__, "N_CPU": 1})
+    nsteps = 0
+    for a, da in pm.loop_scale_factors(cfg_ns(cfg)):
+        pm.step(pos, vel, a, da)
+        rho_o = O.density(pos_h, 8.0, cfg1)
+        O.advance_time(rho_o, pos_h, vel_h, fg_o, a, da, cfg)
+        nsteps += 1
+        if nsteps == 10:   # the 10-step horizon of the north_star
+            assert rel_l2_periodic(pos.cpu().numpy(), pos_h, 128) <= REL_L2
+            assert rel_l2(vel.cpu().numpy(), vel_h) <= REL_L2
+    assert nsteps == 99
+    rho_gpu = pm.density(pos, 8.0).cpu().numpy()
+    rho_cpu = O.density(pos_h, 8.0, cfg1)
+    _, p_gpu = O.power_spectrum(rho_gpu)
+    _, p_cpu = O.power_spectrum(rho_cpu)
+    assert np.max(np.abs(p_gpu / p_cpu - 1.0)) <= 1e-3
