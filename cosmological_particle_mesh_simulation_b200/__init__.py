@@ -22,4 +22,4 @@ from .fourier_utils import fourier_grid, FourierGrid  # noqa: F401
 from .potential import potential  # noqa: F401
 from .integrate import advance_time, integrate  # noqa: F401
 from .cosmology import f  # noqa: F401
-from .pmesh import step, step_host, simulator, loop_scale_factors  # noqa: F401
+from .pmesh import step, step_host, simulator, loop_scale_factors, ResidentParticles  # noqa: F401

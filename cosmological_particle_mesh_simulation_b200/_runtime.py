@@ -65,6 +65,11 @@ def lib():
             "pm_gather_kick_drift": (i32, [vp, vp, vp, i64, vp, f64, f64, f64, vp, vp]),
             "pm_step": (i32, [vp, vp, vp, i64, f64, f64, f64, f64, f64, vp, vp]),
             "pm_step_host": (i32, [vp, vp, vp, i64, f64, f64, f64, f64, f64, vp]),
+            "pm_particles_load": (i32, [vp, vp, vp, i64, vp]),
+            "pm_step_resident": (i32, [vp, f64, f64, f64, f64, f64, vp, vp]),
+            "pm_particles_store": (i32, [vp, vp, vp, vp]),
+            "pm_particles_order": (i32, [vp, vp, vp]),
+            "pm_particles_count": (i64, [vp]),
             "pm_plan_profile_begin": (i32, [vp, i32]),
             "pm_plan_profile_read": (i32, [vp, vp, ctypes.POINTER(i32)]),
         }
@@ -80,7 +85,8 @@ EXPORTED_SYMBOLS = (
     "pm_plan_workspace_bytes", "pm_plan_create", "pm_plan_destroy", "pm_plan_n_cells",
     "pm_plan_np_capacity", "pm_fourier_grid", "pm_cell_keys", "pm_sort_by_cell", "pm_deposit_cic",
     "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_plan_profile_begin",
-    "pm_plan_profile_read",
+    "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_particles_store",
+    "pm_particles_order", "pm_particles_count",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

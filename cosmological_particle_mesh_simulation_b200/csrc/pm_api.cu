@@ -23,8 +23,8 @@ int key_bits_for(int nc)
 
 // Sizes of every workspace segment, in the order they are carved.
 struct Layout {
-    size_t keys, order, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2,
-        pos_stage, vel_stage, total;
+    size_t keys, iota, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2,
+        rpos, rvel, rid, total;
 };
 
 bool config_ok(int nc, int64_t np)
@@ -52,7 +52,7 @@ int compute_layout(int nc, int64_t np, size_t fft_work, Layout *L)
     const size_t m = (size_t)nc * nc * nc;
     const size_t npad = (size_t)((np + 3) / 4 * 4);
     L->keys = align_up(npad * 4);
-    L->order = align_up(npad * 4);
+    L->iota = align_up(npad * 4);
     L->keys_sorted = align_up(npad * 4);
     L->order_sorted = align_up(npad * 4);
     L->cub = align_up(pm_sort_temp_bytes(np > 0 ? np : 1, key_bits_for(nc)));
@@ -62,10 +62,11 @@ int compute_layout(int nc, int64_t np, size_t fft_work, Layout *L)
     L->spec = align_up((size_t)nc * nc * (nc / 2 + 1) * sizeof(float2));
     L->fft = align_up(fft_work);
     L->sin2 = align_up((size_t)nc * 4);
-    L->pos_stage = align_up(3 * npad * 4);
-    L->vel_stage = align_up(3 * npad * 4);
-    L->total = L->keys + L->order + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
-               L->mesh + L->mesh2 + L->spec + L->fft + L->sin2 + L->pos_stage + L->vel_stage;
+    L->rpos = align_up(3 * npad * 4);
+    L->rvel = align_up(3 * npad * 4);
+    L->rid = align_up(npad * 4);
+    L->total = L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
+               L->mesh + L->mesh2 + L->spec + L->fft + L->sin2 + 2 * (L->rpos + L->rvel + L->rid);
     return PM_OK;
 }
 
@@ -163,7 +164,7 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
     }
     char *c = p->ws;
     p->keys = (uint32_t *)c;          c += L.keys;
-    p->order = (uint32_t *)c;         c += L.order;
+    p->iota = (uint32_t *)c;          c += L.iota;
     p->keys_sorted = (uint32_t *)c;   c += L.keys_sorted;
     p->order_sorted = (uint32_t *)c;  c += L.order_sorted;
     p->cub_tmp = c;                   c += L.cub;
@@ -175,8 +176,11 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
     p->fft_work = c;                  c += L.fft;
     p->fft_work_bytes = L.fft;
     p->sin2 = (float *)c;             c += L.sin2;
-    p->pos_stage = (float *)c;        c += L.pos_stage;
-    p->vel_stage = (float *)c;        c += L.vel_stage;
+    for (int k = 0; k < 2; ++k) {
+        p->rpos[k] = (float *)c;      c += L.rpos;
+        p->rvel[k] = (float *)c;      c += L.rvel;
+        p->rid[k] = (uint32_t *)c;    c += L.rid;
+    }
 
     if (cufftSetWorkArea(p->r2c, p->fft_work) != CUFFT_SUCCESS ||
         cufftSetWorkArea(p->c2r, p->fft_work) != CUFFT_SUCCESS) {
@@ -184,6 +188,8 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
         return PM_ERR_CUFFT;
     }
     rc = pm_k_sin2_table(p);
+    if (rc == PM_OK) rc = pm_k_iota(p->iota, np_capacity, 0);
+    if (rc == PM_OK) rc = (int)cudaStreamSynchronize(0);
     if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);
     if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking);
     if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking);
@@ -245,7 +251,7 @@ int pm_fourier_grid(pm_plan *p, float *fgrid_d, pm_stream_t stream)
 
 int pm_cell_keys(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_d, pm_stream_t stream)
 {
-    PM_ARGS(p && pos_d && keys_d && np >= 0 && np <= p->np_cap);
+    PM_ARGS(p && (np == 0 || (pos_d && keys_d)) && np >= 0 && np <= p->np_cap);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
     return pm_k_cell_keys(p, pos_d, np, keys_d, nullptr, pm_cu(stream));
@@ -254,12 +260,14 @@ int pm_cell_keys(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_d, p
 int pm_sort_by_cell(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_sorted_d,
                     uint32_t *order_d, pm_stream_t stream)
 {
-    PM_ARGS(p && pos_d && np >= 0 && np <= p->np_cap);
+    PM_ARGS(p && (np == 0 || pos_d) && np >= 0 && np <= p->np_cap);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
     cudaStream_t st = pm_cu(stream);
-    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, p->order, st));
+    p->rkeys_valid = false;
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, st));
+    if (np == 0) return PM_OK;
     if (keys_sorted_d)
         PM_CUDA(cudaMemcpyAsync(keys_sorted_d, p->keys_sorted, (size_t)np * 4,
                                 cudaMemcpyDeviceToDevice, st));
@@ -271,11 +279,12 @@ int pm_sort_by_cell(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_s
 int pm_deposit_cic(pm_plan *p, const float *pos_d, int64_t np, double mass, float *rho_d,
                    pm_stream_t stream)
 {
-    PM_ARGS(p && pos_d && rho_d && np >= 0 && np <= p->np_cap);
+    PM_ARGS(p && (np == 0 || pos_d) && rho_d && np >= 0 && np <= p->np_cap);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
     cudaStream_t st = pm_cu(stream);
-    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, p->order, st));
+    p->rkeys_valid = false;
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, st));
     PM_TRY(pm_k_row_offsets(p, np, st));
     return pm_k_deposit(p, pos_d, np, mass, rho_d, st);
@@ -293,7 +302,7 @@ int pm_poisson(pm_plan *p, const float *rho_d, double a, double omega_m0, float 
 int pm_gather_kick_drift(pm_plan *p, float *pos_d, float *vel_d, int64_t np, const float *phi_d,
                          double a_val, double f_a1, double da, float *acc_d, pm_stream_t stream)
 {
-    PM_ARGS(p && pos_d && vel_d && phi_d && np >= 0);
+    PM_ARGS(p && (np == 0 || (pos_d && vel_d)) && phi_d && np >= 0);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
     return pm_k_gather_kick_drift(p, pos_d, vel_d, np, phi_d, a_val, f_a1, da, acc_d, pm_cu(stream));
@@ -302,13 +311,14 @@ int pm_gather_kick_drift(pm_plan *p, float *pos_d, float *vel_d, int64_t np, con
 int pm_step(pm_plan *p, float *pos_d, float *vel_d, int64_t np, double mass, double a, double da,
             double f_a1, double omega_m0, float *rho_d, pm_stream_t stream)
 {
-    PM_ARGS(p && pos_d && vel_d && np >= 0 && np <= p->np_cap && a != 0.0);
+    PM_ARGS(p && (np == 0 || (pos_d && vel_d)) && np >= 0 && np <= p->np_cap && a != 0.0);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
     cudaStream_t st = pm_cu(stream);
     float *rho = rho_d ? rho_d : p->mesh;
+    p->rkeys_valid = false;
     pm_prof_mark(p, 0, st);
-    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, p->order, st));
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, nullptr, st));
     pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
     PM_TRY(pm_k_sort(p, np, st));
     pm_prof_mark(p, PM_STAGE_SORT + 1, st);
@@ -359,39 +369,125 @@ int pm_plan_profile_read(pm_plan *p, float *ms, int *n_steps)
     return PM_OK;
 }
 
+// ---- resident particle state -------------------------------------------------------------------
+static int resident_step(pm_plan *p, double mass, double a, double da, double f_a1,
+                         double omega_m0, float *rho_d, cudaStream_t st)
+{
+    const int64_t np = p->rnp;
+    float *rho = rho_d ? rho_d : p->mesh;
+    pm_prof_mark(p, 0, st);
+    if (!p->rkeys_valid) PM_TRY(pm_k_cell_keys(p, p->rpos[p->rcur], np, p->keys, nullptr, st));
+    pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
+    PM_TRY(pm_k_sort(p, np, st));
+    pm_prof_mark(p, PM_STAGE_SORT + 1, st);
+    PM_TRY(pm_k_row_offsets(p, np, st));
+    pm_prof_mark(p, PM_STAGE_ROWS + 1, st);
+    PM_TRY(pm_k_deposit(p, p->rpos[p->rcur], np, mass, rho, st));
+    pm_prof_mark(p, PM_STAGE_DEPOSIT + 1, st);
+    PM_TRY(pm_k_poisson(p, rho, a, omega_m0, p->mesh2, st));
+    PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));
+    pm_prof_mark(p, PM_STAGE_GATHER + 1, st);
+    if (p->prof_ev && p->prof_n < p->prof_cap) ++p->prof_n;
+    p->rcur ^= 1;
+    p->rkeys_valid = (np > 0);
+    return PM_OK;
+}
+
+int pm_particles_load(pm_plan *p, const float *pos_d, const float *vel_d, int64_t np,
+                      pm_stream_t stream)
+{
+    PM_ARGS(p && (np == 0 || (pos_d && vel_d)) && np >= 0 && np <= p->np_cap);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    cudaStream_t st = pm_cu(stream);
+    const size_t b = (size_t)np * 3 * sizeof(float);
+    p->rcur = 0;
+    p->rnp = np;
+    p->rkeys_valid = false;
+    if (np == 0) return PM_OK;
+    PM_CUDA(cudaMemcpyAsync(p->rpos[0], pos_d, b, cudaMemcpyDeviceToDevice, st));
+    PM_CUDA(cudaMemcpyAsync(p->rvel[0], vel_d, b, cudaMemcpyDeviceToDevice, st));
+    PM_CUDA(cudaMemcpyAsync(p->rid[0], p->iota, (size_t)np * 4, cudaMemcpyDeviceToDevice, st));
+    return PM_OK;
+}
+
+int pm_particles_store(pm_plan *p, float *pos_d, float *vel_d, pm_stream_t stream)
+{
+    PM_ARGS(p && (p->rnp == 0 || (pos_d && vel_d)));
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return pm_k_unpermute(p, pos_d, vel_d, pm_cu(stream));
+}
+
+int64_t pm_particles_count(const pm_plan *p) { return p ? p->rnp : 0; }
+
+int pm_particles_order(pm_plan *p, uint32_t *ids_d, pm_stream_t stream)
+{
+    PM_ARGS(p && (p->rnp == 0 || ids_d));
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    if (p->rnp)
+        PM_CUDA(cudaMemcpyAsync(ids_d, p->rid[p->rcur], (size_t)p->rnp * 4, cudaMemcpyDeviceToDevice,
+                                pm_cu(stream)));
+    return PM_OK;
+}
+
+int pm_step_resident(pm_plan *p, double mass, double a, double da, double f_a1, double omega_m0,
+                     float *rho_d, pm_stream_t stream)
+{
+    PM_ARGS(p && a != 0.0);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, pm_cu(stream));
+}
+
 int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass, double a,
                  double da, double f_a1, double omega_m0, float *rho_h)
 {
-    PM_ARGS(p && pos_h && vel_h && np >= 0 && np <= p->np_cap && a != 0.0);
+    PM_ARGS(p && (np == 0 || (pos_h && vel_h)) && np >= 0 && np <= p->np_cap && a != 0.0);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
     const size_t pbytes = (size_t)np * 3 * sizeof(float);
     const size_t mbytes = (size_t)p->nc * p->nc * p->nc * sizeof(float);
-    // positions feed the deposit at once; velocities are not needed until the gather, so their
-    // upload (s_up) and the density download (s_down) overlap the deposit and the Poisson solve.
-    PM_CUDA(cudaMemcpyAsync(p->pos_stage, pos_h, pbytes, cudaMemcpyHostToDevice, p->s_main));
-    PM_CUDA(cudaMemcpyAsync(p->vel_stage, vel_h, pbytes, cudaMemcpyHostToDevice, p->s_up));
+    // The host owns the state, so every call starts from the caller's particle order: upload
+    // into resident set 0 (identity ids), one resident step, un-permute into set 0, download.
+    // Velocities are not needed before the gather, so their upload (s_up) overlaps the deposit
+    // and the Poisson solve; the density download (s_down) overlaps the Poisson solve.
+    p->rcur = 0;
+    p->rnp = np;
+    p->rkeys_valid = false;
+    if (np) {
+        PM_CUDA(cudaMemcpyAsync(p->rpos[0], pos_h, pbytes, cudaMemcpyHostToDevice, p->s_main));
+        PM_CUDA(cudaMemcpyAsync(p->rvel[0], vel_h, pbytes, cudaMemcpyHostToDevice, p->s_up));
+        PM_CUDA(cudaMemcpyAsync(p->rid[0], p->iota, (size_t)np * 4, cudaMemcpyDeviceToDevice, p->s_main));
+    }
     PM_CUDA(cudaEventRecord(p->ev_a, p->s_up));
-    PM_TRY(pm_k_cell_keys(p, p->pos_stage, np, p->keys, p->order, p->s_main));
-    PM_TRY(pm_k_sort(p, np, p->s_main));
-    PM_TRY(pm_k_row_offsets(p, np, p->s_main));
-    PM_TRY(pm_k_deposit(p, p->pos_stage, np, mass, p->mesh, p->s_main));
+    cudaStream_t st = p->s_main;
+    PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->keys, nullptr, st));
+    PM_TRY(pm_k_sort(p, np, st));
+    PM_TRY(pm_k_row_offsets(p, np, st));
+    PM_TRY(pm_k_deposit(p, p->rpos[0], np, mass, p->mesh, st));
     if (rho_h) {
-        PM_CUDA(cudaEventRecord(p->ev_b, p->s_main));
+        PM_CUDA(cudaEventRecord(p->ev_b, st));
         PM_CUDA(cudaStreamWaitEvent(p->s_down, p->ev_b, 0));
         PM_CUDA(cudaMemcpyAsync(rho_h, p->mesh, mbytes, cudaMemcpyDeviceToHost, p->s_down));
     }
-    PM_TRY(pm_k_poisson(p, p->mesh, a, omega_m0, p->mesh2, p->s_main));
-    PM_CUDA(cudaStreamWaitEvent(p->s_main, p->ev_a, 0));
-    PM_TRY(pm_k_gather_kick_drift(p, p->pos_stage, p->vel_stage, np, p->mesh2, a, f_a1, da, nullptr,
-                                  p->s_main));
-    PM_CUDA(cudaEventRecord(p->ev_c, p->s_main));
-    PM_CUDA(cudaMemcpyAsync(pos_h, p->pos_stage, pbytes, cudaMemcpyDeviceToHost, p->s_main));
-    PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
-    PM_CUDA(cudaMemcpyAsync(vel_h, p->vel_stage, pbytes, cudaMemcpyDeviceToHost, p->s_up));
+    PM_TRY(pm_k_poisson(p, p->mesh, a, omega_m0, p->mesh2, st));
+    PM_CUDA(cudaStreamWaitEvent(st, p->ev_a, 0));
+    PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));
+    p->rcur = 1;
+    PM_TRY(pm_k_unpermute(p, p->rpos[0], p->rvel[0], st));
+    if (np) {
+        PM_CUDA(cudaEventRecord(p->ev_c, st));
+        PM_CUDA(cudaMemcpyAsync(pos_h, p->rpos[0], pbytes, cudaMemcpyDeviceToHost, st));
+        PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
+        PM_CUDA(cudaMemcpyAsync(vel_h, p->rvel[0], pbytes, cudaMemcpyDeviceToHost, p->s_up));
+    }
     PM_CUDA(cudaStreamSynchronize(p->s_main));
     PM_CUDA(cudaStreamSynchronize(p->s_up));
     PM_CUDA(cudaStreamSynchronize(p->s_down));
+    p->rnp = 0;  // the resident buffers were scratch for this call
+    p->rkeys_valid = false;
     return PM_OK;
 }
 

@@ -49,7 +49,7 @@ struct pm_plan {
     size_t ws_bytes;
 
     // deposit scratch
-    uint32_t *keys, *order, *keys_sorted, *order_sorted;
+    uint32_t *keys, *iota, *keys_sorted, *order_sorted;  // iota[i] = i, written once
     void *cub_tmp;
     size_t cub_bytes;
     uint32_t *row_start;  // nc*nc + 1 offsets into the sorted particle list
@@ -64,8 +64,13 @@ struct pm_plan {
     cufftHandle r2c, c2r;
     bool have_fft;
 
-    // device residence for the host-buffer entry point
-    float *pos_stage, *vel_stage;
+    // resident particle state (pm_particles_load / pm_step_resident / pm_particles_store), two
+    // buffer sets; set rcur holds the particles in the cell order of the previous step's sort.
+    float *rpos[2], *rvel[2];
+    uint32_t *rid[2];     // original index of the particle in each slot
+    int rcur;
+    int64_t rnp;
+    bool rkeys_valid;     // p->keys already holds the keys of set rcur (written by the last gather)
     cudaStream_t s_main, s_up, s_down;
     cudaEvent_t ev_a, ev_b, ev_c;
 
@@ -93,6 +98,10 @@ int pm_k_deposit(pm_plan *p, const float *pos, int64_t np, double mass, float *r
                  cudaStream_t st);
 int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const float *phi,
                            double a_val, double f_a1, double da, float *acc, cudaStream_t st);
+int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
+                                    double da, cudaStream_t st);
+int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
+int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st);
 
 // pm_poisson.cu
 int pm_k_sin2_table(pm_plan *p);

@@ -98,7 +98,7 @@ int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st)
     if (np == 0) return PM_OK;
     size_t bytes = p->cub_bytes;
     PM_CUDA(cub::DeviceRadixSort::SortPairs(p->cub_tmp, bytes, (const uint32_t *)p->keys,
-                                            p->keys_sorted, (const uint32_t *)p->order,
+                                            p->keys_sorted, (const uint32_t *)p->iota,
                                             p->order_sorted, np, 0, p->key_bits, st));
     return PM_OK;
 }
@@ -282,16 +282,24 @@ __device__ __forceinline__ void pm_push(float &x, float &vel, float s, double k_
     x = (float)pm_pymod(__dadd_rn((double)x, step), (double)nc);
 }
 
-__global__ void __launch_bounds__(256) k_gather_kick_drift(float *__restrict__ pos,
-                                                           float *__restrict__ vel, int64_t np,
-                                                           const float *__restrict__ phi, int nc,
-                                                           double k_kick, double da, double aa,
-                                                           double f_a1, float *__restrict__ acc)
+// PERM = false: stateless call, particle i updated in place (pos_in == pos_out).
+// PERM = true : resident state.  Slot s of the NEW cell order takes particle j = perm[s] of the
+//               current buffers (a near-coalesced gather: the current order is last step's cell
+//               order), and writes position, velocity, id and the cell key of the NEW position to
+//               slot s of the other buffer set -- the permutation costs no pass of its own.
+template <bool PERM>
+__global__ void __launch_bounds__(256) k_gather_kick_drift(
+    const float *pos_in, const float *vel_in,   // may alias pos_out/vel_out when !PERM
+    const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ perm,
+    float *pos_out, float *vel_out, uint32_t *__restrict__ id_out,
+    uint32_t *__restrict__ keys_out, int64_t np, const float *__restrict__ phi, int nc,
+    double k_kick, double da, double aa, double f_a1, float *__restrict__ acc)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
-    float x = pos[i], y = pos[np + i], z = pos[2 * np + i];
-    float vx = vel[i], vy = vel[np + i], vz = vel[2 * np + i];
+    const int64_t j = PERM ? (int64_t)perm[i] : i;
+    float x = pos_in[j], y = pos_in[np + j], z = pos_in[2 * np + j];
+    float vx = vel_in[j], vy = vel_in[np + j], vz = vel_in[2 * np + j];
 
     const int xc = pm_cell(x, nc), yc = pm_cell(y, nc), zc = pm_cell(z, nc);
     // weights (integrate.py:36-51): float64 products left to right, stored float32
@@ -341,8 +349,12 @@ __global__ void __launch_bounds__(256) k_gather_kick_drift(float *__restrict__ p
     pm_push(y, vy, sy, k_kick, da, aa, f_a1, nc, acc ? acc + np + i : nullptr);
     pm_push(z, vz, sz, k_kick, da, aa, f_a1, nc, acc ? acc + 2 * np + i : nullptr);
 
-    pos[i] = x; pos[np + i] = y; pos[2 * np + i] = z;
-    vel[i] = vx; vel[np + i] = vy; vel[2 * np + i] = vz;
+    pos_out[i] = x; pos_out[np + i] = y; pos_out[2 * np + i] = z;
+    vel_out[i] = vx; vel_out[np + i] = vy; vel_out[2 * np + i] = vz;
+    if (PERM) {
+        id_out[i] = id_in[j];
+        keys_out[i] = ((uint32_t)pm_cell(z, nc) * nc + pm_cell(y, nc)) * nc + pm_cell(x, nc);
+    }
 }
 
 int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const float *phi,
@@ -352,8 +364,68 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
     // host scalars evaluated exactly as integrate.py:94-95 does: da*f_a1, (a_val+da)**2
     const double k_kick = da * f_a1;
     const double aa = (a_val + da) * (a_val + da);
-    PM_LAUNCH(k_gather_kick_drift, (unsigned)((np + 255) / 256), 256, 0, st, pos, vel, np, phi,
-              p->nc, k_kick, da, aa, f_a1, acc);
+    PM_LAUNCH(k_gather_kick_drift<false>, (unsigned)((np + 255) / 256), 256, 0, st, pos, vel,
+              (const uint32_t *)nullptr, (const uint32_t *)nullptr, pos, vel, (uint32_t *)nullptr,
+              (uint32_t *)nullptr, np, phi, p->nc, k_kick, da, aa, f_a1, acc);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// Resident variant: reads buffer set `cur` through the new cell order, writes set `cur^1` and the
+// next step's keys (p->keys).
+int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
+                                    double da, cudaStream_t st)
+{
+    const int64_t np = p->rnp;
+    if (np == 0) return PM_OK;
+    const double k_kick = da * f_a1;
+    const double aa = (a_val + da) * (a_val + da);
+    const int c = p->rcur, o = c ^ 1;
+    PM_LAUNCH(k_gather_kick_drift<true>, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c],
+              p->rvel[c], p->rid[c], p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np,
+              phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// out[id[s]] = in[s] for the six particle rows: back to the caller's original particle order.
+__global__ void __launch_bounds__(256) k_unpermute(const float *__restrict__ pos_in,
+                                                   const float *__restrict__ vel_in,
+                                                   const uint32_t *__restrict__ id, int64_t np,
+                                                   float *__restrict__ pos_out,
+                                                   float *__restrict__ vel_out)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= np) return;
+    const int64_t i = id[s];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        pos_out[d * np + i] = pos_in[d * np + s];
+        vel_out[d * np + i] = vel_in[d * np + s];
+    }
+}
+
+int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st)
+{
+    const int64_t np = p->rnp;
+    if (np == 0) return PM_OK;
+    const int c = p->rcur;
+    PM_LAUNCH(k_unpermute, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c], p->rvel[c],
+              p->rid[c], np, pos_out, vel_out);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+__global__ void __launch_bounds__(256) k_iota(uint32_t *out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
+int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st)
+{
+    if (n == 0) return PM_OK;
+    PM_LAUNCH(k_iota, (unsigned)((n + 255) / 256), 256, 0, st, out, n);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }

@@ -1,9 +1,10 @@
 """The per-timestep loop (reference: src/pmesh.py:56-63) as single C-ABI calls.
 
-`step` is one loop body on device-resident state (pm_step), `step_host` the same for state kept
-in host memory (pm_step_host, uploads/downloads overlapped with compute), `simulator` the
-`while a_current < A_END - da` loop itself with the reference's predicate kept verbatim
-(SURVEY Q10).  Initial conditions, snapshots and plots are outside this package's scope: the
+`step` is one loop body on the caller's CUDA tensors (pm_step, original particle order in and
+out), `ResidentParticles` keeps the state inside the plan in cell order between steps (the fast
+path: pm_step_resident), `step_host` serves state kept in host memory (pm_step_host, copies
+overlapped with compute), and `simulator` is the `while a_current < A_END - da` loop itself with
+the reference's predicate kept verbatim.  Initial conditions, snapshots and plots are outside this package's scope: the
 caller supplies positions/velocities and an optional per-step callback."""
 try:
     from . import _runtime as rt
@@ -60,6 +61,57 @@ def step_host(positions, velocities, a, da, mass=None, rho_out=None, device=None
     return positions, velocities
 
 
+class ResidentParticles:
+    """Particle state kept in HBM in cell order across steps (pm_particles_load /
+    pm_step_resident / pm_particles_store).  The caller's arrays are only read at construction and
+    only written by store(), always in ORIGINAL particle order, so results are comparable
+    particle for particle with the reference, which never permutes (src/save_data.py:19-24).
+    One resident state per (N_CELLS, device) at a time: it lives inside the cached plan."""
+
+    def __init__(self, positions, velocities):
+        cfg = rt.config()
+        self.n_cells = int(cfg.N_CELLS)
+        rt.check_dev_f32(positions, name="positions")
+        rt.check_dev_f32(velocities, tuple(positions.shape), "velocities")
+        self.device = positions.device.index
+        self.np = positions.shape[1]
+        self.plan = rt.get_plan(self.n_cells, self.np, self.device)
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_particles_load(self.plan.handle, positions.data_ptr(),
+                                                velocities.data_ptr(), self.np,
+                                                rt.stream_ptr(self.device)), "pm_particles_load")
+
+    def step(self, a, da, mass=None, rho_out=None):
+        cfg = rt.config()
+        if mass is None:
+            mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3  # src/pmesh.py:28
+        if rho_out is not None:
+            rt.check_dev_f32(rho_out, (self.n_cells,) * 3, "rho_out")
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_step_resident(
+                self.plan.handle, float(mass), float(a), float(da), float(_fa1(a, da, cfg)),
+                float(cfg.OMEGA_M0), rho_out.data_ptr() if rho_out is not None else None,
+                rt.stream_ptr(self.device)), "pm_step_resident")
+
+    def store(self, positions, velocities):
+        """Write the state into the caller's (3, Np) CUDA tensors in original particle order."""
+        rt.check_dev_f32(positions, (3, self.np), "positions")
+        rt.check_dev_f32(velocities, (3, self.np), "velocities")
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_particles_store(self.plan.handle, positions.data_ptr(),
+                                                 velocities.data_ptr(), rt.stream_ptr(self.device)),
+                     "pm_particles_store")
+        return positions, velocities
+
+    def order(self):
+        """Original index of the particle in each storage slot (int32 CUDA tensor)."""
+        ids = torch.empty(self.np, dtype=torch.int32, device=f"cuda:{self.device}")
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_particles_order(self.plan.handle, ids.data_ptr(),
+                                                 rt.stream_ptr(self.device)), "pm_particles_order")
+        return ids
+
+
 def loop_scale_factors(cfg=None):
     """The (a_current, da) pairs the loop of src/pmesh.py:30,56,63 visits, predicate verbatim."""
     cfg = cfg or rt.config()
@@ -79,10 +131,12 @@ def simulator(positions, velocities, on_step=None, max_steps=None):
     cfg = rt.config()
     n = int(cfg.N_CELLS)
     rho = torch.empty((n, n, n), dtype=torch.float32, device=positions.device) if on_step else None
+    state = ResidentParticles(positions, velocities)
     for i, (a_current, da) in enumerate(loop_scale_factors(cfg)):
         if max_steps is not None and i >= max_steps:
             break
-        step(positions, velocities, a_current, da, rho_out=rho)
+        state.step(a_current, da, rho_out=rho)
         if on_step:
+            state.store(positions, velocities)
             on_step(i, a_current + da, rho, positions, velocities)
-    return positions, velocities
+    return state.store(positions, velocities)

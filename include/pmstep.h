@@ -131,6 +131,25 @@ PM_API int pm_step(pm_plan *plan, float *pos_d, float *vel_d, int64_t np, double
             double da, double f_a1, double omega_m0, float *rho_d, pm_stream_t stream);
 
 /*
+ * Resident particle state -- the fast way to run many steps.  The reference never permutes its
+ * particle arrays (snapshots are in original order, src/save_data.py:19-24), but a step is far
+ * cheaper when particles sit in HBM in cell order: the deposit and the force gather then stream.
+ * pm_particles_load copies the caller's arrays (original order) into the plan; pm_step_resident
+ * advances that state by one loop body (src/pmesh.py:60-61), keeping it sorted by the cell of the
+ * previous positions and carrying each particle's original index; pm_particles_store scatters the
+ * state back to the caller's arrays in ORIGINAL particle order.  load -> n x step -> store gives
+ * the same particles as n x pm_step.  pm_particles_order returns the original index of the
+ * particle in each storage slot (the sort order the parity tests check).
+ */
+PM_API int pm_particles_load(pm_plan *plan, const float *pos_d, const float *vel_d, int64_t np,
+                             pm_stream_t stream);
+PM_API int pm_step_resident(pm_plan *plan, double mass, double a, double da, double f_a1,
+                            double omega_m0, float *rho_d, pm_stream_t stream);
+PM_API int pm_particles_store(pm_plan *plan, float *pos_d, float *vel_d, pm_stream_t stream);
+PM_API int pm_particles_order(pm_plan *plan, uint32_t *ids_d, pm_stream_t stream);
+PM_API int64_t pm_particles_count(const pm_plan *plan);
+
+/*
  * The same loop body for a caller that keeps its state in host memory like the reference does
  * (NumPy arrays): uploads pos_h/vel_h, runs pm_step, downloads the updated pos_h/vel_h (and
  * rho_h when not NULL).  Pinned host buffers make the copies asynchronous and overlapped;

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import oracle as O
 
-CASES = ["g16_free10", "g32_step2", "g12_nonpow2", "clustered32"]
+CASES = ["g16_free10", "g32_step2", "g12_nonpow2", "clustered32", "free16", "free32"]
 
 
 def _load(golden_dir, name):
@@ -32,8 +32,9 @@ def test_oracle_reproduces_reference_bit_exact(golden_dir, name):
             assert np.array_equal(O.potential(rho, fg, a, cfg), g[f"phi_{s}"]), f"potential step {s}"
         p2, v2 = O.advance_time(rho, pos, vel, fg, a, da, cfg)
         assert p2 is pos and v2 is vel  # in place + returned, like integrate.py:25
-        assert np.array_equal(pos, g[f"pos_{s + 1}"]), f"positions step {s}"
-        assert np.array_equal(vel, g[f"vel_{s + 1}"]), f"velocities step {s}"
+        if f"pos_{s + 1}" in g:
+            assert np.array_equal(pos, g[f"pos_{s + 1}"]), f"positions step {s}"
+            assert np.array_equal(vel, g[f"vel_{s + 1}"]), f"velocities step {s}"
 
 
 @pytest.mark.parametrize("name", CASES)
