@@ -57,6 +57,8 @@ def lib():
             "pm_plan_destroy": (i32, [vp]),
             "pm_plan_n_cells": (i32, [vp]),
             "pm_plan_np_capacity": (i64, [vp]),
+            "pm_plan_set_fft_backend": (i32, [vp, i32]),
+            "pm_plan_fft_backend": (i32, [vp]),
             "pm_fourier_grid": (i32, [vp, vp, vp]),
             "pm_cell_keys": (i32, [vp, vp, i64, vp, vp]),
             "pm_sort_by_cell": (i32, [vp, vp, i64, vp, vp, vp]),
@@ -86,7 +88,7 @@ EXPORTED_SYMBOLS = (
     "pm_plan_np_capacity", "pm_fourier_grid", "pm_cell_keys", "pm_sort_by_cell", "pm_deposit_cic",
     "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_plan_profile_begin",
     "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_particles_store",
-    "pm_particles_order", "pm_particles_count",
+    "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

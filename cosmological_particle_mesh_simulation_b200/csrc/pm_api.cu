@@ -23,7 +23,7 @@ int key_bits_for(int nc)
 
 // Sizes of every workspace segment, in the order they are carved.
 struct Layout {
-    size_t keys, iota, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2,
+    size_t keys, iota, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2, tw,
         rpos, rvel, rid, total;
 };
 
@@ -62,11 +62,12 @@ int compute_layout(int nc, int64_t np, size_t fft_work, Layout *L)
     L->spec = align_up((size_t)nc * nc * (nc / 2 + 1) * sizeof(float2));
     L->fft = align_up(fft_work);
     L->sin2 = align_up((size_t)nc * 4);
+    L->tw = align_up((size_t)nc * 8);
     L->rpos = align_up(3 * npad * 4);
     L->rvel = align_up(3 * npad * 4);
     L->rid = align_up(npad * 4);
     L->total = L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
-               L->mesh + L->mesh2 + L->spec + L->fft + L->sin2 + 2 * (L->rpos + L->rvel + L->rid);
+               L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw + 2 * (L->rpos + L->rvel + L->rid);
     return PM_OK;
 }
 
@@ -176,6 +177,8 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
     p->fft_work = c;                  c += L.fft;
     p->fft_work_bytes = L.fft;
     p->sin2 = (float *)c;             c += L.sin2;
+    p->sin2rev = (float *)c;          c += L.sin2;
+    p->tw = (float2 *)c;              c += L.tw;
     for (int k = 0; k < 2; ++k) {
         p->rpos[k] = (float *)c;      c += L.rpos;
         p->rvel[k] = (float *)c;      c += L.rvel;
@@ -188,6 +191,11 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
         return PM_ERR_CUFFT;
     }
     rc = pm_k_sin2_table(p);
+    {
+        const char *be = getenv("PM_FFT_BACKEND");  // "cufft" forces the library path (A/B checks)
+        p->own_fft = pm_fft_supported(n_cells) && !(be && strcmp(be, "cufft") == 0);
+    }
+    if (rc == PM_OK && pm_fft_supported(n_cells)) rc = pm_k_fft_tables(p);
     if (rc == PM_OK) rc = pm_k_iota(p->iota, np_capacity, 0);
     if (rc == PM_OK) rc = (int)cudaStreamSynchronize(0);
     if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);
@@ -229,6 +237,16 @@ int pm_plan_destroy(pm_plan *p)
 }
 
 int pm_plan_n_cells(const pm_plan *p) { return p ? p->nc : 0; }
+
+int pm_plan_set_fft_backend(pm_plan *p, int backend)
+{
+    if (!p || backend < 0 || backend > 1) return PM_ERR_INVALID;
+    if (backend == 0 && !pm_fft_supported(p->nc)) return PM_ERR_UNSUPPORTED;
+    p->own_fft = (backend == 0);
+    return PM_OK;
+}
+
+int pm_plan_fft_backend(const pm_plan *p) { return p ? (p->own_fft ? 0 : 1) : PM_ERR_INVALID; }
 int64_t pm_plan_np_capacity(const pm_plan *p) { return p ? p->np_cap : 0; }
 
 #define PM_ARGS(cond)                     \

@@ -1,0 +1,519 @@
+// pm_fft.cu -- hand-written 3-D real FFT Poisson solve for power-of-two meshes, sm_100a.
+//
+// Replaces, for N_CELLS in {32 ... 2048}, the cuFFT R2C -> Green -> cuFFT C2R sequence of
+// pm_poisson.cu (which stays as the general-size path).  Reference semantics are unchanged:
+// phi = IFFT(-3*Omega_m/(8a) * G(k) * FFT(rho)) (src/potential.py:7-29, src/fourier_utils.py:5-16).
+//
+// Five passes, each reading and writing the 4*Nc^3-byte array exactly once (40*Nc^3 bytes per
+// solve; cuFFT + a separate Green pass moves 56*Nc^3):
+//   1. rows  R2C : N reals -> N/2 complex per x-row ("packed": slot 0 holds (DC, Nyquist))
+//   2. cols  y   : forward complex FFT along y, 16 adjacent kx columns per CTA
+//   3. cols  z   : forward FFT along z, multiply by the Green's function, inverse FFT along z,
+//                  all inside one CTA -- the spectrum never returns to HBM in between
+//   4. cols  y   : inverse
+//   5. rows  C2R : N/2 complex -> N reals
+// The Nyquist-in-x plane (kx = N/2) lives in a small side array [z][y]; it is split off the
+// packed slot in pass 2 and merged back in pass 4.
+//
+// Every 1-D transform is an in-place decimation-in-frequency FFT (radix 8/8/8 for 512) whose
+// output is left in digit-reversed order; the inverse is the matching decimation-in-time FFT
+// that consumes digit-reversed input.  Nothing is ever un-permuted: the Green's kernel looks
+// sin^2 up in a table stored in the same digit-reversed order (p->sin2rev).  In-place
+// butterflies own disjoint element sets, so one __syncthreads per radix stage suffices and a
+// single shared-memory tile [N][17] float2 serves the whole pass; the first and last stage of
+// a pass exchange data with global memory directly from registers.
+#include <math.h>
+
+#include <type_traits>
+
+#include "pm_internal.cuh"
+
+namespace {
+
+constexpr int kCols = 16;          // adjacent columns (contiguous in memory) per column tile
+constexpr int kPitch = kCols + 1;  // +1: the split-off Nyquist column of the packed slot; also
+                                   // keeps transposing row accesses conflict-free
+constexpr int kThreads = 256;
+
+// ---- compile-time radix plan: as many 8s as divide n, then one 4 or 2 -------------------------
+__host__ __device__ constexpr int fft_radix(int n, int stage)
+{
+    for (int t = 0;; ++t) {
+        const int r = (n % 8 == 0) ? 8 : n;
+        if (t == stage) return r;
+        n /= r;
+    }
+}
+__host__ __device__ constexpr int fft_stages(int n)
+{
+    int s = 0;
+    while (n > 1) {
+        n /= (n % 8 == 0) ? 8 : n;
+        ++s;
+    }
+    return s;
+}
+__host__ __device__ constexpr int fft_len(int n, int stage)  // sub-transform length entering `stage`
+{
+    for (int t = 0; t < stage; ++t) n /= fft_radix(n, 0);
+    return n;
+}
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+
+// position of natural index k after the DIF passes (mixed-radix digit reversal)
+template <int N>
+__host__ __device__ inline int digit_rev(int k)
+{
+    int pos = 0, len = N, n = N;
+#pragma unroll
+    for (int s = 0; s < fft_stages(N); ++s) {
+        const int r = (n % 8 == 0) ? 8 : n;
+        len /= r;
+        pos += (k % r) * len;
+        k /= r;
+        n /= r;
+    }
+    return pos;
+}
+
+// ---- complex helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b)
+{
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b)  // a * conj(b)
+{
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// S = -1: forward kernel exp(-2 pi i jk/R);  S = +1: inverse.  Natural order in and out.
+template <int S>
+__device__ __forceinline__ void dft2(float2 &a, float2 &b)
+{
+    const float2 t = a;
+    a = cadd(t, b);
+    b = csub(t, b);
+}
+template <int S>
+__device__ __forceinline__ void dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3)
+{
+    const float2 s = cadd(v0, v2), d = csub(v0, v2), t = cadd(v1, v3), u = csub(v1, v3);
+    v0 = cadd(s, t);
+    v2 = csub(s, t);
+    v1 = make_float2(d.x - S * u.y, d.y + S * u.x);  // d + S*i*u
+    v3 = make_float2(d.x + S * u.y, d.y - S * u.x);  // d - S*i*u
+}
+template <int S>
+__device__ __forceinline__ void dft8(float2 (&v)[8])
+{
+    dft4<S>(v[0], v[2], v[4], v[6]);
+    dft4<S>(v[1], v[3], v[5], v[7]);
+    const float c = 0.70710678118654752440f;
+    const float2 o0 = v[1];
+    const float2 o1 = make_float2(c * (v[3].x - S * v[3].y), c * (S * v[3].x + v[3].y));
+    const float2 o2 = make_float2(-S * v[5].y, S * v[5].x);
+    const float2 o3 = make_float2(c * (-v[7].x - S * v[7].y), c * (S * v[7].x - v[7].y));
+    const float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+template <int R, int S>
+__device__ __forceinline__ void dft(float2 (&v)[R])
+{
+    if constexpr (R == 8) dft8<S>(v);
+    else if constexpr (R == 4) dft4<S>(v[0], v[1], v[2], v[3]);
+    else dft2<S>(v[0], v[1]);
+}
+
+// One butterfly of stage ST of an N-point transform on the element set
+//   pos(r) = b*L + i + r*(L/R),   u = b*(L/R) + i  in [0, N/R)
+// FWD: DIF  (DFT_R, then twiddle exp(-2 pi i * i*q / L));  !FWD: the exact inverse (DIT).
+// `tw` is the table exp(-2 pi i m / TWN), TWN a multiple of N (rows use the N-point table for
+// their N/2-point transforms).  ld(pos) / st(pos, value) do the addressing.
+template <int N, int ST, bool FWD, int TWN, class Ld, class St, class Mid>
+__device__ __forceinline__ void butterfly(int u, const float2 *__restrict__ tw, Ld ld, St st, Mid mid)
+{
+    constexpr int R = fft_radix(N, ST);
+    constexpr int L = fft_len(N, ST);
+    constexpr int SUB = L / R;
+    const int b = u / SUB, i = u % SUB;  // SUB is a power of two
+    const int pos0 = b * L + i;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = ld(pos0 + r * SUB);
+    if constexpr (FWD) {
+        dft<R, -1>(v);
+        if constexpr (SUB > 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + i * q * (TWN / L)));
+        }
+    } else {
+        if constexpr (SUB > 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + i * q * (TWN / L)));
+        }
+        dft<R, +1>(v);
+    }
+    mid(v, pos0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) st(pos0 + r * SUB, v[r]);
+}
+
+struct NoMid {
+    template <class V>
+    __device__ __forceinline__ void operator()(V &, int) const {}
+};
+
+// G(k) of src/fourier_utils.py:15-16 in float32, summed as (s_axis0 + s_axis1) + s_axis2, 0 at DC
+__device__ __forceinline__ float green_f32(float sz, float sy, float sx)
+{
+    const float ksq = (sz + sy) + sx;
+    return ksq != 0.0f ? 1.0f / ksq : 0.0f;
+}
+
+enum ColMode { COL_FWD = 0, COL_INV = 1, COL_FUSED = 2 };
+
+struct ColArgs {
+    float2 *main;      // [N][N][N/2] spectrum, digit-reversed along transformed axes
+    float2 *side;      // [N][N] Nyquist-in-x plane
+    const float2 *tw;  // exp(-2 pi i m / N)
+    const float *sin2, *sin2rev;
+    float scale;       // -3*Omega_m/(8a)/N^3
+    int axis;          // 1: along y (tiles = z x kx-tile), 0: along z (tiles = y x kx-tile, + side)
+};
+
+// Column FFT pass.  A tile is N points (stride `gs` float2 apart) x 16 adjacent columns.
+template <int N, int MODE>
+__global__ void __launch_bounds__(kThreads) k_fft_cols(ColArgs a)
+{
+    extern __shared__ float2 s_tile[];  // [N][kPitch]
+    constexpr int H = N / 2;
+    constexpr int TPR = H / kCols;      // column tiles per row of the main array
+    constexpr int S = fft_stages(N);
+    const int tid = threadIdx.x;
+
+    // ---- which tile ----
+    const int t = blockIdx.x;
+    float2 *g;            // first element of the tile
+    size_t gs;            // stride between successive points
+    bool extra = false;   // y pass, kx-tile 0: also carries the split-off Nyquist column
+    float2 *gx = nullptr; // its global home (side array), stride N... see below
+    size_t gxs = 0;
+    float sy_fixed = 0.f; // Green's: sin^2 term that is constant over the tile
+    int col0 = 0;         // first column index (kx for main tiles, y position for side tiles)
+    bool side_tile = false;
+    if (a.axis == 1) {
+        const int z = t / TPR, kt = t % TPR;
+        g = a.main + (size_t)z * N * H + kt * kCols;
+        gs = H;
+        if (kt == 0) {
+            extra = true;
+            gx = a.side + (size_t)z * N;
+            gxs = 1;
+        }
+    } else {
+        if (t < N * TPR) {
+            const int y = t / TPR, kt = t % TPR;
+            g = a.main + (size_t)y * H + kt * kCols;
+            gs = (size_t)N * H;
+            col0 = kt * kCols;
+            if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2rev + y);
+        } else {
+            side_tile = true;
+            const int yt = t - N * TPR;
+            g = a.side + yt * kCols;
+            gs = N;
+            col0 = yt * kCols;
+        }
+    }
+
+    auto sm = [&](int pos, int c) -> float2 & { return s_tile[pos * kPitch + c]; };
+
+    // ---- generic stage runner over the 16 main columns (+ the extra one) ----
+    // src/dst: 0 = shared tile, 1 = global.  For the extra column in the y pass the global home
+    // is the side array; its forward input is the imaginary part of packed column 0.
+    auto run_stage = [&](auto st_tag, auto fwd_tag, auto src_tag, auto dst_tag, auto mid_main) {
+        constexpr int ST = decltype(st_tag)::value;
+        constexpr bool FWD = decltype(fwd_tag)::value;
+        constexpr int src = decltype(src_tag)::value, dst = decltype(dst_tag)::value;
+        constexpr int NB = N / fft_radix(N, ST);
+        for (int w = tid; w < NB * kCols; w += kThreads) {
+            const int c = w % kCols, u = w / kCols;
+            auto ld = [&](int pos) -> float2 {
+                if (src == 0) return sm(pos, c);
+                float2 v = g[pos * gs + c];
+                if (extra && c == 0 && FWD) v.y = 0.0f;  // packed slot: real part is the DC column
+                return v;
+            };
+            auto st = [&](int pos, float2 v) {
+                if (dst == 0 || (extra && c == 0 && !FWD)) sm(pos, c) = v;  // inverse: merged later
+                else g[pos * gs + c] = v;
+            };
+            butterfly<N, ST, FWD, N>(u, a.tw, ld, st, [&](auto &v, int pos0) { mid_main(v, pos0, c); });
+        }
+        if (extra) {
+            for (int u = tid; u < NB; u += kThreads) {
+                auto ld = [&](int pos) -> float2 {
+                    if (src == 0) return sm(pos, kCols);
+                    if (FWD) return make_float2(g[pos * gs].y, 0.0f);  // Nyquist column of the packed slot
+                    return gx[pos * gxs];
+                };
+                auto st = [&](int pos, float2 v) {
+                    if (dst == 0 || !FWD) sm(pos, kCols) = v;
+                    else gx[pos * gxs] = v;
+                };
+                butterfly<N, ST, FWD, N>(u, a.tw, ld, st, NoMid());
+            }
+        }
+    };
+    auto nomid = [](auto &, int, int) {};
+    auto tag = [](auto v) { return v; };
+    (void)tag;
+
+#define PM_ST(k) std::integral_constant<int, (k)>()
+#define PM_T std::true_type()
+#define PM_F std::false_type()
+
+    if constexpr (MODE == COL_FWD) {
+        // stage 0 from global, stages 1..S-2 in shared memory, stage S-1 to global
+        run_stage(PM_ST(0), PM_T, PM_ST(1), PM_ST(0), nomid);
+        __syncthreads();
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        run_stage(PM_ST(S - 1), PM_T, PM_ST(0), PM_ST(1), nomid);
+    } else if constexpr (MODE == COL_INV) {
+        run_stage(PM_ST(S - 1), PM_F, PM_ST(1), PM_ST(0), nomid);
+        __syncthreads();
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        run_stage(PM_ST(0), PM_F, PM_ST(0), PM_ST(1), nomid);
+        if (extra) {
+            // merge: packed slot = (Re DC column, Re Nyquist column); both are real up to rounding
+            __syncthreads();
+            for (int pos = tid; pos < N; pos += kThreads)
+                g[pos * gs] = make_float2(sm(pos, 0).x, sm(pos, kCols).x);
+        }
+    } else {
+        // forward along z, Green's function, inverse along z -- one trip through HBM
+        run_stage(PM_ST(0), PM_T, PM_ST(1), PM_ST(0), nomid);
+        __syncthreads();
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        {
+            // last forward stage, multiply, first inverse stage: same R consecutive points
+            constexpr int ST = S - 1;
+            constexpr int R = fft_radix(N, ST);
+            constexpr int NB = N / R;
+            for (int w = tid; w < NB * kCols; w += kThreads) {
+                const int c = w % kCols, u = w / kCols;
+                const int pos0 = u * R;
+                float2 v[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) v[r] = sm(pos0 + r, c);
+                dft<R, -1>(v);
+                const float sy = side_tile ? __ldg(a.sin2rev + col0 + c) : sy_fixed;
+                const float sx = side_tile ? __ldg(a.sin2 + H) : __ldg(a.sin2 + col0 + c);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float gk = a.scale * green_f32(__ldg(a.sin2rev + pos0 + r), sy, sx);
+                    v[r].x *= gk;
+                    v[r].y *= gk;
+                }
+                dft<R, +1>(v);
+#pragma unroll
+                for (int r = 0; r < R; ++r) sm(pos0 + r, c) = v[r];
+            }
+        }
+        __syncthreads();
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        run_stage(PM_ST(0), PM_F, PM_ST(0), PM_ST(1), nomid);
+    }
+}
+
+// Row pass: 16 x-rows per CTA, each an (N/2)-point complex FFT of z_j = x_2j + i x_2j+1 plus the
+// real-transform split (forward) or merge (inverse).  Global accesses run along the row
+// (coalesced), the butterflies run across the 16 rows (conflict-free): the tile is [N/2][17].
+template <int N, bool FWD>
+__global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict__ in,
+                                                       float2 *__restrict__ out,
+                                                       const float2 *__restrict__ tw)
+{
+    extern __shared__ float2 s_tile[];
+    constexpr int H = N / 2;
+    constexpr int S = fft_stages(H);
+    const int tid = threadIdx.x;
+    const size_t row0 = (size_t)blockIdx.x * kCols;
+    auto sm = [&](int pos, int c) -> float2 & { return s_tile[pos * kPitch + c]; };
+
+    if constexpr (FWD) {
+        for (int idx = tid; idx < kCols * H; idx += kThreads) {
+            const int b = idx / H, k = idx % H;
+            sm(k, b) = in[(row0 + b) * H + k];
+        }
+    } else {
+        for (int idx = tid; idx < kCols * H; idx += kThreads) {
+            const int b = idx / H, k = idx % H;
+            const float2 A = in[(row0 + b) * H + k];
+            float2 Z;
+            if (k == 0) {
+                Z = make_float2(A.x + A.y, A.x - A.y);  // (DC + Nyq) + i (DC - Nyq)
+            } else {
+                const float2 Bm = in[(row0 + b) * H + (H - k)];
+                const float2 P = make_float2(A.x + Bm.x, A.y - Bm.y);   // A + conj(B)
+                const float2 Q = make_float2(A.x - Bm.x, A.y + Bm.y);   // A - conj(B)
+                const float2 t = cmulc(Q, __ldg(tw + k));               // conj(w^k) * Q
+                Z = make_float2(P.x - t.y, P.y + t.x);                  // P + i t
+            }
+            sm(digit_rev<H>(k), b) = Z;
+        }
+    }
+    __syncthreads();
+
+    auto run_stage = [&](auto st_tag, auto fwd_tag) {
+        constexpr int ST = decltype(st_tag)::value;
+        constexpr bool F = decltype(fwd_tag)::value;
+        constexpr int NB = H / fft_radix(H, ST);
+        for (int w = tid; w < NB * kCols; w += kThreads) {
+            const int c = w % kCols, u = w / kCols;
+            auto ld = [&](int pos) -> float2 { return sm(pos, c); };
+            auto st = [&](int pos, float2 v) { sm(pos, c) = v; };
+            butterfly<H, ST, F, N>(u, tw, ld, st, NoMid());
+        }
+        __syncthreads();
+    };
+    if constexpr (FWD) {
+        run_stage(PM_ST(0), PM_T);
+        if constexpr (S >= 2) run_stage(PM_ST(1), PM_T);
+        if constexpr (S >= 3) run_stage(PM_ST(2), PM_T);
+        if constexpr (S >= 4) run_stage(PM_ST(3), PM_T);
+        for (int idx = tid; idx < kCols * H; idx += kThreads) {
+            const int b = idx / H, k = idx % H;
+            float2 X;
+            if (k == 0) {
+                const float2 Z0 = sm(0, b);
+                X = make_float2(Z0.x + Z0.y, Z0.x - Z0.y);  // packed (DC, Nyquist)
+            } else {
+                const float2 Zk = sm(digit_rev<H>(k), b);
+                const float2 Zm = sm(digit_rev<H>(H - k), b);
+                const float2 A = make_float2(Zk.x + Zm.x, Zk.y - Zm.y);  // Zk + conj(Zm)
+                const float2 B = make_float2(Zk.x - Zm.x, Zk.y + Zm.y);  // Zk - conj(Zm)
+                const float2 t = cmul(__ldg(tw + k), B);
+                X = make_float2(0.5f * (A.x + t.y), 0.5f * (A.y - t.x)); // (A - i t) / 2
+            }
+            out[(row0 + b) * H + k] = X;
+        }
+    } else {
+        if constexpr (S >= 4) run_stage(PM_ST(3), PM_F);
+        if constexpr (S >= 3) run_stage(PM_ST(2), PM_F);
+        if constexpr (S >= 2) run_stage(PM_ST(1), PM_F);
+        run_stage(PM_ST(0), PM_F);
+        for (int idx = tid; idx < kCols * H; idx += kThreads) {
+            const int b = idx / H, k = idx % H;
+            out[(row0 + b) * H + k] = sm(k, b);
+        }
+    }
+}
+
+template <int N>
+int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const size_t smem_cols = (size_t)N * kPitch * sizeof(float2);
+    const size_t smem_rows = (size_t)H * kPitch * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        attr_set = true;
+    }
+    ColArgs ca;
+    ca.main = p->spec;
+    ca.side = p->spec + (size_t)N * N * H;
+    ca.tw = p->tw;
+    ca.sin2 = p->sin2;
+    ca.sin2rev = p->sin2rev;
+    const double m = (double)N * N * N;
+    ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
+    const int row_ctas = N * N / kCols;
+    const int tiles = N * (H / kCols);
+
+    auto rows_fwd = k_fft_rows<N, true>;
+    auto rows_inv = k_fft_rows<N, false>;
+    auto cols_fwd = k_fft_cols<N, COL_FWD>;
+    auto cols_inv = k_fft_cols<N, COL_INV>;
+    auto cols_fused = k_fft_cols<N, COL_FUSED>;
+    PM_LAUNCH(rows_fwd, row_ctas, kThreads, smem_rows, st, reinterpret_cast<const float2 *>(rho),
+              ca.main, (const float2 *)p->tw);
+    ca.axis = 1;
+    PM_LAUNCH(cols_fwd, tiles, kThreads, smem_cols, st, ca);
+    pm_prof_mark(p, PM_STAGE_R2C + 1, st);
+    ca.axis = 0;
+    PM_LAUNCH(cols_fused, tiles + N / kCols, kThreads, smem_cols, st, ca);
+    pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
+    ca.axis = 1;
+    PM_LAUNCH(cols_inv, tiles, kThreads, smem_cols, st, ca);
+    PM_LAUNCH(rows_inv, row_ctas, kThreads, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
+              reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
+    pm_prof_mark(p, PM_STAGE_C2R + 1, st);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+}  // namespace
+
+bool pm_fft_supported(int nc)
+{
+    return nc == 32 || nc == 64 || nc == 128 || nc == 256 || nc == 512 || nc == 1024;
+}
+
+// exp(-2 pi i m / N) in float64 -> float32, and the digit-reversed sin^2 table of the Green's kernel
+int pm_k_fft_tables(pm_plan *p)
+{
+    const int n = p->nc;
+    float2 *tw = (float2 *)malloc(sizeof(float2) * n);
+    float *sr = (float *)malloc(sizeof(float) * n);
+    if (!tw || !sr) return PM_ERR_NOMEM;
+    for (int m = 0; m < n; ++m) {
+        const double ang = -2.0 * M_PI * (double)m / (double)n;
+        tw[m] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    for (int k = 0; k < n; ++k) {
+        int pos = 0;
+        switch (n) {
+            case 32: pos = digit_rev<32>(k); break;
+            case 64: pos = digit_rev<64>(k); break;
+            case 128: pos = digit_rev<128>(k); break;
+            case 256: pos = digit_rev<256>(k); break;
+            case 512: pos = digit_rev<512>(k); break;
+            case 1024: pos = digit_rev<1024>(k); break;
+        }
+        const double s = sin(M_PI * (double)k / (double)n);
+        sr[pos] = (float)(s * s);
+    }
+    cudaError_t e = cudaMemcpy(p->tw, tw, sizeof(float2) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->sin2rev, sr, sizeof(float) * n, cudaMemcpyHostToDevice);
+    free(tw);
+    free(sr);
+    return (int)e;
+}
+
+int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
+{
+    switch (p->nc) {
+        case 32: return poisson_launch<32>(p, rho, a, omega_m0, phi, st);
+        case 64: return poisson_launch<64>(p, rho, a, omega_m0, phi, st);
+        case 128: return poisson_launch<128>(p, rho, a, omega_m0, phi, st);
+        case 256: return poisson_launch<256>(p, rho, a, omega_m0, phi, st);
+        case 512: return poisson_launch<512>(p, rho, a, omega_m0, phi, st);
+        case 1024: return poisson_launch<1024>(p, rho, a, omega_m0, phi, st);
+    }
+    return PM_ERR_UNSUPPORTED;
+}

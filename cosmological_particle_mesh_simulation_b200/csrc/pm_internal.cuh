@@ -61,6 +61,9 @@ struct pm_plan {
     void *fft_work;
     size_t fft_work_bytes;
     float *sin2;          // sin^2(pi i / nc), i < nc
+    float *sin2rev;       // the same in the digit-reversed order of the hand-written FFT
+    float2 *tw;           // exp(-2 pi i m / nc)
+    bool own_fft;         // power-of-two mesh: pm_fft.cu path; otherwise cuFFT
     cufftHandle r2c, c2r;
     bool have_fft;
 
@@ -102,6 +105,12 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
                                     double da, cudaStream_t st);
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
 int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st);
+
+// pm_fft.cu
+bool pm_fft_supported(int nc);
+int pm_k_fft_tables(pm_plan *p);
+int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
+                     cudaStream_t st);
 
 // pm_poisson.cu
 int pm_k_sin2_table(pm_plan *p);

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) k_green_multiply(float2 *__restrict__ spe
 int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                  cudaStream_t st)
 {
+    if (p->own_fft) return pm_k_poisson_own(p, rho, a, omega_m0, phi, st);
     const int nc = p->nc, nxh = nc / 2 + 1;
     PM_CUFFT(cufftSetStream(p->r2c, st));
     PM_CUFFT(cufftSetStream(p->c2r, st));

@@ -70,6 +70,11 @@ PM_API size_t pm_plan_workspace_bytes(int n_cells, int64_t np_capacity);
 PM_API int pm_plan_create(pm_plan **plan, int n_cells, int64_t np_capacity, int device);
 PM_API int pm_plan_destroy(pm_plan *plan);
 PM_API int pm_plan_n_cells(const pm_plan *plan);
+/* Poisson backend: 0 = hand-written sm_100a FFT with the Green's function fused into the z pass
+ * (default for power-of-two meshes 32..1024), 1 = cuFFT R2C/C2R around a separate Green's kernel
+ * (any mesh size; also selectable with the environment variable PM_FFT_BACKEND=cufft). */
+PM_API int pm_plan_set_fft_backend(pm_plan *plan, int backend);
+PM_API int pm_plan_fft_backend(const pm_plan *plan);
 PM_API int64_t pm_plan_np_capacity(const pm_plan *plan);
 
 /*
