@@ -76,6 +76,22 @@ __host__ __device__ inline int digit_rev(int k)
     return pos;
 }
 
+// inverse of digit_rev: natural index of the element sitting at position pos
+template <int N>
+__host__ __device__ inline int digit_unrev(int pos)
+{
+    int k = 0, len = N, n = N, w = 1;
+#pragma unroll
+    for (int s = 0; s < fft_stages(N); ++s) {
+        const int r = (n % 8 == 0) ? 8 : n;
+        len /= r;
+        k += ((pos / len) % r) * w;
+        w *= r;
+        n /= r;
+    }
+    return k;
+}
+
 // ---- complex helpers ----------------------------------------------------------------------------
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -188,7 +204,7 @@ struct ColArgs {
 
 // Column FFT pass.  A tile is N points (stride `gs` float2 apart) x 16 adjacent columns.
 template <int N, int MODE>
-__global__ void __launch_bounds__(kThreads) k_fft_cols(ColArgs a)
+__global__ void __launch_bounds__(kThreads, 2) k_fft_cols(ColArgs a)
 {
     extern __shared__ float2 s_tile[];  // [N][kPitch]
     constexpr int H = N / 2;
@@ -240,20 +256,56 @@ __global__ void __launch_bounds__(kThreads) k_fft_cols(ColArgs a)
         constexpr int ST = decltype(st_tag)::value;
         constexpr bool FWD = decltype(fwd_tag)::value;
         constexpr int src = decltype(src_tag)::value, dst = decltype(dst_tag)::value;
-        constexpr int NB = N / fft_radix(N, ST);
-        for (int w = tid; w < NB * kCols; w += kThreads) {
-            const int c = w % kCols, u = w / kCols;
-            auto ld = [&](int pos) -> float2 {
-                if (src == 0) return sm(pos, c);
-                float2 v = g[pos * gs + c];
-                if (extra && c == 0 && FWD) v.y = 0.0f;  // packed slot: real part is the DC column
-                return v;
-            };
-            auto st = [&](int pos, float2 v) {
+        constexpr int R = fft_radix(N, ST);
+        constexpr int NB = N / R;
+        constexpr int SUB = fft_len(N, ST) / R;
+        constexpr int ITERS = (NB * kCols + kThreads - 1) / kThreads;
+        auto st_main = [&](int c) {
+            return [&, c](int pos, float2 v) {
                 if (dst == 0 || (extra && c == 0 && !FWD)) sm(pos, c) = v;  // inverse: merged later
                 else g[pos * gs + c] = v;
             };
-            butterfly<N, ST, FWD, N>(u, a.tw, ld, st, [&](auto &v, int pos0) { mid_main(v, pos0, c); });
+        };
+        if constexpr (src == 1) {
+            // Issue every global load of this thread before the first butterfly: the whole tile
+            // (N x 16 x 8 B) is in flight per CTA, which is what keeps HBM busy with 2-3 CTAs/SM.
+            float2 buf[ITERS][R];
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const int w = it * kThreads + tid;
+                const int c = w % kCols, u = w / kCols;
+                const int pos0 = (u / SUB) * (SUB * R) + (u % SUB);
+                if (w < NB * kCols) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) buf[it][r] = g[(size_t)(pos0 + r * SUB) * gs + c];
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const int w = it * kThreads + tid;
+                const int c = w % kCols, u = w / kCols;
+                if (w < NB * kCols) {
+                    const int pos0 = (u / SUB) * (SUB * R) + (u % SUB);
+                    auto ld = [&](int pos) -> float2 {
+                        float2 v = buf[it][(pos - pos0) / SUB];
+                        if (extra && c == 0 && FWD) v.y = 0.0f;  // packed slot: real part is the DC column
+                        return v;
+                    };
+                    butterfly<N, ST, FWD, N>(u, a.tw, ld, st_main(c),
+                                             [&](auto &v, int p0) { mid_main(v, p0, c); });
+                }
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) {
+                const int w = it * kThreads + tid;
+                const int c = w % kCols, u = w / kCols;
+                if (w < NB * kCols) {
+                    auto ld = [&](int pos) -> float2 { return sm(pos, c); };
+                    butterfly<N, ST, FWD, N>(u, a.tw, ld, st_main(c),
+                                             [&](auto &v, int p0) { mid_main(v, p0, c); });
+                }
+            }
         }
         if (extra) {
             for (int u = tid; u < NB; u += kThreads) {
@@ -338,6 +390,9 @@ __global__ void __launch_bounds__(kThreads) k_fft_cols(ColArgs a)
 // Row pass: 16 x-rows per CTA, each an (N/2)-point complex FFT of z_j = x_2j + i x_2j+1 plus the
 // real-transform split (forward) or merge (inverse).  Global accesses run along the row
 // (coalesced), the butterflies run across the 16 rows (conflict-free): the tile is [N/2][17].
+// The split/merge pairs k with N/2-k, so it wants natural order: the last forward stage (and the
+// first inverse stage) is done out of place -- read everything, barrier, write to the natural
+// positions -- which keeps every shared-memory access of the kernel free of bank conflicts.
 template <int N, bool FWD>
 __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict__ in,
                                                        float2 *__restrict__ out,
@@ -346,17 +401,96 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
     extern __shared__ float2 s_tile[];
     constexpr int H = N / 2;
     constexpr int S = fft_stages(H);
+    constexpr int RL = fft_radix(H, S - 1);   // radix of the last DIF stage (sub-length 1)
+    constexpr int NBL = H / RL;
+    constexpr int ITL = (NBL * kCols + kThreads - 1) / kThreads;
+    constexpr int LD_IT = kCols * H / kThreads;   // tile elements per thread
     const int tid = threadIdx.x;
     const size_t row0 = (size_t)blockIdx.x * kCols;
     auto sm = [&](int pos, int c) -> float2 & { return s_tile[pos * kPitch + c]; };
 
+    auto run_stage = [&](auto st_tag, auto fwd_tag) {
+        constexpr int ST = decltype(st_tag)::value;
+        constexpr bool F = decltype(fwd_tag)::value;
+        constexpr int NB = H / fft_radix(H, ST);
+        constexpr int ITERS = (NB * kCols + kThreads - 1) / kThreads;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int w = it * kThreads + tid;
+            const int c = w % kCols, u = w / kCols;
+            if (w < NB * kCols) {
+                auto ld = [&](int pos) -> float2 { return sm(pos, c); };
+                auto st = [&](int pos, float2 v) { sm(pos, c) = v; };
+                butterfly<H, ST, F, N>(u, tw, ld, st, NoMid());
+            }
+        }
+        __syncthreads();
+    };
+
     if constexpr (FWD) {
-        for (int idx = tid; idx < kCols * H; idx += kThreads) {
+        {
+            float2 buf[LD_IT];
+#pragma unroll
+            for (int it = 0; it < LD_IT; ++it) {
+                const int idx = it * kThreads + tid;
+                buf[it] = in[(row0 + idx / H) * H + idx % H];
+            }
+#pragma unroll
+            for (int it = 0; it < LD_IT; ++it) {
+                const int idx = it * kThreads + tid;
+                sm(idx % H, idx / H) = buf[it];
+            }
+        }
+        __syncthreads();
+        if constexpr (S >= 2) run_stage(PM_ST(0), PM_T);
+        if constexpr (S >= 3) run_stage(PM_ST(1), PM_T);
+        if constexpr (S >= 4) run_stage(PM_ST(2), PM_T);
+        {
+            float2 v[ITL][RL];
+#pragma unroll
+            for (int it = 0; it < ITL; ++it) {
+                const int w = it * kThreads + tid;
+                const int c = w % kCols, pos0 = (w / kCols) * RL;
+                if (w < NBL * kCols) {
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) v[it][r] = sm(pos0 + r, c);
+                    dft<RL, -1>(v[it]);
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < ITL; ++it) {
+                const int w = it * kThreads + tid;
+                const int c = w % kCols, pos0 = (w / kCols) * RL;
+                if (w < NBL * kCols) {
+                    const int k0 = digit_unrev<H>(pos0);
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) sm(k0 + r * NBL, c) = v[it][r];
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll 4
+        for (int it = 0; it < LD_IT; ++it) {
+            const int idx = it * kThreads + tid;
             const int b = idx / H, k = idx % H;
-            sm(k, b) = in[(row0 + b) * H + k];
+            float2 X;
+            const float2 Zk = sm(k, b);
+            if (k == 0) {
+                X = make_float2(Zk.x + Zk.y, Zk.x - Zk.y);  // packed (DC, Nyquist)
+            } else {
+                const float2 Zm = sm(H - k, b);
+                const float2 A = make_float2(Zk.x + Zm.x, Zk.y - Zm.y);  // Zk + conj(Zm)
+                const float2 B = make_float2(Zk.x - Zm.x, Zk.y + Zm.y);  // Zk - conj(Zm)
+                const float2 t = cmul(__ldg(tw + k), B);
+                X = make_float2(0.5f * (A.x + t.y), 0.5f * (A.y - t.x)); // (A - i t) / 2
+            }
+            out[(row0 + b) * H + k] = X;
         }
     } else {
-        for (int idx = tid; idx < kCols * H; idx += kThreads) {
+#pragma unroll 4
+        for (int it = 0; it < LD_IT; ++it) {
+            const int idx = it * kThreads + tid;
             const int b = idx / H, k = idx % H;
             const float2 A = in[(row0 + b) * H + k];
             float2 Z;
@@ -369,52 +503,41 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
                 const float2 t = cmulc(Q, __ldg(tw + k));               // conj(w^k) * Q
                 Z = make_float2(P.x - t.y, P.y + t.x);                  // P + i t
             }
-            sm(digit_rev<H>(k), b) = Z;
-        }
-    }
-    __syncthreads();
-
-    auto run_stage = [&](auto st_tag, auto fwd_tag) {
-        constexpr int ST = decltype(st_tag)::value;
-        constexpr bool F = decltype(fwd_tag)::value;
-        constexpr int NB = H / fft_radix(H, ST);
-        for (int w = tid; w < NB * kCols; w += kThreads) {
-            const int c = w % kCols, u = w / kCols;
-            auto ld = [&](int pos) -> float2 { return sm(pos, c); };
-            auto st = [&](int pos, float2 v) { sm(pos, c) = v; };
-            butterfly<H, ST, F, N>(u, tw, ld, st, NoMid());
+            sm(k, b) = Z;
         }
         __syncthreads();
-    };
-    if constexpr (FWD) {
-        run_stage(PM_ST(0), PM_T);
-        if constexpr (S >= 2) run_stage(PM_ST(1), PM_T);
-        if constexpr (S >= 3) run_stage(PM_ST(2), PM_T);
-        if constexpr (S >= 4) run_stage(PM_ST(3), PM_T);
-        for (int idx = tid; idx < kCols * H; idx += kThreads) {
-            const int b = idx / H, k = idx % H;
-            float2 X;
-            if (k == 0) {
-                const float2 Z0 = sm(0, b);
-                X = make_float2(Z0.x + Z0.y, Z0.x - Z0.y);  // packed (DC, Nyquist)
-            } else {
-                const float2 Zk = sm(digit_rev<H>(k), b);
-                const float2 Zm = sm(digit_rev<H>(H - k), b);
-                const float2 A = make_float2(Zk.x + Zm.x, Zk.y - Zm.y);  // Zk + conj(Zm)
-                const float2 B = make_float2(Zk.x - Zm.x, Zk.y + Zm.y);  // Zk - conj(Zm)
-                const float2 t = cmul(__ldg(tw + k), B);
-                X = make_float2(0.5f * (A.x + t.y), 0.5f * (A.y - t.x)); // (A - i t) / 2
+        {
+            float2 v[ITL][RL];
+#pragma unroll
+            for (int it = 0; it < ITL; ++it) {
+                const int w = it * kThreads + tid;
+                const int c = w % kCols, pos0 = (w / kCols) * RL;
+                if (w < NBL * kCols) {
+                    const int k0 = digit_unrev<H>(pos0);
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) v[it][r] = sm(k0 + r * NBL, c);
+                    dft<RL, +1>(v[it]);
+                }
             }
-            out[(row0 + b) * H + k] = X;
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < ITL; ++it) {
+                const int w = it * kThreads + tid;
+                const int c = w % kCols, pos0 = (w / kCols) * RL;
+                if (w < NBL * kCols) {
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) sm(pos0 + r, c) = v[it][r];
+                }
+            }
+            __syncthreads();
         }
-    } else {
-        if constexpr (S >= 4) run_stage(PM_ST(3), PM_F);
-        if constexpr (S >= 3) run_stage(PM_ST(2), PM_F);
-        if constexpr (S >= 2) run_stage(PM_ST(1), PM_F);
-        run_stage(PM_ST(0), PM_F);
-        for (int idx = tid; idx < kCols * H; idx += kThreads) {
-            const int b = idx / H, k = idx % H;
-            out[(row0 + b) * H + k] = sm(k, b);
+        if constexpr (S >= 4) run_stage(PM_ST(2), PM_F);
+        if constexpr (S >= 3) run_stage(PM_ST(1), PM_F);
+        if constexpr (S >= 2) run_stage(PM_ST(0), PM_F);
+#pragma unroll 4
+        for (int it = 0; it < LD_IT; ++it) {
+            const int idx = it * kThreads + tid;
+            out[(row0 + idx / H) * H + idx % H] = sm(idx % H, idx / H);
         }
     }
 }
