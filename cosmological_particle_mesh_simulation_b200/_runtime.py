@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libpmstep.so")
+# PM_LIB lets an experiment point at an alternative build of the same ABI (tuning A/B runs).
+LIB_PATH = os.environ.get("PM_LIB") or os.path.join(_PKG_DIR, "libpmstep.so")
 
 _lib = None
 _lock = threading.Lock()

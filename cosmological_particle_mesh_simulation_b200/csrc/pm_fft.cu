@@ -34,6 +34,14 @@ constexpr int kCols = 16;          // adjacent columns (contiguous in memory) pe
 constexpr int kPitch = kCols + 1;  // +1: the split-off Nyquist column of the packed slot; also
                                    // keeps transposing row accesses conflict-free
 constexpr int kThreads = 256;
+// Column kernels: how many butterflies' worth of global loads a thread issues before it starts
+// computing (memory-level parallelism vs registers), and the CTAs/SM the register budget targets.
+#ifndef PM_FFT_BATCH
+#define PM_FFT_BATCH 2
+#endif
+#ifndef PM_FFT_MINB
+#define PM_FFT_MINB 3
+#endif
 
 // ---- compile-time radix plan: as many 8s as divide n, then one 4 or 2 -------------------------
 __host__ __device__ constexpr int fft_radix(int n, int stage)
@@ -151,7 +159,7 @@ __device__ __forceinline__ void dft(float2 (&v)[R])
 // `tw` is the table exp(-2 pi i m / TWN), TWN a multiple of N (rows use the N-point table for
 // their N/2-point transforms).  ld(pos) / st(pos, value) do the addressing.
 template <int N, int ST, bool FWD, int TWN, class Ld, class St, class Mid>
-__device__ __forceinline__ void butterfly(int u, const float2 *__restrict__ tw, Ld ld, St st, Mid mid)
+__device__ __forceinline__ void butterfly(int u, const float2 *tw, Ld ld, St st, Mid mid)
 {
     constexpr int R = fft_radix(N, ST);
     constexpr int L = fft_len(N, ST);
@@ -165,12 +173,12 @@ __device__ __forceinline__ void butterfly(int u, const float2 *__restrict__ tw, 
         dft<R, -1>(v);
         if constexpr (SUB > 1) {
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + i * q * (TWN / L)));
+            for (int q = 1; q < R; ++q) v[q] = cmul(v[q], tw[i * q * (TWN / L)]);
         }
     } else {
         if constexpr (SUB > 1) {
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + i * q * (TWN / L)));
+            for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], tw[i * q * (TWN / L)]);
         }
         dft<R, +1>(v);
     }
@@ -202,23 +210,76 @@ struct ColArgs {
     int axis;          // 1: along y (tiles = z x kx-tile), 0: along z (tiles = y x kx-tile, + side)
 };
 
-// Column FFT pass.  A tile is N points (stride `gs` float2 apart) x 16 adjacent columns.
-template <int N, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) k_fft_cols(ColArgs a)
+// Two adjacent columns per thread: every tile access is a 16-byte LDS/STS/LDG/STG and the two
+// butterflies share their twiddles -- half the memory instructions per point of a scalar version.
+template <int N, int ST, bool FWD, class Ld4, class St4, class Mid>
+__device__ __forceinline__ void butterfly2(int u, const float2 *tw, Ld4 ld, St4 st, Mid mid)
 {
-    extern __shared__ float2 s_tile[];  // [N][kPitch]
+    constexpr int R = fft_radix(N, ST);
+    constexpr int L = fft_len(N, ST);
+    constexpr int SUB = L / R;
+    const int b = u / SUB, i = u % SUB;
+    const int pos0 = b * L + i;
+    float2 va[R], vb[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float4 q = ld(pos0 + r * SUB);
+        va[r] = make_float2(q.x, q.y);
+        vb[r] = make_float2(q.z, q.w);
+    }
+    if constexpr (FWD) {
+        dft<R, -1>(va);
+        dft<R, -1>(vb);
+        if constexpr (SUB > 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                const float2 w = tw[i * q * (N / L)];
+                va[q] = cmul(va[q], w);
+                vb[q] = cmul(vb[q], w);
+            }
+        }
+    } else {
+        if constexpr (SUB > 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                const float2 w = tw[i * q * (N / L)];
+                va[q] = cmulc(va[q], w);
+                vb[q] = cmulc(vb[q], w);
+            }
+        }
+        dft<R, +1>(va);
+        dft<R, +1>(vb);
+    }
+    mid(va, vb, pos0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) st(pos0 + r * SUB, make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y));
+}
+
+// Column FFT pass.  A tile is N points (stride `gs` float2 apart) x 16 adjacent columns, held in
+// shared memory as [N][16] float2 (128-byte rows: a quarter-warp's 16-byte accesses cover one row,
+// conflict-free), followed by the split-off Nyquist column [N] and the twiddle table [N].
+template <int N, int MODE>
+__global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
+{
+    extern __shared__ float2 s_tile[];
     constexpr int H = N / 2;
     constexpr int TPR = H / kCols;      // column tiles per row of the main array
     constexpr int S = fft_stages(N);
+    constexpr int CP = kCols / 2;       // column pairs
     const int tid = threadIdx.x;
+    float2 *s_x = s_tile + N * kCols;   // extra column
+    // Twiddles live in shared memory: with the carveout these tiles need, L1 is too small to keep
+    // a __ldg table resident against the streaming tile traffic.  A quarter-warp reads one entry.
+    float2 *s_tw = s_x + N;
+    for (int m = tid; m < N; m += kThreads) s_tw[m] = a.tw[m];
+    __syncthreads();
 
     // ---- which tile ----
     const int t = blockIdx.x;
     float2 *g;            // first element of the tile
     size_t gs;            // stride between successive points
     bool extra = false;   // y pass, kx-tile 0: also carries the split-off Nyquist column
-    float2 *gx = nullptr; // its global home (side array), stride N... see below
-    size_t gxs = 0;
+    float2 *gx = nullptr; // its global home: side[z][.]
     float sy_fixed = 0.f; // Green's: sin^2 term that is constant over the tile
     int col0 = 0;         // first column index (kx for main tiles, y position for side tiles)
     bool side_tile = false;
@@ -229,7 +290,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_fft_cols(ColArgs a)
         if (kt == 0) {
             extra = true;
             gx = a.side + (size_t)z * N;
-            gxs = 1;
         }
     } else {
         if (t < N * TPR) {
@@ -247,84 +307,52 @@ __global__ void __launch_bounds__(kThreads, 2) k_fft_cols(ColArgs a)
         }
     }
 
-    auto sm = [&](int pos, int c) -> float2 & { return s_tile[pos * kPitch + c]; };
+    auto sm4 = [&](int pos, int cp) -> float4 & {
+        return *reinterpret_cast<float4 *>(s_tile + pos * kCols + 2 * cp);
+    };
 
-    // ---- generic stage runner over the 16 main columns (+ the extra one) ----
-    // src/dst: 0 = shared tile, 1 = global.  For the extra column in the y pass the global home
-    // is the side array; its forward input is the imaginary part of packed column 0.
-    auto run_stage = [&](auto st_tag, auto fwd_tag, auto src_tag, auto dst_tag, auto mid_main) {
+    // ---- generic stage runner over the 8 column pairs (+ the extra column) ----
+    // src/dst: 0 = shared tile, 1 = global.
+    auto run_stage = [&](auto st_tag, auto fwd_tag, auto src_tag, auto dst_tag) {
         constexpr int ST = decltype(st_tag)::value;
         constexpr bool FWD = decltype(fwd_tag)::value;
         constexpr int src = decltype(src_tag)::value, dst = decltype(dst_tag)::value;
         constexpr int R = fft_radix(N, ST);
         constexpr int NB = N / R;
-        constexpr int SUB = fft_len(N, ST) / R;
-        constexpr int ITERS = (NB * kCols + kThreads - 1) / kThreads;
-        auto st_main = [&](int c) {
-            return [&, c](int pos, float2 v) {
-                if (dst == 0 || (extra && c == 0 && !FWD)) sm(pos, c) = v;  // inverse: merged later
-                else g[pos * gs + c] = v;
-            };
-        };
-        if constexpr (src == 1) {
-            // Issue every global load of this thread before the first butterfly: the whole tile
-            // (N x 16 x 8 B) is in flight per CTA, which is what keeps HBM busy with 2-3 CTAs/SM.
-            float2 buf[ITERS][R];
+        constexpr int ITERS = (NB * CP + kThreads - 1) / kThreads;
 #pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const int w = it * kThreads + tid;
-                const int c = w % kCols, u = w / kCols;
-                const int pos0 = (u / SUB) * (SUB * R) + (u % SUB);
-                if (w < NB * kCols) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) buf[it][r] = g[(size_t)(pos0 + r * SUB) * gs + c];
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const int w = it * kThreads + tid;
-                const int c = w % kCols, u = w / kCols;
-                if (w < NB * kCols) {
-                    const int pos0 = (u / SUB) * (SUB * R) + (u % SUB);
-                    auto ld = [&](int pos) -> float2 {
-                        float2 v = buf[it][(pos - pos0) / SUB];
-                        if (extra && c == 0 && FWD) v.y = 0.0f;  // packed slot: real part is the DC column
-                        return v;
-                    };
-                    butterfly<N, ST, FWD, N>(u, a.tw, ld, st_main(c),
-                                             [&](auto &v, int p0) { mid_main(v, p0, c); });
-                }
-            }
-        } else {
-#pragma unroll
-            for (int it = 0; it < ITERS; ++it) {
-                const int w = it * kThreads + tid;
-                const int c = w % kCols, u = w / kCols;
-                if (w < NB * kCols) {
-                    auto ld = [&](int pos) -> float2 { return sm(pos, c); };
-                    butterfly<N, ST, FWD, N>(u, a.tw, ld, st_main(c),
-                                             [&](auto &v, int p0) { mid_main(v, p0, c); });
-                }
+        for (int it = 0; it < ITERS; ++it) {
+            const int w = it * kThreads + tid;
+            const int cp = w % CP, u = w / CP;
+            if (w < NB * CP) {
+                auto ld = [&](int pos) -> float4 {
+                    if (src == 0) return sm4(pos, cp);
+                    float4 q = *reinterpret_cast<const float4 *>(g + (size_t)pos * gs + 2 * cp);
+                    if (extra && cp == 0 && FWD) q.y = 0.0f;  // packed slot: real part = DC column
+                    return q;
+                };
+                auto st = [&](int pos, float4 q) {
+                    if (dst == 0 || (extra && cp == 0 && !FWD)) sm4(pos, cp) = q;  // inverse: merged later
+                    else *reinterpret_cast<float4 *>(g + (size_t)pos * gs + 2 * cp) = q;
+                };
+                butterfly2<N, ST, FWD>(u, s_tw, ld, st, [](auto &, auto &, int) {});
             }
         }
         if (extra) {
             for (int u = tid; u < NB; u += kThreads) {
                 auto ld = [&](int pos) -> float2 {
-                    if (src == 0) return sm(pos, kCols);
-                    if (FWD) return make_float2(g[pos * gs].y, 0.0f);  // Nyquist column of the packed slot
-                    return gx[pos * gxs];
+                    if (src == 0) return s_x[pos];
+                    if (FWD) return make_float2(g[(size_t)pos * gs].y, 0.0f);  // Nyquist part of the packed slot
+                    return gx[pos];
                 };
                 auto st = [&](int pos, float2 v) {
-                    if (dst == 0 || !FWD) sm(pos, kCols) = v;
-                    else gx[pos * gxs] = v;
+                    if (dst == 0 || !FWD) s_x[pos] = v;
+                    else gx[pos] = v;
                 };
-                butterfly<N, ST, FWD, N>(u, a.tw, ld, st, NoMid());
+                butterfly<N, ST, FWD, N>(u, s_tw, ld, st, NoMid());
             }
         }
     };
-    auto nomid = [](auto &, int, int) {};
-    auto tag = [](auto v) { return v; };
-    (void)tag;
 
 #define PM_ST(k) std::integral_constant<int, (k)>()
 #define PM_T std::true_type()
@@ -332,58 +360,77 @@ __global__ void __launch_bounds__(kThreads, 2) k_fft_cols(ColArgs a)
 
     if constexpr (MODE == COL_FWD) {
         // stage 0 from global, stages 1..S-2 in shared memory, stage S-1 to global
-        run_stage(PM_ST(0), PM_T, PM_ST(1), PM_ST(0), nomid);
+        run_stage(PM_ST(0), PM_T, PM_ST(1), PM_ST(0));
         __syncthreads();
-        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
-        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
-        run_stage(PM_ST(S - 1), PM_T, PM_ST(0), PM_ST(1), nomid);
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_T, PM_ST(0), PM_ST(0)); __syncthreads(); }
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_T, PM_ST(0), PM_ST(0)); __syncthreads(); }
+        run_stage(PM_ST(S - 1), PM_T, PM_ST(0), PM_ST(1));
     } else if constexpr (MODE == COL_INV) {
-        run_stage(PM_ST(S - 1), PM_F, PM_ST(1), PM_ST(0), nomid);
+        run_stage(PM_ST(S - 1), PM_F, PM_ST(1), PM_ST(0));
         __syncthreads();
-        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
-        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
-        run_stage(PM_ST(0), PM_F, PM_ST(0), PM_ST(1), nomid);
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_F, PM_ST(0), PM_ST(0)); __syncthreads(); }
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_F, PM_ST(0), PM_ST(0)); __syncthreads(); }
+        run_stage(PM_ST(0), PM_F, PM_ST(0), PM_ST(1));
         if (extra) {
-            // merge: packed slot = (Re DC column, Re Nyquist column); both are real up to rounding
+            // merge: packed slot = (Re DC column, Re Nyquist column); both are real up to rounding.
+            // Column 1 shared the 16-byte accesses of column 0, so it is flushed here too.
             __syncthreads();
-            for (int pos = tid; pos < N; pos += kThreads)
-                g[pos * gs] = make_float2(sm(pos, 0).x, sm(pos, kCols).x);
+            for (int pos = tid; pos < N; pos += kThreads) {
+                const float4 q = sm4(pos, 0);
+                *reinterpret_cast<float4 *>(g + (size_t)pos * gs) = make_float4(q.x, s_x[pos].x, q.z, q.w);
+            }
         }
     } else {
         // forward along z, Green's function, inverse along z -- one trip through HBM
-        run_stage(PM_ST(0), PM_T, PM_ST(1), PM_ST(0), nomid);
+        run_stage(PM_ST(0), PM_T, PM_ST(1), PM_ST(0));
         __syncthreads();
-        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
-        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_T, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_T, PM_ST(0), PM_ST(0)); __syncthreads(); }
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_T, PM_ST(0), PM_ST(0)); __syncthreads(); }
         {
             // last forward stage, multiply, first inverse stage: same R consecutive points
             constexpr int ST = S - 1;
             constexpr int R = fft_radix(N, ST);
             constexpr int NB = N / R;
-            for (int w = tid; w < NB * kCols; w += kThreads) {
-                const int c = w % kCols, u = w / kCols;
-                const int pos0 = u * R;
-                float2 v[R];
+            constexpr int ITERS = (NB * CP + kThreads - 1) / kThreads;
 #pragma unroll
-                for (int r = 0; r < R; ++r) v[r] = sm(pos0 + r, c);
-                dft<R, -1>(v);
-                const float sy = side_tile ? __ldg(a.sin2rev + col0 + c) : sy_fixed;
-                const float sx = side_tile ? __ldg(a.sin2 + H) : __ldg(a.sin2 + col0 + c);
+            for (int it = 0; it < ITERS; ++it) {
+                const int w = it * kThreads + tid;
+                const int cp = w % CP, pos0 = (w / CP) * R;
+                if (w < NB * CP) {
+                    float2 va[R], vb[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const float gk = a.scale * green_f32(__ldg(a.sin2rev + pos0 + r), sy, sx);
-                    v[r].x *= gk;
-                    v[r].y *= gk;
+                    for (int r = 0; r < R; ++r) {
+                        const float4 q = sm4(pos0 + r, cp);
+                        va[r] = make_float2(q.x, q.y);
+                        vb[r] = make_float2(q.z, q.w);
+                    }
+                    dft<R, -1>(va);
+                    dft<R, -1>(vb);
+                    const int c = col0 + 2 * cp;
+                    const float sya = side_tile ? __ldg(a.sin2rev + c) : sy_fixed;
+                    const float syb = side_tile ? __ldg(a.sin2rev + c + 1) : sy_fixed;
+                    const float sxa = side_tile ? __ldg(a.sin2 + H) : __ldg(a.sin2 + c);
+                    const float sxb = side_tile ? sxa : __ldg(a.sin2 + c + 1);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float sz = __ldg(a.sin2rev + pos0 + r);
+                        const float ga = a.scale * green_f32(sz, sya, sxa);
+                        const float gb = a.scale * green_f32(sz, syb, sxb);
+                        va[r].x *= ga; va[r].y *= ga;
+                        vb[r].x *= gb; vb[r].y *= gb;
+                    }
+                    dft<R, +1>(va);
+                    dft<R, +1>(vb);
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        sm4(pos0 + r, cp) = make_float4(va[r].x, va[r].y, vb[r].x, vb[r].y);
                 }
-                dft<R, +1>(v);
-#pragma unroll
-                for (int r = 0; r < R; ++r) sm(pos0 + r, c) = v[r];
             }
         }
         __syncthreads();
-        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
-        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_F, PM_ST(0), PM_ST(0), nomid); __syncthreads(); }
-        run_stage(PM_ST(0), PM_F, PM_ST(0), PM_ST(1), nomid);
+        if constexpr (S >= 4) { run_stage(PM_ST(2), PM_F, PM_ST(0), PM_ST(0)); __syncthreads(); }
+        if constexpr (S >= 3) { run_stage(PM_ST(1), PM_F, PM_ST(0), PM_ST(0)); __syncthreads(); }
+        run_stage(PM_ST(0), PM_F, PM_ST(0), PM_ST(1));
     }
 }
 
@@ -408,6 +455,8 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
     const int tid = threadIdx.x;
     const size_t row0 = (size_t)blockIdx.x * kCols;
     auto sm = [&](int pos, int c) -> float2 & { return s_tile[pos * kPitch + c]; };
+    float2 *s_tw = s_tile + H * kPitch;   // N-entry twiddle table (visible after the first barrier)
+    for (int m = tid; m < N; m += kThreads) s_tw[m] = tw[m];
 
     auto run_stage = [&](auto st_tag, auto fwd_tag) {
         constexpr int ST = decltype(st_tag)::value;
@@ -421,7 +470,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
             if (w < NB * kCols) {
                 auto ld = [&](int pos) -> float2 { return sm(pos, c); };
                 auto st = [&](int pos, float2 v) { sm(pos, c) = v; };
-                butterfly<H, ST, F, N>(u, tw, ld, st, NoMid());
+                butterfly<H, ST, F, N>(u, s_tw, ld, st, NoMid());
             }
         }
         __syncthreads();
@@ -482,7 +531,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
                 const float2 Zm = sm(H - k, b);
                 const float2 A = make_float2(Zk.x + Zm.x, Zk.y - Zm.y);  // Zk + conj(Zm)
                 const float2 B = make_float2(Zk.x - Zm.x, Zk.y + Zm.y);  // Zk - conj(Zm)
-                const float2 t = cmul(__ldg(tw + k), B);
+                const float2 t = cmul(s_tw[k], B);
                 X = make_float2(0.5f * (A.x + t.y), 0.5f * (A.y - t.x)); // (A - i t) / 2
             }
             out[(row0 + b) * H + k] = X;
@@ -500,7 +549,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
                 const float2 Bm = in[(row0 + b) * H + (H - k)];
                 const float2 P = make_float2(A.x + Bm.x, A.y - Bm.y);   // A + conj(B)
                 const float2 Q = make_float2(A.x - Bm.x, A.y + Bm.y);   // A - conj(B)
-                const float2 t = cmulc(Q, __ldg(tw + k));               // conj(w^k) * Q
+                const float2 t = cmulc(Q, __ldg(tw + k));               // conj(w^k) * Q (before the first barrier)
                 Z = make_float2(P.x - t.y, P.y + t.x);                  // P + i t
             }
             sm(k, b) = Z;
@@ -546,8 +595,8 @@ template <int N>
 int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
 {
     constexpr int H = N / 2;
-    const size_t smem_cols = (size_t)N * kPitch * sizeof(float2);
-    const size_t smem_rows = (size_t)H * kPitch * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
         PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
@@ -555,6 +604,12 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
         PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
         PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
         PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        // ask for the largest shared-memory carveout so the occupancy the tiles were sized for holds
+        PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FWD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_INV>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set = true;
     }
     ColArgs ca;

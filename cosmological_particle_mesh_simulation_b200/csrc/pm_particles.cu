@@ -187,19 +187,25 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
                 v0 = __dmul_rn(__dmul_rn(__dmul_rn(mass, t_x), w_y), w_z);
                 v1 = __dmul_rn(__dmul_rn(__dmul_rn(mass, d_x), w_y), w_z);
             }
-            // warp-segmented inclusive scan over runs of equal x cell
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
+            // Warp-segmented inclusive scan over runs of equal x cell.  The list is sorted, so a
+            // run is a stretch of lanes that are not "heads"; the ballot of heads tells the whole
+            // warp how long the longest run is, and the scan stops after ceil(log2(longest)) steps
+            // (0 or 1 for a near-uniform particle load, 5 inside a halo).  m holds, for step d,
+            // the lanes whose d predecessors all continue their run (m_2d = m_d & (m_d << d)).
+            const int prv = __shfl_up_sync(full, xc, 1);
+            const unsigned heads = __ballot_sync(full, lane == 0 || prv != xc);
+            unsigned m = ~heads;
+#pragma unroll 1
+            for (int d = 1; m != 0; d <<= 1) {
                 const double o0 = __shfl_up_sync(full, v0, d);
                 const double o1 = __shfl_up_sync(full, v1, d);
-                const int oc = __shfl_up_sync(full, xc, d);
-                if (lane >= d && oc == xc) {
+                if ((m >> lane) & 1u) {
                     v0 += o0;
                     v1 += o1;
                 }
+                m &= (m << d);
             }
-            const int nxt = __shfl_down_sync(full, xc, 1);
-            const bool tail = valid && (lane == 31 || nxt != xc);
+            const bool tail = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u));
             if (tail) row[xc] += v0;
             __syncwarp();
             if (tail) row[(xc + 1 == nc) ? 0 : xc + 1] += v1;
