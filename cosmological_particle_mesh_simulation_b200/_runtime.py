@@ -73,6 +73,20 @@ def lib():
             "pm_particles_store": (i32, [vp, vp, vp, vp]),
             "pm_particles_order": (i32, [vp, vp, vp]),
             "pm_particles_count": (i64, [vp]),
+            "pm_plan_create_slab": (i32, [ctypes.POINTER(vp), i32, i64, i32, i32, i32]),
+            "pm_slab_buffer": (i32, [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(sz)]),
+            "pm_slab_load": (i32, [vp, vp, vp, vp, i64, vp]),
+            "pm_slab_count": (i64, [vp]),
+            "pm_slab_entries": (i64, [vp]),
+            "pm_slab_deposit": (i32, [vp, f64, vp]),
+            "pm_slab_ghost_add": (i32, [vp, vp]),
+            "pm_slab_fft_forward": (i32, [vp, vp]),
+            "pm_slab_fft_z": (i32, [vp, f64, f64, vp]),
+            "pm_slab_fft_inverse": (i32, [vp, vp]),
+            "pm_slab_gather": (i32, [vp, f64, f64, f64, vp]),
+            "pm_slab_migrate_pack": (i32, [vp, vp, vp]),
+            "pm_slab_migrate_unpack": (i32, [vp, i64, i64, vp]),
+            "pm_slab_export": (i32, [vp, vp, vp, vp, vp, vp]),
             "pm_plan_profile_begin": (i32, [vp, i32]),
             "pm_plan_profile_read": (i32, [vp, vp, ctypes.POINTER(i32)]),
         }
@@ -90,6 +104,10 @@ EXPORTED_SYMBOLS = (
     "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_plan_profile_begin",
     "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_particles_store",
     "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend",
+    "pm_plan_create_slab", "pm_slab_buffer", "pm_slab_load", "pm_slab_count", "pm_slab_entries",
+    "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_forward", "pm_slab_fft_z",
+    "pm_slab_fft_inverse", "pm_slab_gather", "pm_slab_migrate_pack", "pm_slab_migrate_unpack",
+    "pm_slab_export",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

@@ -24,7 +24,13 @@ int key_bits_for(int nc)
 // Sizes of every workspace segment, in the order they are carved.
 struct Layout {
     size_t keys, iota, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2, tw,
-        rpos, rvel, rid, total;
+        rpos, rvel, rid, tbuf, leave_cnt, leave_slot, mig, total;
+    int64_t leave_cap;
+};
+
+struct Geometry {
+    int nc, rank, nranks;
+    bool slab;   // slab-mode buffers (ghost planes, all-to-all staging, migration lists)
 };
 
 bool config_ok(int nc, int64_t np)
@@ -47,27 +53,35 @@ int make_fft_plans(int nc, cufftHandle *r2c, cufftHandle *c2r, size_t *work)
     return PM_OK;
 }
 
-int compute_layout(int nc, int64_t np, size_t fft_work, Layout *L)
+int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
 {
-    const size_t m = (size_t)nc * nc * nc;
+    const int nc = g.nc, nzl = nc / g.nranks;
+    const size_t plane = (size_t)nc * nc;
     const size_t npad = (size_t)((np + 3) / 4 * 4);
     L->keys = align_up(npad * 4);
     L->iota = align_up(npad * 4);
     L->keys_sorted = align_up(npad * 4);
     L->order_sorted = align_up(npad * 4);
-    L->cub = align_up(pm_sort_temp_bytes(np > 0 ? np : 1, key_bits_for(nc)));
-    L->row_start = align_up(((size_t)nc * nc + 1) * 4);
-    L->mesh = align_up(m * 4);
-    L->mesh2 = align_up(m * 4);
-    L->spec = align_up((size_t)nc * nc * (nc / 2 + 1) * sizeof(float2));
+    L->cub = align_up(pm_sort_temp_bytes(np > 0 ? np : 1, g.slab ? 32 : key_bits_for(nc)));
+    L->row_start = align_up(((size_t)nzl * nc + 1) * 4);
+    L->mesh = align_up(plane * (nzl + (g.slab ? 1 : 0)) * 4);    // rho (+ ghost plane)
+    L->mesh2 = align_up(plane * (nzl + (g.slab ? 3 : 0)) * 4);   // phi (+ 1 + 2 ghost planes)
+    L->spec = align_up((size_t)nzl * nc * (nc / 2 + 1) * sizeof(float2));
     L->fft = align_up(fft_work);
     L->sin2 = align_up((size_t)nc * 4);
     L->tw = align_up((size_t)nc * 8);
     L->rpos = align_up(3 * npad * 4);
     L->rvel = align_up(3 * npad * 4);
     L->rid = align_up(npad * 4);
+    L->tbuf = g.slab ? L->spec : 0;
+    // migration: room for 1/8 of the capacity (at least 4096) to leave towards each rank per step
+    L->leave_cap = g.slab ? (int64_t)((npad / 8 > 4096) ? npad / 8 : 4096) : 0;
+    L->leave_cnt = g.slab ? align_up((size_t)g.nranks * 4) : 0;
+    L->leave_slot = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 4) : 0;
+    L->mig = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 7 * 4) : 0;
     L->total = L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
-               L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw + 2 * (L->rpos + L->rvel + L->rid);
+               L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw +
+               2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot + 2 * L->mig;
     return PM_OK;
 }
 
@@ -121,15 +135,21 @@ size_t pm_plan_workspace_bytes(int n_cells, int64_t np_capacity)
     cufftDestroy(a);
     cufftDestroy(b);
     Layout L;
-    compute_layout(n_cells, np_capacity, work, &L);
+    Geometry g{n_cells, 0, 1, false};
+    compute_layout(g, np_capacity, work, &L);
     return L.total;
 }
 
-int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
+static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, int device)
 {
     if (!out) return PM_ERR_INVALID;
     *out = nullptr;
+    const int n_cells = g.nc;
     if (!config_ok(n_cells, np_capacity)) return PM_ERR_UNSUPPORTED;
+    if (g.nranks < 1 || g.rank < 0 || g.rank >= g.nranks || n_cells % g.nranks != 0)
+        return PM_ERR_INVALID;
+    if (g.slab && (!pm_fft_supported(n_cells) || (n_cells / g.nranks) % 16 != 0))
+        return PM_ERR_UNSUPPORTED;   // slab mode runs the hand-written FFT on 16-column tiles
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -144,19 +164,27 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
     memset(p, 0, sizeof(*p));
     p->nc = n_cells;
     p->np_cap = np_capacity;
-    p->key_bits = key_bits_for(n_cells);
+    p->rank = g.rank;
+    p->nranks = g.nranks;
+    p->nzl = n_cells / g.nranks;
+    p->z0 = g.rank * p->nzl;
+    p->slab = g.slab;
+    p->key_bits = g.slab ? 32 : key_bits_for(n_cells);
+    p->rstride = (np_capacity + 3) / 4 * 4;
     cudaGetDevice(&p->device);
     cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
 
     size_t work = 0;
-    rc = make_fft_plans(n_cells, &p->r2c, &p->c2r, &work);
-    if (rc != PM_OK) {
-        pm_plan_destroy(p);
-        return rc;
+    if (!g.slab) {
+        rc = make_fft_plans(n_cells, &p->r2c, &p->c2r, &work);
+        if (rc != PM_OK) {
+            pm_plan_destroy(p);
+            return rc;
+        }
+        p->have_fft = true;
     }
-    p->have_fft = true;
     Layout L;
-    compute_layout(n_cells, np_capacity, work, &L);
+    compute_layout(g, np_capacity, work, &L);
     p->ws_bytes = L.total;
     if (cudaMalloc((void **)&p->ws, L.total) != cudaSuccess) {
         cudaGetLastError();
@@ -184,16 +212,25 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
         p->rvel[k] = (float *)c;      c += L.rvel;
         p->rid[k] = (uint32_t *)c;    c += L.rid;
     }
+    if (g.slab) {
+        p->tbuf[0] = (float2 *)c;     c += L.tbuf;
+        p->tbuf[1] = (float2 *)c;     c += L.tbuf;
+        p->leave_cnt = (uint32_t *)c; c += L.leave_cnt;
+        p->leave_slot = (uint32_t *)c; c += L.leave_slot;
+        p->mig_send = (float *)c;     c += L.mig;
+        p->mig_recv = (float *)c;     c += L.mig;
+        p->leave_cap = L.leave_cap;
+    }
 
-    if (cufftSetWorkArea(p->r2c, p->fft_work) != CUFFT_SUCCESS ||
-        cufftSetWorkArea(p->c2r, p->fft_work) != CUFFT_SUCCESS) {
+    if (p->have_fft && (cufftSetWorkArea(p->r2c, p->fft_work) != CUFFT_SUCCESS ||
+                        cufftSetWorkArea(p->c2r, p->fft_work) != CUFFT_SUCCESS)) {
         pm_plan_destroy(p);
         return PM_ERR_CUFFT;
     }
     rc = pm_k_sin2_table(p);
     {
         const char *be = getenv("PM_FFT_BACKEND");  // "cufft" forces the library path (A/B checks)
-        p->own_fft = pm_fft_supported(n_cells) && !(be && strcmp(be, "cufft") == 0);
+        p->own_fft = pm_fft_supported(n_cells) && (g.slab || !(be && strcmp(be, "cufft") == 0));
     }
     if (rc == PM_OK && pm_fft_supported(n_cells)) rc = pm_k_fft_tables(p);
     if (rc == PM_OK) rc = pm_k_iota(p->iota, np_capacity, 0);
@@ -210,6 +247,19 @@ int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
     }
     *out = p;
     return PM_OK;
+}
+
+int pm_plan_create(pm_plan **out, int n_cells, int64_t np_capacity, int device)
+{
+    Geometry g{n_cells, 0, 1, false};
+    return plan_create(out, g, np_capacity, device);
+}
+
+int pm_plan_create_slab(pm_plan **out, int n_cells, int64_t np_capacity, int device, int rank,
+                        int nranks)
+{
+    Geometry g{n_cells, rank, nranks, true};
+    return plan_create(out, g, np_capacity, device);
 }
 
 int pm_plan_destroy(pm_plan *p)
@@ -242,6 +292,7 @@ int pm_plan_set_fft_backend(pm_plan *p, int backend)
 {
     if (!p || backend < 0 || backend > 1) return PM_ERR_INVALID;
     if (backend == 0 && !pm_fft_supported(p->nc)) return PM_ERR_UNSUPPORTED;
+    if (backend == 1 && !p->have_fft) return PM_ERR_UNSUPPORTED;   // slab plans carry no cuFFT plan
     p->own_fft = (backend == 0);
     return PM_OK;
 }
@@ -272,7 +323,7 @@ int pm_cell_keys(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_d, p
     PM_ARGS(p && (np == 0 || (pos_d && keys_d)) && np >= 0 && np <= p->np_cap);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
-    return pm_k_cell_keys(p, pos_d, np, keys_d, nullptr, pm_cu(stream));
+    return pm_k_cell_keys(p, pos_d, np, np, keys_d, nullptr, pm_cu(stream));
 }
 
 int pm_sort_by_cell(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_sorted_d,
@@ -283,7 +334,7 @@ int pm_sort_by_cell(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_s
     PM_TRY(guard.enter(p->device));
     cudaStream_t st = pm_cu(stream);
     p->rkeys_valid = false;
-    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, nullptr, st));
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, st));
     if (np == 0) return PM_OK;
     if (keys_sorted_d)
@@ -302,7 +353,7 @@ int pm_deposit_cic(pm_plan *p, const float *pos_d, int64_t np, double mass, floa
     PM_TRY(guard.enter(p->device));
     cudaStream_t st = pm_cu(stream);
     p->rkeys_valid = false;
-    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, nullptr, st));
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, st));
     PM_TRY(pm_k_row_offsets(p, np, st));
     return pm_k_deposit(p, pos_d, np, mass, rho_d, st);
@@ -336,7 +387,7 @@ int pm_step(pm_plan *p, float *pos_d, float *vel_d, int64_t np, double mass, dou
     float *rho = rho_d ? rho_d : p->mesh;
     p->rkeys_valid = false;
     pm_prof_mark(p, 0, st);
-    PM_TRY(pm_k_cell_keys(p, pos_d, np, p->keys, nullptr, st));
+    PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
     pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
     PM_TRY(pm_k_sort(p, np, st));
     pm_prof_mark(p, PM_STAGE_SORT + 1, st);
@@ -394,13 +445,13 @@ static int resident_step(pm_plan *p, double mass, double a, double da, double f_
     const int64_t np = p->rnp;
     float *rho = rho_d ? rho_d : p->mesh;
     pm_prof_mark(p, 0, st);
-    if (!p->rkeys_valid) PM_TRY(pm_k_cell_keys(p, p->rpos[p->rcur], np, p->keys, nullptr, st));
+    if (!p->rkeys_valid) PM_TRY(pm_k_cell_keys(p, p->rpos[p->rcur], np, p->rstride, p->keys, nullptr, st));
     pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
     PM_TRY(pm_k_sort(p, np, st));
     pm_prof_mark(p, PM_STAGE_SORT + 1, st);
     PM_TRY(pm_k_row_offsets(p, np, st));
     pm_prof_mark(p, PM_STAGE_ROWS + 1, st);
-    PM_TRY(pm_k_deposit(p, p->rpos[p->rcur], np, mass, rho, st));
+    PM_TRY(pm_k_deposit(p, p->rpos[p->rcur], p->rstride, mass, rho, st));
     pm_prof_mark(p, PM_STAGE_DEPOSIT + 1, st);
     PM_TRY(pm_k_poisson(p, rho, a, omega_m0, p->mesh2, st));
     PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));
@@ -420,11 +471,13 @@ int pm_particles_load(pm_plan *p, const float *pos_d, const float *vel_d, int64_
     cudaStream_t st = pm_cu(stream);
     const size_t b = (size_t)np * 3 * sizeof(float);
     p->rcur = 0;
-    p->rnp = np;
+    p->rnp = p->rtotal = np;
     p->rkeys_valid = false;
     if (np == 0) return PM_OK;
-    PM_CUDA(cudaMemcpyAsync(p->rpos[0], pos_d, b, cudaMemcpyDeviceToDevice, st));
-    PM_CUDA(cudaMemcpyAsync(p->rvel[0], vel_d, b, cudaMemcpyDeviceToDevice, st));
+    (void)b;
+    const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
+    PM_CUDA(cudaMemcpy2DAsync(p->rpos[0], pitch, pos_d, w, w, 3, cudaMemcpyDeviceToDevice, st));
+    PM_CUDA(cudaMemcpy2DAsync(p->rvel[0], pitch, vel_d, w, w, 3, cudaMemcpyDeviceToDevice, st));
     PM_CUDA(cudaMemcpyAsync(p->rid[0], p->iota, (size_t)np * 4, cudaMemcpyDeviceToDevice, st));
     return PM_OK;
 }
@@ -474,17 +527,19 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     p->rcur = 0;
     p->rnp = np;
     p->rkeys_valid = false;
+    const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
+    (void)pbytes;
     if (np) {
-        PM_CUDA(cudaMemcpyAsync(p->rpos[0], pos_h, pbytes, cudaMemcpyHostToDevice, p->s_main));
-        PM_CUDA(cudaMemcpyAsync(p->rvel[0], vel_h, pbytes, cudaMemcpyHostToDevice, p->s_up));
+        PM_CUDA(cudaMemcpy2DAsync(p->rpos[0], pitch, pos_h, w, w, 3, cudaMemcpyHostToDevice, p->s_main));
+        PM_CUDA(cudaMemcpy2DAsync(p->rvel[0], pitch, vel_h, w, w, 3, cudaMemcpyHostToDevice, p->s_up));
         PM_CUDA(cudaMemcpyAsync(p->rid[0], p->iota, (size_t)np * 4, cudaMemcpyDeviceToDevice, p->s_main));
     }
     PM_CUDA(cudaEventRecord(p->ev_a, p->s_up));
     cudaStream_t st = p->s_main;
-    PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->keys, nullptr, st));
+    PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->rstride, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, st));
     PM_TRY(pm_k_row_offsets(p, np, st));
-    PM_TRY(pm_k_deposit(p, p->rpos[0], np, mass, p->mesh, st));
+    PM_TRY(pm_k_deposit(p, p->rpos[0], p->rstride, mass, p->mesh, st));
     if (rho_h) {
         PM_CUDA(cudaEventRecord(p->ev_b, st));
         PM_CUDA(cudaStreamWaitEvent(p->s_down, p->ev_b, 0));
@@ -494,12 +549,13 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     PM_CUDA(cudaStreamWaitEvent(st, p->ev_a, 0));
     PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));
     p->rcur = 1;
+    // un-permute into set 0 as dense [3][np] arrays (the unpermute kernel writes stride np)
     PM_TRY(pm_k_unpermute(p, p->rpos[0], p->rvel[0], st));
     if (np) {
         PM_CUDA(cudaEventRecord(p->ev_c, st));
-        PM_CUDA(cudaMemcpyAsync(pos_h, p->rpos[0], pbytes, cudaMemcpyDeviceToHost, st));
+        PM_CUDA(cudaMemcpyAsync(pos_h, p->rpos[0], 3 * w, cudaMemcpyDeviceToHost, st));
         PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
-        PM_CUDA(cudaMemcpyAsync(vel_h, p->rvel[0], pbytes, cudaMemcpyDeviceToHost, p->s_up));
+        PM_CUDA(cudaMemcpyAsync(vel_h, p->rvel[0], 3 * w, cudaMemcpyDeviceToHost, p->s_up));
     }
     PM_CUDA(cudaStreamSynchronize(p->s_main));
     PM_CUDA(cudaStreamSynchronize(p->s_up));

@@ -208,6 +208,9 @@ struct ColArgs {
     const float *sin2, *sin2rev;
     float scale;       // -3*Omega_m/(8a)/N^3
     int axis;          // 1: along y (tiles = z x kx-tile), 0: along z (tiles = y x kx-tile, + side)
+    // z pass geometry: the array is [N z][nyl][N/2] holding y positions [y0, y0+nyl) -- the whole
+    // y range on one GPU, this rank's share after the all-to-all transpose in slab mode
+    int nyl, y0;
 };
 
 // Two adjacent columns per thread: every tile access is a 16-byte LDS/STS/LDG/STG and the two
@@ -292,18 +295,18 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
             gx = a.side + (size_t)z * N;
         }
     } else {
-        if (t < N * TPR) {
-            const int y = t / TPR, kt = t % TPR;
-            g = a.main + (size_t)y * H + kt * kCols;
-            gs = (size_t)N * H;
+        if (t < a.nyl * TPR) {
+            const int yl = t / TPR, kt = t % TPR;
+            g = a.main + (size_t)yl * H + kt * kCols;
+            gs = (size_t)a.nyl * H;
             col0 = kt * kCols;
-            if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2rev + y);
+            if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2rev + a.y0 + yl);
         } else {
             side_tile = true;
-            const int yt = t - N * TPR;
+            const int yt = t - a.nyl * TPR;
             g = a.side + yt * kCols;
-            gs = N;
-            col0 = yt * kCols;
+            gs = a.nyl;
+            col0 = a.y0 + yt * kCols;
         }
     }
 
@@ -620,6 +623,8 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     ca.sin2rev = p->sin2rev;
     const double m = (double)N * N * N;
     ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
+    ca.nyl = N;
+    ca.y0 = 0;
     const int row_ctas = N * N / kCols;
     const int tiles = N * (H / kCols);
 
@@ -641,6 +646,101 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     PM_LAUNCH(rows_inv, row_ctas, kThreads, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
               reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
     pm_prof_mark(p, PM_STAGE_C2R + 1, st);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// ---- slab decomposition: the same five passes with an all-to-all between 2|3 and 3|4 ----------
+// pack:   A[zl][y][k] (this rank's planes, all y)  ->  B[s][zl][yl][k], the chunk for rank s holding
+//         its y range [s*nyl, (s+1)*nyl); after the all-to-all the chunks received from ranks
+//         0..P-1 form C[z][yl][k] with z global -- the layout the z pass wants, no unpack needed.
+// unpack: the inverse on the way back.
+template <bool UNPACK>
+__global__ void __launch_bounds__(256) k_slab_pack(const float2 *__restrict__ src,
+                                                   float2 *__restrict__ dst, int nzl, int n, int w,
+                                                   int nyl)
+{
+    const size_t total = (size_t)nzl * n * w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % w);
+        const size_t r = i / w;
+        const int y = (int)(r % n), zl = (int)(r / n);
+        const int s = y / nyl, yl = y - s * nyl;
+        const size_t j = (((size_t)s * nzl + zl) * nyl + yl) * w + k;
+        if (UNPACK) dst[i] = src[j];
+        else dst[j] = src[i];
+    }
+}
+
+template <int N>
+int slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_side, cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const int nzl = p->nzl, nyl = N / p->nranks;
+    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
+    auto rows_fwd = k_fft_rows<N, true>;
+    auto cols_fwd = k_fft_cols<N, COL_FWD>;
+    PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    ColArgs ca;
+    ca.main = p->spec;
+    ca.side = p->spec + (size_t)nzl * N * H;
+    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
+    ca.scale = 0.f; ca.axis = 1; ca.nyl = nyl; ca.y0 = p->rank * nyl;
+    PM_LAUNCH(rows_fwd, nzl * N / kCols, kThreads, smem_rows, st,
+              reinterpret_cast<const float2 *>(rho), ca.main, (const float2 *)p->tw);
+    PM_LAUNCH(cols_fwd, nzl * (H / kCols), kThreads, smem_cols, st, ca);
+    const int grid = p->sm_count * 8;
+    PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.main, send_main, nzl, N, H, nyl);
+    PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.side, send_side, nzl, N, 1, nyl);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+template <int N>
+int slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0, cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const int nyl = N / p->nranks;
+    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    auto cols_fused = k_fft_cols<N, COL_FUSED>;
+    PM_CUDA(cudaFuncSetAttribute(cols_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    ColArgs ca;
+    ca.main = main_t; ca.side = side_t;
+    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
+    const double m = (double)N * N * N;
+    ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
+    ca.axis = 0; ca.nyl = nyl; ca.y0 = p->rank * nyl;
+    PM_LAUNCH(cols_fused, nyl * (H / kCols) + nyl / kCols, kThreads, smem_cols, st, ca);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+template <int N>
+int slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, float *phi, cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const int nzl = p->nzl, nyl = N / p->nranks;
+    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
+    auto rows_inv = k_fft_rows<N, false>;
+    auto cols_inv = k_fft_cols<N, COL_INV>;
+    PM_CUDA(cudaFuncSetAttribute(rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    PM_CUDA(cudaFuncSetAttribute(cols_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    ColArgs ca;
+    ca.main = p->spec;
+    ca.side = p->spec + (size_t)nzl * N * H;
+    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
+    ca.scale = 0.f; ca.axis = 1; ca.nyl = nyl; ca.y0 = p->rank * nyl;
+    const int grid = p->sm_count * 8;
+    PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_main, ca.main, nzl, N, H, nyl);
+    PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_side, ca.side, nzl, N, 1, nyl);
+    PM_LAUNCH(cols_inv, nzl * (H / kCols), kThreads, smem_cols, st, ca);
+    PM_LAUNCH(rows_inv, nzl * N / kCols, kThreads, smem_rows, st,
+              reinterpret_cast<const float2 *>(ca.main), reinterpret_cast<float2 *>(phi),
+              (const float2 *)p->tw);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -694,4 +794,33 @@ int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, fl
         case 1024: return poisson_launch<1024>(p, rho, a, omega_m0, phi, st);
     }
     return PM_ERR_UNSUPPORTED;
+}
+
+#define PM_FFT_DISPATCH(fn, ...)                              \
+    switch (p->nc) {                                          \
+        case 32: return fn<32>(__VA_ARGS__);                  \
+        case 64: return fn<64>(__VA_ARGS__);                  \
+        case 128: return fn<128>(__VA_ARGS__);                \
+        case 256: return fn<256>(__VA_ARGS__);                \
+        case 512: return fn<512>(__VA_ARGS__);                \
+        case 1024: return fn<1024>(__VA_ARGS__);              \
+    }                                                         \
+    return PM_ERR_UNSUPPORTED
+
+int pm_k_fft_slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_side,
+                          cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_forward, p, rho, send_main, send_side, st);
+}
+
+int pm_k_fft_slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0,
+                    cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_z, p, main_t, side_t, a, omega_m0, st);
+}
+
+int pm_k_fft_slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, float *phi,
+                          cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_inverse, p, back_main, back_side, phi, st);
 }

@@ -43,7 +43,11 @@ struct pm_plan {
     int64_t np_cap;   // particle capacity
     int device;
     int sm_count;
-    int key_bits;     // ceil(log2(nc^3))
+    int key_bits;     // bits of the largest cell key (+ the DEAD key in slab mode)
+
+    // slab decomposition along array axis 0 (z): this rank owns planes [z0, z0 + nzl)
+    int rank, nranks, nzl, z0;
+    bool slab;
 
     char *ws;         // one workspace allocation; everything below points into it
     size_t ws_bytes;
@@ -72,10 +76,19 @@ struct pm_plan {
     float *rpos[2], *rvel[2];
     uint32_t *rid[2];     // original index of the particle in each slot
     int rcur;
-    int64_t rnp;
+    int64_t rnp;          // live particles in set rcur
+    int64_t rstride;      // distance between the x, y, z rows of the resident sets (= np_cap)
     bool rkeys_valid;     // p->keys already holds the keys of set rcur (written by the last gather)
     cudaStream_t s_main, s_up, s_down;
     cudaEvent_t ev_a, ev_b, ev_c;
+
+    // slab-mode scratch (nranks > 1, or a 1-rank slab plan used to test the slab kernels)
+    float2 *tbuf[2];        // all-to-all staging: [nranks][nzl][nyl][nc/2] (+ side [nranks][nzl][nyl])
+    uint32_t *leave_cnt;    // [nranks] particles leaving to each rank (written by the gather kernel)
+    uint32_t *leave_slot;   // [nranks][leave_cap] their storage slots
+    int64_t leave_cap;
+    float *mig_send, *mig_recv;  // [nranks*leave_cap][7] packed (x,y,z,vx,vy,vz,id) records
+    int64_t rtotal;         // entries of the current buffer set incl. dead (left) and arrived ones
 
     // optional per-stage timing of pm_step (pm_plan_profile_begin/read)
     cudaEvent_t *prof_ev;   // prof_cap * (PM_NUM_STAGES + 1) events
@@ -93,17 +106,21 @@ static inline cudaStream_t pm_cu(pm_stream_t s) { return reinterpret_cast<cudaSt
 
 // pm_particles.cu
 size_t pm_sort_temp_bytes(int64_t np, int key_bits);
-int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, uint32_t *keys, uint32_t *order,
-                   cudaStream_t st);
+int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uint32_t *keys,
+                   uint32_t *order, cudaStream_t st);
 int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st);
 int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st);
-int pm_k_deposit(pm_plan *p, const float *pos, int64_t np, double mass, float *rho,
+int pm_k_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
                  cudaStream_t st);
 int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const float *phi,
                            double a_val, double f_a1, double da, float *acc, cudaStream_t st);
 int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
                                     double da, cudaStream_t st);
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
+// slab mode (pm_slab.cu / pm_particles.cu)
+int pm_k_deposit_slab(pm_plan *p, const float *pos, double mass, float *rho, cudaStream_t st);
+int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, double f_a1, double da,
+                                cudaStream_t st);
 int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st);
 
 // pm_fft.cu
@@ -111,9 +128,24 @@ bool pm_fft_supported(int nc);
 int pm_k_fft_tables(pm_plan *p);
 int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                      cudaStream_t st);
+// slab pieces of the same transform: local planes (rows + y pass + pack), z pass on the
+// transposed layout, and the way back
+int pm_k_fft_slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_side,
+                          cudaStream_t st);
+int pm_k_fft_slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0,
+                    cudaStream_t st);
+int pm_k_fft_slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, float *phi,
+                          cudaStream_t st);
 
 // pm_poisson.cu
 int pm_k_sin2_table(pm_plan *p);
 int pm_k_fourier_grid(pm_plan *p, float *fgrid, cudaStream_t st);
 int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                  cudaStream_t st);
+
+// slab helpers (pm_particles.cu)
+int pm_k_ghost_add(pm_plan *p, float *plane, const float *ghost, cudaStream_t st);
+int pm_k_migrate_pack(pm_plan *p, int dest, int64_t count, int64_t rec_offset, cudaStream_t st);
+int pm_k_migrate_unpack(pm_plan *p, int64_t n_arrive, cudaStream_t st);
+int pm_k_export(pm_plan *p, float *pos_out, float *vel_out, uint32_t *id_out, uint32_t *live_out,
+                cudaStream_t st);

@@ -32,11 +32,21 @@ __device__ __forceinline__ int pm_cell(float x, int nc)
 // Cell keys: key = (z_c*Nc + y_c)*Nc + x_c            (src/density.py:19-21,37)
 // VEC: one thread takes 4 consecutive particles of each SoA row with 128-bit loads.
 // --------------------------------------------------------------------------------------------
+// Slab mode: the key uses the plane index local to this rank's slab [z0, z0+nzl); a particle
+// outside the slab gets PM_KEY_DEAD, which sorts behind every real key.
+#define PM_KEY_DEAD 0xffffffffu
+__device__ __forceinline__ uint32_t pm_key(float x, float y, float z, int nc, int z0, int nzl)
+{
+    const int zl = pm_cell(z, nc) - z0;
+    if ((unsigned)zl >= (unsigned)nzl) return PM_KEY_DEAD;
+    return ((uint32_t)zl * nc + pm_cell(y, nc)) * nc + pm_cell(x, nc);
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_cell_keys(const float *__restrict__ px,
                                                    const float *__restrict__ py,
                                                    const float *__restrict__ pz, int64_t np, int nc,
-                                                   uint32_t *__restrict__ keys,
+                                                   int z0, int nzl, uint32_t *__restrict__ keys,
                                                    uint32_t *__restrict__ order)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,10 +57,10 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float *__restrict__ px,
         float4 y = *reinterpret_cast<const float4 *>(py + i);
         float4 z = *reinterpret_cast<const float4 *>(pz + i);
         uint4 k;
-        k.x = ((uint32_t)pm_cell(z.x, nc) * nc + pm_cell(y.x, nc)) * nc + pm_cell(x.x, nc);
-        k.y = ((uint32_t)pm_cell(z.y, nc) * nc + pm_cell(y.y, nc)) * nc + pm_cell(x.y, nc);
-        k.z = ((uint32_t)pm_cell(z.z, nc) * nc + pm_cell(y.z, nc)) * nc + pm_cell(x.z, nc);
-        k.w = ((uint32_t)pm_cell(z.w, nc) * nc + pm_cell(y.w, nc)) * nc + pm_cell(x.w, nc);
+        k.x = pm_key(x.x, y.x, z.x, nc, z0, nzl);
+        k.y = pm_key(x.y, y.y, z.y, nc, z0, nzl);
+        k.z = pm_key(x.z, y.z, z.z, nc, z0, nzl);
+        k.w = pm_key(x.w, y.w, z.w, nc, z0, nzl);
         *reinterpret_cast<uint4 *>(keys + i) = k;
         if (order) {
             uint32_t b = (uint32_t)i;
@@ -58,25 +68,25 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float *__restrict__ px,
         }
     } else {
         if (t >= np) return;
-        keys[t] = ((uint32_t)pm_cell(pz[t], nc) * nc + pm_cell(py[t], nc)) * nc + pm_cell(px[t], nc);
+        keys[t] = pm_key(px[t], py[t], pz[t], nc, z0, nzl);
         if (order) order[t] = (uint32_t)t;
     }
 }
 
-int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, uint32_t *keys, uint32_t *order,
-                   cudaStream_t st)
+int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uint32_t *keys,
+                   uint32_t *order, cudaStream_t st)
 {
     if (np == 0) return PM_OK;
-    const float *px = pos, *py = pos + np, *pz = pos + 2 * np;
-    bool vec = (np % 4 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)keys % 16 == 0) &&
+    const float *px = pos, *py = pos + stride, *pz = pos + 2 * stride;
+    bool vec = (np % 4 == 0) && (stride % 4 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)keys % 16 == 0) &&
                (!order || (uintptr_t)order % 16 == 0);
     if (vec) {
         int64_t nthr = np / 4;
         PM_LAUNCH(k_cell_keys<true>, (unsigned)((nthr + 255) / 256), 256, 0, st, px, py, pz, np,
-                  p->nc, keys, order);
+                  p->nc, p->z0, p->nzl, keys, order);
     } else {
         PM_LAUNCH(k_cell_keys<false>, (unsigned)((np + 255) / 256), 256, 0, st, px, py, pz, np,
-                  p->nc, keys, order);
+                  p->nc, p->z0, p->nzl, keys, order);
     }
     PM_CHECK_LAUNCH();
     return PM_OK;
@@ -108,21 +118,24 @@ int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st)
 // One thread per boundary j in [0, np]; it fills every row that starts at j (empty rows too).
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_row_offsets(const uint32_t *__restrict__ keys_sorted,
-                                                     int64_t np, int nc,
+                                                     int64_t np, int nc, int64_t nrows,
                                                      uint32_t *__restrict__ row_start)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j > np) return;
-    int64_t nrows = (int64_t)nc * nc;
+    // rows past the last real one (PM_KEY_DEAD entries of a slab) clamp to nrows, so
+    // row_start[nrows] is the number of live particles
     int64_t prev = (j == 0) ? -1 : (int64_t)(keys_sorted[j - 1] / (uint32_t)nc);
     int64_t cur = (j == np) ? nrows : (int64_t)(keys_sorted[j] / (uint32_t)nc);
+    if (prev > nrows) prev = nrows;
+    if (cur > nrows) cur = nrows;
     for (int64_t r = prev + 1; r <= cur; ++r) row_start[r] = (uint32_t)j;
 }
 
 int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st)
 {
     PM_LAUNCH(k_row_offsets, (unsigned)((np + 1 + 255) / 256), 256, 0, st, p->keys_sorted, np,
-              p->nc, p->row_start);
+              p->nc, (int64_t)p->nzl * p->nc, p->row_start);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -149,8 +162,12 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
                                                           const uint32_t *__restrict__ order,
                                                           const uint32_t *__restrict__ row_start,
                                                           int nc, double mass,
-                                                          float *__restrict__ rho)
+                                                          float *__restrict__ rho, int z0, int nzl,
+                                                          int slab)
 {
+    // slab != 0: this rank owns planes [z0, z0+nzl) and writes nzl+1 output planes; plane nzl is
+    // the ghost that holds the d_z share of the top plane's particles (it belongs to rank+1), and
+    // output plane 0 lacks the d_z share of rank-1's top plane until pm_k_ghost_add.  No z wrap.
     extern __shared__ double s_rows[];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,13 +178,15 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
     for (int x = lane; x < nc; x += 32) row[x] = 0.0;
     __syncwarp();
 
-    const int Zm = (Z == 0) ? nc - 1 : Z - 1;
+    const int Zm = slab ? Z - 1 : ((Z == 0) ? nc - 1 : Z - 1);
     const int ym = (y == 0) ? nc - 1 : y - 1;
 #pragma unroll 1
     for (int src = 0; src < 4; ++src) {
-        const int zs = (src & 2) ? Zm : Z;
+        const int zsl = (src & 2) ? Zm : Z;    // source plane, slab-local
+        if (slab && (zsl < 0 || zsl >= nzl)) continue;
+        const int zs = z0 + zsl;               // global cell coordinate of that plane
         const int ys = (src & 1) ? ym : y;
-        const uint32_t r = (uint32_t)zs * nc + ys;
+        const uint32_t r = (uint32_t)zsl * nc + ys;
         const uint32_t beg = row_start[r], end = row_start[r + 1];
         for (uint32_t base = beg; base < end; base += 32) {
             const uint32_t j = base + lane;
@@ -218,7 +237,8 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
 
 static const int PM_DEPOSIT_RY = 8;
 
-int pm_k_deposit(pm_plan *p, const float *pos, int64_t np, double mass, float *rho, cudaStream_t st)
+int pm_k_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
+                 cudaStream_t st)
 {
     const int nc = p->nc;
     size_t smem = (size_t)PM_DEPOSIT_RY * nc * sizeof(double);
@@ -229,11 +249,28 @@ int pm_k_deposit(pm_plan *p, const float *pos, int64_t np, double mass, float *r
         smem_set = smem;
     }
     dim3 grid((nc + PM_DEPOSIT_RY - 1) / PM_DEPOSIT_RY, nc);
-    PM_LAUNCH(k_deposit_rows<PM_DEPOSIT_RY>, grid, PM_DEPOSIT_RY * 32, smem, st, pos, pos + np,
-              pos + 2 * np, p->order_sorted, p->row_start, nc, mass, rho);
+    PM_LAUNCH(k_deposit_rows<PM_DEPOSIT_RY>, grid, PM_DEPOSIT_RY * 32, smem, st, pos, pos + stride,
+              pos + 2 * stride, p->order_sorted, p->row_start, nc, mass, rho, 0, nc, 0);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
+
+// Slab variant on the resident state: nzl+1 output planes into rho[(nzl+1)][nc][nc].
+int pm_k_deposit_slab(pm_plan *p, const float *pos, double mass, float *rho, cudaStream_t st)
+{
+    const int nc = p->nc;
+    const int64_t np = p->rstride;  // row stride of the SoA arrays
+    size_t smem = (size_t)PM_DEPOSIT_RY * nc * sizeof(double);
+    PM_CUDA(cudaFuncSetAttribute(k_deposit_rows<PM_DEPOSIT_RY>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((nc + PM_DEPOSIT_RY - 1) / PM_DEPOSIT_RY, p->nzl + 1);
+    PM_LAUNCH(k_deposit_rows<PM_DEPOSIT_RY>, grid, PM_DEPOSIT_RY * 32, smem, st, pos, pos + np,
+              pos + 2 * np, p->order_sorted, p->row_start, nc, mass, rho, p->z0, p->nzl, 1);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+
 
 // --------------------------------------------------------------------------------------------
 // Fused force gather + kick + drift (src/integrate.py:15-97), one thread per particle.
@@ -293,19 +330,31 @@ __device__ __forceinline__ void pm_push(float &x, float &vel, float s, double k_
 //               current buffers (a near-coalesced gather: the current order is last step's cell
 //               order), and writes position, velocity, id and the cell key of the NEW position to
 //               slot s of the other buffer set -- the permutation costs no pass of its own.
-template <bool PERM>
+// SLAB        : (implies PERM) phi is this rank's (nzl+3)-plane buffer whose plane 0 is global
+//               plane z0-1, so z needs no wrap; a particle whose new z cell belongs to another
+//               rank gets PM_KEY_DEAD and its slot is appended to that rank's leave list.
+struct SlabArgs {
+    int z0, nzl, rank;
+    const uint32_t *np_valid;  // live particle count (row_start[nzl*nc]) -- no host round trip
+    uint32_t *leave_cnt, *leave_slot;
+    int64_t leave_cap;
+};
+
+template <bool PERM, bool SLAB>
 __global__ void __launch_bounds__(256) k_gather_kick_drift(
     const float *pos_in, const float *vel_in,   // may alias pos_out/vel_out when !PERM
     const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ perm,
     float *pos_out, float *vel_out, uint32_t *__restrict__ id_out,
-    uint32_t *__restrict__ keys_out, int64_t np, const float *__restrict__ phi, int nc,
-    double k_kick, double da, double aa, double f_a1, float *__restrict__ acc)
+    uint32_t *__restrict__ keys_out, int64_t np, int64_t sin, int64_t sout,
+    const float *__restrict__ phi, int nc, double k_kick, double da, double aa, double f_a1,
+    float *__restrict__ acc, SlabArgs sl)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
+    if (SLAB && i >= (int64_t)*sl.np_valid) return;
     const int64_t j = PERM ? (int64_t)perm[i] : i;
-    float x = pos_in[j], y = pos_in[np + j], z = pos_in[2 * np + j];
-    float vx = vel_in[j], vy = vel_in[np + j], vz = vel_in[2 * np + j];
+    float x = pos_in[j], y = pos_in[sin + j], z = pos_in[2 * sin + j];
+    float vx = vel_in[j], vy = vel_in[sin + j], vz = vel_in[2 * sin + j];
 
     const int xc = pm_cell(x, nc), yc = pm_cell(y, nc), zc = pm_cell(z, nc);
     // weights (integrate.py:36-51): float64 products left to right, stored float32
@@ -330,8 +379,13 @@ __global__ void __launch_bounds__(256) k_gather_kick_drift(
         xo[0] = xc == 0 ? n - 1 : xc - 1; xo[1] = xc; xo[2] = a1; xo[3] = a1 + 1 == n ? 0 : a1 + 1;
         int b1 = yc + 1 == n ? 0 : yc + 1;
         yo[0] = yc == 0 ? n - 1 : yc - 1; yo[1] = yc; yo[2] = b1; yo[3] = b1 + 1 == n ? 0 : b1 + 1;
-        int c1 = zc + 1 == n ? 0 : zc + 1;
-        zo[0] = zc == 0 ? n - 1 : zc - 1; zo[1] = zc; zo[2] = c1; zo[3] = c1 + 1 == n ? 0 : c1 + 1;
+        if (SLAB) {
+            const int p0 = zc - sl.z0;   // buffer plane of global plane zc-1
+            zo[0] = p0; zo[1] = p0 + 1; zo[2] = p0 + 2; zo[3] = p0 + 3;
+        } else {
+            int c1 = zc + 1 == n ? 0 : zc + 1;
+            zo[0] = zc == 0 ? n - 1 : zc - 1; zo[1] = zc; zo[2] = c1; zo[3] = c1 + 1 == n ? 0 : c1 + 1;
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             yo[k] *= (uint32_t)n;
@@ -355,11 +409,23 @@ __global__ void __launch_bounds__(256) k_gather_kick_drift(
     pm_push(y, vy, sy, k_kick, da, aa, f_a1, nc, acc ? acc + np + i : nullptr);
     pm_push(z, vz, sz, k_kick, da, aa, f_a1, nc, acc ? acc + 2 * np + i : nullptr);
 
-    pos_out[i] = x; pos_out[np + i] = y; pos_out[2 * np + i] = z;
-    vel_out[i] = vx; vel_out[np + i] = vy; vel_out[2 * np + i] = vz;
+    pos_out[i] = x; pos_out[sout + i] = y; pos_out[2 * sout + i] = z;
+    vel_out[i] = vx; vel_out[sout + i] = vy; vel_out[2 * sout + i] = vz;
     if (PERM) {
         id_out[i] = id_in[j];
-        keys_out[i] = ((uint32_t)pm_cell(z, nc) * nc + pm_cell(y, nc)) * nc + pm_cell(x, nc);
+        if (SLAB) {
+            const int dest = pm_cell(z, nc) / sl.nzl;
+            uint32_t key = PM_KEY_DEAD;
+            if (dest == sl.rank) {
+                key = pm_key(x, y, z, nc, sl.z0, sl.nzl);
+            } else {
+                const uint32_t k = atomicAdd(sl.leave_cnt + dest, 1u);
+                if ((int64_t)k < sl.leave_cap) sl.leave_slot[(int64_t)dest * sl.leave_cap + k] = (uint32_t)i;
+            }
+            keys_out[i] = key;
+        } else {
+            keys_out[i] = pm_key(x, y, z, nc, 0, nc);
+        }
     }
 }
 
@@ -370,9 +436,10 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
     // host scalars evaluated exactly as integrate.py:94-95 does: da*f_a1, (a_val+da)**2
     const double k_kick = da * f_a1;
     const double aa = (a_val + da) * (a_val + da);
-    PM_LAUNCH(k_gather_kick_drift<false>, (unsigned)((np + 255) / 256), 256, 0, st, pos, vel,
+    auto kern = k_gather_kick_drift<false, false>;
+    PM_LAUNCH(kern, (unsigned)((np + 255) / 256), 256, 0, st, pos, vel,
               (const uint32_t *)nullptr, (const uint32_t *)nullptr, pos, vel, (uint32_t *)nullptr,
-              (uint32_t *)nullptr, np, phi, p->nc, k_kick, da, aa, f_a1, acc);
+              (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, f_a1, acc, SlabArgs());
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -387,9 +454,33 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
     const double k_kick = da * f_a1;
     const double aa = (a_val + da) * (a_val + da);
     const int c = p->rcur, o = c ^ 1;
-    PM_LAUNCH(k_gather_kick_drift<true>, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c],
+    auto kern = k_gather_kick_drift<true, false>;
+    PM_LAUNCH(kern, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c],
               p->rvel[c], p->rid[c], p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np,
-              phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr);
+              p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, SlabArgs());
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// Slab variant: launched over every entry of the current set (dead ones sort last and are cut
+// off on the device by np_valid), clears and fills the leave lists.
+int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, double f_a1, double da,
+                                cudaStream_t st)
+{
+    const int64_t np = p->rtotal;
+    PM_CUDA(cudaMemsetAsync(p->leave_cnt, 0, sizeof(uint32_t) * p->nranks, st));
+    if (np == 0) return PM_OK;
+    const double k_kick = da * f_a1;
+    const double aa = (a_val + da) * (a_val + da);
+    const int c = p->rcur, o = c ^ 1;
+    SlabArgs sl;
+    sl.z0 = p->z0; sl.nzl = p->nzl; sl.rank = p->rank;
+    sl.np_valid = p->row_start + (size_t)p->nzl * p->nc;
+    sl.leave_cnt = p->leave_cnt; sl.leave_slot = p->leave_slot; sl.leave_cap = p->leave_cap;
+    auto kern = k_gather_kick_drift<true, true>;
+    PM_LAUNCH(kern, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c], p->rvel[c], p->rid[c],
+              p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np, p->rstride, p->rstride,
+              phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, sl);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -398,7 +489,7 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
 __global__ void __launch_bounds__(256) k_unpermute(const float *__restrict__ pos_in,
                                                    const float *__restrict__ vel_in,
                                                    const uint32_t *__restrict__ id, int64_t np,
-                                                   float *__restrict__ pos_out,
+                                                   int64_t sin, float *__restrict__ pos_out,
                                                    float *__restrict__ vel_out)
 {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,8 +497,8 @@ __global__ void __launch_bounds__(256) k_unpermute(const float *__restrict__ pos
     const int64_t i = id[s];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        pos_out[d * np + i] = pos_in[d * np + s];
-        vel_out[d * np + i] = vel_in[d * np + s];
+        pos_out[d * np + i] = pos_in[d * sin + s];
+        vel_out[d * np + i] = vel_in[d * sin + s];
     }
 }
 
@@ -417,7 +508,7 @@ int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st)
     if (np == 0) return PM_OK;
     const int c = p->rcur;
     PM_LAUNCH(k_unpermute, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c], p->rvel[c],
-              p->rid[c], np, pos_out, vel_out);
+              p->rid[c], np, p->rstride, pos_out, vel_out);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -432,6 +523,127 @@ int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st)
 {
     if (n == 0) return PM_OK;
     PM_LAUNCH(k_iota, (unsigned)((n + 255) / 256), 256, 0, st, out, n);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Slab mode: ghost-plane add and particle migration (no reference counterpart).
+// --------------------------------------------------------------------------------------------
+// rho plane 0 += the ghost plane received from rank-1 (its d_z share of our bottom plane).
+__global__ void __launch_bounds__(256) k_ghost_add(float4 *__restrict__ plane,
+                                                   const float4 *__restrict__ ghost, size_t n4)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = plane[i];
+        const float4 b = ghost[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        plane[i] = a;
+    }
+}
+
+int pm_k_ghost_add(pm_plan *p, float *plane, const float *ghost, cudaStream_t st)
+{
+    const size_t n4 = (size_t)p->nc * p->nc / 4;
+    PM_LAUNCH(k_ghost_add, p->sm_count * 4, 256, 0, st, reinterpret_cast<float4 *>(plane),
+              reinterpret_cast<const float4 *>(ghost), n4);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// Leavers -> 7-float records (x, y, z, vx, vy, vz, id bits), in ascending slot order per
+// destination so that the receiver's storage order (and with it every later summation order)
+// does not depend on the atomics that built the leave lists.
+__global__ void __launch_bounds__(256) k_migrate_pack(const float *__restrict__ pos,
+                                                      const float *__restrict__ vel,
+                                                      const uint32_t *__restrict__ id, int64_t stride,
+                                                      const uint32_t *__restrict__ slots, int64_t n,
+                                                      float *__restrict__ rec)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t s = slots[i];
+    float *r = rec + i * 7;
+    r[0] = pos[s]; r[1] = pos[stride + s]; r[2] = pos[2 * stride + s];
+    r[3] = vel[s]; r[4] = vel[stride + s]; r[5] = vel[2 * stride + s];
+    r[6] = __uint_as_float(id[s]);
+}
+
+int pm_k_migrate_pack(pm_plan *p, int dest, int64_t count, int64_t rec_offset, cudaStream_t st)
+{
+    if (count == 0) return PM_OK;
+    uint32_t *sorted = p->keys_sorted;  // free between the deposit and the next sort
+    size_t bytes = p->cub_bytes;
+    PM_CUDA(cub::DeviceRadixSort::SortKeys(p->cub_tmp, bytes,
+                                           (const uint32_t *)(p->leave_slot + (size_t)dest * p->leave_cap),
+                                           sorted, count, 0, 32, st));
+    const int c = p->rcur;
+    PM_LAUNCH(k_migrate_pack, (unsigned)((count + 255) / 256), 256, 0, st, p->rpos[c], p->rvel[c],
+              p->rid[c], p->rstride, sorted, count, p->mig_send + rec_offset * 7);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// Arrivals are appended behind the current entries; their keys are formed here so the next
+// sort files them into cell order together with everything else.
+__global__ void __launch_bounds__(256) k_migrate_unpack(const float *__restrict__ rec, int64_t n,
+                                                        float *__restrict__ pos,
+                                                        float *__restrict__ vel,
+                                                        uint32_t *__restrict__ id,
+                                                        uint32_t *__restrict__ keys, int64_t stride,
+                                                        int64_t first, int nc, int z0, int nzl)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *r = rec + i * 7;
+    const int64_t s = first + i;
+    pos[s] = r[0]; pos[stride + s] = r[1]; pos[2 * stride + s] = r[2];
+    vel[s] = r[3]; vel[stride + s] = r[4]; vel[2 * stride + s] = r[5];
+    id[s] = __float_as_uint(r[6]);
+    keys[s] = pm_key(r[0], r[1], r[2], nc, z0, nzl);
+}
+
+int pm_k_migrate_unpack(pm_plan *p, int64_t n_arrive, cudaStream_t st)
+{
+    if (n_arrive == 0) return PM_OK;
+    const int c = p->rcur;
+    PM_LAUNCH(k_migrate_unpack, (unsigned)((n_arrive + 255) / 256), 256, 0, st, p->mig_recv, n_arrive,
+              p->rpos[c], p->rvel[c], p->rid[c], p->keys, p->rstride, p->rtotal, p->nc, p->z0, p->nzl);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// live particles of the current set, storage order, dense [3][n] rows
+__global__ void __launch_bounds__(256) k_export(const float *__restrict__ pos,
+                                                const float *__restrict__ vel,
+                                                const uint32_t *__restrict__ id,
+                                                const uint32_t *__restrict__ keys, int64_t stride,
+                                                int64_t n, float *__restrict__ pos_out,
+                                                float *__restrict__ vel_out,
+                                                uint32_t *__restrict__ id_out,
+                                                uint32_t *__restrict__ live_out)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        pos_out[d * n + s] = pos[d * stride + s];
+        vel_out[d * n + s] = vel[d * stride + s];
+    }
+    id_out[s] = id[s];
+    live_out[s] = keys ? (keys[s] != PM_KEY_DEAD) : 1u;
+}
+
+int pm_k_export(pm_plan *p, float *pos_out, float *vel_out, uint32_t *id_out, uint32_t *live_out,
+                cudaStream_t st)
+{
+    const int64_t n = p->rtotal;
+    if (n == 0) return PM_OK;
+    const int c = p->rcur;
+    PM_LAUNCH(k_export, (unsigned)((n + 255) / 256), 256, 0, st, p->rpos[c], p->rvel[c], p->rid[c],
+              p->rkeys_valid ? p->keys : (const uint32_t *)nullptr, p->rstride, n, pos_out, vel_out,
+              id_out, live_out);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }

@@ -1,0 +1,326 @@
+"""Slab-decomposed particle-mesh step for 2/4/8 GPUs of one box.
+
+The reference is single-process; nothing here has a reference counterpart except the physics,
+which must equal the single-GPU step.  Layout of the work:
+
+  * rank r owns mesh planes [r*Nc/P, (r+1)*Nc/P) along array axis 0 (the reference's z =
+    positions[2], density.py:14,21,37) and the particles whose z cell lies in them
+    (`slab_of_particles`: slab = (int(floor(z)) mod Nc) // (Nc/P), bit-exact incl. SURVEY Q4);
+  * all computation is in libpmstep.so (pm_slab_* entry points, csrc/pm_slab.cu);
+  * this module only sequences those calls and moves the plan's buffers between ranks through a
+    `Comm`: `DistComm` = torch.distributed (NCCL on GPUs; send/recv for the ghost planes,
+    all_to_all_single around the pack/unpack transposes, all_to_all_single with split sizes for
+    migrating particles), `LocalComm` = all P ranks inside one process on one GPU, exchanges by
+    tensor copies -- the single-GPU rank loop the tests use to check every slab kernel against the
+    plain single-GPU step.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+try:
+    from . import _runtime as rt
+    from .cosmology import f
+except ImportError:  # flat layout
+    import _runtime as rt
+    from cosmology import f
+
+BUF = dict(RHO=0, RHO_GHOST_SEND=1, RHO_GHOST_RECV=2, FFT_SEND_MAIN=3, FFT_SEND_SIDE=4,
+           FFT_RECV_MAIN=5, FFT_RECV_SIDE=6, PHI=7, PHI_LO_SEND=8, PHI_HI_SEND=9, PHI_LO_RECV=10,
+           PHI_HI_RECV=11, MIG_SEND=12, MIG_RECV=13, LEAVE_COUNTS=14)
+
+
+class _RawCudaBuffer:
+    """Zero-copy view of plan-owned device memory for torch (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes, owner):
+        self._owner = owner  # keep the plan alive
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def slab_of_particles(pos_z, n_cells: int, nranks: int):
+    """Owner rank of each particle from its z coordinate (NumPy array or tensor, float32):
+    (int(floor(z)) mod Nc) // (Nc/P) -- the cell index rule of density.py:21."""
+    nzl = n_cells // nranks
+    if isinstance(pos_z, torch.Tensor):
+        c = torch.remainder(torch.floor(pos_z).to(torch.int64), n_cells)
+        return (c // nzl).to(torch.int32)
+    c = np.floor(pos_z).astype(np.int64) % n_cells
+    return (c // nzl).astype(np.int32)
+
+
+class SlabRank:
+    """One rank's plan and the views of its exchange buffers."""
+
+    def __init__(self, n_cells: int, np_capacity: int, device: int, rank: int, nranks: int):
+        self.n_cells, self.rank, self.nranks, self.device = int(n_cells), int(rank), int(nranks), int(device)
+        self.nzl = self.n_cells // self.nranks
+        self.np_capacity = int(np_capacity)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_plan_create_slab(ctypes.byref(h), self.n_cells, self.np_capacity,
+                                                  self.device, self.rank, self.nranks),
+                     f"pm_plan_create_slab(n_cells={n_cells}, np={np_capacity}, rank={rank}/{nranks})")
+        self.handle = h
+        self.buf = {}
+        n, nzl, nyl, hh, P = self.n_cells, self.nzl, self.nzl, self.n_cells // 2, self.nranks
+        shapes = dict(RHO=(torch.float32, (nzl, n, n)), RHO_GHOST_SEND=(torch.float32, (n, n)),
+                      RHO_GHOST_RECV=(torch.float32, (n, n)),
+                      FFT_SEND_MAIN=(torch.float32, (P, nzl * nyl * hh * 2)),
+                      FFT_SEND_SIDE=(torch.float32, (P, nzl * nyl * 2)),
+                      FFT_RECV_MAIN=(torch.float32, (P, nzl * nyl * hh * 2)),
+                      FFT_RECV_SIDE=(torch.float32, (P, nzl * nyl * 2)),
+                      PHI=(torch.float32, (nzl, n, n)), PHI_LO_SEND=(torch.float32, (2, n, n)),
+                      PHI_HI_SEND=(torch.float32, (n, n)), PHI_LO_RECV=(torch.float32, (n, n)),
+                      PHI_HI_RECV=(torch.float32, (2, n, n)), MIG_SEND=(torch.float32, (-1, 7)),
+                      MIG_RECV=(torch.float32, (-1, 7)), LEAVE_COUNTS=(torch.int32, (P,)))
+        for name, which in BUF.items():
+            ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+            rt.check(rt.lib().pm_slab_buffer(self.handle, which, ctypes.byref(ptr), ctypes.byref(nbytes)),
+                     "pm_slab_buffer")
+            raw = torch.as_tensor(_RawCudaBuffer(ptr.value, nbytes.value, self), device=f"cuda:{self.device}")
+            dtype, shape = shapes[name]
+            self.buf[name] = raw.view(dtype).view(*shape)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.buf = {}
+            rt.lib().pm_plan_destroy(self.handle)
+            self.handle = None
+
+    def _call(self, fn, *args):
+        with torch.cuda.device(self.device):
+            rt.check(getattr(rt.lib(), fn)(self.handle, *args, rt.stream_ptr(self.device)), fn)
+
+    # -- state -------------------------------------------------------------------------------
+    def load(self, pos, vel, ids):
+        rt.check_dev_f32(pos, name="positions")
+        rt.check_dev_f32(vel, tuple(pos.shape), "velocities")
+        ids = ids.to(torch.int32).contiguous()
+        self._call("pm_slab_load", pos.data_ptr(), vel.data_ptr(), ids.data_ptr(), pos.shape[1])
+
+    @property
+    def count(self):
+        return int(rt.lib().pm_slab_count(self.handle))
+
+    def export(self):
+        """(pos[3,n], vel[3,n], ids[n]) of the live particles, storage order."""
+        n = int(rt.lib().pm_slab_entries(self.handle))
+        dev = f"cuda:{self.device}"
+        pos = torch.empty((3, n), dtype=torch.float32, device=dev)
+        vel = torch.empty_like(pos)
+        ids = torch.empty(n, dtype=torch.int32, device=dev)
+        live = torch.empty(n, dtype=torch.int32, device=dev)
+        self._call("pm_slab_export", pos.data_ptr(), vel.data_ptr(), ids.data_ptr(), live.data_ptr())
+        keep = live != 0
+        return pos[:, keep], vel[:, keep], ids[keep]
+
+    # -- compute phases ------------------------------------------------------------------------
+    def deposit(self, mass):
+        self._call("pm_slab_deposit", float(mass))
+
+    def ghost_add(self):
+        self._call("pm_slab_ghost_add")
+
+    def fft_forward(self):
+        self._call("pm_slab_fft_forward")
+
+    def fft_z(self, a, omega_m0):
+        self._call("pm_slab_fft_z", float(a), float(omega_m0))
+
+    def fft_inverse(self):
+        self._call("pm_slab_fft_inverse")
+
+    def gather(self, a, f_a1, da):
+        self._call("pm_slab_gather", float(a), float(f_a1), float(da))
+
+    def migrate_pack(self, counts):
+        arr = (ctypes.c_int64 * self.nranks)(*[int(c) for c in counts])
+        self._call("pm_slab_migrate_pack", arr)
+
+    def migrate_unpack(self, n_arrive, n_leave):
+        self._call("pm_slab_migrate_unpack", int(n_arrive), int(n_leave))
+
+
+# -------------------------------------------------------------------------------------------------
+# communication back ends
+# -------------------------------------------------------------------------------------------------
+class LocalComm:
+    """All P ranks live in this process (one GPU): exchanges are copies.  Test harness."""
+
+    def __init__(self, nranks):
+        self.nranks = nranks
+        self.local_ranks = list(range(nranks))
+
+    def shift(self, send, recv, direction):
+        P = self.nranks
+        for i in range(P):
+            recv[(i + direction) % P].copy_(send[i])
+
+    def all_to_all(self, send, recv):
+        P = self.nranks
+        staged = [s.clone() for s in send]  # send and recv may alias across calls
+        for i in range(P):
+            for j in range(P):
+                recv[j][i].copy_(staged[i][j])
+
+    def exchange_counts(self, counts):
+        P = self.nranks
+        return [[int(counts[src][dst]) for src in range(P)] for dst in range(P)]
+
+    def all_to_all_v(self, send, send_counts, recv, recv_counts):
+        P = self.nranks
+        off_s = [np.concatenate([[0], np.cumsum(c)]) for c in send_counts]
+        off_r = [np.concatenate([[0], np.cumsum(c)]) for c in recv_counts]
+        for src in range(P):
+            for dst in range(P):
+                n = int(send_counts[src][dst])
+                if n:
+                    recv[dst][off_r[dst][src]:off_r[dst][src] + n].copy_(
+                        send[src][off_s[src][dst]:off_s[src][dst] + n])
+
+
+class DistComm:
+    """One rank per process over torch.distributed (NCCL on GPUs, gloo on CPU for the tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.nranks = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.local_ranks = [self.rank]
+        self._count_device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+
+    def shift(self, send, recv, direction):
+        P, r, dist = self.nranks, self.rank, self.dist
+        if P == 1:
+            recv[0].copy_(send[0])
+            return
+        ops = [dist.P2POp(dist.isend, send[0], (r + direction) % P, self.group),
+               dist.P2POp(dist.irecv, recv[0], (r - direction) % P, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def all_to_all(self, send, recv):
+        if self.nranks == 1:
+            recv[0].copy_(send[0])
+            return
+        self.dist.all_to_all_single(recv[0].view(-1), send[0].view(-1), group=self.group)
+
+    def exchange_counts(self, counts):
+        c = torch.tensor([int(x) for x in counts[0]], dtype=torch.int64, device=self._count_device)
+        out = torch.empty_like(c)
+        if self.nranks == 1:
+            out.copy_(c)
+        else:
+            self.dist.all_to_all_single(out, c, group=self.group)
+        return [out.tolist()]
+
+    _count_device = "cpu"
+
+    def all_to_all_v(self, send, send_counts, recv, recv_counts):
+        sc, rc = [int(x) for x in send_counts[0]], [int(x) for x in recv_counts[0]]
+        ns, nr = sum(sc), sum(rc)
+        if self.nranks == 1:
+            recv[0][:nr].copy_(send[0][:ns])
+            return
+        width = send[0].shape[1]
+        self.dist.all_to_all_single(recv[0][:nr].reshape(-1), send[0][:ns].reshape(-1),
+                                    output_split_sizes=[c * width for c in rc],
+                                    input_split_sizes=[c * width for c in sc], group=self.group)
+
+
+# -------------------------------------------------------------------------------------------------
+# the step
+# -------------------------------------------------------------------------------------------------
+def slab_step(ranks, comm, a, da, mass=None, cfg=None):
+    """One body of the loop src/pmesh.py:60-61 across the slabs.  `ranks`: the SlabRank objects
+    of comm.local_ranks (one for DistComm, all P for LocalComm)."""
+    cfg = cfg or rt.config()
+    if mass is None:
+        mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3          # src/pmesh.py:28
+    f_a1 = f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])   # src/integrate.py:12
+    B = lambda name: [r.buf[name] for r in ranks]    # noqa: E731
+
+    for r in ranks:
+        r.deposit(mass)
+    comm.shift(B("RHO_GHOST_SEND"), B("RHO_GHOST_RECV"), +1)
+    for r in ranks:
+        r.ghost_add()
+        r.fft_forward()
+    comm.all_to_all(B("FFT_SEND_MAIN"), B("FFT_RECV_MAIN"))
+    comm.all_to_all(B("FFT_SEND_SIDE"), B("FFT_RECV_SIDE"))
+    for r in ranks:
+        r.fft_z(a, cfg.OMEGA_M0)
+    comm.all_to_all(B("FFT_RECV_MAIN"), B("FFT_SEND_MAIN"))
+    comm.all_to_all(B("FFT_RECV_SIDE"), B("FFT_SEND_SIDE"))
+    for r in ranks:
+        r.fft_inverse()
+    comm.shift(B("PHI_HI_SEND"), B("PHI_LO_RECV"), +1)    # my last plane is rank+1's plane z0-1
+    comm.shift(B("PHI_LO_SEND"), B("PHI_HI_RECV"), -1)    # my first two planes close rank-1's stencil
+    for r in ranks:
+        r.gather(a, f_a1, da)
+    # migration: one small device->host read per step (the leave counts size the messages)
+    send_counts = [r.buf["LEAVE_COUNTS"].tolist() for r in ranks]
+    recv_counts = comm.exchange_counts(send_counts)
+    for r, sc in zip(ranks, send_counts):
+        r.migrate_pack(sc)
+    comm.all_to_all_v(B("MIG_SEND"), send_counts, B("MIG_RECV"), recv_counts)
+    for r, sc, rc in zip(ranks, send_counts, recv_counts):
+        r.migrate_unpack(sum(rc), sum(sc))
+
+
+def make_ranks(n_cells, pos, vel, comm, device=None, slack=1.25, ids=None):
+    """Create the SlabRank(s) of this process and load their share of the particles.
+    pos/vel: the FULL particle set (CUDA tensors, original order) -- every process passes the
+    same arrays (tests, bench); ids default to the original particle index."""
+    P = comm.nranks
+    dev = torch.cuda.current_device() if device is None else device
+    npart = pos.shape[1]
+    owner = slab_of_particles(pos[2], n_cells, P)
+    if ids is None:
+        ids = torch.arange(npart, dtype=torch.int32, device=pos.device)
+    cap = int(npart / P * slack) + 4096
+    out = []
+    for r in comm.local_ranks:
+        sel = owner == r
+        sr = SlabRank(n_cells, max(cap, int(sel.sum().item()) + 4096), dev, r, P)
+        sr.load(pos[:, sel].contiguous(), vel[:, sel].contiguous(), ids[sel].contiguous())
+        out.append(sr)
+    return out
+
+
+def collect(ranks, comm, npart):
+    """Gather every rank's particles back into original particle order (tests / snapshots).
+    LocalComm only needs concatenation; DistComm uses all_gather of padded buffers."""
+    parts = [r.export() for r in ranks]
+    dev = parts[0][0].device
+    pos = torch.empty((3, npart), dtype=torch.float32, device=dev)
+    vel = torch.empty_like(pos)
+    if isinstance(comm, LocalComm):
+        for p, v, i in parts:
+            pos[:, i.long()] = p
+            vel[:, i.long()] = v
+        return pos, vel
+    dist = comm.dist
+    p, v, i = parts[0]
+    n = torch.tensor([p.shape[1]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(comm.nranks)]
+    dist.all_gather(counts, n, group=comm.group)
+    nmax = int(max(c.item() for c in counts))
+    pad = torch.zeros((7, nmax), dtype=torch.float32, device=dev)
+    pad[0:3, :p.shape[1]], pad[3:6, :p.shape[1]] = p, v
+    pad[6, :p.shape[1]] = i.view(torch.float32)
+    bufs = [torch.empty_like(pad) for _ in range(comm.nranks)]
+    dist.all_gather(bufs, pad, group=comm.group)
+    for b, c in zip(bufs, counts):
+        k = int(c.item())
+        idx = b[6, :k].contiguous().view(torch.int32).long()
+        pos[:, idx] = b[0:3, :k]
+        vel[:, idx] = b[3:6, :k]
+    return pos, vel

@@ -155,6 +155,49 @@ PM_API int pm_particles_order(pm_plan *plan, uint32_t *ids_d, pm_stream_t stream
 PM_API int64_t pm_particles_count(const pm_plan *plan);
 
 /*
+ * Slab-decomposed step for 2/4/8 GPUs of one box (no reference counterpart: the reference is
+ * single-process; design in SURVEY.md 8e / DESIGN.md 6).  One plan per rank; rank r owns mesh planes
+ * [r*Nc/P, (r+1)*Nc/P) along array axis 0 and the particles whose z cell lies in them.  The entry
+ * points only compute; the caller moves the buffers pm_slab_buffer() names between ranks (NCCL
+ * send/recv for ghost planes, NCCL all-to-all around the hand-written pack/unpack transposes of
+ * the distributed FFT, all-to-all-v for migrating particles).  Order of calls: see csrc/pm_slab.cu.
+ * Requires a power-of-two mesh with Nc/P a multiple of 16.
+ */
+#define PM_BUF_RHO 0             /* float[nzl][Nc][Nc]   density of the owned planes              */
+#define PM_BUF_RHO_GHOST_SEND 1  /* float[Nc][Nc]        plane nzl of the deposit -> rank+1        */
+#define PM_BUF_RHO_GHOST_RECV 2  /* float[Nc][Nc]        <- rank-1, added by pm_slab_ghost_add     */
+#define PM_BUF_FFT_SEND_MAIN 3   /* float2[P][nzl][nyl][Nc/2]  packed spectrum, chunk s -> rank s  */
+#define PM_BUF_FFT_SEND_SIDE 4   /* float2[P][nzl][nyl]        packed Nyquist plane                */
+#define PM_BUF_FFT_RECV_MAIN 5   /* float2[Nc][nyl][Nc/2]      transposed spectrum (z pass)        */
+#define PM_BUF_FFT_RECV_SIDE 6   /* float2[Nc][nyl]                                               */
+#define PM_BUF_PHI 7             /* float[nzl][Nc][Nc]   potential of the owned planes            */
+#define PM_BUF_PHI_LO_SEND 8     /* float[2][Nc][Nc]     first two owned planes -> rank-1          */
+#define PM_BUF_PHI_HI_SEND 9     /* float[Nc][Nc]        last owned plane -> rank+1                */
+#define PM_BUF_PHI_LO_RECV 10    /* float[Nc][Nc]        ghost plane z0-1 <- rank-1's HI_SEND      */
+#define PM_BUF_PHI_HI_RECV 11    /* float[2][Nc][Nc]     ghost planes z0+nzl, +1 <- rank+1's LO_SEND */
+#define PM_BUF_MIG_SEND 12       /* float[.][7]          (x,y,z,vx,vy,vz,id) of leavers, by dest   */
+#define PM_BUF_MIG_RECV 13       /* float[.][7]          arrivals                                  */
+#define PM_BUF_LEAVE_COUNTS 14   /* uint32[P]            leavers per destination (after gather)    */
+PM_API int pm_plan_create_slab(pm_plan **plan, int n_cells, int64_t np_capacity, int device, int rank,
+                               int nranks);
+PM_API int pm_slab_buffer(pm_plan *plan, int which, void **ptr, size_t *bytes);
+PM_API int pm_slab_load(pm_plan *plan, const float *pos_d, const float *vel_d, const uint32_t *ids_d,
+                        int64_t np, pm_stream_t stream);
+PM_API int64_t pm_slab_count(const pm_plan *plan);   /* live particles owned by this rank */
+PM_API int64_t pm_slab_entries(const pm_plan *plan); /* storage entries incl. departed ones */
+PM_API int pm_slab_deposit(pm_plan *plan, double mass, pm_stream_t stream);
+PM_API int pm_slab_ghost_add(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_fft_forward(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_fft_z(pm_plan *plan, double a, double omega_m0, pm_stream_t stream);
+PM_API int pm_slab_fft_inverse(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_gather(pm_plan *plan, double a, double f_a1, double da, pm_stream_t stream);
+PM_API int pm_slab_migrate_pack(pm_plan *plan, const int64_t *counts_h, pm_stream_t stream);
+PM_API int pm_slab_migrate_unpack(pm_plan *plan, int64_t n_arrive, int64_t n_leave, pm_stream_t stream);
+/* live_d[s] = 0 for entries whose particle has left; rows are dense [3][pm_slab_entries()] */
+PM_API int pm_slab_export(pm_plan *plan, float *pos_d, float *vel_d, uint32_t *ids_d, uint32_t *live_d,
+                          pm_stream_t stream);
+
+/*
  * The same loop body for a caller that keeps its state in host memory like the reference does
  * (NumPy arrays): uploads pos_h/vel_h, runs pm_step, downloads the updated pos_h/vel_h (and
  * rho_h when not NULL).  Pinned host buffers make the copies asynchronous and overlapped;

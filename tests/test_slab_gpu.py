@@ -1,0 +1,110 @@
+"""Slab-decomposed step checked on ONE GPU by looping the ranks: P plans on the
+same device, exchanges by tensor copies (slab.LocalComm).  The kernels, buffers and call sequence
+are exactly those of the multi-process NCCL run; only the transport differs."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pm():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import cosmological_particle_mesh_simulation_b200 as pm
+    yield pm
+    pm.set_config(None)
+    pm.release_plans()
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm())
+
+
+def rel_periodic(a, b, n):
+    d = torch.remainder(a.double() - b.double() + n / 2, n) - n / 2
+    return float(d.norm() / b.double().norm())
+
+
+def test_particle_to_slab_assignment_bit_exact(pm):
+    n, P = 64, 4
+    pos, _ = O.lattice_ic(16, n, seed=3)
+    pos[2, :5] = [64.0, 0.0, 15.999999, 16.0, 63.99999]       # Q4: z == Nc belongs to plane 0 -> rank 0
+    want = (np.floor(pos[2]).astype(np.int64) % n) // (n // P)
+    got_np = pm.slab.slab_of_particles(pos[2], n, P)
+    got_t = pm.slab.slab_of_particles(torch.from_numpy(pos[2]).cuda(), n, P).cpu().numpy()
+    assert np.array_equal(got_np, want) and np.array_equal(got_t, want)
+    assert want[0] == 0 and want[2] == 0 and want[3] == 1 and want[4] == 3
+    keys = O.cell_keys(pos, O.Config(N_CELLS=n))
+    assert np.array_equal(want, (keys // (n * n)) // (n // P))  # same rule as the cell key
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+@pytest.mark.parametrize("n_parts,n_cells", [(32, 64), (64, 128)])
+def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells):
+    cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
+    pm.set_config(cfg)
+    if n_cells // P < 16:
+        pytest.skip("slab thinner than one FFT column tile")
+    pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=11, vel_rms=0.3)
+    # a few particles parked right at slab boundaries and at z == Nc so that migration, the ghost
+    # planes and Q4 are exercised from step 1
+    nzl = n_cells // P
+    pos_h[2, :4] = [n_cells, nzl - 1e-3, nzl + 1e-3, n_cells - 1e-3]
+    vel_h[2, :4] = [0.5, 2.0, -2.0, 3.0]
+    pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
+    npart = pos.shape[1]
+    mass = (n_cells / n_parts) ** 3
+
+    comm = pm.slab.LocalComm(P)
+    ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
+    assert sum(r.count for r in ranks) == npart
+    ref_p, ref_v = pos.clone(), vel.clone()
+    moved = 0
+    a, da = 0.3, 0.0099
+    for step in range(6):
+        rho_ref = torch.empty((n_cells,) * 3, device="cuda")
+        pm.step(ref_p, ref_v, a, da, mass=mass, rho_out=rho_ref)
+        before = [r.count for r in ranks]
+        pm.slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg)
+        moved += sum(abs(x - r.count) for x, r in zip(before, ranks))
+        assert sum(r.count for r in ranks) == npart            # nobody lost in migration
+        rho = torch.cat([r.buf["RHO"] for r in ranks])          # density the step just used
+        phi = torch.cat([r.buf["PHI"] for r in ranks])
+        assert rel(rho, rho_ref) <= 1e-6, f"density step {step}"
+        got_p, got_v = pm.slab.collect(ranks, comm, npart)
+        assert rel_periodic(got_p, ref_p, n_cells) <= 1e-6, f"positions step {step}"
+        assert rel(got_v, ref_v) <= 1e-5, f"velocities step {step}"
+        # every particle sits on the rank that owns its z cell
+        for r in ranks:
+            p, _, _ = r.export()
+            own = pm.slab.slab_of_particles(p[2], n_cells, P)
+            assert bool((own == r.rank).all())
+        a += da
+    assert torch.isfinite(phi).all()
+    for r in ranks:
+        r.close()
+
+
+def test_slab_run_is_deterministic(pm):
+    n_parts, n_cells, P = 32, 64, 2
+    cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
+    pm.set_config(cfg)
+    pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=2, vel_rms=1.0)
+    outs = []
+    for _ in range(2):
+        pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
+        comm = pm.slab.LocalComm(P)
+        ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
+        for s in range(4):
+            pm.slab.slab_step(ranks, comm, 0.5 + 0.0099 * s, 0.0099, mass=8.0, cfg=cfg)
+        outs.append(pm.slab.collect(ranks, comm, pos.shape[1]))
+        for r in ranks:
+            r.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
