@@ -203,7 +203,134 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_slab(args, rank, world, local_rank):
+    """N > 1: the 256^3/512^3 step slab-decomposed over the GPUs of the box (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+    import cosmological_particle_mesh_simulation_b200 as pm
+    slab = pm.slab
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
+    n_parts, n_cells = args.n_parts, args.n_cells
+    cfg = cfg_namespace(n_parts, n_cells)
+    pm.set_config(cfg)
+    npart = n_parts ** 3
+    mass = (n_cells / n_parts) ** 3
+    pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
+    comm = slab.DistComm()
+    pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
+    ranks = slab.make_ranks(n_cells, pos, vel, comm, device=dev)
+    del pos, vel
+    sched = pm.loop_scale_factors(cfg)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, args.warmup
+    step_i = 0
+    for _ in range(W):
+        a, da = sched[step_i % len(sched)]
+        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg)
+        step_i += 1
+    barrier()
+    sampler = ClockSampler(dev)
+    sampler.start()
+    time.sleep(0.3)
+    timer = slab.PhaseTimer()
+    launches0 = pm.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        a, da = sched[step_i % len(sched)]
+        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, timer=timer)
+        step_i += 1
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = pm.launch_count() - launches0
+    clocks = sampler.stop()
+    phases = timer.mean_ms()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=f"cuda:{dev}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = npart * K / (ms_total * 1e-3)
+
+    # e2e: the rank's particles live in pinned host memory; every step uploads them, runs the
+    # slab step and downloads the rank's (migrated) particles again
+    sr = ranks[0]
+    p, v, ids = sr.export()
+    hp, hv, hi = p.cpu().pin_memory(), v.cpu().pin_memory(), ids.cpu().pin_memory()
+    ke = max(3, min(K, 10))
+    h2d = d2h = 0
+
+    def host_step():
+        nonlocal hp, hv, hi, h2d, d2h, step_i
+        a, da = sched[step_i % len(sched)]
+        step_i += 1
+        dp = hp.to(f"cuda:{dev}", non_blocking=True)
+        dv = hv.to(f"cuda:{dev}", non_blocking=True)
+        di = hi.to(f"cuda:{dev}", non_blocking=True)
+        h2d += dp.numel() * 4 * 2 + di.numel() * 4
+        sr.load(dp.contiguous(), dv.contiguous(), di)
+        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg)
+        p, v, ids = sr.export()
+        hp, hv, hi = p.cpu().pin_memory(), v.cpu().pin_memory(), ids.cpu().pin_memory()
+        d2h += p.numel() * 4 * 2 + ids.numel() * 4
+
+    for _ in range(2):
+        host_step()
+    barrier()
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        host_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s, float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{dev}")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    e2e_value = npart * ke / float(tmax[0].item())
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        bstep = b_step_bytes(npart, n_cells)
+        nvlink_bytes = 2 * (4 * n_cells ** 3 / world) * (world - 1) / world   # per GPU per step (SURVEY 8e)
+        t_roof = (bstep / world) / (peak * 1e9) + nvlink_bytes / 900e9
+        dominant = max(phases, key=phases.get)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": value / 4.7e6, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step, BASELINE configs[1]",
+                       "n_parts": n_parts, "n_cells": n_cells,
+                       "particles": "lattice + uniform(-2,2) jitter, seed 38",
+                       "l2": "inputs larger than L2",
+                       "parallelism": f"slab decomposition along z over {world} GPUs: NCCL send/recv ghost planes, "
+                                      "all-to-all transposed FFT, all-to-all-v particle migration"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
+                    "d2h_bytes_per_step": float(t[2].item()) / ke, "steps": ke,
+                    "api": "per rank: pinned host pos+vel+ids -> pm_slab_load -> slab step -> pm_slab_export -> host"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm+nvlink", "kernel": "phase:" + dominant, "achieved": None, "peak": peak,
+                         "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                         "ms_per_launch": phases[dominant]},
+            "roofline_step": {"bound": "hbm+nvlink", "t_roof_ms": 1e3 * t_roof, "frac": 1e3 * t_roof / ms_per_step,
+                              "formula": "(60*Np+64*Nc^3)/P/hbm + 2*(4*Nc^3/P)*(P-1)/P/900e9 (SURVEY 8e, serial bound)"},
+            "phases_ms_rank0": phases,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def run_ours(args, rank, world, local_rank):
+    if world > 1:
+        return run_slab(args, rank, world, local_rank)
     import torch
     import cosmological_particle_mesh_simulation_b200 as pm
     rt = pm._runtime

@@ -238,10 +238,42 @@ class DistComm:
 # -------------------------------------------------------------------------------------------------
 # the step
 # -------------------------------------------------------------------------------------------------
-def slab_step(ranks, comm, a, da, mass=None, cfg=None):
+class PhaseTimer:
+    """CUDA-event timing of the phases of slab_step on the current stream (bench.py)."""
+    NAMES = ("deposit", "rho_ghost", "fft_local_fwd", "a2a_fwd", "fft_z", "a2a_bwd", "fft_local_inv",
+             "phi_ghost", "gather", "migrate")
+
+    def __init__(self):
+        self.records = []
+
+    def begin_step(self):
+        self.cur = [torch.cuda.Event(enable_timing=True)]
+        self.cur[0].record()
+
+    def mark(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.cur.append(e)
+
+    def end_step(self):
+        self.records.append(self.cur)
+
+    def mean_ms(self):
+        torch.cuda.synchronize()
+        out = {n: 0.0 for n in self.NAMES}
+        for rec in self.records:
+            for n, (e0, e1) in zip(self.NAMES, zip(rec[:-1], rec[1:])):
+                out[n] += e0.elapsed_time(e1) / len(self.records)
+        return out
+
+
+def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None):
     """One body of the loop src/pmesh.py:60-61 across the slabs.  `ranks`: the SlabRank objects
     of comm.local_ranks (one for DistComm, all P for LocalComm)."""
     cfg = cfg or rt.config()
+    mark = timer.mark if timer else (lambda: None)
+    if timer:
+        timer.begin_step()
     if mass is None:
         mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3          # src/pmesh.py:28
     f_a1 = f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])   # src/integrate.py:12 (SURVEY Q1)
@@ -249,22 +281,32 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None):
 
     for r in ranks:
         r.deposit(mass)
+    mark()
     comm.shift(B("RHO_GHOST_SEND"), B("RHO_GHOST_RECV"), +1)
     for r in ranks:
         r.ghost_add()
+    mark()
+    for r in ranks:
         r.fft_forward()
+    mark()
     comm.all_to_all(B("FFT_SEND_MAIN"), B("FFT_RECV_MAIN"))
     comm.all_to_all(B("FFT_SEND_SIDE"), B("FFT_RECV_SIDE"))
+    mark()
     for r in ranks:
         r.fft_z(a, cfg.OMEGA_M0)
+    mark()
     comm.all_to_all(B("FFT_RECV_MAIN"), B("FFT_SEND_MAIN"))
     comm.all_to_all(B("FFT_RECV_SIDE"), B("FFT_SEND_SIDE"))
+    mark()
     for r in ranks:
         r.fft_inverse()
+    mark()
     comm.shift(B("PHI_HI_SEND"), B("PHI_LO_RECV"), +1)    # my last plane is rank+1's plane z0-1
     comm.shift(B("PHI_LO_SEND"), B("PHI_HI_RECV"), -1)    # my first two planes close rank-1's stencil
+    mark()
     for r in ranks:
         r.gather(a, f_a1, da)
+    mark()
     # migration: one small device->host read per step (the leave counts size the messages)
     send_counts = [r.buf["LEAVE_COUNTS"].tolist() for r in ranks]
     recv_counts = comm.exchange_counts(send_counts)
@@ -273,6 +315,9 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None):
     comm.all_to_all_v(B("MIG_SEND"), send_counts, B("MIG_RECV"), recv_counts)
     for r, sc, rc in zip(ranks, send_counts, recv_counts):
         r.migrate_unpack(sum(rc), sum(sc))
+    mark()
+    if timer:
+        timer.end_step()
 
 
 def make_ranks(n_cells, pos, vel, comm, device=None, slack=1.25, ids=None):

@@ -38,7 +38,7 @@ c = comm.exchange_counts([counts[r]]); assert c[0] == rc[r], (c, rc)
 z = torch.zeros(16, 7); comm.all_to_all_v([recs[r]], [counts[r]], [z], c); assert torch.equal(z, rv[r])
 assert slab.slab_of_particles(torch.tensor([0.0, 15.9, 16.0, 32.0]), 32, 2).tolist() == [0, 0, 1, 0]
 dist.barrier(); dist.destroy_process_group()
-sys.stdout.write("rank%d-ok\n" % r); sys.stdout.flush()
+sys.stdout.write("rank" + str(r) + "-ok\n"); sys.stdout.flush()
 '''
 
 

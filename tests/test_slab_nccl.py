@@ -1,0 +1,54 @@
+"""Two-process NCCL run of the slab step against the single-GPU step (needs >= 2 GPUs; skipped on
+the one-GPU box, where tests/test_slab_gpu.py covers the same kernels through the rank loop)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import sys, types, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import cosmological_particle_mesh_simulation_b200 as pm
+from oracle import oracle as O
+local = int(__import__("os").environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda:%%d" %% local))
+n_parts, n_cells = 64, 128
+cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
+pm.set_config(cfg)
+pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=11, vel_rms=0.3)
+pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
+comm = pm.slab.DistComm()
+ranks = pm.slab.make_ranks(n_cells, pos, vel, comm, device=local)
+ref_p, ref_v = pos.clone(), vel.clone()
+a, da = 0.3, 0.0099
+for s in range(5):
+    pm.step(ref_p, ref_v, a, da, mass=8.0)
+    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg)
+    a += da
+got_p, got_v = pm.slab.collect(ranks, comm, pos.shape[1])
+d = torch.remainder(got_p.double() - ref_p.double() + n_cells / 2, n_cells) - n_cells / 2
+ep = float(d.norm() / ref_p.double().norm()); ev = float((got_v.double() - ref_v.double()).norm() / ref_v.double().norm())
+assert ep <= 1e-6 and ev <= 1e-5, (ep, ev)
+tot = torch.tensor([ranks[0].count], device="cuda"); dist.all_reduce(tot)
+assert int(tot.item()) == pos.shape[1]
+dist.barrier(); dist.destroy_process_group()
+sys.stdout.write("rank" + str(comm.rank) + "-ok %%.2e %%.2e\n" %% (ep, ev)); sys.stdout.flush()
+'''
+
+
+def test_two_rank_nccl_slab_step_matches_single_gpu(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % REPO)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("-ok") == 2, out.stdout
