@@ -30,10 +30,25 @@
 
 namespace {
 
-constexpr int kCols = 16;          // adjacent columns (contiguous in memory) per column tile
+#ifndef PM_FFT_COLS
+#define PM_FFT_COLS 16
+#endif
+#ifndef PM_FFT_CTHREADS
+#define PM_FFT_CTHREADS 256
+#endif
+constexpr int kColsC = PM_FFT_COLS;  // adjacent columns (contiguous in memory) per column tile
+template <int N>
+constexpr int kThrC = (N >= 256) ? PM_FFT_CTHREADS : 256;   // threads of a column-pass CTA
+constexpr int kCols = 16;          // x-rows per CTA of the row passes
 constexpr int kPitch = kCols + 1;  // +1: the split-off Nyquist column of the packed slot; also
                                    // keeps transposing row accesses conflict-free
-constexpr int kThreads = 256;
+#ifndef PM_FFT_THREADS
+#define PM_FFT_THREADS 256
+#endif
+// threads per CTA: PM_FFT_THREADS for the large transforms, 256 for the small ones (whose tiles
+// hold fewer butterflies than that many threads)
+template <int N>
+constexpr int kThr = (N >= 256) ? PM_FFT_THREADS : 256;
 // Column kernels: how many butterflies' worth of global loads a thread issues before it starts
 // computing (memory-level parallelism vs registers), and the CTAs/SM the register budget targets.
 #ifndef PM_FFT_BATCH
@@ -262,19 +277,19 @@ __device__ __forceinline__ void butterfly2(int u, const float2 *tw, Ld4 ld, St4 
 // shared memory as [N][16] float2 (128-byte rows: a quarter-warp's 16-byte accesses cover one row,
 // conflict-free), followed by the split-off Nyquist column [N] and the twiddle table [N].
 template <int N, int MODE>
-__global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
+__global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
 {
     extern __shared__ float2 s_tile[];
     constexpr int H = N / 2;
-    constexpr int TPR = H / kCols;      // column tiles per row of the main array
+    constexpr int TPR = H / kColsC;      // column tiles per row of the main array
     constexpr int S = fft_stages(N);
-    constexpr int CP = kCols / 2;       // column pairs
+    constexpr int CP = kColsC / 2;       // column pairs
     const int tid = threadIdx.x;
-    float2 *s_x = s_tile + N * kCols;   // extra column
+    float2 *s_x = s_tile + N * kColsC;   // extra column
     // Twiddles live in shared memory: with the carveout these tiles need, L1 is too small to keep
     // a __ldg table resident against the streaming tile traffic.  A quarter-warp reads one entry.
     float2 *s_tw = s_x + N;
-    for (int m = tid; m < N; m += kThreads) s_tw[m] = a.tw[m];
+    for (int m = tid; m < N; m += kThrC<N>) s_tw[m] = a.tw[m];
     __syncthreads();
 
     // ---- which tile ----
@@ -288,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
     bool side_tile = false;
     if (a.axis == 1) {
         const int z = t / TPR, kt = t % TPR;
-        g = a.main + (size_t)z * N * H + kt * kCols;
+        g = a.main + (size_t)z * N * H + kt * kColsC;
         gs = H;
         if (kt == 0) {
             extra = true;
@@ -297,21 +312,21 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
     } else {
         if (t < a.nyl * TPR) {
             const int yl = t / TPR, kt = t % TPR;
-            g = a.main + (size_t)yl * H + kt * kCols;
+            g = a.main + (size_t)yl * H + kt * kColsC;
             gs = (size_t)a.nyl * H;
-            col0 = kt * kCols;
+            col0 = kt * kColsC;
             if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2rev + a.y0 + yl);
         } else {
             side_tile = true;
             const int yt = t - a.nyl * TPR;
-            g = a.side + yt * kCols;
+            g = a.side + yt * kColsC;
             gs = a.nyl;
-            col0 = a.y0 + yt * kCols;
+            col0 = a.y0 + yt * kColsC;
         }
     }
 
     auto sm4 = [&](int pos, int cp) -> float4 & {
-        return *reinterpret_cast<float4 *>(s_tile + pos * kCols + 2 * cp);
+        return *reinterpret_cast<float4 *>(s_tile + pos * kColsC + 2 * cp);
     };
 
     // ---- generic stage runner over the 8 column pairs (+ the extra column) ----
@@ -322,10 +337,10 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
         constexpr int src = decltype(src_tag)::value, dst = decltype(dst_tag)::value;
         constexpr int R = fft_radix(N, ST);
         constexpr int NB = N / R;
-        constexpr int ITERS = (NB * CP + kThreads - 1) / kThreads;
+        constexpr int ITERS = (NB * CP + kThrC<N> - 1) / kThrC<N>;
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-            const int w = it * kThreads + tid;
+            const int w = it * kThrC<N> + tid;
             const int cp = w % CP, u = w / CP;
             if (w < NB * CP) {
                 auto ld = [&](int pos) -> float4 {
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
             }
         }
         if (extra) {
-            for (int u = tid; u < NB; u += kThreads) {
+            for (int u = tid; u < NB; u += kThrC<N>) {
                 auto ld = [&](int pos) -> float2 {
                     if (src == 0) return s_x[pos];
                     if (FWD) return make_float2(g[(size_t)pos * gs].y, 0.0f);  // Nyquist part of the packed slot
@@ -378,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
             // merge: packed slot = (Re DC column, Re Nyquist column); both are real up to rounding.
             // Column 1 shared the 16-byte accesses of column 0, so it is flushed here too.
             __syncthreads();
-            for (int pos = tid; pos < N; pos += kThreads) {
+            for (int pos = tid; pos < N; pos += kThrC<N>) {
                 const float4 q = sm4(pos, 0);
                 *reinterpret_cast<float4 *>(g + (size_t)pos * gs) = make_float4(q.x, s_x[pos].x, q.z, q.w);
             }
@@ -394,10 +409,10 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
             constexpr int ST = S - 1;
             constexpr int R = fft_radix(N, ST);
             constexpr int NB = N / R;
-            constexpr int ITERS = (NB * CP + kThreads - 1) / kThreads;
+            constexpr int ITERS = (NB * CP + kThrC<N> - 1) / kThrC<N>;
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) {
-                const int w = it * kThreads + tid;
+                const int w = it * kThrC<N> + tid;
                 const int cp = w % CP, pos0 = (w / CP) * R;
                 if (w < NB * CP) {
                     float2 va[R], vb[R];
@@ -444,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, PM_FFT_MINB) k_fft_cols(ColArgs a)
 // first inverse stage) is done out of place -- read everything, barrier, write to the natural
 // positions -- which keeps every shared-memory access of the kernel free of bank conflicts.
 template <int N, bool FWD>
-__global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict__ in,
+__global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__ in,
                                                        float2 *__restrict__ out,
                                                        const float2 *__restrict__ tw)
 {
@@ -453,22 +468,22 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
     constexpr int S = fft_stages(H);
     constexpr int RL = fft_radix(H, S - 1);   // radix of the last DIF stage (sub-length 1)
     constexpr int NBL = H / RL;
-    constexpr int ITL = (NBL * kCols + kThreads - 1) / kThreads;
-    constexpr int LD_IT = kCols * H / kThreads;   // tile elements per thread
+    constexpr int ITL = (NBL * kCols + kThr<N> - 1) / kThr<N>;
+    constexpr int LD_IT = kCols * H / kThr<N>;   // tile elements per thread
     const int tid = threadIdx.x;
     const size_t row0 = (size_t)blockIdx.x * kCols;
     auto sm = [&](int pos, int c) -> float2 & { return s_tile[pos * kPitch + c]; };
     float2 *s_tw = s_tile + H * kPitch;   // N-entry twiddle table (visible after the first barrier)
-    for (int m = tid; m < N; m += kThreads) s_tw[m] = tw[m];
+    for (int m = tid; m < N; m += kThr<N>) s_tw[m] = tw[m];
 
     auto run_stage = [&](auto st_tag, auto fwd_tag) {
         constexpr int ST = decltype(st_tag)::value;
         constexpr bool F = decltype(fwd_tag)::value;
         constexpr int NB = H / fft_radix(H, ST);
-        constexpr int ITERS = (NB * kCols + kThreads - 1) / kThreads;
+        constexpr int ITERS = (NB * kCols + kThr<N> - 1) / kThr<N>;
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
-            const int w = it * kThreads + tid;
+            const int w = it * kThr<N> + tid;
             const int c = w % kCols, u = w / kCols;
             if (w < NB * kCols) {
                 auto ld = [&](int pos) -> float2 { return sm(pos, c); };
@@ -484,12 +499,12 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
             float2 buf[LD_IT];
 #pragma unroll
             for (int it = 0; it < LD_IT; ++it) {
-                const int idx = it * kThreads + tid;
+                const int idx = it * kThr<N> + tid;
                 buf[it] = in[(row0 + idx / H) * H + idx % H];
             }
 #pragma unroll
             for (int it = 0; it < LD_IT; ++it) {
-                const int idx = it * kThreads + tid;
+                const int idx = it * kThr<N> + tid;
                 sm(idx % H, idx / H) = buf[it];
             }
         }
@@ -501,7 +516,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
             float2 v[ITL][RL];
 #pragma unroll
             for (int it = 0; it < ITL; ++it) {
-                const int w = it * kThreads + tid;
+                const int w = it * kThr<N> + tid;
                 const int c = w % kCols, pos0 = (w / kCols) * RL;
                 if (w < NBL * kCols) {
 #pragma unroll
@@ -512,7 +527,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
             __syncthreads();
 #pragma unroll
             for (int it = 0; it < ITL; ++it) {
-                const int w = it * kThreads + tid;
+                const int w = it * kThr<N> + tid;
                 const int c = w % kCols, pos0 = (w / kCols) * RL;
                 if (w < NBL * kCols) {
                     const int k0 = digit_unrev<H>(pos0);
@@ -524,7 +539,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
         }
 #pragma unroll 4
         for (int it = 0; it < LD_IT; ++it) {
-            const int idx = it * kThreads + tid;
+            const int idx = it * kThr<N> + tid;
             const int b = idx / H, k = idx % H;
             float2 X;
             const float2 Zk = sm(k, b);
@@ -542,7 +557,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
     } else {
 #pragma unroll 4
         for (int it = 0; it < LD_IT; ++it) {
-            const int idx = it * kThreads + tid;
+            const int idx = it * kThr<N> + tid;
             const int b = idx / H, k = idx % H;
             const float2 A = in[(row0 + b) * H + k];
             float2 Z;
@@ -562,7 +577,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
             float2 v[ITL][RL];
 #pragma unroll
             for (int it = 0; it < ITL; ++it) {
-                const int w = it * kThreads + tid;
+                const int w = it * kThr<N> + tid;
                 const int c = w % kCols, pos0 = (w / kCols) * RL;
                 if (w < NBL * kCols) {
                     const int k0 = digit_unrev<H>(pos0);
@@ -574,7 +589,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
             __syncthreads();
 #pragma unroll
             for (int it = 0; it < ITL; ++it) {
-                const int w = it * kThreads + tid;
+                const int w = it * kThr<N> + tid;
                 const int c = w % kCols, pos0 = (w / kCols) * RL;
                 if (w < NBL * kCols) {
 #pragma unroll
@@ -588,7 +603,7 @@ __global__ void __launch_bounds__(kThreads) k_fft_rows(const float2 *__restrict_
         if constexpr (S >= 2) run_stage(PM_ST(0), PM_F);
 #pragma unroll 4
         for (int it = 0; it < LD_IT; ++it) {
-            const int idx = it * kThreads + tid;
+            const int idx = it * kThr<N> + tid;
             out[(row0 + idx / H) * H + idx % H] = sm(idx % H, idx / H);
         }
     }
@@ -598,7 +613,7 @@ template <int N>
 int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
 {
     constexpr int H = N / 2;
-    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
@@ -626,24 +641,24 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     ca.nyl = N;
     ca.y0 = 0;
     const int row_ctas = N * N / kCols;
-    const int tiles = N * (H / kCols);
+    const int tiles = N * (H / kColsC);
 
     auto rows_fwd = k_fft_rows<N, true>;
     auto rows_inv = k_fft_rows<N, false>;
     auto cols_fwd = k_fft_cols<N, COL_FWD>;
     auto cols_inv = k_fft_cols<N, COL_INV>;
     auto cols_fused = k_fft_cols<N, COL_FUSED>;
-    PM_LAUNCH(rows_fwd, row_ctas, kThreads, smem_rows, st, reinterpret_cast<const float2 *>(rho),
+    PM_LAUNCH(rows_fwd, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(rho),
               ca.main, (const float2 *)p->tw);
     ca.axis = 1;
-    PM_LAUNCH(cols_fwd, tiles, kThreads, smem_cols, st, ca);
+    PM_LAUNCH(cols_fwd, tiles, kThrC<N>, smem_cols, st, ca);
     pm_prof_mark(p, PM_STAGE_R2C + 1, st);
     ca.axis = 0;
-    PM_LAUNCH(cols_fused, tiles + N / kCols, kThreads, smem_cols, st, ca);
+    PM_LAUNCH(cols_fused, tiles + N / kColsC, kThrC<N>, smem_cols, st, ca);
     pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
     ca.axis = 1;
-    PM_LAUNCH(cols_inv, tiles, kThreads, smem_cols, st, ca);
-    PM_LAUNCH(rows_inv, row_ctas, kThreads, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
+    PM_LAUNCH(cols_inv, tiles, kThrC<N>, smem_cols, st, ca);
+    PM_LAUNCH(rows_inv, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
               reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
     pm_prof_mark(p, PM_STAGE_C2R + 1, st);
     PM_CHECK_LAUNCH();
@@ -678,7 +693,7 @@ int slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_s
 {
     constexpr int H = N / 2;
     const int nzl = p->nzl, nyl = N / p->nranks;
-    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
     auto rows_fwd = k_fft_rows<N, true>;
     auto cols_fwd = k_fft_cols<N, COL_FWD>;
@@ -689,9 +704,9 @@ int slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_s
     ca.side = p->spec + (size_t)nzl * N * H;
     ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
     ca.scale = 0.f; ca.axis = 1; ca.nyl = nyl; ca.y0 = p->rank * nyl;
-    PM_LAUNCH(rows_fwd, nzl * N / kCols, kThreads, smem_rows, st,
+    PM_LAUNCH(rows_fwd, nzl * N / kCols, kThr<N>, smem_rows, st,
               reinterpret_cast<const float2 *>(rho), ca.main, (const float2 *)p->tw);
-    PM_LAUNCH(cols_fwd, nzl * (H / kCols), kThreads, smem_cols, st, ca);
+    PM_LAUNCH(cols_fwd, nzl * (H / kColsC), kThrC<N>, smem_cols, st, ca);
     const int grid = p->sm_count * 8;
     PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.main, send_main, nzl, N, H, nyl);
     PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.side, send_side, nzl, N, 1, nyl);
@@ -704,7 +719,7 @@ int slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0
 {
     constexpr int H = N / 2;
     const int nyl = N / p->nranks;
-    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
     auto cols_fused = k_fft_cols<N, COL_FUSED>;
     PM_CUDA(cudaFuncSetAttribute(cols_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     ColArgs ca;
@@ -713,7 +728,7 @@ int slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0
     const double m = (double)N * N * N;
     ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
     ca.axis = 0; ca.nyl = nyl; ca.y0 = p->rank * nyl;
-    PM_LAUNCH(cols_fused, nyl * (H / kCols) + nyl / kCols, kThreads, smem_cols, st, ca);
+    PM_LAUNCH(cols_fused, nyl * (H / kColsC) + nyl / kColsC, kThrC<N>, smem_cols, st, ca);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -723,7 +738,7 @@ int slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, f
 {
     constexpr int H = N / 2;
     const int nzl = p->nzl, nyl = N / p->nranks;
-    const size_t smem_cols = ((size_t)N * kCols + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
     auto rows_inv = k_fft_rows<N, false>;
     auto cols_inv = k_fft_cols<N, COL_INV>;
@@ -737,8 +752,8 @@ int slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, f
     const int grid = p->sm_count * 8;
     PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_main, ca.main, nzl, N, H, nyl);
     PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_side, ca.side, nzl, N, 1, nyl);
-    PM_LAUNCH(cols_inv, nzl * (H / kCols), kThreads, smem_cols, st, ca);
-    PM_LAUNCH(rows_inv, nzl * N / kCols, kThreads, smem_rows, st,
+    PM_LAUNCH(cols_inv, nzl * (H / kColsC), kThrC<N>, smem_cols, st, ca);
+    PM_LAUNCH(rows_inv, nzl * N / kCols, kThr<N>, smem_rows, st,
               reinterpret_cast<const float2 *>(ca.main), reinterpret_cast<float2 *>(phi),
               (const float2 *)p->tw);
     PM_CHECK_LAUNCH();

@@ -7,6 +7,9 @@
 // rounding points visible (and keep them if the flag is ever lost).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include "pm_internal.cuh"
 
 // --------------------------------------------------------------------------------------------
@@ -340,8 +343,14 @@ struct SlabArgs {
     int64_t leave_cap;
 };
 
+#ifndef PM_GATHER_THREADS
+#define PM_GATHER_THREADS 256
+#endif
+#ifndef PM_GATHER_MINB
+#define PM_GATHER_MINB 4
+#endif
 template <bool PERM, bool SLAB>
-__global__ void __launch_bounds__(256) k_gather_kick_drift(
+__global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_kick_drift(
     const float *pos_in, const float *vel_in,   // may alias pos_out/vel_out when !PERM
     const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ perm,
     float *pos_out, float *vel_out, uint32_t *__restrict__ id_out,
@@ -437,7 +446,7 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
     const double k_kick = da * f_a1;
     const double aa = (a_val + da) * (a_val + da);
     auto kern = k_gather_kick_drift<false, false>;
-    PM_LAUNCH(kern, (unsigned)((np + 255) / 256), 256, 0, st, pos, vel,
+    PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, pos, vel,
               (const uint32_t *)nullptr, (const uint32_t *)nullptr, pos, vel, (uint32_t *)nullptr,
               (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, f_a1, acc, SlabArgs());
     PM_CHECK_LAUNCH();
@@ -455,7 +464,7 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
     const double aa = (a_val + da) * (a_val + da);
     const int c = p->rcur, o = c ^ 1;
     auto kern = k_gather_kick_drift<true, false>;
-    PM_LAUNCH(kern, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c],
+    PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c],
               p->rvel[c], p->rid[c], p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np,
               p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, SlabArgs());
     PM_CHECK_LAUNCH();
@@ -478,7 +487,7 @@ int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, doub
     sl.np_valid = p->row_start + (size_t)p->nzl * p->nc;
     sl.leave_cnt = p->leave_cnt; sl.leave_slot = p->leave_slot; sl.leave_cap = p->leave_cap;
     auto kern = k_gather_kick_drift<true, true>;
-    PM_LAUNCH(kern, (unsigned)((np + 255) / 256), 256, 0, st, p->rpos[c], p->rvel[c], p->rid[c],
+    PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c], p->rvel[c], p->rid[c],
               p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np, p->rstride, p->rstride,
               phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, sl);
     PM_CHECK_LAUNCH();

@@ -201,6 +201,28 @@ def test_hand_written_fft_against_cufft_and_float64(pm, n):
             assert np.abs(phi - want).max() < 2e-5 * np.abs(want).max(), (axis, m)
 
 
+@pytest.mark.parametrize("n", [512, 1024])
+def test_hand_written_fft_large_meshes_against_cufft(pm, n):
+    """BASELINE configs 2 and 3 mesh sizes: own FFT vs the cuFFT path on device-generated input."""
+    cfg = O.Config(N_CELLS=n)
+    pm.set_config(cfg_ns(cfg))
+    rt = pm._runtime
+    g = torch.Generator(device="cuda").manual_seed(n)
+    rho = torch.rand((n, n, n), generator=g, device="cuda") * 4.0
+    rho[n // 3, n // 5, n // 7] += 500.0
+    fg = pm.fourier_grid()
+    plan = rt.get_plan(n, 1, 0)
+    phi_own = pm.potential(rho, fg, 0.5)
+    rt.check(rt.lib().pm_plan_set_fft_backend(plan.handle, 1), "backend")
+    phi_lib = pm.potential(rho, fg, 0.5)
+    rt.check(rt.lib().pm_plan_set_fft_backend(plan.handle, 0), "backend")
+    err = float((phi_own.double() - phi_lib.double()).norm() / phi_lib.double().norm())
+    assert err <= 2e-6, err
+    del phi_own, phi_lib, rho
+    pm.release_plans()
+    torch.cuda.empty_cache()
+
+
 def test_single_mode_potential(pm):
     cfg = O.Config(N_CELLS=32)
     pm.set_config(cfg_ns(cfg))
