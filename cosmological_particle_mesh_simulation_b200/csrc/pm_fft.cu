@@ -36,7 +36,10 @@ namespace {
 #ifndef PM_FFT_CTHREADS
 #define PM_FFT_CTHREADS 256
 #endif
-constexpr int kColsC = PM_FFT_COLS;  // adjacent columns (contiguous in memory) per column tile
+// adjacent columns (contiguous in memory) per column tile: 16 (128-byte segments) while three
+// tiles fit an SM, 8 for the 1024-point transforms (a 16-wide tile would be 147 KB: one CTA/SM)
+template <int N>
+constexpr int kColsCN = (N >= 1024) ? 8 : PM_FFT_COLS;
 template <int N>
 constexpr int kThrC = (N >= 256) ? PM_FFT_CTHREADS : 256;   // threads of a column-pass CTA
 constexpr int kCols = 16;          // x-rows per CTA of the row passes
@@ -281,11 +284,11 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
 {
     extern __shared__ float2 s_tile[];
     constexpr int H = N / 2;
-    constexpr int TPR = H / kColsC;      // column tiles per row of the main array
+    constexpr int TPR = H / kColsCN<N>;      // column tiles per row of the main array
     constexpr int S = fft_stages(N);
-    constexpr int CP = kColsC / 2;       // column pairs
+    constexpr int CP = kColsCN<N> / 2;       // column pairs
     const int tid = threadIdx.x;
-    float2 *s_x = s_tile + N * kColsC;   // extra column
+    float2 *s_x = s_tile + N * kColsCN<N>;   // extra column
     // Twiddles live in shared memory: with the carveout these tiles need, L1 is too small to keep
     // a __ldg table resident against the streaming tile traffic.  A quarter-warp reads one entry.
     float2 *s_tw = s_x + N;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
     bool side_tile = false;
     if (a.axis == 1) {
         const int z = t / TPR, kt = t % TPR;
-        g = a.main + (size_t)z * N * H + kt * kColsC;
+        g = a.main + (size_t)z * N * H + kt * kColsCN<N>;
         gs = H;
         if (kt == 0) {
             extra = true;
@@ -312,21 +315,21 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
     } else {
         if (t < a.nyl * TPR) {
             const int yl = t / TPR, kt = t % TPR;
-            g = a.main + (size_t)yl * H + kt * kColsC;
+            g = a.main + (size_t)yl * H + kt * kColsCN<N>;
             gs = (size_t)a.nyl * H;
-            col0 = kt * kColsC;
+            col0 = kt * kColsCN<N>;
             if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2rev + a.y0 + yl);
         } else {
             side_tile = true;
             const int yt = t - a.nyl * TPR;
-            g = a.side + yt * kColsC;
+            g = a.side + yt * kColsCN<N>;
             gs = a.nyl;
-            col0 = a.y0 + yt * kColsC;
+            col0 = a.y0 + yt * kColsCN<N>;
         }
     }
 
     auto sm4 = [&](int pos, int cp) -> float4 & {
-        return *reinterpret_cast<float4 *>(s_tile + pos * kColsC + 2 * cp);
+        return *reinterpret_cast<float4 *>(s_tile + pos * kColsCN<N> + 2 * cp);
     };
 
     // ---- generic stage runner over the 8 column pairs (+ the extra column) ----
@@ -613,7 +616,7 @@ template <int N>
 int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
 {
     constexpr int H = N / 2;
-    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
@@ -641,7 +644,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     ca.nyl = N;
     ca.y0 = 0;
     const int row_ctas = N * N / kCols;
-    const int tiles = N * (H / kColsC);
+    const int tiles = N * (H / kColsCN<N>);
 
     auto rows_fwd = k_fft_rows<N, true>;
     auto rows_inv = k_fft_rows<N, false>;
@@ -654,7 +657,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     PM_LAUNCH(cols_fwd, tiles, kThrC<N>, smem_cols, st, ca);
     pm_prof_mark(p, PM_STAGE_R2C + 1, st);
     ca.axis = 0;
-    PM_LAUNCH(cols_fused, tiles + N / kColsC, kThrC<N>, smem_cols, st, ca);
+    PM_LAUNCH(cols_fused, tiles + N / kColsCN<N>, kThrC<N>, smem_cols, st, ca);
     pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
     ca.axis = 1;
     PM_LAUNCH(cols_inv, tiles, kThrC<N>, smem_cols, st, ca);
@@ -693,7 +696,7 @@ int slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_s
 {
     constexpr int H = N / 2;
     const int nzl = p->nzl, nyl = N / p->nranks;
-    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
     auto rows_fwd = k_fft_rows<N, true>;
     auto cols_fwd = k_fft_cols<N, COL_FWD>;
@@ -706,7 +709,7 @@ int slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_s
     ca.scale = 0.f; ca.axis = 1; ca.nyl = nyl; ca.y0 = p->rank * nyl;
     PM_LAUNCH(rows_fwd, nzl * N / kCols, kThr<N>, smem_rows, st,
               reinterpret_cast<const float2 *>(rho), ca.main, (const float2 *)p->tw);
-    PM_LAUNCH(cols_fwd, nzl * (H / kColsC), kThrC<N>, smem_cols, st, ca);
+    PM_LAUNCH(cols_fwd, nzl * (H / kColsCN<N>), kThrC<N>, smem_cols, st, ca);
     const int grid = p->sm_count * 8;
     PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.main, send_main, nzl, N, H, nyl);
     PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.side, send_side, nzl, N, 1, nyl);
@@ -719,7 +722,7 @@ int slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0
 {
     constexpr int H = N / 2;
     const int nyl = N / p->nranks;
-    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
     auto cols_fused = k_fft_cols<N, COL_FUSED>;
     PM_CUDA(cudaFuncSetAttribute(cols_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     ColArgs ca;
@@ -728,7 +731,7 @@ int slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0
     const double m = (double)N * N * N;
     ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
     ca.axis = 0; ca.nyl = nyl; ca.y0 = p->rank * nyl;
-    PM_LAUNCH(cols_fused, nyl * (H / kColsC) + nyl / kColsC, kThrC<N>, smem_cols, st, ca);
+    PM_LAUNCH(cols_fused, nyl * (H / kColsCN<N>) + nyl / kColsCN<N>, kThrC<N>, smem_cols, st, ca);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -738,7 +741,7 @@ int slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, f
 {
     constexpr int H = N / 2;
     const int nzl = p->nzl, nyl = N / p->nranks;
-    const size_t smem_cols = ((size_t)N * kColsC + 2 * N) * sizeof(float2);
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
     auto rows_inv = k_fft_rows<N, false>;
     auto cols_inv = k_fft_cols<N, COL_INV>;
@@ -752,7 +755,7 @@ int slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, f
     const int grid = p->sm_count * 8;
     PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_main, ca.main, nzl, N, H, nyl);
     PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_side, ca.side, nzl, N, 1, nyl);
-    PM_LAUNCH(cols_inv, nzl * (H / kColsC), kThrC<N>, smem_cols, st, ca);
+    PM_LAUNCH(cols_inv, nzl * (H / kColsCN<N>), kThrC<N>, smem_cols, st, ca);
     PM_LAUNCH(rows_inv, nzl * N / kCols, kThr<N>, smem_rows, st,
               reinterpret_cast<const float2 *>(ca.main), reinterpret_cast<float2 *>(phi),
               (const float2 *)p->tw);
