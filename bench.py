@@ -211,6 +211,9 @@ def run_slab(args, rank, world, local_rank):
     slab = pm.slab
     torch.cuda.set_device(local_rank)
     dev = local_rank
+    # NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION; stdout must hold only the JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
     n_parts, n_cells = args.n_parts, args.n_cells
     cfg = cfg_namespace(n_parts, n_cells)
