@@ -127,6 +127,56 @@ def make_particles_torch(n_parts, n_cells, device, seed=38):
     return pos, vel
 
 
+def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38):
+    """The same IC-like particle load (lattice + uniform(-2,2) jitter), generated on the GPU for ONE
+    slab: only lattice planes that can land in the slab are visited, the jitter is a counter-based
+    hash of the global particle index so every rank draws the same numbers.  Used for the large
+    configurations, where building 10^9 particles on the host of every process is not an option."""
+    import torch
+    res = n_cells / n_parts
+    nzl = n_cells // nranks
+    z0 = rank * nzl
+    device = f"cuda:{dev}"
+
+    def i64(v):                 # wrap a Python int into the int64 range (two's complement)
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def uniform(idx, stream):   # idx: int64 tensor -> float64 in [0, 1)
+        x = idx * 3 + stream + i64(seed * 0x9E3779B97F4A7C15)
+        x = (x ^ (x >> 30)) * (-4658895280553007687)          # 0xBF58476D1CE4E5B9 as int64
+        x = (x ^ (x >> 27)) * (-7723592293110705685)          # 0x94D049BB133111EB as int64
+        x = x ^ (x >> 31)
+        return ((x >> 11) & ((1 << 53) - 1)).to(torch.float64) / float(1 << 53)
+
+    iz_lo = int((z0 - 3.0) // res) - 1
+    iz_hi = int((z0 + nzl + 3.0) // res) + 2
+    izs = torch.arange(iz_lo, iz_hi, device=device, dtype=torch.int64) % n_parts
+    if iz_hi - iz_lo >= n_parts:
+        izs = torch.arange(n_parts, device=device, dtype=torch.int64)
+    iy = torch.arange(n_parts, device=device, dtype=torch.int64)
+    out_p, out_i = [], []
+    chunk = max(1, min(n_parts, (1 << 25) // max(1, n_parts * izs.numel())))
+    for ix0 in range(0, n_parts, chunk):
+        ix = torch.arange(ix0, min(n_parts, ix0 + chunk), device=device, dtype=torch.int64)
+        gid = ((ix[:, None, None] * n_parts + iy[None, :, None]) * n_parts + izs[None, None, :]).reshape(-1)
+        comp = (gid // (n_parts * n_parts), (gid // n_parts) % n_parts, gid % n_parts)
+        z = torch.remainder(comp[2].to(torch.float64) * res + 0.5 + uniform(gid, 2) * 4.0 - 2.0,
+                            float(n_cells)).to(torch.float32)
+        own = (torch.remainder(torch.floor(z).to(torch.int64), n_cells) // nzl) == rank
+        gid = gid[own]
+        p = torch.empty((3, gid.numel()), dtype=torch.float32, device=device)
+        p[2] = z[own]
+        for d in (0, 1):
+            c = ((gid // (n_parts * n_parts)) if d == 0 else ((gid // n_parts) % n_parts)).to(torch.float64)
+            p[d] = torch.remainder(c * res + 0.5 + uniform(gid, d) * 4.0 - 2.0, float(n_cells)).to(torch.float32)
+        out_p.append(p)
+        out_i.append(gid.to(torch.int32))
+    pos = torch.cat(out_p, dim=1).clamp_(max=float(n_cells)).contiguous()
+    ids = torch.cat(out_i).contiguous()
+    return pos, torch.zeros_like(pos), ids
+
+
 def cfg_namespace(n_parts, n_cells, steps_cfg=1000):
     return types.SimpleNamespace(N_PARTS=n_parts, N_CELLS=n_cells, N_CPU=1, STEPS=steps_cfg,
                                  OMEGA_M0=0.31, OMEGA_K0=0.0, OMEGA_LAMBDA0=0.69, H0=0.68,
@@ -220,11 +270,23 @@ def run_slab(args, rank, world, local_rank):
     pm.set_config(cfg)
     npart = n_parts ** 3
     mass = (n_cells / n_parts) ** 3
-    pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
     comm = slab.DistComm()
-    pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
-    ranks = slab.make_ranks(n_cells, pos, vel, comm, device=dev)
-    del pos, vel
+    if n_parts > 256:
+        # large configurations: every rank generates its own slab on its GPU
+        pl, vl, il = make_particles_slab_gpu(n_parts, n_cells, rank, world, dev)
+        ranks = [slab.make_rank_from_local(n_cells, pl, vl, il, rank, world, device=dev)]
+        cnt = torch.tensor([pl.shape[1]], dtype=torch.int64, device=f"cuda:{dev}")
+        dist.all_reduce(cnt)
+        assert int(cnt.item()) == npart, (int(cnt.item()), npart)
+        del pl, vl, il
+        particles_desc = "lattice + uniform(-2,2) jitter (counter-based hash, seed 38), generated per slab on the GPU"
+    else:
+        pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
+        pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
+        ranks = slab.make_ranks(n_cells, pos, vel, comm, device=dev)
+        del pos, vel
+        particles_desc = "lattice + uniform(-2,2) jitter, seed 38"
+    torch.cuda.empty_cache()
     sched = pm.loop_scale_factors(cfg)
 
     def barrier():
@@ -238,6 +300,11 @@ def run_slab(args, rank, world, local_rank):
         slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg)
         step_i += 1
     barrier()
+    # sanity on the distributed state: total mass of the last deposit == Np * mass
+    msum = ranks[0].buf["RHO"].sum(dtype=torch.float64).reshape(1)
+    dist.all_reduce(msum)
+    mass_err = abs(float(msum.item()) / (npart * mass) - 1.0)
+    assert mass_err < 1e-5, mass_err
     sampler = ClockSampler(dev)
     sampler.start()
     time.sleep(0.3)
@@ -311,7 +378,7 @@ def run_slab(args, rank, world, local_rank):
             "vs_baseline": value / 4.7e6, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step, BASELINE configs[1]",
                        "n_parts": n_parts, "n_cells": n_cells,
-                       "particles": "lattice + uniform(-2,2) jitter, seed 38",
+                       "particles": particles_desc,
                        "l2": "inputs larger than L2",
                        "parallelism": f"slab decomposition along z over {world} GPUs: NCCL send/recv ghost planes, "
                                       "all-to-all transposed FFT, all-to-all-v particle migration"},
@@ -326,6 +393,7 @@ def run_slab(args, rank, world, local_rank):
             "roofline_step": {"bound": "hbm+nvlink", "t_roof_ms": 1e3 * t_roof, "frac": 1e3 * t_roof / ms_per_step,
                               "formula": "(60*Np+64*Nc^3)/P/hbm + 2*(4*Nc^3/P)*(P-1)/P/900e9 (SURVEY 8e, serial bound)"},
             "phases_ms_rank0": phases,
+            "mass_conservation_rel_err": mass_err,
         }
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

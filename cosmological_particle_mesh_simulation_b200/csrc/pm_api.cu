@@ -35,7 +35,7 @@ struct Geometry {
 
 bool config_ok(int nc, int64_t np)
 {
-    if (nc < 4 || nc > 1625) return false;  // nc^3 < 2^32: 32-bit cell keys and mesh offsets
+    if (nc < 4 || nc > 2048) return false;
     if (np < 0 || np > (int64_t)0xfffffff0u) return false;
     return true;
 }
@@ -74,8 +74,8 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->rvel = align_up(3 * npad * 4);
     L->rid = align_up(npad * 4);
     L->tbuf = g.slab ? L->spec : 0;
-    // migration: room for 1/8 of the capacity (at least 4096) to leave towards each rank per step
-    L->leave_cap = g.slab ? (int64_t)((npad / 8 > 4096) ? npad / 8 : 4096) : 0;
+    // migration: room for 1/32 of the capacity (at least 65536) to leave towards each rank per step
+    L->leave_cap = g.slab ? (int64_t)((npad / 32 > 65536) ? npad / 32 : 65536) : 0;
     L->leave_cnt = g.slab ? align_up((size_t)g.nranks * 4) : 0;
     L->leave_slot = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 4) : 0;
     L->mig = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 7 * 4) : 0;
@@ -150,6 +150,10 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         return PM_ERR_INVALID;
     if (g.slab && (!pm_fft_supported(n_cells) || (n_cells / g.nranks) % 16 != 0))
         return PM_ERR_UNSUPPORTED;   // slab mode runs the hand-written FFT on 16-column tiles
+    // 32-bit cell keys and mesh offsets: a slab plan needs (nzl+3)*Nc^2 < 2^32, a whole-mesh plan Nc^3
+    if (g.slab ? ((uint64_t)(n_cells / g.nranks + 3) * n_cells * n_cells >= (1ull << 32))
+               : ((uint64_t)n_cells * n_cells * n_cells >= (1ull << 32)))
+        return PM_ERR_UNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();

@@ -51,7 +51,7 @@ constexpr int kPitch = kCols + 1;  // +1: the split-off Nyquist column of the pa
 // threads per CTA: PM_FFT_THREADS for the large transforms, 256 for the small ones (whose tiles
 // hold fewer butterflies than that many threads)
 template <int N>
-constexpr int kThr = (N >= 256) ? PM_FFT_THREADS : 256;
+constexpr int kThr = (N >= 2048) ? 512 : ((N >= 256) ? PM_FFT_THREADS : 256);
 // Column kernels: how many butterflies' worth of global loads a thread issues before it starts
 // computing (memory-level parallelism vs registers), and the CTAs/SM the register budget targets.
 #ifndef PM_FFT_BATCH
@@ -767,7 +767,7 @@ int slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, f
 
 bool pm_fft_supported(int nc)
 {
-    return nc == 32 || nc == 64 || nc == 128 || nc == 256 || nc == 512 || nc == 1024;
+    return nc == 32 || nc == 64 || nc == 128 || nc == 256 || nc == 512 || nc == 1024 || nc == 2048;
 }
 
 // exp(-2 pi i m / N) in float64 -> float32, and the digit-reversed sin^2 table of the Green's kernel
@@ -790,6 +790,7 @@ int pm_k_fft_tables(pm_plan *p)
             case 256: pos = digit_rev<256>(k); break;
             case 512: pos = digit_rev<512>(k); break;
             case 1024: pos = digit_rev<1024>(k); break;
+            case 2048: pos = digit_rev<2048>(k); break;
         }
         const double s = sin(M_PI * (double)k / (double)n);
         sr[pos] = (float)(s * s);
@@ -810,6 +811,7 @@ int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, fl
         case 256: return poisson_launch<256>(p, rho, a, omega_m0, phi, st);
         case 512: return poisson_launch<512>(p, rho, a, omega_m0, phi, st);
         case 1024: return poisson_launch<1024>(p, rho, a, omega_m0, phi, st);
+        case 2048: return poisson_launch<2048>(p, rho, a, omega_m0, phi, st);
     }
     return PM_ERR_UNSUPPORTED;
 }
@@ -822,6 +824,7 @@ int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, fl
         case 256: return fn<256>(__VA_ARGS__);                \
         case 512: return fn<512>(__VA_ARGS__);                \
         case 1024: return fn<1024>(__VA_ARGS__);              \
+        case 2048: return fn<2048>(__VA_ARGS__);              \
     }                                                         \
     return PM_ERR_UNSUPPORTED
 

@@ -340,6 +340,17 @@ def make_ranks(n_cells, pos, vel, comm, device=None, slack=1.25, ids=None):
     return out
 
 
+def make_rank_from_local(n_cells, pos_l, vel_l, ids_l, rank, nranks, device=None, capacity=None):
+    """A SlabRank loaded with particles the caller already knows belong to `rank` (e.g. initial
+    conditions generated per slab)."""
+    dev = torch.cuda.current_device() if device is None else device
+    n = pos_l.shape[1]
+    cap = int(capacity) if capacity else int(n * 1.25) + 4096
+    sr = SlabRank(n_cells, max(cap, n + 4096), dev, rank, nranks)
+    sr.load(pos_l.contiguous(), vel_l.contiguous(), ids_l.contiguous())
+    return sr
+
+
 def collect(ranks, comm, npart):
     """Gather every rank's particles back into original particle order (tests / snapshots).
     LocalComm only needs concatenation; DistComm uses all_gather of padded buffers."""
