@@ -63,7 +63,7 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->keys_sorted = align_up(npad * 4);
     L->order_sorted = align_up(npad * 4);
     L->cub = align_up(pm_sort_temp_bytes(np > 0 ? np : 1, g.slab ? 32 : key_bits_for(nc)));
-    L->row_start = align_up(((size_t)nzl * nc + 1) * 4);
+    L->row_start = align_up(((size_t)nzl * nc * pm_deposit_segments(nc) + 1) * 4);
     L->mesh = align_up(plane * (nzl + (g.slab ? 1 : 0)) * 4);    // rho (+ ghost plane)
     L->mesh2 = align_up(plane * (nzl + (g.slab ? 3 : 0)) * 4);   // phi (+ 1 + 2 ghost planes)
     L->spec = align_up((size_t)nzl * nc * (nc / 2 + 1) * sizeof(float2));
@@ -173,6 +173,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     p->nzl = n_cells / g.nranks;
     p->z0 = g.rank * p->nzl;
     p->slab = g.slab;
+    p->dep_nseg = pm_deposit_segments(n_cells);
     p->key_bits = g.slab ? 32 : key_bits_for(n_cells);
     p->rstride = (np_capacity + 3) / 4 * 4;
     cudaGetDevice(&p->device);

@@ -56,7 +56,8 @@ struct pm_plan {
     uint32_t *keys, *iota, *keys_sorted, *order_sorted;  // iota[i] = i, written once
     void *cub_tmp;
     size_t cub_bytes;
-    uint32_t *row_start;  // nc*nc + 1 offsets into the sorted particle list
+    uint32_t *row_start;  // nzl*nc*dep_nseg + 1 offsets into the sorted particle list
+    int dep_nseg;         // segments per mesh row in the deposit (1 unless the mesh is wide)
 
     // Poisson scratch
     float *mesh;          // nc^3: rho when the caller does not keep it
@@ -119,6 +120,7 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
 // slab mode (pm_slab.cu / pm_particles.cu)
 int pm_k_deposit_slab(pm_plan *p, const float *pos, double mass, float *rho, cudaStream_t st);
+int pm_deposit_segments(int nc);
 int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, double f_a1, double da,
                                 cudaStream_t st);
 int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st);

@@ -120,16 +120,17 @@ int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st)
 // row_start[r] = first sorted particle whose mesh row (z_c*Nc + y_c) is >= r, r in [0, Nc^2].
 // One thread per boundary j in [0, np]; it fills every row that starts at j (empty rows too).
 // --------------------------------------------------------------------------------------------
+// (With the deposit's row segmentation the "rows" are row segments of xseg cells: key / xseg.)
 __global__ void __launch_bounds__(256) k_row_offsets(const uint32_t *__restrict__ keys_sorted,
-                                                     int64_t np, int nc, int64_t nrows,
+                                                     int64_t np, int xseg, int64_t nrows,
                                                      uint32_t *__restrict__ row_start)
 {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j > np) return;
     // rows past the last real one (PM_KEY_DEAD entries of a slab) clamp to nrows, so
     // row_start[nrows] is the number of live particles
-    int64_t prev = (j == 0) ? -1 : (int64_t)(keys_sorted[j - 1] / (uint32_t)nc);
-    int64_t cur = (j == np) ? nrows : (int64_t)(keys_sorted[j] / (uint32_t)nc);
+    int64_t prev = (j == 0) ? -1 : (int64_t)(keys_sorted[j - 1] / (uint32_t)xseg);
+    int64_t cur = (j == np) ? nrows : (int64_t)(keys_sorted[j] / (uint32_t)xseg);
     if (prev > nrows) prev = nrows;
     if (cur > nrows) cur = nrows;
     for (int64_t r = prev + 1; r <= cur; ++r) row_start[r] = (uint32_t)j;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) k_row_offsets(const uint32_t *__restrict_
 int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st)
 {
     PM_LAUNCH(k_row_offsets, (unsigned)((np + 1 + 255) / 256), 256, 0, st, p->keys_sorted, np,
-              p->nc, (int64_t)p->nzl * p->nc, p->row_start);
+              p->nc / p->dep_nseg, (int64_t)p->nzl * p->nc * p->dep_nseg, p->row_start);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -164,32 +165,42 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
                                                           const float *__restrict__ pz,
                                                           const uint32_t *__restrict__ order,
                                                           const uint32_t *__restrict__ row_start,
-                                                          int nc, double mass,
+                                                          int nc, int nseg, double mass,
                                                           float *__restrict__ rho, int z0, int nzl,
                                                           int slab)
 {
     // slab != 0: this rank owns planes [z0, z0+nzl) and writes nzl+1 output planes; plane nzl is
     // the ghost that holds the d_z share of the top plane's particles (it belongs to rank+1), and
     // output plane 0 lacks the d_z share of rank-1's top plane until pm_k_ghost_add.  No z wrap.
+    //
+    // Wide meshes: a row is cut into nseg segments of xseg = nc/nseg cells and a warp owns one
+    // segment of one output row, so shared memory per warp stays (xseg+1) doubles whatever nc is
+    // (nseg = nc/512 for nc = 1024, 2048).  row_start is indexed by (row*nseg + segment).  A
+    // particle in the last cell of a segment spills its d_x share into bin xseg, which the owner
+    // of the next segment (same CTA) folds into its bin 0 after the barrier -- for nseg = 1 that
+    // is the periodic wrap of the row onto itself.
     extern __shared__ double s_rows[];
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xseg = nc / nseg;
+    const int rslot = warp / nseg, seg = warp - rslot * nseg;
+    const int xs = seg * xseg;
     const int Z = blockIdx.y;
-    const int y = blockIdx.x * RY + warp;
-    if (y >= nc) return;  // warp-uniform; no block-wide barrier is used below
-    double *row = s_rows + (size_t)warp * nc;
-    for (int x = lane; x < nc; x += 32) row[x] = 0.0;
+    const int y = blockIdx.x * (RY / nseg) + rslot;
+    const bool active = y < nc;  // warp-uniform
+    double *row = s_rows + (size_t)warp * (xseg + 1);
+    for (int x = lane; x <= xseg; x += 32) row[x] = 0.0;
     __syncwarp();
 
     const int Zm = slab ? Z - 1 : ((Z == 0) ? nc - 1 : Z - 1);
     const int ym = (y == 0) ? nc - 1 : y - 1;
 #pragma unroll 1
-    for (int src = 0; src < 4; ++src) {
+    for (int src = 0; src < 4 && active; ++src) {
         const int zsl = (src & 2) ? Zm : Z;    // source plane, slab-local
         if (slab && (zsl < 0 || zsl >= nzl)) continue;
         const int zs = z0 + zsl;               // global cell coordinate of that plane
         const int ys = (src & 1) ? ym : y;
-        const uint32_t r = (uint32_t)zsl * nc + ys;
+        const uint32_t r = ((uint32_t)zsl * nc + ys) * nseg + seg;
         const uint32_t beg = row_start[r], end = row_start[r + 1];
         for (uint32_t base = beg; base < end; base += 32) {
             const uint32_t j = base + lane;
@@ -228,52 +239,72 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
                 m &= (m << d);
             }
             const bool tail = valid && (lane == 31 || ((heads >> (lane + 1)) & 1u));
-            if (tail) row[xc] += v0;
+            const int lb = xc - xs;   // bin inside the segment; lb + 1 may be the spill bin xseg
+            if (tail) row[lb] += v0;
             __syncwarp();
-            if (tail) row[(xc + 1 == nc) ? 0 : xc + 1] += v1;
+            if (tail) row[lb + 1] += v1;
             __syncwarp();
         }
     }
-    float *out = rho + ((size_t)Z * nc + y) * nc;
-    for (int x = lane; x < nc; x += 32) out[x] = (float)row[x];
+    __syncthreads();
+    if (!active) return;
+    const int pseg = (seg == 0) ? nseg - 1 : seg - 1;
+    const double spill = s_rows[(size_t)(rslot * nseg + pseg) * (xseg + 1) + xseg];
+    float *out = rho + ((size_t)Z * nc + y) * nc + xs;
+    for (int x = lane; x < xseg; x += 32) out[x] = (float)(x == 0 ? row[0] + spill : row[x]);
 }
 
 static const int PM_DEPOSIT_RY = 8;
 
-int pm_k_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
-                 cudaStream_t st)
+int pm_deposit_segments(int nc)
 {
-    const int nc = p->nc;
-    size_t smem = (size_t)PM_DEPOSIT_RY * nc * sizeof(double);
+    // segments per mesh row in the deposit: 512-cell segments for wide power-of-two meshes.
+    // PM_DEPOSIT_XSEG=<cells> overrides the segment length (tests exercise the segmented path on
+    // small meshes with it).
+    if (const char *e = getenv("PM_DEPOSIT_XSEG")) {
+        const int xseg = atoi(e);
+        if (xseg > 0 && nc % xseg == 0) {
+            const int s = nc / xseg;
+            if (s == 1 || s == 2 || s == 4 || s == 8) return s;
+        }
+    }
+    if (nc >= 1024 && nc % 512 == 0) {
+        const int s = nc / 512;
+        if (s == 2 || s == 4 || s == 8) return s;
+    }
+    return 1;
+}
+
+static int pm_launch_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
+                             int nz_out, int slab, cudaStream_t st)
+{
+    const int nc = p->nc, nseg = p->dep_nseg;
+    const int rows_per_cta = PM_DEPOSIT_RY / nseg;
+    const size_t smem = (size_t)PM_DEPOSIT_RY * (nc / nseg + 1) * sizeof(double);
     static size_t smem_set = 0;
     if (smem > smem_set) {
         PM_CUDA(cudaFuncSetAttribute(k_deposit_rows<PM_DEPOSIT_RY>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    dim3 grid((nc + PM_DEPOSIT_RY - 1) / PM_DEPOSIT_RY, nc);
+    dim3 grid((nc + rows_per_cta - 1) / rows_per_cta, nz_out);
     PM_LAUNCH(k_deposit_rows<PM_DEPOSIT_RY>, grid, PM_DEPOSIT_RY * 32, smem, st, pos, pos + stride,
-              pos + 2 * stride, p->order_sorted, p->row_start, nc, mass, rho, 0, nc, 0);
+              pos + 2 * stride, p->order_sorted, p->row_start, nc, nseg, mass, rho, p->z0, p->nzl, slab);
     PM_CHECK_LAUNCH();
     return PM_OK;
+}
+
+int pm_k_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
+                 cudaStream_t st)
+{
+    return pm_launch_deposit(p, pos, stride, mass, rho, p->nc, 0, st);
 }
 
 // Slab variant on the resident state: nzl+1 output planes into rho[(nzl+1)][nc][nc].
 int pm_k_deposit_slab(pm_plan *p, const float *pos, double mass, float *rho, cudaStream_t st)
 {
-    const int nc = p->nc;
-    const int64_t np = p->rstride;  // row stride of the SoA arrays
-    size_t smem = (size_t)PM_DEPOSIT_RY * nc * sizeof(double);
-    PM_CUDA(cudaFuncSetAttribute(k_deposit_rows<PM_DEPOSIT_RY>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((nc + PM_DEPOSIT_RY - 1) / PM_DEPOSIT_RY, p->nzl + 1);
-    PM_LAUNCH(k_deposit_rows<PM_DEPOSIT_RY>, grid, PM_DEPOSIT_RY * 32, smem, st, pos, pos + np,
-              pos + 2 * np, p->order_sorted, p->row_start, nc, mass, rho, p->z0, p->nzl, 1);
-    PM_CHECK_LAUNCH();
-    return PM_OK;
+    return pm_launch_deposit(p, pos, p->rstride, mass, rho, p->nzl + 1, 1, st);
 }
-
-
 
 // --------------------------------------------------------------------------------------------
 // Fused force gather + kick + drift (src/integrate.py:15-97), one thread per particle.
@@ -484,7 +515,7 @@ int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, doub
     const int c = p->rcur, o = c ^ 1;
     SlabArgs sl;
     sl.z0 = p->z0; sl.nzl = p->nzl; sl.rank = p->rank;
-    sl.np_valid = p->row_start + (size_t)p->nzl * p->nc;
+    sl.np_valid = p->row_start + (size_t)p->nzl * p->nc * p->dep_nseg;
     sl.leave_cnt = p->leave_cnt; sl.leave_slot = p->leave_slot; sl.leave_cap = p->leave_cap;
     auto kern = k_gather_kick_drift<true, true>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c], p->rvel[c], p->rid[c],

@@ -135,6 +135,38 @@ def test_density_single_particle_weights_and_wrap(pm):
     assert float(rho.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("xseg", [8, 16])
+def test_density_with_segmented_rows(pm, golden_dir, xseg, monkeypatch):
+    """Wide meshes (1024, 2048) cut every mesh row into 512-cell segments, one warp each; force the
+    same code path on the small fixtures and demand the same densities as the unsegmented kernel."""
+    for name in ["free16", "clustered32", "g32_step2", "g16_free10"]:
+        g, cfg = load_case(golden_dir, name)
+        pm.set_config(cfg_ns(cfg))
+        pos = dev(g["pos0"])
+        pm.release_plans()
+        monkeypatch.delenv("PM_DEPOSIT_XSEG", raising=False)
+        ref = pm.density(pos, float(g["mass"]))
+        pm.release_plans()
+        monkeypatch.setenv("PM_DEPOSIT_XSEG", str(xseg))
+        got = pm.density(pos, float(g["mass"]))
+        pm.release_plans()
+        assert rel_l2(got.cpu().numpy(), ref.cpu().numpy()) <= 1e-7
+        want = g["rho_0"] if "rho_0" in g else O.density(g["pos0"], float(g["mass"]), cfg)
+        assert rel_l2(got.cpu().numpy(), want) <= 2e-6
+        # a full step through the segmented deposit (row table feeds the gather's live count too)
+        p1, v1 = dev(g["pos0"]), dev(g["vel0"])
+        st = pm.ResidentParticles(p1, v1)
+        st.step(float(g["a_list"][0]), float(g["da"]), mass=float(g["mass"]))
+        st.store(p1, v1)
+        pm.release_plans()
+        monkeypatch.delenv("PM_DEPOSIT_XSEG")
+        p2, v2 = dev(g["pos0"]), dev(g["vel0"])
+        pm.step(p2, v2, float(g["a_list"][0]), float(g["da"]), mass=float(g["mass"]))
+        assert rel_l2_periodic(p1.cpu().numpy(), p2.cpu().numpy(), cfg.N_CELLS) <= 1e-6
+    monkeypatch.delenv("PM_DEPOSIT_XSEG", raising=False)
+    pm.release_plans()
+
+
 def test_density_ragged_sizes(pm):
     # particle counts that are not multiples of 4/32 and unaligned row starts (scalar key path)
     cfg = O.Config(N_CELLS=24, N_PARTS=8)
