@@ -372,6 +372,7 @@ def run_slab(args, rank, world, local_rank):
         nvlink_bytes = 2 * (4 * n_cells ** 3 / world) * (world - 1) / world   # per GPU per step
         t_roof = (bstep / world) / (peak * 1e9) + nvlink_bytes / 900e9
         dominant = max(phases, key=phases.get)
+        chunks = slab.default_chunks(n_cells)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -381,7 +382,8 @@ def run_slab(args, rank, world, local_rank):
                        "particles": particles_desc,
                        "l2": "inputs larger than L2",
                        "parallelism": f"slab decomposition along z over {world} GPUs: NCCL send/recv ghost planes, "
-                                      "all-to-all transposed FFT, all-to-all-v particle migration"},
+                                      f"all-to-all transposed FFT pipelined in {chunks} kx chunks on a second stream, "
+                                      "all-to-all-v particle migration"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
                     "d2h_bytes_per_step": float(t[2].item()) / ke, "steps": ke,

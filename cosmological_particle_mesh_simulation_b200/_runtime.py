@@ -80,9 +80,11 @@ def lib():
             "pm_slab_entries": (i64, [vp]),
             "pm_slab_deposit": (i32, [vp, f64, vp]),
             "pm_slab_ghost_add": (i32, [vp, vp]),
-            "pm_slab_fft_forward": (i32, [vp, vp]),
-            "pm_slab_fft_z": (i32, [vp, f64, f64, vp]),
-            "pm_slab_fft_inverse": (i32, [vp, vp]),
+            "pm_slab_fft_rows_forward": (i32, [vp, vp]),
+            "pm_slab_fft_y_forward": (i32, [vp, i32, i32, vp]),
+            "pm_slab_fft_z": (i32, [vp, i32, i32, f64, f64, vp]),
+            "pm_slab_fft_y_inverse": (i32, [vp, i32, i32, vp]),
+            "pm_slab_fft_rows_inverse": (i32, [vp, vp]),
             "pm_slab_gather": (i32, [vp, f64, f64, f64, vp]),
             "pm_slab_migrate_pack": (i32, [vp, vp, vp]),
             "pm_slab_migrate_unpack": (i32, [vp, i64, i64, vp]),
@@ -105,9 +107,9 @@ EXPORTED_SYMBOLS = (
     "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_particles_store",
     "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend",
     "pm_plan_create_slab", "pm_slab_buffer", "pm_slab_load", "pm_slab_count", "pm_slab_entries",
-    "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_forward", "pm_slab_fft_z",
-    "pm_slab_fft_inverse", "pm_slab_gather", "pm_slab_migrate_pack", "pm_slab_migrate_unpack",
-    "pm_slab_export",
+    "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_rows_forward", "pm_slab_fft_y_forward",
+    "pm_slab_fft_z", "pm_slab_fft_y_inverse", "pm_slab_fft_rows_inverse", "pm_slab_gather",
+    "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

@@ -226,9 +226,13 @@ struct ColArgs {
     const float *sin2, *sin2rev;
     float scale;       // -3*Omega_m/(8a)/N^3
     int axis;          // 1: along y (tiles = z x kx-tile), 0: along z (tiles = y x kx-tile, + side)
-    // z pass geometry: the array is [N z][nyl][N/2] holding y positions [y0, y0+nyl) -- the whole
+    // z pass geometry: the array is [N z][nyl][hw] holding y positions [y0, y0+nyl) -- the whole
     // y range on one GPU, this rank's share after the all-to-all transpose in slab mode
     int nyl, y0;
+    // kx chunking (slab pipeline): this launch covers kx tiles [kt0, kt0+tpr); the z-pass array
+    // holds only those columns, hw = tpr*16 float2 per row (y pass: the full-width array, hw = N/2)
+    int tpr, kt0, hw;
+    int side_tiles;    // z pass: also process the Nyquist plane tiles (first chunk only)
 };
 
 // Two adjacent columns per thread: every tile access is a 16-byte LDS/STS/LDG/STG and the two
@@ -284,7 +288,6 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
 {
     extern __shared__ float2 s_tile[];
     constexpr int H = N / 2;
-    constexpr int TPR = H / kColsCN<N>;      // column tiles per row of the main array
     constexpr int S = fft_stages(N);
     constexpr int CP = kColsCN<N> / 2;       // column pairs
     const int tid = threadIdx.x;
@@ -304,8 +307,9 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
     float sy_fixed = 0.f; // Green's: sin^2 term that is constant over the tile
     int col0 = 0;         // first column index (kx for main tiles, y position for side tiles)
     bool side_tile = false;
+    const int TPR = a.tpr;
     if (a.axis == 1) {
-        const int z = t / TPR, kt = t % TPR;
+        const int z = t / TPR, kt = a.kt0 + t % TPR;
         g = a.main + (size_t)z * N * H + kt * kColsCN<N>;
         gs = H;
         if (kt == 0) {
@@ -314,10 +318,10 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
         }
     } else {
         if (t < a.nyl * TPR) {
-            const int yl = t / TPR, kt = t % TPR;
-            g = a.main + (size_t)yl * H + kt * kColsCN<N>;
-            gs = (size_t)a.nyl * H;
-            col0 = kt * kColsCN<N>;
+            const int yl = t / TPR, ktl = t % TPR;
+            g = a.main + (size_t)yl * a.hw + ktl * kColsCN<N>;
+            gs = (size_t)a.nyl * a.hw;
+            col0 = (a.kt0 + ktl) * kColsCN<N>;
             if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2rev + a.y0 + yl);
         } else {
             side_tile = true;
@@ -643,6 +647,10 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
     ca.nyl = N;
     ca.y0 = 0;
+    ca.tpr = H / kColsCN<N>;
+    ca.kt0 = 0;
+    ca.hw = H;
+    ca.side_tiles = 1;
     const int row_ctas = N * N / kCols;
     const int tiles = N * (H / kColsCN<N>);
 
@@ -669,95 +677,130 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
 }
 
 // ---- slab decomposition: the same five passes with an all-to-all between 2|3 and 3|4 ----------
-// pack:   A[zl][y][k] (this rank's planes, all y)  ->  B[s][zl][yl][k], the chunk for rank s holding
-//         its y range [s*nyl, (s+1)*nyl); after the all-to-all the chunks received from ranks
-//         0..P-1 form C[z][yl][k] with z global -- the layout the z pass wants, no unpack needed.
-// unpack: the inverse on the way back.
+// Chunked slab pipeline.  The kx range is cut into C chunks of hc = (N/2)/C columns; chunk c of the
+// packed send buffer is B_c[s][zl][yl][kc] at offset c*nzl*N*hc, and after the all-to-all the
+// matching chunk of the receive buffer is C_c[z][yl][kc] -- so the y pass + pack of chunk c+1 and the
+// z pass of chunk c-1 run while chunk c is on the wire.  The Nyquist plane travels with chunk 0.
 template <bool UNPACK>
-__global__ void __launch_bounds__(256) k_slab_pack(const float2 *__restrict__ src,
-                                                   float2 *__restrict__ dst, int nzl, int n, int w,
-                                                   int nyl)
+__global__ void __launch_bounds__(256) k_slab_pack_chunk(const float2 *__restrict__ full,
+                                                         float2 *__restrict__ packed, int nzl, int n,
+                                                         int h, int k0, int hc, int nyl)
 {
-    const size_t total = (size_t)nzl * n * w;
+    // full: [nzl][n][h] (this rank's planes, all y); packed: [P][nzl][nyl][hc]
+    const size_t total = (size_t)nzl * n * hc;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(i % w);
-        const size_t r = i / w;
+        const int kc = (int)(i % hc);
+        const size_t r = i / hc;
         const int y = (int)(r % n), zl = (int)(r / n);
         const int s = y / nyl, yl = y - s * nyl;
-        const size_t j = (((size_t)s * nzl + zl) * nyl + yl) * w + k;
-        if (UNPACK) dst[i] = src[j];
-        else dst[j] = src[i];
+        const size_t jf = ((size_t)zl * n + y) * h + k0 + kc;
+        const size_t jp = (((size_t)s * nzl + zl) * nyl + yl) * hc + kc;
+        if (UNPACK) const_cast<float2 *>(full)[jf] = packed[jp];
+        else packed[jp] = full[jf];
     }
 }
 
 template <int N>
-int slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_side, cudaStream_t st)
+ColArgs slab_args(pm_plan *p)
 {
-    constexpr int H = N / 2;
-    const int nzl = p->nzl, nyl = N / p->nranks;
-    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
-    const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
-    auto rows_fwd = k_fft_rows<N, true>;
-    auto cols_fwd = k_fft_cols<N, COL_FWD>;
-    PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-    PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     ColArgs ca;
     ca.main = p->spec;
-    ca.side = p->spec + (size_t)nzl * N * H;
+    ca.side = p->spec + (size_t)p->nzl * N * (N / 2);
     ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
-    ca.scale = 0.f; ca.axis = 1; ca.nyl = nyl; ca.y0 = p->rank * nyl;
-    PM_LAUNCH(rows_fwd, nzl * N / kCols, kThr<N>, smem_rows, st,
-              reinterpret_cast<const float2 *>(rho), ca.main, (const float2 *)p->tw);
-    PM_LAUNCH(cols_fwd, nzl * (H / kColsCN<N>), kThrC<N>, smem_cols, st, ca);
-    const int grid = p->sm_count * 8;
-    PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.main, send_main, nzl, N, H, nyl);
-    PM_LAUNCH(k_slab_pack<false>, grid, 256, 0, st, (const float2 *)ca.side, send_side, nzl, N, 1, nyl);
+    ca.scale = 0.f; ca.axis = 1;
+    ca.nyl = N / p->nranks; ca.y0 = p->rank * ca.nyl;
+    ca.tpr = (N / 2) / kColsCN<N>; ca.kt0 = 0; ca.hw = N / 2; ca.side_tiles = 1;
+    return ca;
+}
+
+template <int N>
+int slab_rows_fwd(pm_plan *p, const float *rho, cudaStream_t st)
+{
+    const size_t smem_rows = ((size_t)(N / 2) * kPitch + N) * sizeof(float2);
+    auto rows_fwd = k_fft_rows<N, true>;
+    PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    PM_LAUNCH(rows_fwd, p->nzl * N / kCols, kThr<N>, smem_rows, st,
+              reinterpret_cast<const float2 *>(rho), p->spec, (const float2 *)p->tw);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
 
 template <int N>
-int slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0, cudaStream_t st)
+int slab_y_fwd_pack(pm_plan *p, int c, int C, float2 *send_main_c, float2 *send_side, cudaStream_t st)
 {
     constexpr int H = N / 2;
-    const int nyl = N / p->nranks;
+    const int nzl = p->nzl, nyl = N / p->nranks, hc = H / C;
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
+    auto cols_fwd = k_fft_cols<N, COL_FWD>;
+    PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    ColArgs ca = slab_args<N>(p);
+    ca.tpr = hc / kColsCN<N>;
+    ca.kt0 = c * ca.tpr;
+    PM_LAUNCH(cols_fwd, nzl * ca.tpr, kThrC<N>, smem_cols, st, ca);
+    const int grid = p->sm_count * 8;
+    PM_LAUNCH(k_slab_pack_chunk<false>, grid, 256, 0, st, (const float2 *)ca.main, send_main_c, nzl, N,
+              H, c * hc, hc, nyl);
+    if (c == 0)
+        PM_LAUNCH(k_slab_pack_chunk<false>, grid, 256, 0, st, (const float2 *)ca.side, send_side, nzl,
+                  N, 1, 0, 1, nyl);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+template <int N>
+int slab_z_chunk(pm_plan *p, int c, int C, float2 *main_t_c, float2 *side_t, double a, double omega_m0,
+                 cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const int hc = H / C;
     const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
     auto cols_fused = k_fft_cols<N, COL_FUSED>;
     PM_CUDA(cudaFuncSetAttribute(cols_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    ColArgs ca;
-    ca.main = main_t; ca.side = side_t;
-    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
+    ColArgs ca = slab_args<N>(p);
+    ca.main = main_t_c; ca.side = side_t;
     const double m = (double)N * N * N;
     ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
-    ca.axis = 0; ca.nyl = nyl; ca.y0 = p->rank * nyl;
-    PM_LAUNCH(cols_fused, nyl * (H / kColsCN<N>) + nyl / kColsCN<N>, kThrC<N>, smem_cols, st, ca);
+    ca.axis = 0;
+    ca.tpr = hc / kColsCN<N>; ca.kt0 = c * ca.tpr; ca.hw = hc;
+    ca.side_tiles = (c == 0);
+    const int tiles = ca.nyl * ca.tpr + (c == 0 ? ca.nyl / kColsCN<N> : 0);
+    PM_LAUNCH(cols_fused, tiles, kThrC<N>, smem_cols, st, ca);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
 
 template <int N>
-int slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, float *phi, cudaStream_t st)
+int slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main_c, const float2 *back_side,
+                      cudaStream_t st)
 {
     constexpr int H = N / 2;
-    const int nzl = p->nzl, nyl = N / p->nranks;
+    const int nzl = p->nzl, nyl = N / p->nranks, hc = H / C;
     const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
-    const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
-    auto rows_inv = k_fft_rows<N, false>;
     auto cols_inv = k_fft_cols<N, COL_INV>;
-    PM_CUDA(cudaFuncSetAttribute(rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     PM_CUDA(cudaFuncSetAttribute(cols_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    ColArgs ca;
-    ca.main = p->spec;
-    ca.side = p->spec + (size_t)nzl * N * H;
-    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
-    ca.scale = 0.f; ca.axis = 1; ca.nyl = nyl; ca.y0 = p->rank * nyl;
+    ColArgs ca = slab_args<N>(p);
+    ca.tpr = hc / kColsCN<N>;
+    ca.kt0 = c * ca.tpr;
     const int grid = p->sm_count * 8;
-    PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_main, ca.main, nzl, N, H, nyl);
-    PM_LAUNCH(k_slab_pack<true>, grid, 256, 0, st, back_side, ca.side, nzl, N, 1, nyl);
-    PM_LAUNCH(cols_inv, nzl * (H / kColsCN<N>), kThrC<N>, smem_cols, st, ca);
-    PM_LAUNCH(rows_inv, nzl * N / kCols, kThr<N>, smem_rows, st,
-              reinterpret_cast<const float2 *>(ca.main), reinterpret_cast<float2 *>(phi),
+    PM_LAUNCH(k_slab_pack_chunk<true>, grid, 256, 0, st, (const float2 *)ca.main,
+              const_cast<float2 *>(back_main_c), nzl, N, H, c * hc, hc, nyl);
+    if (c == 0)
+        PM_LAUNCH(k_slab_pack_chunk<true>, grid, 256, 0, st, (const float2 *)ca.side,
+                  const_cast<float2 *>(back_side), nzl, N, 1, 0, 1, nyl);
+    PM_LAUNCH(cols_inv, nzl * ca.tpr, kThrC<N>, smem_cols, st, ca);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+template <int N>
+int slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
+{
+    const size_t smem_rows = ((size_t)(N / 2) * kPitch + N) * sizeof(float2);
+    auto rows_inv = k_fft_rows<N, false>;
+    PM_CUDA(cudaFuncSetAttribute(rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    PM_LAUNCH(rows_inv, p->nzl * N / kCols, kThr<N>, smem_rows, st,
+              reinterpret_cast<const float2 *>(p->spec), reinterpret_cast<float2 *>(phi),
               (const float2 *)p->tw);
     PM_CHECK_LAUNCH();
     return PM_OK;
@@ -828,20 +871,32 @@ int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, fl
     }                                                         \
     return PM_ERR_UNSUPPORTED
 
-int pm_k_fft_slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_side,
-                          cudaStream_t st)
+int pm_k_fft_slab_rows_fwd(pm_plan *p, const float *rho, cudaStream_t st)
 {
-    PM_FFT_DISPATCH(slab_forward, p, rho, send_main, send_side, st);
+    PM_FFT_DISPATCH(slab_rows_fwd, p, rho, st);
 }
 
-int pm_k_fft_slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0,
-                    cudaStream_t st)
+int pm_k_fft_slab_y_fwd_pack(pm_plan *p, int c, int C, float2 *send_main_c, float2 *send_side,
+                             cudaStream_t st)
 {
-    PM_FFT_DISPATCH(slab_z, p, main_t, side_t, a, omega_m0, st);
+    PM_FFT_DISPATCH(slab_y_fwd_pack, p, c, C, send_main_c, send_side, st);
 }
 
-int pm_k_fft_slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, float *phi,
-                          cudaStream_t st)
+int pm_k_fft_slab_z_chunk(pm_plan *p, int c, int C, float2 *main_t_c, float2 *side_t, double a,
+                          double omega_m0, cudaStream_t st)
 {
-    PM_FFT_DISPATCH(slab_inverse, p, back_main, back_side, phi, st);
+    PM_FFT_DISPATCH(slab_z_chunk, p, c, C, main_t_c, side_t, a, omega_m0, st);
 }
+
+int pm_k_fft_slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main_c,
+                               const float2 *back_side, cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_unpack_y_inv, p, c, C, back_main_c, back_side, st);
+}
+
+int pm_k_fft_slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_rows_inv, p, phi, st);
+}
+
+int pm_fft_cols_per_tile(int nc) { return nc >= 1024 ? 8 : PM_FFT_COLS; }

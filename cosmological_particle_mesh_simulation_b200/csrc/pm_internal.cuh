@@ -130,14 +130,17 @@ bool pm_fft_supported(int nc);
 int pm_k_fft_tables(pm_plan *p);
 int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                      cudaStream_t st);
-// slab pieces of the same transform: local planes (rows + y pass + pack), z pass on the
-// transposed layout, and the way back
-int pm_k_fft_slab_forward(pm_plan *p, const float *rho, float2 *send_main, float2 *send_side,
-                          cudaStream_t st);
-int pm_k_fft_slab_z(pm_plan *p, float2 *main_t, float2 *side_t, double a, double omega_m0,
-                    cudaStream_t st);
-int pm_k_fft_slab_inverse(pm_plan *p, const float2 *back_main, const float2 *back_side, float *phi,
-                          cudaStream_t st);
+// slab pieces of the same transform, cut into C chunks of kx columns so that the all-to-all of
+// one chunk overlaps the passes of its neighbours (pm_slab.cu sequences them)
+int pm_k_fft_slab_rows_fwd(pm_plan *p, const float *rho, cudaStream_t st);
+int pm_k_fft_slab_y_fwd_pack(pm_plan *p, int c, int C, float2 *send_main_c, float2 *send_side,
+                             cudaStream_t st);
+int pm_k_fft_slab_z_chunk(pm_plan *p, int c, int C, float2 *main_t_c, float2 *side_t, double a,
+                          double omega_m0, cudaStream_t st);
+int pm_k_fft_slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main_c,
+                               const float2 *back_side, cudaStream_t st);
+int pm_k_fft_slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st);
+int pm_fft_cols_per_tile(int nc);
 
 // pm_poisson.cu
 int pm_k_sin2_table(pm_plan *p);

@@ -9,11 +9,14 @@
 //   pm_slab_deposit      keys -> sort -> rows -> CIC deposit into nzl+1 planes
 //        exchange  RHO_GHOST_SEND (plane nzl) -> rank+1's RHO_GHOST_RECV
 //   pm_slab_ghost_add    plane 0 += RHO_GHOST_RECV
-//   pm_slab_fft_forward  rows R2C + y pass on the local planes, pack per destination rank
-//        exchange  all-to-all FFT_SEND_{MAIN,SIDE} -> FFT_RECV_{MAIN,SIDE}
-//   pm_slab_fft_z        z forward + Green + z inverse on the transposed layout, in place
-//        exchange  all-to-all FFT_RECV_* -> FFT_SEND_*   (the way back)
-//   pm_slab_fft_inverse  unpack + y inverse + rows C2R -> phi planes 1..nzl
+//   pm_slab_fft_rows_forward   rows R2C on the local planes
+//   for each of C chunks of kx columns (the chunks pipeline against each other):
+//     pm_slab_fft_y_forward(c)  y pass on the chunk's columns, pack per destination rank
+//        exchange  all-to-all chunk c of FFT_SEND_MAIN -> FFT_RECV_MAIN (+ SIDE with chunk 0)
+//     pm_slab_fft_z(c)          z forward + Green + z inverse on the transposed chunk, in place
+//        exchange  all-to-all chunk c of FFT_RECV_MAIN -> FFT_SEND_MAIN   (the way back)
+//     pm_slab_fft_y_inverse(c)  unpack + y inverse
+//   pm_slab_fft_rows_inverse   rows C2R -> phi planes 1..nzl
 //        exchange  PHI_HI_SEND (own last plane) -> rank+1's PHI_LO_RECV (its plane 0)
 //                  PHI_LO_SEND (own first two planes) -> rank-1's PHI_HI_RECV (its planes nzl+1, nzl+2)
 //   pm_slab_gather       gather + kick + drift into the other buffer set; leavers -> leave lists
@@ -122,26 +125,44 @@ int pm_slab_ghost_add(pm_plan *p, pm_stream_t stream)
     return pm_k_ghost_add(p, p->mesh, reinterpret_cast<const float *>(p->tbuf[1]), st);
 }
 
-int pm_slab_fft_forward(pm_plan *p, pm_stream_t stream)
+// Chunk c of C: byte ranges inside FFT_SEND_MAIN / FFT_RECV_MAIN are [c, c+1) * bytes / C.
+static int chunk_ok(const pm_plan *p, int c, int C)
 {
-    PM_SLAB_ENTER(true);
-    const size_t main_n = (size_t)p->nzl * p->nc * (p->nc / 2);
-    return pm_k_fft_slab_forward(p, p->mesh, p->tbuf[0], p->tbuf[0] + main_n, st);
+    const int h = p->nc / 2;
+    return C >= 1 && c >= 0 && c < C && h % C == 0 && (h / C) % pm_fft_cols_per_tile(p->nc) == 0;
 }
 
-int pm_slab_fft_z(pm_plan *p, double a, double omega_m0, pm_stream_t stream)
-{
-    PM_SLAB_ENTER(a != 0.0);
-    const size_t main_n = (size_t)p->nzl * p->nc * (p->nc / 2);
-    return pm_k_fft_slab_z(p, p->tbuf[1], p->tbuf[1] + main_n, a, omega_m0, st);
-}
-
-int pm_slab_fft_inverse(pm_plan *p, pm_stream_t stream)
+int pm_slab_fft_rows_forward(pm_plan *p, pm_stream_t stream)
 {
     PM_SLAB_ENTER(true);
+    return pm_k_fft_slab_rows_fwd(p, p->mesh, st);
+}
+
+int pm_slab_fft_y_forward(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C));
     const size_t main_n = (size_t)p->nzl * p->nc * (p->nc / 2);
-    return pm_k_fft_slab_inverse(p, p->tbuf[0], p->tbuf[0] + main_n,
-                                 p->mesh2 + (size_t)p->nc * p->nc, st);
+    return pm_k_fft_slab_y_fwd_pack(p, c, C, p->tbuf[0] + main_n / C * c, p->tbuf[0] + main_n, st);
+}
+
+int pm_slab_fft_z(pm_plan *p, int c, int C, double a, double omega_m0, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(a != 0.0 && chunk_ok(p, c, C));
+    const size_t main_n = (size_t)p->nzl * p->nc * (p->nc / 2);
+    return pm_k_fft_slab_z_chunk(p, c, C, p->tbuf[1] + main_n / C * c, p->tbuf[1] + main_n, a, omega_m0, st);
+}
+
+int pm_slab_fft_y_inverse(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C));
+    const size_t main_n = (size_t)p->nzl * p->nc * (p->nc / 2);
+    return pm_k_fft_slab_unpack_y_inv(p, c, C, p->tbuf[0] + main_n / C * c, p->tbuf[0] + main_n, st);
+}
+
+int pm_slab_fft_rows_inverse(pm_plan *p, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(true);
+    return pm_k_fft_slab_rows_inv(p, p->mesh2 + (size_t)p->nc * p->nc, st);
 }
 
 int pm_slab_gather(pm_plan *p, double a, double f_a1, double da, pm_stream_t stream)

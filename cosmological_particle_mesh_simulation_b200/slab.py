@@ -126,14 +126,26 @@ class SlabRank:
     def ghost_add(self):
         self._call("pm_slab_ghost_add")
 
-    def fft_forward(self):
-        self._call("pm_slab_fft_forward")
+    def fft_rows_forward(self):
+        self._call("pm_slab_fft_rows_forward")
 
-    def fft_z(self, a, omega_m0):
-        self._call("pm_slab_fft_z", float(a), float(omega_m0))
+    def fft_y_forward(self, c, C):
+        self._call("pm_slab_fft_y_forward", int(c), int(C))
 
-    def fft_inverse(self):
-        self._call("pm_slab_fft_inverse")
+    def fft_z(self, c, C, a, omega_m0):
+        self._call("pm_slab_fft_z", int(c), int(C), float(a), float(omega_m0))
+
+    def fft_y_inverse(self, c, C):
+        self._call("pm_slab_fft_y_inverse", int(c), int(C))
+
+    def fft_rows_inverse(self):
+        self._call("pm_slab_fft_rows_inverse")
+
+    def chunk(self, name, c, C):
+        """Chunk c of C of an FFT_*_MAIN buffer as a (P, .) view (one row per peer rank)."""
+        flat = self.buf[name].view(-1)
+        n = flat.numel() // C
+        return flat[c * n:(c + 1) * n].view(self.nranks, -1)
 
     def gather(self, a, f_a1, da):
         self._call("pm_slab_gather", float(a), float(f_a1), float(da))
@@ -194,7 +206,10 @@ class DistComm:
         self.nranks = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.local_ranks = [self.rank]
-        self._count_device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        nccl = dist.get_backend(group) == "nccl"
+        self._count_device = "cuda" if nccl else "cpu"
+        # collectives of the FFT pipeline run here so they overlap the compute stream
+        self.side_stream = torch.cuda.Stream() if (nccl and self.nranks > 1) else None
 
     def shift(self, send, recv, direction):
         P, r, dist = self.nranks, self.rank, self.dist
@@ -239,74 +254,128 @@ class DistComm:
 # the step
 # -------------------------------------------------------------------------------------------------
 class PhaseTimer:
-    """CUDA-event timing of the phases of slab_step on the current stream (bench.py)."""
-    NAMES = ("deposit", "rho_ghost", "fft_local_fwd", "a2a_fwd", "fft_z", "a2a_bwd", "fft_local_inv",
-             "phi_ghost", "gather", "migrate")
+    """CUDA-event timing of the phases of slab_step on the compute stream (bench.py)."""
 
     def __init__(self):
         self.records = []
 
     def begin_step(self):
-        self.cur = [torch.cuda.Event(enable_timing=True)]
-        self.cur[0].record()
-
-    def mark(self):
         e = torch.cuda.Event(enable_timing=True)
         e.record()
-        self.cur.append(e)
+        self.cur = [("", e)]
+
+    def mark(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.cur.append((name, e))
 
     def end_step(self):
         self.records.append(self.cur)
 
     def mean_ms(self):
         torch.cuda.synchronize()
-        out = {n: 0.0 for n in self.NAMES}
+        out = {}
         for rec in self.records:
-            for n, (e0, e1) in zip(self.NAMES, zip(rec[:-1], rec[1:])):
-                out[n] += e0.elapsed_time(e1) / len(self.records)
+            for (_, e0), (name, e1) in zip(rec[:-1], rec[1:]):
+                out[name] = out.get(name, 0.0) + e0.elapsed_time(e1) / len(self.records)
         return out
 
 
-def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None):
+def default_chunks(n_cells):
+    """kx chunks of the distributed FFT pipeline: 4 when the half spectrum allows it."""
+    tile = 8 if n_cells >= 1024 else 16
+    for c in (4, 2):
+        if (n_cells // 2) % c == 0 and ((n_cells // 2) // c) % tile == 0:
+            return c
+    return 1
+
+
+def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None):
     """One body of the loop src/pmesh.py:60-61 across the slabs.  `ranks`: the SlabRank objects
-    of comm.local_ranks (one for DistComm, all P for LocalComm)."""
+    of comm.local_ranks (one for DistComm, all P for LocalComm).  The distributed FFT runs as a
+    pipeline of `chunks` kx chunks: with DistComm on GPUs the all-to-alls go to a second stream
+    and overlap the y and z passes of the neighbouring chunks."""
     cfg = cfg or rt.config()
-    mark = timer.mark if timer else (lambda: None)
     if timer:
         timer.begin_step()
+    mark = timer.mark if timer else (lambda name: None)
     if mass is None:
         mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3          # src/pmesh.py:28
     f_a1 = f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])   # src/integrate.py:12 (SURVEY Q1)
     B = lambda name: [r.buf[name] for r in ranks]    # noqa: E731
+    C = chunks or default_chunks(ranks[0].n_cells)
+    CH = lambda name, c: [r.chunk(name, c, C) for r in ranks]    # noqa: E731
 
     for r in ranks:
         r.deposit(mass)
-    mark()
+    mark("deposit")
     comm.shift(B("RHO_GHOST_SEND"), B("RHO_GHOST_RECV"), +1)
     for r in ranks:
         r.ghost_add()
-    mark()
+    mark("rho_ghost")
+
+    # ---- distributed FFT, pipelined over kx chunks ----
+    side = getattr(comm, "side_stream", None)
+    main = torch.cuda.current_stream() if side is not None else None
+
+    def on_comm(after, fn):
+        """Run the collective `fn` after compute event `after`; returns the event it completes at."""
+        if side is None:
+            fn()
+            return None
+        side.wait_event(after)
+        with torch.cuda.stream(side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(side)
+        return done
+
+    def ev():
+        if side is None:
+            return None
+        e = torch.cuda.Event()
+        e.record(main)
+        return e
+
     for r in ranks:
-        r.fft_forward()
-    mark()
-    comm.all_to_all(B("FFT_SEND_MAIN"), B("FFT_RECV_MAIN"))
-    comm.all_to_all(B("FFT_SEND_SIDE"), B("FFT_RECV_SIDE"))
-    mark()
+        r.fft_rows_forward()
+    arrived = []
+    for c in range(C):
+        for r in ranks:
+            r.fft_y_forward(c, C)
+
+        def fwd(c=c):
+            comm.all_to_all(CH("FFT_SEND_MAIN", c), CH("FFT_RECV_MAIN", c))
+            if c == 0:
+                comm.all_to_all(B("FFT_SEND_SIDE"), B("FFT_RECV_SIDE"))
+        arrived.append(on_comm(ev(), fwd))
+    returned = []
+    for c in range(C):
+        if arrived[c] is not None:
+            main.wait_event(arrived[c])
+        for r in ranks:
+            r.fft_z(c, C, a, cfg.OMEGA_M0)
+
+        def bwd(c=c):
+            comm.all_to_all(CH("FFT_RECV_MAIN", c), CH("FFT_SEND_MAIN", c))
+            if c == 0:
+                comm.all_to_all(B("FFT_RECV_SIDE"), B("FFT_SEND_SIDE"))
+        returned.append(on_comm(ev(), bwd))
+    for c in range(C):
+        if returned[c] is not None:
+            main.wait_event(returned[c])
+        for r in ranks:
+            r.fft_y_inverse(c, C)
     for r in ranks:
-        r.fft_z(a, cfg.OMEGA_M0)
-    mark()
-    comm.all_to_all(B("FFT_RECV_MAIN"), B("FFT_SEND_MAIN"))
-    comm.all_to_all(B("FFT_RECV_SIDE"), B("FFT_SEND_SIDE"))
-    mark()
-    for r in ranks:
-        r.fft_inverse()
-    mark()
+        r.fft_rows_inverse()
+    mark("fft_distributed")
+
     comm.shift(B("PHI_HI_SEND"), B("PHI_LO_RECV"), +1)    # my last plane is rank+1's plane z0-1
     comm.shift(B("PHI_LO_SEND"), B("PHI_HI_RECV"), -1)    # my first two planes close rank-1's stencil
-    mark()
+    mark("phi_ghost")
     for r in ranks:
         r.gather(a, f_a1, da)
-    mark()
+    mark("gather")
     # migration: one small device->host read per step (the leave counts size the messages)
     send_counts = [r.buf["LEAVE_COUNTS"].tolist() for r in ranks]
     recv_counts = comm.exchange_counts(send_counts)
@@ -315,7 +384,7 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None):
     comm.all_to_all_v(B("MIG_SEND"), send_counts, B("MIG_RECV"), recv_counts)
     for r, sc, rc in zip(ranks, send_counts, recv_counts):
         r.migrate_unpack(sum(rc), sum(sc))
-    mark()
+    mark("migrate")
     if timer:
         timer.end_step()
 

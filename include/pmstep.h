@@ -187,9 +187,16 @@ PM_API int64_t pm_slab_count(const pm_plan *plan);   /* live particles owned by 
 PM_API int64_t pm_slab_entries(const pm_plan *plan); /* storage entries incl. departed ones */
 PM_API int pm_slab_deposit(pm_plan *plan, double mass, pm_stream_t stream);
 PM_API int pm_slab_ghost_add(pm_plan *plan, pm_stream_t stream);
-PM_API int pm_slab_fft_forward(pm_plan *plan, pm_stream_t stream);
-PM_API int pm_slab_fft_z(pm_plan *plan, double a, double omega_m0, pm_stream_t stream);
-PM_API int pm_slab_fft_inverse(pm_plan *plan, pm_stream_t stream);
+/* The distributed transform in C chunks of kx columns (chunk c occupies bytes [c, c+1)/C of the
+ * FFT_*_MAIN buffers; the Nyquist plane FFT_*_SIDE travels with chunk 0): the all-to-all of one
+ * chunk overlaps the y and z passes of its neighbours.  (Nc/2)/C must be a multiple of the column
+ * tile width (16; 8 for Nc >= 1024). */
+PM_API int pm_slab_fft_rows_forward(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_fft_y_forward(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+PM_API int pm_slab_fft_z(pm_plan *plan, int chunk, int nchunks, double a, double omega_m0,
+                         pm_stream_t stream);
+PM_API int pm_slab_fft_y_inverse(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+PM_API int pm_slab_fft_rows_inverse(pm_plan *plan, pm_stream_t stream);
 PM_API int pm_slab_gather(pm_plan *plan, double a, double f_a1, double da, pm_stream_t stream);
 PM_API int pm_slab_migrate_pack(pm_plan *plan, const int64_t *counts_h, pm_stream_t stream);
 PM_API int pm_slab_migrate_unpack(pm_plan *plan, int64_t n_arrive, int64_t n_leave, pm_stream_t stream);
