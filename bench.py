@@ -297,7 +297,7 @@ def run_slab(args, rank, world, local_rank):
     step_i = 0
     for _ in range(W):
         a, da = sched[step_i % len(sched)]
-        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg)
+        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=args.chunks or None)
         step_i += 1
     barrier()
     # sanity on the distributed state: total mass of the last deposit == Np * mass
@@ -315,7 +315,7 @@ def run_slab(args, rank, world, local_rank):
     ev0.record()
     for _ in range(K):
         a, da = sched[step_i % len(sched)]
-        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, timer=timer)
+        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, timer=timer, chunks=args.chunks or None)
         step_i += 1
     ev1.record()
     barrier()
@@ -372,7 +372,7 @@ def run_slab(args, rank, world, local_rank):
         nvlink_bytes = 2 * (4 * n_cells ** 3 / world) * (world - 1) / world   # per GPU per step
         t_roof = (bstep / world) / (peak * 1e9) + nvlink_bytes / 900e9
         dominant = max(phases, key=phases.get)
-        chunks = slab.default_chunks(n_cells)
+        chunks = args.chunks or slab.default_chunks(n_cells, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -559,6 +559,7 @@ def main():
     ap.add_argument("--n-parts", type=int, default=256)
     ap.add_argument("--n-cells", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
     ap.add_argument("--reference-budget-s", type=float, default=90.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -281,11 +281,15 @@ class PhaseTimer:
         return out
 
 
-def default_chunks(n_cells):
-    """kx chunks of the distributed FFT pipeline: 4 when the half spectrum allows it."""
+def default_chunks(n_cells, nranks=1):
+    """kx chunks of the distributed FFT pipeline, by the size of one rank's half spectrum: deep
+    pipelines pay off when a chunk's all-to-all is long against a kernel launch (measured on
+    8 B200: 67 MB/rank is faster unchunked, 268 MB/rank and up is faster pipelined)."""
     tile = 8 if n_cells >= 1024 else 16
-    for c in (4, 2):
-        if (n_cells // 2) % c == 0 and ((n_cells // 2) // c) % tile == 0:
+    mb = 4.0 * n_cells ** 3 / max(nranks, 1) / 2 ** 20
+    want = 8 if mb >= 2048 else 4 if mb >= 256 else 2 if mb >= 128 else 1
+    for c in (8, 4, 2):
+        if c <= want and (n_cells // 2) % c == 0 and ((n_cells // 2) // c) % tile == 0:
             return c
     return 1
 
@@ -303,7 +307,7 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None):
         mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3          # src/pmesh.py:28
     f_a1 = f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])   # src/integrate.py:12
     B = lambda name: [r.buf[name] for r in ranks]    # noqa: E731
-    C = chunks or default_chunks(ranks[0].n_cells)
+    C = chunks or default_chunks(ranks[0].n_cells, ranks[0].nranks)
     CH = lambda name, c: [r.chunk(name, c, C) for r in ranks]    # noqa: E731
 
     for r in ranks:

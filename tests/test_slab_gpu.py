@@ -72,7 +72,9 @@ def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells):
         rho_ref = torch.empty((n_cells,) * 3, device="cuda")
         pm.step(ref_p, ref_v, a, da, mass=mass, rho_out=rho_ref)
         before = [r.count for r in ranks]
-        chunks = (1, 2, None)[step % 3]         # unchunked, two kx chunks, default pipeline depth
+        chunks = (1, 2, 4)[step % 3]            # unchunked, two and four kx chunks
+        if chunks == 4 and (n_cells // 2 // 4) % 16:
+            chunks = 2
         if chunks == 2 and (n_cells // 2 // 2) % 16:
             chunks = 1
         pm.slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=chunks)
