@@ -23,4 +23,4 @@ from .potential import potential  # noqa: F401
 from .integrate import advance_time, integrate  # noqa: F401
 from .cosmology import f  # noqa: F401
 from .pmesh import step, step_host, simulator, loop_scale_factors, ResidentParticles  # noqa: F401
-from . import slab  # noqa: F401,E402
+from . import slab, analysis  # noqa: F401,E402

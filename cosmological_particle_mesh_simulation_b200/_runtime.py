@@ -66,6 +66,7 @@ def lib():
             "pm_deposit_cic": (i32, [vp, vp, i64, f64, vp, vp]),
             "pm_poisson": (i32, [vp, vp, f64, f64, vp, vp]),
             "pm_gather_kick_drift": (i32, [vp, vp, vp, i64, vp, f64, f64, f64, vp, vp]),
+            "pm_power_spectrum": (i32, [vp, vp, i32, vp, vp, vp]),
             "pm_step": (i32, [vp, vp, vp, i64, f64, f64, f64, f64, f64, vp, vp]),
             "pm_step_host": (i32, [vp, vp, vp, i64, f64, f64, f64, f64, f64, vp]),
             "pm_particles_load": (i32, [vp, vp, vp, i64, vp]),

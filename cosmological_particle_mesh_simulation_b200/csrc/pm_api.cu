@@ -373,6 +373,16 @@ int pm_poisson(pm_plan *p, const float *rho_d, double a, double omega_m0, float 
     return pm_k_poisson(p, rho_d, a, omega_m0, phi_d, pm_cu(stream));
 }
 
+int pm_power_spectrum(pm_plan *p, const float *rho_d, int nbins, double *psum_d, double *pcnt_d,
+                      pm_stream_t stream)
+{
+    PM_ARGS(p && rho_d && psum_d && pcnt_d && nbins >= 2 && nbins <= 4096);
+    if (p->slab || !pm_fft_supported(p->nc)) return PM_ERR_UNSUPPORTED;
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return pm_k_power_spectrum(p, rho_d, nbins, psum_d, pcnt_d, pm_cu(stream));
+}
+
 int pm_gather_kick_drift(pm_plan *p, float *pos_d, float *vel_d, int64_t np, const float *phi_d,
                          double a_val, double f_a1, double da, float *acc_d, pm_stream_t stream)
 {

@@ -806,6 +806,78 @@ int slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
     return PM_OK;
 }
 
+// ---- matter power spectrum (the reference has no estimator) --------------------
+// After rows R2C + y forward + z forward the array holds rho_k at (zpos, ypos, kx) with zpos/ypos
+// digit-reversed.  Each mode adds w*|rho_k|^2 to the spherical bin round(|k|) (integer frequency
+// units, edges at half-integers), w = 2 for 0 < kx < N/2 (the Hermitian half that is not stored),
+// 1 for kx = 0 and kx = N/2.  Block-level float64 partial sums, then one atomicAdd per bin.
+template <int N>
+__global__ void __launch_bounds__(256) k_pk_bin(const float2 *__restrict__ main,
+                                                const float2 *__restrict__ side, int nbins,
+                                                double *__restrict__ psum, double *__restrict__ pcnt)
+{
+    extern __shared__ double s_bins[];   // [2][nbins]
+    constexpr int H = N / 2;
+    for (int i = threadIdx.x; i < 2 * nbins; i += blockDim.x) s_bins[i] = 0.0;
+    __syncthreads();
+    const size_t total = (size_t)N * N * (H + 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int kx = (int)(i % (H + 1));
+        const size_t r = i / (H + 1);
+        const int ypos = (int)(r % N), zpos = (int)(r / N);
+        const float2 v = (kx < H) ? main[((size_t)zpos * N + ypos) * H + kx] : side[(size_t)zpos * N + ypos];
+        int kz = digit_unrev<N>(zpos), ky = digit_unrev<N>(ypos);
+        if (kz > N / 2) kz -= N;
+        if (ky > N / 2) ky -= N;
+        const double kk = sqrt((double)kz * kz + (double)ky * ky + (double)kx * kx);
+        const int b = (int)floor(kk + 0.5);
+        if (b >= 1 && b < nbins) {
+            const double w = (kx > 0 && kx < H) ? 2.0 : 1.0;
+            atomicAdd(&s_bins[b], w * ((double)v.x * v.x + (double)v.y * v.y));
+            atomicAdd(&s_bins[nbins + b], w);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < nbins; b += blockDim.x) {
+        if (s_bins[nbins + b] != 0.0) {
+            atomicAdd(psum + b, s_bins[b]);
+            atomicAdd(pcnt + b, s_bins[nbins + b]);
+        }
+    }
+}
+
+template <int N>
+int pk_launch(pm_plan *p, const float *rho, int nbins, double *psum, double *pcnt, cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
+    const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
+    auto rows_fwd = k_fft_rows<N, true>;
+    auto cols_fwd = k_fft_cols<N, COL_FWD>;
+    PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    ColArgs ca;
+    ca.main = p->spec;
+    ca.side = p->spec + (size_t)N * N * H;
+    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
+    ca.scale = 0.f; ca.nyl = N; ca.y0 = 0;
+    ca.tpr = H / kColsCN<N>; ca.kt0 = 0; ca.hw = H; ca.side_tiles = 1;
+    PM_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * nbins, st));
+    PM_CUDA(cudaMemsetAsync(pcnt, 0, sizeof(double) * nbins, st));
+    PM_LAUNCH(rows_fwd, N * N / kCols, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(rho),
+              ca.main, (const float2 *)p->tw);
+    ca.axis = 1;
+    PM_LAUNCH(cols_fwd, N * ca.tpr, kThrC<N>, smem_cols, st, ca);
+    ca.axis = 0;
+    PM_LAUNCH(cols_fwd, N * ca.tpr + N / kColsCN<N>, kThrC<N>, smem_cols, st, ca);
+    auto bin = k_pk_bin<N>;
+    PM_LAUNCH(bin, p->sm_count * 4, 256, 2 * nbins * sizeof(double), st, (const float2 *)ca.main,
+              (const float2 *)ca.side, nbins, psum, pcnt);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
 }  // namespace
 
 bool pm_fft_supported(int nc)
@@ -900,3 +972,9 @@ int pm_k_fft_slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
 }
 
 int pm_fft_cols_per_tile(int nc) { return nc >= 1024 ? 8 : PM_FFT_COLS; }
+
+int pm_k_power_spectrum(pm_plan *p, const float *rho, int nbins, double *psum, double *pcnt,
+                        cudaStream_t st)
+{
+    PM_FFT_DISPATCH(pk_launch, p, rho, nbins, psum, pcnt, st);
+}

@@ -141,6 +141,8 @@ int pm_k_fft_slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main
                                const float2 *back_side, cudaStream_t st);
 int pm_k_fft_slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st);
 int pm_fft_cols_per_tile(int nc);
+int pm_k_power_spectrum(pm_plan *p, const float *rho, int nbins, double *psum, double *pcnt,
+                        cudaStream_t st);
 
 // pm_poisson.cu
 int pm_k_sin2_table(pm_plan *p);

@@ -116,6 +116,17 @@ PM_API int pm_poisson(pm_plan *plan, const float *rho_d, double a, double omega_
                pm_stream_t stream);
 
 /*
+ * Matter power spectrum of a density mesh (SURVEY 8f row f3 -- the reference has no estimator;
+ * the acceptance check "P(k) within 0.1 %" needs one).  Reuses the forward half of the Poisson
+ * transform: psum_d[b] = sum of w*|rho_k|^2 over the modes with round(|k|) == b (integer frequency
+ * units), pcnt_d[b] = sum of w, w = 2 for the modes whose Hermitian partner is not stored.
+ * P(b) = psum/pcnt / (mean(rho)^2 * Nc^6) is the spectrum of the density contrast.  Power-of-two
+ * meshes, single-GPU plans.  The plan's spectrum scratch is overwritten; rho_d is not.
+ */
+PM_API int pm_power_spectrum(pm_plan *plan, const float *rho_d, int nbins, double *psum_d,
+                             double *pcnt_d, pm_stream_t stream);
+
+/*
  * integrate(positions, velocities, a_val, f_a1, da, potentials) (src/integrate.py:15-97):
  * CIC force gather (central difference of phi at the 8 corners), kick and drift with periodic
  * wrap, fused in one kernel; pos_d and vel_d are updated in place.  f_a1 is the host scalar

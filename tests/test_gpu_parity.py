@@ -403,6 +403,52 @@ def test_numpy_drop_in_signatures(pm, golden_dir):
     assert rel_l2(vel, g["vel_1"]) <= REL_L2
 
 
+@pytest.mark.parametrize("n", [32, 64, 128])
+def test_device_power_spectrum_matches_estimator(pm, n):
+    """pm_power_spectrum (forward half of the hand-written FFT + on-device binning) against the
+    NumPy estimator the parity tests use, on a clustered density."""
+    cfg = O.Config(N_CELLS=n, N_PARTS=n // 2)
+    pm.set_config(cfg_ns(cfg))
+    rs = np.random.RandomState(n)
+    npart = (n // 2) ** 3
+    blob = rs.normal(n / 2, n / 10.0, size=(3, npart // 2))
+    uni = rs.uniform(0, n, size=(3, npart - npart // 2))
+    pos = (np.concatenate([blob, uni], axis=1) % n).astype(np.float32)
+    rho = pm.density(dev(np.ascontiguousarray(pos)), 8.0)
+    k, p = pm.analysis.power_spectrum(rho)
+    kc, pc = O.power_spectrum(rho.cpu().numpy())
+    assert k.shape[0] == n // 2 - 1 and len(pc) == n // 2 - 1
+    assert np.allclose(p.cpu().numpy(), pc, rtol=2e-5, atol=0)
+    proj = pm.analysis.project(rho, 5).cpu().numpy()
+    assert np.allclose(proj, rho.cpu().numpy()[:5].astype(np.float64).sum(axis=0), rtol=1e-12)
+
+
+def test_simulator_loop_equals_manual_steps(pm, golden_dir):
+    """pmesh.simulator: the reference's while-loop (pmesh.py:56-63) on resident state; on_step sees
+    the PRE-step density with the POST-step particles."""
+    g, cfg = load_case(golden_dir, "free16")
+    c = cfg_ns(cfg)
+    pm.set_config(c)
+    pos, vel = dev(g["pos0"]), dev(g["vel0"])
+    seen = []
+
+    def on_step(i, a, rho, p, v):
+        seen.append((i, a, float(rho.sum(dtype=torch.float64)), p.clone(), v.clone()))
+
+    pm.simulator(pos, vel, on_step=on_step, max_steps=3)
+    p2, v2 = dev(g["pos0"]), dev(g["vel0"])
+    sched = pm.loop_scale_factors(c)
+    for i in range(3):
+        a, da = sched[i]
+        rho = pm.density(p2, (c.N_CELLS / c.N_PARTS) ** 3)
+        pm.advance_time(rho, p2, v2, pm.fourier_grid(), a, da)
+        assert seen[i][0] == i and seen[i][1] == a + da
+        assert abs(seen[i][2] - float(rho.sum(dtype=torch.float64))) <= 1e-6 * abs(seen[i][2])
+        assert rel_l2_periodic(seen[i][3].cpu().numpy(), p2.cpu().numpy(), c.N_CELLS) <= 1e-6
+    assert rel_l2_periodic(pos.cpu().numpy(), g["pos_3"], c.N_CELLS) <= REL_L2
+    assert rel_l2(vel.cpu().numpy(), g["vel_3"]) <= REL_L2
+
+
 def test_errors_are_loud(pm):
     cfg = O.Config(N_CELLS=16, N_PARTS=8)
     pm.set_config(cfg_ns(cfg))
