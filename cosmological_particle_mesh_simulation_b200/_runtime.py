@@ -110,7 +110,7 @@ EXPORTED_SYMBOLS = (
     "pm_plan_create_slab", "pm_slab_buffer", "pm_slab_load", "pm_slab_count", "pm_slab_entries",
     "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_rows_forward", "pm_slab_fft_y_forward",
     "pm_slab_fft_z", "pm_slab_fft_y_inverse", "pm_slab_fft_rows_inverse", "pm_slab_gather",
-    "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export",
+    "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export", "pm_power_spectrum",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")
