@@ -52,11 +52,7 @@ constexpr int kPitch = kCols + 1;  // +1: the split-off Nyquist column of the pa
 // hold fewer butterflies than that many threads)
 template <int N>
 constexpr int kThr = (N >= 2048) ? 512 : ((N >= 256) ? PM_FFT_THREADS : 256);
-// Column kernels: how many butterflies' worth of global loads a thread issues before it starts
-// computing (memory-level parallelism vs registers), and the CTAs/SM the register budget targets.
-#ifndef PM_FFT_BATCH
-#define PM_FFT_BATCH 2
-#endif
+// Column kernels: the CTAs/SM the register budget targets (3 tiles of 72 KB fit an SM at Nc = 512).
 #ifndef PM_FFT_MINB
 #define PM_FFT_MINB 3
 #endif
