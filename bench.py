@@ -26,6 +26,7 @@ tests/test_oracle_golden.py pins bit-for-bit to the reference's own code) with a
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -107,10 +108,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # workload
 # ------------------------------------------------------------------------------------------------
-def make_particles_torch(n_parts, n_cells, device, seed=38):
+VEL_SIGMA = 0.05   # code units; ~0.05 cells of drift per axis per step at a = 0.01 (da*f/(a+da)^2 ~ 1)
+
+
+def make_particles_torch(n_parts, n_cells, device, seed=38, vel_sigma=VEL_SIGMA):
     """Lattice (zeldovich.py:79-83: row-0 coordinate slowest, +0.5) + uniform(-2,2) jitter
-    (zeldovich.py:89-91) wrapped to [0, Nc); zero initial velocities.  Generated on the host with
-    torch's CPU generator (deterministic), float32."""
+    (zeldovich.py:89-91) wrapped to [0, Nc); Gaussian velocities of rms `vel_sigma` per axis, so
+    that ~10 % of the particles change cell in a step as in a running simulation (the reference's
+    probed maximum drift is 0.125 cells per step).  Generated on the host with torch's
+    CPU generator (deterministic), float32."""
     import torch
     g = torch.Generator().manual_seed(seed)
     res = n_cells / n_parts
@@ -123,11 +129,11 @@ def make_particles_torch(n_parts, n_cells, device, seed=38):
         jit = (torch.rand(npart, generator=g, dtype=torch.float64) * 4.0 - 2.0)
         pos[d] = torch.remainder(ax[comps[d]] + jit, float(n_cells)).to(torch.float32)
     pos.clamp_(max=float(n_cells))
-    vel = torch.zeros((3, npart), dtype=torch.float32)
+    vel = (torch.randn((3, npart), generator=g, dtype=torch.float32) * vel_sigma)
     return pos, vel
 
 
-def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38):
+def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38, vel_sigma=VEL_SIGMA):
     """The same IC-like particle load (lattice + uniform(-2,2) jitter), generated on the GPU for ONE
     slab: only lattice planes that can land in the slab are visited, the jitter is a counter-based
     hash of the global particle index so every rank draws the same numbers.  Used for the large
@@ -142,8 +148,8 @@ def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38):
         v &= (1 << 64) - 1
         return v - (1 << 64) if v >= (1 << 63) else v
 
-    def uniform(idx, stream):   # idx: int64 tensor -> float64 in [0, 1)
-        x = idx * 3 + stream + i64(seed * 0x9E3779B97F4A7C15)
+    def uniform(idx, stream, salt=0):   # idx: int64 tensor -> float64 in [0, 1)
+        x = idx * 3 + stream + i64((seed + 1000003 * salt) * 0x9E3779B97F4A7C15)
         x = (x ^ (x >> 30)) * (-4658895280553007687)          # 0xBF58476D1CE4E5B9 as int64
         x = (x ^ (x >> 27)) * (-7723592293110705685)          # 0x94D049BB133111EB as int64
         x = x ^ (x >> 31)
@@ -155,7 +161,7 @@ def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38):
     if iz_hi - iz_lo >= n_parts:
         izs = torch.arange(n_parts, device=device, dtype=torch.int64)
     iy = torch.arange(n_parts, device=device, dtype=torch.int64)
-    out_p, out_i = [], []
+    out_p, out_v, out_i = [], [], []
     chunk = max(1, min(n_parts, (1 << 25) // max(1, n_parts * izs.numel())))
     for ix0 in range(0, n_parts, chunk):
         ix = torch.arange(ix0, min(n_parts, ix0 + chunk), device=device, dtype=torch.int64)
@@ -170,11 +176,18 @@ def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38):
         for d in (0, 1):
             c = ((gid // (n_parts * n_parts)) if d == 0 else ((gid // n_parts) % n_parts)).to(torch.float64)
             p[d] = torch.remainder(c * res + 0.5 + uniform(gid, d) * 4.0 - 2.0, float(n_cells)).to(torch.float32)
+        v = torch.empty_like(p)
+        for d in range(3):      # Box-Muller on two more hash streams per axis
+            u1 = uniform(gid, d, 1).clamp_(min=1e-300)
+            u2 = uniform(gid, d, 2)
+            v[d] = (torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2.0 * math.pi * u2) * vel_sigma).to(torch.float32)
         out_p.append(p)
+        out_v.append(v)
         out_i.append(gid.to(torch.int32))
     pos = torch.cat(out_p, dim=1).clamp_(max=float(n_cells)).contiguous()
+    vel = torch.cat(out_v, dim=1).contiguous()
     ids = torch.cat(out_i).contiguous()
-    return pos, torch.zeros_like(pos), ids
+    return pos, vel, ids
 
 
 def cfg_namespace(n_parts, n_cells, steps_cfg=1000):
@@ -196,7 +209,7 @@ def stage_alg_bytes(npart, n_cells):
         "deposit": 12 * npart + 4 * m,               # SURVEY 8d deposit row
         "green": 8 * m,                              # read + write half spectrum
         "gather_kick_drift": 48 * npart + 4 * m,     # SURVEY 8d gather row
-        "sort": 4 * 16 * npart + 4 * npart,          # 4 radix passes over (key,index) r+w + histogram read
+        "sort": 8 * npart + 8 * npart,               # read keys + previous keys; write sorted keys + order
         "fft_r2c": 24 * m, "fft_c2r": 24 * m,
     }
 
@@ -279,13 +292,14 @@ def run_slab(args, rank, world, local_rank):
         dist.all_reduce(cnt)
         assert int(cnt.item()) == npart, (int(cnt.item()), npart)
         del pl, vl, il
-        particles_desc = "lattice + uniform(-2,2) jitter (counter-based hash, seed 38), generated per slab on the GPU"
+        particles_desc = ("lattice + uniform(-2,2) jitter, Gaussian velocities rms %g (counter-based hash, seed 38), "
+                          "generated per slab on the GPU" % VEL_SIGMA)
     else:
         pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
         pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
         ranks = slab.make_ranks(n_cells, pos, vel, comm, device=dev)
         del pos, vel
-        particles_desc = "lattice + uniform(-2,2) jitter, seed 38"
+        particles_desc = "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA
     torch.cuda.empty_cache()
     sched = pm.loop_scale_factors(cfg)
 
@@ -458,6 +472,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = pm.launch_count() - launches0
+    sort_n, sort_movers, sort_mode = state.sort_stats()
+    fft_sync_errors = int(rt.lib().pm_plan_fft_sync_errors(plan.handle))
     import ctypes
     import numpy as np
     nst = len(rt.STAGE_NAMES)
@@ -519,7 +535,11 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step "
                                "(CIC deposit + FFT Poisson + gather/kick/drift), BASELINE configs[1]",
-                   "n_parts": n_parts, "n_cells": n_cells, "particles": "lattice + uniform(-2,2) jitter, seed 38",
+                   "n_parts": n_parts, "n_cells": n_cells,
+                   "particles": "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA,
+                   "sort": {"mode": sort_mode, "mover_fraction_last_step": sort_movers / max(sort_n, 1)},
+                   "fft": {"fused_plane_passes": os.environ.get("PM_FFT_FUSE", "1") != "0",
+                           "sync_errors": fft_sync_errors},
                    "l2": "inputs larger than L2 (201 MB particles rows, 537 MB meshes vs 126 MB L2)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab path pending)"},
         "clocks": clocks,

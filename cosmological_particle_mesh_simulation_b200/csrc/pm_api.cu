@@ -24,8 +24,9 @@ int key_bits_for(int nc)
 // Sizes of every workspace segment, in the order they are carved.
 struct Layout {
     size_t keys, iota, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2, tw,
-        rpos, rvel, rid, tbuf, leave_cnt, leave_slot, mig, total;
-    int64_t leave_cap;
+        rpos, rvel, rid, tbuf, leave_cnt, leave_slot, leave_sorted, mig, inc_a, inc_b, inc_tile, fft_sync,
+        total;
+    int64_t leave_cap, inc_bcap;
 };
 
 struct Geometry {
@@ -78,10 +79,18 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->leave_cap = g.slab ? (int64_t)((npad / 32 > 65536) ? npad / 32 : 65536) : 0;
     L->leave_cnt = g.slab ? align_up((size_t)g.nranks * 4) : 0;
     L->leave_slot = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 4) : 0;
+    L->leave_sorted = g.slab ? align_up((size_t)L->leave_cap * 4) : 0;
     L->mig = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 7 * 4) : 0;
-    L->total = L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
+    // incremental sort: stayers (np), movers in and out (capacity each), tile tables
+    L->inc_bcap = pm_sort_mover_capacity((int64_t)npad);
+    L->inc_a = align_up(npad * 8);
+    L->inc_b = align_up((size_t)L->inc_bcap * 8);
+    L->inc_tile = align_up(((size_t)pm_sort_tiles((int64_t)npad) + 2) * 4);
+    L->fft_sync = align_up((size_t)(2 * (nc + 1) + 1) * 4);
+    L->total = L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
                L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw +
-               2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot + 2 * L->mig;
+               2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot +
+               L->leave_sorted + 2 * L->mig + L->inc_a + 2 * L->inc_b + 2 * L->inc_tile;
     return PM_OK;
 }
 
@@ -222,9 +231,35 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         p->tbuf[1] = (float2 *)c;     c += L.tbuf;
         p->leave_cnt = (uint32_t *)c; c += L.leave_cnt;
         p->leave_slot = (uint32_t *)c; c += L.leave_slot;
+        p->leave_sorted = (uint32_t *)c; c += L.leave_sorted;
         p->mig_send = (float *)c;     c += L.mig;
         p->mig_recv = (float *)c;     c += L.mig;
         p->leave_cap = L.leave_cap;
+    }
+    p->inc_a = (uint64_t *)c;         c += L.inc_a;
+    p->inc_b = (uint64_t *)c;         c += L.inc_b;
+    p->inc_bs = (uint64_t *)c;        c += L.inc_b;
+    p->inc_tile = (uint32_t *)c;      c += L.inc_tile;
+    p->inc_split = (uint32_t *)c;     c += L.inc_tile;
+    p->inc_bcap = L.inc_bcap;
+    p->fft_sync = (unsigned *)c;      c += L.fft_sync;
+    {
+        const char *fu = getenv("PM_FFT_FUSE");   // "0": separate row and y launches (A/B checks)
+        const char *lg = getenv("PM_FFT_LAG");
+        p->fft_fuse = !(fu && strcmp(fu, "0") == 0);
+        p->fft_lag = lg ? atoi(lg) : 12;
+        if (p->fft_lag < 1) p->fft_lag = 1;
+        if (p->fft_lag > n_cells) p->fft_lag = n_cells;
+    }
+    {
+        const char *sm = getenv("PM_SORT");   // "full" forces the radix sort of every entry (A/B checks)
+        p->sort_mode = (sm && strcmp(sm, "full") == 0) ? PM_SORT_FULL : PM_SORT_AUTO;
+    }
+    if (cudaHostAlloc((void **)&p->h_word, 64, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        p->h_word = nullptr;
+        pm_plan_destroy(p);
+        return PM_ERR_NOMEM;
     }
 
     if (p->have_fft && (cufftSetWorkArea(p->r2c, p->fft_work) != CUFFT_SUCCESS ||
@@ -238,6 +273,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         p->own_fft = pm_fft_supported(n_cells) && (g.slab || !(be && strcmp(be, "cufft") == 0));
     }
     if (rc == PM_OK && pm_fft_supported(n_cells)) rc = pm_k_fft_tables(p);
+    if (rc == PM_OK) rc = (int)cudaMemset(p->fft_sync, 0, sizeof(unsigned));
     if (rc == PM_OK) rc = pm_k_iota(p->iota, np_capacity, 0);
     if (rc == PM_OK) rc = (int)cudaStreamSynchronize(0);
     if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);
@@ -283,6 +319,7 @@ int pm_plan_destroy(pm_plan *p)
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_down) cudaStreamDestroy(p->s_down);
     if (p->ws) cudaFree(p->ws);
+    if (p->h_word) cudaFreeHost(p->h_word);
     if (p->prof_ev) {
         for (int i = 0; i < p->prof_cap * (PM_NUM_STAGES + 1); ++i) cudaEventDestroy(p->prof_ev[i]);
         free(p->prof_ev);
@@ -302,7 +339,42 @@ int pm_plan_set_fft_backend(pm_plan *p, int backend)
     return PM_OK;
 }
 
+int pm_plan_set_sort_mode(pm_plan *p, int mode)
+{
+    if (!p || (mode != PM_SORT_AUTO && mode != PM_SORT_FULL)) return PM_ERR_INVALID;
+    p->sort_mode = mode;
+    return PM_OK;
+}
+
+int pm_plan_sort_stats(const pm_plan *p, int64_t *entries, int64_t *movers, int *mode)
+{
+    if (!p) return PM_ERR_INVALID;
+    if (entries) *entries = p->sort_last_n;
+    if (movers) *movers = p->sort_last_movers;
+    if (mode) *mode = p->sort_last_mode;
+    return PM_OK;
+}
+
 int pm_plan_fft_backend(const pm_plan *p) { return p ? (p->own_fft ? 0 : 1) : PM_ERR_INVALID; }
+
+int pm_plan_set_fft_fuse(pm_plan *p, int fuse, int lag)
+{
+    if (!p || lag < 0 || lag > p->nc) return PM_ERR_INVALID;
+    p->fft_fuse = (fuse != 0);
+    if (lag > 0) p->fft_lag = lag;
+    return PM_OK;
+}
+
+int pm_plan_fft_sync_errors(pm_plan *p)
+{
+    if (!p) return PM_ERR_INVALID;
+    DeviceGuard guard;
+    int rc = guard.enter(p->device);
+    if (rc != PM_OK) return rc;
+    unsigned v = 0;
+    PM_CUDA(cudaMemcpy(&v, p->fft_sync, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    return v ? 1 : 0;
+}
 int64_t pm_plan_np_capacity(const pm_plan *p) { return p ? p->np_cap : 0; }
 
 #define PM_ARGS(cond)                     \
@@ -339,8 +411,9 @@ int pm_sort_by_cell(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_s
     PM_TRY(guard.enter(p->device));
     cudaStream_t st = pm_cu(stream);
     p->rkeys_valid = false;
+    p->rsorted_n = 0;
     PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
-    PM_TRY(pm_k_sort(p, np, st));
+    PM_TRY(pm_k_sort(p, np, 0, st));
     if (np == 0) return PM_OK;
     if (keys_sorted_d)
         PM_CUDA(cudaMemcpyAsync(keys_sorted_d, p->keys_sorted, (size_t)np * 4,
@@ -358,8 +431,9 @@ int pm_deposit_cic(pm_plan *p, const float *pos_d, int64_t np, double mass, floa
     PM_TRY(guard.enter(p->device));
     cudaStream_t st = pm_cu(stream);
     p->rkeys_valid = false;
+    p->rsorted_n = 0;
     PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
-    PM_TRY(pm_k_sort(p, np, st));
+    PM_TRY(pm_k_sort(p, np, 0, st));
     PM_TRY(pm_k_row_offsets(p, np, st));
     return pm_k_deposit(p, pos_d, np, mass, rho_d, st);
 }
@@ -401,10 +475,11 @@ int pm_step(pm_plan *p, float *pos_d, float *vel_d, int64_t np, double mass, dou
     cudaStream_t st = pm_cu(stream);
     float *rho = rho_d ? rho_d : p->mesh;
     p->rkeys_valid = false;
+    p->rsorted_n = 0;
     pm_prof_mark(p, 0, st);
     PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
     pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
-    PM_TRY(pm_k_sort(p, np, st));
+    PM_TRY(pm_k_sort(p, np, 0, st));
     pm_prof_mark(p, PM_STAGE_SORT + 1, st);
     PM_TRY(pm_k_row_offsets(p, np, st));
     pm_prof_mark(p, PM_STAGE_ROWS + 1, st);
@@ -460,9 +535,12 @@ static int resident_step(pm_plan *p, double mass, double a, double da, double f_
     const int64_t np = p->rnp;
     float *rho = rho_d ? rho_d : p->mesh;
     pm_prof_mark(p, 0, st);
-    if (!p->rkeys_valid) PM_TRY(pm_k_cell_keys(p, p->rpos[p->rcur], np, p->rstride, p->keys, nullptr, st));
+    if (!p->rkeys_valid) {
+        PM_TRY(pm_k_cell_keys(p, p->rpos[p->rcur], np, p->rstride, p->keys, nullptr, st));
+        p->rsorted_n = 0;
+    }
     pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
-    PM_TRY(pm_k_sort(p, np, st));
+    PM_TRY(pm_k_sort(p, np, p->rsorted_n, st));
     pm_prof_mark(p, PM_STAGE_SORT + 1, st);
     PM_TRY(pm_k_row_offsets(p, np, st));
     pm_prof_mark(p, PM_STAGE_ROWS + 1, st);
@@ -474,6 +552,7 @@ static int resident_step(pm_plan *p, double mass, double a, double da, double f_
     if (p->prof_ev && p->prof_n < p->prof_cap) ++p->prof_n;
     p->rcur ^= 1;
     p->rkeys_valid = (np > 0);
+    p->rsorted_n = np;   // set rcur is stored in the order of this step's sort
     return PM_OK;
 }
 
@@ -488,6 +567,7 @@ int pm_particles_load(pm_plan *p, const float *pos_d, const float *vel_d, int64_
     p->rcur = 0;
     p->rnp = p->rtotal = np;
     p->rkeys_valid = false;
+    p->rsorted_n = 0;
     if (np == 0) return PM_OK;
     (void)b;
     const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
@@ -542,6 +622,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     p->rcur = 0;
     p->rnp = np;
     p->rkeys_valid = false;
+    p->rsorted_n = 0;
     const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
     (void)pbytes;
     if (np) {
@@ -552,7 +633,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     PM_CUDA(cudaEventRecord(p->ev_a, p->s_up));
     cudaStream_t st = p->s_main;
     PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->rstride, p->keys, nullptr, st));
-    PM_TRY(pm_k_sort(p, np, st));
+    PM_TRY(pm_k_sort(p, np, 0, st));
     PM_TRY(pm_k_row_offsets(p, np, st));
     PM_TRY(pm_k_deposit(p, p->rpos[0], p->rstride, mass, p->mesh, st));
     if (rho_h) {

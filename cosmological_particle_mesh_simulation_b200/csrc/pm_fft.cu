@@ -279,23 +279,27 @@ __device__ __forceinline__ void butterfly2(int u, const float2 *tw, Ld4 ld, St4 
 // Column FFT pass.  A tile is N points (stride `gs` float2 apart) x 16 adjacent columns, held in
 // shared memory as [N][16] float2 (128-byte rows: a quarter-warp's 16-byte accesses cover one row,
 // conflict-free), followed by the split-off Nyquist column [N] and the twiddle table [N].
-template <int N, int MODE>
-__global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
+// CG: global loads bypass L1 (ld.global.cg).  The plane kernels below read data that another CTA
+// of the same launch wrote moments ago; L1 is not coherent across SMs, L2 is.
+template <bool CG, class T>
+__device__ __forceinline__ T pm_ld(const T *p)
 {
-    extern __shared__ float2 s_tile[];
+    if constexpr (CG) return __ldcg(p);
+    else return *p;
+}
+
+// One tile of a column pass.  s_tile: [N][cols] float2, s_x: [N] (split-off Nyquist column),
+// s_tw: [N] twiddles, already loaded and visible.
+template <int N, int MODE, bool CG>
+__device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, float2 *s_tile,
+                                              float2 *s_x, const float2 *s_tw)
+{
     constexpr int H = N / 2;
     constexpr int S = fft_stages(N);
     constexpr int CP = kColsCN<N> / 2;       // column pairs
     const int tid = threadIdx.x;
-    float2 *s_x = s_tile + N * kColsCN<N>;   // extra column
-    // Twiddles live in shared memory: with the carveout these tiles need, L1 is too small to keep
-    // a __ldg table resident against the streaming tile traffic.  A quarter-warp reads one entry.
-    float2 *s_tw = s_x + N;
-    for (int m = tid; m < N; m += kThrC<N>) s_tw[m] = a.tw[m];
-    __syncthreads();
 
     // ---- which tile ----
-    const int t = blockIdx.x;
     float2 *g;            // first element of the tile
     size_t gs;            // stride between successive points
     bool extra = false;   // y pass, kx-tile 0: also carries the split-off Nyquist column
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
             if (w < NB * CP) {
                 auto ld = [&](int pos) -> float4 {
                     if (src == 0) return sm4(pos, cp);
-                    float4 q = *reinterpret_cast<const float4 *>(g + (size_t)pos * gs + 2 * cp);
+                    float4 q = pm_ld<CG>(reinterpret_cast<const float4 *>(g + (size_t)pos * gs + 2 * cp));
                     if (extra && cp == 0 && FWD) q.y = 0.0f;  // packed slot: real part = DC column
                     return q;
                 };
@@ -363,8 +367,8 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
             for (int u = tid; u < NB; u += kThrC<N>) {
                 auto ld = [&](int pos) -> float2 {
                     if (src == 0) return s_x[pos];
-                    if (FWD) return make_float2(g[(size_t)pos * gs].y, 0.0f);  // Nyquist part of the packed slot
-                    return gx[pos];
+                    if (FWD) return make_float2(pm_ld<CG>(g + (size_t)pos * gs).y, 0.0f);  // Nyquist part of the packed slot
+                    return pm_ld<CG>(gx + pos);
                 };
                 auto st = [&](int pos, float2 v) {
                     if (dst == 0 || !FWD) s_x[pos] = v;
@@ -455,18 +459,33 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
     }
 }
 
+// Column FFT pass, one tile per CTA.  Twiddles live in shared memory: with the carveout these
+// tiles need, L1 is too small to keep a __ldg table resident against the streaming tile traffic.
+template <int N, int MODE>
+__global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
+{
+    extern __shared__ float2 s_dyn[];
+    float2 *s_tile = s_dyn;
+    float2 *s_x = s_tile + N * kColsCN<N>;   // extra column
+    float2 *s_tw = s_x + N;
+    for (int m = threadIdx.x; m < N; m += kThrC<N>) s_tw[m] = a.tw[m];
+    __syncthreads();
+    fft_cols_tile<N, MODE, false>(a, blockIdx.x, s_tile, s_x, s_tw);
+}
+
 // Row pass: 16 x-rows per CTA, each an (N/2)-point complex FFT of z_j = x_2j + i x_2j+1 plus the
 // real-transform split (forward) or merge (inverse).  Global accesses run along the row
 // (coalesced), the butterflies run across the 16 rows (conflict-free): the tile is [N/2][17].
 // The split/merge pairs k with N/2-k, so it wants natural order: the last forward stage (and the
 // first inverse stage) is done out of place -- read everything, barrier, write to the natural
 // positions -- which keeps every shared-memory access of the kernel free of bank conflicts.
-template <int N, bool FWD>
-__global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__ in,
-                                                       float2 *__restrict__ out,
-                                                       const float2 *__restrict__ tw)
+// One 16-row tile of a row pass.  s_tile: [N/2][17] float2; s_tw: [N] twiddles in shared memory
+// (they only need to be visible after the first barrier; `tw` is the same table in global memory).
+template <int N, bool FWD, bool CG>
+__device__ __forceinline__ void fft_rows_tile(const float2 *__restrict__ in, float2 *__restrict__ out,
+                                              const float2 *__restrict__ tw, const size_t row0,
+                                              float2 *s_tile, const float2 *s_tw)
 {
-    extern __shared__ float2 s_tile[];
     constexpr int H = N / 2;
     constexpr int S = fft_stages(H);
     constexpr int RL = fft_radix(H, S - 1);   // radix of the last DIF stage (sub-length 1)
@@ -474,10 +493,7 @@ __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__
     constexpr int ITL = (NBL * kCols + kThr<N> - 1) / kThr<N>;
     constexpr int LD_IT = kCols * H / kThr<N>;   // tile elements per thread
     const int tid = threadIdx.x;
-    const size_t row0 = (size_t)blockIdx.x * kCols;
     auto sm = [&](int pos, int c) -> float2 & { return s_tile[pos * kPitch + c]; };
-    float2 *s_tw = s_tile + H * kPitch;   // N-entry twiddle table (visible after the first barrier)
-    for (int m = tid; m < N; m += kThr<N>) s_tw[m] = tw[m];
 
     auto run_stage = [&](auto st_tag, auto fwd_tag) {
         constexpr int ST = decltype(st_tag)::value;
@@ -503,7 +519,7 @@ __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__
 #pragma unroll
             for (int it = 0; it < LD_IT; ++it) {
                 const int idx = it * kThr<N> + tid;
-                buf[it] = in[(row0 + idx / H) * H + idx % H];
+                buf[it] = in[(row0 + idx / H) * H + idx % H];   // rho: written by an earlier launch
             }
 #pragma unroll
             for (int it = 0; it < LD_IT; ++it) {
@@ -562,12 +578,12 @@ __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__
         for (int it = 0; it < LD_IT; ++it) {
             const int idx = it * kThr<N> + tid;
             const int b = idx / H, k = idx % H;
-            const float2 A = in[(row0 + b) * H + k];
+            const float2 A = pm_ld<CG>(in + (row0 + b) * H + k);
             float2 Z;
             if (k == 0) {
                 Z = make_float2(A.x + A.y, A.x - A.y);  // (DC + Nyq) + i (DC - Nyq)
             } else {
-                const float2 Bm = in[(row0 + b) * H + (H - k)];
+                const float2 Bm = pm_ld<CG>(in + (row0 + b) * H + (H - k));
                 const float2 P = make_float2(A.x + Bm.x, A.y - Bm.y);   // A + conj(B)
                 const float2 Q = make_float2(A.x - Bm.x, A.y + Bm.y);   // A - conj(B)
                 const float2 t = cmulc(Q, __ldg(tw + k));               // conj(w^k) * Q (before the first barrier)
@@ -612,6 +628,106 @@ __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__
     }
 }
 
+template <int N, bool FWD>
+__global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__ in,
+                                                       float2 *__restrict__ out,
+                                                       const float2 *__restrict__ tw)
+{
+    extern __shared__ float2 s_dyn[];
+    float2 *s_tw = s_dyn + (N / 2) * kPitch;   // N-entry twiddle table (visible after the first barrier)
+    for (int m = threadIdx.x; m < N; m += kThr<N>) s_tw[m] = tw[m];
+    fft_rows_tile<N, FWD, false>(in, out, tw, (size_t)blockIdx.x * kCols, s_dyn, s_tw);
+}
+
+// ---- x and y passes of one direction in ONE persistent launch ------------------------------------
+// The row pass and the y pass of a mesh plane touch the same 4*N^2 bytes.  Run as two launches
+// over the whole mesh, the spectrum makes a round trip through HBM between them (the mesh is
+// several times the 126 MB L2).  k_fft_plane hands out work items through a ticket counter in an
+// order that keeps the consumer of a plane `lag` planes behind its producer:
+//     forward:  slot q = [row tiles of plane q][y tiles of plane q - lag]
+//     inverse:  slot q = [y tiles of plane q][row tiles of plane q - lag]
+// so the intermediate plane is still in L2 when it is read back and each direction moves 8*N^3
+// bytes through HBM instead of 16*N^3.  A consumer item waits (acquire) on its plane's counter of
+// finished producer items; producers never wait and tickets are taken in order, so every wait is
+// on an item some running CTA already holds: no deadlock, whatever the number of resident CTAs.
+// Consumers read the intermediate with ld.global.cg (L1 is not coherent across SMs).
+struct PlaneArgs {
+    ColArgs ca;             // the y pass (axis = 1, all kx tiles)
+    const float2 *rows_in;  // forward: rho viewed as float2 rows; inverse: the spectrum
+    float2 *rows_out;       // forward: the spectrum; inverse: phi viewed as float2 rows
+    unsigned *ticket;       // [0] ticket counter, [1 + z] finished producer items of plane z
+    unsigned *err;          // set if a wait gave up (must never happen; checked by the tests)
+    int nplanes, lag;
+};
+
+__device__ __forceinline__ unsigned pm_ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int N, bool FWD>
+__global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_plane(PlaneArgs pa)
+{
+    static_assert(kThr<N> == kThrC<N>, "row and column tiles share the CTA");
+    extern __shared__ float2 s_dyn[];
+    __shared__ int s_ticket;
+    float2 *s_tw = s_dyn;                      // [N]
+    float2 *s_tile = s_dyn + N;                // column tile [N][cols] + [N], or row tile [N/2][17]
+    float2 *s_x = s_tile + N * kColsCN<N>;
+    static_assert(N * kColsCN<N> + N >= (N / 2) * kPitch, "row tile fits the column tile's space");
+    for (int m = threadIdx.x; m < N; m += kThrC<N>) s_tw[m] = pa.ca.tw[m];
+    constexpr int RPP = N / kCols;             // row tiles per plane
+    const int TPP = pa.ca.tpr;                 // y tiles per plane
+    const int nprod = FWD ? RPP : TPP;         // producer items per plane (first in a slot)
+    const int per = RPP + TPP;
+    const int total = (pa.nplanes + pa.lag) * per;
+    unsigned *done = pa.ticket + 1;
+    for (;;) {
+        __syncthreads();                       // the previous item is finished with shared memory
+        if (threadIdx.x == 0) s_ticket = (int)atomicAdd(pa.ticket, 1u);
+        __syncthreads();
+        const int t = s_ticket;
+        if (t >= total) break;
+        const int q = t / per, r = t - q * per;
+        const bool producer = r < nprod;
+        const int z = producer ? q : q - pa.lag;
+        if (z < 0 || z >= pa.nplanes) continue;
+        const int idx = producer ? r : r - nprod;
+        if (!producer) {
+            if (threadIdx.x == 0) {
+                int spins = 0;
+                while (pm_ld_acquire(done + z) < (unsigned)nprod) {
+                    if (++spins > (1 << 20) || pm_ld_acquire(pa.err) != 0u) {   // never hang the GPU
+                        atomicExch(pa.err, 1u);
+                        break;
+                    }
+                    __nanosleep(200);
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        if (FWD == producer) {
+            fft_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, pa.ca.tw,
+                                        (size_t)z * N + (size_t)idx * kCols, s_tile, s_tw);
+        } else {
+            fft_cols_tile<N, FWD ? COL_FWD : COL_INV, FWD>(pa.ca, z * TPP + idx, s_tile, s_x, s_tw);
+        }
+        if (producer) {
+            __syncthreads();                   // every thread's stores are issued
+            if (threadIdx.x == 0) {
+                __threadfence();               // ... and visible device-wide before the count moves
+                atomicAdd(done + z, 1u);
+            }
+        }
+    }
+}
+
+template <int N>
+constexpr bool kPlaneFused = (N >= 256 && N <= 1024);
+
 template <int N>
 int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
 {
@@ -655,18 +771,65 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     auto cols_fwd = k_fft_cols<N, COL_FWD>;
     auto cols_inv = k_fft_cols<N, COL_INV>;
     auto cols_fused = k_fft_cols<N, COL_FUSED>;
-    PM_LAUNCH(rows_fwd, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(rho),
-              ca.main, (const float2 *)p->tw);
-    ca.axis = 1;
-    PM_LAUNCH(cols_fwd, tiles, kThrC<N>, smem_cols, st, ca);
+    bool fused = false;
+    if constexpr (kPlaneFused<N>) fused = p->fft_fuse && p->fft_sync;
+    PlaneArgs pa;
+    int plane_grid = 0;
+    if constexpr (kPlaneFused<N>) {
+        if (fused) {
+            static bool plane_attr = false;
+            if (!plane_attr) {
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                plane_attr = true;
+            }
+            // one CTA per resident slot: the ticket loop hands every CTA its share of the items
+            int per_sm = 0;
+            PM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_plane<N, true>, kThrC<N>, smem_cols));
+            if (per_sm < 1) per_sm = 1;
+            plane_grid = per_sm * p->sm_count;
+            PM_CUDA(cudaMemsetAsync(p->fft_sync + 1, 0, sizeof(unsigned) * 2 * (N + 1), st));
+            pa.ca = ca;
+            pa.ca.axis = 1;
+            pa.err = p->fft_sync;
+            pa.nplanes = N;
+            pa.lag = p->fft_lag;
+        }
+    }
+    if (fused) {
+        if constexpr (kPlaneFused<N>) {
+            pa.rows_in = reinterpret_cast<const float2 *>(rho);
+            pa.rows_out = ca.main;
+            pa.ticket = p->fft_sync + 1;
+            auto plane_fwd = k_fft_plane<N, true>;
+            PM_LAUNCH(plane_fwd, plane_grid, kThrC<N>, smem_cols, st, pa);
+        }
+    } else {
+        PM_LAUNCH(rows_fwd, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(rho),
+                  ca.main, (const float2 *)p->tw);
+        ca.axis = 1;
+        PM_LAUNCH(cols_fwd, tiles, kThrC<N>, smem_cols, st, ca);
+    }
     pm_prof_mark(p, PM_STAGE_R2C + 1, st);
     ca.axis = 0;
     PM_LAUNCH(cols_fused, tiles + N / kColsCN<N>, kThrC<N>, smem_cols, st, ca);
     pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
-    ca.axis = 1;
-    PM_LAUNCH(cols_inv, tiles, kThrC<N>, smem_cols, st, ca);
-    PM_LAUNCH(rows_inv, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
-              reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
+    if (fused) {
+        if constexpr (kPlaneFused<N>) {
+            pa.rows_in = ca.main;
+            pa.rows_out = reinterpret_cast<float2 *>(phi);
+            pa.ticket = p->fft_sync + 1 + (N + 1);
+            auto plane_inv = k_fft_plane<N, false>;
+            PM_LAUNCH(plane_inv, plane_grid, kThrC<N>, smem_cols, st, pa);
+        }
+    } else {
+        ca.axis = 1;
+        PM_LAUNCH(cols_inv, tiles, kThrC<N>, smem_cols, st, ca);
+        PM_LAUNCH(rows_inv, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
+                  reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
+    }
     pm_prof_mark(p, PM_STAGE_C2R + 1, st);
     PM_CHECK_LAUNCH();
     return PM_OK;

@@ -57,6 +57,18 @@ struct pm_plan {
     void *cub_tmp;
     size_t cub_bytes;
     uint32_t *row_start;  // nzl*nc*dep_nseg + 1 offsets into the sorted particle list
+
+    // incremental sort (pm_sort.cu): stayers / movers as (key << 32 | slot), tile tables
+    uint64_t *inc_a, *inc_b, *inc_bs;
+    int64_t inc_bcap;       // capacity of inc_b / inc_bs in entries
+    uint32_t *inc_tile;     // movers per 2048-entry tile -> exclusive offsets; [ntiles] = total
+    uint32_t *inc_split;    // merge-path split of every output tile boundary
+    uint32_t *h_word;       // pinned host word the mover count is copied to
+    int sort_mode;          // PM_SORT_AUTO / PM_SORT_FULL
+    int64_t rsorted_n;      // the first rsorted_n entries of set rcur are stored in the order of
+                            // the previous sort and keys_sorted[] still holds the keys they had
+    int sort_last_mode;     // what the last pm_k_sort did (pm_plan_sort_stats)
+    int64_t sort_last_n, sort_last_movers;
     int dep_nseg;         // segments per mesh row in the deposit (1 unless the mesh is wide)
 
     // Poisson scratch
@@ -69,6 +81,9 @@ struct pm_plan {
     float *sin2rev;       // the same in the digit-reversed order of the hand-written FFT
     float2 *tw;           // exp(-2 pi i m / nc)
     bool own_fft;         // power-of-two mesh: pm_fft.cu path; otherwise cuFFT
+    bool fft_fuse;        // x and y passes of a direction in one persistent launch (k_fft_plane)
+    int fft_lag;          // planes between the producer and the consumer pass of that launch
+    unsigned *fft_sync;   // [0] error flag, then per direction: ticket + per-plane counters
     cufftHandle r2c, c2r;
     bool have_fft;
 
@@ -87,6 +102,7 @@ struct pm_plan {
     float2 *tbuf[2];        // all-to-all staging: [nranks][nzl][nyl][nc/2] (+ side [nranks][nzl][nyl])
     uint32_t *leave_cnt;    // [nranks] particles leaving to each rank (written by the gather kernel)
     uint32_t *leave_slot;   // [nranks][leave_cap] their storage slots
+    uint32_t *leave_sorted; // [leave_cap] one destination's slots in ascending order
     int64_t leave_cap;
     float *mig_send, *mig_recv;  // [nranks*leave_cap][7] packed (x,y,z,vx,vy,vz,id) records
     int64_t rtotal;         // entries of the current buffer set incl. dead (left) and arrived ones
@@ -105,11 +121,17 @@ static inline void pm_prof_mark(pm_plan *p, int k, cudaStream_t st)
 
 static inline cudaStream_t pm_cu(pm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// pm_particles.cu
+// pm_sort.cu
+#define PM_SORT_TILE 2048
 size_t pm_sort_temp_bytes(int64_t np, int key_bits);
+int64_t pm_sort_tiles(int64_t np);
+int64_t pm_sort_mover_capacity(int64_t np);
+int pm_k_sort(pm_plan *p, int64_t np, int64_t n_old, cudaStream_t st);
+int pm_k_sort_u32(pm_plan *p, const uint32_t *in, uint32_t *out, int64_t count, cudaStream_t st);
+
+// pm_particles.cu
 int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uint32_t *keys,
                    uint32_t *order, cudaStream_t st);
-int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st);
 int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st);
 int pm_k_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
                  cudaStream_t st);

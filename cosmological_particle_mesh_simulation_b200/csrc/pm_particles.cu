@@ -5,8 +5,6 @@
 // gather/kick/drift arithmetic below is written to be bit-identical to it given the same phi
 // (reference: src/integrate.py:27-97).  The explicit __f*_rn / __d*_rn intrinsics make the
 // rounding points visible (and keep them if the flag is ever lost).
-#include <cub/device/device_radix_sort.cuh>
-
 #include <stdlib.h>
 #include <string.h>
 
@@ -92,27 +90,6 @@ int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uin
                   p->nc, p->z0, p->nzl, keys, order);
     }
     PM_CHECK_LAUNCH();
-    return PM_OK;
-}
-
-// --------------------------------------------------------------------------------------------
-// Stable LSD radix sort of (key, original index) on the low key_bits bits.
-// --------------------------------------------------------------------------------------------
-size_t pm_sort_temp_bytes(int64_t np, int key_bits)
-{
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (const uint32_t *)nullptr, (uint32_t *)nullptr, np, 0, key_bits);
-    return bytes;
-}
-
-int pm_k_sort(pm_plan *p, int64_t np, cudaStream_t st)
-{
-    if (np == 0) return PM_OK;
-    size_t bytes = p->cub_bytes;
-    PM_CUDA(cub::DeviceRadixSort::SortPairs(p->cub_tmp, bytes, (const uint32_t *)p->keys,
-                                            p->keys_sorted, (const uint32_t *)p->iota,
-                                            p->order_sorted, np, 0, p->key_bits, st));
     return PM_OK;
 }
 
@@ -650,11 +627,11 @@ __global__ void __launch_bounds__(256) k_migrate_pack(const float *__restrict__ 
 int pm_k_migrate_pack(pm_plan *p, int dest, int64_t count, int64_t rec_offset, cudaStream_t st)
 {
     if (count == 0) return PM_OK;
-    uint32_t *sorted = p->keys_sorted;  // free between the deposit and the next sort
-    size_t bytes = p->cub_bytes;
-    PM_CUDA(cub::DeviceRadixSort::SortKeys(p->cub_tmp, bytes,
-                                           (const uint32_t *)(p->leave_slot + (size_t)dest * p->leave_cap),
-                                           sorted, count, 0, 32, st));
+    uint32_t *sorted = p->leave_sorted;
+    {
+        const int rc = pm_k_sort_u32(p, p->leave_slot + (size_t)dest * p->leave_cap, sorted, count, st);
+        if (rc != PM_OK) return rc;
+    }
     const int c = p->rcur;
     PM_LAUNCH(k_migrate_pack, (unsigned)((count + 255) / 256), 256, 0, st, p->rpos[c], p->rvel[c],
               p->rid[c], p->rstride, sorted, count, p->mig_send + rec_offset * 7);

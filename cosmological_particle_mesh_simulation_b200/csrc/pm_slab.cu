@@ -97,6 +97,7 @@ int pm_slab_load(pm_plan *p, const float *pos_d, const float *vel_d, const uint3
     p->rcur = 0;
     p->rnp = p->rtotal = np;
     p->rkeys_valid = false;
+    p->rsorted_n = 0;
     if (np == 0) return PM_OK;
     const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
     PM_CUDA(cudaMemcpy2DAsync(p->rpos[0], pitch, pos_d, w, w, 3, cudaMemcpyDeviceToDevice, st));
@@ -112,9 +113,11 @@ int pm_slab_deposit(pm_plan *p, double mass, pm_stream_t stream)
 {
     PM_SLAB_ENTER(true);
     const int64_t n = p->rtotal;
-    if (!p->rkeys_valid)
+    if (!p->rkeys_valid) {
         PM_TRY(pm_k_cell_keys(p, p->rpos[p->rcur], n, p->rstride, p->keys, nullptr, st));
-    PM_TRY(pm_k_sort(p, n, st));
+        p->rsorted_n = 0;
+    }
+    PM_TRY(pm_k_sort(p, n, p->rsorted_n, st));
     PM_TRY(pm_k_row_offsets(p, n, st));
     return pm_k_deposit_slab(p, p->rpos[p->rcur], mass, p->mesh, st);
 }
@@ -172,6 +175,7 @@ int pm_slab_gather(pm_plan *p, double a, double f_a1, double da, pm_stream_t str
     p->rcur ^= 1;
     p->rtotal = p->rnp;       // the kernel wrote the live particles, leavers now carry dead keys
     p->rkeys_valid = true;
+    p->rsorted_n = p->rnp;    // ... in the order of this step's sort (arrivals are appended behind)
     return PM_OK;
 }
 

@@ -103,6 +103,21 @@ class ResidentParticles:
                      "pm_particles_store")
         return positions, velocities
 
+    def set_sort_mode(self, mode):
+        """"auto": re-sort only the particles whose cell changed and merge them into the rest
+        (falls back to the full sort by itself); "full": radix-sort every particle every step.
+        Both give the same storage order bit for bit (include/pmstep.h, pm_plan_set_sort_mode)."""
+        code = {"auto": 0, "full": 1}[mode]
+        rt.check(rt.lib().pm_plan_set_sort_mode(self.plan.handle, code), "pm_plan_set_sort_mode")
+
+    def sort_stats(self):
+        """(entries, movers, mode) of the last sort; mode is "full" or "incremental"."""
+        import ctypes
+        n, m, mode = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+        rt.check(rt.lib().pm_plan_sort_stats(self.plan.handle, ctypes.byref(n), ctypes.byref(m),
+                                             ctypes.byref(mode)), "pm_plan_sort_stats")
+        return n.value, m.value, {1: "full", 2: "incremental"}.get(mode.value, "none")
+
     def order(self):
         """Original index of the particle in each storage slot (int32 CUDA tensor)."""
         ids = torch.empty(self.np, dtype=torch.int32, device=f"cuda:{self.device}")

@@ -75,6 +75,29 @@ PM_API int pm_plan_n_cells(const pm_plan *plan);
  * (any mesh size; also selectable with the environment variable PM_FFT_BACKEND=cufft). */
 PM_API int pm_plan_set_fft_backend(pm_plan *plan, int backend);
 PM_API int pm_plan_fft_backend(const pm_plan *plan);
+/* Hand-written FFT, meshes 256..1024: fuse != 0 (default) runs the row pass and the y pass of each
+ * direction in one persistent launch that keeps the intermediate plane in L2 (pm_fft.cu,
+ * k_fft_plane); 0 runs them as two launches (also PM_FFT_FUSE=0).  lag > 0 sets the distance in
+ * planes between the two passes (default 12, PM_FFT_LAG).  Results are identical either way.
+ * pm_plan_fft_sync_errors: 1 if a wait inside the fused launch ever gave up (a bug), else 0;
+ * synchronises the device. */
+PM_API int pm_plan_set_fft_fuse(pm_plan *plan, int fuse, int lag);
+PM_API int pm_plan_fft_sync_errors(pm_plan *plan);
+/* How the resident paths (pm_step_resident, pm_slab_deposit) order the particle list by cell key
+ * (the order fixes the deposit's summation tree and the locality of deposit and gather; the
+ * reference scatters in particle-index order, src/density.py:17, and has no counterpart):
+ *   PM_SORT_AUTO  re-sort only the entries whose cell key changed since the previous step and merge
+ *                 them into the still-sorted rest; falls back to PM_SORT_FULL when there is no
+ *                 previous order or more than 40 % of the entries moved.  One 4-byte device->host
+ *                 read (the mover count) per step.
+ *   PM_SORT_FULL  stable radix sort of every entry (also: environment variable PM_SORT=full).
+ * Both give the same order bit for bit.  pm_plan_sort_stats reports what the last sort did
+ * (mode: PM_SORT_FULL or PM_SORT_INCREMENTAL). */
+#define PM_SORT_AUTO 0
+#define PM_SORT_FULL 1
+#define PM_SORT_INCREMENTAL 2
+PM_API int pm_plan_set_sort_mode(pm_plan *plan, int mode);
+PM_API int pm_plan_sort_stats(const pm_plan *plan, int64_t *entries, int64_t *movers, int *mode);
 PM_API int64_t pm_plan_np_capacity(const pm_plan *plan);
 
 /*

@@ -255,6 +255,35 @@ def test_hand_written_fft_large_meshes_against_cufft(pm, n):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("n", [256, 512, 1024])
+def test_fused_plane_fft_equals_separate_passes_bit_for_bit(pm, n):
+    """k_fft_plane (row pass + y pass of a direction in one persistent launch, the intermediate
+    plane staying in L2) does the same arithmetic as the two separate launches: the potential must
+    be identical bit for bit, for the default lag, for lag 1 (consumers wait on their producers
+    almost every time) and for a lag of the whole mesh (all producers first)."""
+    cfg = O.Config(N_CELLS=n)
+    pm.set_config(cfg_ns(cfg))
+    rt = pm._runtime
+    g = torch.Generator(device="cuda").manual_seed(7 * n)
+    rho = torch.rand((n, n, n), generator=g, device="cuda") * 4.0
+    rho[n // 3, n // 5, n // 7] += 500.0
+    fg = pm.fourier_grid()
+    plan = rt.get_plan(n, 1, 0)
+    L = rt.lib()
+    rt.check(L.pm_plan_set_fft_fuse(plan.handle, 0, 0), "fuse off")
+    ref = pm.potential(rho, fg, 0.5)
+    for lag in (12, 1, 3, n):
+        rt.check(L.pm_plan_set_fft_fuse(plan.handle, 1, lag), "fuse on")
+        for _ in range(2):
+            phi = pm.potential(rho, fg, 0.5)
+            assert torch.equal(phi, ref), (n, lag)
+    assert L.pm_plan_fft_sync_errors(plan.handle) == 0
+    rt.check(L.pm_plan_set_fft_fuse(plan.handle, 1, 12), "fuse default")
+    del phi, ref, rho
+    pm.release_plans()
+    torch.cuda.empty_cache()
+
+
 def test_single_mode_potential(pm):
     cfg = O.Config(N_CELLS=32)
     pm.set_config(cfg_ns(cfg))
@@ -363,6 +392,47 @@ def test_resident_state_matches_stateless_steps_and_golden(pm, golden_dir, name)
         want = prev_ids[np.argsort(keys_prev[prev_ids], kind="stable")]
         assert np.array_equal(ids, want)
         prev_ids, prev_pos = ids, out_p.cpu().numpy()
+
+
+@pytest.mark.parametrize("n_parts,n_cells,vsig", [(32, 64, 0.05), (48, 64, 0.3), (40, 128, 0.02)])
+def test_incremental_sort_equals_full_sort_bit_for_bit(pm, n_parts, n_cells, vsig):
+    """The resident path re-sorts only the particles whose cell changed and merges them into the
+    still-sorted rest (pm_sort.cu).  Storage order, positions and velocities must equal those of the
+    full radix sort bit for bit, step after step, with a realistic and with a large mover fraction
+    (the latter crosses the 40 % threshold and exercises the fall-back)."""
+    cfg = types.SimpleNamespace(N_CELLS=n_cells, N_PARTS=n_parts, OMEGA_M0=0.31, OMEGA_K0=0.0,
+                                OMEGA_LAMBDA0=0.69, H0=0.68, A_INIT=0.01, A_END=1.0, STEPS=1000)
+    pm.set_config(cfg)
+    rng = np.random.default_rng(5)
+    npart = n_parts ** 3 - 37           # ragged: not a multiple of the 2048-entry tile or of 4
+    pos = rng.uniform(0, n_cells, (3, npart)).astype(np.float32)
+    pos[:, : npart // 8] = (n_cells / 2 + rng.normal(0, 1.5, (3, npart // 8))).astype(np.float32) % n_cells
+    vel = rng.normal(0, vsig, (3, npart)).astype(np.float32)
+    sched = pm.loop_scale_factors(cfg)[:6]
+    out = {}
+    for mode in ("full", "auto"):
+        st = pm.ResidentParticles(dev(pos), dev(vel))
+        st.set_sort_mode(mode)
+        seen = []
+        for a, da in sched:
+            st.step(a, da)
+            torch.cuda.synchronize()
+            seen.append(st.sort_stats())
+        p, v = torch.empty(3, npart, device="cuda"), torch.empty(3, npart, device="cuda")
+        st.store(p, v)
+        out[mode] = (st.order().cpu().numpy(), p.cpu().numpy(), v.cpu().numpy(), seen)
+        st.set_sort_mode("auto")
+    assert np.array_equal(out["full"][0], out["auto"][0])
+    assert np.array_equal(out["full"][1], out["auto"][1])
+    assert np.array_equal(out["full"][2], out["auto"][2])
+    assert all(s[2] == "full" for s in out["full"][3])
+    modes = [s[2] for s in out["auto"][3]]
+    assert modes[0] == "full"                                   # no previous order on the first step
+    fracs = [s[1] / s[0] for s in out["auto"][3][1:]]
+    if vsig <= 0.05:
+        assert all(m == "incremental" for m in modes[1:]), modes
+        assert all(0.0 < f < 0.4 for f in fracs), fracs
+    assert sorted(out["auto"][0].tolist()) == list(range(npart))
 
 
 @pytest.mark.parametrize("name", ["g16_free10", "clustered32"])
