@@ -246,6 +246,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     {
         const char *fu = getenv("PM_FFT_FUSE");   // "0": separate row and y launches (A/B checks)
         const char *lg = getenv("PM_FFT_LAG");
+        const char *v2 = getenv("PM_FFT_V2");     // "0": the three-stage radix-8 kernels
+        p->fft_v2 = !(v2 && strcmp(v2, "0") == 0);
         p->fft_fuse = !(fu && strcmp(fu, "0") == 0);
         p->fft_lag = lg ? atoi(lg) : 12;
         if (p->fft_lag < 1) p->fft_lag = 1;
@@ -356,6 +358,13 @@ int pm_plan_sort_stats(const pm_plan *p, int64_t *entries, int64_t *movers, int 
 }
 
 int pm_plan_fft_backend(const pm_plan *p) { return p ? (p->own_fft ? 0 : 1) : PM_ERR_INVALID; }
+
+int pm_plan_set_fft_variant(pm_plan *p, int two_stage)
+{
+    if (!p) return PM_ERR_INVALID;
+    p->fft_v2 = (two_stage != 0);
+    return PM_OK;
+}
 
 int pm_plan_set_fft_fuse(pm_plan *p, int fuse, int lag)
 {

@@ -639,6 +639,30 @@ __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__
     fft_rows_tile<N, FWD, false>(in, out, tw, (size_t)blockIdx.x * kCols, s_dyn, s_tw);
 }
 
+#include "pm_fft2.cuh"
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(kThr2, 2) k_fft2_cols(ColArgs a)
+{
+    extern __shared__ float2 s_dyn[];
+    float2 *s_tw = s_dyn, *s_tile = s_dyn + N;
+    for (int m = threadIdx.x; m < N; m += kThr2) s_tw[m] = a.tw[m];
+    __syncthreads();
+    fft2_cols_tile<N, MODE, false>(a, blockIdx.x, s_tile, s_tw);
+}
+
+template <int N, bool FWD>
+__global__ void __launch_bounds__(kThr2, 2) k_fft2_rows(const float2 *__restrict__ in,
+                                                        float2 *__restrict__ out,
+                                                        const float2 *__restrict__ tw)
+{
+    extern __shared__ float2 s_dyn[];
+    float2 *s_tw = s_dyn, *s_tile = s_dyn + N;
+    for (int m = threadIdx.x; m < N; m += kThr2) s_tw[m] = tw[m];
+    __syncthreads();
+    fft2_rows_tile<N, FWD, false>(in, out, (size_t)blockIdx.x * kRowsPT2<N>, s_tile, s_tw);
+}
+
 // ---- x and y passes of one direction in ONE persistent launch ------------------------------------
 // The row pass and the y pass of a mesh plane touch the same 4*N^2 bytes.  Run as two launches
 // over the whole mesh, the spectrum makes a round trip through HBM between them (the mesh is
@@ -667,18 +691,20 @@ __device__ __forceinline__ unsigned pm_ld_acquire(const unsigned *p)
     return v;
 }
 
-template <int N, bool FWD>
-__global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_plane(PlaneArgs pa)
+template <int N, bool FWD, bool V2>
+__global__ void __launch_bounds__(kThrC<N>, V2 ? 2 : PM_FFT_MINB) k_fft_plane(PlaneArgs pa)
 {
-    static_assert(kThr<N> == kThrC<N>, "row and column tiles share the CTA");
+    static_assert(kThr<N> == kThrC<N> && kThrC<N> == kThr2, "row and column tiles share the CTA");
     extern __shared__ float2 s_dyn[];
     __shared__ int s_ticket;
     float2 *s_tw = s_dyn;                      // [N]
     float2 *s_tile = s_dyn + N;                // column tile [N][cols] + [N], or row tile [N/2][17]
     float2 *s_x = s_tile + N * kColsCN<N>;
     static_assert(N * kColsCN<N> + N >= (N / 2) * kPitch, "row tile fits the column tile's space");
+    static_assert(!V2 || N * kColsCN<N> >= kRowsPT2<N> * RowFac<N>::RA * (RowFac<N>::RB + 1), "two-stage row tile fits");
     for (int m = threadIdx.x; m < N; m += kThrC<N>) s_tw[m] = pa.ca.tw[m];
-    constexpr int RPP = N / kCols;             // row tiles per plane
+    constexpr int RT = V2 ? kRowsPT2<N> : kCols;   // x-rows per row tile
+    constexpr int RPP = N / RT;                // row tiles per plane
     const int TPP = pa.ca.tpr;                 // y tiles per plane
     const int nprod = FWD ? RPP : TPP;         // producer items per plane (first in a slot)
     const int per = RPP + TPP;
@@ -710,10 +736,12 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_plane(PlaneArgs p
             __syncthreads();
         }
         if (FWD == producer) {
-            fft_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, pa.ca.tw,
-                                        (size_t)z * N + (size_t)idx * kCols, s_tile, s_tw);
+            const size_t row0 = (size_t)z * N + (size_t)idx * RT;
+            if constexpr (V2) fft2_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, row0, s_tile, s_tw);
+            else fft_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, pa.ca.tw, row0, s_tile, s_tw);
         } else {
-            fft_cols_tile<N, FWD ? COL_FWD : COL_INV, FWD>(pa.ca, z * TPP + idx, s_tile, s_x, s_tw);
+            if constexpr (V2) fft2_cols_tile<N, FWD ? COL_FWD : COL_INV, FWD>(pa.ca, z * TPP + idx, s_tile, s_tw);
+            else fft_cols_tile<N, FWD ? COL_FWD : COL_INV, FWD>(pa.ca, z * TPP + idx, s_tile, s_x, s_tw);
         }
         if (producer) {
             __syncthreads();                   // every thread's stores are issued
@@ -728,9 +756,105 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_plane(PlaneArgs p
 template <int N>
 constexpr bool kPlaneFused = (N >= 256 && N <= 1024);
 
+// The two-stage path (pm_fft2.cuh): natural order on every axis.
+template <int N>
+int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
+{
+    if constexpr (!kHasV2<N>) {
+        return PM_ERR_UNSUPPORTED;
+    } else {
+        constexpr int H = N / 2, C = kColsCN<N>;
+        constexpr int RT = kRowsPT2<N>;
+        const size_t smem_cols = ((size_t)N + (size_t)N * C) * sizeof(float2);
+        const size_t smem_rows = ((size_t)N + (size_t)RT * RowFac<N>::RA * (RowFac<N>::RB + 1)) * sizeof(float2);
+        auto rows_fwd = k_fft2_rows<N, true>;
+        auto rows_inv = k_fft2_rows<N, false>;
+        auto cols_fwd = k_fft2_cols<N, COL_FWD>;
+        auto cols_inv = k_fft2_cols<N, COL_INV>;
+        auto cols_fused = k_fft2_cols<N, COL_FUSED>;
+        auto plane_fwd = k_fft_plane<N, true, true>;
+        auto plane_inv = k_fft_plane<N, false, true>;
+        static bool attr_set = false;
+        static int plane_per_sm = 1;
+        if (!attr_set) {
+            PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+            PM_CUDA(cudaFuncSetAttribute(rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+            PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+            PM_CUDA(cudaFuncSetAttribute(cols_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+            PM_CUDA(cudaFuncSetAttribute(cols_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+            PM_CUDA(cudaFuncSetAttribute(plane_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+            PM_CUDA(cudaFuncSetAttribute(plane_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+            PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PM_CUDA(cudaFuncSetAttribute(cols_inv, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PM_CUDA(cudaFuncSetAttribute(cols_fused, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PM_CUDA(cudaFuncSetAttribute(plane_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PM_CUDA(cudaFuncSetAttribute(plane_inv, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plane_per_sm, plane_fwd, kThr2, smem_cols));
+            if (plane_per_sm < 1) plane_per_sm = 1;
+            attr_set = true;
+        }
+        ColArgs ca;
+        ca.main = p->spec;
+        ca.side = p->spec + (size_t)N * N * H;
+        ca.tw = p->tw;
+        ca.sin2 = p->sin2;
+        ca.sin2rev = p->sin2;   // natural order everywhere on this path
+        const double m = (double)N * N * N;
+        ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
+        ca.nyl = N;
+        ca.y0 = 0;
+        ca.tpr = H / C;
+        ca.kt0 = 0;
+        ca.hw = H;
+        ca.side_tiles = 1;
+        const int row_ctas = N * N / RT;
+        const int tiles = N * (H / C);
+        const bool fused = p->fft_fuse && p->fft_sync;
+        PlaneArgs pa;
+        if (fused) {
+            PM_CUDA(cudaMemsetAsync(p->fft_sync + 1, 0, sizeof(unsigned) * 2 * (N + 1), st));
+            pa.ca = ca;
+            pa.ca.axis = 1;
+            pa.err = p->fft_sync;
+            pa.nplanes = N;
+            pa.lag = p->fft_lag;
+            pa.rows_in = reinterpret_cast<const float2 *>(rho);
+            pa.rows_out = ca.main;
+            pa.ticket = p->fft_sync + 1;
+            PM_LAUNCH(plane_fwd, plane_per_sm * p->sm_count, kThr2, smem_cols, st, pa);
+        } else {
+            PM_LAUNCH(rows_fwd, row_ctas, kThr2, smem_rows, st, reinterpret_cast<const float2 *>(rho), ca.main,
+                      (const float2 *)p->tw);
+            ca.axis = 1;
+            PM_LAUNCH(cols_fwd, tiles, kThr2, smem_cols, st, ca);
+        }
+        pm_prof_mark(p, PM_STAGE_R2C + 1, st);
+        ca.axis = 0;
+        PM_LAUNCH(cols_fused, tiles + N / C, kThr2, smem_cols, st, ca);
+        pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
+        if (fused) {
+            pa.rows_in = ca.main;
+            pa.rows_out = reinterpret_cast<float2 *>(phi);
+            pa.ticket = p->fft_sync + 1 + (N + 1);
+            PM_LAUNCH(plane_inv, plane_per_sm * p->sm_count, kThr2, smem_cols, st, pa);
+        } else {
+            ca.axis = 1;
+            PM_LAUNCH(cols_inv, tiles, kThr2, smem_cols, st, ca);
+            PM_LAUNCH(rows_inv, row_ctas, kThr2, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
+                      reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
+        }
+        pm_prof_mark(p, PM_STAGE_C2R + 1, st);
+        PM_CHECK_LAUNCH();
+        return PM_OK;
+    }
+}
+
 template <int N>
 int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
 {
+    if constexpr (kHasV2<N>) {
+        if (p->fft_v2) return poisson_launch_v2<N>(p, rho, a, omega_m0, phi, st);
+    }
     constexpr int H = N / 2;
     const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
@@ -779,15 +903,15 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
         if (fused) {
             static bool plane_attr = false;
             if (!plane_attr) {
-                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 plane_attr = true;
             }
             // one CTA per resident slot: the ticket loop hands every CTA its share of the items
             int per_sm = 0;
-            PM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_plane<N, true>, kThrC<N>, smem_cols));
+            PM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_plane<N, true, false>, kThrC<N>, smem_cols));
             if (per_sm < 1) per_sm = 1;
             plane_grid = per_sm * p->sm_count;
             PM_CUDA(cudaMemsetAsync(p->fft_sync + 1, 0, sizeof(unsigned) * 2 * (N + 1), st));
@@ -803,7 +927,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
             pa.rows_in = reinterpret_cast<const float2 *>(rho);
             pa.rows_out = ca.main;
             pa.ticket = p->fft_sync + 1;
-            auto plane_fwd = k_fft_plane<N, true>;
+            auto plane_fwd = k_fft_plane<N, true, false>;
             PM_LAUNCH(plane_fwd, plane_grid, kThrC<N>, smem_cols, st, pa);
         }
     } else {
@@ -821,7 +945,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
             pa.rows_in = ca.main;
             pa.rows_out = reinterpret_cast<float2 *>(phi);
             pa.ticket = p->fft_sync + 1 + (N + 1);
-            auto plane_inv = k_fft_plane<N, false>;
+            auto plane_inv = k_fft_plane<N, false, false>;
             PM_LAUNCH(plane_inv, plane_grid, kThrC<N>, smem_cols, st, pa);
         }
     } else {

@@ -67,6 +67,7 @@ struct pm_plan {
     int sort_mode;          // PM_SORT_AUTO / PM_SORT_FULL
     int64_t rsorted_n;      // the first rsorted_n entries of set rcur are stored in the order of
                             // the previous sort and keys_sorted[] still holds the keys they had
+    bool rows_valid;        // row_start matches keys_sorted (set by the sort's merge or pm_k_row_offsets)
     int sort_last_mode;     // what the last pm_k_sort did (pm_plan_sort_stats)
     int64_t sort_last_n, sort_last_movers;
     int dep_nseg;         // segments per mesh row in the deposit (1 unless the mesh is wide)
@@ -81,6 +82,7 @@ struct pm_plan {
     float *sin2rev;       // the same in the digit-reversed order of the hand-written FFT
     float2 *tw;           // exp(-2 pi i m / nc)
     bool own_fft;         // power-of-two mesh: pm_fft.cu path; otherwise cuFFT
+    bool fft_v2;          // two-stage register-resident transforms (pm_fft2.cuh), meshes 256..1024
     bool fft_fuse;        // x and y passes of a direction in one persistent launch (k_fft_plane)
     int fft_lag;          // planes between the producer and the consumer pass of that launch
     unsigned *fft_sync;   // [0] error flag, then per direction: ticket + per-plane counters

@@ -94,61 +94,6 @@ int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uin
 }
 
 // --------------------------------------------------------------------------------------------
-// row_start[r] = first sorted particle whose mesh row (z_c*Nc + y_c) is >= r, r in [0, Nc^2].
-// One thread per boundary j in [0, np]; it fills every row that starts at j (empty rows too).
-// --------------------------------------------------------------------------------------------
-// (With the deposit's row segmentation the "rows" are row segments of xseg cells: key / xseg.)
-// Four boundaries per thread from one 16-byte load; a shift replaces the division when xseg is a
-// power of two (shift >= 0).
-__device__ __forceinline__ int64_t pm_rowseg(uint32_t key, int xseg, int shift, int64_t nrows)
-{
-    const int64_t r = shift >= 0 ? (int64_t)(key >> shift) : (int64_t)(key / (uint32_t)xseg);
-    return r > nrows ? nrows : r;
-}
-
-__global__ void __launch_bounds__(256) k_row_offsets(const uint32_t *__restrict__ keys_sorted,
-                                                     int64_t np, int xseg, int shift, int64_t nrows,
-                                                     uint32_t *__restrict__ row_start)
-{
-    // rows past the last real one (PM_KEY_DEAD entries of a slab) clamp to nrows, so
-    // row_start[nrows] is the number of live particles
-    const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (j0 > np) return;
-    uint32_t k[4];
-    if (j0 + 4 <= np) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(keys_sorted + j0);
-        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
-    } else {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) k[t] = (j0 + t < np) ? keys_sorted[j0 + t] : 0u;
-    }
-    int64_t prev = (j0 == 0) ? -1 : pm_rowseg(keys_sorted[j0 - 1], xseg, shift, nrows);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int64_t j = j0 + t;
-        if (j > np) break;
-        const int64_t cur = (j == np) ? nrows : pm_rowseg(k[t], xseg, shift, nrows);
-        for (int64_t r = prev + 1; r <= cur; ++r) row_start[r] = (uint32_t)j;
-        prev = cur;
-    }
-}
-
-int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st)
-{
-    const int xseg = p->nc / p->dep_nseg;
-    int shift = -1;
-    if ((xseg & (xseg - 1)) == 0) {
-        shift = 0;
-        while ((1 << shift) < xseg) ++shift;
-    }
-    const int64_t nthr = np / 4 + 1;
-    PM_LAUNCH(k_row_offsets, (unsigned)((nthr + 255) / 256), 256, 0, st, p->keys_sorted, np, xseg,
-              shift, (int64_t)p->nzl * p->nc * p->dep_nseg, p->row_start);
-    PM_CHECK_LAUNCH();
-    return PM_OK;
-}
-
-// --------------------------------------------------------------------------------------------
 // CIC deposit (src/density.py:7-48), deterministic and atomic-free.
 //
 // One warp owns one output mesh row (Z, y) held in shared memory (pm_acc_t, see below).  The row receives

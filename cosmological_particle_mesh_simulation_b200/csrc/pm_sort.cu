@@ -13,7 +13,8 @@
 //                  3. k_mover_partition  stayers -> A, movers -> B as 64-bit (key << 32 | slot)
 //                  4. cub radix sort of B on the key bits (stable: slots stay ascending per key)
 //                  5. k_merge_splits     merge-path split of every 2048-entry output tile
-//                  6. k_merge_tiles      merge A and B by (key, slot) -> keys_sorted, order_sorted
+//                  6. k_merge_tiles      merge A and B by (key, slot) -> keys_sorted, order_sorted,
+//                                        and the row table of the deposit (row_start) on the way
 //                Because both inputs are ordered by the composite (key, slot), the merge reproduces
 //                exactly the order a stable sort of all entries gives.  The host reads the mover
 //                count (one 4-byte copy) to size the sort of B; if more than 40 % of the entries
@@ -185,14 +186,36 @@ __global__ void __launch_bounds__(256) k_merge_splits(const uint64_t *__restrict
     split[t] = pm_merge_split(a, na, b, nb, d);
 }
 
+// row_start[r] = first sorted entry whose mesh row segment (key / xseg) is >= r, r in [0, nrows];
+// entries past the last real row (PM_KEY_DEAD of a slab) clamp to nrows, so row_start[nrows] is the
+// number of live particles.  A boundary j (between sorted entries j-1 and j) fills every row that
+// starts there, empty rows included.
+__device__ __forceinline__ int64_t pm_rowseg(uint32_t key, int xseg, int shift, int64_t nrows)
+{
+    const int64_t r = shift >= 0 ? (int64_t)(key >> shift) : (int64_t)(key / (uint32_t)xseg);
+    return r > nrows ? nrows : r;
+}
+
+struct RowArgs {
+    uint32_t *row_start;
+    int xseg, shift;
+    int64_t nrows;
+};
+
+// shared-memory index of element j of a 64-bit tile: one pad slot per 16 elements, so that threads
+// walking 8 consecutive elements each (stride 64 bytes) spread over all banks
+__device__ __forceinline__ uint32_t pm_pad(uint32_t j) { return j + (j >> 4); }
+constexpr int kTilePad = kTile + kTile / 16;
+
 __global__ void __launch_bounds__(kThreads) k_merge_tiles(const uint64_t *__restrict__ a,
                                                           const uint64_t *__restrict__ b,
                                                           const uint32_t *__restrict__ split,
                                                           uint32_t n, uint32_t *__restrict__ keys_sorted,
-                                                          uint32_t *__restrict__ order_sorted)
+                                                          uint32_t *__restrict__ order_sorted, RowArgs ra)
 {
-    __shared__ uint64_t s_in[kTile];
-    __shared__ uint64_t s_out[kTile];
+    __shared__ uint64_t s_in[kTilePad];
+    __shared__ uint64_t s_out[kTilePad];
+    __shared__ int64_t s_prev_row;
     const int tid = threadIdx.x;
     const uint64_t d064 = (uint64_t)blockIdx.x * kTile;
     const uint32_t d0 = (uint32_t)d064;
@@ -200,27 +223,101 @@ __global__ void __launch_bounds__(kThreads) k_merge_tiles(const uint64_t *__rest
     const uint32_t a0 = split[blockIdx.x], a1 = split[blockIdx.x + 1];
     const uint32_t b0 = d0 - a0, b1 = d1 - a1;
     const uint32_t ca = a1 - a0, cb = b1 - b0, total = ca + cb;   // total == d1 - d0
-    for (uint32_t j = tid; j < total; j += kThreads) s_in[j] = (j < ca) ? a[a0 + j] : b[b0 + (j - ca)];
+    for (uint32_t j = tid; j < total; j += kThreads)
+        s_in[pm_pad(j)] = (j < ca) ? a[a0 + j] : b[b0 + (j - ca)];
+    if (tid == 0) {
+        // row of the last entry of the previous tile (-1 before the first entry)
+        int64_t pr = -1;
+        if (d0 > 0) {
+            const uint64_t la = a0 > 0 ? a[a0 - 1] : 0ull, lb = b0 > 0 ? b[b0 - 1] : 0ull;
+            const uint64_t last = la > lb ? la : lb;
+            pr = pm_rowseg((uint32_t)(last >> 32), ra.xseg, ra.shift, ra.nrows);
+        }
+        s_prev_row = pr;
+    }
     __syncthreads();
-    const uint64_t *sa = s_in, *sb = s_in + ca;
+    auto sa = [&](uint32_t i) { return s_in[pm_pad(i)]; };
+    auto sb = [&](uint32_t i) { return s_in[pm_pad(ca + i)]; };
     const uint32_t ld = min((uint32_t)tid * kRounds, total);
-    uint32_t la = pm_merge_split(sa, ca, sb, cb, ld);
+    uint32_t la;
+    {
+        uint32_t lo = ld > cb ? ld - cb : 0u, hi = ld < ca ? ld : ca;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (sa(mid) < sb(ld - 1 - mid)) lo = mid + 1;
+            else hi = mid;
+        }
+        la = lo;
+    }
     uint32_t lb = ld - la;
 #pragma unroll
     for (int k = 0; k < kRounds; ++k) {
         if (ld + k < total) {
-            const bool take_a = (lb >= cb) || (la < ca && sa[la] < sb[lb]);
-            s_out[ld + k] = take_a ? sa[la] : sb[lb];
+            const bool take_a = (lb >= cb) || (la < ca && sa(la) < sb(lb));
+            s_out[pm_pad(ld + k)] = take_a ? sa(la) : sb(lb);
             la += take_a ? 1u : 0u;
             lb += take_a ? 0u : 1u;
         }
     }
     __syncthreads();
     for (uint32_t j = tid; j < total; j += kThreads) {
-        const uint64_t v = s_out[j];
-        keys_sorted[d0 + j] = (uint32_t)(v >> 32);
+        const uint64_t v = s_out[pm_pad(j)];
+        const uint32_t key = (uint32_t)(v >> 32);
+        keys_sorted[d0 + j] = key;
         order_sorted[d0 + j] = (uint32_t)v;
+        // boundary d0 + j
+        const int64_t prev = (j == 0) ? s_prev_row
+                                      : pm_rowseg((uint32_t)(s_out[pm_pad(j - 1)] >> 32), ra.xseg, ra.shift, ra.nrows);
+        const int64_t cur = pm_rowseg(key, ra.xseg, ra.shift, ra.nrows);
+        for (int64_t r = prev + 1; r <= cur; ++r) ra.row_start[r] = d0 + j;
     }
+    if (d1 == n && tid == 0) {
+        // boundary n: everything after the last entry's row
+        const int64_t prev = total > 0 ? pm_rowseg((uint32_t)(s_out[pm_pad(total - 1)] >> 32), ra.xseg, ra.shift, ra.nrows)
+                                       : s_prev_row;
+        for (int64_t r = prev + 1; r <= ra.nrows; ++r) ra.row_start[r] = n;
+    }
+}
+
+// The same table from an already sorted key array (full-sort path).  One thread per four
+// boundaries j in [0, np].
+__global__ void __launch_bounds__(256) k_row_offsets(const uint32_t *__restrict__ keys_sorted,
+                                                     int64_t np, int xseg, int shift, int64_t nrows,
+                                                     uint32_t *__restrict__ row_start)
+{
+    const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 > np) return;
+    uint32_t k[4];
+    if (j0 + 4 <= np) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(keys_sorted + j0);
+        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) k[t] = (j0 + t < np) ? keys_sorted[j0 + t] : 0u;
+    }
+    int64_t prev = (j0 == 0) ? -1 : pm_rowseg(keys_sorted[j0 - 1], xseg, shift, nrows);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int64_t j = j0 + t;
+        if (j > np) break;
+        const int64_t cur = (j == np) ? nrows : pm_rowseg(k[t], xseg, shift, nrows);
+        for (int64_t r = prev + 1; r <= cur; ++r) row_start[r] = (uint32_t)j;
+        prev = cur;
+    }
+}
+
+RowArgs row_args(pm_plan *p)
+{
+    RowArgs ra;
+    ra.row_start = p->row_start;
+    ra.xseg = p->nc / p->dep_nseg;
+    ra.shift = -1;
+    if ((ra.xseg & (ra.xseg - 1)) == 0) {
+        ra.shift = 0;
+        while ((1 << ra.shift) < ra.xseg) ++ra.shift;
+    }
+    ra.nrows = (int64_t)p->nzl * p->nc * p->dep_nseg;
+    return ra;
 }
 
 int full_sort(pm_plan *p, int64_t n, cudaStream_t st)
@@ -229,6 +326,7 @@ int full_sort(pm_plan *p, int64_t n, cudaStream_t st)
     PM_CUDA(cub::DeviceRadixSort::SortPairs(p->cub_tmp, bytes, (const uint32_t *)p->keys,
                                             p->keys_sorted, (const uint32_t *)p->iota,
                                             p->order_sorted, n, 0, p->key_bits, st));
+    p->rows_valid = false;
     p->sort_last_mode = PM_SORT_FULL;
     p->sort_last_n = n;
     p->sort_last_movers = n;
@@ -260,6 +358,7 @@ size_t pm_sort_temp_bytes(int64_t np, int key_bits)
 // p->keys_sorted[0..n_old) still holds the keys they were sorted by -> incremental path.
 int pm_k_sort(pm_plan *p, int64_t np, int64_t n_old, cudaStream_t st)
 {
+    p->rows_valid = false;
     if (np == 0) return PM_OK;
     if (n_old > np) n_old = np;
     if (p->sort_mode == PM_SORT_FULL || n_old <= 0 || !p->inc_a) return full_sort(p, np, st);
@@ -288,11 +387,25 @@ int pm_k_sort(pm_plan *p, int64_t np, int64_t n_old, cudaStream_t st)
     PM_LAUNCH(k_merge_splits, (nt + 1 + 255) / 256, 256, 0, st, (const uint64_t *)p->inc_a, bs,
               (uint32_t)nb, (uint32_t)np, nt, p->inc_split);
     PM_LAUNCH(k_merge_tiles, nt, kThreads, 0, st, (const uint64_t *)p->inc_a, bs,
-              (const uint32_t *)p->inc_split, (uint32_t)np, p->keys_sorted, p->order_sorted);
+              (const uint32_t *)p->inc_split, (uint32_t)np, p->keys_sorted, p->order_sorted, row_args(p));
     PM_CHECK_LAUNCH();
+    p->rows_valid = true;   // the merge wrote row_start as well
     p->sort_last_mode = PM_SORT_INCREMENTAL;
     p->sort_last_n = np;
     p->sort_last_movers = nb;
+    return PM_OK;
+}
+
+// Row table of the sorted list (no-op when the merge of the incremental sort already wrote it).
+int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st)
+{
+    if (p->rows_valid && np > 0) return PM_OK;
+    const RowArgs ra = row_args(p);
+    const int64_t nthr = np / 4 + 1;
+    PM_LAUNCH(k_row_offsets, (unsigned)((nthr + 255) / 256), 256, 0, st, (const uint32_t *)p->keys_sorted, np,
+              ra.xseg, ra.shift, ra.nrows, p->row_start);
+    PM_CHECK_LAUNCH();
+    p->rows_valid = true;
     return PM_OK;
 }
 

@@ -82,6 +82,10 @@ PM_API int pm_plan_fft_backend(const pm_plan *plan);
  * pm_plan_fft_sync_errors: 1 if a wait inside the fused launch ever gave up (a bug), else 0;
  * synchronises the device. */
 PM_API int pm_plan_set_fft_fuse(pm_plan *plan, int fuse, int lag);
+/* Hand-written FFT, meshes 256..1024: two_stage != 0 (default) uses the register-resident two-stage
+ * transforms (one shared-memory exchange per 1-D transform, pm_fft2.cuh); 0 the three-stage radix-8
+ * kernels (also PM_FFT_V2=0).  Same mathematics, results agree to float32 rounding. */
+PM_API int pm_plan_set_fft_variant(pm_plan *plan, int two_stage);
 PM_API int pm_plan_fft_sync_errors(pm_plan *plan);
 /* How the resident paths (pm_step_resident, pm_slab_deposit) order the particle list by cell key
  * (the order fixes the deposit's summation tree and the locality of deposit and gather; the

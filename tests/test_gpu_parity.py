@@ -284,6 +284,40 @@ def test_fused_plane_fft_equals_separate_passes_bit_for_bit(pm, n):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("n", [256, 512, 1024])
+def test_two_stage_fft_matches_three_stage_and_cufft(pm, n):
+    """pm_fft2.cuh (two in-register DFT stages, natural order) against the radix-8 kernels of
+    pm_fft.cu (digit-reversed order) and cuFFT: three independent implementations of the same solve."""
+    cfg = O.Config(N_CELLS=n)
+    pm.set_config(cfg_ns(cfg))
+    rt = pm._runtime
+    L = rt.lib()
+    g = torch.Generator(device="cuda").manual_seed(11 * n)
+    rho = torch.rand((n, n, n), generator=g, device="cuda") * 4.0
+    rho[n // 2, n - 1, 0] += 700.0
+    rho[0, 0, n - 1] -= 300.0
+    fg = pm.fourier_grid()
+    plan = rt.get_plan(n, 1, 0)
+    out = {}
+    for name, variant, fuse in (("v2_fused", 1, 1), ("v2_split", 1, 0), ("v1", 0, 0)):
+        rt.check(L.pm_plan_set_fft_variant(plan.handle, variant), "variant")
+        rt.check(L.pm_plan_set_fft_fuse(plan.handle, fuse, 0), "fuse")
+        out[name] = pm.potential(rho, fg, 0.5).double()
+    rt.check(L.pm_plan_set_fft_backend(plan.handle, 1), "backend")
+    lib = pm.potential(rho, fg, 0.5).double()
+    rt.check(L.pm_plan_set_fft_backend(plan.handle, 0), "backend")
+    rt.check(L.pm_plan_set_fft_variant(plan.handle, 1), "variant")
+    rt.check(L.pm_plan_set_fft_fuse(plan.handle, 1, 0), "fuse")
+    assert torch.equal(out["v2_fused"], out["v2_split"])
+    for name in ("v2_fused", "v1"):
+        err = float((out[name] - lib).norm() / lib.norm())
+        assert err <= 2e-6, (name, err)
+    assert L.pm_plan_fft_sync_errors(plan.handle) == 0
+    del out, lib, rho
+    pm.release_plans()
+    torch.cuda.empty_cache()
+
+
 def test_single_mode_potential(pm):
     cfg = O.Config(N_CELLS=32)
     pm.set_config(cfg_ns(cfg))
