@@ -538,7 +538,11 @@ def run_ours(args, rank, world, local_rank):
                    "n_parts": n_parts, "n_cells": n_cells,
                    "particles": "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA,
                    "sort": {"mode": sort_mode, "mover_fraction_last_step": sort_movers / max(sort_n, 1)},
-                   "fft": {"fused_plane_passes": os.environ.get("PM_FFT_FUSE", "1") != "0",
+                   "fft": {"fused_plane_passes": os.environ.get("PM_FFT_FUSE", "0") == "1",
+                           "kernels": ("radix-8.8.8" if os.environ.get("PM_FFT_V2", "1") == "0" else
+                                       "two-stage" if os.environ.get("PM_FFT_ZMIX", "1") == "0" else
+                                       "two-stage rows + %s y + radix-8.8.8 fused z" %
+                                       ("two-stage" if os.environ.get("PM_FFT_V3", "2") == "0" else "pipelined two-stage")),
                            "sync_errors": fft_sync_errors},
                    "l2": "inputs larger than L2 (201 MB particles rows, 537 MB meshes vs 126 MB L2)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab path pending)"},

@@ -248,7 +248,14 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         const char *lg = getenv("PM_FFT_LAG");
         const char *v2 = getenv("PM_FFT_V2");     // "0": the three-stage radix-8 kernels
         p->fft_v2 = !(v2 && strcmp(v2, "0") == 0);
-        p->fft_fuse = !(fu && strcmp(fu, "0") == 0);
+        // measured at 512^3 (profiles/r01_notes.md): separate row and y launches 0.46 ms per
+        // direction, the persistent plane launch 0.48 ms -> off unless PM_FFT_FUSE=1
+        p->fft_fuse = (fu && strcmp(fu, "1") == 0);
+        const char *zm = getenv("PM_FFT_ZMIX");   // "0": two-stage kernel for the fused z pass too
+        p->fft_zmix = !(zm && strcmp(zm, "0") == 0);
+        const char *v3 = getenv("PM_FFT_V3");     // ring depth of the pipelined y passes: 0 (off), 2, 3
+        p->fft_v3 = v3 ? atoi(v3) : 2;
+        if (p->fft_v3 != 2 && p->fft_v3 != 3) p->fft_v3 = 0;
         p->fft_lag = lg ? atoi(lg) : 12;
         if (p->fft_lag < 1) p->fft_lag = 1;
         if (p->fft_lag > n_cells) p->fft_lag = n_cells;
@@ -363,6 +370,8 @@ int pm_plan_set_fft_variant(pm_plan *p, int two_stage)
 {
     if (!p) return PM_ERR_INVALID;
     p->fft_v2 = (two_stage != 0);
+    p->fft_zmix = (two_stage == 1 || two_stage >= 3);
+    p->fft_v3 = two_stage == 3 ? 2 : two_stage == 4 ? 3 : 0;
     return PM_OK;
 }
 

@@ -209,8 +209,13 @@ struct NoMid {
 // G(k) of src/fourier_utils.py:15-16 in float32, summed as (s_axis0 + s_axis1) + s_axis2, 0 at DC
 __device__ __forceinline__ float green_f32(float sz, float sy, float sx)
 {
+    // 1/ksq by MUFU.RCP plus one Newton step (<= 1 ulp; the IEEE division sequence costs three
+    // times the instructions and this runs once per spectrum element inside the issue-bound z pass)
     const float ksq = (sz + sy) + sx;
-    return ksq != 0.0f ? 1.0f / ksq : 0.0f;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ksq));
+    r = fmaf(r, fmaf(-ksq, r, 1.0f), r);
+    return ksq != 0.0f ? r : 0.0f;
 }
 
 enum ColMode { COL_FWD = 0, COL_INV = 1, COL_FUSED = 2 };
@@ -219,7 +224,8 @@ struct ColArgs {
     float2 *main;      // [N][N][N/2] spectrum, digit-reversed along transformed axes
     float2 *side;      // [N][N] Nyquist-in-x plane
     const float2 *tw;  // exp(-2 pi i m / N)
-    const float *sin2, *sin2rev;
+    const float *sin2, *sin2rev;   // natural / digit-reversed sin^2(pi i/N)
+    const float *sin2y;            // in the order the y pass left the y axis in (v1: sin2rev, v2: sin2)
     float scale;       // -3*Omega_m/(8a)/N^3
     int axis;          // 1: along y (tiles = z x kx-tile), 0: along z (tiles = y x kx-tile, + side)
     // z pass geometry: the array is [N z][nyl][hw] holding y positions [y0, y0+nyl) -- the whole
@@ -322,7 +328,7 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
             g = a.main + (size_t)yl * a.hw + ktl * kColsCN<N>;
             gs = (size_t)a.nyl * a.hw;
             col0 = (a.kt0 + ktl) * kColsCN<N>;
-            if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2rev + a.y0 + yl);
+            if (MODE == COL_FUSED) sy_fixed = __ldg(a.sin2y + a.y0 + yl);
         } else {
             side_tile = true;
             const int yt = t - a.nyl * TPR;
@@ -432,8 +438,8 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
                     dft<R, -1>(va);
                     dft<R, -1>(vb);
                     const int c = col0 + 2 * cp;
-                    const float sya = side_tile ? __ldg(a.sin2rev + c) : sy_fixed;
-                    const float syb = side_tile ? __ldg(a.sin2rev + c + 1) : sy_fixed;
+                    const float sya = side_tile ? __ldg(a.sin2y + c) : sy_fixed;
+                    const float syb = side_tile ? __ldg(a.sin2y + c + 1) : sy_fixed;
                     const float sxa = side_tile ? __ldg(a.sin2 + H) : __ldg(a.sin2 + c);
                     const float sxb = side_tile ? sxa : __ldg(a.sin2 + c + 1);
 #pragma unroll
@@ -640,6 +646,7 @@ __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__
 }
 
 #include "pm_fft2.cuh"
+#include "pm_fft3.cuh"
 
 template <int N, int MODE>
 __global__ void __launch_bounds__(kThr2, 2) k_fft2_cols(ColArgs a)
@@ -774,6 +781,14 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
         auto cols_fused = k_fft2_cols<N, COL_FUSED>;
         auto plane_fwd = k_fft_plane<N, true, true>;
         auto plane_inv = k_fft_plane<N, false, true>;
+        auto cols_fused_v1 = k_fft_cols<N, COL_FUSED>;
+        auto cols3_fwd2 = k_fft3_cols<N, COL_FWD, 2, kThr2>;
+        auto cols3_inv2 = k_fft3_cols<N, COL_INV, 2, kThr2>;
+        auto cols3_fwd3 = k_fft3_cols<N, COL_FWD, 3, kThr2>;
+        auto cols3_inv3 = k_fft3_cols<N, COL_INV, 3, kThr2>;
+        constexpr size_t smem3_2 = kSmem3<N, 2>, smem3_3 = kSmem3<N, 3>;
+        constexpr bool ring3_fits = smem3_3 <= 227 * 1024;
+        const size_t smem_cols_v1 = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
         static bool attr_set = false;
         static int plane_per_sm = 1;
         if (!attr_set) {
@@ -787,6 +802,14 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
             PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             PM_CUDA(cudaFuncSetAttribute(cols_inv, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             PM_CUDA(cudaFuncSetAttribute(cols_fused, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PM_CUDA(cudaFuncSetAttribute(cols3_fwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3_2));
+            PM_CUDA(cudaFuncSetAttribute(cols3_inv2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3_2));
+            if (ring3_fits) {
+                PM_CUDA(cudaFuncSetAttribute(cols3_fwd3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3_3));
+                PM_CUDA(cudaFuncSetAttribute(cols3_inv3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3_3));
+            }
+            PM_CUDA(cudaFuncSetAttribute(cols_fused_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols_v1));
+            PM_CUDA(cudaFuncSetAttribute(cols_fused_v1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             PM_CUDA(cudaFuncSetAttribute(plane_fwd, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             PM_CUDA(cudaFuncSetAttribute(plane_inv, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             PM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plane_per_sm, plane_fwd, kThr2, smem_cols));
@@ -799,6 +822,7 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
         ca.tw = p->tw;
         ca.sin2 = p->sin2;
         ca.sin2rev = p->sin2;   // natural order everywhere on this path
+        ca.sin2y = p->sin2;
         const double m = (double)N * N * N;
         ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
         ca.nyl = N;
@@ -809,6 +833,7 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
         ca.side_tiles = 1;
         const int row_ctas = N * N / RT;
         const int tiles = N * (H / C);
+        const int grid3 = tiles < p->sm_count ? tiles : p->sm_count;   // one persistent CTA per SM
         const bool fused = p->fft_fuse && p->fft_sync;
         PlaneArgs pa;
         if (fused) {
@@ -826,11 +851,22 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
             PM_LAUNCH(rows_fwd, row_ctas, kThr2, smem_rows, st, reinterpret_cast<const float2 *>(rho), ca.main,
                       (const float2 *)p->tw);
             ca.axis = 1;
-            PM_LAUNCH(cols_fwd, tiles, kThr2, smem_cols, st, ca);
+            if (p->fft_v3 == 3 && ring3_fits) PM_LAUNCH(cols3_fwd3, grid3, kThr2, smem3_3, st, ca, tiles);
+            else if (p->fft_v3) PM_LAUNCH(cols3_fwd2, grid3, kThr2, smem3_2, st, ca, tiles);
+            else PM_LAUNCH(cols_fwd, tiles, kThr2, smem_cols, st, ca);
         }
         pm_prof_mark(p, PM_STAGE_R2C + 1, st);
         ca.axis = 0;
-        PM_LAUNCH(cols_fused, tiles + N / C, kThr2, smem_cols, st, ca);
+        if (p->fft_zmix) {
+            // z pass + Green + inverse z pass by the radix-8.8.8 kernel: 80 registers and three
+            // CTAs per SM beat the two-stage version's 128 registers here (measured 0.35 vs 0.48 ms
+            // at 512^3).  Its z order is internal to the pass; y stays natural (sin2y).
+            ColArgs cz = ca;
+            cz.sin2rev = p->sin2rev;
+            PM_LAUNCH(cols_fused_v1, tiles + N / C, kThrC<N>, smem_cols_v1, st, cz);
+        } else {
+            PM_LAUNCH(cols_fused, tiles + N / C, kThr2, smem_cols, st, ca);
+        }
         pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
         if (fused) {
             pa.rows_in = ca.main;
@@ -839,7 +875,9 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
             PM_LAUNCH(plane_inv, plane_per_sm * p->sm_count, kThr2, smem_cols, st, pa);
         } else {
             ca.axis = 1;
-            PM_LAUNCH(cols_inv, tiles, kThr2, smem_cols, st, ca);
+            if (p->fft_v3 == 3 && ring3_fits) PM_LAUNCH(cols3_inv3, grid3, kThr2, smem3_3, st, ca, tiles);
+            else if (p->fft_v3) PM_LAUNCH(cols3_inv2, grid3, kThr2, smem3_2, st, ca, tiles);
+            else PM_LAUNCH(cols_inv, tiles, kThr2, smem_cols, st, ca);
             PM_LAUNCH(rows_inv, row_ctas, kThr2, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
                       reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
         }
@@ -879,6 +917,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     ca.tw = p->tw;
     ca.sin2 = p->sin2;
     ca.sin2rev = p->sin2rev;
+    ca.sin2y = p->sin2rev;
     const double m = (double)N * N * N;
     ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
     ca.nyl = N;
@@ -990,7 +1029,7 @@ ColArgs slab_args(pm_plan *p)
     ColArgs ca;
     ca.main = p->spec;
     ca.side = p->spec + (size_t)p->nzl * N * (N / 2);
-    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
+    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev; ca.sin2y = p->sin2rev;
     ca.scale = 0.f; ca.axis = 1;
     ca.nyl = N / p->nranks; ca.y0 = p->rank * ca.nyl;
     ca.tpr = (N / 2) / kColsCN<N>; ca.kt0 = 0; ca.hw = N / 2; ca.side_tiles = 1;
@@ -1143,7 +1182,7 @@ int pk_launch(pm_plan *p, const float *rho, int nbins, double *psum, double *pcn
     ColArgs ca;
     ca.main = p->spec;
     ca.side = p->spec + (size_t)N * N * H;
-    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev;
+    ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev; ca.sin2y = p->sin2rev;
     ca.scale = 0.f; ca.nyl = N; ca.y0 = 0;
     ca.tpr = H / kColsCN<N>; ca.kt0 = 0; ca.hw = H; ca.side_tiles = 1;
     PM_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * nbins, st));

@@ -67,6 +67,7 @@ struct pm_plan {
     int sort_mode;          // PM_SORT_AUTO / PM_SORT_FULL
     int64_t rsorted_n;      // the first rsorted_n entries of set rcur are stored in the order of
                             // the previous sort and keys_sorted[] still holds the keys they had
+    bool inc_counted;       // inc_tile already holds this step's movers per tile (counted by the resident gather)
     bool rows_valid;        // row_start matches keys_sorted (set by the sort's merge or pm_k_row_offsets)
     int sort_last_mode;     // what the last pm_k_sort did (pm_plan_sort_stats)
     int64_t sort_last_n, sort_last_movers;
@@ -83,6 +84,8 @@ struct pm_plan {
     float2 *tw;           // exp(-2 pi i m / nc)
     bool own_fft;         // power-of-two mesh: pm_fft.cu path; otherwise cuFFT
     bool fft_v2;          // two-stage register-resident transforms (pm_fft2.cuh), meshes 256..1024
+    bool fft_zmix;        // with fft_v2: the fused z pass still runs the radix-8.8.8 kernel (faster at 80 registers)
+    int fft_v3;           // with fft_v2: y passes by the cp.async-pipelined persistent kernel (pm_fft3.cuh); value = ring depth (0 off, 2, 3)
     bool fft_fuse;        // x and y passes of a direction in one persistent launch (k_fft_plane)
     int fft_lag;          // planes between the producer and the consumer pass of that launch
     unsigned *fft_sync;   // [0] error flag, then per direction: ticket + per-plane counters

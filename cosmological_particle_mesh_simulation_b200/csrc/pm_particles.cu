@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
     float *pos_out, float *vel_out, uint32_t *__restrict__ id_out,
     uint32_t *__restrict__ keys_out, int64_t np, int64_t sin, int64_t sout,
     const float *__restrict__ phi, int nc, double k_kick, double da, double aa, double f_a1,
-    float *__restrict__ acc, SlabArgs sl)
+    float *__restrict__ acc, SlabArgs sl, uint32_t *__restrict__ mover_cnt)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
     float vx = vel_in[j], vy = vel_in[sin + j], vz = vel_in[2 * sin + j];
 
     const int xc = pm_cell(x, nc), yc = pm_cell(y, nc), zc = pm_cell(z, nc);
+    const uint32_t kold = ((uint32_t)zc * nc + yc) * nc + xc;   // the key slot i was filed under (!SLAB)
     // weights (integrate.py:36-51): float64 products left to right, stored float32
     const double d_x = (double)x - (double)xc, d_y = (double)y - (double)yc,
                  d_z = (double)z - (double)zc;
@@ -423,7 +424,16 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
             }
             keys_out[i] = key;
         } else {
-            keys_out[i] = pm_key(x, y, z, nc, 0, nc);
+            const uint32_t knew = pm_key(x, y, z, nc, 0, nc);
+            keys_out[i] = knew;
+            if (mover_cnt) {
+                // The incremental sort's first pass, for free: slot i was filed under the key of the
+                // pre-step position, so it is a "mover" iff the key changed.  A warp's 32 slots lie
+                // in one sort tile; integer atomics keep the counts exact in any order.
+                const unsigned act = __activemask();
+                const unsigned mv = __ballot_sync(act, knew != kold);
+                if (mv && (threadIdx.x & 31) == __ffs(act) - 1) atomicAdd(mover_cnt + i / PM_SORT_TILE, __popc(mv));
+            }
         }
     }
 }
@@ -438,7 +448,7 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
     auto kern = k_gather_kick_drift<false, false>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, pos, vel,
               (const uint32_t *)nullptr, (const uint32_t *)nullptr, pos, vel, (uint32_t *)nullptr,
-              (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, f_a1, acc, SlabArgs());
+              (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, f_a1, acc, SlabArgs(), (uint32_t *)nullptr);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -453,11 +463,16 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
     const double k_kick = da * f_a1;
     const double aa = (a_val + da) * (a_val + da);
     const int c = p->rcur, o = c ^ 1;
+    // movers per sort tile, counted on the way (pm_sort.cu then skips its counting pass)
+    static const bool count_here = !(getenv("PM_GATHER_COUNT") && strcmp(getenv("PM_GATHER_COUNT"), "0") == 0);
+    uint32_t *cnt = (count_here && p->inc_a && p->sort_mode != PM_SORT_FULL) ? p->inc_tile : nullptr;
+    if (cnt) PM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (pm_sort_tiles(np) + 1), st));
     auto kern = k_gather_kick_drift<true, false>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c],
               p->rvel[c], p->rid[c], p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np,
-              p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, SlabArgs());
+              p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, SlabArgs(), cnt);
     PM_CHECK_LAUNCH();
+    p->inc_counted = (cnt != nullptr);
     return PM_OK;
 }
 
@@ -479,7 +494,7 @@ int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, doub
     auto kern = k_gather_kick_drift<true, true>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c], p->rvel[c], p->rid[c],
               p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np, p->rstride, p->rstride,
-              phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, sl);
+              phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, sl, (uint32_t *)nullptr);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }

@@ -361,11 +361,17 @@ int pm_k_sort(pm_plan *p, int64_t np, int64_t n_old, cudaStream_t st)
     p->rows_valid = false;
     if (np == 0) return PM_OK;
     if (n_old > np) n_old = np;
-    if (p->sort_mode == PM_SORT_FULL || n_old <= 0 || !p->inc_a) return full_sort(p, np, st);
+    if (p->sort_mode == PM_SORT_FULL || n_old <= 0 || !p->inc_a) {
+        p->inc_counted = false;
+        return full_sort(p, np, st);
+    }
 
     const int nt = (int)pm_sort_tiles(np);
-    PM_LAUNCH(k_mover_count, nt, kThreads, 0, st, (const uint32_t *)p->keys,
-              (const uint32_t *)p->keys_sorted, np, n_old, p->inc_tile);
+    // the resident gather counts the movers of each tile while it writes the keys (inc_counted)
+    if (!(p->inc_counted && n_old == np))
+        PM_LAUNCH(k_mover_count, nt, kThreads, 0, st, (const uint32_t *)p->keys,
+                  (const uint32_t *)p->keys_sorted, np, n_old, p->inc_tile);
+    p->inc_counted = false;
     PM_LAUNCH(k_mover_scan, 1, 1024, 0, st, p->inc_tile, nt);
     PM_CHECK_LAUNCH();
     PM_CUDA(cudaMemcpyAsync(p->h_word, p->inc_tile + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));

@@ -75,16 +75,23 @@ PM_API int pm_plan_n_cells(const pm_plan *plan);
  * (any mesh size; also selectable with the environment variable PM_FFT_BACKEND=cufft). */
 PM_API int pm_plan_set_fft_backend(pm_plan *plan, int backend);
 PM_API int pm_plan_fft_backend(const pm_plan *plan);
-/* Hand-written FFT, meshes 256..1024: fuse != 0 (default) runs the row pass and the y pass of each
+/* Hand-written FFT, meshes 256..1024: fuse != 0 runs the row pass and the y pass of each
  * direction in one persistent launch that keeps the intermediate plane in L2 (pm_fft.cu,
- * k_fft_plane); 0 runs them as two launches (also PM_FFT_FUSE=0).  lag > 0 sets the distance in
+ * k_fft_plane; also PM_FFT_FUSE=1); 0 (default: measured 4 % faster at 512^3, the passes are
+ * bound on the SM side, not by HBM) runs them as two launches.  lag > 0 sets the distance in
  * planes between the two passes (default 12, PM_FFT_LAG).  Results are identical either way.
  * pm_plan_fft_sync_errors: 1 if a wait inside the fused launch ever gave up (a bug), else 0;
  * synchronises the device. */
 PM_API int pm_plan_set_fft_fuse(pm_plan *plan, int fuse, int lag);
-/* Hand-written FFT, meshes 256..1024: two_stage != 0 (default) uses the register-resident two-stage
- * transforms (one shared-memory exchange per 1-D transform, pm_fft2.cuh); 0 the three-stage radix-8
- * kernels (also PM_FFT_V2=0).  Same mathematics, results agree to float32 rounding. */
+/* Hand-written FFT, meshes 256..1024, kernel selection (same mathematics, results agree to float32
+ * rounding; 1, 3 and 4 are bit-identical to each other):
+ *   0  three-stage radix-8 kernels for every pass (also PM_FFT_V2=0)
+ *   1  register-resident two-stage transforms (one shared-memory exchange per 1-D transform,
+ *      pm_fft2.cuh) for the row and y passes, radix-8 kernel for the fused z + Green + z^-1 pass
+ *   2  two-stage kernels for every pass (also PM_FFT_ZMIX=0)
+ *   3  (default) as 1, with the y passes run by the persistent cp.async-pipelined kernel of
+ *      pm_fft3.cuh, ring of 2 tiles per SM (PM_FFT_V3=2; PM_FFT_V3=0 gives 1)
+ *   4  as 3 with a ring of 3 tiles (PM_FFT_V3=3) */
 PM_API int pm_plan_set_fft_variant(pm_plan *plan, int two_stage);
 PM_API int pm_plan_fft_sync_errors(pm_plan *plan);
 /* How the resident paths (pm_step_resident, pm_slab_deposit) order the particle list by cell key

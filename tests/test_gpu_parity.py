@@ -278,7 +278,7 @@ def test_fused_plane_fft_equals_separate_passes_bit_for_bit(pm, n):
             phi = pm.potential(rho, fg, 0.5)
             assert torch.equal(phi, ref), (n, lag)
     assert L.pm_plan_fft_sync_errors(plan.handle) == 0
-    rt.check(L.pm_plan_set_fft_fuse(plan.handle, 1, 12), "fuse default")
+    rt.check(L.pm_plan_set_fft_fuse(plan.handle, 0, 12), "fuse default (off)")
     del phi, ref, rho
     pm.release_plans()
     torch.cuda.empty_cache()
@@ -299,17 +299,22 @@ def test_two_stage_fft_matches_three_stage_and_cufft(pm, n):
     fg = pm.fourier_grid()
     plan = rt.get_plan(n, 1, 0)
     out = {}
-    for name, variant, fuse in (("v2_fused", 1, 1), ("v2_split", 1, 0), ("v1", 0, 0)):
+    for name, variant, fuse in (("v2_fused", 2, 1), ("v2_split", 2, 0), ("mix_fused", 1, 1),
+                                ("mix_split", 1, 0), ("pipe2", 3, 0), ("pipe3", 4, 0), ("v1", 0, 0)):
         rt.check(L.pm_plan_set_fft_variant(plan.handle, variant), "variant")
         rt.check(L.pm_plan_set_fft_fuse(plan.handle, fuse, 0), "fuse")
         out[name] = pm.potential(rho, fg, 0.5).double()
     rt.check(L.pm_plan_set_fft_backend(plan.handle, 1), "backend")
     lib = pm.potential(rho, fg, 0.5).double()
     rt.check(L.pm_plan_set_fft_backend(plan.handle, 0), "backend")
-    rt.check(L.pm_plan_set_fft_variant(plan.handle, 1), "variant")
-    rt.check(L.pm_plan_set_fft_fuse(plan.handle, 1, 0), "fuse")
+    rt.check(L.pm_plan_set_fft_variant(plan.handle, 3), "variant (default)")
+    rt.check(L.pm_plan_set_fft_fuse(plan.handle, 0, 0), "fuse")
     assert torch.equal(out["v2_fused"], out["v2_split"])
-    for name in ("v2_fused", "v1"):
+    assert torch.equal(out["mix_fused"], out["mix_split"])
+    # the cp.async-pipelined y passes (pm_fft3.cuh) do the arithmetic of the two-stage kernels
+    assert torch.equal(out["pipe2"], out["mix_split"])
+    assert torch.equal(out["pipe3"], out["mix_split"])
+    for name in ("v2_fused", "mix_split", "v1"):
         err = float((out[name] - lib).norm() / lib.norm())
         assert err <= 2e-6, (name, err)
     assert L.pm_plan_fft_sync_errors(plan.handle) == 0
