@@ -212,10 +212,14 @@ __device__ __forceinline__ float green_f32(float sz, float sy, float sx)
     // 1/ksq by MUFU.RCP plus one Newton step (<= 1 ulp; the IEEE division sequence costs three
     // times the instructions and this runs once per spectrum element inside the issue-bound z pass)
     const float ksq = (sz + sy) + sx;
+#ifdef PM_GREEN_IEEE_DIV
+    return ksq != 0.0f ? 1.0f / ksq : 0.0f;
+#else
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ksq));
     r = fmaf(r, fmaf(-ksq, r, 1.0f), r);
     return ksq != 0.0f ? r : 0.0f;
+#endif
 }
 
 enum ColMode { COL_FWD = 0, COL_INV = 1, COL_FUSED = 2 };

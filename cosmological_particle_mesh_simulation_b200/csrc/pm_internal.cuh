@@ -127,7 +127,9 @@ static inline void pm_prof_mark(pm_plan *p, int k, cudaStream_t st)
 static inline cudaStream_t pm_cu(pm_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // pm_sort.cu
+#ifndef PM_SORT_TILE
 #define PM_SORT_TILE 2048
+#endif
 size_t pm_sort_temp_bytes(int64_t np, int key_bits);
 int64_t pm_sort_tiles(int64_t np);
 int64_t pm_sort_mover_capacity(int64_t np);

@@ -117,6 +117,11 @@ int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uin
 #define PM_DEPOSIT_ACC float
 #endif
 typedef PM_DEPOSIT_ACC pm_acc_t;
+// 16-byte zero-fill and write-out of the shared-memory rows (float accumulators only)
+#ifndef PM_DEPOSIT_VEC4
+#define PM_DEPOSIT_VEC4 (sizeof(pm_acc_t) == 4)
+#endif
+__host__ __device__ __forceinline__ int pm_deposit_pitch(int xseg) { return (xseg + 1 + 3) & ~3; }
 
 template <int RY>
 __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restrict__ px,
@@ -147,8 +152,15 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
     const int Z = blockIdx.y;
     const int y = blockIdx.x * (RY / nseg) + rslot;
     const bool active = y < nc;  // warp-uniform
-    pm_acc_t *row = s_rows + (size_t)warp * (xseg + 1);
-    for (int x = lane; x <= xseg; x += 32) row[x] = 0;
+    // row pitch: xseg bins + the spill bin, padded so every row starts on a 16-byte boundary
+    const int pitch = pm_deposit_pitch(xseg);
+    pm_acc_t *row = s_rows + (size_t)warp * pitch;
+    if (PM_DEPOSIT_VEC4 && (xseg & 3) == 0) {
+        float4 *row4 = reinterpret_cast<float4 *>(row);
+        for (int x = lane; x < pitch / 4; x += 32) row4[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        for (int x = lane; x <= xseg; x += 32) row[x] = 0;
+    }
     __syncwarp();
 
     const int Zm = slab ? Z - 1 : ((Z == 0) ? nc - 1 : Z - 1);
@@ -208,12 +220,27 @@ __global__ void __launch_bounds__(RY * 32) k_deposit_rows(const float *__restric
     __syncthreads();
     if (!active) return;
     const int pseg = (seg == 0) ? nseg - 1 : seg - 1;
-    const pm_acc_t spill = s_rows[(size_t)(rslot * nseg + pseg) * (xseg + 1) + xseg];
+    const pm_acc_t spill = s_rows[(size_t)(rslot * nseg + pseg) * pitch + xseg];
     float *out = rho + ((size_t)Z * nc + y) * nc + xs;
-    for (int x = lane; x < xseg; x += 32) out[x] = (float)(x == 0 ? row[0] + spill : row[x]);
+    if (PM_DEPOSIT_VEC4 && (xseg & 3) == 0 && (nc & 3) == 0) {
+        // 16-byte row reads and mesh stores: a quarter of the instructions of the scalar loop
+        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+        float4 *out4 = reinterpret_cast<float4 *>(out);
+        for (int x = lane; x < xseg / 4; x += 32) {
+            float4 v = row4[x];
+            if (x == 0) v.x += spill;
+            out4[x] = v;
+        }
+    } else {
+        for (int x = lane; x < xseg; x += 32) out[x] = (float)(x == 0 ? row[0] + spill : row[x]);
+    }
 }
 
-static const int PM_DEPOSIT_RY = 8;
+// warps (output row segments) per CTA: 4 measured best at 512^3 (0.406 ms; 8: 0.429, 16: 0.460);
+// a CTA must hold all segments of a row, so meshes cut into more than 4 segments use 8
+#ifndef PM_DEPOSIT_RY
+#define PM_DEPOSIT_RY 4
+#endif
 
 int pm_deposit_segments(int nc)
 {
@@ -234,23 +261,31 @@ int pm_deposit_segments(int nc)
     return 1;
 }
 
-static int pm_launch_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
-                             int nz_out, int slab, cudaStream_t st)
+template <int RY>
+static int pm_launch_deposit_ry(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
+                                int nz_out, int slab, cudaStream_t st)
 {
     const int nc = p->nc, nseg = p->dep_nseg;
-    const int rows_per_cta = PM_DEPOSIT_RY / nseg;
-    const size_t smem = (size_t)PM_DEPOSIT_RY * (nc / nseg + 1) * sizeof(pm_acc_t);
+    const int rows_per_cta = RY / nseg;
+    const size_t smem = (size_t)RY * pm_deposit_pitch(nc / nseg) * sizeof(pm_acc_t);
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        PM_CUDA(cudaFuncSetAttribute(k_deposit_rows<PM_DEPOSIT_RY>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PM_CUDA(cudaFuncSetAttribute(k_deposit_rows<RY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     dim3 grid((nc + rows_per_cta - 1) / rows_per_cta, nz_out);
-    PM_LAUNCH(k_deposit_rows<PM_DEPOSIT_RY>, grid, PM_DEPOSIT_RY * 32, smem, st, pos, pos + stride,
-              pos + 2 * stride, p->order_sorted, p->row_start, nc, nseg, mass, rho, p->z0, p->nzl, slab);
+    PM_LAUNCH(k_deposit_rows<RY>, grid, RY * 32, smem, st, pos, pos + stride, pos + 2 * stride,
+              p->order_sorted, p->row_start, nc, nseg, mass, rho, p->z0, p->nzl, slab);
     PM_CHECK_LAUNCH();
     return PM_OK;
+}
+
+static int pm_launch_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
+                             int nz_out, int slab, cudaStream_t st)
+{
+    if (p->dep_nseg <= PM_DEPOSIT_RY && PM_DEPOSIT_RY % p->dep_nseg == 0)
+        return pm_launch_deposit_ry<PM_DEPOSIT_RY>(p, pos, stride, mass, rho, nz_out, slab, st);
+    return pm_launch_deposit_ry<8>(p, pos, stride, mass, rho, nz_out, slab, st);
 }
 
 int pm_k_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
@@ -308,13 +343,34 @@ __device__ __forceinline__ float pm_gp(const float (&v)[4][4][4], const float (&
     return s;
 }
 
+// x / b for a divisor that is the same for every particle of a launch: with r = RN(1/b) formed on
+// the host, q = RN(x*r) is within an ulp of the quotient, e = x - b*q is exact in one FMA, and
+// RN(q + e*r) is the correctly rounded x/b (Markstein's final division step) -- three FP64
+// instructions instead of the ~35 of the IEEE division sequence, same bits.  Valid away from
+// overflow/underflow (pm_div_rcp checks the ranges on the host and returns 0 to ask for __ddiv_rn);
+// oracle/check_const_div.py replays the sequence in exact rational arithmetic.
+__device__ __forceinline__ double pm_div_const(double x, double b, double r)
+{
+    if (r == 0.0) return __ddiv_rn(x, b);   // launch-uniform
+    const double q = __dmul_rn(x, r);
+    const double e = __fma_rn(-b, q, x);
+    return __fma_rn(e, r, q);
+}
+
+static double pm_div_rcp(double b, double da)
+{
+    const double ab = fabs(b), ad = fabs(da);
+    if (!(ab > 1e-60 && ab < 1e60) || !(ad < 1e60) || (ad != 0.0 && ad < 1e-60)) return 0.0;
+    return 1.0 / b;
+}
+
 __device__ __forceinline__ void pm_push(float &x, float &vel, float s, double k_kick, double da,
-                                        double aa, double f_a1, int nc, float *acc_out)
+                                        double aa, double raa, double f_a1, int nc, float *acc_out)
 {
     const double g_p = (double)s / 2.0;
     if (acc_out) *acc_out = (float)g_p;
     vel = (float)__dadd_rn((double)vel, __dmul_rn(k_kick, g_p));
-    const double step = __dmul_rn(__ddiv_rn(__dmul_rn(da, (double)vel), aa), f_a1);
+    const double step = __dmul_rn(pm_div_const(__dmul_rn(da, (double)vel), aa, raa), f_a1);
     x = (float)pm_pymod(__dadd_rn((double)x, step), (double)nc);
 }
 
@@ -336,6 +392,12 @@ struct SlabArgs {
 #ifndef PM_GATHER_THREADS
 #define PM_GATHER_THREADS 256
 #endif
+// how the resident gather learns the key a slot was filed under when it counts the movers:
+// 0 = keep it in a register from the cell computation (measured 0.584 ms), 1 = reload
+// keys_sorted[i] at the end (0.606 ms: a dependent load at the end of every warp's life)
+#ifndef PM_GATHER_KOLD_LOAD
+#define PM_GATHER_KOLD_LOAD 0
+#endif
 #ifndef PM_GATHER_MINB
 #define PM_GATHER_MINB 4
 #endif
@@ -345,8 +407,9 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
     const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ perm,
     float *pos_out, float *vel_out, uint32_t *__restrict__ id_out,
     uint32_t *__restrict__ keys_out, int64_t np, int64_t sin, int64_t sout,
-    const float *__restrict__ phi, int nc, double k_kick, double da, double aa, double f_a1,
-    float *__restrict__ acc, SlabArgs sl, uint32_t *__restrict__ mover_cnt)
+    const float *__restrict__ phi, int nc, double k_kick, double da, double aa, double raa,
+    double f_a1, float *__restrict__ acc, SlabArgs sl, uint32_t *__restrict__ mover_cnt,
+    const uint32_t *__restrict__ keys_old)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
@@ -356,7 +419,9 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
     float vx = vel_in[j], vy = vel_in[sin + j], vz = vel_in[2 * sin + j];
 
     const int xc = pm_cell(x, nc), yc = pm_cell(y, nc), zc = pm_cell(z, nc);
+#if !PM_GATHER_KOLD_LOAD
     const uint32_t kold = ((uint32_t)zc * nc + yc) * nc + xc;   // the key slot i was filed under (!SLAB)
+#endif
     // weights (integrate.py:36-51): float64 products left to right, stored float32
     const double d_x = (double)x - (double)xc, d_y = (double)y - (double)yc,
                  d_z = (double)z - (double)zc;
@@ -405,9 +470,9 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
             }
 
     const float sx = pm_gp<0>(v, t), sy = pm_gp<1>(v, t), sz = pm_gp<2>(v, t);
-    pm_push(x, vx, sx, k_kick, da, aa, f_a1, nc, acc ? acc + i : nullptr);
-    pm_push(y, vy, sy, k_kick, da, aa, f_a1, nc, acc ? acc + np + i : nullptr);
-    pm_push(z, vz, sz, k_kick, da, aa, f_a1, nc, acc ? acc + 2 * np + i : nullptr);
+    pm_push(x, vx, sx, k_kick, da, aa, raa, f_a1, nc, acc ? acc + i : nullptr);
+    pm_push(y, vy, sy, k_kick, da, aa, raa, f_a1, nc, acc ? acc + np + i : nullptr);
+    pm_push(z, vz, sz, k_kick, da, aa, raa, f_a1, nc, acc ? acc + 2 * np + i : nullptr);
 
     pos_out[i] = x; pos_out[sout + i] = y; pos_out[2 * sout + i] = z;
     vel_out[i] = vx; vel_out[sout + i] = vy; vel_out[2 * sout + i] = vz;
@@ -430,6 +495,9 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
                 // The incremental sort's first pass, for free: slot i was filed under the key of the
                 // pre-step position, so it is a "mover" iff the key changed.  A warp's 32 slots lie
                 // in one sort tile; integer atomics keep the counts exact in any order.
+#if PM_GATHER_KOLD_LOAD
+                const uint32_t kold = keys_old[i];   // the key slot i was filed under
+#endif
                 const unsigned act = __activemask();
                 const unsigned mv = __ballot_sync(act, knew != kold);
                 if (mv && (threadIdx.x & 31) == __ffs(act) - 1) atomicAdd(mover_cnt + i / PM_SORT_TILE, __popc(mv));
@@ -448,7 +516,7 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
     auto kern = k_gather_kick_drift<false, false>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, pos, vel,
               (const uint32_t *)nullptr, (const uint32_t *)nullptr, pos, vel, (uint32_t *)nullptr,
-              (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, f_a1, acc, SlabArgs(), (uint32_t *)nullptr);
+              (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, acc, SlabArgs(), (uint32_t *)nullptr, (const uint32_t *)nullptr);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -470,7 +538,7 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
     auto kern = k_gather_kick_drift<true, false>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c],
               p->rvel[c], p->rid[c], p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np,
-              p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, SlabArgs(), cnt);
+              p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, (float *)nullptr, SlabArgs(), cnt, (const uint32_t *)p->keys_sorted);
     PM_CHECK_LAUNCH();
     p->inc_counted = (cnt != nullptr);
     return PM_OK;
@@ -494,7 +562,7 @@ int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, doub
     auto kern = k_gather_kick_drift<true, true>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c], p->rvel[c], p->rid[c],
               p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np, p->rstride, p->rstride,
-              phi, p->nc, k_kick, da, aa, f_a1, (float *)nullptr, sl, (uint32_t *)nullptr);
+              phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, (float *)nullptr, sl, (uint32_t *)nullptr, (const uint32_t *)nullptr);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }

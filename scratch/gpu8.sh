@@ -1,0 +1,26 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== default lib" > gpurun_out/h_diag.log
+timeout 300 python scratch/diag_seg.py >> gpurun_out/h_diag.log 2>&1
+echo "== IEEE division in Green" >> gpurun_out/h_diag.log
+PM_LIB=$PWD/scratch/variants/libpmstep_ieee.so timeout 300 python scratch/diag_seg.py >> gpurun_out/h_diag.log 2>&1
+echo "== scalar deposit zero/writeout" >> gpurun_out/h_diag.log
+PM_LIB=$PWD/scratch/variants/libpmstep_k.so timeout 300 python scratch/diag_seg.py >> gpurun_out/h_diag.log 2>&1
+cat gpurun_out/h_diag.log
+timeout 900 python -m pytest tests -m gpu -q --maxfail=10 > gpurun_out/h_pytest.log 2>&1
+echo "rc=$?" >> gpurun_out/h_pytest.log
+tail -4 gpurun_out/h_pytest.log
+B="python bench.py --steps 20 --warmup 3 --no-cpu-baseline"
+timeout 300 $B > gpurun_out/h_bench_a.json 2> gpurun_out/h_bench_a.err
+for v in i j; do
+PM_LIB=$PWD/scratch/variants/libpmstep_$v.so timeout 300 $B > gpurun_out/h_bench_$v.json 2> gpurun_out/h_bench_$v.err
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/h_bench_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['stages_ms'].items()})
+    except Exception as e:
+        print(f, 'ERR', e, open(f.replace('.json','.err')).read()[-600:])
+PY

@@ -162,7 +162,10 @@ def test_density_with_segmented_rows(pm, golden_dir, xseg, monkeypatch):
         monkeypatch.delenv("PM_DEPOSIT_XSEG")
         p2, v2 = dev(g["pos0"]), dev(g["vel0"])
         pm.step(p2, v2, float(g["a_list"][0]), float(g["da"]), mass=float(g["mass"]))
-        assert rel_l2_periodic(p1.cpu().numpy(), p2.cpu().numpy(), cfg.N_CELLS) <= 1e-6
+        # the segment boundaries change the float32 summation order of the deposit (a few cells differ in
+        # the last bit); on the spike fixtures one ulp of the 8192-32768-high cells is amplified to the
+        # float32 floor documented at SPIKE_CASES (scratch/diag_seg.py prints the per-fixture numbers)
+        assert rel_l2_periodic(p1.cpu().numpy(), p2.cpu().numpy(), cfg.N_CELLS) <= SPIKE_CASES.get(name, 1e-6)
     monkeypatch.delenv("PM_DEPOSIT_XSEG", raising=False)
     pm.release_plans()
 

@@ -111,3 +111,10 @@ def test_threaded_oracle_matches_serial_to_rounding():
     O.advance_time(r1, p1, v1, fg, 0.3, 0.001, cfg1)
     O.advance_time(r1, p4, v4, fg, 0.3, 0.001, cfg4)
     assert np.array_equal(p1, p4) and np.array_equal(v1, v4)
+
+
+def test_constant_divisor_division_is_correctly_rounded():
+    """The gather kernel divides by (a+da)^2 with a host reciprocal and two FMAs (pm_div_const); the
+    replay in exact arithmetic must give the IEEE quotient every time."""
+    from oracle.check_const_div import mismatches
+    assert mismatches(60, 300) == 0
