@@ -63,6 +63,7 @@ def lib():
             "pm_plan_set_fft_fuse": (i32, [vp, i32, i32]),
             "pm_plan_fft_sync_errors": (i32, [vp]),
             "pm_plan_set_fft_variant": (i32, [vp, i32]),
+            "pm_plan_set_gather_tiled": (i32, [vp, i32]),
             "pm_plan_set_sort_mode": (i32, [vp, i32]),
             "pm_plan_sort_stats": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32)]),
             "pm_fourier_grid": (i32, [vp, vp, vp]),
@@ -117,7 +118,7 @@ EXPORTED_SYMBOLS = (
     "pm_slab_fft_z", "pm_slab_fft_y_inverse", "pm_slab_fft_rows_inverse", "pm_slab_gather",
     "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export", "pm_power_spectrum",
     "pm_plan_set_sort_mode", "pm_plan_sort_stats", "pm_plan_set_fft_fuse", "pm_plan_fft_sync_errors",
-    "pm_plan_set_fft_variant",
+    "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

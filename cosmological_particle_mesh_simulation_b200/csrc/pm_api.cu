@@ -261,6 +261,10 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         if (p->fft_lag > n_cells) p->fft_lag = n_cells;
     }
     {
+        const char *gt = getenv("PM_GATHER_TILED");   // "1": shared-memory phi slabs in the resident gather
+        p->gather_tiled = (gt && strcmp(gt, "1") == 0);
+    }
+    {
         const char *sm = getenv("PM_SORT");   // "full" forces the radix sort of every entry (A/B checks)
         p->sort_mode = (sm && strcmp(sm, "full") == 0) ? PM_SORT_FULL : PM_SORT_AUTO;
     }
@@ -372,6 +376,13 @@ int pm_plan_set_fft_variant(pm_plan *p, int two_stage)
     p->fft_v2 = (two_stage != 0);
     p->fft_zmix = (two_stage == 1 || two_stage >= 3);
     p->fft_v3 = two_stage == 3 ? 2 : two_stage == 4 ? 3 : 0;
+    return PM_OK;
+}
+
+int pm_plan_set_gather_tiled(pm_plan *p, int tiled)
+{
+    if (!p) return PM_ERR_INVALID;
+    p->gather_tiled = (tiled != 0);
     return PM_OK;
 }
 

@@ -67,6 +67,7 @@ struct pm_plan {
     int sort_mode;          // PM_SORT_AUTO / PM_SORT_FULL
     int64_t rsorted_n;      // the first rsorted_n entries of set rcur are stored in the order of
                             // the previous sort and keys_sorted[] still holds the keys they had
+    bool gather_tiled;      // resident gather through shared-memory phi slabs (pm_gather_tiled.cuh) where supported
     bool inc_counted;       // inc_tile already holds this step's movers per tile (counted by the resident gather)
     bool rows_valid;        // row_start matches keys_sorted (set by the sort's merge or pm_k_row_offsets)
     int sort_last_mode;     // what the last pm_k_sort did (pm_plan_sort_stats)

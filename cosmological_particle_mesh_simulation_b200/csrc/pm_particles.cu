@@ -523,6 +523,67 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
     return PM_OK;
 }
 
+#include "pm_gather_tiled.cuh"
+
+#ifndef PM_GT_YB
+#define PM_GT_YB 4      // particle rows per CTA
+#endif
+#ifndef PM_GT_NT
+#define PM_GT_NT 384    // threads: one round covers the ~64*YB particles of a step with margin; 384 measured faster than 320, 288
+#endif
+#ifndef PM_GT_MINB
+#define PM_GT_MINB 2    // CTAs per SM the ring is sized for
+#endif
+#ifndef PM_GT_CAP
+#define PM_GT_CAP 384   // staged particles per step
+#endif
+
+// Tiled variant (pm_gather_tiled.cuh) when the mesh and the plan allow it; returns PM_ERR_UNSUPPORTED
+// otherwise so that the caller falls back to the one-thread-per-particle kernel.
+template <int NC>
+static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
+                                  uint32_t *cnt, cudaStream_t st)
+{
+    int zc = 32;
+    while (zc > 1 && (NC % zc || (int64_t)(NC / PM_GT_YB) * (NC / zc) < 8LL * p->sm_count)) zc /= 2;
+    constexpr size_t smem = kGtSmem<NC, PM_GT_YB, PM_GT_CAP>;
+    static_assert(smem <= 227 * 1024 / PM_GT_MINB, "PM_GT_MINB CTAs per SM");
+    auto kern = k_gather_tiled<NC, PM_GT_YB, PM_GT_NT, PM_GT_CAP, PM_GT_MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    const int c = p->rcur, o = c ^ 1;
+    GatherTiledArgs A;
+    A.px = p->rpos[c]; A.py = A.px + p->rstride; A.pz = A.py + p->rstride;
+    A.vx = p->rvel[c]; A.vy = A.vx + p->rstride; A.vz = A.vy + p->rstride;
+    A.id_in = p->rid[c];
+    A.perm = p->order_sorted; A.row_start = p->row_start;
+    A.pos_out = p->rpos[o]; A.vel_out = p->rvel[o]; A.id_out = p->rid[o];
+    A.keys_out = p->keys; A.mover_cnt = cnt; A.phi = phi;
+    A.sout = p->rstride;
+    A.zc = zc;
+    A.k_kick = k_kick; A.da = da; A.aa = aa; A.raa = pm_div_rcp(aa, da); A.f_a1 = f_a1;
+    dim3 grid(NC / PM_GT_YB, NC / zc);
+    PM_LAUNCH(kern, grid, PM_GT_NT, smem, st, A);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+static int pm_try_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
+                               uint32_t *cnt, cudaStream_t st)
+{
+    if (!p->gather_tiled || p->dep_nseg != 1 || !p->rows_valid) return PM_ERR_UNSUPPORTED;
+    switch (p->nc) {
+    case 128: return pm_launch_gather_tiled<128>(p, phi, k_kick, da, aa, f_a1, cnt, st);
+    case 256: return pm_launch_gather_tiled<256>(p, phi, k_kick, da, aa, f_a1, cnt, st);
+    case 512: return pm_launch_gather_tiled<512>(p, phi, k_kick, da, aa, f_a1, cnt, st);
+    default: return PM_ERR_UNSUPPORTED;
+    }
+}
+
 // Resident variant: reads buffer set `cur` through the new cell order, writes set `cur^1` and the
 // next step's keys (p->keys).
 int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
@@ -537,6 +598,14 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
     static const bool count_here = !(getenv("PM_GATHER_COUNT") && strcmp(getenv("PM_GATHER_COUNT"), "0") == 0);
     uint32_t *cnt = (count_here && p->inc_a && p->sort_mode != PM_SORT_FULL) ? p->inc_tile : nullptr;
     if (cnt) PM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (pm_sort_tiles(np) + 1), st));
+    {
+        const int rc = pm_try_gather_tiled(p, phi, k_kick, da, aa, f_a1, cnt, st);
+        if (rc == PM_OK) {
+            p->inc_counted = (cnt != nullptr);
+            return PM_OK;
+        }
+        if (rc != PM_ERR_UNSUPPORTED) return rc;
+    }
     auto kern = k_gather_kick_drift<true, false>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c],
               p->rvel[c], p->rid[c], p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np,

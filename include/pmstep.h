@@ -94,6 +94,11 @@ PM_API int pm_plan_set_fft_fuse(pm_plan *plan, int fuse, int lag);
  *   4  as 3 with a ring of 3 tiles (PM_FFT_V3=3) */
 PM_API int pm_plan_set_fft_variant(pm_plan *plan, int two_stage);
 PM_API int pm_plan_fft_sync_errors(pm_plan *plan);
+/* Resident gather + kick + drift (pm_step_resident): tiled != 0 stages the potential through shared
+ * memory (a CTA owns a block of particle rows and marches along z with a ring of phi slabs fed by
+ * cp.async; csrc/pm_gather_tiled.cuh) on meshes of 128, 256 or 512 cells; 0 runs one thread per
+ * particle with scattered loads.  Bit-identical results.  Also PM_GATHER_TILED=1 / 0. */
+PM_API int pm_plan_set_gather_tiled(pm_plan *plan, int tiled);
 /* How the resident paths (pm_step_resident, pm_slab_deposit) order the particle list by cell key
  * (the order fixes the deposit's summation tree and the locality of deposit and gather; the
  * reference scatters in particle-index order, src/density.py:17, and has no counterpart):
