@@ -261,8 +261,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         if (p->fft_lag > n_cells) p->fft_lag = n_cells;
     }
     {
-        const char *gt = getenv("PM_GATHER_TILED");   // "1": shared-memory phi slabs in the resident gather
-        p->gather_tiled = (gt && strcmp(gt, "1") == 0);
+        const char *gt = getenv("PM_GATHER_TILED");   // "0": one thread per particle, scattered phi loads
+        p->gather_tiled = !(gt && strcmp(gt, "0") == 0);
     }
     {
         const char *sm = getenv("PM_SORT");   // "full" forces the radix sort of every entry (A/B checks)

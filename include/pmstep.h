@@ -97,7 +97,8 @@ PM_API int pm_plan_fft_sync_errors(pm_plan *plan);
 /* Resident gather + kick + drift (pm_step_resident): tiled != 0 stages the potential through shared
  * memory (a CTA owns a block of particle rows and marches along z with a ring of phi slabs fed by
  * cp.async; csrc/pm_gather_tiled.cuh) on meshes of 128, 256 or 512 cells; 0 runs one thread per
- * particle with scattered loads.  Bit-identical results.  Also PM_GATHER_TILED=1 / 0. */
+ * particle with scattered loads (also PM_GATHER_TILED=0).  Default on: 0.50 ms against 0.55 ms at
+ * 256^3 particles on 512^3 cells.  Bit-identical results. */
 PM_API int pm_plan_set_gather_tiled(pm_plan *plan, int tiled);
 /* How the resident paths (pm_step_resident, pm_slab_deposit) order the particle list by cell key
  * (the order fixes the deposit's summation tree and the locality of deposit and gather; the
