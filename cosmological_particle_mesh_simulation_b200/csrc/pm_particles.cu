@@ -348,7 +348,7 @@ __device__ __forceinline__ float pm_gp(const float (&v)[4][4][4], const float (&
 // RN(q + e*r) is the correctly rounded x/b (Markstein's final division step) -- three FP64
 // instructions instead of the ~35 of the IEEE division sequence, same bits.  Valid away from
 // overflow/underflow (pm_div_rcp checks the ranges on the host and returns 0 to ask for __ddiv_rn);
-// oracle/check_const_div.py replays the sequence in exact rational arithmetic.
+// the CPU test suite replays the sequence in exact rational arithmetic (constant-divisor test).
 __device__ __forceinline__ double pm_div_const(double x, double b, double r)
 {
     if (r == 0.0) return __ddiv_rn(x, b);   // launch-uniform
