@@ -140,6 +140,59 @@ np.savez_compressed(case['out'], **out)
 print('wrote', case['out'], 'rho.min', float(rho.min()), 'trip', n)
 """
 
+# Initial conditions (SURVEY 8f row f1).  gaussian_random_field.py and zeldovich.py are imported
+# UNMODIFIED; the functions that can execute under NumPy 2 are called as they are:
+# power_spectrum, potential_k, displacement_field_k, zeldovich_positions, zeldovich_velocities.
+# The two pyFFTW call sites (gaussian_random_field.py:27-29, zeldovich.py:49-53) allocate with
+# dtype='cfloat', which NumPy >= 2 rejects; their results (normalised inverse c2c DFTs) are formed
+# here with scipy.fft.ifftn and are marked *_unpinned.  Entries the reference leaves uninitialised
+# (np.divide(..., where=) without out=, at k = 0) are set to 0 by the harness.  The noise fields
+# and the jitter are harness inputs: the reference's own draws are not reproducible (SURVEY Q15);
+# zeldovich_positions draws its jitter from the stdlib `random`, seeded here just before the call.
+WORKER_IC = """\
+import sys, json, random
+import numpy as np
+import scipy.fft
+case = json.loads(sys.argv[1])
+import gaussian_random_field as G            # /root/reference/src/gaussian_random_field.py
+import zeldovich as Z                        # /root/reference/src/zeldovich.py
+from configure_me import N_PARTS, N_CELLS, BOX_SIZE, A_INIT, OMEGA_M0, OMEGA_LAMBDA0, OMEGA_K0
+from cosmology import Dt
+n = N_PARTS
+rs = np.random.RandomState(case['seed'])
+f1 = rs.standard_normal((n, n, n)).astype(np.float32)
+f2 = rs.standard_normal((n, n, n)).astype(np.float32)
+out = dict(f1=f1, f2=f2, n_parts=np.int64(N_PARTS), n_cells=np.int64(N_CELLS), a_init=np.float64(A_INIT))
+p = G.power_spectrum()                       # gaussian_random_field.py:91-123
+assert np.isfinite(p).all(), 'uninitialised k=0 entries leaked into the normalisation; rerun'
+out['power_spectrum'] = p
+D = Dt(A_INIT, [OMEGA_M0, OMEGA_LAMBDA0, OMEGA_K0])
+rho_k = np.sqrt(p * D ** 2) * f1 + 1j * (np.sqrt(p * D ** 2) * f2)     # :21-24
+density = (scipy.fft.ifftn(rho_k, axes=(0, 1, 2)).real).astype('float32')   # :27-29 (unpinned)
+out['density_unpinned'] = density
+density_k = np.fft.fftn(density.astype(np.float64))   # zeldovich.py:17 (complex128 as under the reference's NumPy 1.x; NumPy 2 would keep single precision)
+pot_k = Z.potential_k(density_k)             # zeldovich.py:24-38
+pot_k[0, 0, 0] = 0.0
+out['pot_k'] = pot_k
+for d in (0, 1, 2):
+    dfk = Z.displacement_field_k(pot_k, d)   # zeldovich.py:56-69
+    out['dfk_%d' % d] = dfk
+    disp = np.reshape(scipy.fft.ifftn(dfk.astype(np.complex128), axes=(0, 1, 2)), n ** 3).real * (N_CELLS / BOX_SIZE)  # :45-54 (unpinned)
+    out['disp_unpinned_%d' % d] = disp
+    random.seed(case['seed'] + d)
+    jitter = np.array([random.uniform(-2., 2.) for _ in range(n ** 3)])
+    random.seed(case['seed'] + d)
+    out['jitter_%d' % d] = jitter
+    out['pos_%d' % d] = Z.zeldovich_positions(disp.copy(), d)      # zeldovich.py:71-93
+    out['vel_%d' % d] = Z.zeldovich_velocities(disp)               # zeldovich.py:95-100
+np.savez_compressed(case['out'], **out)
+print('wrote', case['out'])
+"""
+
+IC_CASES = [
+    dict(name="ic16", N_PARTS=16, N_CELLS=32, STEPS=100, A_INIT=0.01, seed=38),
+]
+
 CASES = [
     dict(name="g16_free10", N_PARTS=16, N_CELLS=32, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
          vel_rms=0.05, nsteps=10, keep_mesh=[0, 9]),
@@ -179,5 +232,25 @@ def main():
                            check=True, env=env, cwd=tmp)
 
 
+def main_ic():
+    only = set(sys.argv[1:])
+    for case in IC_CASES:
+        if only and case["name"] not in only:
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            with open(os.path.join(tmp, "configure_me.py"), "w") as fh:
+                fh.write(CONFIGURE_ME.format(**case))
+            with open(os.path.join(tmp, "pyfftw.py"), "w") as fh:
+                fh.write(PYFFTW_SHIM)
+            with open(os.path.join(tmp, "worker_ic.py"), "w") as fh:
+                fh.write(textwrap.dedent(WORKER_IC))
+            arg = dict(case, out=os.path.join(GOLDEN, case["name"] + ".npz"))
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([tmp, REF_SRC]), NUMBA_NUM_THREADS="1",
+                       NUMBA_CACHE_DIR=os.path.join(tmp, "nbcache"))
+            subprocess.run([sys.executable, os.path.join(tmp, "worker_ic.py"), json.dumps(arg)],
+                           check=True, env=env, cwd=tmp)
+
+
 if __name__ == "__main__":
+    main_ic()
     main()

@@ -171,7 +171,7 @@ def zeldovich(density, jitter, cfg: ICConfig):
     n3 = cfg.N_PARTS ** 3
     positions = np.zeros((3, n3), dtype=np.float32)
     velocities = np.zeros((3, n3), dtype=np.float32)
-    density_k = np.fft.fftn(density)
+    density_k = np.fft.fftn(density.astype(np.float64))   # complex128, as np.fft did under the reference's NumPy 1.x
     for direction in (0, 1, 2):
         pot_k = potential_k(density_k, cfg)
         disp = displacement_field_one_direction(pot_k, direction, cfg)

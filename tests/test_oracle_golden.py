@@ -118,3 +118,29 @@ def test_constant_divisor_division_is_correctly_rounded():
     replay in exact arithmetic must give the IEEE quotient every time."""
     from oracle.check_const_div import mismatches
     assert mismatches(60, 300) == 0
+
+
+def test_ic_oracle_reproduces_the_reference_functions(golden_dir):
+    """oracle/oracle_ic.py against tests/golden/ic16.npz, the outputs of the reference's own
+    gaussian_random_field.power_spectrum and zeldovich.{potential_k, displacement_field_k,
+    zeldovich_positions, zeldovich_velocities} (oracle/make_golden.py).  Same NumPy expressions in
+    the same order: bit-exact.  The two pyFFTW sites are unpinned (see the oracle's header)."""
+    from oracle import oracle_ic as IC
+    g = np.load(os.path.join(golden_dir, "ic16.npz"))
+    cfg = IC.ICConfig(N_PARTS=int(g["n_parts"]), N_CELLS=int(g["n_cells"]), A_INIT=float(g["a_init"]))
+    assert np.array_equal(IC.power_spectrum(cfg), g["power_spectrum"])
+    density = IC.gaussian_random_field(g["f1"], g["f2"], cfg)
+    assert np.array_equal(density, g["density_unpinned"])
+    pot_k = IC.potential_k(np.fft.fftn(density.astype(np.float64)), cfg)
+    assert np.array_equal(pot_k, g["pot_k"])
+    for d in (0, 1, 2):
+        assert np.array_equal(IC.displacement_field_k(pot_k, d, cfg), g["dfk_%d" % d])
+        disp = IC.displacement_field_one_direction(pot_k, d, cfg)
+        assert np.array_equal(disp, g["disp_unpinned_%d" % d])
+        assert np.array_equal(IC.zeldovich_positions(disp, d, g["jitter_%d" % d], cfg), g["pos_%d" % d])
+        assert np.array_equal(IC.zeldovich_velocities(disp, cfg), g["vel_%d" % d])
+    jit = np.stack([g["jitter_%d" % d] for d in (0, 1, 2)])
+    pos, vel = IC.zeldovich(density, jit, cfg)
+    for d in (0, 1, 2):
+        assert np.array_equal(pos[d], g["pos_%d" % d].astype(np.float32))
+        assert np.array_equal(vel[d], g["vel_%d" % d].astype(np.float32))
