@@ -10,6 +10,8 @@ The module names and call signatures mirror the reference's flat source tree:
     integrate.integrate(positions, velocities, a_val, f_a1, da, potentials) src/integrate.py:16
     cosmology.f(a, cosmology)                              src/cosmology.py:20
     configure_me.*                                         src/configure_me.py:7-40
+    gaussian_random_field.gaussian_random_field()          src/gaussian_random_field.py:9   (initial conditions)
+    zeldovich.zeldovich(density)                           src/zeldovich.py:10
 
 All arithmetic runs in libpmstep.so (hand-written sm_100a CUDA + cuFFT) through the C ABI of
 include/pmstep.h.  CUDA tensors in -> CUDA tensors out (state stays in HBM); NumPy arrays in ->
@@ -24,3 +26,5 @@ from .integrate import advance_time, integrate  # noqa: F401
 from .cosmology import f  # noqa: F401
 from .pmesh import step, step_host, simulator, loop_scale_factors, ResidentParticles  # noqa: F401
 from . import slab, analysis  # noqa: F401,E402
+from .gaussian_random_field import gaussian_random_field  # noqa: F401,E402
+from .zeldovich import zeldovich  # noqa: F401,E402

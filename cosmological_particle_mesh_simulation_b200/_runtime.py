@@ -32,6 +32,23 @@ class PMStepError(RuntimeError):
         super().__init__(f"{where}: libpmstep error {self.code}: {msg}")
 
 
+class ICParams(ctypes.Structure):
+    """pm_ic_params of include/pmstep.h."""
+    _fields_ = [("n_parts", ctypes.c_int), ("n_cells", ctypes.c_int), ("box_size", ctypes.c_double),
+                ("power", ctypes.c_double), ("lcdm_transfer", ctypes.c_int), ("omega_m0", ctypes.c_double),
+                ("omega_b0", ctypes.c_double), ("omega_k0", ctypes.c_double),
+                ("omega_lambda0", ctypes.c_double), ("h0", ctypes.c_double), ("a_init", ctypes.c_double)]
+
+
+def ic_params(cfg=None) -> ICParams:
+    """pm_ic_params from the configure_me names the reference's IC modules read
+    (src/gaussian_random_field.py:4-5, src/zeldovich.py:7-8)."""
+    c = cfg if cfg is not None else config()
+    return ICParams(int(c.N_PARTS), int(c.N_CELLS), float(c.BOX_SIZE), float(c.POWER),
+                    int(bool(c.LCDM_TRANSFER_FUNCTION)), float(c.OMEGA_M0), float(c.OMEGA_B0),
+                    float(c.OMEGA_K0), float(c.OMEGA_LAMBDA0), float(c.H0), float(c.A_INIT))
+
+
 def lib():
     """Load libpmstep.so (once).  Raises if it has not been built -- run
     ``python -c 'import __graft_entry__ as g; g.build()'`` or ``make -C <pkg>/csrc``."""
@@ -96,6 +113,12 @@ def lib():
             "pm_slab_migrate_pack": (i32, [vp, vp, vp]),
             "pm_slab_migrate_unpack": (i32, [vp, i64, i64, vp]),
             "pm_slab_export": (i32, [vp, vp, vp, vp, vp, vp]),
+            "pm_ic_workspace_bytes": (sz, [i32]),
+            "pm_ic_noise": (i32, [vp, vp, i64, ctypes.c_uint64, vp]),
+            "pm_ic_jitter": (i32, [vp, i64, ctypes.c_uint64, vp]),
+            "pm_ic_power_spectrum": (i32, [ctypes.POINTER(ICParams), vp, vp, sz, vp]),
+            "pm_ic_gaussian_random_field": (i32, [ctypes.POINTER(ICParams), vp, vp, vp, vp, sz, vp]),
+            "pm_ic_zeldovich": (i32, [ctypes.POINTER(ICParams), vp, vp, vp, vp, vp, sz, vp]),
             "pm_plan_profile_begin": (i32, [vp, i32]),
             "pm_plan_profile_read": (i32, [vp, vp, ctypes.POINTER(i32)]),
         }
@@ -118,7 +141,8 @@ EXPORTED_SYMBOLS = (
     "pm_slab_fft_z", "pm_slab_fft_y_inverse", "pm_slab_fft_rows_inverse", "pm_slab_gather",
     "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export", "pm_power_spectrum",
     "pm_plan_set_sort_mode", "pm_plan_sort_stats", "pm_plan_set_fft_fuse", "pm_plan_fft_sync_errors",
-    "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled",
+    "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled", "pm_ic_workspace_bytes", "pm_ic_noise",
+    "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

@@ -283,6 +283,40 @@ PM_API int pm_step_host(pm_plan *plan, float *pos_h, float *vel_h, int64_t np, d
 PM_API int pm_plan_profile_begin(pm_plan *plan, int max_steps);
 PM_API int pm_plan_profile_read(pm_plan *plan, float *ms, int *n_steps);
 
+/* ------------------------------------------------------------------------------------------------
+ * Initial conditions (not part of the per-step path).  Replaces
+ * gaussian_random_field() (src/gaussian_random_field.py:9-29) and zeldovich(density)
+ * (src/zeldovich.py:10-22), called once from src/pmesh.py:40,42.  float64 / complex128 arithmetic
+ * like the reference (cuFFT Z2Z for its two pyFFTW inverse transforms and its np.fft.fftn), float32
+ * where the reference stores float32.  The two things the reference draws irreproducibly
+ * are explicit arrays here, so a caller can also supply its own:
+ *   pm_ic_noise   f1, f2: float32[n] standard normals by the reference's polar Box-Muller
+ *                 (gaussian_random_field.py:31-63) from Philox4x32-10(seed, element index);
+ *   pm_ic_jitter  float64[3][n] uniform(-2, 2) (zeldovich.py:89-91), same generator.
+ * Entries the reference leaves uninitialised at k = 0 are 0.  All pointers are device pointers;
+ * work_d needs pm_ic_workspace_bytes(n_parts) bytes.  cuFFT allocates its own plan work area inside
+ * the calls (one-time setup code, unlike the per-step path).  The calls synchronise the stream.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pm_ic_params {
+    int n_parts, n_cells;     /* configure_me.N_PARTS, N_CELLS */
+    double box_size;          /* BOX_SIZE [Mpc/h] */
+    double power;             /* POWER */
+    int lcdm_transfer;        /* LCDM_TRANSFER_FUNCTION */
+    double omega_m0, omega_b0, omega_k0, omega_lambda0, h0, a_init;
+} pm_ic_params;
+PM_API size_t pm_ic_workspace_bytes(int n_parts);
+PM_API int pm_ic_noise(float *f1_d, float *f2_d, int64_t n, uint64_t seed, pm_stream_t stream);
+PM_API int pm_ic_jitter(double *jitter_d, int64_t n, uint64_t seed, pm_stream_t stream);
+/* p_d: float64[n_parts^3], the grid power_spectrum() returns (gaussian_random_field.py:91-123) */
+PM_API int pm_ic_power_spectrum(const pm_ic_params *prm, double *p_d, void *work_d, size_t work_bytes,
+                                pm_stream_t stream);
+/* density_d: float32[n_parts^3] = (ifftn(sqrt(p D^2) (f1 + i f2)).real).astype(float32) */
+PM_API int pm_ic_gaussian_random_field(const pm_ic_params *prm, const float *f1_d, const float *f2_d,
+                                       float *density_d, void *work_d, size_t work_bytes, pm_stream_t stream);
+/* pos_d, vel_d: float32[3][n_parts^3] in the reference's particle order; jitter_d: float64[3][n_parts^3] */
+PM_API int pm_ic_zeldovich(const pm_ic_params *prm, const float *density_d, const double *jitter_d,
+                           float *pos_d, float *vel_d, void *work_d, size_t work_bytes, pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
