@@ -12,6 +12,9 @@ The module names and call signatures mirror the reference's flat source tree:
     configure_me.*                                         src/configure_me.py:7-40
     gaussian_random_field.gaussian_random_field()          src/gaussian_random_field.py:9   (initial conditions)
     zeldovich.zeldovich(density)                           src/zeldovich.py:10
+    save_data.save_file(rho, positions, velocities, step, a), from_file(step)   src/save_data.py:7,29
+    plot_helper.plot_step / plot_grf / plot_projection / project               src/plot_helper.py:12-72
+    pmesh.simulator()                                      src/pmesh.py:18  (the whole driver)
 
 All arithmetic runs in libpmstep.so (hand-written sm_100a CUDA + cuFFT) through the C ABI of
 include/pmstep.h.  CUDA tensors in -> CUDA tensors out (state stays in HBM); NumPy arrays in ->
@@ -24,7 +27,9 @@ from .fourier_utils import fourier_grid, FourierGrid  # noqa: F401
 from .potential import potential  # noqa: F401
 from .integrate import advance_time, integrate  # noqa: F401
 from .cosmology import f  # noqa: F401
-from .pmesh import step, step_host, simulator, loop_scale_factors, ResidentParticles  # noqa: F401
+from .pmesh import step, step_host, simulator, run, loop_scale_factors, ResidentParticles  # noqa: F401
 from . import slab, analysis  # noqa: F401,E402
 from .gaussian_random_field import gaussian_random_field  # noqa: F401,E402
 from .zeldovich import zeldovich  # noqa: F401,E402
+from .save_data import save_file, from_file  # noqa: F401,E402
+from . import save_data, plot_helper  # noqa: F401,E402

@@ -4,8 +4,9 @@
 out), `ResidentParticles` keeps the state inside the plan in cell order between steps (the fast
 path: pm_step_resident), `step_host` serves state kept in host memory (pm_step_host, copies
 overlapped with compute), and `simulator` is the `while a_current < A_END - da` loop itself with
-the reference's predicate kept verbatim.  Initial conditions, snapshots and plots are outside this package's scope: the
-caller supplies positions/velocities and an optional per-step callback."""
+the reference's predicate kept verbatim.  `run` (= `simulator()` without arguments) is
+the reference's whole driver, src/pmesh.py:18-79: initial conditions or restart, the loop, the
+snapshot/plot cadences and the status line, with the state resident in HBM throughout."""
 try:
     from . import _runtime as rt
     from .cosmology import f
@@ -139,10 +140,14 @@ def loop_scale_factors(cfg=None):
     return out
 
 
-def simulator(positions, velocities, on_step=None, max_steps=None):
-    """Run the loop of src/pmesh.py:56-63 on CUDA tensors.  on_step(i, a_current, rho, positions,
-    velocities) is called after each step with the PRE-step density and POST-step particles,
-    the pairing the reference's save_file sees (src/pmesh.py:60-67)."""
+def simulator(positions=None, velocities=None, on_step=None, max_steps=None):
+    """Without arguments: the reference's driver, src/pmesh.py:18-79 (see `run`).
+
+    With CUDA tensors: run the loop of src/pmesh.py:56-63 on them.  on_step(i, a_current, rho,
+    positions, velocities) is called after each step with the PRE-step density and POST-step
+    particles, the pairing the reference's save_file sees (src/pmesh.py:60-67)."""
+    if positions is None:
+        return run(max_steps=max_steps)
     cfg = rt.config()
     n = int(cfg.N_CELLS)
     rho = torch.empty((n, n, n), dtype=torch.float32, device=positions.device) if on_step else None
@@ -155,3 +160,106 @@ def simulator(positions, velocities, on_step=None, max_steps=None):
             state.store(positions, velocities)
             on_step(i, a_current + da, rho, positions, velocities)
     return state.store(positions, velocities)
+
+
+def run(max_steps=None, device=None):
+    """The reference's whole driver, src/pmesh.py:18-79, statement for statement: initial
+    conditions or restart (:39-52), the integration loop with its predicate (:56-63), the snapshot
+    and plot cadences (:65-74) and the status line (:76-77, :81-84).
+
+    B200 specifics: the particle state stays in HBM in cell order for the whole run
+    (ResidentParticles); the density mesh is only written out of the step, and the particles only
+    brought back to original order, on the steps whose cadence test fires (decided before the step
+    from the same floating-point expressions the reference evaluates after it); snapshots leave
+    through save_data's copy stream and writer thread, so the following steps overlap the
+    device->host copy and the disk write.  Returns (positions, velocities, a_current)."""
+    from time import time
+    try:
+        from .gaussian_random_field import gaussian_random_field
+        from .zeldovich import zeldovich
+        from .save_data import save_file, from_file, wait
+        from .plot_helper import plot_step, plot_grf, plot_projection
+    except ImportError:
+        from gaussian_random_field import gaussian_random_field
+        from zeldovich import zeldovich
+        from save_data import save_file, from_file, wait
+        from plot_helper import plot_step, plot_grf, plot_projection
+    cfg = rt.config()
+    dev = rt.current_device() if device is None else int(device)
+    N_CELLS, N_PARTS, STEPS = int(cfg.N_CELLS), int(cfg.N_PARTS), cfg.STEPS
+    A_INIT, A_END = cfg.A_INIT, cfg.A_END
+    flag = lambda name: bool(getattr(cfg, name, False))    # noqa: E731
+
+    print('Starting the simulation for {}^3 particles'.format(N_PARTS), 'with {}^3 grid cells'.format(N_CELLS))
+    particle_mass = 1.32 * 10 ** 5 * (cfg.OMEGA_M0 * cfg.H0 ** 2) * (cfg.BOX_SIZE / (N_PARTS / 128)) ** 3
+    print('Particle mass in solar mass for this configuration: {:.3E}'.format(particle_mass))
+    dens_contrast = (N_CELLS / N_PARTS) ** 3
+    print('Particle mass in code units: {:.3e}'.format(dens_contrast))
+    da = (A_END - A_INIT) / STEPS
+    da_save = (A_END - A_INIT) / cfg.N_SAVE_FILES
+    da_plot = (A_END - A_INIT) / cfg.N_PLOTS
+    a_current = A_INIT
+    n_file = 0
+    n_plot = 0
+
+    with torch.cuda.device(dev):
+        if flag("RESTART"):
+            print("Restarting from file data.{}.hdf5".format(cfg.RESTART_FROM_N))
+            n_file = cfg.RESTART_FROM_N
+            n_plot = (cfg.RESTART_FROM_N) / cfg.N_SAVE_FILES * cfg.N_PLOTS
+            positions, velocities, a_current = from_file(n_file, device=dev)
+        else:
+            rho = gaussian_random_field(device=dev)
+            positions, velocities = zeldovich(rho)
+            if flag("SAVE_DATA"):
+                save_file(rho, positions, velocities, 0, a_current)
+                n_file += 1
+            if flag("PLOT_GRF"):
+                plot_grf(rho)
+            del rho
+
+        rho = torch.empty((N_CELLS,) * 3, dtype=torch.float32, device=positions.device)
+        state = ResidentParticles(positions, velocities)       # fourier_grid(): tables live in the plan
+        print('Starting the integrations...')
+        n_steps = 0
+        while a_current < A_END - da:
+            if max_steps is not None and n_steps >= max_steps:
+                break
+            start_time = time()
+            a_next = a_current + da                                  # the value the cadence tests see
+            saving = a_next >= A_INIT + n_file * da_save
+            plotting = a_next >= A_INIT + n_plot * da_plot
+            want_save = saving and flag("SAVE_DATA")
+            want_plot = plotting and (flag("PLOT_STEPS") or flag("PLOT_PROJECTIONS"))
+            need_rho = want_plot or (want_save and flag("SAVE_DENSITY"))
+
+            state.step(a_current, da, mass=dens_contrast, rho_out=rho if need_rho else None)
+            a_current += da
+
+            if saving:
+                if want_save:
+                    state.store(positions, velocities)
+                    save_file(rho if need_rho else None, positions, velocities, n_file, a_current)
+                n_file += 1
+            if plotting:
+                if flag("PLOT_STEPS"):
+                    plot_step(rho, n_plot)
+                if flag("PLOT_PROJECTIONS"):
+                    plot_projection(rho, n_plot, 15)
+                n_plot += 1
+            if flag("PRINT_STATUS"):
+                torch.cuda.synchronize(dev)          # the reference's line reports a finished step
+                print_status(a_current, start_time, cfg)
+            n_steps += 1
+        state.store(positions, velocities)
+        torch.cuda.synchronize(dev)
+    wait()
+    return positions, velocities, a_current
+
+
+def print_status(a_current, start_time, cfg=None):
+    """src/pmesh.py:81-84."""
+    from time import time
+    cfg = cfg or rt.config()
+    percentile = 100 * (a_current - cfg.A_INIT) / (cfg.A_END - cfg.A_INIT)
+    print("%.5f" % percentile, "%", " Save step time: --- %.5f seconds ---" % (time() - start_time))

@@ -177,6 +177,34 @@ def loop_trip_count(cfg: Config) -> int:
     return n
 
 
+def loop_cadence(cfg, a_start=None, n_file=1, n_plot=0):
+    """pmesh.py:30-34,56-74 restated: which loop iterations write a snapshot / a plot, under which
+    file index and at which a_current.  cfg needs N_SAVE_FILES and N_PLOTS besides the Config names;
+    n_file = 1 is the state after the initial-conditions snapshot (pmesh.py:46-48)."""
+    da = (cfg.A_END - cfg.A_INIT) / cfg.STEPS
+    da_save = (cfg.A_END - cfg.A_INIT) / cfg.N_SAVE_FILES
+    da_plot = (cfg.A_END - cfg.A_INIT) / cfg.N_PLOTS
+    a_current = cfg.A_INIT if a_start is None else a_start
+    saves, plots, i = [], [], 0
+    while a_current < cfg.A_END - da:
+        a_current += da
+        if a_current >= cfg.A_INIT + n_file * da_save:
+            saves.append((i, n_file, a_current))
+            n_file += 1
+        if a_current >= cfg.A_INIT + n_plot * da_plot:
+            plots.append((i, n_plot))
+            n_plot += 1
+        i += 1
+    return saves, plots
+
+
+def snapshot_units(a, cfg):
+    """save_data.py:10-11: (unit_conv_pos [Mpc], unit_conv_vel [km/s]); cfg needs BOX_SIZE."""
+    unit_conv_pos = 7.8 * (cfg.BOX_SIZE / (cfg.N_CELLS / 128)) / 10 ** 3
+    unit_conv_vel = 0.781 * cfg.BOX_SIZE * cfg.H0 / (a * cfg.N_CELLS / 128)
+    return unit_conv_pos, unit_conv_vel
+
+
 def step(positions, velocities, fgrid, a_current, da, cfg: Config, mass=None):
     """One body of the loop pmesh.py:56-63.  Returns (rho, positions, velocities)."""
     if mass is None:
