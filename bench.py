@@ -284,23 +284,25 @@ def run_slab(args, rank, world, local_rank):
     npart = n_parts ** 3
     mass = (n_cells / n_parts) ** 3
     comm = slab.DistComm()
-    if n_parts > 256:
-        # large configurations: every rank generates its own slab on its GPU
-        pl, vl, il = make_particles_slab_gpu(n_parts, n_cells, rank, world, dev)
-        ranks = [slab.make_rank_from_local(n_cells, pl, vl, il, rank, world, device=dev)]
-        cnt = torch.tensor([pl.shape[1]], dtype=torch.int64, device=f"cuda:{dev}")
-        dist.all_reduce(cnt)
-        assert int(cnt.item()) == npart, (int(cnt.item()), npart)
-        del pl, vl, il
-        particles_desc = ("lattice + uniform(-2,2) jitter, Gaussian velocities rms %g (counter-based hash, seed 38), "
-                          "generated per slab on the GPU" % VEL_SIGMA)
-    else:
-        pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
-        pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
-        ranks = slab.make_ranks(n_cells, pos, vel, comm, device=dev)
-        del pos, vel
-        particles_desc = "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA
-    torch.cuda.empty_cache()
+    def build_ranks():
+        if n_parts > 256:
+            # large configurations: every rank generates its own slab on its GPU
+            pl, vl, il = make_particles_slab_gpu(n_parts, n_cells, rank, world, dev)
+            out = [slab.make_rank_from_local(n_cells, pl, vl, il, rank, world, device=dev)]
+            cnt = torch.tensor([pl.shape[1]], dtype=torch.int64, device=f"cuda:{dev}")
+            dist.all_reduce(cnt)
+            assert int(cnt.item()) == npart, (int(cnt.item()), npart)
+            desc = ("lattice + uniform(-2,2) jitter, Gaussian velocities rms %g (counter-based hash, seed 38), "
+                    "generated per slab on the GPU" % VEL_SIGMA)
+        else:
+            pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
+            pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
+            out = slab.make_ranks(n_cells, pos, vel, comm, device=dev)
+            desc = "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA
+        torch.cuda.empty_cache()
+        return out, desc
+
+    ranks, particles_desc = build_ranks()
     sched = pm.loop_scale_factors(cfg)
 
     def barrier():
@@ -309,11 +311,38 @@ def run_slab(args, rank, world, local_rank):
 
     K, W = args.steps, args.warmup
     step_i = 0
-    for _ in range(W):
-        a, da = sched[step_i % len(sched)]
-        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=args.chunks or None)
-        step_i += 1
-    barrier()
+
+    def warm_up(transport):
+        nonlocal step_i
+        for _ in range(W):
+            a, da = sched[step_i % len(sched)]
+            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=args.chunks or None, transport=transport)
+            step_i += 1
+        barrier()
+
+    # FFT transposes through peer memory (CUDA IPC + NVLink stores/loads) unless --transport nccl.
+    # setup_peers() ends with a flag handshake through the mapped memory and all ranks agree on the
+    # outcome; if the set-up fails, or a flag wait times out during warm-up on any rank, every rank
+    # rebuilds its state and runs the NCCL all-to-all path instead -- and the JSON line says which.
+    transport, transport_note = "nccl", ""
+    if args.transport != "nccl":
+        transport = "peer" if slab.setup_peers(ranks, comm) else "nccl"
+        if transport != "peer":
+            transport_note = "peer-memory set-up failed; "
+    warm_up(transport)
+    if transport == "peer":
+        bad = torch.tensor([ranks[0].peer_timeouts()], dtype=torch.int64, device=f"cuda:{dev}")
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            transport, transport_note = "nccl", "peer-memory flag wait timed out in warm-up; "
+            slab.release_peers(ranks, comm)
+            for r in ranks:
+                r.close()
+            ranks, particles_desc = build_ranks()
+            step_i = 0
+            warm_up(transport)
+    if args.transport == "peer" and transport != "peer":
+        raise RuntimeError("--transport peer: " + transport_note)
     # sanity on the distributed state: total mass of the last deposit == Np * mass
     msum = ranks[0].buf["RHO"].sum(dtype=torch.float64).reshape(1)
     dist.all_reduce(msum)
@@ -329,7 +358,8 @@ def run_slab(args, rank, world, local_rank):
     ev0.record()
     for _ in range(K):
         a, da = sched[step_i % len(sched)]
-        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, timer=timer, chunks=args.chunks or None)
+        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, timer=timer, chunks=args.chunks or None,
+                       transport=transport)
         step_i += 1
     ev1.record()
     barrier()
@@ -360,7 +390,7 @@ def run_slab(args, rank, world, local_rank):
         di = hi.to(f"cuda:{dev}", non_blocking=True)
         h2d += dp.numel() * 4 * 2 + di.numel() * 4
         sr.load(dp.contiguous(), dv.contiguous(), di)
-        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg)
+        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, transport=transport)
         p, v, ids = sr.export()
         hp, hv, hi = p.cpu().pin_memory(), v.cpu().pin_memory(), ids.cpu().pin_memory()
         d2h += p.numel() * 4 * 2 + ids.numel() * 4
@@ -396,8 +426,10 @@ def run_slab(args, rank, world, local_rank):
                        "particles": particles_desc,
                        "l2": "inputs larger than L2",
                        "parallelism": f"slab decomposition along z over {world} GPUs: NCCL send/recv ghost planes, "
-                                      f"all-to-all transposed FFT pipelined in {chunks} kx chunks on a second stream, "
-                                      "all-to-all-v particle migration"},
+                                      + (f"FFT transposes by peer-memory stores/loads over NVLink (CUDA IPC, flag-word barriers), "
+                                         if transport == "peer" else "FFT transposes by NCCL all-to-all, ")
+                                      + f"pipelined in {chunks} kx chunks on a second stream, all-to-all-v particle migration",
+                       "fft_transport": transport_note + transport},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
                     "d2h_bytes_per_step": float(t[2].item()) / ke, "steps": ke,
@@ -412,6 +444,9 @@ def run_slab(args, rank, world, local_rank):
             "mass_conservation_rel_err": mass_err,
         }
         print(json.dumps(line), flush=True)
+    slab.release_peers(ranks, comm)
+    for r in ranks:
+        r.close()
     dist.destroy_process_group()
 
 
@@ -584,6 +619,8 @@ def main():
     ap.add_argument("--n-cells", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+                    help="FFT transposes of the multi-GPU path: peer-memory copy kernels or NCCL all-to-all")
     ap.add_argument("--reference-budget-s", type=float, default=90.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -24,7 +24,7 @@ int key_bits_for(int nc)
 // Sizes of every workspace segment, in the order they are carved.
 struct Layout {
     size_t keys, iota, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2, tw,
-        rpos, rvel, rid, tbuf, leave_cnt, leave_slot, leave_sorted, mig, inc_a, inc_b, inc_tile, fft_sync,
+        rpos, rvel, rid, tbuf, leave_cnt, leave_slot, leave_sorted, mig, peer_flags, inc_a, inc_b, inc_tile, fft_sync,
         total;
     int64_t leave_cap, inc_bcap;
 };
@@ -81,6 +81,7 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->leave_slot = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 4) : 0;
     L->leave_sorted = g.slab ? align_up((size_t)L->leave_cap * 4) : 0;
     L->mig = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 7 * 4) : 0;
+    L->peer_flags = g.slab ? align_up((size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4) : 0;
     // incremental sort: stayers (np), movers in and out (capacity each), tile tables
     L->inc_bcap = pm_sort_mover_capacity((int64_t)npad);
     L->inc_a = align_up(npad * 8);
@@ -90,7 +91,7 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->total = L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
                L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw +
                2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot +
-               L->leave_sorted + 2 * L->mig + L->inc_a + 2 * L->inc_b + 2 * L->inc_tile;
+               L->leave_sorted + 2 * L->mig + L->peer_flags + L->inc_a + 2 * L->inc_b + 2 * L->inc_tile;
     return PM_OK;
 }
 
@@ -235,6 +236,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         p->mig_send = (float *)c;     c += L.mig;
         p->mig_recv = (float *)c;     c += L.mig;
         p->leave_cap = L.leave_cap;
+        p->peer_flags = (uint32_t *)c; c += L.peer_flags;
     }
     p->inc_a = (uint64_t *)c;         c += L.inc_a;
     p->inc_b = (uint64_t *)c;         c += L.inc_b;
@@ -287,6 +289,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     }
     if (rc == PM_OK && pm_fft_supported(n_cells)) rc = pm_k_fft_tables(p);
     if (rc == PM_OK) rc = (int)cudaMemset(p->fft_sync, 0, sizeof(unsigned));
+    if (rc == PM_OK && p->peer_flags)
+        rc = (int)cudaMemset(p->peer_flags, 0, (size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4);
     if (rc == PM_OK) rc = pm_k_iota(p->iota, np_capacity, 0);
     if (rc == PM_OK) rc = (int)cudaStreamSynchronize(0);
     if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);
@@ -331,6 +335,8 @@ int pm_plan_destroy(pm_plan *p)
     if (p->s_main) cudaStreamDestroy(p->s_main);
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_down) cudaStreamDestroy(p->s_down);
+    for (int s = 0; s < PM_PEER_MAX; ++s)
+        if (p->peer_ipc[s]) cudaIpcCloseMemHandle(p->peer_ipc[s]);
     if (p->ws) cudaFree(p->ws);
     if (p->h_word) cudaFreeHost(p->h_word);
     if (p->prof_ev) {

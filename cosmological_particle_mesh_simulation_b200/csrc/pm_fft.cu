@@ -1132,6 +1132,123 @@ int slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
     return PM_OK;
 }
 
+// ---- peer-memory transposes (pm_slab_fft_push / pm_slab_fft_pull) ---------------------------------
+// The all-to-all of the distributed transform done by the copy kernels themselves.  Rank r's
+// z-pass array (tbuf[1]) chunk c is C_c[z][yl][kc]; the planes z in [s*nzl, (s+1)*nzl) of it belong
+// to rank s's slab.  PUSH (forward leg): rank r stores its y-transformed planes into block [r] of
+// every rank's array -- 16-byte stores, 2*hc*8 bytes contiguous per (zl, y) row, over NVLink for
+// s != r.  PULL (way back): rank r loads block [r] of every rank's array into its spectrum.
+struct PeerPtrs {
+    float2 *p[PM_PEER_MAX];
+};
+
+// VEC = 2: two kx per thread (16-byte accesses; hc even), VEC = 1: the Nyquist plane (hc = 1)
+template <bool PULL, int VEC>
+__global__ void __launch_bounds__(256) k_slab_peer_copy(float2 *__restrict__ full, PeerPtrs peers,
+                                                        size_t peer_off, int rank, int nzl, int n,
+                                                        int h, int k0, int hc, int nyl)
+{
+    // full: [nzl][n][h] local spectrum; peers.p[s] + peer_off: [P*nzl][nyl][hc] on rank s
+    const int hv = hc / VEC;
+    const size_t total = (size_t)nzl * n * hv;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int kc = (int)(i % hv) * VEC;
+        const size_t r = i / hv;
+        const int y = (int)(r % n), zl = (int)(r / n);
+        const int s = y / nyl, yl = y - s * nyl;
+        float2 *loc = full + ((size_t)zl * n + y) * h + k0 + kc;
+        float2 *rem = peers.p[s] + peer_off + (((size_t)rank * nzl + zl) * nyl + yl) * hc + kc;
+        if (VEC == 2) {
+            if (PULL) *reinterpret_cast<float4 *>(loc) = *reinterpret_cast<const float4 *>(rem);
+            else *reinterpret_cast<float4 *>(rem) = *reinterpret_cast<const float4 *>(loc);
+        } else {
+            if (PULL) *loc = *rem;
+            else *rem = *loc;
+        }
+    }
+}
+
+template <bool PULL>
+int slab_peer_copy(pm_plan *p, int c, int C, cudaStream_t st)
+{
+    const int N = p->nc, H = N / 2;
+    const int nzl = p->nzl, nyl = N / p->nranks, hc = H / C;
+    if (hc % 2) return PM_ERR_UNSUPPORTED;
+    PeerPtrs pp;
+    for (int s = 0; s < PM_PEER_MAX; ++s) pp.p[s] = s < p->nranks ? p->peer_recv[s] : nullptr;
+    const size_t main_n = (size_t)nzl * N * H;
+    float2 *spec_main = p->spec, *spec_side = p->spec + main_n;
+    const int grid = p->sm_count * 8;
+    auto copy2 = k_slab_peer_copy<PULL, 2>;
+    auto copy1 = k_slab_peer_copy<PULL, 1>;
+    PM_LAUNCH(copy2, grid, 256, 0, st, spec_main, pp, main_n / C * c, p->rank, nzl, N,
+              H, c * hc, hc, nyl);
+    if (c == 0)
+        PM_LAUNCH(copy1, p->sm_count * 2, 256, 0, st, spec_side, pp, main_n, p->rank, nzl,
+                  N, 1, 0, 1, nyl);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// Flag words: rank r's word [slot][s] is written by rank s.  Signal: one thread per peer stores this
+// step's epoch (the kernel boundary before it has already made the pushed data visible; the fence
+// orders it for the system scope anyway).  Wait: one thread per peer polls its word; after ~2 s it
+// gives up and counts a timeout instead of hanging the device.
+struct PeerFlagPtrs {
+    uint32_t *p[PM_PEER_MAX];
+};
+
+__global__ void k_peer_signal_impl(PeerFlagPtrs peers, int nranks, int rank, int slot, uint32_t epoch)
+{
+    const int s = threadIdx.x;
+    if (s >= nranks) return;
+    __threadfence_system();
+    volatile uint32_t *w = peers.p[s] + (size_t)slot * PM_PEER_MAX + rank;
+    *w = epoch;
+}
+
+__global__ void k_peer_wait_impl(uint32_t *flags, int nranks, int slot, uint32_t epoch)
+{
+    const int s = threadIdx.x;
+    if (s < nranks) {
+        const volatile uint32_t *w = flags + (size_t)slot * PM_PEER_MAX + s;
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(*w - epoch) < 0) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 2000000000ull) {
+                atomicAdd(flags + (size_t)PM_PEER_SLOTS * PM_PEER_MAX, 1u);
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+template <int N>
+int slab_y_only(pm_plan *p, int c, int C, bool fwd, cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const int nzl = p->nzl, hc = H / C;
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
+    ColArgs ca = slab_args<N>(p);
+    ca.tpr = hc / kColsCN<N>;
+    ca.kt0 = c * ca.tpr;
+    if (fwd) {
+        auto cols_fwd = k_fft_cols<N, COL_FWD>;
+        PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        PM_LAUNCH(cols_fwd, nzl * ca.tpr, kThrC<N>, smem_cols, st, ca);
+    } else {
+        auto cols_inv = k_fft_cols<N, COL_INV>;
+        PM_CUDA(cudaFuncSetAttribute(cols_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        PM_LAUNCH(cols_inv, nzl * ca.tpr, kThrC<N>, smem_cols, st, ca);
+    }
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
 // ---- matter power spectrum (the reference has no estimator) --------------------
 // After rows R2C + y forward + z forward the array holds rho_k at (zpos, ypos, kx) with zpos/ypos
 // digit-reversed.  Each mode adds w*|rho_k|^2 to the spherical bin round(|k|) (integer frequency
@@ -1295,6 +1412,35 @@ int pm_k_fft_slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main
 int pm_k_fft_slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
 {
     PM_FFT_DISPATCH(slab_rows_inv, p, phi, st);
+}
+
+int pm_k_fft_slab_y_fwd(pm_plan *p, int c, int C, cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_y_only, p, c, C, true, st);
+}
+
+int pm_k_fft_slab_y_inv(pm_plan *p, int c, int C, cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_y_only, p, c, C, false, st);
+}
+
+int pm_k_fft_slab_push(pm_plan *p, int c, int C, cudaStream_t st) { return slab_peer_copy<false>(p, c, C, st); }
+int pm_k_fft_slab_pull(pm_plan *p, int c, int C, cudaStream_t st) { return slab_peer_copy<true>(p, c, C, st); }
+
+int pm_k_peer_signal(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st)
+{
+    PeerFlagPtrs pf;
+    for (int s = 0; s < PM_PEER_MAX; ++s) pf.p[s] = s < p->nranks ? p->peer_flag_of[s] : nullptr;
+    PM_LAUNCH(k_peer_signal_impl, 1, 32, 0, st, pf, p->nranks, p->rank, slot, epoch);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+int pm_k_peer_wait(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st)
+{
+    PM_LAUNCH(k_peer_wait_impl, 1, 32, 0, st, p->peer_flags, p->nranks, slot, epoch);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
 }
 
 int pm_fft_cols_per_tile(int nc) { return nc >= 1024 ? 8 : PM_FFT_COLS; }

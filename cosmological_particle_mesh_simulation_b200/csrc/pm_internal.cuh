@@ -38,6 +38,9 @@ extern int g_pm_last_cufft;
         }                                               \
     } while (0)
 
+#define PM_PEER_MAX 16
+#define PM_PEER_SLOTS 16
+
 struct pm_plan {
     int nc;           // N_CELLS
     int64_t np_cap;   // particle capacity
@@ -113,6 +116,17 @@ struct pm_plan {
     float *mig_send, *mig_recv;  // [nranks*leave_cap][7] packed (x,y,z,vx,vy,vz,id) records
     int64_t rtotal;         // entries of the current buffer set incl. dead (left) and arrived ones
 
+    // peer-memory transposes of the distributed FFT (pm_slab_peer_*): the pack kernel stores its
+    // blocks straight into the peers' z-pass arrays and the unpack kernel loads from them, over
+    // NVLink (CUDA IPC mappings between the one-process-per-GPU ranks, plain pointers between the
+    // plans of a single-process rank loop); flag words replace the collective as the barrier
+    uint32_t *peer_flags;                   // [PM_PEER_SLOTS + 1][PM_PEER_MAX] in ws; last row [0] = timeouts
+    float2 *peer_recv[PM_PEER_MAX];         // rank s's tbuf[1] as seen from this device
+    uint32_t *peer_flag_of[PM_PEER_MAX];    // rank s's peer_flags
+    void *peer_ipc[PM_PEER_MAX];            // cudaIpcOpenMemHandle mappings to close
+    uint32_t peer_epoch_sig[PM_PEER_SLOTS], peer_epoch_wait[PM_PEER_SLOTS];
+    int peers_set;                          // how many of the nranks entries are filled in
+
     // optional per-stage timing of pm_step (pm_plan_profile_begin/read)
     cudaEvent_t *prof_ev;   // prof_cap * (PM_NUM_STAGES + 1) events
     int prof_cap, prof_n;
@@ -170,6 +184,13 @@ int pm_k_fft_slab_z_chunk(pm_plan *p, int c, int C, float2 *main_t_c, float2 *si
 int pm_k_fft_slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main_c,
                                const float2 *back_side, cudaStream_t st);
 int pm_k_fft_slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st);
+// peer-memory variant: y pass / push into the peers' z-pass arrays / pull from them / y inverse
+int pm_k_fft_slab_y_fwd(pm_plan *p, int c, int C, cudaStream_t st);
+int pm_k_fft_slab_push(pm_plan *p, int c, int C, cudaStream_t st);
+int pm_k_fft_slab_pull(pm_plan *p, int c, int C, cudaStream_t st);
+int pm_k_fft_slab_y_inv(pm_plan *p, int c, int C, cudaStream_t st);
+int pm_k_peer_signal(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st);
+int pm_k_peer_wait(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st);
 int pm_fft_cols_per_tile(int nc);
 int pm_k_power_spectrum(pm_plan *p, const float *rho, int nbins, double *psum, double *pcnt,
                         cudaStream_t st);

@@ -25,6 +25,7 @@
 //        exchange  all-to-all-v MIG_SEND -> MIG_RECV (7 floats per particle)
 //   pm_slab_migrate_unpack  append the arrivals and their keys
 #include "pm_internal.cuh"
+#include <cstring>
 
 namespace {
 struct Guard {
@@ -72,7 +73,9 @@ int pm_slab_buffer(pm_plan *p, int which, void **ptr, size_t *bytes)
     switch (which) {
         case PM_BUF_RHO: *ptr = p->mesh; *bytes = pb * p->nzl; break;
         case PM_BUF_RHO_GHOST_SEND: *ptr = p->mesh + plane * p->nzl; *bytes = pb; break;
-        case PM_BUF_RHO_GHOST_RECV: *ptr = p->tbuf[1]; *bytes = pb; break;
+        // the phi buffer is dead between the gather and the inverse transform; the z-pass array
+        // tbuf[1] cannot be used here because peers may already be storing into it (pm_slab_fft_push)
+        case PM_BUF_RHO_GHOST_RECV: *ptr = p->mesh2; *bytes = pb; break;
         case PM_BUF_FFT_SEND_MAIN: *ptr = p->tbuf[0]; *bytes = main_n * sizeof(float2); break;
         case PM_BUF_FFT_SEND_SIDE: *ptr = p->tbuf[0] + main_n; *bytes = side_n * sizeof(float2); break;
         case PM_BUF_FFT_RECV_MAIN: *ptr = p->tbuf[1]; *bytes = main_n * sizeof(float2); break;
@@ -85,6 +88,7 @@ int pm_slab_buffer(pm_plan *p, int which, void **ptr, size_t *bytes)
         case PM_BUF_MIG_SEND: *ptr = p->mig_send; *bytes = (size_t)p->nranks * p->leave_cap * 28; break;
         case PM_BUF_MIG_RECV: *ptr = p->mig_recv; *bytes = (size_t)p->nranks * p->leave_cap * 28; break;
         case PM_BUF_LEAVE_COUNTS: *ptr = p->leave_cnt; *bytes = (size_t)p->nranks * 4; break;
+        case PM_BUF_PEER_FLAGS: *ptr = p->peer_flags; *bytes = (size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4; break;
         default: return PM_ERR_INVALID;
     }
     return PM_OK;
@@ -125,7 +129,7 @@ int pm_slab_deposit(pm_plan *p, double mass, pm_stream_t stream)
 int pm_slab_ghost_add(pm_plan *p, pm_stream_t stream)
 {
     PM_SLAB_ENTER(true);
-    return pm_k_ghost_add(p, p->mesh, reinterpret_cast<const float *>(p->tbuf[1]), st);
+    return pm_k_ghost_add(p, p->mesh, p->mesh2, st);
 }
 
 // Chunk c of C: byte ranges inside FFT_SEND_MAIN / FFT_RECV_MAIN are [c, c+1) * bytes / C.
@@ -166,6 +170,136 @@ int pm_slab_fft_rows_inverse(pm_plan *p, pm_stream_t stream)
 {
     PM_SLAB_ENTER(true);
     return pm_k_fft_slab_rows_inv(p, p->mesh2 + (size_t)p->nc * p->nc, st);
+}
+
+// ---- peer-memory transposes ------------------------------------------------------------------
+// Every rank publishes where its z-pass array (tbuf[1]) and its flag words live; after that
+//   pm_slab_fft_y_forward_local(c)   y pass of chunk c, left in the local spectrum
+//   pm_slab_fft_push(c)              local spectrum chunk -> block [rank] of EVERY peer's z-pass array
+//   pm_slab_peer_signal(c)           "my blocks of chunk c have landed" -> flag word on every peer
+//   pm_slab_peer_wait(c)             spin until all P flags of chunk c carry this step's epoch
+//   pm_slab_fft_z(c)                 unchanged
+//   pm_slab_peer_signal(SLOTS/2+c)   "my z pass of chunk c is done"
+//   pm_slab_peer_wait(SLOTS/2+c); pm_slab_fft_pull(c)   every peer's block [rank] -> local spectrum
+//   pm_slab_fft_y_inverse_local(c)
+// No staging buffer, no collective: the all-to-all is the stores / loads of the two copy kernels.
+int pm_slab_peer_export(pm_plan *p, void *handle64, uint64_t *recv_offset, uint64_t *flags_offset)
+{
+    if (!p || !p->slab || !handle64 || !recv_offset || !flags_offset) return PM_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    Guard g;
+    int rc = g.enter(p->device);
+    if (rc != PM_OK) return rc;
+    cudaIpcMemHandle_t h;
+    PM_CUDA(cudaIpcGetMemHandle(&h, p->ws));
+    memcpy(handle64, &h, 64);
+    *recv_offset = (uint64_t)((char *)p->tbuf[1] - p->ws);
+    *flags_offset = (uint64_t)((char *)p->peer_flags - p->ws);
+    return PM_OK;
+}
+
+static int peer_store(pm_plan *p, int peer, void *recv, void *flags)
+{
+    if (!p->peer_recv[peer]) ++p->peers_set;
+    p->peer_recv[peer] = (float2 *)recv;
+    p->peer_flag_of[peer] = (uint32_t *)flags;
+    return PM_OK;
+}
+
+int pm_slab_peer_import(pm_plan *p, int peer, const void *handle64, uint64_t recv_offset,
+                        uint64_t flags_offset)
+{
+    if (!p || !p->slab || peer < 0 || peer >= p->nranks || peer >= PM_PEER_MAX) return PM_ERR_INVALID;
+    if (peer == p->rank) return peer_store(p, peer, p->tbuf[1], p->peer_flags);
+    if (!handle64) return PM_ERR_INVALID;
+    Guard g;
+    int rc = g.enter(p->device);
+    if (rc != PM_OK) return rc;
+    if (p->peer_ipc[peer]) {
+        cudaIpcCloseMemHandle(p->peer_ipc[peer]);
+        p->peer_ipc[peer] = nullptr;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *base = nullptr;
+    PM_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_ipc[peer] = base;
+    return peer_store(p, peer, (char *)base + recv_offset, (char *)base + flags_offset);
+}
+
+// Plans of several ranks inside ONE process (single-GPU rank loop of the tests, or one process
+// driving several GPUs with peer access enabled): plain device pointers.
+int pm_slab_peer_set(pm_plan *p, int peer, void *recv_main, void *flags)
+{
+    if (!p || !p->slab || peer < 0 || peer >= p->nranks || peer >= PM_PEER_MAX || !recv_main || !flags)
+        return PM_ERR_INVALID;
+    return peer_store(p, peer, recv_main, flags);
+}
+
+int pm_slab_peer_signal(pm_plan *p, int slot, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(slot >= 0 && slot < PM_PEER_SLOTS && p->peers_set == p->nranks);
+    return pm_k_peer_signal(p, slot, ++p->peer_epoch_sig[slot], st);
+}
+
+int pm_slab_peer_wait(pm_plan *p, int slot, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(slot >= 0 && slot < PM_PEER_SLOTS && p->peers_set == p->nranks);
+    return pm_k_peer_wait(p, slot, ++p->peer_epoch_wait[slot], st);
+}
+
+// Unmap the other ranks' workspaces (every rank does this, then a barrier, before any plan is
+// destroyed: freeing memory that another process still has mapped is undefined).
+int pm_slab_peer_release(pm_plan *p)
+{
+    if (!p || !p->slab) return PM_ERR_INVALID;
+    Guard g;
+    int rc = g.enter(p->device);
+    if (rc != PM_OK) return rc;
+    cudaStreamSynchronize(0);
+    for (int s = 0; s < PM_PEER_MAX; ++s) {
+        if (p->peer_ipc[s]) cudaIpcCloseMemHandle(p->peer_ipc[s]);
+        p->peer_ipc[s] = nullptr;
+        p->peer_recv[s] = nullptr;
+        p->peer_flag_of[s] = nullptr;
+    }
+    p->peers_set = 0;
+    return PM_OK;
+}
+
+// Number of pm_slab_peer_wait calls that gave up (2 s without the peers' flags): 0 on a healthy run.
+int pm_slab_peer_timeouts(pm_plan *p, uint32_t *timeouts)
+{
+    if (!p || !p->slab || !timeouts) return PM_ERR_INVALID;
+    Guard g;
+    int rc = g.enter(p->device);
+    if (rc != PM_OK) return rc;
+    PM_CUDA(cudaMemcpy(timeouts, p->peer_flags + (size_t)PM_PEER_SLOTS * PM_PEER_MAX, 4, cudaMemcpyDeviceToHost));
+    return PM_OK;
+}
+
+int pm_slab_fft_y_forward_local(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C));
+    return pm_k_fft_slab_y_fwd(p, c, C, st);
+}
+
+int pm_slab_fft_push(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C) && p->peers_set == p->nranks);
+    return pm_k_fft_slab_push(p, c, C, st);
+}
+
+int pm_slab_fft_pull(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C) && p->peers_set == p->nranks);
+    return pm_k_fft_slab_pull(p, c, C, st);
+}
+
+int pm_slab_fft_y_inverse_local(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C));
+    return pm_k_fft_slab_y_inv(p, c, C, st);
 }
 
 int pm_slab_gather(pm_plan *p, double a, double f_a1, double da, pm_stream_t stream)

@@ -30,7 +30,8 @@ except ImportError:  # flat layout
 
 BUF = dict(RHO=0, RHO_GHOST_SEND=1, RHO_GHOST_RECV=2, FFT_SEND_MAIN=3, FFT_SEND_SIDE=4,
            FFT_RECV_MAIN=5, FFT_RECV_SIDE=6, PHI=7, PHI_LO_SEND=8, PHI_HI_SEND=9, PHI_LO_RECV=10,
-           PHI_HI_RECV=11, MIG_SEND=12, MIG_RECV=13, LEAVE_COUNTS=14)
+           PHI_HI_RECV=11, MIG_SEND=12, MIG_RECV=13, LEAVE_COUNTS=14, PEER_FLAGS=15)
+PEER_SLOTS_HALF = 8     # flag slots 0..7: "chunk c pushed", 8..15: "z pass of chunk c done"
 
 
 class _RawCudaBuffer:
@@ -77,7 +78,9 @@ class SlabRank:
                       PHI=(torch.float32, (nzl, n, n)), PHI_LO_SEND=(torch.float32, (2, n, n)),
                       PHI_HI_SEND=(torch.float32, (n, n)), PHI_LO_RECV=(torch.float32, (n, n)),
                       PHI_HI_RECV=(torch.float32, (2, n, n)), MIG_SEND=(torch.float32, (-1, 7)),
-                      MIG_RECV=(torch.float32, (-1, 7)), LEAVE_COUNTS=(torch.int32, (P,)))
+                      MIG_RECV=(torch.float32, (-1, 7)), LEAVE_COUNTS=(torch.int32, (P,)),
+                      PEER_FLAGS=(torch.int32, (-1, 16)))
+        self.peers_ready = False
         for name, which in BUF.items():
             ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
             rt.check(rt.lib().pm_slab_buffer(self.handle, which, ctypes.byref(ptr), ctypes.byref(nbytes)),
@@ -141,6 +144,56 @@ class SlabRank:
     def fft_rows_inverse(self):
         self._call("pm_slab_fft_rows_inverse")
 
+    # -- peer-memory transposes (pm_slab_peer_* / pm_slab_fft_push / pm_slab_fft_pull) -------------
+    def peer_export(self):
+        """(64-byte CUDA IPC handle of the plan's workspace, offset of the z-pass array, offset of
+        the flag words) -- what the other ranks need to map this rank's buffers."""
+        h = (ctypes.c_ubyte * 64)()
+        o1, o2 = ctypes.c_uint64(), ctypes.c_uint64()
+        rt.check(rt.lib().pm_slab_peer_export(self.handle, h, ctypes.byref(o1), ctypes.byref(o2)),
+                 "pm_slab_peer_export")
+        return bytes(h), int(o1.value), int(o2.value)
+
+    def peer_import(self, peer, handle, recv_offset, flags_offset):
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_slab_peer_import(self.handle, int(peer), buf, int(recv_offset), int(flags_offset)),
+                     f"pm_slab_peer_import(peer={peer})")
+
+    def peer_set(self, peer, recv_ptr, flags_ptr):
+        rt.check(rt.lib().pm_slab_peer_set(self.handle, int(peer), ctypes.c_void_p(recv_ptr),
+                                           ctypes.c_void_p(flags_ptr)), "pm_slab_peer_set")
+
+    def peer_timeouts(self):
+        n = ctypes.c_uint32()
+        rt.check(rt.lib().pm_slab_peer_timeouts(self.handle, ctypes.byref(n)), "pm_slab_peer_timeouts")
+        return int(n.value)
+
+    def peer_release(self):
+        if getattr(self, "handle", None):
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                rt.check(rt.lib().pm_slab_peer_release(self.handle), "pm_slab_peer_release")
+        self.peers_ready = False
+
+    def signal(self, slot):
+        self._call("pm_slab_peer_signal", int(slot))
+
+    def wait(self, slot):
+        self._call("pm_slab_peer_wait", int(slot))
+
+    def fft_y_forward_local(self, c, C):
+        self._call("pm_slab_fft_y_forward_local", int(c), int(C))
+
+    def fft_push(self, c, C):
+        self._call("pm_slab_fft_push", int(c), int(C))
+
+    def fft_pull(self, c, C):
+        self._call("pm_slab_fft_pull", int(c), int(C))
+
+    def fft_y_inverse_local(self, c, C):
+        self._call("pm_slab_fft_y_inverse_local", int(c), int(C))
+
     def chunk(self, name, c, C):
         """Chunk c of C of an FFT_*_MAIN buffer as a (P, .) view (one row per peer rank)."""
         flat = self.buf[name].view(-1)
@@ -184,6 +237,12 @@ class LocalComm:
         P = self.nranks
         return [[int(counts[src][dst]) for src in range(P)] for dst in range(P)]
 
+    def exchange_count_tensors(self, counts):
+        """counts: per local rank an integer tensor [P] (leavers per destination).  Returns
+        (send_counts, recv_counts) as lists of Python ints per local rank."""
+        send = [c.tolist() for c in counts]
+        return send, self.exchange_counts(send)
+
     def all_to_all_v(self, send, send_counts, recv, recv_counts):
         P = self.nranks
         off_s = [np.concatenate([[0], np.cumsum(c)]) for c in send_counts]
@@ -197,7 +256,10 @@ class LocalComm:
 
 
 class DistComm:
-    """One rank per process over torch.distributed (NCCL on GPUs, gloo on CPU for the tests)."""
+    """One rank per process over torch.distributed (NCCL on GPUs, gloo on CPU for the tests).
+    With a backend that cannot move CUDA tensors (gloo) the exchanges are staged through host
+    memory -- slow, but it lets two processes SHARE one GPU, which is how the CUDA IPC mappings of
+    the peer transport are tested on a one-GPU box (tests/test_slab_gpu.py)."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -210,11 +272,20 @@ class DistComm:
         self._count_device = "cuda" if nccl else "cpu"
         # collectives of the FFT pipeline run here so they overlap the compute stream
         self.side_stream = torch.cuda.Stream() if (nccl and self.nranks > 1) else None
+        self._staged = not nccl
+
+    def _host(self, t):
+        return t.cpu() if (self._staged and t.is_cuda) else t
 
     def shift(self, send, recv, direction):
         P, r, dist = self.nranks, self.rank, self.dist
         if P == 1:
             recv[0].copy_(send[0])
+            return
+        if self._staged and send[0].is_cuda:
+            hs, hr = send[0].cpu(), torch.empty(recv[0].shape, dtype=recv[0].dtype)
+            self.shift([hs], [hr], direction)
+            recv[0].copy_(hr)
             return
         ops = [dist.P2POp(dist.isend, send[0], (r + direction) % P, self.group),
                dist.P2POp(dist.irecv, recv[0], (r - direction) % P, self.group)]
@@ -224,6 +295,11 @@ class DistComm:
     def all_to_all(self, send, recv):
         if self.nranks == 1:
             recv[0].copy_(send[0])
+            return
+        if self._staged and send[0].is_cuda:
+            hs, hr = send[0].cpu(), torch.empty(recv[0].shape, dtype=recv[0].dtype)
+            self.dist.all_to_all_single(hr.view(-1), hs.view(-1), group=self.group)
+            recv[0].copy_(hr)
             return
         self.dist.all_to_all_single(recv[0].view(-1), send[0].view(-1), group=self.group)
 
@@ -238,6 +314,19 @@ class DistComm:
 
     _count_device = "cpu"
 
+    def exchange_count_tensors(self, counts):
+        """As LocalComm.exchange_count_tensors, with ONE device->host read per step: the counts
+        are exchanged on the device (all-to-all of P integers) and both vectors come back together."""
+        c = self._host(counts[0])
+        if self.nranks == 1:
+            v = c.tolist()
+            return [v], [v]
+        both = torch.empty((2, self.nranks), dtype=c.dtype, device=c.device)
+        both[0].copy_(c)
+        self.dist.all_to_all_single(both[1], both[0], group=self.group)
+        v = both.tolist()
+        return [v[0]], [v[1]]
+
     def all_to_all_v(self, send, send_counts, recv, recv_counts):
         sc, rc = [int(x) for x in send_counts[0]], [int(x) for x in recv_counts[0]]
         ns, nr = sum(sc), sum(rc)
@@ -245,9 +334,77 @@ class DistComm:
             recv[0][:nr].copy_(send[0][:ns])
             return
         width = send[0].shape[1]
+        if self._staged and send[0].is_cuda:
+            hs, hr = send[0][:ns].cpu(), torch.empty((nr, width), dtype=recv[0].dtype)
+            self.dist.all_to_all_single(hr.view(-1), hs.view(-1), output_split_sizes=[c * width for c in rc],
+                                        input_split_sizes=[c * width for c in sc], group=self.group)
+            recv[0][:nr].copy_(hr)
+            return
         self.dist.all_to_all_single(recv[0][:nr].reshape(-1), send[0][:ns].reshape(-1),
                                     output_split_sizes=[c * width for c in rc],
                                     input_split_sizes=[c * width for c in sc], group=self.group)
+
+
+def setup_peers(ranks, comm):
+    """Give every rank the addresses of everybody's z-pass array and flag words so the FFT
+    transposes can go through peer memory (slab_step(transport="peer")).  LocalComm: plain pointers.
+    DistComm: CUDA IPC handles exchanged with all_gather_object, then a flag round trip through the
+    mapped memory as a handshake; all ranks agree on the outcome.  Returns True when the peer path is
+    usable (and marks the ranks), False otherwise -- the NCCL path needs no set-up."""
+    P = comm.nranks
+    if P > 16:
+        return False
+    if isinstance(comm, LocalComm):
+        for r in ranks:
+            for s in ranks:
+                r.peer_set(s.rank, s.buf["FFT_RECV_MAIN"].data_ptr(), s.buf["PEER_FLAGS"].data_ptr())
+        for r in ranks:
+            r.signal(PEER_SLOTS_HALF - 1)
+        for r in ranks:
+            r.wait(PEER_SLOTS_HALF - 1)
+        torch.cuda.synchronize()
+        ok = all(r.peer_timeouts() == 0 for r in ranks)
+        for r in ranks:
+            r.peers_ready = ok
+        return ok
+    dist, r = comm.dist, ranks[0]
+    ok = 1
+    try:
+        mine = r.peer_export()
+    except Exception:
+        mine, ok = None, 0
+    table = [None] * P
+    dist.all_gather_object(table, mine, group=comm.group)
+    if ok and all(t is not None for t in table):
+        try:
+            for s, (h, o1, o2) in enumerate(table):
+                r.peer_import(s, None if s == r.rank else h, o1, o2)
+        except Exception:
+            ok = 0
+    else:
+        ok = 0
+    dev = r.buf["RHO"].device if dist.get_backend(comm.group) == "nccl" else "cpu"
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
+    if int(flag.item()) == 0:
+        return False
+    # handshake through the mapped memory (slot 7 is never used by the pipeline: at most 4 chunks)
+    r.signal(PEER_SLOTS_HALF - 1)
+    r.wait(PEER_SLOTS_HALF - 1)
+    torch.cuda.synchronize()
+    flag = torch.tensor([1 if r.peer_timeouts() == 0 else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
+    r.peers_ready = bool(int(flag.item()))
+    return r.peers_ready
+
+
+def release_peers(ranks, comm):
+    """Unmap the other ranks' buffers on every rank, then a barrier: call before closing the ranks
+    of a DistComm run (memory must not be freed while another process still has it mapped)."""
+    for r in ranks:
+        r.peer_release()
+    if isinstance(comm, DistComm) and comm.nranks > 1:
+        comm.dist.barrier(group=comm.group)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -294,11 +451,13 @@ def default_chunks(n_cells, nranks=1):
     return 1
 
 
-def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None):
+def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, transport=None):
     """One body of the loop src/pmesh.py:60-61 across the slabs.  `ranks`: the SlabRank objects
     of comm.local_ranks (one for DistComm, all P for LocalComm).  The distributed FFT runs as a
-    pipeline of `chunks` kx chunks: with DistComm on GPUs the all-to-alls go to a second stream
-    and overlap the y and z passes of the neighbouring chunks."""
+    pipeline of `chunks` kx chunks: with DistComm on GPUs the transposes go to a second stream
+    and overlap the y and z passes of the neighbouring chunks.  transport: "peer" = the copy
+    kernels store into / load from the other ranks' buffers over NVLink (needs setup_peers),
+    "nccl" = pack -> all-to-all -> unpack; default: "peer" when the ranks are set up for it."""
     cfg = cfg or rt.config()
     if timer:
         timer.begin_step()
@@ -341,10 +500,56 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None):
         e.record(main)
         return e
 
+    if transport is None:
+        transport = "peer" if all(r.peers_ready for r in ranks) else "nccl"
+    if transport == "peer" and not all(r.peers_ready for r in ranks):
+        raise RuntimeError("transport='peer' needs slab.setup_peers(ranks, comm) first")
+    if transport == "peer" and C > PEER_SLOTS_HALF - 1:
+        raise ValueError("at most %d chunks with the peer transport" % (PEER_SLOTS_HALF - 1))
+
     for r in ranks:
         r.fft_rows_forward()
     arrived = []
-    for c in range(C):
+    for c in range(C if transport == "peer" else 0):
+        for r in ranks:
+            r.fft_y_forward_local(c, C)
+
+        def push(c=c):
+            for r in ranks:
+                r.fft_push(c, C)
+            for r in ranks:
+                r.signal(c)
+        arrived.append(on_comm(ev(), push))
+    zdone = []
+    for c in range(C if transport == "peer" else 0):
+        if arrived[c] is not None:
+            main.wait_event(arrived[c])       # my own block is in place
+        for r in ranks:
+            r.wait(c)                          # ... and so is everybody else's
+        for r in ranks:
+            r.fft_z(c, C, a, cfg.OMEGA_M0)
+        for r in ranks:
+            r.signal(PEER_SLOTS_HALF + c)      # "my z pass of chunk c is done: pull your planes"
+        zdone.append(ev())
+    pulled = []
+    for c in range(C if transport == "peer" else 0):
+        def pull(c=c):
+            for r in ranks:
+                r.wait(PEER_SLOTS_HALF + c)
+            for r in ranks:
+                r.fft_pull(c, C)
+        pulled.append(on_comm(zdone[c], pull))
+    for c in range(C if transport == "peer" else 0):
+        if pulled[c] is not None:
+            main.wait_event(pulled[c])
+        for r in ranks:
+            r.fft_y_inverse_local(c, C)
+    if transport == "peer":
+        C_nccl = 0
+    else:
+        C_nccl = C
+    arrived = []
+    for c in range(C_nccl):
         for r in ranks:
             r.fft_y_forward(c, C)
 
@@ -354,7 +559,7 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None):
                 comm.all_to_all(B("FFT_SEND_SIDE"), B("FFT_RECV_SIDE"))
         arrived.append(on_comm(ev(), fwd))
     returned = []
-    for c in range(C):
+    for c in range(C_nccl):
         if arrived[c] is not None:
             main.wait_event(arrived[c])
         for r in ranks:
@@ -365,7 +570,7 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None):
             if c == 0:
                 comm.all_to_all(B("FFT_RECV_SIDE"), B("FFT_SEND_SIDE"))
         returned.append(on_comm(ev(), bwd))
-    for c in range(C):
+    for c in range(C_nccl):
         if returned[c] is not None:
             main.wait_event(returned[c])
         for r in ranks:
@@ -380,9 +585,9 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None):
     for r in ranks:
         r.gather(a, f_a1, da)
     mark("gather")
-    # migration: one small device->host read per step (the leave counts size the messages)
-    send_counts = [r.buf["LEAVE_COUNTS"].tolist() for r in ranks]
-    recv_counts = comm.exchange_counts(send_counts)
+    # migration: the leave counts are exchanged on the device; one small device->host read per
+    # step brings both count vectors back (they size the messages)
+    send_counts, recv_counts = comm.exchange_count_tensors([r.buf["LEAVE_COUNTS"] for r in ranks])
     for r, sc in zip(ranks, send_counts):
         r.migrate_pack(sc)
     comm.all_to_all_v(B("MIG_SEND"), send_counts, B("MIG_RECV"), recv_counts)

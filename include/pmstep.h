@@ -229,6 +229,7 @@ PM_API int64_t pm_particles_count(const pm_plan *plan);
 #define PM_BUF_MIG_SEND 12       /* float[.][7]          (x,y,z,vx,vy,vz,id) of leavers, by dest   */
 #define PM_BUF_MIG_RECV 13       /* float[.][7]          arrivals                                  */
 #define PM_BUF_LEAVE_COUNTS 14   /* uint32[P]            leavers per destination (after gather)    */
+#define PM_BUF_PEER_FLAGS 15     /* uint32[17][16]       flag words of the peer-memory transposes  */
 PM_API int pm_plan_create_slab(pm_plan **plan, int n_cells, int64_t np_capacity, int device, int rank,
                                int nranks);
 PM_API int pm_slab_buffer(pm_plan *plan, int which, void **ptr, size_t *bytes);
@@ -248,6 +249,27 @@ PM_API int pm_slab_fft_z(pm_plan *plan, int chunk, int nchunks, double a, double
                          pm_stream_t stream);
 PM_API int pm_slab_fft_y_inverse(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
 PM_API int pm_slab_fft_rows_inverse(pm_plan *plan, pm_stream_t stream);
+/* Peer-memory transposes: instead of pack -> NCCL all-to-all -> unpack, the copy kernels store into
+ * (push, forward leg) and load from (pull, way back) the z-pass arrays of the other ranks over
+ * NVLink, and flag words replace the collective as the barrier.  Each rank publishes its workspace
+ * once (pm_slab_peer_export -> 64-byte CUDA IPC handle + two offsets, exchanged by the caller) and
+ * maps everybody else's (pm_slab_peer_import; its own entry needs no handle); plans that live in one
+ * process use pm_slab_peer_set with the addresses of PM_BUF_FFT_RECV_MAIN / PM_BUF_PEER_FLAGS.
+ * Slots 0..7: "chunk c pushed", 8..15: "z pass of chunk c done".  signal/wait pair up by call
+ * count, so every rank must make the same calls every step.  A wait gives up after 2 s and counts
+ * a timeout (pm_slab_peer_timeouts) instead of hanging the device.  Order of calls: csrc/pm_slab.cu. */
+PM_API int pm_slab_peer_export(pm_plan *plan, void *handle64, uint64_t *recv_offset, uint64_t *flags_offset);
+PM_API int pm_slab_peer_import(pm_plan *plan, int peer, const void *handle64, uint64_t recv_offset,
+                               uint64_t flags_offset);
+PM_API int pm_slab_peer_set(pm_plan *plan, int peer, void *recv_main, void *flags);
+PM_API int pm_slab_peer_signal(pm_plan *plan, int slot, pm_stream_t stream);
+PM_API int pm_slab_peer_wait(pm_plan *plan, int slot, pm_stream_t stream);
+PM_API int pm_slab_peer_timeouts(pm_plan *plan, uint32_t *timeouts);
+PM_API int pm_slab_peer_release(pm_plan *plan);   /* unmap the peers (all ranks, then a barrier, then destroy) */
+PM_API int pm_slab_fft_y_forward_local(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+PM_API int pm_slab_fft_push(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+PM_API int pm_slab_fft_pull(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+PM_API int pm_slab_fft_y_inverse_local(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
 PM_API int pm_slab_gather(pm_plan *plan, double a, double f_a1, double da, pm_stream_t stream);
 PM_API int pm_slab_migrate_pack(pm_plan *plan, const int64_t *counts_h, pm_stream_t stream);
 PM_API int pm_slab_migrate_unpack(pm_plan *plan, int64_t n_arrive, int64_t n_leave, pm_stream_t stream);

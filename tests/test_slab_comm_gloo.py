@@ -35,6 +35,10 @@ x = torch.empty(4, 4); comm.shift([planes[r]], [x], +1); assert torch.equal(x, u
 x = torch.empty(4, 4); comm.shift([planes[r]], [x], -1); assert torch.equal(x, dn[r])
 y = torch.empty(P, 6); comm.all_to_all([chunks[r]], [y]); assert torch.equal(y, a2a[r])
 c = comm.exchange_counts([counts[r]]); assert c[0] == rc[r], (c, rc)
+sc2, rc2 = comm.exchange_count_tensors([torch.tensor(counts[r], dtype=torch.int32)])   # one read per step
+assert sc2[0] == list(counts[r]) and rc2[0] == rc[r], (sc2, rc2)
+ls, lr = loc.exchange_count_tensors([torch.tensor(c_, dtype=torch.int32) for c_ in counts])
+assert ls == [list(c_) for c_ in counts] and lr == rc
 z = torch.zeros(16, 7); comm.all_to_all_v([recs[r]], [counts[r]], [z], c); assert torch.equal(z, rv[r])
 assert slab.slab_of_particles(torch.tensor([0.0, 15.9, 16.0, 32.0]), 32, 2).tolist() == [0, 0, 1, 0]
 dist.barrier(); dist.destroy_process_group()

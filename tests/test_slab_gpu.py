@@ -45,9 +45,10 @@ def test_particle_to_slab_assignment_bit_exact(pm):
     assert np.array_equal(want, (keys // (n * n)) // (n // P))  # same rule as the cell key
 
 
+@pytest.mark.parametrize("transport", ["nccl", "peer"])
 @pytest.mark.parametrize("P", [1, 2, 4])
 @pytest.mark.parametrize("n_parts,n_cells", [(32, 64), (64, 128)])
-def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells):
+def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells, transport):
     cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
     pm.set_config(cfg)
     if n_cells // P < 16:
@@ -65,6 +66,8 @@ def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells):
     comm = pm.slab.LocalComm(P)
     ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
     assert sum(r.count for r in ranks) == npart
+    if transport == "peer":      # transposes by stores into / loads from the other ranks' buffers
+        assert pm.slab.setup_peers(ranks, comm)
     ref_p, ref_v = pos.clone(), vel.clone()
     moved = 0
     a, da = 0.3, 0.0099
@@ -77,7 +80,7 @@ def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells):
             chunks = 2
         if chunks == 2 and (n_cells // 2 // 2) % 16:
             chunks = 1
-        pm.slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=chunks)
+        pm.slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=chunks, transport=transport)
         moved += sum(abs(x - r.count) for x, r in zip(before, ranks))
         assert sum(r.count for r in ranks) == npart            # nobody lost in migration
         rho = torch.cat([r.buf["RHO"] for r in ranks])          # density the step just used
@@ -93,8 +96,86 @@ def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells):
             assert bool((own == r.rank).all())
         a += da
     assert torch.isfinite(phi).all()
+    if transport == "peer":
+        assert all(r.peer_timeouts() == 0 for r in ranks)
     for r in ranks:
         r.close()
+
+
+def test_peer_and_nccl_transports_are_bit_identical(pm):
+    """The two transports move the same numbers: the whole state must agree bit for bit."""
+    n_parts, n_cells, P = 64, 128, 4
+    cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
+    pm.set_config(cfg)
+    pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=5, vel_rms=0.5)
+    outs = []
+    for transport in ("nccl", "peer"):
+        pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
+        comm = pm.slab.LocalComm(P)
+        ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
+        if transport == "peer":
+            assert pm.slab.setup_peers(ranks, comm)
+        for s in range(4):
+            pm.slab.slab_step(ranks, comm, 0.4 + 0.0099 * s, 0.0099, mass=8.0, cfg=cfg, chunks=(1, 2, 4, 2)[s],
+                              transport=transport)
+        phi = torch.cat([r.buf["PHI"] for r in ranks]).clone()
+        outs.append(pm.slab.collect(ranks, comm, pos.shape[1]) + (phi,))
+        for r in ranks:
+            r.close()
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+
+
+IPC_WORKER = r'''
+import os, sys, types, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import cosmological_particle_mesh_simulation_b200 as pm
+from oracle import oracle as O
+torch.cuda.set_device(0)                       # both processes share the one GPU
+dist.init_process_group("gloo")                # control plane only; data exchanges staged through the host
+n_parts, n_cells = 32, 64
+cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
+pm.set_config(cfg)
+pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=11, vel_rms=0.3)
+pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
+comm = pm.slab.DistComm()
+ranks = pm.slab.make_ranks(n_cells, pos, vel, comm, device=0)
+assert pm.slab.setup_peers(ranks, comm), "CUDA IPC mapping / flag handshake failed"
+ref_p, ref_v = pos.clone(), vel.clone()
+a, da = 0.3, 0.0099
+for s in range(3):
+    pm.step(ref_p, ref_v, a, da, mass=8.0)
+    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2, 1)[s], transport="peer")
+    a += da
+torch.cuda.synchronize()
+assert ranks[0].peer_timeouts() == 0
+p, v, ids = ranks[0].export()
+d = torch.remainder(p.double() - ref_p[:, ids.long()].double() + n_cells / 2, n_cells) - n_cells / 2
+ep = float(d.norm() / ref_p.double().norm()); ev = float((v.double() - ref_v[:, ids.long()].double()).norm() / ref_v.double().norm())
+assert ep <= 1e-6 and ev <= 1e-5, (ep, ev)
+tot = torch.tensor([ranks[0].count]); dist.all_reduce(tot)
+assert int(tot.item()) == pos.shape[1]
+pm.slab.release_peers(ranks, comm)
+for r in ranks: r.close()
+dist.barrier(); dist.destroy_process_group()
+sys.stdout.write("rank" + str(comm.rank) + "-ok %%.2e %%.2e\n" %% (ep, ev)); sys.stdout.flush()
+'''
+
+
+def test_peer_transport_through_cuda_ipc_two_processes_one_gpu(tmp_path):
+    """Two ranks = two processes on the SAME GPU: the z-pass arrays and flag words of the other rank
+    are reached through cudaIpcOpenMemHandle mappings exactly as between two GPUs of a box."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(IPC_WORKER % repo)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29547", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("-ok") == 2, out.stdout
 
 
 def test_slab_run_is_deterministic(pm):

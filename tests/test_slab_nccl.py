@@ -25,18 +25,25 @@ pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=11, vel_rms=0.3)
 pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
 comm = pm.slab.DistComm()
 ranks = pm.slab.make_ranks(n_cells, pos, vel, comm, device=local)
+peer_ok = pm.slab.setup_peers(ranks, comm)     # CUDA IPC over NVLink; the NCCL path needs no set-up
+assert peer_ok, "peer-memory transport could not be set up on this box"
 ref_p, ref_v = pos.clone(), vel.clone()
 a, da = 0.3, 0.0099
-for s in range(5):
+for s in range(6):
     pm.step(ref_p, ref_v, a, da, mass=8.0)
-    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg)
+    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2)[s %% 2],
+                      transport=("peer", "peer", "nccl")[s %% 3])
     a += da
+torch.cuda.synchronize()
+assert ranks[0].peer_timeouts() == 0
 got_p, got_v = pm.slab.collect(ranks, comm, pos.shape[1])
 d = torch.remainder(got_p.double() - ref_p.double() + n_cells / 2, n_cells) - n_cells / 2
 ep = float(d.norm() / ref_p.double().norm()); ev = float((got_v.double() - ref_v.double()).norm() / ref_v.double().norm())
 assert ep <= 1e-6 and ev <= 1e-5, (ep, ev)
 tot = torch.tensor([ranks[0].count], device="cuda"); dist.all_reduce(tot)
 assert int(tot.item()) == pos.shape[1]
+pm.slab.release_peers(ranks, comm)
+for r in ranks: r.close()
 dist.barrier(); dist.destroy_process_group()
 sys.stdout.write("rank" + str(comm.rank) + "-ok %%.2e %%.2e\n" %% (ep, ev)); sys.stdout.flush()
 '''
