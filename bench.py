@@ -326,11 +326,11 @@ def run_slab(args, rank, world, local_rank):
     # rebuilds its state and runs the NCCL all-to-all path instead -- and the JSON line says which.
     transport, transport_note = "nccl", ""
     if args.transport != "nccl":
-        transport = "peer" if slab.setup_peers(ranks, comm) else "nccl"
-        if transport != "peer":
+        transport = ("peer" if args.transport == "peer" else "fused") if slab.setup_peers(ranks, comm) else "nccl"
+        if transport == "nccl":
             transport_note = "peer-memory set-up failed; "
     warm_up(transport)
-    if transport == "peer":
+    if transport != "nccl":
         bad = torch.tensor([ranks[0].peer_timeouts()], dtype=torch.int64, device=f"cuda:{dev}")
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
         if int(bad.item()):
@@ -341,8 +341,8 @@ def run_slab(args, rank, world, local_rank):
             ranks, particles_desc = build_ranks()
             step_i = 0
             warm_up(transport)
-    if args.transport == "peer" and transport != "peer":
-        raise RuntimeError("--transport peer: " + transport_note)
+    if args.transport in ("peer", "fused") and transport != args.transport:
+        raise RuntimeError(f"--transport {args.transport}: " + transport_note)
     # sanity on the distributed state: total mass of the last deposit == Np * mass
     msum = ranks[0].buf["RHO"].sum(dtype=torch.float64).reshape(1)
     dist.all_reduce(msum)
@@ -426,9 +426,12 @@ def run_slab(args, rank, world, local_rank):
                        "particles": particles_desc,
                        "l2": "inputs larger than L2",
                        "parallelism": f"slab decomposition along z over {world} GPUs: NCCL send/recv ghost planes, "
-                                      + (f"FFT transposes by peer-memory stores/loads over NVLink (CUDA IPC, flag-word barriers), "
-                                         if transport == "peer" else "FFT transposes by NCCL all-to-all, ")
-                                      + f"pipelined in {chunks} kx chunks on a second stream, all-to-all-v particle migration",
+                                      + {"fused": "FFT transposes fused into the y passes (stores into / loads from the peers' "
+                                                  "z-pass arrays over NVLink, CUDA IPC, flag-word barriers), ",
+                                         "peer": "FFT transposes by peer-memory copy kernels over NVLink (CUDA IPC, flag-word barriers), ",
+                                         "nccl": "FFT transposes by NCCL all-to-all, "}[transport]
+                                      + f"pipelined in {chunks} kx chunks" + ("" if transport == "fused" else " on a second stream")
+                                      + ", all-to-all-v particle migration",
                        "fft_transport": transport_note + transport},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
@@ -619,7 +622,7 @@ def main():
     ap.add_argument("--n-cells", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
-    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "nccl"],
+    ap.add_argument("--transport", default="auto", choices=["auto", "fused", "peer", "nccl"],
                     help="FFT transposes of the multi-GPU path: peer-memory copy kernels or NCCL all-to-all")
     ap.add_argument("--reference-budget-s", type=float, default=90.0)
     args = ap.parse_args()

@@ -124,6 +124,8 @@ def lib():
             "pm_slab_fft_push": (i32, [vp, i32, i32, vp]),
             "pm_slab_fft_pull": (i32, [vp, i32, i32, vp]),
             "pm_slab_fft_y_inverse_local": (i32, [vp, i32, i32, vp]),
+            "pm_slab_fft_y_forward_push": (i32, [vp, i32, i32, vp]),
+            "pm_slab_fft_y_inverse_pull": (i32, [vp, i32, i32, vp]),
             "pm_ic_workspace_bytes": (sz, [i32]),
             "pm_ic_noise": (i32, [vp, vp, i64, ctypes.c_uint64, vp]),
             "pm_ic_jitter": (i32, [vp, i64, ctypes.c_uint64, vp]),
@@ -153,7 +155,7 @@ EXPORTED_SYMBOLS = (
     "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export",
     "pm_slab_peer_export", "pm_slab_peer_import", "pm_slab_peer_set", "pm_slab_peer_signal", "pm_slab_peer_wait",
     "pm_slab_peer_timeouts", "pm_slab_peer_release", "pm_slab_fft_y_forward_local", "pm_slab_fft_push", "pm_slab_fft_pull",
-    "pm_slab_fft_y_inverse_local", "pm_power_spectrum",
+    "pm_slab_fft_y_inverse_local", "pm_slab_fft_y_forward_push", "pm_slab_fft_y_inverse_pull", "pm_power_spectrum",
     "pm_plan_set_sort_mode", "pm_plan_sort_stats", "pm_plan_set_fft_fuse", "pm_plan_fft_sync_errors",
     "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled", "pm_ic_workspace_bytes", "pm_ic_noise",
     "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",

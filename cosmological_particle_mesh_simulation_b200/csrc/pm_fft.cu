@@ -298,11 +298,24 @@ __device__ __forceinline__ T pm_ld(const T *p)
     else return *p;
 }
 
+// Peer-memory y passes (slab decomposition): the forward y pass stores its result straight into
+// the z-pass arrays of the ranks that own the y positions (position pos -> rank pos / nyl, over
+// NVLink when that is another GPU), the inverse y pass loads its input from there -- the
+// all-to-all transposes of the distributed transform happen in the store / load phase of the
+// butterflies, with no pack kernel, staging buffer or collective.
+struct PeerArgs {
+    float2 *p[PM_PEER_MAX];   // every rank's z-pass array C[z][nyl][hc] (+ side plane [z][nyl])
+    size_t main_off;          // this kx chunk's offset inside that array
+    size_t side_off;          // offset of the Nyquist plane
+    int rank, nzl, nyl_shift, hc;
+};
+
 // One tile of a column pass.  s_tile: [N][cols] float2, s_x: [N] (split-off Nyquist column),
 // s_tw: [N] twiddles, already loaded and visible.
-template <int N, int MODE, bool CG>
+template <int N, int MODE, bool CG, bool PEER = false>
 __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, float2 *s_tile,
-                                              float2 *s_x, const float2 *s_tw)
+                                              float2 *s_x, const float2 *s_tw,
+                                              const PeerArgs *pa = nullptr)
 {
     constexpr int H = N / 2;
     constexpr int S = fft_stages(N);
@@ -318,6 +331,8 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
     int col0 = 0;         // first column index (kx for main tiles, y position for side tiles)
     bool side_tile = false;
     const int TPR = a.tpr;
+    size_t peer_row = 0;   // PEER: row of (this rank's plane z, y position 0) in a peer's array
+    int peer_col = 0;      //       first column of the tile inside the chunk
     if (a.axis == 1) {
         const int z = t / TPR, kt = a.kt0 + t % TPR;
         g = a.main + (size_t)z * N * H + kt * kColsCN<N>;
@@ -325,6 +340,10 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
         if (kt == 0) {
             extra = true;
             gx = a.side + (size_t)z * N;
+        }
+        if constexpr (PEER) {
+            peer_row = ((size_t)pa->rank * pa->nzl + z) << pa->nyl_shift;
+            peer_col = (t % TPR) * kColsCN<N>;
         }
     } else {
         if (t < a.nyl * TPR) {
@@ -345,6 +364,15 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
     auto sm4 = [&](int pos, int cp) -> float4 & {
         return *reinterpret_cast<float4 *>(s_tile + pos * kColsCN<N> + 2 * cp);
     };
+    // PEER: where y position `pos` of this tile lives on the rank that owns it
+    auto peer_main = [&](int pos) -> float2 * {
+        const int s = pos >> pa->nyl_shift, yl = pos & ((1 << pa->nyl_shift) - 1);
+        return pa->p[s] + pa->main_off + (peer_row + yl) * pa->hc + peer_col;
+    };
+    auto peer_side = [&](int pos) -> float2 * {
+        const int s = pos >> pa->nyl_shift, yl = pos & ((1 << pa->nyl_shift) - 1);
+        return pa->p[s] + pa->side_off + peer_row + yl;
+    };
 
     // ---- generic stage runner over the 8 column pairs (+ the extra column) ----
     // src/dst: 0 = shared tile, 1 = global.
@@ -362,12 +390,16 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
             if (w < NB * CP) {
                 auto ld = [&](int pos) -> float4 {
                     if (src == 0) return sm4(pos, cp);
+                    if constexpr (PEER && !FWD)   // inverse y pass: pull from the owner of this y position
+                        return *reinterpret_cast<const float4 *>(peer_main(pos) + 2 * cp);
                     float4 q = pm_ld<CG>(reinterpret_cast<const float4 *>(g + (size_t)pos * gs + 2 * cp));
                     if (extra && cp == 0 && FWD) q.y = 0.0f;  // packed slot: real part = DC column
                     return q;
                 };
                 auto st = [&](int pos, float4 q) {
                     if (dst == 0 || (extra && cp == 0 && !FWD)) sm4(pos, cp) = q;  // inverse: merged later
+                    else if constexpr (PEER && FWD)   // forward y pass: push to the owner of this y position
+                        *reinterpret_cast<float4 *>(peer_main(pos) + 2 * cp) = q;
                     else *reinterpret_cast<float4 *>(g + (size_t)pos * gs + 2 * cp) = q;
                 };
                 butterfly2<N, ST, FWD>(u, s_tw, ld, st, [](auto &, auto &, int) {});
@@ -378,10 +410,12 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
                 auto ld = [&](int pos) -> float2 {
                     if (src == 0) return s_x[pos];
                     if (FWD) return make_float2(pm_ld<CG>(g + (size_t)pos * gs).y, 0.0f);  // Nyquist part of the packed slot
+                    if constexpr (PEER) return *peer_side(pos);
                     return pm_ld<CG>(gx + pos);
                 };
                 auto st = [&](int pos, float2 v) {
                     if (dst == 0 || !FWD) s_x[pos] = v;
+                    else if constexpr (PEER) *peer_side(pos) = v;
                     else gx[pos] = v;
                 };
                 butterfly<N, ST, FWD, N>(u, s_tw, ld, st, NoMid());
@@ -481,6 +515,20 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
     for (int m = threadIdx.x; m < N; m += kThrC<N>) s_tw[m] = a.tw[m];
     __syncthreads();
     fft_cols_tile<N, MODE, false>(a, blockIdx.x, s_tile, s_x, s_tw);
+}
+
+// The y passes of the slab path with the transposes fused in (PeerArgs above).
+template <int N, int MODE>
+__global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols_peer(ColArgs a, PeerArgs pa)
+{
+    static_assert(MODE == COL_FWD || MODE == COL_INV, "y passes only");
+    extern __shared__ float2 s_dyn[];
+    float2 *s_tile = s_dyn;
+    float2 *s_x = s_tile + N * kColsCN<N>;
+    float2 *s_tw = s_x + N;
+    for (int m = threadIdx.x; m < N; m += kThrC<N>) s_tw[m] = a.tw[m];
+    __syncthreads();
+    fft_cols_tile<N, MODE, false, true>(a, blockIdx.x, s_tile, s_x, s_tw, &pa);
 }
 
 // Row pass: 16 x-rows per CTA, each an (N/2)-point complex FFT of z_j = x_2j + i x_2j+1 plus the
@@ -1228,6 +1276,39 @@ __global__ void k_peer_wait_impl(uint32_t *flags, int nranks, int slot, uint32_t
 }
 
 template <int N>
+int slab_y_peer(pm_plan *p, int c, int C, bool fwd, cudaStream_t st)
+{
+    constexpr int H = N / 2;
+    const int nzl = p->nzl, nyl = N / p->nranks, hc = H / C;
+    const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
+    ColArgs ca = slab_args<N>(p);
+    ca.tpr = hc / kColsCN<N>;
+    ca.kt0 = c * ca.tpr;
+    PeerArgs pa;
+    for (int s = 0; s < PM_PEER_MAX; ++s) pa.p[s] = s < p->nranks ? p->peer_recv[s] : nullptr;
+    const size_t main_n = (size_t)nzl * N * H;
+    pa.main_off = main_n / C * c;
+    pa.side_off = main_n;
+    pa.rank = p->rank;
+    pa.nzl = nzl;
+    pa.hc = hc;
+    pa.nyl_shift = 0;
+    while ((1 << pa.nyl_shift) < nyl) ++pa.nyl_shift;
+    if ((1 << pa.nyl_shift) != nyl) return PM_ERR_UNSUPPORTED;
+    if (fwd) {
+        auto k = k_fft_cols_peer<N, COL_FWD>;
+        PM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        PM_LAUNCH(k, nzl * ca.tpr, kThrC<N>, smem_cols, st, ca, pa);
+    } else {
+        auto k = k_fft_cols_peer<N, COL_INV>;
+        PM_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        PM_LAUNCH(k, nzl * ca.tpr, kThrC<N>, smem_cols, st, ca, pa);
+    }
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+template <int N>
 int slab_y_only(pm_plan *p, int c, int C, bool fwd, cudaStream_t st)
 {
     constexpr int H = N / 2;
@@ -1422,6 +1503,16 @@ int pm_k_fft_slab_y_fwd(pm_plan *p, int c, int C, cudaStream_t st)
 int pm_k_fft_slab_y_inv(pm_plan *p, int c, int C, cudaStream_t st)
 {
     PM_FFT_DISPATCH(slab_y_only, p, c, C, false, st);
+}
+
+int pm_k_fft_slab_y_fwd_push(pm_plan *p, int c, int C, cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_y_peer, p, c, C, true, st);
+}
+
+int pm_k_fft_slab_y_inv_pull(pm_plan *p, int c, int C, cudaStream_t st)
+{
+    PM_FFT_DISPATCH(slab_y_peer, p, c, C, false, st);
 }
 
 int pm_k_fft_slab_push(pm_plan *p, int c, int C, cudaStream_t st) { return slab_peer_copy<false>(p, c, C, st); }

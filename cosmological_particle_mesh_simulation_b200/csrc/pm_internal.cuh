@@ -189,6 +189,9 @@ int pm_k_fft_slab_y_fwd(pm_plan *p, int c, int C, cudaStream_t st);
 int pm_k_fft_slab_push(pm_plan *p, int c, int C, cudaStream_t st);
 int pm_k_fft_slab_pull(pm_plan *p, int c, int C, cudaStream_t st);
 int pm_k_fft_slab_y_inv(pm_plan *p, int c, int C, cudaStream_t st);
+// ... and with the transposes fused into the y passes themselves
+int pm_k_fft_slab_y_fwd_push(pm_plan *p, int c, int C, cudaStream_t st);
+int pm_k_fft_slab_y_inv_pull(pm_plan *p, int c, int C, cudaStream_t st);
 int pm_k_peer_signal(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st);
 int pm_k_peer_wait(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st);
 int pm_fft_cols_per_tile(int nc);

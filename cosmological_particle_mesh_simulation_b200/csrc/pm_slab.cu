@@ -296,6 +296,20 @@ int pm_slab_fft_pull(pm_plan *p, int c, int C, pm_stream_t stream)
     return pm_k_fft_slab_pull(p, c, C, st);
 }
 
+// The same two legs fused into the y passes: the forward y pass stores its output into the peers'
+// z-pass arrays, the inverse y pass loads its input from them (pm_fft.cu, PeerArgs).
+int pm_slab_fft_y_forward_push(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C) && p->peers_set == p->nranks);
+    return pm_k_fft_slab_y_fwd_push(p, c, C, st);
+}
+
+int pm_slab_fft_y_inverse_pull(pm_plan *p, int c, int C, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(chunk_ok(p, c, C) && p->peers_set == p->nranks);
+    return pm_k_fft_slab_y_inv_pull(p, c, C, st);
+}
+
 int pm_slab_fft_y_inverse_local(pm_plan *p, int c, int C, pm_stream_t stream)
 {
     PM_SLAB_ENTER(chunk_ok(p, c, C));

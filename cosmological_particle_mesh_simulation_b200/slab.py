@@ -191,6 +191,12 @@ class SlabRank:
     def fft_pull(self, c, C):
         self._call("pm_slab_fft_pull", int(c), int(C))
 
+    def fft_y_forward_push(self, c, C):
+        self._call("pm_slab_fft_y_forward_push", int(c), int(C))
+
+    def fft_y_inverse_pull(self, c, C):
+        self._call("pm_slab_fft_y_inverse_pull", int(c), int(C))
+
     def fft_y_inverse_local(self, c, C):
         self._call("pm_slab_fft_y_inverse_local", int(c), int(C))
 
@@ -455,9 +461,10 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
     """One body of the loop src/pmesh.py:60-61 across the slabs.  `ranks`: the SlabRank objects
     of comm.local_ranks (one for DistComm, all P for LocalComm).  The distributed FFT runs as a
     pipeline of `chunks` kx chunks: with DistComm on GPUs the transposes go to a second stream
-    and overlap the y and z passes of the neighbouring chunks.  transport: "peer" = the copy
-    kernels store into / load from the other ranks' buffers over NVLink (needs setup_peers),
-    "nccl" = pack -> all-to-all -> unpack; default: "peer" when the ranks are set up for it."""
+    and overlap the y and z passes of the neighbouring chunks.  transport: "fused" = the y passes
+    themselves store into / load from the other ranks' z-pass arrays over NVLink (one stream, no
+    copy kernel; needs setup_peers), "peer" = separate push / pull copy kernels on the second
+    stream, "nccl" = pack -> all-to-all -> unpack; default: "fused" when the ranks are set up for it."""
     cfg = cfg or rt.config()
     if timer:
         timer.begin_step()
@@ -501,14 +508,36 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
         return e
 
     if transport is None:
-        transport = "peer" if all(r.peers_ready for r in ranks) else "nccl"
-    if transport == "peer" and not all(r.peers_ready for r in ranks):
-        raise RuntimeError("transport='peer' needs slab.setup_peers(ranks, comm) first")
-    if transport == "peer" and C > PEER_SLOTS_HALF - 1:
-        raise ValueError("at most %d chunks with the peer transport" % (PEER_SLOTS_HALF - 1))
+        transport = "fused" if all(r.peers_ready for r in ranks) else "nccl"
+    if transport not in ("fused", "peer", "nccl"):
+        raise ValueError(f"unknown transport {transport!r}")
+    if transport != "nccl" and not all(r.peers_ready for r in ranks):
+        raise RuntimeError(f"transport={transport!r} needs slab.setup_peers(ranks, comm) first")
+    if transport != "nccl" and C > PEER_SLOTS_HALF - 1:
+        raise ValueError("at most %d chunks with the peer-memory transports" % (PEER_SLOTS_HALF - 1))
 
     for r in ranks:
         r.fft_rows_forward()
+    if transport == "fused":
+        # one stream: chunk c's stores drain over NVLink while chunk c+1 is transformed; the flag
+        # waits sit right before the first consumer of the data
+        for c in range(C):
+            for r in ranks:
+                r.fft_y_forward_push(c, C)
+            for r in ranks:
+                r.signal(c)
+        for c in range(C):
+            for r in ranks:
+                r.wait(c)
+            for r in ranks:
+                r.fft_z(c, C, a, cfg.OMEGA_M0)
+            for r in ranks:
+                r.signal(PEER_SLOTS_HALF + c)
+        for c in range(C):
+            for r in ranks:
+                r.wait(PEER_SLOTS_HALF + c)
+            for r in ranks:
+                r.fft_y_inverse_pull(c, C)
     arrived = []
     for c in range(C if transport == "peer" else 0):
         for r in ranks:
@@ -544,10 +573,7 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
             main.wait_event(pulled[c])
         for r in ranks:
             r.fft_y_inverse_local(c, C)
-    if transport == "peer":
-        C_nccl = 0
-    else:
-        C_nccl = C
+    C_nccl = C if transport == "nccl" else 0
     arrived = []
     for c in range(C_nccl):
         for r in ranks:

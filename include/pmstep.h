@@ -270,6 +270,10 @@ PM_API int pm_slab_fft_y_forward_local(pm_plan *plan, int chunk, int nchunks, pm
 PM_API int pm_slab_fft_push(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
 PM_API int pm_slab_fft_pull(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
 PM_API int pm_slab_fft_y_inverse_local(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+/* ... or fused: the forward y pass stores its result straight into the peers' z-pass arrays and
+ * the inverse y pass loads its input from them -- no copy kernel at all (same signal/wait calls). */
+PM_API int pm_slab_fft_y_forward_push(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+PM_API int pm_slab_fft_y_inverse_pull(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
 PM_API int pm_slab_gather(pm_plan *plan, double a, double f_a1, double da, pm_stream_t stream);
 PM_API int pm_slab_migrate_pack(pm_plan *plan, const int64_t *counts_h, pm_stream_t stream);
 PM_API int pm_slab_migrate_unpack(pm_plan *plan, int64_t n_arrive, int64_t n_leave, pm_stream_t stream);

@@ -45,7 +45,7 @@ def test_particle_to_slab_assignment_bit_exact(pm):
     assert np.array_equal(want, (keys // (n * n)) // (n // P))  # same rule as the cell key
 
 
-@pytest.mark.parametrize("transport", ["nccl", "peer"])
+@pytest.mark.parametrize("transport", ["nccl", "peer", "fused"])
 @pytest.mark.parametrize("P", [1, 2, 4])
 @pytest.mark.parametrize("n_parts,n_cells", [(32, 64), (64, 128)])
 def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells, transport):
@@ -66,7 +66,7 @@ def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells, transport):
     comm = pm.slab.LocalComm(P)
     ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
     assert sum(r.count for r in ranks) == npart
-    if transport == "peer":      # transposes by stores into / loads from the other ranks' buffers
+    if transport != "nccl":      # transposes by stores into / loads from the other ranks' buffers
         assert pm.slab.setup_peers(ranks, comm)
     ref_p, ref_v = pos.clone(), vel.clone()
     moved = 0
@@ -96,24 +96,24 @@ def test_slab_steps_equal_single_gpu_steps(pm, P, n_parts, n_cells, transport):
             assert bool((own == r.rank).all())
         a += da
     assert torch.isfinite(phi).all()
-    if transport == "peer":
+    if transport != "nccl":
         assert all(r.peer_timeouts() == 0 for r in ranks)
     for r in ranks:
         r.close()
 
 
 def test_peer_and_nccl_transports_are_bit_identical(pm):
-    """The two transports move the same numbers: the whole state must agree bit for bit."""
+    """The three transports move the same numbers: the whole state must agree bit for bit."""
     n_parts, n_cells, P = 64, 128, 4
     cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
     pm.set_config(cfg)
     pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=5, vel_rms=0.5)
     outs = []
-    for transport in ("nccl", "peer"):
+    for transport in ("nccl", "peer", "fused"):
         pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
         comm = pm.slab.LocalComm(P)
         ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
-        if transport == "peer":
+        if transport != "nccl":
             assert pm.slab.setup_peers(ranks, comm)
         for s in range(4):
             pm.slab.slab_step(ranks, comm, 0.4 + 0.0099 * s, 0.0099, mass=8.0, cfg=cfg, chunks=(1, 2, 4, 2)[s],
@@ -122,8 +122,9 @@ def test_peer_and_nccl_transports_are_bit_identical(pm):
         outs.append(pm.slab.collect(ranks, comm, pos.shape[1]) + (phi,))
         for r in ranks:
             r.close()
-    for x, y in zip(*outs):
-        assert torch.equal(x, y)
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert torch.equal(x, y)
 
 
 IPC_WORKER = r'''
@@ -145,7 +146,7 @@ ref_p, ref_v = pos.clone(), vel.clone()
 a, da = 0.3, 0.0099
 for s in range(3):
     pm.step(ref_p, ref_v, a, da, mass=8.0)
-    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2, 1)[s], transport="peer")
+    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2, 1)[s], transport=("fused", "peer", "fused")[s])
     a += da
 torch.cuda.synchronize()
 assert ranks[0].peer_timeouts() == 0

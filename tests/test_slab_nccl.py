@@ -32,7 +32,7 @@ a, da = 0.3, 0.0099
 for s in range(6):
     pm.step(ref_p, ref_v, a, da, mass=8.0)
     pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2)[s %% 2],
-                      transport=("peer", "peer", "nccl")[s %% 3])
+                      transport=("fused", "peer", "nccl")[s %% 3])
     a += da
 torch.cuda.synchronize()
 assert ranks[0].peer_timeouts() == 0
