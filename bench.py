@@ -373,42 +373,63 @@ def run_slab(args, rank, world, local_rank):
     ms_per_step = ms_total / K
     value = npart * K / (ms_total * 1e-3)
 
-    # e2e: the rank's particles live in pinned host memory; every step uploads them, runs the
-    # slab step and downloads the rank's (migrated) particles again
-    sr = ranks[0]
-    p, v, ids = sr.export()
-    hp, hv, hi = p.cpu().pin_memory(), v.cpu().pin_memory(), ids.cpu().pin_memory()
-    ke = max(3, min(K, 10))
-    h2d = d2h = 0
-
-    def host_step():
-        nonlocal hp, hv, hi, h2d, d2h, step_i
-        a, da = sched[step_i % len(sched)]
-        step_i += 1
-        dp = hp.to(f"cuda:{dev}", non_blocking=True)
-        dv = hv.to(f"cuda:{dev}", non_blocking=True)
-        di = hi.to(f"cuda:{dev}", non_blocking=True)
-        h2d += dp.numel() * 4 * 2 + di.numel() * 4
-        sr.load(dp.contiguous(), dv.contiguous(), di)
-        slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, transport=transport)
+    e2e_value, ke = None, 0
+    t = torch.zeros(3, dtype=torch.float64, device=f"cuda:{dev}")
+    if not args.no_e2e:
+        # e2e: the rank's particles live in pinned host memory; every step uploads them, runs the
+        # slab step and downloads the rank's (migrated) particles again
+        sr = ranks[0]
         p, v, ids = sr.export()
-        hp, hv, hi = p.cpu().pin_memory(), v.cpu().pin_memory(), ids.cpu().pin_memory()
-        d2h += p.numel() * 4 * 2 + ids.numel() * 4
+        cap = sr.np_capacity
+        # pinned host state of this rank, allocated once (capacity of the plan): the timed steps only copy
+        hp_flat = torch.empty(3 * cap, dtype=torch.float32).pin_memory()
+        hv_flat = torch.empty(3 * cap, dtype=torch.float32).pin_memory()
+        hi = torch.empty(cap, dtype=torch.int32).pin_memory()
+        n_host = p.shape[1]
 
-    for _ in range(2):
-        host_step()
-    barrier()
-    h2d = d2h = 0
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        host_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s, float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{dev}")
-    tmax = t.clone()
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    e2e_value = npart * ke / float(tmax[0].item())
+        def host_views(n):      # contiguous [3, n] views, so every copy is one plain DMA
+            return hp_flat[:3 * n].view(3, n), hv_flat[:3 * n].view(3, n), hi[:n]
+
+        hp, hv, hid = host_views(n_host)
+        hp.copy_(p); hv.copy_(v); hid.copy_(ids)
+        torch.cuda.synchronize()
+        ke = max(3, min(K, 10))
+        h2d = d2h = 0
+
+        def host_step():
+            nonlocal n_host, h2d, d2h, step_i
+            a, da = sched[step_i % len(sched)]
+            step_i += 1
+            hp, hv, hid = host_views(n_host)
+            dp = hp.to(f"cuda:{dev}", non_blocking=True)
+            dv = hv.to(f"cuda:{dev}", non_blocking=True)
+            di = hid.to(f"cuda:{dev}", non_blocking=True)
+            h2d += n_host * 4 * 7
+            sr.load(dp, dv, di)
+            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, transport=transport)
+            p, v, ids = sr.export()
+            n_host = p.shape[1]
+            hp, hv, hid = host_views(n_host)
+            hp.copy_(p, non_blocking=True)
+            hv.copy_(v, non_blocking=True)
+            hid.copy_(ids, non_blocking=True)
+            torch.cuda.synchronize()          # the step's results are in host memory
+            d2h += n_host * 4 * 7
+
+        for _ in range(2):
+            host_step()
+        barrier()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            host_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s, float(h2d), float(d2h)], dtype=torch.float64, device=f"cuda:{dev}")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_value = npart * ke / float(tmax[0].item())
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -416,7 +437,7 @@ def run_slab(args, rank, world, local_rank):
         nvlink_bytes = 2 * (4 * n_cells ** 3 / world) * (world - 1) / world   # per GPU per step
         t_roof = (bstep / world) / (peak * 1e9) + nvlink_bytes / 900e9
         dominant = max(phases, key=phases.get)
-        chunks = args.chunks or slab.default_chunks(n_cells, world)
+        chunks = args.chunks or slab.default_chunks(n_cells, world, transport)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -434,7 +455,8 @@ def run_slab(args, rank, world, local_rank):
                                       + ", all-to-all-v particle migration",
                        "fft_transport": transport_note + transport},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
+            "e2e": None if e2e_value is None else {
+                    "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
                     "d2h_bytes_per_step": float(t[2].item()) / ke, "steps": ke,
                     "api": "per rank: pinned host pos+vel+ids -> pm_slab_load -> slab step -> pm_slab_export -> host"},
             "gpu_launches": int(launches),
@@ -621,6 +643,7 @@ def main():
     ap.add_argument("--n-parts", type=int, default=256)
     ap.add_argument("--n-cells", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="multi-GPU exploration runs: skip the host-buffer leg")
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
     ap.add_argument("--transport", default="auto", choices=["auto", "fused", "peer", "nccl"],
                     help="FFT transposes of the multi-GPU path: peer-memory copy kernels or NCCL all-to-all")

@@ -444,10 +444,14 @@ class PhaseTimer:
         return out
 
 
-def default_chunks(n_cells, nranks=1):
+def default_chunks(n_cells, nranks=1, transport="nccl"):
     """kx chunks of the distributed FFT pipeline, by the size of one rank's half spectrum: deep
     pipelines pay off when a chunk's all-to-all is long against a kernel launch (measured on
     8 B200: 67 MB/rank is faster unchunked, 268 MB/rank and up is faster pipelined)."""
+    if transport == "fused":
+        # the transfer already overlaps the transform inside the y-pass kernels; chunking only adds
+        # launches and flag waits (measured on 2 B200: 512^3 mesh 0.87 / 0.94 / 1.09 ms for 1 / 2 / 4 chunks)
+        return 1
     tile = 8 if n_cells >= 1024 else 16
     mb = 4.0 * n_cells ** 3 / max(nranks, 1) / 2 ** 20
     want = 4 if mb >= 256 else 2 if mb >= 128 else 1   # 8 chunks measured no better than 4 at 4.3 GB/rank
@@ -473,7 +477,13 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
         mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3          # src/pmesh.py:28
     f_a1 = f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])   # src/integrate.py:12
     B = lambda name: [r.buf[name] for r in ranks]    # noqa: E731
-    C = chunks or default_chunks(ranks[0].n_cells, ranks[0].nranks)
+    if transport is None:
+        transport = "fused" if all(r.peers_ready for r in ranks) else "nccl"
+    if transport not in ("fused", "peer", "nccl"):
+        raise ValueError(f"unknown transport {transport!r}")
+    if transport != "nccl" and not all(r.peers_ready for r in ranks):
+        raise RuntimeError(f"transport={transport!r} needs slab.setup_peers(ranks, comm) first")
+    C = chunks or default_chunks(ranks[0].n_cells, ranks[0].nranks, transport)
     CH = lambda name, c: [r.chunk(name, c, C) for r in ranks]    # noqa: E731
 
     for r in ranks:
@@ -507,12 +517,6 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
         e.record(main)
         return e
 
-    if transport is None:
-        transport = "fused" if all(r.peers_ready for r in ranks) else "nccl"
-    if transport not in ("fused", "peer", "nccl"):
-        raise ValueError(f"unknown transport {transport!r}")
-    if transport != "nccl" and not all(r.peers_ready for r in ranks):
-        raise RuntimeError(f"transport={transport!r} needs slab.setup_peers(ranks, comm) first")
     if transport != "nccl" and C > PEER_SLOTS_HALF - 1:
         raise ValueError("at most %d chunks with the peer-memory transports" % (PEER_SLOTS_HALF - 1))
 
