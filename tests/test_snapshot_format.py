@@ -263,3 +263,32 @@ def test_reference_cadence_restatement_is_consistent(steps, n_save, n_plot):
         assert a == a_next
         i += 1
     assert pre == saves and len(saves) >= 1
+
+
+# ------------------------------------------------------------------------------------------------
+# property test: any set of supported arrays survives the container
+# ------------------------------------------------------------------------------------------------
+try:
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+    HAVE_HYPOTHESIS = True
+except Exception:  # pragma: no cover
+    HAVE_HYPOTHESIS = False
+
+if HAVE_HYPOTHESIS:
+    _dtypes = st.sampled_from([np.float32, np.float64, np.int32, np.int64, np.uint32, np.uint8, np.int16])
+    _arrays = _dtypes.flatmap(lambda dt: hnp.arrays(dt, hnp.array_shapes(min_dims=0, max_dims=3, min_side=0, max_side=7)))
+    _names = st.text(alphabet="abcdefghijklmnopqrstuvwxyzABCXYZ0123456789_.", min_size=1, max_size=20)
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.dictionaries(_names, _arrays, min_size=0, max_size=12))
+    def test_any_flat_group_of_arrays_round_trips(tmp_path_factory, data):
+        path = str(tmp_path_factory.mktemp("h5") / "p.hdf5")
+        H.write(path, data)
+        r = H.Reader(path)
+        assert sorted(r.keys()) == sorted(data)
+        assert os.path.getsize(path) == struct.unpack_from("<Q", open(path, "rb").read(48), 40)[0]   # EOF address
+        for k, v in data.items():
+            got = r[k]
+            assert got.dtype == v.dtype and got.shape == v.shape
+            assert got.tobytes() == np.ascontiguousarray(v).tobytes()      # bit-exact, NaN payloads included
