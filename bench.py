@@ -332,7 +332,7 @@ def run_slab(args, rank, world, local_rank):
     # rebuilds its state and runs the NCCL all-to-all path instead -- and the JSON line says which.
     transport, transport_note = "nccl", ""
     if args.transport != "nccl":
-        transport = ("peer" if args.transport == "peer" else "fused") if slab.setup_peers(ranks, comm) else "nccl"
+        transport = (args.transport if args.transport in ("peer", "fused2") else "fused") if slab.setup_peers(ranks, comm) else "nccl"
         if transport == "nccl":
             transport_note = "peer-memory set-up failed; "
     warm_up(transport)
@@ -347,7 +347,7 @@ def run_slab(args, rank, world, local_rank):
             ranks, particles_desc = build_ranks()
             step_i = 0
             warm_up(transport)
-    if args.transport in ("peer", "fused") and transport != args.transport:
+    if args.transport in ("peer", "fused", "fused2") and transport != args.transport:
         raise RuntimeError(f"--transport {args.transport}: " + transport_note)
     # sanity on the distributed state: total mass of the last deposit == Np * mass
     msum = ranks[0].buf["RHO"].sum(dtype=torch.float64).reshape(1)
@@ -455,9 +455,10 @@ def run_slab(args, rank, world, local_rank):
                        "parallelism": f"slab decomposition along z over {world} GPUs: NCCL send/recv ghost planes, "
                                       + {"fused": "FFT transposes fused into the y passes (stores into / loads from the peers' "
                                                   "z-pass arrays over NVLink, CUDA IPC, flag-word barriers), ",
+                                         "fused2": "FFT transposes fused into the y passes, y passes and z passes on two streams (experimental), ",
                                          "peer": "FFT transposes by peer-memory copy kernels over NVLink (CUDA IPC, flag-word barriers), ",
                                          "nccl": "FFT transposes by NCCL all-to-all, "}[transport]
-                                      + f"pipelined in {chunks} kx chunks" + ("" if transport == "fused" else " on a second stream")
+                                      + f"pipelined in {chunks} kx chunks" + ("" if transport == "fused" else " on two streams")
                                       + ", all-to-all-v particle migration",
                        "fft_transport": transport_note + transport},
             "clocks": clocks,
@@ -651,7 +652,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="multi-GPU exploration runs: skip the host-buffer leg")
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
-    ap.add_argument("--transport", default="auto", choices=["auto", "fused", "peer", "nccl"],
+    ap.add_argument("--transport", default="auto", choices=["auto", "fused", "fused2", "peer", "nccl"],
                     help="FFT transposes of the multi-GPU path: peer-memory copy kernels or NCCL all-to-all")
     ap.add_argument("--reference-budget-s", type=float, default=90.0)
     args = ap.parse_args()

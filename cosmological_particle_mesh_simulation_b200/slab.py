@@ -452,6 +452,8 @@ def default_chunks(n_cells, nranks=1, transport="nccl"):
         # the transfer already overlaps the transform inside the y-pass kernels; chunking only adds
         # launches and flag waits (measured on 2 B200: 512^3 mesh 0.87 / 0.94 / 1.09 ms for 1 / 2 / 4 chunks)
         return 1
+    if transport == "fused2":
+        return 2 if (n_cells // 2) % 2 == 0 and ((n_cells // 2) // 2) % (8 if n_cells >= 1024 else 16) == 0 else 1
     tile = 8 if n_cells >= 1024 else 16
     mb = 4.0 * n_cells ** 3 / max(nranks, 1) / 2 ** 20
     want = 4 if mb >= 256 else 2 if mb >= 128 else 1   # 8 chunks measured no better than 4 at 4.3 GB/rank
@@ -479,7 +481,7 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
     B = lambda name: [r.buf[name] for r in ranks]    # noqa: E731
     if transport is None:
         transport = "fused" if all(r.peers_ready for r in ranks) else "nccl"
-    if transport not in ("fused", "peer", "nccl"):
+    if transport not in ("fused", "fused2", "peer", "nccl"):
         raise ValueError(f"unknown transport {transport!r}")
     if transport != "nccl" and not all(r.peers_ready for r in ranks):
         raise RuntimeError(f"transport={transport!r} needs slab.setup_peers(ranks, comm) first")
@@ -577,6 +579,38 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
             main.wait_event(pulled[c])
         for r in ranks:
             r.fft_y_inverse_local(c, C)
+    if transport == "fused2":
+        # EXPERIMENTAL (not yet measured on hardware): the fused y passes -- NVLink-bound when most of
+        # the data is remote -- on the second stream, the z passes -- HBM-bound -- on the first, so
+        # that chunk c's z pass overlaps chunk c+1's push and chunk c's pull overlaps chunk c+1's z
+        # pass.  Without a second stream this is the order of "fused".  Schedule checked by
+        # tests/test_slab_schedule_sim.py.
+        def pushes():
+            for c in range(C):
+                for r in ranks:
+                    r.fft_y_forward_push(c, C)
+                for r in ranks:
+                    r.signal(c)
+        on_comm(ev(), pushes)
+        zdone = []
+        for c in range(C):
+            for r in ranks:
+                r.wait(c)
+            for r in ranks:
+                r.fft_z(c, C, a, cfg.OMEGA_M0)
+            for r in ranks:
+                r.signal(PEER_SLOTS_HALF + c)
+            zdone.append(ev())
+
+        def pulls():
+            for c in range(C):
+                for r in ranks:
+                    r.wait(PEER_SLOTS_HALF + c)
+                for r in ranks:
+                    r.fft_y_inverse_pull(c, C)
+        back = on_comm(zdone[0], pulls)
+        if back is not None:
+            main.wait_event(back)
     C_nccl = C if transport == "nccl" else 0
     arrived = []
     for c in range(C_nccl):

@@ -1,0 +1,266 @@
+"""CPU model check of the multi-GPU step's SCHEDULE (slab.slab_step): no GPU, no kernels.
+
+`slab_step` only sequences library calls, stream/event dependencies, flag signals/waits and
+collectives.  Here every one of those is replaced by a recorder (a fake `torch.cuda`, fake ranks, a
+fake communicator), the per-rank op queues of P ranks x 2 streams x several steps are then executed
+"concurrently" by a randomised scheduler with the semantics of the real things:
+
+* ops of one stream run in order; `wait_event` blocks until the event was recorded;
+* `signal(slot)` stores this rank's epoch into every rank's flag word, `wait(slot)` blocks until all P
+  words of the slot carry the waiter's epoch (pm_slab_peer_signal / pm_slab_peer_wait);
+* a collective completes when every participant has reached it, and one rank's collectives complete
+  in the order the host issued them (one NCCL communicator).
+
+The run must drain (no deadlock) under every interleaving tried, and the data hazards of the
+distributed transform must be ordered in all of them:
+
+  H1  a rank's z pass of chunk c runs after EVERY rank has delivered its block of chunk c;
+  H2  a rank fetches chunk c back only after EVERY rank has finished its z pass of chunk c;
+  H3  no rank stores step n+1's chunk c into the z-pass arrays before EVERY rank has fetched step n's.
+"""
+import contextlib
+import itertools
+import random
+import types
+
+import pytest
+
+from cosmological_particle_mesh_simulation_b200 import slab
+
+HALF = slab.PEER_SLOTS_HALF
+
+
+# ------------------------------------------------------------------------------------------------
+# recorders
+# ------------------------------------------------------------------------------------------------
+class Stream:
+    def __init__(self, name):
+        self.name, self.ops = name, []
+
+    def wait_event(self, e):
+        self.ops.append(("wait_event", e))
+
+
+class Event:
+    def __init__(self, **_):
+        self.done = False
+
+    def record(self, stream=None):
+        (stream or FakeCuda.state.current).ops.append(("record", self))
+
+
+class FakeCuda:
+    state = None
+    Event = Event
+
+    @staticmethod
+    def current_stream(*_):
+        return FakeCuda.state.current
+
+    @staticmethod
+    @contextlib.contextmanager
+    def stream(s):
+        prev, FakeCuda.state.current = FakeCuda.state.current, s
+        try:
+            yield
+        finally:
+            FakeCuda.state.current = prev
+
+
+class RankRecorder:
+    """Stands in for slab.SlabRank: every compute entry point becomes an op on the current stream."""
+    KERNELS = ["deposit", "ghost_add", "fft_rows_forward", "fft_y_forward", "fft_z", "fft_y_inverse",
+               "fft_rows_inverse", "fft_y_forward_local", "fft_push", "fft_pull", "fft_y_inverse_local",
+               "fft_y_forward_push", "fft_y_inverse_pull", "gather", "migrate_pack", "migrate_unpack",
+               "signal", "wait"]
+
+    def __init__(self, rank, nranks, n_cells=512):
+        self.rank, self.nranks, self.n_cells, self.peers_ready = rank, nranks, n_cells, True
+        self.buf = {k: (k, rank) for k in slab.BUF}
+        self.main, self.side = Stream("main"), Stream("side")
+        self.current = self.main
+        self.issued = itertools.count()
+        for k in self.KERNELS:
+            setattr(self, k, self._recorder(k))
+
+    def _recorder(self, name):
+        def call(*args):
+            c = args[0] if args and name.startswith("fft_") and name not in ("fft_rows_forward", "fft_rows_inverse") else None
+            kind = name if name in ("signal", "wait") else "kernel"
+            self.current.ops.append((kind, name, args[0] if kind != "kernel" else c))
+        return call
+
+    def chunk(self, name, c, C):
+        return (name, self.rank, c)
+
+
+class CommRecorder:
+    """Stands in for slab.DistComm (one rank per process, collectives on the current stream)."""
+
+    def __init__(self, rank_rec, two_streams):
+        self.r = rank_rec
+        self.nranks = rank_rec.nranks
+        self.side_stream = rank_rec.side if two_streams else None
+
+    def _coll(self, kind, peers):
+        r = self.r
+        r.current.ops.append(("collective", kind, frozenset(peers), next(r.issued)))
+
+    def shift(self, send, recv, direction):
+        P, me = self.nranks, self.r.rank
+        self._coll("shift%+d" % direction, {me, (me + direction) % P, (me - direction) % P})
+
+    def all_to_all(self, send, recv):
+        self._coll("a2a", range(self.nranks))
+
+    def exchange_count_tensors(self, counts):
+        self._coll("counts", range(self.nranks))
+        z = [0] * self.nranks
+        return [z], [z]
+
+    def all_to_all_v(self, send, sc, recv, rc):
+        self._coll("a2av", range(self.nranks))
+
+
+def record_program(P, steps, transport, chunks, two_streams, monkeypatch):
+    """Run slab_step `steps` times for each rank against the recorders -> per-rank op queues."""
+    monkeypatch.setattr(slab, "torch", types.SimpleNamespace(cuda=FakeCuda))
+    cfg = types.SimpleNamespace(N_CELLS=512, N_PARTS=256, H0=0.68, OMEGA_LAMBDA0=0.69, OMEGA_K0=0.0, OMEGA_M0=0.31)
+    ranks = []
+    for r in range(P):
+        rec = RankRecorder(r, P)
+        FakeCuda.state = rec
+        comm = CommRecorder(rec, two_streams)
+        for s in range(steps):
+            slab.slab_step([rec], comm, 0.1 + 0.01 * s, 0.01, mass=8.0, cfg=cfg, chunks=chunks, transport=transport)
+        ranks.append(rec)
+    return ranks
+
+
+# ------------------------------------------------------------------------------------------------
+# the executor
+# ------------------------------------------------------------------------------------------------
+class Hazard(AssertionError):
+    pass
+
+
+def execute(ranks, transport, chunks, rng):
+    P = len(ranks)
+    pc = {(r.rank, s.name): 0 for r in ranks for s in (r.main, r.side)}
+    queues = {(r.rank, s.name): s.ops for r in ranks for s in (r.main, r.side)}
+    flags = [[[0] * P for _ in range(2 * HALF)] for _ in range(P)]       # flags[owner][slot][writer]
+    sig_epoch = [[0] * (2 * HALF) for _ in range(P)]
+    wait_epoch = {}                                                       # (rank, stream, pc) -> epoch
+    wait_count = [[0] * (2 * HALF) for _ in range(P)]
+    arrived = {}                                                          # collective key -> set of ranks at it
+    coll_done = [0] * P                                                   # collectives completed per rank (issue order)
+    step = [0] * P                                                        # deposits executed
+    delivered, z_done, fetched = {}, {}, {}                               # (step, c) -> set of ranks
+
+    def mark(table, key, r):
+        table.setdefault(key, set()).add(r)
+
+    def full(table, key):
+        return len(table.get(key, ())) == P
+
+    def runnable(r, sname):
+        q, i = queues[(r, sname)], pc[(r, sname)]
+        if i >= len(q):
+            return False
+        op = q[i]
+        if op[0] == "wait_event":
+            return op[1].done
+        if op[0] == "wait":
+            slot = op[2]
+            key = (r, sname, i)
+            if key not in wait_epoch:
+                wait_count[r][slot] += 1
+                wait_epoch[key] = wait_count[r][slot]
+            return all(flags[r][slot][s] >= wait_epoch[key] for s in range(P))
+        if op[0] == "collective":
+            _, kind, peers, seq = op
+            if seq != coll_done[r]:
+                return False                       # an earlier collective of this rank is still pending
+            arrived.setdefault(seq, {})[r] = kind
+            return all(p in arrived[seq] for p in peers)
+        return True
+
+    def run(r, sname):
+        q, i = queues[(r, sname)], pc[(r, sname)]
+        op = q[i]
+        if op[0] == "record":
+            op[1].done = True
+        elif op[0] == "signal":
+            slot = op[2]
+            sig_epoch[r][slot] += 1
+            for owner in range(P):
+                flags[owner][slot][r] = sig_epoch[r][slot]
+        elif op[0] == "collective":
+            coll_done[r] += 1
+        elif op[0] == "kernel":
+            name, c = op[1], op[2]
+            n = step[r]
+            if name == "deposit":
+                step[r] += 1
+            elif name in ("fft_push", "fft_y_forward_push"):
+                if n > 1 and not full(fetched, (n - 1, c)):
+                    raise Hazard(f"H3: rank {r} stores step {n} chunk {c} before everyone fetched step {n - 1}'s")
+                mark(delivered, (n, c), r)
+            elif name == "fft_z":
+                if transport != "nccl" and not full(delivered, (n, c)):
+                    raise Hazard(f"H1: rank {r} runs z pass of step {n} chunk {c} before every block arrived")
+                mark(z_done, (n, c), r)
+            elif name in ("fft_pull", "fft_y_inverse_pull"):
+                if not full(z_done, (n, c)):
+                    raise Hazard(f"H2: rank {r} fetches step {n} chunk {c} before every z pass finished")
+                mark(fetched, (n, c), r)
+        pc[(r, sname)] = i + 1
+
+    keys = list(queues)
+    total = sum(len(q) for q in queues.values())
+    executed = 0
+    while executed < total:
+        ready = [k for k in keys if runnable(*k)]
+        if not ready:
+            heads = {k: queues[k][pc[k]][:3] for k in keys if pc[k] < len(queues[k])}
+            raise AssertionError(f"deadlock after {executed}/{total} ops; heads: {heads}")
+        run(*rng.choice(ready))
+        executed += 1
+    return executed
+
+
+@pytest.mark.parametrize("transport,chunks,two_streams", [
+    ("fused", 1, True), ("fused", 2, True), ("fused", 4, False),
+    ("fused2", 1, True), ("fused2", 2, True), ("fused2", 4, True), ("fused2", 2, False),
+    ("peer", 1, True), ("peer", 2, True), ("peer", 4, True), ("peer", 2, False),
+    ("nccl", 1, True), ("nccl", 4, True), ("nccl", 2, False)])
+@pytest.mark.parametrize("P", [2, 4])
+def test_schedule_drains_and_orders_its_hazards(monkeypatch, P, transport, chunks, two_streams):
+    ranks = record_program(P, steps=3, transport=transport, chunks=chunks, two_streams=two_streams,
+                           monkeypatch=monkeypatch)
+    for r in ranks:        # every rank issued the same program (signal/wait pair up by call count)
+        assert [op[:3] for op in r.main.ops if op[0] != "collective" and op[0] not in ("record", "wait_event")] == \
+               [op[:3] for op in ranks[0].main.ops if op[0] != "collective" and op[0] not in ("record", "wait_event")]
+    n_ops = sum(len(s.ops) for r in ranks for s in (r.main, r.side))
+    for seed in range(25):
+        for r in ranks:    # events are one-shot per run
+            for s in (r.main, r.side):
+                for op in s.ops:
+                    if op[0] == "record":
+                        op[1].done = False
+        assert execute(ranks, transport, chunks, random.Random(seed)) == n_ops
+
+
+def test_the_model_catches_a_missing_barrier(monkeypatch):
+    """Sanity of the checker itself: drop the 'chunk pushed' waits and H1 must fire for some interleaving."""
+    ranks = record_program(2, steps=2, transport="fused", chunks=1, two_streams=False, monkeypatch=monkeypatch)
+    for r in ranks:
+        r.main.ops = [op for op in r.main.ops if not (op[0] == "wait" and op[2] < HALF)]
+    fired = 0
+    for seed in range(40):
+        try:
+            execute(ranks, "fused", 1, random.Random(seed))
+        except Hazard as e:
+            assert "H1" in str(e)
+            fired += 1
+    assert fired > 0
