@@ -133,6 +133,26 @@ def make_particles_torch(n_parts, n_cells, device, seed=38, vel_sigma=VEL_SIGMA)
     return pos, vel
 
 
+def make_particles_clustered(n_parts, n_cells, seed=38, vel_sigma=VEL_SIGMA):
+    """BASELINE configs[4] / SURVEY 8d(iii): the adversarial load for the deposit, the sort and the
+    gather -- half of the particles in a Gaussian blob of one cell rms around the box centre (the
+    probe behind SURVEY's "13 239 particles in one cell"), half uniform.  Host generator, float32."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    npart = n_parts ** 3
+    nblob = npart // 2
+    pos = torch.empty((3, npart), dtype=torch.float32)
+    for d in range(3):
+        blob = torch.randn(nblob, generator=g, dtype=torch.float64) + n_cells / 2.0
+        uni = torch.rand(npart - nblob, generator=g, dtype=torch.float64) * n_cells
+        pos[d] = torch.remainder(torch.cat([blob, uni]), float(n_cells)).to(torch.float32)
+    pos.clamp_(max=float(n_cells))
+    perm = torch.randperm(npart, generator=g)          # no favourable storage order
+    pos = pos[:, perm].contiguous()
+    vel = (torch.randn((3, npart), generator=g, dtype=torch.float32) * vel_sigma)
+    return pos, vel
+
+
 def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38, vel_sigma=VEL_SIGMA):
     """The same IC-like particle load (lattice + uniform(-2,2) jitter), generated on the GPU for ONE
     slab: only lattice planes that can land in the slab are visited, the jitter is a counter-based
@@ -503,7 +523,13 @@ def run_ours(args, rank, world, local_rank):
     pm.set_config(cfg)
     npart = n_parts ** 3
     mass = (n_cells / n_parts) ** 3
-    pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
+    if args.particles == "clustered":
+        pos_h, vel_h = make_particles_clustered(n_parts, n_cells)
+        particles_desc = ("clustered microbench load (BASELINE configs[4]): half in a 1-cell-rms Gaussian blob at the "
+                          "box centre, half uniform, shuffled; Gaussian velocities rms %g, seed 38" % VEL_SIGMA)
+    else:
+        pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
+        particles_desc = "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA
     pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
     plan = rt.get_plan(n_cells, npart, dev)
     sched = pm.loop_scale_factors(cfg)
@@ -601,9 +627,10 @@ def run_ours(args, rank, world, local_rank):
         "scaling": "strong" if world == 1 else "weak", "vs_baseline": published_ratio(value, n_parts, n_cells),
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step "
-                               "(CIC deposit + FFT Poisson + gather/kick/drift), BASELINE configs[1]",
+                               "(CIC deposit + FFT Poisson + gather/kick/drift), BASELINE "
+                               + ("configs[4] clustered microbench load" if args.particles == "clustered" else "configs[1]"),
                    "n_parts": n_parts, "n_cells": n_cells,
-                   "particles": "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA,
+                   "particles": particles_desc,
                    "sort": {"mode": sort_mode, "mover_fraction_last_step": sort_movers / max(sort_n, 1)},
                    "fft": {"fused_plane_passes": os.environ.get("PM_FFT_FUSE", "0") == "1",
                            "kernels": ("radix-8.8.8" if os.environ.get("PM_FFT_V2", "1") == "0" else
@@ -649,6 +676,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-parts", type=int, default=256)
     ap.add_argument("--n-cells", type=int, default=512)
+    ap.add_argument("--particles", default="ic", choices=["ic", "clustered"],
+                    help="N=1 workload: IC-like lattice+jitter (default, the metric's configuration) or the clustered "
+                         "microbench load of BASELINE configs[4] (per-stage times show deposit/sort/gather under skew)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="multi-GPU exploration runs: skip the host-buffer leg")
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
