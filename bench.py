@@ -624,7 +624,8 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if world == 1 else "weak", "vs_baseline": published_ratio(value, n_parts, n_cells),
+        "scaling": "strong" if world == 1 else "weak",
+        "vs_baseline": published_ratio(value, n_parts, n_cells) if args.particles == "ic" else None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step "
                                "(CIC deposit + FFT Poisson + gather/kick/drift), BASELINE "
