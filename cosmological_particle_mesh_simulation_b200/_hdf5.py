@@ -327,3 +327,186 @@ class Reader:
 def read(path):
     r = Reader(path)
     return {k: r[k] for k in r.keys()}
+
+
+# ------------------------------------------------------------------------------------------------
+# structural validator
+# ------------------------------------------------------------------------------------------------
+def check(path):
+    """Walk a file the way libhdf5 does when it opens every object, applying the consistency rules
+    its decoders enforce (format spec v1.1, sections II-IV; H5Fsuper, H5Oprefix/chunk, H5HL, H5B,
+    H5Gnode, H5S, H5T, H5Dlayout decode routines), plus one global rule: no two allocated regions
+    (superblock, object headers, B-tree nodes, heaps, symbol nodes, raw data) may overlap and all must
+    end before the end-of-file address.  Returns {name: (shape, dtype)}; raises ValueError on the first
+    violation.  Used by the tests on our own files AND on a libhdf5-written one, so the rules are
+    known not to be stricter than the library's."""
+    r = Reader(path)
+    b, base = r.b, r.base
+    regions = []
+
+    def need(cond, msg):
+        if not cond:
+            raise ValueError(f"{path}: {msg}")
+
+    def claim(addr, n, what):
+        need(addr != UNDEF, f"{what}: undefined address")
+        need(base + addr + n <= r.f_size, f"{what} [{addr}, {addr + n}) runs past the end of the file")
+        need(addr + n <= r.eof, f"{what} [{addr}, {addr + n}) runs past the end-of-file address {r.eof}")
+        regions.append((addr, addr + n, what))
+
+    ver = b[base + 8]            # (addresses below are relative to the base address)
+    need(ver in (0, 1), "superblock version")
+    need(b[base + 13] == 8 and b[base + 14] == 8, "sizes of offsets/lengths")
+    need(r.leaf_k > 0 and r.internal_k > 0, "group B-tree K values must be non-zero")
+    # libhdf5 refuses a file that is shorter than its stored end-of-file address ("truncated file")
+    need(r.eof <= r.f_size, f"file is shorter ({r.f_size}) than its end-of-file address ({r.eof})")
+    sb_len = 56 + (4 if ver == 1 else 0) + 40
+    regions.append((0, sb_len, "superblock"))
+    o = base + 24 + (4 if ver == 1 else 0) + 32
+    name_off, root_hdr, cache, _ = struct.unpack_from("<QQII", b, o)
+    need(cache in (0, 1), "root entry cache type")
+
+    def object_header(addr, what):
+        h = r._at(addr, 16)
+        v, _, nmsg, nlink, size = struct.unpack_from("<BBHII", h, 0)
+        need(v == 1, f"{what}: object header version {v}")
+        need(nlink >= 1, f"{what}: link count")
+        need(size % 8 == 0, f"{what}: header size {size} is not a multiple of 8")
+        claim(addr, 16 + size, what + " header")
+        blocks, out = [(addr + 16, size)], []
+        while blocks:
+            a, sz = blocks.pop(0)
+            blk, p = r._at(a, sz), 0
+            while p < sz:
+                need(p + 8 <= sz, f"{what}: {sz - p} stray bytes at the end of a header block")
+                mtype, msz, flags = struct.unpack_from("<HHB", blk, p)
+                need(msz % 8 == 0, f"{what}: message 0x{mtype:x} size {msz} is not a multiple of 8")
+                need(p + 8 + msz <= sz, f"{what}: message 0x{mtype:x} runs past its header block")
+                body = blk[p + 8:p + 8 + msz]
+                if mtype == _MSG_CONT:
+                    ca, cl = struct.unpack_from("<QQ", body, 0)
+                    claim(ca, cl, what + " continuation block")
+                    blocks.append((ca, cl))
+                out.append((mtype, body))
+                p += 8 + msz
+        need(len(out) == nmsg, f"{what}: header says {nmsg} messages, found {len(out)}")
+        return out
+
+    def heap(addr):
+        h = r._at(addr, 32)
+        need(h[:4] == b"HEAP" and h[4] == 0, "local heap signature/version")
+        size, free, data = struct.unpack_from("<QQQ", h, 8)
+        claim(addr, 32, "local heap header")
+        claim(data, size, "local heap data")
+        seg = r._at(data, size)
+        free_blocks, seen = [], set()
+        while free != 1:                                   # H5HL_FREE_NULL
+            need(free % 8 == 0 and free + 16 <= size and free not in seen, f"bad heap free-list offset {free}")
+            seen.add(free)
+            nxt, fsz = struct.unpack_from("<QQ", seg, free)
+            need(fsz >= 16 and free + fsz <= size, "heap free block size")
+            free_blocks.append((free, free + fsz))
+            free = nxt
+        need(seg[:1] == b"\0", "heap offset 0 must hold the empty name")
+        return seg, free_blocks
+
+    def group(btree, heap_addr, what):
+        seg, free_blocks = heap(heap_addr)
+        names = {}
+
+        def name_at(off):
+            need(off < len(seg), f"{what}: name offset {off} outside the heap")
+            end = seg.find(b"\0", off)
+            need(end >= 0, f"{what}: unterminated name")
+            need(not any(lo < end + 1 and off < hi for lo, hi in free_blocks), f"{what}: name overlaps a free heap block")
+            return seg[off:end]
+
+        def node(addr, level_expected=None):
+            h = r._at(addr, 8)
+            if h[:4] == b"SNOD":
+                need(h[4] == 1, "symbol node version")
+                n = struct.unpack_from("<H", h, 6)[0]
+                need(n <= 2 * r.leaf_k, f"symbol node holds {n} > 2*{r.leaf_k} entries")
+                claim(addr, 8 + 2 * r.leaf_k * 40, "symbol node")
+                body, prev, local = r._at(addr + 8, n * 40), None, []
+                for i in range(n):
+                    off, hdr, ctype = struct.unpack_from("<QQI", body, i * 40)
+                    nm = name_at(off)
+                    need(prev is None or prev < nm, f"{what}: symbol node entries not in ascending name order")
+                    need(ctype in (0, 1, 2), "symbol entry cache type")
+                    prev = nm
+                    names[nm.decode()] = hdr
+                    local.append(nm)
+                return local
+            need(h[:4] == b"TREE" and h[4] == 0, "group B-tree node signature/type")
+            level, used = h[5], struct.unpack_from("<H", h, 6)[0]
+            need(used <= 2 * r.internal_k, "B-tree entries used > 2K")
+            need(level_expected is None or level == level_expected, "B-tree level")
+            claim(addr, 24 + (2 * r.internal_k + 1) * 8 + 2 * r.internal_k * 8, "B-tree node")
+            body = r._at(addr + 24, (2 * used + 1) * 8)
+            last = None
+            for i in range(used):
+                key_lo, child, key_hi = struct.unpack_from("<QQQ", body, 16 * i)
+                got = node(child, level - 1 if level > 0 else None)
+                if got:
+                    need(name_at(key_lo) < got[0] or (i == 0 and name_at(key_lo) == b""), "B-tree left key must be below its child")
+                    need(name_at(key_hi) == got[-1], "B-tree right key must equal the child's largest name")
+                    need(last is None or last < got[0], "B-tree children out of order")
+                    last = got[-1]
+            return []
+
+        node(btree)
+        return names
+
+    msgs = object_header(root_hdr, "root group")
+    stab = [body for t, body in msgs if t == _MSG_SYMTAB]
+    need(len(stab) == 1, "root group needs exactly one symbol-table message")
+    btree, heap_addr = struct.unpack_from("<QQ", stab[0], 0)
+    if cache == 1:
+        need(struct.unpack_from("<QQ", b, o + 24) == (btree, heap_addr), "root entry scratch pad disagrees with the symbol-table message")
+    entries = group(btree, heap_addr, "root group")
+
+    out = {}
+    for name, hdr in entries.items():
+        msgs = object_header(hdr, f"dataset {name!r}")
+        kinds = [t for t, _ in msgs]
+        for t, label in ((_MSG_DATASPACE, "dataspace"), (_MSG_DATATYPE, "datatype"), (_MSG_LAYOUT, "layout")):
+            need(kinds.count(t) == 1, f"dataset {name!r}: needs exactly one {label} message")
+        space = next(body for t, body in msgs if t == _MSG_DATASPACE)
+        need(space[0] in (1, 2) and space[1] <= 32, "dataspace version/rank")
+        rank, flags = space[1], space[2]
+        need(flags & ~0x3 == 0, "dataspace flags")
+        dims_off = 8 if space[0] == 1 else 4
+        need(len(space) >= dims_off + 8 * rank * (2 if flags & 1 else 1), "dataspace message too short for its dimensions")
+        dt_body = next(body for t, body in msgs if t == _MSG_DATATYPE)
+        cls, vers = dt_body[0] & 0x0F, dt_body[0] >> 4
+        need(vers in (1, 2, 3), "datatype version")
+        dsize = struct.unpack_from("<I", dt_body, 4)[0]
+        if cls == 1:
+            boff, prec, epos, esize, mpos, msize, bias = struct.unpack_from("<HHBBBBI", dt_body, 8)
+            sign = dt_body[2]
+            need(boff + prec <= 8 * dsize, "float: precision exceeds the size")
+            need(sign < prec and epos + esize <= prec and mpos + msize <= prec, "float: field outside the precision")
+            need(mpos + msize <= epos or epos + esize <= mpos, "float: exponent and mantissa overlap")
+            need(not (epos <= sign < epos + esize) and not (mpos <= sign < mpos + msize), "float: sign bit inside a field")
+            need(bias == (1 << (esize - 1)) - 1, "float: exponent bias")
+        elif cls == 0:
+            boff, prec = struct.unpack_from("<HH", dt_body, 8)
+            need(boff + prec <= 8 * dsize, "integer: precision exceeds the size")
+        shape, dt, where, nbytes = r.info(name)
+        need(dt.itemsize == dsize, "datatype size")
+        lay = next(body for t, body in msgs if t == _MSG_LAYOUT)
+        if lay[0] == 3 and lay[1] == 1:
+            addr, size = struct.unpack_from("<QQ", lay, 2)
+            npts = int(np.prod(shape, dtype=np.int64)) if shape else 1
+            need(size == npts * dsize, f"dataset {name!r}: layout size {size} != {npts} x {dsize}")
+            if size:
+                claim(addr, size, f"dataset {name!r} raw data")
+        elif isinstance(where, int):
+            claim(where - base, nbytes, f"dataset {name!r} raw data")
+        out[name] = (shape, dt)
+
+    regions.sort()
+    for (a0, a1, w0), (b0, b1, w1) in zip(regions, regions[1:]):
+        need(a1 <= b0, f"{w0} [{a0}, {a1}) overlaps {w1} [{b0}, {b1})")
+    return out

@@ -65,6 +65,7 @@ def test_round_trip_all_supported_types(tmp_path):
         got = r[k]
         assert got.dtype == np.asarray(v).dtype and got.shape == np.asarray(v).shape, k
         assert np.array_equal(got, v), k
+    assert set(H.check(path)) == set(data)                         # passes the structural validator
     assert r["a"].shape == () and float(r.get("a")) == 0.123456789   # np.float32(hf.get('a')) works
     assert np.float32(r.get("a")) == np.float32(0.123456789)
 
@@ -167,6 +168,46 @@ def test_reader_on_a_file_written_by_libhdf5(tmp_path):
     assert ref[s_ref:s_ref + 8] == ours[s_ours:s_ours + 8]
 
 
+def test_validator_accepts_libhdf5_output_and_rejects_damaged_files(tmp_path):
+    """`_hdf5.check` applies the consistency rules of libhdf5's decoders.  It must accept the file
+    libhdf5 itself wrote (so it is not stricter than the library) and our files, and reject ours
+    once any of the fields those rules guard is damaged."""
+    if SCIPY_SAMPLE is not None:
+        assert list(H.check(SCIPY_SAMPLE)) == ["testdouble"]
+    path = str(tmp_path / "ok.hdf5")
+    names = ["x1", "x2", "x3", "vx1", "vx2", "vx3", "a", "density"]
+    H.write(path, [(n, np.full(5, i, dtype=np.float32)) for i, n in enumerate(names)])
+    assert sorted(H.check(path)) == sorted(names)
+    good = open(path, "rb").read()
+    r = H.Reader(path)
+    heap = good.index(b"HEAP")
+    snod = good.index(b"SNOD")
+    hdr = r.entries["x2"]
+
+    def damaged(label, edit):
+        b = bytearray(good)
+        edit(b)
+        q = str(tmp_path / (label + ".hdf5"))
+        open(q, "wb").write(bytes(b))
+        with pytest.raises(ValueError):
+            H.check(q)
+
+    damaged("msg_size", lambda b: struct.pack_into("<H", b, hdr + 16 + 2, 12))            # message size not 8-aligned
+    damaged("nmsgs", lambda b: struct.pack_into("<H", b, hdr + 2, 5))                      # message count mismatch
+    damaged("free_undef", lambda b: struct.pack_into("<Q", b, heap + 16, H.UNDEF))         # free list must end with 1
+    damaged("snod_count", lambda b: struct.pack_into("<H", b, snod + 6, 2 * H.LEAF_K + 1)) # too many symbols
+    def swap(b):                                                                           # names out of order
+        e0, e1 = bytes(b[snod + 8:snod + 48]), bytes(b[snod + 48:snod + 88])
+        b[snod + 8:snod + 48], b[snod + 48:snod + 88] = e1, e0
+    damaged("unsorted", swap)
+    lay = good.index(struct.pack("<HH", 0x8, 24), hdr)                                      # layout message of x2
+    damaged("layout_size", lambda b: struct.pack_into("<Q", b, lay + 8 + 10, 24))          # 5 x float32 is 20 bytes
+    damaged("layout_addr", lambda b: struct.pack_into("<Q", b, lay + 8 + 2, len(good) - 8))  # data past the end
+    damaged("overlap", lambda b: struct.pack_into("<Q", b, lay + 8 + 2, hdr))              # data on top of a header
+    damaged("truncated", lambda b: b.__delitem__(slice(len(b) - 16, len(b))))              # shorter than the EOF address
+    damaged("float_bias", lambda b: struct.pack_into("<I", b, good.index(bytes([0x11, 0x20, 31, 0]), hdr) + 16, 126))
+
+
 # ------------------------------------------------------------------------------------------------
 # save_file / from_file on host arrays
 # ------------------------------------------------------------------------------------------------
@@ -186,6 +227,7 @@ def test_save_file_and_from_file_follow_the_reference_arithmetic(tmp_path, monke
         S.save_file(rho, pos, vel, 5, a)
         assert os.path.exists("Data/data.5.hdf5") and not os.path.exists("Data/data.5.hdf5.part")
         hf = H.Reader("Data/data.5.hdf5")
+        assert len(H.check("Data/data.5.hdf5")) == 8                 # structurally valid, 8 datasets
         unit_conv_pos, unit_conv_vel = O.snapshot_units(a, cfg)      # src/save_data.py:10-11
         assert sorted(hf.keys()) == sorted(["density", "x1", "x2", "x3", "vx1", "vx2", "vx3", "a"])
         for i, n in enumerate(["x1", "x2", "x3"]):      # :19-21
@@ -288,6 +330,7 @@ if HAVE_HYPOTHESIS:
         r = H.Reader(path)
         assert sorted(r.keys()) == sorted(data)
         assert os.path.getsize(path) == struct.unpack_from("<Q", open(path, "rb").read(48), 40)[0]   # EOF address
+        assert set(H.check(path)) == set(data)
         for k, v in data.items():
             got = r[k]
             assert got.dtype == v.dtype and got.shape == v.shape
