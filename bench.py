@@ -398,6 +398,11 @@ def run_slab(args, rank, world, local_rank):
     ms_total = float(t.item())
     ms_per_step = ms_total / K
     value = npart * K / (ms_total * 1e-3)
+    # a flag wait that gave up (2 s) inside the timed steps would have let a kernel read stale data:
+    # report it instead of a silently wrong number (0 on a healthy run; the max over ranks)
+    tmo = torch.tensor([ranks[0].peer_timeouts() if transport != "nccl" else 0], dtype=torch.int64, device=f"cuda:{dev}")
+    dist.all_reduce(tmo, op=dist.ReduceOp.MAX)
+    peer_timeouts = int(tmo.item())
 
     e2e_value, ke = None, 0
     t = torch.zeros(3, dtype=torch.float64, device=f"cuda:{dev}")
@@ -494,6 +499,7 @@ def run_slab(args, rank, world, local_rank):
                               "formula": "(60*Np+64*Nc^3)/P/hbm + 2*(4*Nc^3/P)*(P-1)/P/900e9 (SURVEY 8e, serial bound)"},
             "phases_ms_rank0": phases,
             "mass_conservation_rel_err": mass_err,
+            "peer_flag_timeouts": peer_timeouts,
         }
         print(json.dumps(line), flush=True)
     slab.release_peers(ranks, comm)
