@@ -342,7 +342,8 @@ def run_slab(args, rank, world, local_rank):
         nonlocal step_i
         for _ in range(W):
             a, da = sched[step_i % len(sched)]
-            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=args.chunks or None, transport=transport)
+            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=args.chunks or None, transport=transport,
+                           ghosts=ghosts)
             step_i += 1
         barrier()
 
@@ -350,17 +351,21 @@ def run_slab(args, rank, world, local_rank):
     # setup_peers() ends with a flag handshake through the mapped memory and all ranks agree on the
     # outcome; if the set-up fails, or a flag wait times out during warm-up on any rank, every rank
     # rebuilds its state and runs the NCCL all-to-all path instead -- and the JSON line says which.
-    transport, transport_note = "nccl", ""
+    transport, transport_note, ghosts = "nccl", "", "nccl"
     if args.transport != "nccl":
         transport = (args.transport if args.transport in ("peer", "fused2") else "fused") if slab.setup_peers(ranks, comm) else "nccl"
         if transport == "nccl":
             transport_note = "peer-memory set-up failed; "
+    if args.ghosts == "peer":
+        if transport == "nccl" or not slab.setup_ghost_peers(ranks, comm):
+            raise RuntimeError("--ghosts peer needs a working peer-memory set-up")
+        ghosts = "peer"
     warm_up(transport)
     if transport != "nccl":
         bad = torch.tensor([ranks[0].peer_timeouts()], dtype=torch.int64, device=f"cuda:{dev}")
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
         if int(bad.item()):
-            transport, transport_note = "nccl", "peer-memory flag wait timed out in warm-up; "
+            transport, transport_note, ghosts = "nccl", "peer-memory flag wait timed out in warm-up; ", "nccl"
             slab.release_peers(ranks, comm)
             for r in ranks:
                 r.close()
@@ -385,7 +390,7 @@ def run_slab(args, rank, world, local_rank):
     for _ in range(K):
         a, da = sched[step_i % len(sched)]
         slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, timer=timer, chunks=args.chunks or None,
-                       transport=transport)
+                       transport=transport, ghosts=ghosts)
         step_i += 1
     ev1.record()
     barrier()
@@ -437,7 +442,7 @@ def run_slab(args, rank, world, local_rank):
             di = hid.to(f"cuda:{dev}", non_blocking=True)
             h2d += n_host * 4 * 7
             sr.load(dp, dv, di)
-            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, transport=transport)
+            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, transport=transport, ghosts=ghosts)
             p, v, ids = sr.export()
             n_host = p.shape[1]
             hp, hv, hid = host_views(n_host)
@@ -485,7 +490,7 @@ def run_slab(args, rank, world, local_rank):
                                          "nccl": "FFT transposes by NCCL all-to-all, "}[transport]
                                       + f"pipelined in {chunks} kx chunks" + ("" if transport == "fused" else " on two streams")
                                       + ", all-to-all-v particle migration",
-                       "fft_transport": transport_note + transport},
+                       "fft_transport": transport_note + transport, "ghost_planes": ghosts},
             "clocks": clocks,
             "e2e": None if e2e_value is None else {
                     "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
@@ -691,6 +696,8 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
     ap.add_argument("--transport", default="auto", choices=["auto", "fused", "fused2", "peer", "nccl"],
                     help="FFT transposes of the multi-GPU path: peer-memory copy kernels or NCCL all-to-all")
+    ap.add_argument("--ghosts", default="nccl", choices=["nccl", "peer"],
+                    help="multi-GPU ghost planes: NCCL send/recv (default) or EXPERIMENTAL pushes through peer memory")
     ap.add_argument("--reference-budget-s", type=float, default=90.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -124,6 +124,13 @@ def lib():
             "pm_slab_fft_push": (i32, [vp, i32, i32, vp]),
             "pm_slab_fft_pull": (i32, [vp, i32, i32, vp]),
             "pm_slab_fft_y_inverse_local": (i32, [vp, i32, i32, vp]),
+            "pm_slab_peer_ghost_export": (i32, [vp, ctypes.POINTER(ctypes.c_uint64)]),
+            "pm_slab_peer_ghost_import": (i32, [vp, i32, ctypes.c_uint64]),
+            "pm_slab_peer_ghost_set": (i32, [vp, i32, vp]),
+            "pm_slab_ghost_push_rho": (i32, [vp, vp]),
+            "pm_slab_ghost_wait_rho": (i32, [vp, vp]),
+            "pm_slab_ghost_push_phi": (i32, [vp, vp]),
+            "pm_slab_ghost_wait_phi": (i32, [vp, vp]),
             "pm_slab_fft_y_forward_push": (i32, [vp, i32, i32, vp]),
             "pm_slab_fft_y_inverse_pull": (i32, [vp, i32, i32, vp]),
             "pm_ic_workspace_bytes": (sz, [i32]),
@@ -155,7 +162,9 @@ EXPORTED_SYMBOLS = (
     "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export",
     "pm_slab_peer_export", "pm_slab_peer_import", "pm_slab_peer_set", "pm_slab_peer_signal", "pm_slab_peer_wait",
     "pm_slab_peer_timeouts", "pm_slab_peer_release", "pm_slab_fft_y_forward_local", "pm_slab_fft_push", "pm_slab_fft_pull",
-    "pm_slab_fft_y_inverse_local", "pm_slab_fft_y_forward_push", "pm_slab_fft_y_inverse_pull", "pm_power_spectrum",
+    "pm_slab_fft_y_inverse_local", "pm_slab_fft_y_forward_push", "pm_slab_fft_y_inverse_pull",
+    "pm_slab_peer_ghost_export", "pm_slab_peer_ghost_import", "pm_slab_peer_ghost_set", "pm_slab_ghost_push_rho",
+    "pm_slab_ghost_wait_rho", "pm_slab_ghost_push_phi", "pm_slab_ghost_wait_phi", "pm_power_spectrum",
     "pm_plan_set_sort_mode", "pm_plan_sort_stats", "pm_plan_set_fft_fuse", "pm_plan_fft_sync_errors",
     "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled", "pm_ic_workspace_bytes", "pm_ic_noise",
     "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",

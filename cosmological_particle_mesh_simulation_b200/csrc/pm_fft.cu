@@ -1275,6 +1275,35 @@ __global__ void k_peer_wait_impl(uint32_t *flags, int nranks, int slot, uint32_t
     __threadfence_system();
 }
 
+// Neighbour-only variants for the ghost planes: one flag word to one rank, wait for one rank.
+__global__ void k_peer_signal_one(uint32_t *word, uint32_t epoch)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(word) = epoch;
+}
+
+__global__ void k_peer_wait_one(uint32_t *flags, int slot, int src, uint32_t epoch)
+{
+    const volatile uint32_t *w = flags + (size_t)slot * PM_PEER_MAX + src;
+    unsigned long long t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(*w - epoch) < 0) {
+        __nanosleep(100);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 2000000000ull) {
+            atomicAdd(flags + (size_t)PM_PEER_SLOTS * PM_PEER_MAX, 1u);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) k_peer_put(float4 *__restrict__ dst, const float4 *__restrict__ src, size_t n4)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 template <int N>
 int slab_y_peer(pm_plan *p, int c, int C, bool fwd, cudaStream_t st)
 {
@@ -1530,6 +1559,31 @@ int pm_k_peer_signal(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st)
 int pm_k_peer_wait(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st)
 {
     PM_LAUNCH(k_peer_wait_impl, 1, 32, 0, st, p->peer_flags, p->nranks, slot, epoch);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+int pm_k_peer_put(pm_plan *p, float *dst, const float *src, size_t nfloat, cudaStream_t st)
+{
+    const size_t n4 = nfloat / 4;      // planes: nc*nc floats, nc a multiple of 16
+    const size_t want = (n4 + 255) / 256;
+    const int grid = (int)(want < (size_t)p->sm_count * 4 ? want : (size_t)p->sm_count * 4);
+    PM_LAUNCH(k_peer_put, grid, 256, 0, st, reinterpret_cast<float4 *>(dst), reinterpret_cast<const float4 *>(src), n4);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+int pm_k_peer_signal_to(pm_plan *p, int slot, int dst_rank, uint32_t epoch, cudaStream_t st)
+{
+    uint32_t *word = p->peer_flag_of[dst_rank] + (size_t)slot * PM_PEER_MAX + p->rank;
+    PM_LAUNCH(k_peer_signal_one, 1, 1, 0, st, word, epoch);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+int pm_k_peer_wait_from(pm_plan *p, int slot, int src_rank, uint32_t epoch, cudaStream_t st)
+{
+    PM_LAUNCH(k_peer_wait_one, 1, 1, 0, st, p->peer_flags, slot, src_rank, epoch);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }

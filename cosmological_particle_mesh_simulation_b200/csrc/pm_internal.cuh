@@ -39,7 +39,10 @@ extern int g_pm_last_cufft;
     } while (0)
 
 #define PM_PEER_MAX 16
-#define PM_PEER_SLOTS 16
+#define PM_PEER_SLOTS 24      // 0..7 "chunk pushed", 8..15 "z pass done", 16..18 ghost planes (pm_slab_ghost_*)
+#define PM_SLOT_GHOST_RHO 16  // density ghost plane written into rank+1
+#define PM_SLOT_GHOST_PHI_UP 17   // my last phi plane written into rank+1
+#define PM_SLOT_GHOST_PHI_DN 18   // my first two phi planes written into rank-1
 
 struct pm_plan {
     int nc;           // N_CELLS
@@ -126,6 +129,8 @@ struct pm_plan {
     void *peer_ipc[PM_PEER_MAX];            // cudaIpcOpenMemHandle mappings to close
     uint32_t peer_epoch_sig[PM_PEER_SLOTS], peer_epoch_wait[PM_PEER_SLOTS];
     int peers_set;                          // how many of the nranks entries are filled in
+    float *peer_mesh2[PM_PEER_MAX];         // rank s's phi buffer (ghost planes pushed through peer memory)
+    int ghosts_set;
 
     // optional per-stage timing of pm_step (pm_plan_profile_begin/read)
     cudaEvent_t *prof_ev;   // prof_cap * (PM_NUM_STAGES + 1) events
@@ -194,6 +199,10 @@ int pm_k_fft_slab_y_fwd_push(pm_plan *p, int c, int C, cudaStream_t st);
 int pm_k_fft_slab_y_inv_pull(pm_plan *p, int c, int C, cudaStream_t st);
 int pm_k_peer_signal(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st);
 int pm_k_peer_wait(pm_plan *p, int slot, uint32_t epoch, cudaStream_t st);
+// ghost planes through peer memory: plane copy into a neighbour + flag to that neighbour only
+int pm_k_peer_put(pm_plan *p, float *dst, const float *src, size_t nfloat, cudaStream_t st);
+int pm_k_peer_signal_to(pm_plan *p, int slot, int dst_rank, uint32_t epoch, cudaStream_t st);
+int pm_k_peer_wait_from(pm_plan *p, int slot, int src_rank, uint32_t epoch, cudaStream_t st);
 int pm_fft_cols_per_tile(int nc);
 int pm_k_power_spectrum(pm_plan *p, const float *rho, int nbins, double *psum, double *pcnt,
                         cudaStream_t st);

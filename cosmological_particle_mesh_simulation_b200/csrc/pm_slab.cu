@@ -262,8 +262,10 @@ int pm_slab_peer_release(pm_plan *p)
         p->peer_ipc[s] = nullptr;
         p->peer_recv[s] = nullptr;
         p->peer_flag_of[s] = nullptr;
+        p->peer_mesh2[s] = nullptr;
     }
     p->peers_set = 0;
+    p->ghosts_set = 0;
     return PM_OK;
 }
 
@@ -276,6 +278,77 @@ int pm_slab_peer_timeouts(pm_plan *p, uint32_t *timeouts)
     if (rc != PM_OK) return rc;
     PM_CUDA(cudaMemcpy(timeouts, p->peer_flags + (size_t)PM_PEER_SLOTS * PM_PEER_MAX, 4, cudaMemcpyDeviceToHost));
     return PM_OK;
+}
+
+// ---- ghost planes through the same peer mappings (EXPERIMENTAL: not yet validated on hardware) ----
+// Instead of ncclSend/Recv: copy the plane into the neighbour's phi buffer, then one flag word to that
+// neighbour; the neighbour waits for that one word.  The density ghost lands in the neighbour's phi
+// plane 0 (dead at that time), exactly where the NCCL path receives it.
+int pm_slab_peer_ghost_export(pm_plan *p, uint64_t *mesh2_offset)
+{
+    if (!p || !p->slab || !mesh2_offset) return PM_ERR_INVALID;
+    *mesh2_offset = (uint64_t)((char *)p->mesh2 - p->ws);
+    return PM_OK;
+}
+
+static int ghost_store(pm_plan *p, int peer, void *mesh2)
+{
+    if (!p->peer_mesh2[peer]) ++p->ghosts_set;
+    p->peer_mesh2[peer] = (float *)mesh2;
+    return PM_OK;
+}
+
+// after pm_slab_peer_import(peer): uses that mapping
+int pm_slab_peer_ghost_import(pm_plan *p, int peer, uint64_t mesh2_offset)
+{
+    if (!p || !p->slab || peer < 0 || peer >= p->nranks || peer >= PM_PEER_MAX) return PM_ERR_INVALID;
+    if (peer == p->rank) return ghost_store(p, peer, p->mesh2);
+    if (!p->peer_ipc[peer]) return PM_ERR_INVALID;
+    return ghost_store(p, peer, (char *)p->peer_ipc[peer] + mesh2_offset);
+}
+
+int pm_slab_peer_ghost_set(pm_plan *p, int peer, void *mesh2)
+{
+    if (!p || !p->slab || peer < 0 || peer >= p->nranks || peer >= PM_PEER_MAX || !mesh2) return PM_ERR_INVALID;
+    return ghost_store(p, peer, mesh2);
+}
+
+#define PM_GHOST_READY (p->peers_set == p->nranks && p->ghosts_set == p->nranks)
+
+int pm_slab_ghost_push_rho(pm_plan *p, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(PM_GHOST_READY);
+    const size_t plane = (size_t)p->nc * p->nc;
+    const int up = (p->rank + 1) % p->nranks;
+    PM_TRY(pm_k_peer_put(p, p->peer_mesh2[up], p->mesh + plane * p->nzl, plane, st));
+    return pm_k_peer_signal_to(p, PM_SLOT_GHOST_RHO, up, ++p->peer_epoch_sig[PM_SLOT_GHOST_RHO], st);
+}
+
+int pm_slab_ghost_wait_rho(pm_plan *p, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(PM_GHOST_READY);
+    const int dn = (p->rank + p->nranks - 1) % p->nranks;
+    return pm_k_peer_wait_from(p, PM_SLOT_GHOST_RHO, dn, ++p->peer_epoch_wait[PM_SLOT_GHOST_RHO], st);
+}
+
+int pm_slab_ghost_push_phi(pm_plan *p, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(PM_GHOST_READY);
+    const size_t plane = (size_t)p->nc * p->nc;
+    const int up = (p->rank + 1) % p->nranks, dn = (p->rank + p->nranks - 1) % p->nranks;
+    // my last owned plane is rank+1's plane z0-1; my first two owned planes close rank-1's stencil
+    PM_TRY(pm_k_peer_put(p, p->peer_mesh2[up], p->mesh2 + plane * p->nzl, plane, st));
+    PM_TRY(pm_k_peer_signal_to(p, PM_SLOT_GHOST_PHI_UP, up, ++p->peer_epoch_sig[PM_SLOT_GHOST_PHI_UP], st));
+    PM_TRY(pm_k_peer_put(p, p->peer_mesh2[dn] + plane * (p->nzl + 1), p->mesh2 + plane, 2 * plane, st));
+    return pm_k_peer_signal_to(p, PM_SLOT_GHOST_PHI_DN, dn, ++p->peer_epoch_sig[PM_SLOT_GHOST_PHI_DN], st);
+}
+
+int pm_slab_ghost_wait_phi(pm_plan *p, pm_stream_t stream)
+{
+    PM_SLAB_ENTER(PM_GHOST_READY);
+    const int up = (p->rank + 1) % p->nranks, dn = (p->rank + p->nranks - 1) % p->nranks;
+    PM_TRY(pm_k_peer_wait_from(p, PM_SLOT_GHOST_PHI_UP, dn, ++p->peer_epoch_wait[PM_SLOT_GHOST_PHI_UP], st));
+    return pm_k_peer_wait_from(p, PM_SLOT_GHOST_PHI_DN, up, ++p->peer_epoch_wait[PM_SLOT_GHOST_PHI_DN], st);
 }
 
 int pm_slab_fft_y_forward_local(pm_plan *p, int c, int C, pm_stream_t stream)

@@ -81,6 +81,7 @@ class SlabRank:
                       MIG_RECV=(torch.float32, (-1, 7)), LEAVE_COUNTS=(torch.int32, (P,)),
                       PEER_FLAGS=(torch.int32, (-1, 16)))
         self.peers_ready = False
+        self.ghosts_ready = False
         for name, which in BUF.items():
             ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
             rt.check(rt.lib().pm_slab_buffer(self.handle, which, ctypes.byref(ptr), ctypes.byref(nbytes)),
@@ -170,6 +171,7 @@ class SlabRank:
         return int(n.value)
 
     def peer_release(self):
+        self.ghosts_ready = False
         if getattr(self, "handle", None):
             with torch.cuda.device(self.device):
                 torch.cuda.synchronize()
@@ -190,6 +192,19 @@ class SlabRank:
 
     def fft_pull(self, c, C):
         self._call("pm_slab_fft_pull", int(c), int(C))
+
+    # ghost planes through peer memory (experimental; pm_slab_ghost_*)
+    def ghost_push_rho(self):
+        self._call("pm_slab_ghost_push_rho")
+
+    def ghost_wait_rho(self):
+        self._call("pm_slab_ghost_wait_rho")
+
+    def ghost_push_phi(self):
+        self._call("pm_slab_ghost_push_phi")
+
+    def ghost_wait_phi(self):
+        self._call("pm_slab_ghost_wait_phi")
 
     def fft_y_forward_push(self, c, C):
         self._call("pm_slab_fft_y_forward_push", int(c), int(C))
@@ -404,6 +419,38 @@ def setup_peers(ranks, comm):
     return r.peers_ready
 
 
+def setup_ghost_peers(ranks, comm):
+    """EXPERIMENTAL (not yet validated on hardware).  After setup_peers(): also publish where every
+    rank's phi buffer lives, so slab_step(ghosts="peer") can push the density and potential ghost
+    planes into the neighbours' memory instead of NCCL send/recv.  Returns True when usable."""
+    if not all(r.peers_ready for r in ranks):
+        return False
+    if isinstance(comm, LocalComm):
+        for r in ranks:
+            for s in ranks:
+                rt.check(rt.lib().pm_slab_peer_ghost_set(r.handle, s.rank, ctypes.c_void_p(s.buf["PHI_LO_RECV"].data_ptr())),
+                         "pm_slab_peer_ghost_set")
+        for r in ranks:
+            r.ghosts_ready = True
+        return True
+    dist, r = comm.dist, ranks[0]
+    off = ctypes.c_uint64()
+    rt.check(rt.lib().pm_slab_peer_ghost_export(r.handle, ctypes.byref(off)), "pm_slab_peer_ghost_export")
+    table = [None] * comm.nranks
+    dist.all_gather_object(table, int(off.value), group=comm.group)
+    ok = 1
+    try:
+        for s, o in enumerate(table):
+            rt.check(rt.lib().pm_slab_peer_ghost_import(r.handle, s, int(o)), "pm_slab_peer_ghost_import")
+    except Exception:
+        ok = 0
+    dev = r.buf["RHO"].device if dist.get_backend(comm.group) == "nccl" else "cpu"
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
+    r.ghosts_ready = bool(int(flag.item()))
+    return r.ghosts_ready
+
+
 def release_peers(ranks, comm):
     """Unmap the other ranks' buffers on every rank, then a barrier: call before closing the ranks
     of a DistComm run (memory must not be freed while another process still has it mapped)."""
@@ -463,14 +510,16 @@ def default_chunks(n_cells, nranks=1, transport="nccl"):
     return 1
 
 
-def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, transport=None):
+def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, transport=None, ghosts="nccl"):
     """One body of the loop src/pmesh.py:60-61 across the slabs.  `ranks`: the SlabRank objects
     of comm.local_ranks (one for DistComm, all P for LocalComm).  The distributed FFT runs as a
     pipeline of `chunks` kx chunks: with DistComm on GPUs the transposes go to a second stream
     and overlap the y and z passes of the neighbouring chunks.  transport: "fused" = the y passes
     themselves store into / load from the other ranks' z-pass arrays over NVLink (one stream, no
     copy kernel; needs setup_peers), "peer" = separate push / pull copy kernels on the second
-    stream, "nccl" = pack -> all-to-all -> unpack; default: "fused" when the ranks are set up for it."""
+    stream, "nccl" = pack -> all-to-all -> unpack; default: "fused" when the ranks are set up for it.
+    ghosts: "nccl" = send/recv of the ghost planes (default), "peer" = EXPERIMENTAL pushes through the
+    peer mappings (needs setup_ghost_peers)."""
     cfg = cfg or rt.config()
     if timer:
         timer.begin_step()
@@ -491,7 +540,17 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
     for r in ranks:
         r.deposit(mass)
     mark("deposit")
-    comm.shift(B("RHO_GHOST_SEND"), B("RHO_GHOST_RECV"), +1)
+    if ghosts not in ("nccl", "peer"):
+        raise ValueError(f"unknown ghosts mode {ghosts!r}")
+    if ghosts == "peer" and not all(r.ghosts_ready for r in ranks):
+        raise RuntimeError("ghosts='peer' needs slab.setup_ghost_peers(ranks, comm) first")
+    if ghosts == "peer":
+        for r in ranks:
+            r.ghost_push_rho()
+        for r in ranks:
+            r.ghost_wait_rho()
+    else:
+        comm.shift(B("RHO_GHOST_SEND"), B("RHO_GHOST_RECV"), +1)
     for r in ranks:
         r.ghost_add()
     mark("rho_ghost")
@@ -643,8 +702,14 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
         r.fft_rows_inverse()
     mark("fft_distributed")
 
-    comm.shift(B("PHI_HI_SEND"), B("PHI_LO_RECV"), +1)    # my last plane is rank+1's plane z0-1
-    comm.shift(B("PHI_LO_SEND"), B("PHI_HI_RECV"), -1)    # my first two planes close rank-1's stencil
+    if ghosts == "peer":
+        for r in ranks:
+            r.ghost_push_phi()
+        for r in ranks:
+            r.ghost_wait_phi()
+    else:
+        comm.shift(B("PHI_HI_SEND"), B("PHI_LO_RECV"), +1)    # my last plane is rank+1's plane z0-1
+        comm.shift(B("PHI_LO_SEND"), B("PHI_HI_RECV"), -1)    # my first two planes close rank-1's stencil
     mark("phi_ghost")
     for r in ranks:
         r.gather(a, f_a1, da)

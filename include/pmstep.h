@@ -229,7 +229,7 @@ PM_API int64_t pm_particles_count(const pm_plan *plan);
 #define PM_BUF_MIG_SEND 12       /* float[.][7]          (x,y,z,vx,vy,vz,id) of leavers, by dest   */
 #define PM_BUF_MIG_RECV 13       /* float[.][7]          arrivals                                  */
 #define PM_BUF_LEAVE_COUNTS 14   /* uint32[P]            leavers per destination (after gather)    */
-#define PM_BUF_PEER_FLAGS 15     /* uint32[17][16]       flag words of the peer-memory transposes  */
+#define PM_BUF_PEER_FLAGS 15     /* uint32[25][16]       flag words of the peer-memory exchanges   */
 PM_API int pm_plan_create_slab(pm_plan **plan, int n_cells, int64_t np_capacity, int device, int rank,
                                int nranks);
 PM_API int pm_slab_buffer(pm_plan *plan, int which, void **ptr, size_t *bytes);
@@ -274,6 +274,19 @@ PM_API int pm_slab_fft_y_inverse_local(pm_plan *plan, int chunk, int nchunks, pm
  * the inverse y pass loads its input from them -- no copy kernel at all (same signal/wait calls). */
 PM_API int pm_slab_fft_y_forward_push(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
 PM_API int pm_slab_fft_y_inverse_pull(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
+/* EXPERIMENTAL (not yet validated on hardware): ghost planes through the same peer mappings instead of
+ * NCCL send/recv.  push = copy the plane(s) into the neighbour's phi buffer + one flag word to that
+ * neighbour; wait = poll that one word.  Set-up: pm_slab_peer_ghost_export -> exchange ->
+ * pm_slab_peer_ghost_import (after pm_slab_peer_import), or pm_slab_peer_ghost_set with the address
+ * of PM_BUF_PHI_LO_RECV for plans in one process.  Per step: deposit, push_rho, wait_rho, ghost_add,
+ * transform, push_phi, wait_phi, gather. */
+PM_API int pm_slab_peer_ghost_export(pm_plan *plan, uint64_t *mesh2_offset);
+PM_API int pm_slab_peer_ghost_import(pm_plan *plan, int peer, uint64_t mesh2_offset);
+PM_API int pm_slab_peer_ghost_set(pm_plan *plan, int peer, void *phi_lo_recv);
+PM_API int pm_slab_ghost_push_rho(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_ghost_wait_rho(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_ghost_push_phi(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_ghost_wait_phi(pm_plan *plan, pm_stream_t stream);
 PM_API int pm_slab_gather(pm_plan *plan, double a, double f_a1, double da, pm_stream_t stream);
 PM_API int pm_slab_migrate_pack(pm_plan *plan, const int64_t *counts_h, pm_stream_t stream);
 PM_API int pm_slab_migrate_unpack(pm_plan *plan, int64_t n_arrive, int64_t n_leave, pm_stream_t stream);

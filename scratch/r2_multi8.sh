@@ -11,6 +11,7 @@ run c4_peer_c4   --steps 5 --warmup 3 --n-parts 1024 --n-cells 2048 --transport 
 run c4_fused2_c2 --steps 5 --warmup 3 --n-parts 1024 --n-cells 2048 --transport fused2 --chunks 2
 run c2_fused2_c2 --steps 20 --warmup 3 --transport fused2 --chunks 2
 run c2_peer_c1   --steps 20 --warmup 3 --transport peer --chunks 1
+run c2_fused_gp  --steps 20 --warmup 3 --transport fused --ghosts peer     # after PM_TEST_EXPERIMENTAL=1 pytest passed on one GPU
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/x_*.json')):

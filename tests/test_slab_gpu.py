@@ -179,6 +179,34 @@ def test_peer_transport_through_cuda_ipc_two_processes_one_gpu(tmp_path):
     assert out.stdout.count("-ok") == 2, out.stdout
 
 
+@pytest.mark.skipif(__import__("os").environ.get("PM_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental paths (ghost planes through peer memory, two-stream fused schedule): "
+                           "written without GPU time left in round 1 -- run with PM_TEST_EXPERIMENTAL=1 to validate them")
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_experimental_ghost_pushes_and_two_stream_schedule_are_bit_identical(pm, P):
+    n_parts, n_cells = 64, 128
+    cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
+    pm.set_config(cfg)
+    pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=5, vel_rms=0.5)
+    outs = []
+    for transport, ghosts in (("fused", "nccl"), ("fused", "peer"), ("fused2", "peer"), ("nccl", "peer")):
+        pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
+        comm = pm.slab.LocalComm(P)
+        ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
+        assert pm.slab.setup_peers(ranks, comm) and pm.slab.setup_ghost_peers(ranks, comm)
+        for s in range(4):
+            pm.slab.slab_step(ranks, comm, 0.4 + 0.0099 * s, 0.0099, mass=8.0, cfg=cfg, chunks=(1, 2, 2, 1)[s],
+                              transport=transport, ghosts=ghosts)
+        assert all(r.peer_timeouts() == 0 for r in ranks)
+        phi = torch.cat([r.buf["PHI"] for r in ranks]).clone()
+        outs.append(pm.slab.collect(ranks, comm, pos.shape[1]) + (phi,))
+        for r in ranks:
+            r.close()
+    for other in outs[1:]:
+        for x, y in zip(outs[0], other):
+            assert torch.equal(x, y)
+
+
 def test_slab_run_is_deterministic(pm):
     n_parts, n_cells, P = 32, 64, 2
     cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)

@@ -17,6 +17,15 @@ distributed transform must be ordered in all of them:
   H1  a rank's z pass of chunk c runs after EVERY rank has delivered its block of chunk c;
   H2  a rank fetches chunk c back only after EVERY rank has finished its z pass of chunk c;
   H3  no rank stores step n+1's chunk c into the z-pass arrays before EVERY rank has fetched step n's.
+
+and, with the ghost planes pushed through peer memory (ghosts="peer", experimental):
+
+  H4  ghost_add runs after rank-1 delivered this step's density ghost plane;
+  H5  the gather runs after both neighbours delivered this step's potential ghost planes;
+  H6  a neighbour's density ghost (and its two upper potential planes) land in a rank's phi buffer only
+      after that rank's gather of the previous step has read it;
+  H7  rank-1's potential plane lands on phi plane 0 only after this step's ghost_add has read the density
+      ghost from there.
 """
 import contextlib
 import itertools
@@ -72,10 +81,10 @@ class RankRecorder:
     KERNELS = ["deposit", "ghost_add", "fft_rows_forward", "fft_y_forward", "fft_z", "fft_y_inverse",
                "fft_rows_inverse", "fft_y_forward_local", "fft_push", "fft_pull", "fft_y_inverse_local",
                "fft_y_forward_push", "fft_y_inverse_pull", "gather", "migrate_pack", "migrate_unpack",
-               "signal", "wait"]
+               "ghost_push_rho", "ghost_wait_rho", "ghost_push_phi", "ghost_wait_phi", "signal", "wait"]
 
     def __init__(self, rank, nranks, n_cells=512):
-        self.rank, self.nranks, self.n_cells, self.peers_ready = rank, nranks, n_cells, True
+        self.rank, self.nranks, self.n_cells, self.peers_ready, self.ghosts_ready = rank, nranks, n_cells, True, True
         self.buf = {k: (k, rank) for k in slab.BUF}
         self.main, self.side = Stream("main"), Stream("side")
         self.current = self.main
@@ -122,7 +131,7 @@ class CommRecorder:
         self._coll("a2av", range(self.nranks))
 
 
-def record_program(P, steps, transport, chunks, two_streams, monkeypatch):
+def record_program(P, steps, transport, chunks, two_streams, monkeypatch, ghosts="nccl"):
     """Run slab_step `steps` times for each rank against the recorders -> per-rank op queues."""
     monkeypatch.setattr(slab, "torch", types.SimpleNamespace(cuda=FakeCuda))
     cfg = types.SimpleNamespace(N_CELLS=512, N_PARTS=256, H0=0.68, OMEGA_LAMBDA0=0.69, OMEGA_K0=0.0, OMEGA_M0=0.31)
@@ -132,7 +141,8 @@ def record_program(P, steps, transport, chunks, two_streams, monkeypatch):
         FakeCuda.state = rec
         comm = CommRecorder(rec, two_streams)
         for s in range(steps):
-            slab.slab_step([rec], comm, 0.1 + 0.01 * s, 0.01, mass=8.0, cfg=cfg, chunks=chunks, transport=transport)
+            slab.slab_step([rec], comm, 0.1 + 0.01 * s, 0.01, mass=8.0, cfg=cfg, chunks=chunks, transport=transport,
+                           ghosts=ghosts)
         ranks.append(rec)
     return ranks
 
@@ -156,6 +166,10 @@ def execute(ranks, transport, chunks, rng):
     coll_done = [0] * P                                                   # collectives completed per rank (issue order)
     step = [0] * P                                                        # deposits executed
     delivered, z_done, fetched = {}, {}, {}                               # (step, c) -> set of ranks
+    gflag = {}                                                            # (owner, kind) -> pushes received
+    gwaited = {}                                                          # (rank, stream, pc) -> epochs awaited
+    gcount = [[0, 0] for _ in range(P)]                                   # ghost waits issued per rank (rho, phi)
+    added, gathered = [0] * P, [0] * P                                    # ghost_add / gather executed per rank
 
     def mark(table, key, r):
         table.setdefault(key, set()).add(r)
@@ -177,6 +191,14 @@ def execute(ranks, transport, chunks, rng):
                 wait_count[r][slot] += 1
                 wait_epoch[key] = wait_count[r][slot]
             return all(flags[r][slot][s] >= wait_epoch[key] for s in range(P))
+        if op[0] == "kernel" and op[1] in ("ghost_wait_rho", "ghost_wait_phi"):
+            which = 0 if op[1] == "ghost_wait_rho" else 1
+            key = (r, sname, i)
+            if key not in gwaited:
+                gcount[r][which] += 1
+                gwaited[key] = gcount[r][which]
+            kinds = ("rho",) if which == 0 else ("phi_up", "phi_dn")
+            return all(gflag.get((r, k), 0) >= gwaited[key] for k in kinds)
         if op[0] == "collective":
             _, kind, peers, seq = op
             if seq != coll_done[r]:
@@ -200,8 +222,28 @@ def execute(ranks, transport, chunks, rng):
         elif op[0] == "kernel":
             name, c = op[1], op[2]
             n = step[r]
+            up, dn = (r + 1) % P, (r - 1) % P
             if name == "deposit":
                 step[r] += 1
+            elif name == "ghost_push_rho":
+                if gathered[up] < n - 1:
+                    raise Hazard(f"H6: rank {r} writes step {n}'s density ghost into rank {up} before its gather of step {n - 1}")
+                gflag[(up, "rho")] = gflag.get((up, "rho"), 0) + 1
+            elif name == "ghost_add":
+                if any(o[1] == "ghost_push_rho" for o in q) and gflag.get((r, "rho"), 0) < n:
+                    raise Hazard(f"H4: rank {r} adds the density ghost of step {n} before it arrived")
+                added[r] += 1
+            elif name == "ghost_push_phi":
+                if added[up] < n:
+                    raise Hazard(f"H7: rank {r} overwrites rank {up}'s phi plane 0 before its ghost_add of step {n}")
+                if gathered[dn] < n - 1:
+                    raise Hazard(f"H6: rank {r} writes potential planes into rank {dn} before its gather of step {n - 1}")
+                gflag[(up, "phi_up")] = gflag.get((up, "phi_up"), 0) + 1
+                gflag[(dn, "phi_dn")] = gflag.get((dn, "phi_dn"), 0) + 1
+            elif name == "gather":
+                if any(o[1] == "ghost_push_phi" for o in q) and min(gflag.get((r, "phi_up"), 0), gflag.get((r, "phi_dn"), 0)) < n:
+                    raise Hazard(f"H5: rank {r} gathers step {n} before its potential ghost planes arrived")
+                gathered[r] += 1
             elif name in ("fft_push", "fft_y_forward_push"):
                 if n > 1 and not full(fetched, (n - 1, c)):
                     raise Hazard(f"H3: rank {r} stores step {n} chunk {c} before everyone fetched step {n - 1}'s")
@@ -249,6 +291,39 @@ def test_schedule_drains_and_orders_its_hazards(monkeypatch, P, transport, chunk
                     if op[0] == "record":
                         op[1].done = False
         assert execute(ranks, transport, chunks, random.Random(seed)) == n_ops
+
+
+@pytest.mark.parametrize("transport,chunks,two_streams", [("fused", 1, True), ("fused2", 2, True), ("peer", 2, True)])
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_ghost_planes_through_peer_memory_are_ordered(monkeypatch, P, transport, chunks, two_streams):
+    ranks = record_program(P, steps=3, transport=transport, chunks=chunks, two_streams=two_streams,
+                           monkeypatch=monkeypatch, ghosts="peer")
+    assert not any(op[0] == "collective" and op[1].startswith("shift") for r in ranks for op in r.main.ops)
+    n_ops = sum(len(s.ops) for r in ranks for s in (r.main, r.side))
+    for seed in range(25):
+        for r in ranks:
+            for s in (r.main, r.side):
+                for op in s.ops:
+                    if op[0] == "record":
+                        op[1].done = False
+        assert execute(ranks, transport, chunks, random.Random(seed)) == n_ops
+
+
+def test_the_model_catches_an_unordered_ghost_push(monkeypatch):
+    """Without the FFT's flag barriers between them, rank-1's potential plane could land on phi plane 0
+    before ghost_add has read the density ghost from it (H7): drop every flag wait of the transform and
+    the model must say so."""
+    ranks = record_program(2, steps=2, transport="fused", chunks=1, two_streams=False, monkeypatch=monkeypatch,
+                           ghosts="peer")
+    for r in ranks:
+        r.main.ops = [op for op in r.main.ops if op[0] != "wait" and op[1] != "ghost_wait_rho"]
+    fired = set()
+    for seed in range(60):
+        try:
+            execute(ranks, "fused", 1, random.Random(seed))
+        except Hazard as e:
+            fired.add(str(e)[:2])
+    assert fired & {"H4", "H7", "H1"}
 
 
 def test_the_model_catches_a_missing_barrier(monkeypatch):
