@@ -105,8 +105,8 @@ special = np.array([
 ], dtype=np.float32).T
 if case.get('special', 'all') == 'single':   # realistic: at most one axis at == N_CELLS
     special = np.delete(special, 4, axis=1)
-k = special.shape[1]
-pos[:, :k] = special
+k = special.shape[1] if case.get('special', 'all') != 'none' else 0
+pos[:, :k] = special[:, :k]
 pos = np.ascontiguousarray(pos); vel = np.ascontiguousarray(vel)
 
 out = dict(pos0=pos.copy(), vel0=vel.copy(), mass=np.float64(mass), n_cells=np.int64(N_CELLS),
@@ -189,6 +189,16 @@ np.savez_compressed(case['out'], **out)
 print('wrote', case['out'])
 """
 
+# Digest-only case at the size of BASELINE configs[0] (64^3 particles on a 128^3 mesh, STEPS = 100): the
+# arrays are too large to commit, so only their SHA-256 digests are kept (tests/golden/*_sha256.json);
+# the oracle must reproduce every one of them -- bit-for-bit parity with the reference's own code at
+# the size the reference is meant to run at.  Input: oracle.lattice_ic(64, 128, seed=38, vel_rms=0.05)
+# with no edge-case particles planted, so the test can regenerate it (its digest is kept too).
+HASH_CASES = [
+    dict(name="c1_64_128", N_PARTS=64, N_CELLS=128, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
+         vel_rms=0.05, nsteps=12, keep_mesh=[0, 5, 11], special="none"),
+]
+
 IC_CASES = [
     dict(name="ic16", N_PARTS=16, N_CELLS=32, STEPS=100, A_INIT=0.01, seed=38),
 ]
@@ -232,6 +242,39 @@ def main():
                            check=True, env=env, cwd=tmp)
 
 
+def main_hashes():
+    import hashlib
+    import numpy as np
+    only = set(sys.argv[1:])
+    for case in HASH_CASES:
+        if only and case["name"] not in only:
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            with open(os.path.join(tmp, "configure_me.py"), "w") as fh:
+                fh.write(CONFIGURE_ME.format(**case))
+            with open(os.path.join(tmp, "pyfftw.py"), "w") as fh:
+                fh.write(PYFFTW_SHIM)
+            with open(os.path.join(tmp, "worker.py"), "w") as fh:
+                fh.write(textwrap.dedent(WORKER.format(repo=REPO)))
+            npz = os.path.join(tmp, case["name"] + ".npz")
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([tmp, REF_SRC]), NUMBA_NUM_THREADS="1",
+                       NUMBA_CACHE_DIR=os.path.join(tmp, "nbcache"))
+            subprocess.run([sys.executable, os.path.join(tmp, "worker.py"), json.dumps(dict(case, out=npz))],
+                           check=True, env=env, cwd=tmp)
+            g = np.load(npz)
+            digests = {}
+            for k in sorted(g.files):
+                a = g[k]
+                if a.ndim >= 1 and a.size > 16 and a.dtype.kind == "f":
+                    digests[k] = dict(sha256=hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest(),
+                                      dtype=str(a.dtype), shape=list(a.shape))
+            meta = dict(case=case, a_list=[float(x) for x in g["a_list"]], da=float(g["da"]), mass=float(g["mass"]),
+                        trip_count=int(g["trip_count"]), digests=digests)
+            with open(os.path.join(GOLDEN, case["name"] + "_sha256.json"), "w") as fh:
+                json.dump(meta, fh, indent=1, sort_keys=True)
+            print("wrote", case["name"] + "_sha256.json", len(digests), "digests")
+
+
 def main_ic():
     only = set(sys.argv[1:])
     for case in IC_CASES:
@@ -254,3 +297,4 @@ def main_ic():
 if __name__ == "__main__":
     main_ic()
     main()
+    main_hashes()

@@ -144,3 +144,33 @@ def test_ic_oracle_reproduces_the_reference_functions(golden_dir):
     for d in (0, 1, 2):
         assert np.array_equal(pos[d], g["pos_%d" % d].astype(np.float32))
         assert np.array_equal(vel[d], g["vel_%d" % d].astype(np.float32))
+
+
+def test_oracle_reproduces_reference_digests_at_config_1_size(golden_dir):
+    """BASELINE configs[0] size (64^3 particles on a 128^3 mesh, STEPS = 100): the reference's own code
+    was run for 12 steps by oracle/make_golden.py (HASH_CASES) and only SHA-256 digests of its arrays
+    were kept; the oracle must hit every digest -- density and potential at steps 0, 5, 11, positions
+    and velocities after each of the 12 steps."""
+    import hashlib
+    import json
+    meta = json.load(open(os.path.join(golden_dir, "c1_64_128_sha256.json")))
+    case, dig = meta["case"], meta["digests"]
+    cfg = O.Config(N_CELLS=case["N_CELLS"], N_PARTS=case["N_PARTS"], STEPS=case["STEPS"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
+    pos, vel = O.lattice_ic(case["N_PARTS"], case["N_CELLS"], seed=case["seed"], jitter=2.0, vel_rms=case["vel_rms"])
+    assert sha(pos) == dig["pos0"]["sha256"] and sha(vel) == dig["vel0"]["sha256"]     # same input as the reference run
+    assert O.loop_trip_count(cfg) == meta["trip_count"] == 99
+    fg = O.fourier_grid(cfg)
+    checked = 2
+    for s, a in enumerate(meta["a_list"]):
+        rho = O.density(pos, meta["mass"], cfg)
+        if f"rho_{s}" in dig:
+            assert rho.dtype == np.float32 and list(rho.shape) == dig[f"rho_{s}"]["shape"]
+            assert sha(rho) == dig[f"rho_{s}"]["sha256"], f"density step {s}"
+            assert sha(O.potential(rho, fg, a, cfg)) == dig[f"phi_{s}"]["sha256"], f"potential step {s}"
+            checked += 2
+        O.advance_time(rho, pos, vel, fg, a, meta["da"], cfg)
+        assert sha(pos) == dig[f"pos_{s + 1}"]["sha256"], f"positions step {s}"
+        assert sha(vel) == dig[f"vel_{s + 1}"]["sha256"], f"velocities step {s}"
+        checked += 2
+    assert checked == len(dig) == 32
