@@ -197,6 +197,10 @@ print('wrote', case['out'])
 HASH_CASES = [
     dict(name="c1_64_128", N_PARTS=64, N_CELLS=128, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
          vel_rms=0.05, nsteps=12, keep_mesh=[0, 5, 11], special="none"),
+    # the headline configuration itself (BASELINE configs[1]): two steps of 256^3 particles on a 512^3
+    # mesh, ~13 GB of host memory and a few minutes single-threaded
+    dict(name="c2_256_512", N_PARTS=256, N_CELLS=512, STEPS=1000, A_INIT=0.01, kind="lattice", seed=38,
+         vel_rms=0.05, nsteps=2, keep_mesh=[0, 1], special="none"),
 ]
 
 IC_CASES = [

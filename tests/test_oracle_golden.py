@@ -146,20 +146,16 @@ def test_ic_oracle_reproduces_the_reference_functions(golden_dir):
         assert np.array_equal(vel[d], g["vel_%d" % d].astype(np.float32))
 
 
-def test_oracle_reproduces_reference_digests_at_config_1_size(golden_dir):
-    """BASELINE configs[0] size (64^3 particles on a 128^3 mesh, STEPS = 100): the reference's own code
-    was run for 12 steps by oracle/make_golden.py (HASH_CASES) and only SHA-256 digests of its arrays
-    were kept; the oracle must hit every digest -- density and potential at steps 0, 5, 11, positions
-    and velocities after each of the 12 steps."""
+def _digest_case(golden_dir, fname, want_digests, want_trips):
     import hashlib
     import json
-    meta = json.load(open(os.path.join(golden_dir, "c1_64_128_sha256.json")))
+    meta = json.load(open(os.path.join(golden_dir, fname)))
     case, dig = meta["case"], meta["digests"]
     cfg = O.Config(N_CELLS=case["N_CELLS"], N_PARTS=case["N_PARTS"], STEPS=case["STEPS"])
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()   # noqa: E731
     pos, vel = O.lattice_ic(case["N_PARTS"], case["N_CELLS"], seed=case["seed"], jitter=2.0, vel_rms=case["vel_rms"])
     assert sha(pos) == dig["pos0"]["sha256"] and sha(vel) == dig["vel0"]["sha256"]     # same input as the reference run
-    assert O.loop_trip_count(cfg) == meta["trip_count"] == 99
+    assert O.loop_trip_count(cfg) == meta["trip_count"] == want_trips
     fg = O.fourier_grid(cfg)
     checked = 2
     for s, a in enumerate(meta["a_list"]):
@@ -173,4 +169,22 @@ def test_oracle_reproduces_reference_digests_at_config_1_size(golden_dir):
         assert sha(pos) == dig[f"pos_{s + 1}"]["sha256"], f"positions step {s}"
         assert sha(vel) == dig[f"vel_{s + 1}"]["sha256"], f"velocities step {s}"
         checked += 2
-    assert checked == len(dig) == 32
+    assert checked == len(dig) == want_digests
+
+
+def test_oracle_reproduces_reference_digests_at_config_1_size(golden_dir):
+    """BASELINE configs[0] size (64^3 particles on a 128^3 mesh, STEPS = 100): the reference's own code
+    was run for 12 steps by oracle/make_golden.py (HASH_CASES) and only SHA-256 digests of its arrays
+    were kept; the oracle must hit every digest -- density and potential at steps 0, 5, 11, positions
+    and velocities after each of the 12 steps."""
+    _digest_case(golden_dir, "c1_64_128_sha256.json", 32, 99)
+
+
+@pytest.mark.skipif(os.environ.get("PM_TEST_FULLSIZE") != "1",
+                    reason="two single-threaded oracle steps of 256^3 on 512^3: ~2 minutes and 13 GB of host memory; "
+                           "run with PM_TEST_FULLSIZE=1")
+def test_oracle_reproduces_reference_digests_at_the_headline_size(golden_dir):
+    """BASELINE configs[1] itself (256^3 particles on a 512^3 mesh): two steps of the reference's own
+    code, digests only.  The oracle runs single-threaded like the reference did (the deposit's float32
+    running sums depend on the particle order)."""
+    _digest_case(golden_dir, "c2_256_512_sha256.json", 10, 999)
