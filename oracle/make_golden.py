@@ -197,6 +197,9 @@ print('wrote', case['out'])
 HASH_CASES = [
     dict(name="c1_64_128", N_PARTS=64, N_CELLS=128, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
          vel_rms=0.05, nsteps=12, keep_mesh=[0, 5, 11], special="none"),
+    # ... and the whole configs[0] run (all 99 loop iterations of STEPS = 100, to a ~ 1): final state only
+    dict(name="c1_64_128_full_run", N_PARTS=64, N_CELLS=128, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
+         vel_rms=0.05, nsteps=99, keep_mesh=[98], keep_particles=[50, 99], special="none"),
     # the headline configuration itself (BASELINE configs[1]): two steps of 256^3 particles on a 512^3
     # mesh, ~13 GB of host memory and a few minutes single-threaded
     dict(name="c2_256_512", N_PARTS=256, N_CELLS=512, STEPS=1000, A_INIT=0.01, kind="lattice", seed=38,

@@ -166,10 +166,11 @@ def _digest_case(golden_dir, fname, want_digests, want_trips):
             assert sha(O.potential(rho, fg, a, cfg)) == dig[f"phi_{s}"]["sha256"], f"potential step {s}"
             checked += 2
         O.advance_time(rho, pos, vel, fg, a, meta["da"], cfg)
-        assert sha(pos) == dig[f"pos_{s + 1}"]["sha256"], f"positions step {s}"
-        assert sha(vel) == dig[f"vel_{s + 1}"]["sha256"], f"velocities step {s}"
-        checked += 2
-    assert checked == len(dig) == want_digests
+        if f"pos_{s + 1}" in dig:
+            assert sha(pos) == dig[f"pos_{s + 1}"]["sha256"], f"positions step {s}"
+            assert sha(vel) == dig[f"vel_{s + 1}"]["sha256"], f"velocities step {s}"
+            checked += 2
+    assert checked == len([k for k in dig if k != "a_list"]) == want_digests
 
 
 def test_oracle_reproduces_reference_digests_at_config_1_size(golden_dir):
@@ -178,6 +179,13 @@ def test_oracle_reproduces_reference_digests_at_config_1_size(golden_dir):
     were kept; the oracle must hit every digest -- density and potential at steps 0, 5, 11, positions
     and velocities after each of the 12 steps."""
     _digest_case(golden_dir, "c1_64_128_sha256.json", 32, 99)
+
+
+def test_oracle_reproduces_the_reference_over_the_whole_config_1_run(golden_dir):
+    """All 99 loop iterations of the STEPS = 100 run at 64^3 / 128^3 (a = 0.01 -> 0.9901, the state the
+    P(k) acceptance check looks at): positions and velocities after steps 50 and 99 and the last density
+    and potential carry the digests of the reference's own run."""
+    _digest_case(golden_dir, "c1_64_128_full_run_sha256.json", 8, 99)
 
 
 @pytest.mark.skipif(os.environ.get("PM_TEST_FULLSIZE") != "1",
