@@ -206,6 +206,91 @@ HASH_CASES = [
          vel_rms=0.05, nsteps=2, keep_mesh=[0, 1], special="none"),
 ]
 
+# Snapshot arithmetic and driver cadence, from the reference's OWN save_data.py
+# and pmesh.py.  h5py / matplotlib / mpl_scatter_density are not installed, so stand-in modules are
+# placed on sys.path: `h5py.File` keeps the datasets of create_dataset() in a dict (that is all
+# save_data.py uses), the plotting modules are empty shells (never called: PLOT_* are False).
+#   * save_data: save_file() and from_file() are called unmodified on seeded inputs; every dataset the
+#     reference would have written, and what from_file() returns, go into tests/golden/save_data8.npz.
+#   * pmesh: simulator() is called unmodified with the expensive callables it imported replaced by
+#     no-ops (gaussian_random_field, zeldovich, fourier_grid, density, advance_time) and save_file
+#     replaced by a recorder: the sequence (file index, a_current) it produces IS the reference's
+#     cadence logic (pmesh.py:30-34, 56-74), for several STEPS / N_SAVE_FILES combinations.
+H5PY_STUB = """\
+import numpy as np
+_FILES = {}
+class _DS:
+    def __init__(self, a): self.a = np.array(a)
+    def __array__(self, dtype=None, copy=None): return self.a if dtype is None else self.a.astype(dtype)
+    def __float__(self): return float(self.a)
+class File:
+    def __init__(self, name, mode='r'):
+        self.name, self.mode = name, mode
+        if mode == 'w': _FILES[name] = {}
+        self.d = _FILES[name]
+    def create_dataset(self, name, data=None): self.d[name] = np.array(data)
+    def get(self, name): return _DS(self.d[name])
+    def close(self): pass
+"""
+
+WORKER_DRIVER = """\
+import sys, json, types
+import numpy as np
+case = json.loads(sys.argv[1])
+for name in ['matplotlib', 'matplotlib.colors', 'matplotlib.pyplot', 'mpl_scatter_density']:
+    m = types.ModuleType(name); sys.modules[name] = m
+sys.modules['matplotlib.colors'].LogNorm = object
+sys.modules['matplotlib'].colors = sys.modules['matplotlib.colors']
+sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+import h5py                                  # the stand-in above
+import save_data as S                        # /root/reference/src/save_data.py
+from configure_me import N_PARTS, N_CELLS
+out = {}
+if case['what'] == 'save_data':
+    rs = np.random.RandomState(case['seed'])
+    n3 = N_PARTS ** 3
+    pos = (rs.uniform(0, N_CELLS, size=(3, n3))).astype(np.float32)
+    vel = rs.standard_normal((3, n3)).astype(np.float32)
+    rho = rs.uniform(0, 20, size=(N_CELLS,) * 3).astype(np.float32)
+    out.update(pos=pos, vel=vel, rho=rho)
+    for i, a in enumerate(case['a_values']):
+        S.save_file(rho, pos, vel, i, a)                       # save_data.py:7-27
+        for k, v in h5py._FILES['Data/data.%d.hdf5' % i].items():
+            out['file%d_%s' % (i, k)] = v
+        p2, v2, a2 = S.from_file(i)                            # save_data.py:29-50
+        out['from%d_pos' % i], out['from%d_vel' % i] = p2, v2
+        out['from%d_a' % i] = np.array(a2); out['from%d_a_dtype' % i] = np.array(str(np.asarray(a2).dtype))
+    out['a_values'] = np.array(case['a_values'], dtype=np.float64)
+    np.savez_compressed(case['out'], **out)
+else:
+    import pmesh as P                          # /root/reference/src/pmesh.py
+    calls = []
+    pos = np.zeros((3, 1), dtype=np.float32); vel = np.zeros((3, 1), dtype=np.float32); rho = np.zeros((1, 1, 1), dtype=np.float32)
+    P.gaussian_random_field = lambda: rho
+    P.zeldovich = lambda r: (pos, vel)
+    P.fourier_grid = lambda: None
+    P.density = lambda p, m: rho
+    P.advance_time = lambda r, p, v, k, a, da: (p, v)
+    P.save_file = lambda r, p, v, n, a: calls.append(('save', int(n), float(a)))
+    P.plot_step = lambda r, n: calls.append(('plot', float(n)))
+    P.plot_projection = lambda r, n, d: calls.append(('proj', float(n), float(d)))
+    P.print_status = lambda a, t: calls.append(('status', float(a)))
+    P.simulator()                              # pmesh.py:18-79, unmodified
+    json.dump(dict(case=case, calls=calls), open(case['out'], 'w'))
+print('wrote', case['out'])
+"""
+
+DRIVER_CASES = [
+    dict(name="save_data8", what="save_data", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01, seed=4,
+         a_values=[0.01, 0.2575, 1.0], SAVE_DENSITY=True),
+    dict(name="cadence_100_100", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01, N_SAVE_FILES=100, N_PLOTS=100),
+    dict(name="cadence_1000_100", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=1000, A_INIT=0.01, N_SAVE_FILES=100, N_PLOTS=100),
+    dict(name="cadence_20_5", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=20, A_INIT=0.01, N_SAVE_FILES=5, N_PLOTS=4,
+         PLOT_STEPS=True, PLOT_PROJECTIONS=True, PRINT_STATUS=True),
+    dict(name="cadence_37_10", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=37, A_INIT=0.01, N_SAVE_FILES=10, N_PLOTS=3,
+         PLOT_STEPS=True),
+]
+
 IC_CASES = [
     dict(name="ic16", N_PARTS=16, N_CELLS=32, STEPS=100, A_INIT=0.01, seed=38),
 ]
@@ -282,6 +367,35 @@ def main_hashes():
             print("wrote", case["name"] + "_sha256.json", len(digests), "digests")
 
 
+def main_driver():
+    only = set(sys.argv[1:])
+    for case in DRIVER_CASES:
+        if only and case["name"] not in only:
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            cm = CONFIGURE_ME.format(**case)
+            for key in ("N_SAVE_FILES", "N_PLOTS", "SAVE_DENSITY", "PLOT_STEPS", "PLOT_PROJECTIONS", "PRINT_STATUS"):
+                if key in case:
+                    cm = "\n".join((f"{key} = {case[key]!r}" if ln.startswith(key + " ") else ln) for ln in cm.splitlines()) + "\n"
+            if case["what"] == "cadence":
+                cm = cm.replace("SAVE_DATA = False", "SAVE_DATA = True")
+            with open(os.path.join(tmp, "configure_me.py"), "w") as fh:
+                fh.write(cm)
+            with open(os.path.join(tmp, "pyfftw.py"), "w") as fh:
+                fh.write(PYFFTW_SHIM)
+            with open(os.path.join(tmp, "h5py.py"), "w") as fh:
+                fh.write(H5PY_STUB)
+            with open(os.path.join(tmp, "worker_driver.py"), "w") as fh:
+                fh.write(textwrap.dedent(WORKER_DRIVER))
+            ext = ".npz" if case["what"] == "save_data" else ".json"
+            arg = dict(case, out=os.path.join(GOLDEN, case["name"] + ext))
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([tmp, REF_SRC]), NUMBA_NUM_THREADS="1",
+                       NUMBA_CACHE_DIR=os.path.join(tmp, "nbcache"))
+            subprocess.run([sys.executable, os.path.join(tmp, "worker_driver.py"), json.dumps(arg)],
+                           check=True, env=env, cwd=tmp, stdout=subprocess.DEVNULL if case["what"] == "cadence" else None)
+            print("wrote", case["name"] + ext)
+
+
 def main_ic():
     only = set(sys.argv[1:])
     for case in IC_CASES:
@@ -305,3 +419,4 @@ if __name__ == "__main__":
     main_ic()
     main()
     main_hashes()
+    main_driver()

@@ -7,7 +7,10 @@
 * `save_file` / `from_file` with NumPy arrays reproduce the arithmetic of src/save_data.py:10-24,
   :35-48 bit for bit (restated inline below with the line cites);
 * the pre-step cadence prediction of `pmesh.run` equals the reference's post-step tests
-  (src/pmesh.py:63-74).
+  (src/pmesh.py:63-74);
+* both are also pinned to the reference's OWN code: tests/golden/save_data8.npz holds what its
+  unmodified save_file()/from_file() produce (stand-in h5py module), tests/golden/cadence_*.json the
+  calls its unmodified simulator() makes (oracle/make_golden.py, main_driver).
 """
 import os
 import struct
@@ -335,3 +338,55 @@ if HAVE_HYPOTHESIS:
             got = r[k]
             assert got.dtype == v.dtype and got.shape == v.shape
             assert got.tobytes() == np.ascontiguousarray(v).tobytes()      # bit-exact, NaN payloads included
+
+
+# ------------------------------------------------------------------------------------------------
+# pinned to the reference's own save_data.py / pmesh.py (tests/golden/save_data8.npz, cadence_*.json,
+# produced by oracle/make_golden.py main_driver() with stand-in h5py / matplotlib modules)
+# ------------------------------------------------------------------------------------------------
+def test_save_file_and_from_file_equal_the_reference_bit_for_bit(tmp_path, monkeypatch, golden_dir):
+    import cosmological_particle_mesh_simulation_b200 as pm
+    from cosmological_particle_mesh_simulation_b200 import save_data as S
+    g = np.load(os.path.join(golden_dir, "save_data8.npz"))
+    cfg = _cfg(N_PARTS=8, N_CELLS=16, SAVE_DENSITY=True)
+    pm.set_config(cfg)
+    monkeypatch.chdir(tmp_path)
+    try:
+        pos, vel, rho = g["pos"], g["vel"], g["rho"]
+        for i, a in enumerate(g["a_values"].tolist()):
+            S.save_file(rho, pos, vel, i, a)
+            hf = H.Reader("Data/data.%d.hdf5" % i)
+            names = sorted(k[len("file%d_" % i):] for k in g.files if k.startswith("file%d_" % i))
+            assert sorted(hf.keys()) == names
+            for n in names:
+                want = g["file%d_%s" % (i, n)]
+                got = hf[n]
+                assert got.dtype == want.dtype and got.shape == want.shape, n
+                assert got.tobytes() == want.tobytes(), f"dataset {n} of snapshot {i}"
+            p2, v2, a2 = S.from_file(i)
+            assert str(np.asarray(a2).dtype) == str(g["from%d_a_dtype" % i]) and np.asarray(a2).tobytes() == g["from%d_a" % i].tobytes()
+            assert p2.tobytes() == g["from%d_pos" % i].tobytes() and v2.tobytes() == g["from%d_vel" % i].tobytes()
+    finally:
+        pm.set_config(None)
+
+
+@pytest.mark.parametrize("name", ["cadence_100_100", "cadence_1000_100", "cadence_20_5", "cadence_37_10"])
+def test_cadence_restatement_equals_the_reference_driver(golden_dir, name):
+    """oracle.loop_cadence (which tests/test_gpu_driver.py holds pmesh.run() to) against the calls the
+    reference's own simulator() made: which iterations saved under which index at which a_current,
+    which plotted, and one status line per iteration when PRINT_STATUS."""
+    import json
+    d = json.load(open(os.path.join(golden_dir, name + ".json")))
+    case, calls = d["case"], d["calls"]
+    cfg = _cfg(STEPS=case["STEPS"], N_SAVE_FILES=case["N_SAVE_FILES"], N_PLOTS=case["N_PLOTS"], A_INIT=case["A_INIT"])
+    saves, plots = O.loop_cadence(cfg)
+    ref_saves = [(n, a) for kind, n, *rest in calls if kind == "save" for a in rest]
+    assert ref_saves[0] == (0, cfg.A_INIT)                                   # the IC snapshot, pmesh.py:46-48
+    assert [(n, a) for _, n, a in saves] == ref_saves[1:]
+    if case.get("PLOT_STEPS"):
+        assert [float(n) for _, n in plots] == [c[1] for c in calls if c[0] == "plot"]
+    if case.get("PLOT_PROJECTIONS"):
+        assert [c[1:] for c in calls if c[0] == "proj"] == [[float(n), 15.0] for _, n in plots]
+    if case.get("PRINT_STATUS"):
+        trips = O.loop_trip_count(O.Config(STEPS=case["STEPS"], A_INIT=case["A_INIT"]))
+        assert sum(1 for c in calls if c[0] == "status") == trips
