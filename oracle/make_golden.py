@@ -262,6 +262,19 @@ if case['what'] == 'save_data':
         out['from%d_a' % i] = np.array(a2); out['from%d_a_dtype' % i] = np.array(str(np.asarray(a2).dtype))
     out['a_values'] = np.array(case['a_values'], dtype=np.float64)
     np.savez_compressed(case['out'], **out)
+elif case['what'] == 'cosmology':
+    import cosmology as C                        # /root/reference/src/cosmology.py
+    from configure_me import H0, OMEGA_M0, OMEGA_LAMBDA0, OMEGA_K0
+    rows = []
+    da = 0.99 / 1000
+    for a in [0.01, 0.01 + da, 0.0199, 0.1, 0.25, 0.5, 0.731, 0.99901, 1.0]:
+        rows.append(dict(a=a,
+                         f_loop=float(C.f(a, [H0, OMEGA_LAMBDA0, OMEGA_K0])),            # the loop's call, integrate.py:12 (SURVEY Q1)
+                         f=float(C.f(a, [OMEGA_M0, OMEGA_LAMBDA0, OMEGA_K0])),
+                         H=float(C.H(a, H0, [OMEGA_M0, OMEGA_LAMBDA0, OMEGA_K0])),
+                         Dt=float(C.Dt(a, [OMEGA_M0, OMEGA_LAMBDA0, OMEGA_K0]))))
+    json.dump(dict(case=case, H0=H0, OMEGA_M0=OMEGA_M0, OMEGA_LAMBDA0=OMEGA_LAMBDA0, OMEGA_K0=OMEGA_K0, rows=rows),
+              open(case['out'], 'w'), indent=1)
 else:
     import pmesh as P                          # /root/reference/src/pmesh.py
     calls = []
@@ -283,6 +296,7 @@ print('wrote', case['out'])
 DRIVER_CASES = [
     dict(name="save_data8", what="save_data", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01, seed=4,
          a_values=[0.01, 0.2575, 1.0], SAVE_DENSITY=True),
+    dict(name="cosmology", what="cosmology", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01),
     dict(name="cadence_100_100", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01, N_SAVE_FILES=100, N_PLOTS=100),
     dict(name="cadence_1000_100", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=1000, A_INIT=0.01, N_SAVE_FILES=100, N_PLOTS=100),
     dict(name="cadence_20_5", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=20, A_INIT=0.01, N_SAVE_FILES=5, N_PLOTS=4,
@@ -392,7 +406,7 @@ def main_driver():
             env = dict(os.environ, PYTHONPATH=os.pathsep.join([tmp, REF_SRC]), NUMBA_NUM_THREADS="1",
                        NUMBA_CACHE_DIR=os.path.join(tmp, "nbcache"))
             subprocess.run([sys.executable, os.path.join(tmp, "worker_driver.py"), json.dumps(arg)],
-                           check=True, env=env, cwd=tmp, stdout=subprocess.DEVNULL if case["what"] == "cadence" else None)
+                           check=True, env=env, cwd=tmp, stdout=subprocess.DEVNULL if case["what"] != "save_data" else None)
             print("wrote", case["name"] + ext)
 
 

@@ -109,6 +109,21 @@ def test_f_matches_oracle_bitwise_and_loop_predicate():
         assert sched[0] == (0.01, (1.00 - 0.01) / steps)
 
 
+def test_cosmology_functions_equal_the_reference_bitwise(golden_dir):
+    """tests/golden/cosmology.json: f (with the loop's argument order, SURVEY Q1, and the intended one),
+    H and Dt evaluated by the reference's own cosmology.py (oracle/make_golden.py, main_driver)."""
+    import json
+    from cosmological_particle_mesh_simulation_b200 import cosmology as C
+    g = json.load(open(os.path.join(golden_dir, "cosmology.json")))
+    H0, om, ol, ok = g["H0"], g["OMEGA_M0"], g["OMEGA_LAMBDA0"], g["OMEGA_K0"]
+    for r in g["rows"]:
+        a = r["a"]
+        assert float(C.f(a, [H0, ol, ok])) == r["f_loop"] == float(O.f(a, [H0, ol, ok]))
+        assert float(C.f(a, [om, ol, ok])) == r["f"]
+        assert float(C.H(a, H0, [om, ol, ok])) == r["H"]
+        assert float(C.Dt(a, [om, ol, ok])) == r["Dt"]
+
+
 def test_config_lookup_order():
     import cosmological_particle_mesh_simulation_b200 as pm
     pm.set_config(types.SimpleNamespace(N_CELLS=48))
