@@ -114,7 +114,7 @@ out = dict(pos0=pos.copy(), vel0=vel.copy(), mass=np.float64(mass), n_cells=np.i
 fgrid = fourier_grid()
 fgrid[0, 0, 0] = 0.0                          # SURVEY Q5
 out['fgrid_shape'] = np.array(fgrid.shape); out['fgrid_dtype'] = np.array(str(fgrid.dtype))
-if N_CELLS <= 32:
+if N_CELLS <= 32 or case.get('hash_fgrid'):
     out['fgrid'] = fgrid
 da = (A_END - A_INIT) / STEPS                 # pmesh.py:30
 a_current = case.get('a_start', A_INIT)
@@ -196,7 +196,7 @@ print('wrote', case['out'])
 # with no edge-case particles planted, so the test can regenerate it (its digest is kept too).
 HASH_CASES = [
     dict(name="c1_64_128", N_PARTS=64, N_CELLS=128, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
-         vel_rms=0.05, nsteps=12, keep_mesh=[0, 5, 11], special="none"),
+         vel_rms=0.05, nsteps=12, keep_mesh=[0, 5, 11], special="none", hash_fgrid=True),
     # ... and the whole configs[0] run (all 99 loop iterations of STEPS = 100, to a ~ 1): final state only
     dict(name="c1_64_128_full_run", N_PARTS=64, N_CELLS=128, STEPS=100, A_INIT=0.01, kind="lattice", seed=38,
          vel_rms=0.05, nsteps=99, keep_mesh=[98], keep_particles=[50, 99], special="none"),

@@ -158,6 +158,9 @@ def _digest_case(golden_dir, fname, want_digests, want_trips):
     assert O.loop_trip_count(cfg) == meta["trip_count"] == want_trips
     fg = O.fourier_grid(cfg)
     checked = 2
+    if "fgrid" in dig:        # the Green's table itself (fourier_utils.py:5-16, DC entry := 0)
+        assert sha(fg) == dig["fgrid"]["sha256"]
+        checked += 1
     for s, a in enumerate(meta["a_list"]):
         rho = O.density(pos, meta["mass"], cfg)
         if f"rho_{s}" in dig:
@@ -176,9 +179,9 @@ def _digest_case(golden_dir, fname, want_digests, want_trips):
 def test_oracle_reproduces_reference_digests_at_config_1_size(golden_dir):
     """BASELINE configs[0] size (64^3 particles on a 128^3 mesh, STEPS = 100): the reference's own code
     was run for 12 steps by oracle/make_golden.py (HASH_CASES) and only SHA-256 digests of its arrays
-    were kept; the oracle must hit every digest -- density and potential at steps 0, 5, 11, positions
-    and velocities after each of the 12 steps."""
-    _digest_case(golden_dir, "c1_64_128_sha256.json", 32, 99)
+    were kept; the oracle must hit every digest -- the Green's table, density and potential at steps 0, 5,
+    11, positions and velocities after each of the 12 steps."""
+    _digest_case(golden_dir, "c1_64_128_sha256.json", 33, 99)
 
 
 def test_oracle_reproduces_the_reference_over_the_whole_config_1_run(golden_dir):
