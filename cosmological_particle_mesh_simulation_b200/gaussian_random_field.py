@@ -9,7 +9,10 @@ Unlike the reference (seeded NumPy draws inside a parallel numba loop, SURVEY Q1
 counter-based Philox stream keyed by RANDOM_SEED: the same seed gives the same field bit for bit."""
 import torch
 
-from . import _runtime as rt
+try:
+    from . import _runtime as rt
+except ImportError:  # flat layout (package directory on sys.path)
+    import _runtime as rt
 
 
 def _workspace(n_parts, device):

@@ -263,3 +263,11 @@ def print_status(a_current, start_time, cfg=None):
     cfg = cfg or rt.config()
     percentile = 100 * (a_current - cfg.A_INIT) / (cfg.A_END - cfg.A_INIT)
     print("%.5f" % percentile, "%", " Save step time: --- %.5f seconds ---" % (time() - start_time))
+
+
+if __name__ == "__main__":      # src/pmesh.py:86-93 (`python pmesh.py` from the package directory)
+    from time import time
+    _t0 = time()
+    simulator()
+    print("Finished in")
+    print("--- %.2f seconds ---" % (time() - _t0))

@@ -8,8 +8,12 @@ per-particle uniform(-2, 2) jitter of zeldovich.py:89-91, which the reference dr
 stdlib ``random``, is a Philox stream keyed by RANDOM_SEED here, or an explicit array."""
 import torch
 
-from . import _runtime as rt
-from .gaussian_random_field import _workspace
+try:
+    from . import _runtime as rt
+    from .gaussian_random_field import _workspace
+except ImportError:  # flat layout (package directory on sys.path)
+    import _runtime as rt
+    from gaussian_random_field import _workspace
 
 
 def jitter(seed=None, device=None):

@@ -139,7 +139,15 @@ def test_flat_module_drop_in_layout():
             "from density import density; from integrate import advance_time, integrate;"
             "from fourier_utils import fourier_grid; from potential import potential;"
             "from cosmology import f, H, Dt; import configure_me;"
-            "print(configure_me.N_CELLS, density.__name__, advance_time.__name__)") % PKG
+            "from zeldovich import zeldovich; from gaussian_random_field import gaussian_random_field;"   # pmesh.py:7,9
+            "from save_data import save_file, from_file;"                                                 # pmesh.py:11
+            "from plot_helper import plot_step, plot_grf, plot_projection;"                               # pmesh.py:12
+            "import pmesh;"
+            "print(configure_me.N_CELLS, density.__name__, advance_time.__name__, pmesh.simulator.__name__)") % PKG
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
-    assert out.stdout.split() == ["512", "density", "advance_time"]
+    assert out.stdout.split() == ["512", "density", "advance_time", "simulator"]
+    # `python pmesh.py` (pmesh.py:86-93) from that directory: without a GPU it must fail loudly, not fall back
+    out = subprocess.run([sys.executable, "pmesh.py"], capture_output=True, text=True, cwd=PKG,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
