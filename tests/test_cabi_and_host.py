@@ -151,3 +151,25 @@ def test_flat_module_drop_in_layout():
     out = subprocess.run([sys.executable, "pmesh.py"], capture_output=True, text=True, cwd=PKG,
                          env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert out.returncode != 0 and "no CPU fallback" in out.stderr
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/pmesh.py"), reason="needs the reference checkout (build container only)")
+def test_unmodified_reference_driver_resolves_every_import_to_the_package(tmp_path):
+    """the reference's own pmesh.py, run with the package directory ahead of
+    its src/ on sys.path.  Its imports (density, integrate, zeldovich, fourier_utils,
+    gaussian_random_field, cosmology, save_data, plot_helper, configure_me) must all bind to the GPU
+    modules -- the reference's versions would die on `import pyfftw` / `h5py` / `matplotlib` -- and without
+    a GPU the run must stop at the first device call, loudly."""
+    (tmp_path / "configure_me.py").write_text(
+        "N_PARTS=16; N_CELLS=32; BOX_SIZE=100; N_CPU=1; RANDOM_SEED=38; STEPS=10; N_SAVE_FILES=5; N_PLOTS=5\n"
+        "PLOT_STEPS=False; PLOT_PROJECTIONS=False; PLOT_GRF=False; SAVE_DATA=True; SAVE_DENSITY=False; PRINT_STATUS=True\n"
+        "RESTART=False; RESTART_FROM_N=0; POWER=1.0; LCDM_TRANSFER_FUNCTION=True\n"
+        "OMEGA_M0=0.31; OMEGA_B0=0.04; OMEGA_K0=0.0; OMEGA_LAMBDA0=0.69; H0=0.68; A_INIT=0.01; A_END=1.0\n")
+    code = ("import sys, runpy; sys.path[:0] = [%r, %r, '/root/reference/src'];"
+            "runpy.run_path('/root/reference/src/pmesh.py', run_name='__main__')") % (str(tmp_path), PKG)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path),
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode != 0
+    assert "ModuleNotFoundError" not in out.stderr, out.stderr[-1500:]
+    assert "no CPU fallback" in out.stderr and os.path.join(PKG, "gaussian_random_field.py") in out.stderr
+    assert "Starting the simulation for 16^3 particles with 32^3 grid cells" in out.stdout     # pmesh.py:20, its own banner
