@@ -262,6 +262,14 @@ if case['what'] == 'save_data':
         out['from%d_a' % i] = np.array(a2); out['from%d_a_dtype' % i] = np.array(str(np.asarray(a2).dtype))
     out['a_values'] = np.array(case['a_values'], dtype=np.float64)
     np.savez_compressed(case['out'], **out)
+elif case['what'] == 'project':
+    import plot_helper as PH                     # /root/reference/src/plot_helper.py (matplotlib stand-ins above)
+    rs = np.random.RandomState(case['seed'])
+    rho = (rs.lognormal(0.0, 1.5, size=(N_CELLS,) * 3)).astype(np.float32)
+    out = dict(rho=rho)
+    for n in case['n_slices']:
+        out['proj_%d' % n] = PH.project(rho, np.int32(n))       # plot_helper.py:65-72 (numba njit)
+    np.savez_compressed(case['out'], **out)
 elif case['what'] == 'cosmology':
     import cosmology as C                        # /root/reference/src/cosmology.py
     from configure_me import H0, OMEGA_M0, OMEGA_LAMBDA0, OMEGA_K0
@@ -296,6 +304,7 @@ print('wrote', case['out'])
 DRIVER_CASES = [
     dict(name="save_data8", what="save_data", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01, seed=4,
          a_values=[0.01, 0.2575, 1.0], SAVE_DENSITY=True),
+    dict(name="project16", what="project", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01, seed=9, n_slices=[1, 6, 16]),
     dict(name="cosmology", what="cosmology", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01),
     dict(name="cadence_100_100", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=100, A_INIT=0.01, N_SAVE_FILES=100, N_PLOTS=100),
     dict(name="cadence_1000_100", what="cadence", N_PARTS=8, N_CELLS=16, STEPS=1000, A_INIT=0.01, N_SAVE_FILES=100, N_PLOTS=100),
@@ -401,7 +410,7 @@ def main_driver():
                 fh.write(H5PY_STUB)
             with open(os.path.join(tmp, "worker_driver.py"), "w") as fh:
                 fh.write(textwrap.dedent(WORKER_DRIVER))
-            ext = ".npz" if case["what"] == "save_data" else ".json"
+            ext = ".npz" if case["what"] in ("save_data", "project") else ".json"
             arg = dict(case, out=os.path.join(GOLDEN, case["name"] + ext))
             env = dict(os.environ, PYTHONPATH=os.pathsep.join([tmp, REF_SRC]), NUMBA_NUM_THREADS="1",
                        NUMBA_CACHE_DIR=os.path.join(tmp, "nbcache"))

@@ -390,3 +390,16 @@ def test_cadence_restatement_equals_the_reference_driver(golden_dir, name):
     if case.get("PRINT_STATUS"):
         trips = O.loop_trip_count(O.Config(STEPS=case["STEPS"], A_INIT=case["A_INIT"]))
         assert sum(1 for c in calls if c[0] == "status") == trips
+
+
+def test_projection_equals_the_reference_bitwise(golden_dir):
+    """analysis.project (what plot_projection images) against the reference's own numba `project`
+    (src/plot_helper.py:65-72, tests/golden/project16.npz): float64 sums of the first n planes."""
+    import torch
+    from cosmological_particle_mesh_simulation_b200 import analysis
+    g = np.load(os.path.join(golden_dir, "project16.npz"))
+    rho = torch.from_numpy(g["rho"])
+    for k in [k for k in g.files if k.startswith("proj_")]:
+        n = int(k.split("_")[1])
+        got = analysis.project(rho, n).numpy()
+        assert got.dtype == g[k].dtype == np.float64 and got.tobytes() == g[k].tobytes(), k
