@@ -86,6 +86,48 @@ def test_single_mode_potential():
     assert np.abs(phi - want).max() < 2e-5 * np.abs(want).max()
 
 
+def test_gather_weight_order_known_answer():
+    """t[5] = d_x t_y d_z pairs with g_xz and t[6] = t_x d_y d_z with g_yz
+    (integrate.py:49-50 vs :89-90).  For phi = x*(B*y + C*z) the x sweep has g_c = -2*(B*(y_c+oy) +
+    C*(z_c+oz)), so the CIC sum is exactly -(B*y_p + C*z_p) -- and NOT that if two weights are swapped
+    (d_x != d_y here).  Same for the y sweep with phi = y*(B*x + C*z)."""
+    n = 16
+    cfg = O.Config(N_CELLS=n, N_PARTS=1)
+    z, y, x = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    B, C = 3.0, 5.0
+    px, py, pz = 6.25, 7.5, 9.125                          # dyadic offsets: every product below is exact
+    for direction, phi in ((0, x * (B * y + C * z)), (1, y * (B * x + C * z))):
+        pos = np.array([[px], [py], [pz]], dtype=np.float32)
+        vel = np.zeros((3, 1), dtype=np.float32)
+        acc = np.zeros((3, 1), dtype=np.float64)
+        O.integrate(pos, vel, 0.5, 1.0, 0.0, phi.astype(np.float32), cfg, acc=acc)   # da = 0: nothing moves
+        want = -(B * py + C * pz) if direction == 0 else -(B * px + C * pz)
+        assert acc[direction, 0] == want
+        # the swapped pairing would be off by B*(d_x*t_y - t_x*d_y)*d_z (x sweep): make sure that is visible
+        dx, dy, dz = px % 1, py % 1, pz % 1
+        assert abs(B * (dx * (1 - dy) - (1 - dx) * dy) * dz) > 0.01
+
+
+def test_gather_reads_across_the_periodic_boundary():
+    """integrate.py:64: the lower neighbour of cell 0 is index -1, i.e. plane Nc-1; :65 the upper
+    neighbour of cell Nc-1 is (c+1) % Nc = 0."""
+    n = 16
+    cfg = O.Config(N_CELLS=n, N_PARTS=1)
+    for direction in range(3):
+        phi = np.zeros((n, n, n), dtype=np.float32)
+        idx = [slice(None)] * 3
+        idx[2 - direction] = n - 1                          # array axes are [z, y, x]
+        phi[tuple(idx)] = 1.0
+        pos = np.full((3, 1), 4.0, dtype=np.float32)
+        pos[direction, 0] = 0.0                             # on the corner of cell 0: weight 1 on that corner
+        acc = np.zeros((3, 1), dtype=np.float64)
+        O.integrate(pos.copy(), np.zeros((3, 1), np.float32), 0.5, 1.0, 0.0, phi, cfg, acc=acc)
+        assert acc[direction, 0] == 0.5                     # (phi[-1] - phi[1]) / 2
+        pos[direction, 0] = n - 2.0                         # cell Nc-2: its upper neighbour is plane Nc-1
+        O.integrate(pos.copy(), np.zeros((3, 1), np.float32), 0.5, 1.0, 0.0, phi, cfg, acc=acc)
+        assert acc[direction, 0] == -0.5
+
+
 def test_sort_order_is_stable_and_keys_match_definition():
     cfg = O.Config(N_CELLS=8, N_PARTS=4)
     pos, _ = O.lattice_ic(4, 8, seed=1)
