@@ -216,7 +216,8 @@ PM_API int64_t pm_particles_count(const pm_plan *plan);
  */
 #define PM_BUF_RHO 0             /* float[nzl][Nc][Nc]   density of the owned planes              */
 #define PM_BUF_RHO_GHOST_SEND 1  /* float[Nc][Nc]        plane nzl of the deposit -> rank+1        */
-#define PM_BUF_RHO_GHOST_RECV 2  /* float[Nc][Nc]        <- rank-1, added by pm_slab_ghost_add     */
+#define PM_BUF_RHO_GHOST_RECV 2  /* float[Nc][Nc]        <- rank-1, added by pm_slab_ghost_add (aliases
+                                    PM_BUF_PHI_LO_RECV: the phi buffer is dead at that point of the step) */
 #define PM_BUF_FFT_SEND_MAIN 3   /* float2[P][nzl][nyl][Nc/2]  packed spectrum, chunk s -> rank s  */
 #define PM_BUF_FFT_SEND_SIDE 4   /* float2[P][nzl][nyl]        packed Nyquist plane                */
 #define PM_BUF_FFT_RECV_MAIN 5   /* float2[Nc][nyl][Nc/2]      transposed spectrum (z pass)        */
