@@ -210,10 +210,57 @@ def make_particles_slab_gpu(n_parts, n_cells, rank, nranks, dev, seed=38, vel_si
     return pos, vel, ids
 
 
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    omp_get_max_threads() (oracle.max_threads) obeys -- the CPU arm must not: it is the reference timed
+    on ALL of the box's host cores, whatever launched it (the oracle takes the count explicitly)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
+def workload_label(n_parts, n_cells, particles="ic"):
+    """config.workload, derived from the sizes actually run (never a literal)."""
+    base = f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step (CIC deposit + FFT Poisson + gather/kick/drift)"
+    which = {(64, 128): "configs[0]", (256, 512): "configs[1]", (512, 1024): "configs[2]",
+             (1024, 2048): "configs[3]"}.get((n_parts, n_cells))
+    if particles == "clustered":
+        return base + ", BASELINE configs[4] clustered microbench load (synthetic blob)"
+    if particles == "evolved":
+        return base + ", BASELINE configs[4] clustered z=0 snapshot (own ICs evolved by the step itself)"
+    return base + (f", BASELINE {which}" if which else "")
+
+
 def cfg_namespace(n_parts, n_cells, steps_cfg=1000):
-    return types.SimpleNamespace(N_PARTS=n_parts, N_CELLS=n_cells, N_CPU=1, STEPS=steps_cfg,
-                                 OMEGA_M0=0.31, OMEGA_K0=0.0, OMEGA_LAMBDA0=0.69, H0=0.68,
-                                 A_INIT=0.01, A_END=1.0)
+    """configure_me defaults (src/configure_me.py:7-40) with the run's sizes."""
+    from cosmological_particle_mesh_simulation_b200 import configure_me as cm
+    d = {name: entry[0] for name, entry in cm.PARAMETERS.items()}
+    d.update(N_PARTS=n_parts, N_CELLS=n_cells, N_CPU=1, STEPS=steps_cfg)
+    return types.SimpleNamespace(**d)
+
+
+def make_particles_evolved(pm, cfg, dev, evolve_steps=None):
+    """BASELINE configs[4] / SURVEY 8d(ii): the z = 0 snapshot.  The package's own initial conditions
+    (gaussian_random_field -> zeldovich, RANDOM_SEED 38, on the GPU) evolved by the resident step itself
+    over the reference's whole schedule (src/pmesh.py:56-63: 999 iterations for STEPS = 1000).
+    Returns (pos, vel, a_last, da, n_evolved) with the particles in original order on the device."""
+    import torch
+    with torch.cuda.device(dev):
+        rho0 = pm.gaussian_random_field(device=dev)
+        pos, vel = pm.zeldovich(rho0)
+        del rho0
+    sched = pm.loop_scale_factors(cfg)
+    if evolve_steps is not None:
+        sched = sched[:int(evolve_steps)]
+    mass = (cfg.N_CELLS / cfg.N_PARTS) ** 3
+    state = pm.ResidentParticles(pos, vel)
+    for a, da in sched:
+        state.step(a, da, mass=mass)
+    state.store(pos, vel)
+    torch.cuda.synchronize()
+    a_last, da = sched[-1]
+    return pos, vel, a_last, da, len(sched)
 
 
 def published_ratio(value, n_parts, n_cells):
@@ -233,10 +280,14 @@ def stage_alg_bytes(npart, n_cells):
         "keys": 4 * npart,                           # resident path: keys come out of the gather kernel
         "rows": 4 * npart + 4 * n_cells ** 2,        # read sorted keys; write row offsets
         "deposit": 12 * npart + 4 * m,               # SURVEY 8d deposit row
-        "green": 8 * m,                              # read + write half spectrum
+        # The hand-written Poisson solve is FIVE passes over a 4*M-byte array: rows + y
+        # forward (stage "fft_r2c": 2 x 8*M), the fused z pass = z forward + Green + z inverse (stage
+        # "green": 8*M), y + rows inverse (stage "fft_c2r": 2 x 8*M).  The contract figure B_step still
+        # charges the solve 56*M; these are the bytes each STAGE really has to move.
+        "green": 8 * m,
         "gather_kick_drift": 48 * npart + 4 * m,     # SURVEY 8d gather row
         "sort": 8 * npart + 8 * npart,               # read keys + previous keys; write sorted keys + order
-        "fft_r2c": 24 * m, "fft_c2r": 24 * m,
+        "fft_r2c": 16 * m, "fft_c2r": 16 * m,
     }
 
 
@@ -266,7 +317,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as O
-    threads = O.max_threads()
+    threads = host_threads()
     n_parts, n_cells = args.n_parts, args.n_cells
     pos, vel = make_particles_torch(n_parts, n_cells, "cpu")
     pos_h, vel_h = pos.numpy(), vel.numpy()
@@ -282,7 +333,7 @@ def run_reference(args, rank, world):
         "steps": k, "warmup": 1, "requested_steps": args.steps, "ms_per_step": 1e3 * dt / k,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": published_ratio(rate, n_parts, n_cells),
         "dtype": "f64 (complex128 FFT, float32 state)", "data": "synthetic",
-        "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step",
+        "config": {"workload": workload_label(n_parts, n_cells),
                    "n_parts": n_parts, "n_cells": n_cells},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -478,7 +529,7 @@ def run_slab(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": published_ratio(value, n_parts, n_cells), "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step, BASELINE configs[1]",
+            "config": {"workload": workload_label(n_parts, n_cells),
                        "n_parts": n_parts, "n_cells": n_cells,
                        "particles": particles_desc,
                        "l2": "inputs larger than L2",
@@ -538,12 +589,19 @@ def run_ours(args, rank, world, local_rank):
         pos_h, vel_h = make_particles_clustered(n_parts, n_cells)
         particles_desc = ("clustered microbench load (BASELINE configs[4]): half in a 1-cell-rms Gaussian blob at the "
                           "box centre, half uniform, shuffled; Gaussian velocities rms %g, seed 38" % VEL_SIGMA)
+    elif args.particles == "evolved":
+        pos, vel, a_last, da_last, n_ev = make_particles_evolved(pm, cfg, dev, args.evolve_steps or None)
+        pos_h, vel_h = pos.cpu(), vel.cpu()
+        particles_desc = ("z=0-like snapshot (BASELINE configs[4]): own Zel'dovich ICs (RANDOM_SEED 38) evolved by "
+                          "%d resident steps of the reference schedule to a = %.4f" % (n_ev, a_last + da_last))
     else:
         pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
         particles_desc = "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA
     pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
     plan = rt.get_plan(n_cells, npart, dev)
     sched = pm.loop_scale_factors(cfg)
+    if args.particles == "evolved":
+        sched = [(a_last, da_last)]          # keep stepping at the late-time scale factor
 
     def barrier():
         if dist is not None:
@@ -577,6 +635,7 @@ def run_ours(args, rank, world, local_rank):
     ms_total = ev0.elapsed_time(ev1)
     launches = pm.launch_count() - launches0
     sort_n, sort_movers, sort_mode = state.sort_stats()
+    block_stats = state.block_stats()
     fft_sync_errors = int(rt.lib().pm_plan_fft_sync_errors(plan.handle))
     import ctypes
     import numpy as np
@@ -596,26 +655,28 @@ def run_ours(args, rank, world, local_rank):
     value = npart * world * K / (ms_total * 1e-3)   # replicas until the slab path lands
 
     # ---- e2e: host-buffer C-ABI call, pinned host memory, copies inside the timed region ----
-    state.store(pos, vel)
-    ph, vh = pos.cpu().pin_memory(), vel.cpu().pin_memory()
-    ke = max(3, min(K, 10))
-    for _ in range(2):
-        a, da = sched[step_i % len(sched)]
-        pm.step_host(ph, vh, a, da, mass=mass, device=dev)
-        step_i += 1
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        a, da = sched[step_i % len(sched)]
-        pm.step_host(ph, vh, a, da, mass=mass, device=dev)
-        step_i += 1
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = npart * world * ke / e2e_s
+    e2e_value, ke = None, 0
+    if not args.no_e2e:
+        state.store(pos, vel)
+        ph, vh = pos.cpu().pin_memory(), vel.cpu().pin_memory()
+        ke = max(3, min(K, 10))
+        for _ in range(2):
+            a, da = sched[step_i % len(sched)]
+            pm.step_host(ph, vh, a, da, mass=mass, device=dev)
+            step_i += 1
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            a, da = sched[step_i % len(sched)]
+            pm.step_host(ph, vh, a, da, mass=mass, device=dev)
+            step_i += 1
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_value = npart * world * ke / e2e_s
 
     if rank != 0:
         return
@@ -637,13 +698,13 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if world == 1 else "weak",
         "vs_baseline": published_ratio(value, n_parts, n_cells) if args.particles == "ic" else None,
+        "particles_kind": args.particles,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{n_parts}^3 particles on {n_cells}^3 mesh, full PM step "
-                               "(CIC deposit + FFT Poisson + gather/kick/drift), BASELINE "
-                               + ("configs[4] clustered microbench load" if args.particles == "clustered" else "configs[1]"),
+        "config": {"workload": workload_label(n_parts, n_cells, args.particles),
                    "n_parts": n_parts, "n_cells": n_cells,
                    "particles": particles_desc,
                    "sort": {"mode": sort_mode, "mover_fraction_last_step": sort_movers / max(sort_n, 1)},
+                   "gather_blocks": block_stats,
                    "fft": {"fused_plane_passes": os.environ.get("PM_FFT_FUSE", "0") == "1",
                            "kernels": ("radix-8.8.8" if os.environ.get("PM_FFT_V2", "1") == "0" else
                                        "two-stage" if os.environ.get("PM_FFT_ZMIX", "1") == "0" else
@@ -653,7 +714,8 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (201 MB particles rows, 537 MB meshes vs 126 MB L2)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (slab path pending)"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * npart,
+        "e2e": None if e2e_value is None else {
+                "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * npart,
                 "d2h_bytes_per_step": 24 * npart, "steps": ke,
                 "api": "pm_step_host (pinned host pos+vel in, pos+vel out; density stays on device, "
                        "as with the reference defaults SAVE_DENSITY=False, PLOT_*=False)"},
@@ -668,8 +730,7 @@ def run_ours(args, rank, world, local_rank):
         "stage_frac_of_peak": {n: alg[n] / (stage_ms[n] * 1e-3) / 1e9 / peak for n in stage_ms if stage_ms[n] > 0.01},
     }
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
-        threads = O.max_threads()
+        threads = host_threads()
         pc, vc = pos_h.numpy().copy(), vel_h.numpy().copy()
         rate, dt = cpu_baseline_sample(n_parts, n_cells, pc, vc, threads, 1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
@@ -688,9 +749,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-parts", type=int, default=256)
     ap.add_argument("--n-cells", type=int, default=512)
-    ap.add_argument("--particles", default="ic", choices=["ic", "clustered"],
-                    help="N=1 workload: IC-like lattice+jitter (default, the metric's configuration) or the clustered "
-                         "microbench load of BASELINE configs[4] (per-stage times show deposit/sort/gather under skew)")
+    ap.add_argument("--particles", default="ic", choices=["ic", "clustered", "evolved"],
+                    help="N=1 workload: IC-like lattice+jitter (default, the metric's configuration); the synthetic clustered "
+                         "microbench load of BASELINE configs[4]; or `evolved`, the z=0 snapshot obtained by running the "
+                         "package's own ICs through the whole schedule (per-stage times show deposit/sort/gather under skew)")
+    ap.add_argument("--evolve-steps", type=int, default=0, help="--particles evolved: steps to evolve (0 = the whole schedule)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="multi-GPU exploration runs: skip the host-buffer leg")
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")

@@ -81,6 +81,8 @@ def lib():
             "pm_plan_fft_sync_errors": (i32, [vp]),
             "pm_plan_set_fft_variant": (i32, [vp, i32]),
             "pm_plan_set_gather_tiled": (i32, [vp, i32]),
+            "pm_plan_gather_tile": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
+            "pm_plan_block_stats": (i32, [vp, i32, i32, ctypes.POINTER(i64), vp]),
             "pm_plan_set_sort_mode": (i32, [vp, i32]),
             "pm_plan_sort_stats": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32)]),
             "pm_fourier_grid": (i32, [vp, vp, vp]),
@@ -166,7 +168,7 @@ EXPORTED_SYMBOLS = (
     "pm_slab_peer_ghost_export", "pm_slab_peer_ghost_import", "pm_slab_peer_ghost_set", "pm_slab_ghost_push_rho",
     "pm_slab_ghost_wait_rho", "pm_slab_ghost_push_phi", "pm_slab_ghost_wait_phi", "pm_power_spectrum",
     "pm_plan_set_sort_mode", "pm_plan_sort_stats", "pm_plan_set_fft_fuse", "pm_plan_fft_sync_errors",
-    "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled", "pm_ic_workspace_bytes", "pm_ic_noise",
+    "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled", "pm_plan_gather_tile", "pm_plan_block_stats", "pm_ic_workspace_bytes", "pm_ic_noise",
     "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",
 )
 

@@ -88,7 +88,7 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->inc_b = align_up((size_t)L->inc_bcap * 8);
     L->inc_tile = align_up(((size_t)pm_sort_tiles((int64_t)npad) + 2) * 4);
     L->fft_sync = align_up((size_t)(2 * (nc + 1) + 1) * 4);
-    L->total = L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
+    L->total = kAlign /* diag */ + L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
                L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw +
                2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot +
                L->leave_sorted + 2 * L->mig + L->peer_flags + L->inc_a + 2 * L->inc_b + 2 * L->inc_tile;
@@ -245,6 +245,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     p->inc_split = (uint32_t *)c;     c += L.inc_tile;
     p->inc_bcap = L.inc_bcap;
     p->fft_sync = (unsigned *)c;      c += L.fft_sync;
+    p->diag = c;                      c += kAlign;
     {
         const char *fu = getenv("PM_FFT_FUSE");   // "0": separate row and y launches (A/B checks)
         const char *lg = getenv("PM_FFT_LAG");
@@ -390,6 +391,22 @@ int pm_plan_set_gather_tiled(pm_plan *p, int tiled)
     if (!p) return PM_ERR_INVALID;
     p->gather_tiled = (tiled != 0);
     return PM_OK;
+}
+
+int pm_plan_gather_tile(const pm_plan *p, int *rows_per_block, int *cap)
+{
+    if (!p || !rows_per_block || !cap) return PM_ERR_INVALID;
+    pm_gather_tile_shape(rows_per_block, cap);
+    return PM_OK;
+}
+
+int pm_plan_block_stats(pm_plan *p, int rows_per_block, int cap, int64_t *out4, pm_stream_t stream)
+{
+    if (!p || !out4 || cap < 0) return PM_ERR_INVALID;
+    DeviceGuard guard;
+    int rc = guard.enter(p->device);
+    if (rc != PM_OK) return rc;
+    return pm_k_block_stats(p, rows_per_block, cap, out4, pm_cu(stream));
 }
 
 int pm_plan_set_fft_fuse(pm_plan *p, int fuse, int lag)

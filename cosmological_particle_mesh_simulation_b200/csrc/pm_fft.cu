@@ -841,9 +841,9 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
         constexpr size_t smem3_2 = kSmem3<N, 2>, smem3_3 = kSmem3<N, 3>;
         constexpr bool ring3_fits = smem3_3 <= 227 * 1024;
         const size_t smem_cols_v1 = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
-        static bool attr_set = false;
-        static int plane_per_sm = 1;
-        if (!attr_set) {
+        static int plane_per_sm_dev[64];
+        int &plane_per_sm = plane_per_sm_dev[p->device & 63];
+        PM_ONCE_PER_DEVICE_BEGIN(p->device)
             PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
             PM_CUDA(cudaFuncSetAttribute(rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
             PM_CUDA(cudaFuncSetAttribute(cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
@@ -866,8 +866,7 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
             PM_CUDA(cudaFuncSetAttribute(plane_inv, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             PM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plane_per_sm, plane_fwd, kThr2, smem_cols));
             if (plane_per_sm < 1) plane_per_sm = 1;
-            attr_set = true;
-        }
+        PM_ONCE_PER_DEVICE_END()
         ColArgs ca;
         ca.main = p->spec;
         ca.side = p->spec + (size_t)N * N * H;
@@ -948,8 +947,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     constexpr int H = N / 2;
     const size_t smem_cols = ((size_t)N * kColsCN<N> + 2 * N) * sizeof(float2);
     const size_t smem_rows = ((size_t)H * kPitch + N) * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
+    PM_ONCE_PER_DEVICE_BEGIN(p->device)
         PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
         PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
         PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
@@ -961,8 +959,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
         PM_CUDA(cudaFuncSetAttribute(k_fft_cols<N, COL_FUSED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         PM_CUDA(cudaFuncSetAttribute(k_fft_rows<N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
-    }
+    PM_ONCE_PER_DEVICE_END()
     ColArgs ca;
     ca.main = p->spec;
     ca.side = p->spec + (size_t)N * N * H;
@@ -992,14 +989,12 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     int plane_grid = 0;
     if constexpr (kPlaneFused<N>) {
         if (fused) {
-            static bool plane_attr = false;
-            if (!plane_attr) {
+            PM_ONCE_PER_DEVICE_BEGIN(p->device)
                 PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
                 PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
                 PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 PM_CUDA(cudaFuncSetAttribute(k_fft_plane<N, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                plane_attr = true;
-            }
+            PM_ONCE_PER_DEVICE_END()
             // one CTA per resident slot: the ticket loop hands every CTA its share of the items
             int per_sm = 0;
             PM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fft_plane<N, true, false>, kThrC<N>, smem_cols));

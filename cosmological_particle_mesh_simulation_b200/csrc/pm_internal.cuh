@@ -38,6 +38,20 @@ extern int g_pm_last_cufft;
         }                                               \
     } while (0)
 
+// Function attributes (dynamic shared-memory opt-in, carveout) are per DEVICE: guard their one-time
+// set-up by a bit per device ordinal, not by a process-wide flag, so that a plan on a second GPU of
+// the same process opts in there as well.  Setting them twice from two threads is harmless.
+#include <atomic>
+#define PM_ONCE_PER_DEVICE_BEGIN(dev)                                                   \
+    {                                                                                   \
+        static std::atomic<unsigned long long> once_{0ull};                             \
+        const unsigned long long bit_ = 1ull << ((unsigned)(dev) & 63u);                \
+        if (!(once_.load(std::memory_order_acquire) & bit_)) {
+#define PM_ONCE_PER_DEVICE_END()                                                        \
+            once_.fetch_or(bit_, std::memory_order_release);                            \
+        }                                                                               \
+    }
+
 #define PM_PEER_MAX 16
 #define PM_PEER_SLOTS 24      // 0..7 "chunk pushed", 8..15 "z pass done", 16..18 ghost planes (pm_slab_ghost_*)
 #define PM_SLOT_GHOST_RHO 16  // density ghost plane written into rank+1
@@ -132,6 +146,8 @@ struct pm_plan {
     float *peer_mesh2[PM_PEER_MAX];         // rank s's phi buffer (ghost planes pushed through peer memory)
     int ghosts_set;
 
+    void *diag;             // 64 bytes of device scratch for diagnostics (pm_plan_block_stats)
+
     // optional per-stage timing of pm_step (pm_plan_profile_begin/read)
     cudaEvent_t *prof_ev;   // prof_cap * (PM_NUM_STAGES + 1) events
     int prof_cap, prof_n;
@@ -167,6 +183,8 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
                                     double da, cudaStream_t st);
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
+int pm_k_block_stats(pm_plan *p, int rows_per_block, int cap, int64_t *out4, cudaStream_t st);
+void pm_gather_tile_shape(int *rows_per_block, int *cap);
 // slab mode (pm_slab.cu / pm_particles.cu)
 int pm_k_deposit_slab(pm_plan *p, const float *pos, double mass, float *rho, cudaStream_t st);
 int pm_deposit_segments(int nc);

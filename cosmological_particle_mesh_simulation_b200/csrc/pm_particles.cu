@@ -268,7 +268,8 @@ static int pm_launch_deposit_ry(pm_plan *p, const float *pos, int64_t stride, do
     const int nc = p->nc, nseg = p->dep_nseg;
     const int rows_per_cta = RY / nseg;
     const size_t smem = (size_t)RY * pm_deposit_pitch(nc / nseg) * sizeof(pm_acc_t);
-    static size_t smem_set = 0;
+    static size_t smem_set_dev[64];   // per device ordinal (function attributes are per device)
+    size_t &smem_set = smem_set_dev[p->device & 63];
     if (smem > smem_set) {
         PM_CUDA(cudaFuncSetAttribute(k_deposit_rows<RY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
@@ -549,12 +550,10 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
     constexpr size_t smem = kGtSmem<NC, PM_GT_YB, PM_GT_CAP>;
     static_assert(smem <= 227 * 1024 / PM_GT_MINB, "PM_GT_MINB CTAs per SM");
     auto kern = k_gather_tiled<NC, PM_GT_YB, PM_GT_NT, PM_GT_CAP, PM_GT_MINB>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    PM_ONCE_PER_DEVICE_BEGIN(p->device)
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
-    }
+    PM_ONCE_PER_DEVICE_END()
     const int c = p->rcur, o = c ^ 1;
     GatherTiledArgs A;
     A.px = p->rpos[c]; A.py = A.px + p->rstride; A.pz = A.py + p->rstride;
@@ -582,6 +581,46 @@ static int pm_try_gather_tiled(pm_plan *p, const float *phi, double k_kick, doub
     case 512: return pm_launch_gather_tiled<512>(p, phi, k_kick, da, aa, f_a1, cnt, st);
     default: return PM_ERR_UNSUPPORTED;
     }
+}
+
+// ---- diagnostics: particles per block of mesh rows, from the row table of the last sort ----------
+__global__ void __launch_bounds__(256) k_block_stats(const uint32_t *__restrict__ row_start, int64_t nblocks,
+                                                     int rows_per_block, int nseg, uint32_t cap,
+                                                     unsigned long long *__restrict__ out)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const int64_t r0 = b * rows_per_block * nseg, r1 = r0 + (int64_t)rows_per_block * nseg;
+    const uint32_t n = row_start[r1] - row_start[r0];
+    if (n > cap) {
+        atomicAdd(out + 1, 1ull);
+        atomicAdd(out + 2, (unsigned long long)(n - cap));
+    }
+    atomicMax(out + 3, (unsigned long long)n);
+}
+
+int pm_k_block_stats(pm_plan *p, int rows_per_block, int cap, int64_t *out4, cudaStream_t st)
+{
+    if (!p->rows_valid) return PM_ERR_INVALID;
+    const int64_t nrows = (int64_t)p->nzl * p->nc;
+    if (rows_per_block < 1 || nrows % rows_per_block) return PM_ERR_INVALID;
+    const int64_t nblocks = nrows / rows_per_block;
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(p->diag);
+    PM_CUDA(cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), st));
+    PM_LAUNCH(k_block_stats, (unsigned)((nblocks + 255) / 256), 256, 0, st, (const uint32_t *)p->row_start, nblocks,
+              rows_per_block, p->dep_nseg, (uint32_t)cap, d);
+    PM_CHECK_LAUNCH();
+    unsigned long long h[4];
+    PM_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PM_CUDA(cudaStreamSynchronize(st));
+    out4[0] = nblocks; out4[1] = (int64_t)h[1]; out4[2] = (int64_t)h[2]; out4[3] = (int64_t)h[3];
+    return PM_OK;
+}
+
+void pm_gather_tile_shape(int *rows_per_block, int *cap)
+{
+    *rows_per_block = PM_GT_YB;
+    *cap = PM_GT_CAP;
 }
 
 // Resident variant: reads buffer set `cur` through the new cell order, writes set `cur^1` and the

@@ -119,6 +119,22 @@ class ResidentParticles:
                                              ctypes.byref(mode)), "pm_plan_sort_stats")
         return n.value, m.value, {1: "full", 2: "incremental"}.get(mode.value, "none")
 
+    def block_stats(self, rows_per_block=None, cap=None):
+        """Skew diagnostics from the row table of the last sort (pm_plan_block_stats): dict with the
+        number of row blocks, how many hold more than `cap` particles, the particles beyond `cap` and
+        the fullest block.  Defaults: the tile shape of the tiled gather kernel."""
+        import ctypes
+        rb, cp = ctypes.c_int(0), ctypes.c_int(0)
+        rt.check(rt.lib().pm_plan_gather_tile(self.plan.handle, ctypes.byref(rb), ctypes.byref(cp)), "pm_plan_gather_tile")
+        rows_per_block = rb.value if rows_per_block is None else int(rows_per_block)
+        cap = cp.value if cap is None else int(cap)
+        out = (ctypes.c_int64 * 4)()
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_plan_block_stats(self.plan.handle, rows_per_block, cap, out,
+                                                  rt.stream_ptr(self.device)), "pm_plan_block_stats")
+        return {"rows_per_block": rows_per_block, "cap": cap, "blocks": int(out[0]), "blocks_over_cap": int(out[1]),
+                "particles_over_cap": int(out[2]), "max_block_particles": int(out[3])}
+
     def order(self):
         """Original index of the particle in each storage slot (int32 CUDA tensor)."""
         ids = torch.empty(self.np, dtype=torch.int32, device=f"cuda:{self.device}")

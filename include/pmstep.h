@@ -100,6 +100,16 @@ PM_API int pm_plan_fft_sync_errors(pm_plan *plan);
  * particle with scattered loads (also PM_GATHER_TILED=0).  Default on: 0.50 ms against 0.55 ms at
  * 256^3 particles on 512^3 cells.  Bit-identical results. */
 PM_API int pm_plan_set_gather_tiled(pm_plan *plan, int tiled);
+/* Diagnostics of the resident gather under particle skew (bench.py reports them for the clustered
+ * loads of BASELINE configs[4]).  pm_plan_gather_tile: the tile shape of the tiled kernel -- mesh
+ * rows per CTA and the staged-particle capacity of one (z, row-block) step; a block holding more
+ * particles than the capacity handles the excess in further rounds.  pm_plan_block_stats: over the
+ * row table of the LAST sort (synchronises the stream), for blocks of `rows_per_block` consecutive
+ * mesh rows: out[0] = blocks, out[1] = blocks with more than `cap` particles, out[2] = particles
+ * beyond `cap` summed over those blocks, out[3] = particles of the fullest block.  No reference
+ * counterpart (the reference never sorts, src/density.py:17). */
+PM_API int pm_plan_gather_tile(const pm_plan *plan, int *rows_per_block, int *cap);
+PM_API int pm_plan_block_stats(pm_plan *plan, int rows_per_block, int cap, int64_t *out4, pm_stream_t stream);
 /* How the resident paths (pm_step_resident, pm_slab_deposit) order the particle list by cell key
  * (the order fixes the deposit's summation tree and the locality of deposit and gather; the
  * reference scatters in particle-index order, src/density.py:17, and has no counterpart):

@@ -630,35 +630,104 @@ def test_full_size_properties_256_on_512(pm):
     assert float(vl.abs().max()) <= 1e-5
 
 
-@pytest.mark.skipif(os.environ.get("PM_TEST_FULLSIZE") != "1",
-                    reason="one oracle step of 256^3 on 512^3 (13 GB of host memory, a few seconds on the GPU box's cores); "
-                           "written after round 1's GPU budget was spent -- run with PM_TEST_FULLSIZE=1")
 def test_full_size_parity_against_the_oracle_256_on_512(pm):
-    """BASELINE configs[1] at full size, two steps, against the oracle -- which itself reproduces the
-    reference's digests at this size (tests/golden/c2_256_512_sha256.json).  Tolerances of north_star:
-    1e-5 relative L2 on density, potential, positions (periodic) and velocities, per step."""
+    """BASELINE configs[1] at FULL size -- the size bench.py times -- three free-running steps against
+    the oracle (which itself reproduces the reference's digests at this size:
+    tests/golden/c2_256_512_sha256.json), through BOTH product paths: the stateless drop-in calls
+    (pm.density / pm.potential / pm.step) and the resident cell-ordered state bench.py measures
+    (ResidentParticles -> pm_step_resident: incremental sort, k_deposit_rows, the 512-point FFT kernels,
+    k_gather_tiled<512>).  Tolerances of north_star: 1e-5 relative L2 on density, potential, positions
+    (periodic) and velocities, per step.  Single-axis `pos == N_CELLS` particles (~1.5 such
+    events per step occur naturally at this size) are planted on each axis so the quirk is exercised at
+    full size for certain.  Needs ~13 GB of host memory and ~1 minute of host time."""
     cfg = O.Config(N_CELLS=512, N_PARTS=256, STEPS=1000, N_CPU=O.max_threads())
+    cfg1 = O.Config(**{**cfg.__dict__, "N_CPU": 1})           # density in particle order: the deterministic reference result
     pm.set_config(cfg_ns(cfg))
     pos_h, vel_h = O.lattice_ic(256, 512, seed=38, jitter=2.0, vel_rms=0.05)      # the digest case's input
+    npart = pos_h.shape[1]
+    planted = {0: [11, 5000011], 1: [77, 9000077], 2: [123, 16000123]}        # axis -> particle indices
+    for axis, idx in planted.items():
+        pos_h[axis, idx] = np.float32(512.0)
     pos, vel = dev(pos_h), dev(vel_h)
+    state = pm.ResidentParticles(pos, vel)
+    rp, rv = torch.empty_like(pos), torch.empty_like(vel)
     fg_o = O.fourier_grid(cfg)
     fg = pm.fourier_grid()
     rho = torch.empty((512, 512, 512), dtype=torch.float32, device="cuda")
+    rho_r = torch.empty_like(rho)
     da = (cfg.A_END - cfg.A_INIT) / cfg.STEPS
     a = cfg.A_INIT
-    for s in range(2):
-        rho_o = O.density(pos_h, 8.0, cfg)
-        phi_o = O.potential(rho_o, fg_o, a, cfg).astype(np.float64)
+    phi_o = np.empty((512, 512, 512), dtype=np.float32)
+
+    def pos_err(t):
+        d = (t.cpu().numpy().astype(np.float64) - pos_h + 256.0) % 512.0 - 256.0
+        return np.linalg.norm(d) / np.linalg.norm(pos_h.astype(np.float64))
+
+    for s in range(3):
+        keys_o = O.cell_keys(pos_h, cfg)
+        rho_o = O.density(pos_h, 8.0, cfg1)
+        if s == 0:
+            # the planted particles deposit -(Nc-1)*m*w and +Nc*m*w (Q4): the mesh holds negative cells
+            assert rho_o.min() < -100.0
+            keys = torch.empty(npart, dtype=torch.int32, device="cuda")
+            plan = pm._runtime.get_plan(512, npart, 0)
+            pm._runtime.check(pm._runtime.lib().pm_cell_keys(plan.handle, pos.data_ptr(), npart, keys.data_ptr(), None), "keys")
+            assert np.array_equal(keys.cpu().numpy().astype(np.int64), keys_o)        # bit-exact at full size
+            del keys
         phi = pm.potential(pm.density(pos, 8.0), fg, a).cpu().numpy()
-        assert rel_l2(phi - phi.mean(dtype=np.float64), phi_o - phi_o.mean()) <= REL_L2, f"potential step {s}"
-        del phi, phi_o
-        O.advance_time(rho_o, pos_h, vel_h, fg_o, a, da, cfg)
-        pm.step(pos, vel, a, da, rho_out=rho)
-        assert rel_l2(rho.cpu().numpy(), rho_o) <= REL_L2, f"density step {s}"
-        d = (pos.cpu().numpy().astype(np.float64) - pos_h + 256.0) % 512.0 - 256.0
-        assert np.linalg.norm(d) / np.linalg.norm(pos_h.astype(np.float64)) <= REL_L2, f"positions step {s}"
-        assert rel_l2(vel.cpu().numpy(), vel_h) <= REL_L2, f"velocities step {s}"
+        O.advance_time(rho_o, pos_h, vel_h, fg_o, a, da, cfg, phi_out=phi_o)
+        assert rel_l2(phi - phi.mean(dtype=np.float64), phi_o.astype(np.float64) - phi_o.mean(dtype=np.float64)) <= REL_L2, \
+            f"potential step {s}"
+        del phi
+        pm.step(pos, vel, a, da, rho_out=rho)                     # stateless path, caller order
+        state.step(a, da, rho_out=rho_r)                          # resident path (what bench.py times)
+        state.store(rp, rv)
+        for name, r_, p_, v_ in (("stateless", rho, pos, vel), ("resident", rho_r, rp, rv)):
+            assert rel_l2(r_.cpu().numpy(), rho_o) <= REL_L2, f"{name}: density step {s}"
+            assert pos_err(p_) <= REL_L2, f"{name}: positions step {s}"
+            assert rel_l2(v_.cpu().numpy(), vel_h) <= REL_L2, f"{name}: velocities step {s}"
         a += da
+    # the resident run really took the fast path: incremental sort after the first step
+    assert state.sort_stats()[2] == "incremental"
+    del state
+    pm.release_plans()
+    torch.cuda.empty_cache()
+
+
+def test_tiled_gather_512_equals_flat_gather_bit_for_bit(pm):
+    """k_gather_tiled<512,...> -- the kernel bench.py's roofline line is about -- against
+    k_gather_kick_drift at the headline size, 256^3 particles on 512^3 cells: positions, velocities and
+    storage order bit for bit over three resident steps, with a blob that overflows the staging
+    capacity of a (z, row-block) step and particles sitting exactly on z == N_CELLS."""
+    cfg = O.Config(N_CELLS=512, N_PARTS=256, STEPS=1000)
+    pm.set_config(cfg_ns(cfg))
+    rt = pm._runtime
+    g = torch.Generator().manual_seed(7)
+    pos_c = torch.rand((3, 256 ** 3), generator=g) * 512.0
+    vel_c = torch.randn((3, 256 ** 3), generator=g) * 0.3
+    pos_c[:, :40000] = torch.remainder(256.0 + 0.7 * torch.randn((3, 40000), generator=g), 512.0)
+    pos_c[2, 40000:40100] = 512.0
+    pos_c[0, 40100:40200] = 512.0
+    out = {}
+    for tiled in (0, 1):
+        pm.release_plans()
+        p, v = pos_c.cuda(), vel_c.cuda()
+        st = pm.ResidentParticles(p, v)
+        rt.check(rt.lib().pm_plan_set_gather_tiled(st.plan.handle, tiled), "tiled")
+        a, da = 0.02, 0.00099
+        for _ in range(3):
+            st.step(a, da)
+            a += da
+        if tiled:
+            assert st.block_stats()["blocks_over_cap"] > 0       # the overflow path really ran
+        st.store(p, v)
+        out[tiled] = (p.cpu(), v.cpu(), st.order().cpu())
+        del st, p, v
+    pm.release_plans()
+    torch.cuda.empty_cache()
+    assert torch.equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][1], out[1][1])
+    assert torch.equal(out[0][2], out[1][2])
 
 
 def test_full_run_power_spectrum_64_on_128(pm):
