@@ -365,7 +365,7 @@ def run_slab(args, rank, world, local_rank):
         if n_parts > 256:
             # large configurations: every rank generates its own slab on its GPU
             pl, vl, il = make_particles_slab_gpu(n_parts, n_cells, rank, world, dev)
-            out = [slab.make_rank_from_local(n_cells, pl, vl, il, rank, world, device=dev)]
+            out = [slab.make_rank_from_local(n_cells, pl, vl, il, rank, world, device=dev, total_particles=npart)]
             cnt = torch.tensor([pl.shape[1]], dtype=torch.int64, device=f"cuda:{dev}")
             dist.all_reduce(cnt)
             assert int(cnt.item()) == npart, (int(cnt.item()), npart)
@@ -394,7 +394,7 @@ def run_slab(args, rank, world, local_rank):
         for _ in range(W):
             a, da = sched[step_i % len(sched)]
             slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, chunks=args.chunks or None, transport=transport,
-                           ghosts=ghosts)
+                           ghosts=ghosts, migrate=migrate)
             step_i += 1
         barrier()
 
@@ -402,21 +402,24 @@ def run_slab(args, rank, world, local_rank):
     # setup_peers() ends with a flag handshake through the mapped memory and all ranks agree on the
     # outcome; if the set-up fails, or a flag wait times out during warm-up on any rank, every rank
     # rebuilds its state and runs the NCCL all-to-all path instead -- and the JSON line says which.
-    transport, transport_note, ghosts = "nccl", "", "nccl"
+    transport, transport_note, ghosts, migrate = "nccl", "", "nccl", "nccl"
     if args.transport != "nccl":
         transport = (args.transport if args.transport in ("peer", "fused2") else "fused") if slab.setup_peers(ranks, comm) else "nccl"
         if transport == "nccl":
             transport_note = "peer-memory set-up failed; "
-    if args.ghosts == "peer":
-        if transport == "nccl" or not slab.setup_ghost_peers(ranks, comm):
-            raise RuntimeError("--ghosts peer needs a working peer-memory set-up")
-        ghosts = "peer"
+    if transport != "nccl" and (args.ghosts != "nccl" or args.migrate != "nccl"):
+        # ghost planes and particle migration through the same peer mappings (default when they can be set up)
+        if slab.setup_ghost_peers(ranks, comm):
+            ghosts = "nccl" if args.ghosts == "nccl" else "peer"
+            migrate = "nccl" if args.migrate == "nccl" else "peer"
+        elif "peer" in (args.ghosts, args.migrate):
+            raise RuntimeError("--ghosts/--migrate peer need a working peer-memory set-up")
     warm_up(transport)
     if transport != "nccl":
         bad = torch.tensor([ranks[0].peer_timeouts()], dtype=torch.int64, device=f"cuda:{dev}")
         dist.all_reduce(bad, op=dist.ReduceOp.MAX)
         if int(bad.item()):
-            transport, transport_note, ghosts = "nccl", "peer-memory flag wait timed out in warm-up; ", "nccl"
+            transport, transport_note, ghosts, migrate = "nccl", "peer-memory flag wait timed out in warm-up; ", "nccl", "nccl"
             slab.release_peers(ranks, comm)
             for r in ranks:
                 r.close()
@@ -441,7 +444,7 @@ def run_slab(args, rank, world, local_rank):
     for _ in range(K):
         a, da = sched[step_i % len(sched)]
         slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, timer=timer, chunks=args.chunks or None,
-                       transport=transport, ghosts=ghosts)
+                       transport=transport, ghosts=ghosts, migrate=migrate)
         step_i += 1
     ev1.record()
     barrier()
@@ -493,7 +496,7 @@ def run_slab(args, rank, world, local_rank):
             di = hid.to(f"cuda:{dev}", non_blocking=True)
             h2d += n_host * 4 * 7
             sr.load(dp, dv, di)
-            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, transport=transport, ghosts=ghosts)
+            slab.slab_step(ranks, comm, a, da, mass=mass, cfg=cfg, transport=transport, ghosts=ghosts, migrate=migrate)
             p, v, ids = sr.export()
             n_host = p.shape[1]
             hp, hv, hid = host_views(n_host)
@@ -533,15 +536,17 @@ def run_slab(args, rank, world, local_rank):
                        "n_parts": n_parts, "n_cells": n_cells,
                        "particles": particles_desc,
                        "l2": "inputs larger than L2",
-                       "parallelism": f"slab decomposition along z over {world} GPUs: NCCL send/recv ghost planes, "
+                       "parallelism": f"slab decomposition along z over {world} GPUs: ghost planes by "
+                                      + ("peer-memory stores" if ghosts == "peer" else "NCCL send/recv") + ", "
                                       + {"fused": "FFT transposes fused into the y passes (stores into / loads from the peers' "
                                                   "z-pass arrays over NVLink, CUDA IPC, flag-word barriers), ",
                                          "fused2": "FFT transposes fused into the y passes, y passes and z passes on two streams (experimental), ",
                                          "peer": "FFT transposes by peer-memory copy kernels over NVLink (CUDA IPC, flag-word barriers), ",
                                          "nccl": "FFT transposes by NCCL all-to-all, "}[transport]
                                       + f"pipelined in {chunks} kx chunks" + ("" if transport == "fused" else " on two streams")
-                                      + ", all-to-all-v particle migration",
-                       "fft_transport": transport_note + transport, "ghost_planes": ghosts},
+                                      + (", particle migration through peer memory (count matrix + records, one host read)"
+                                         if migrate == "peer" else ", all-to-all-v particle migration"),
+                       "fft_transport": transport_note + transport, "ghost_planes": ghosts, "migration": migrate},
             "clocks": clocks,
             "e2e": None if e2e_value is None else {
                     "value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": float(t[1].item()) / ke,
@@ -598,7 +603,6 @@ def run_ours(args, rank, world, local_rank):
         pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
         particles_desc = "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA
     pos, vel = pos_h.to(f"cuda:{dev}"), vel_h.to(f"cuda:{dev}")
-    plan = rt.get_plan(n_cells, npart, dev)
     sched = pm.loop_scale_factors(cfg)
     if args.particles == "evolved":
         sched = [(a_last, da_last)]          # keep stepping at the late-time scale factor
@@ -611,6 +615,7 @@ def run_ours(args, rank, world, local_rank):
     K, W = args.steps, args.warmup
     step_i = 0
     state = pm.ResidentParticles(pos, vel)   # state resident in HBM, cell-ordered between steps
+    plan = state.plan
     for _ in range(W):
         a, da = sched[step_i % len(sched)]
         state.step(a, da, mass=mass)
@@ -759,8 +764,10 @@ def main():
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
     ap.add_argument("--transport", default="auto", choices=["auto", "fused", "fused2", "peer", "nccl"],
                     help="FFT transposes of the multi-GPU path: peer-memory copy kernels or NCCL all-to-all")
-    ap.add_argument("--ghosts", default="nccl", choices=["nccl", "peer"],
-                    help="multi-GPU ghost planes: NCCL send/recv (default) or EXPERIMENTAL pushes through peer memory")
+    ap.add_argument("--ghosts", default="auto", choices=["auto", "nccl", "peer"],
+                    help="multi-GPU ghost planes: stores into the neighbours' memory (default when the peer set-up works) or NCCL send/recv")
+    ap.add_argument("--migrate", default="auto", choices=["auto", "nccl", "peer"],
+                    help="multi-GPU particle migration: through peer memory (default when the peer set-up works) or NCCL all-to-all-v")
     ap.add_argument("--reference-budget-s", type=float, default=90.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -96,6 +96,10 @@ def lib():
             "pm_step_host": (i32, [vp, vp, vp, i64, f64, f64, f64, f64, f64, vp]),
             "pm_particles_load": (i32, [vp, vp, vp, i64, vp]),
             "pm_step_resident": (i32, [vp, f64, f64, f64, f64, f64, vp, vp]),
+            "pm_plan_set_graph": (i32, [vp, i32]),
+            "pm_plan_graph_replays": (i32, [vp]),
+            "pm_resident_deposit": (i32, [vp, f64, vp, vp]),
+            "pm_resident_advance": (i32, [vp, vp, f64, f64, f64, f64, f64, vp]),
             "pm_particles_store": (i32, [vp, vp, vp, vp]),
             "pm_particles_order": (i32, [vp, vp, vp]),
             "pm_particles_count": (i64, [vp]),
@@ -107,6 +111,7 @@ def lib():
             "pm_slab_deposit": (i32, [vp, f64, vp]),
             "pm_slab_ghost_add": (i32, [vp, vp]),
             "pm_slab_fft_rows_forward": (i32, [vp, vp]),
+            "pm_slab_set_rho_mean": (i32, [vp, f64]),
             "pm_slab_fft_y_forward": (i32, [vp, i32, i32, vp]),
             "pm_slab_fft_z": (i32, [vp, i32, i32, f64, f64, vp]),
             "pm_slab_fft_y_inverse": (i32, [vp, i32, i32, vp]),
@@ -133,6 +138,14 @@ def lib():
             "pm_slab_ghost_wait_rho": (i32, [vp, vp]),
             "pm_slab_ghost_push_phi": (i32, [vp, vp]),
             "pm_slab_ghost_wait_phi": (i32, [vp, vp]),
+            "pm_slab_peer_aux_export": (i32, [vp, ctypes.POINTER(ctypes.c_uint64)]),
+            "pm_slab_peer_aux_import": (i32, [vp, i32, ctypes.POINTER(ctypes.c_uint64)]),
+            "pm_slab_peer_aux_set": (i32, [vp, i32, vp, vp, vp]),
+            "pm_slab_aux_buffers": (i32, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]),
+            "pm_slab_migrate_counts_push": (i32, [vp, vp]),
+            "pm_slab_migrate_counts_read": (i32, [vp, vp, vp]),
+            "pm_slab_migrate_push": (i32, [vp, vp, vp, vp]),
+            "pm_slab_migrate_wait": (i32, [vp, vp]),
             "pm_slab_fft_y_forward_push": (i32, [vp, i32, i32, vp]),
             "pm_slab_fft_y_inverse_pull": (i32, [vp, i32, i32, vp]),
             "pm_ic_workspace_bytes": (sz, [i32]),
@@ -156,10 +169,10 @@ EXPORTED_SYMBOLS = (
     "pm_plan_workspace_bytes", "pm_plan_create", "pm_plan_destroy", "pm_plan_n_cells",
     "pm_plan_np_capacity", "pm_fourier_grid", "pm_cell_keys", "pm_sort_by_cell", "pm_deposit_cic",
     "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_plan_profile_begin",
-    "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_particles_store",
+    "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_resident_deposit", "pm_resident_advance", "pm_plan_set_graph", "pm_plan_graph_replays", "pm_particles_store",
     "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend",
     "pm_plan_create_slab", "pm_slab_buffer", "pm_slab_load", "pm_slab_count", "pm_slab_entries",
-    "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_rows_forward", "pm_slab_fft_y_forward",
+    "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_rows_forward", "pm_slab_set_rho_mean", "pm_slab_fft_y_forward",
     "pm_slab_fft_z", "pm_slab_fft_y_inverse", "pm_slab_fft_rows_inverse", "pm_slab_gather",
     "pm_slab_migrate_pack", "pm_slab_migrate_unpack", "pm_slab_export",
     "pm_slab_peer_export", "pm_slab_peer_import", "pm_slab_peer_set", "pm_slab_peer_signal", "pm_slab_peer_wait",
@@ -167,6 +180,8 @@ EXPORTED_SYMBOLS = (
     "pm_slab_fft_y_inverse_local", "pm_slab_fft_y_forward_push", "pm_slab_fft_y_inverse_pull",
     "pm_slab_peer_ghost_export", "pm_slab_peer_ghost_import", "pm_slab_peer_ghost_set", "pm_slab_ghost_push_rho",
     "pm_slab_ghost_wait_rho", "pm_slab_ghost_push_phi", "pm_slab_ghost_wait_phi", "pm_power_spectrum",
+    "pm_slab_peer_aux_export", "pm_slab_peer_aux_import", "pm_slab_peer_aux_set", "pm_slab_aux_buffers",
+    "pm_slab_migrate_counts_push", "pm_slab_migrate_counts_read", "pm_slab_migrate_push", "pm_slab_migrate_wait",
     "pm_plan_set_sort_mode", "pm_plan_sort_stats", "pm_plan_set_fft_fuse", "pm_plan_fft_sync_errors",
     "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled", "pm_plan_gather_tile", "pm_plan_block_stats", "pm_ic_workspace_bytes", "pm_ic_noise",
     "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",
@@ -254,6 +269,11 @@ def get_plan(n_cells: int, np_needed: int, device: int) -> Plan:
 
 
 def release_plans():
+    try:
+        from . import _session
+    except ImportError:
+        import _session
+    _session.forget()
     for plan in _plans.values():
         plan.close()
     _plans.clear()

@@ -1,4 +1,5 @@
 // pm_api.cu -- the extern "C" surface declared in include/pmstep.h.
+#include <math.h>
 #include <new>
 #include <stdlib.h>
 #include <string.h>
@@ -63,7 +64,7 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->iota = align_up(npad * 4);
     L->keys_sorted = align_up(npad * 4);
     L->order_sorted = align_up(npad * 4);
-    L->cub = align_up(pm_sort_temp_bytes(np > 0 ? np : 1, g.slab ? 32 : key_bits_for(nc)));
+    L->cub = align_up(npad * 8) + align_up(256) + align_up(((size_t)PM_SORT_MAX_GRID * 2 + 1) * 512 * 4);   // sort_tmp, sort_ctl, sort_hist (+ prefixes, totals)
     L->row_start = align_up(((size_t)nzl * nc * pm_deposit_segments(nc) + 1) * 4);
     L->mesh = align_up(plane * (nzl + (g.slab ? 1 : 0)) * 4);    // rho (+ ghost plane)
     L->mesh2 = align_up(plane * (nzl + (g.slab ? 3 : 0)) * 4);   // phi (+ 1 + 2 ghost planes)
@@ -81,14 +82,15 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->leave_slot = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 4) : 0;
     L->leave_sorted = g.slab ? align_up((size_t)L->leave_cap * 4) : 0;
     L->mig = g.slab ? align_up((size_t)g.nranks * L->leave_cap * 7 * 4) : 0;
-    L->peer_flags = g.slab ? align_up((size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4) : 0;
+    L->peer_flags = g.slab ? align_up((size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4) + align_up((size_t)PM_PEER_MAX * PM_MIG_ROW * 4) : 0;
     // incremental sort: stayers (np), movers in and out (capacity each), tile tables
     L->inc_bcap = pm_sort_mover_capacity((int64_t)npad);
     L->inc_a = align_up(npad * 8);
     L->inc_b = align_up((size_t)L->inc_bcap * 8);
     L->inc_tile = align_up(((size_t)pm_sort_tiles((int64_t)npad) + 2) * 4);
     L->fft_sync = align_up((size_t)(2 * (nc + 1) + 1) * 4);
-    L->total = kAlign /* diag */ + L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
+    L->total = align_up((size_t)512 * 8192 * 8) /* dep_scratch */ + align_up(64 + 512 * 4) /* dep ctl + slot_tile */ +
+               align_up((size_t)16384 * 16) /* dep_items */ + kAlign /* diag */ + align_up(1024 * sizeof(double) + 64) /* mean */ + L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
                L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw +
                2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot +
                L->leave_sorted + 2 * L->mig + L->peer_flags + L->inc_a + 2 * L->inc_b + 2 * L->inc_tile;
@@ -211,8 +213,10 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     p->iota = (uint32_t *)c;          c += L.iota;
     p->keys_sorted = (uint32_t *)c;   c += L.keys_sorted;
     p->order_sorted = (uint32_t *)c;  c += L.order_sorted;
-    p->cub_tmp = c;                   c += L.cub;
-    p->cub_bytes = L.cub;
+    p->sort_tmp = (uint64_t *)c;
+    p->sort_ctl = c + align_up((size_t)((np_capacity + 3) / 4 * 4) * 8);
+    p->sort_hist = (uint32_t *)((char *)p->sort_ctl + align_up(256));
+    c += L.cub;
     p->row_start = (uint32_t *)c;     c += L.row_start;
     p->mesh = (float *)c;             c += L.mesh;
     p->mesh2 = (float *)c;            c += L.mesh2;
@@ -236,7 +240,9 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         p->mig_send = (float *)c;     c += L.mig;
         p->mig_recv = (float *)c;     c += L.mig;
         p->leave_cap = L.leave_cap;
-        p->peer_flags = (uint32_t *)c; c += L.peer_flags;
+        p->peer_flags = (uint32_t *)c;
+        p->mig_matrix = (uint32_t *)(c + align_up((size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4));
+        c += L.peer_flags;
     }
     p->inc_a = (uint64_t *)c;         c += L.inc_a;
     p->inc_b = (uint64_t *)c;         c += L.inc_b;
@@ -245,7 +251,13 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     p->inc_split = (uint32_t *)c;     c += L.inc_tile;
     p->inc_bcap = L.inc_bcap;
     p->fft_sync = (unsigned *)c;      c += L.fft_sync;
-    p->diag = c;                      c += kAlign;
+    p->diag = c;                      p->step_params_d = (PmStepParams *)(c + 256);  c += kAlign;
+    p->dep_scratch = (unsigned long long *)c;  c += align_up((size_t)512 * 8192 * 8);
+    p->dep_ctl = (uint32_t *)c;       p->dep_slot_tile = (uint32_t *)(c + 64);  c += align_up(64 + 512 * 4);
+    p->dep_items = c;                 c += align_up((size_t)16384 * 16);
+    p->mean_ws = (double *)c;         p->rho_mean_d = (float *)(c + 1024 * sizeof(double));
+    c += align_up(1024 * sizeof(double) + 64);
+    p->rho_mean_hint = NAN;
     {
         const char *fu = getenv("PM_FFT_FUSE");   // "0": separate row and y launches (A/B checks)
         const char *lg = getenv("PM_FFT_LAG");
@@ -266,16 +278,20 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     {
         const char *gt = getenv("PM_GATHER_TILED");   // "0": one thread per particle, scattered phi loads
         p->gather_tiled = !(gt && strcmp(gt, "0") == 0);
+        const char *gw = getenv("PM_GATHER_WS");      // "0": the barrier-per-step tiled kernel (A/B checks)
+        p->gather_ws = !(gw && strcmp(gw, "0") == 0);
+    }
+    {
+        const char *gr = getenv("PM_GRAPH");     // "0": never replay the resident step as a CUDA graph
+        p->use_graph = !(gr && strcmp(gr, "0") == 0);
+    }
+    {
+        const char *dp = getenv("PM_DEPOSIT");   // "rows": one warp per output row (k_deposit_rows; A/B checks)
+        p->deposit_tiles = !(dp && strcmp(dp, "rows") == 0);
     }
     {
         const char *sm = getenv("PM_SORT");   // "full" forces the radix sort of every entry (A/B checks)
         p->sort_mode = (sm && strcmp(sm, "full") == 0) ? PM_SORT_FULL : PM_SORT_AUTO;
-    }
-    if (cudaHostAlloc((void **)&p->h_word, 64, cudaHostAllocDefault) != cudaSuccess) {
-        cudaGetLastError();
-        p->h_word = nullptr;
-        pm_plan_destroy(p);
-        return PM_ERR_NOMEM;
     }
 
     if (p->have_fft && (cufftSetWorkArea(p->r2c, p->fft_work) != CUFFT_SUCCESS ||
@@ -290,8 +306,16 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     }
     if (rc == PM_OK && pm_fft_supported(n_cells)) rc = pm_k_fft_tables(p);
     if (rc == PM_OK) rc = (int)cudaMemset(p->fft_sync, 0, sizeof(unsigned));
+    if (rc == PM_OK) rc = (int)cudaMemset(p->sort_ctl, 0, 256);
+    if (rc == PM_OK) rc = (int)cudaMemset(p->dep_scratch, 0, (size_t)512 * 8192 * 8);   // all-zero between steps (k_deposit_slots)
     if (rc == PM_OK && p->peer_flags)
         rc = (int)cudaMemset(p->peer_flags, 0, (size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4);
+    if (rc == PM_OK && p->mig_matrix) rc = (int)cudaMemset(p->mig_matrix, 0, (size_t)PM_PEER_MAX * PM_MIG_ROW * 4);
+    if (rc == PM_OK && g.slab && cudaHostAlloc((void **)&p->mig_matrix_h, (size_t)PM_PEER_MAX * PM_MIG_ROW * 4, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        p->mig_matrix_h = nullptr;
+        rc = PM_ERR_NOMEM;
+    }
     if (rc == PM_OK) rc = pm_k_iota(p->iota, np_capacity, 0);
     if (rc == PM_OK) rc = (int)cudaStreamSynchronize(0);
     if (rc == PM_OK) rc = (int)cudaStreamCreateWithFlags(&p->s_main, cudaStreamNonBlocking);
@@ -338,8 +362,10 @@ int pm_plan_destroy(pm_plan *p)
     if (p->s_down) cudaStreamDestroy(p->s_down);
     for (int s = 0; s < PM_PEER_MAX; ++s)
         if (p->peer_ipc[s]) cudaIpcCloseMemHandle(p->peer_ipc[s]);
+    for (int k = 0; k < 2; ++k)
+        if (p->graph_exec[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[k]);
+    if (p->mig_matrix_h) cudaFreeHost(p->mig_matrix_h);
     if (p->ws) cudaFree(p->ws);
-    if (p->h_word) cudaFreeHost(p->h_word);
     if (p->prof_ev) {
         for (int i = 0; i < p->prof_cap * (PM_NUM_STAGES + 1); ++i) cudaEventDestroy(p->prof_ev[i]);
         free(p->prof_ev);
@@ -369,10 +395,10 @@ int pm_plan_set_sort_mode(pm_plan *p, int mode)
 int pm_plan_sort_stats(const pm_plan *p, int64_t *entries, int64_t *movers, int *mode)
 {
     if (!p) return PM_ERR_INVALID;
-    if (entries) *entries = p->sort_last_n;
-    if (movers) *movers = p->sort_last_movers;
-    if (mode) *mode = p->sort_last_mode;
-    return PM_OK;
+    DeviceGuard guard;
+    int rc = guard.enter(p->device);
+    if (rc != PM_OK) return rc;
+    return pm_k_sort_stats(const_cast<pm_plan *>(p), entries, movers, mode);
 }
 
 int pm_plan_fft_backend(const pm_plan *p) { return p ? (p->own_fft ? 0 : 1) : PM_ERR_INVALID; }
@@ -464,6 +490,7 @@ int pm_sort_by_cell(pm_plan *p, const float *pos_d, int64_t np, uint32_t *keys_s
     cudaStream_t st = pm_cu(stream);
     p->rkeys_valid = false;
     p->rsorted_n = 0;
+    p->rsort_done = false;
     PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, 0, st));
     if (np == 0) return PM_OK;
@@ -484,6 +511,7 @@ int pm_deposit_cic(pm_plan *p, const float *pos_d, int64_t np, double mass, floa
     cudaStream_t st = pm_cu(stream);
     p->rkeys_valid = false;
     p->rsorted_n = 0;
+    p->rsort_done = false;
     PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, 0, st));
     PM_TRY(pm_k_row_offsets(p, np, st));
@@ -496,6 +524,7 @@ int pm_poisson(pm_plan *p, const float *rho_d, double a, double omega_m0, float 
     PM_ARGS(p && rho_d && phi_d && a != 0.0);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
+    p->rho_mean_hint = NAN;   // an arbitrary mesh: its mean is measured
     return pm_k_poisson(p, rho_d, a, omega_m0, phi_d, pm_cu(stream));
 }
 
@@ -528,6 +557,7 @@ int pm_step(pm_plan *p, float *pos_d, float *vel_d, int64_t np, double mass, dou
     float *rho = rho_d ? rho_d : p->mesh;
     p->rkeys_valid = false;
     p->rsorted_n = 0;
+    p->rsort_done = false;
     pm_prof_mark(p, 0, st);
     PM_TRY(pm_k_cell_keys(p, pos_d, np, np, p->keys, nullptr, st));
     pm_prof_mark(p, PM_STAGE_KEYS + 1, st);
@@ -537,6 +567,7 @@ int pm_step(pm_plan *p, float *pos_d, float *vel_d, int64_t np, double mass, dou
     pm_prof_mark(p, PM_STAGE_ROWS + 1, st);
     PM_TRY(pm_k_deposit(p, pos_d, np, mass, rho, st));
     pm_prof_mark(p, PM_STAGE_DEPOSIT + 1, st);
+    p->rho_mean_hint = (double)np * mass / ((double)p->nc * p->nc * p->nc);   // CIC weights sum to 1 (density.py:28-47)
     PM_TRY(pm_k_poisson(p, rho, a, omega_m0, p->mesh2, st));  // marks R2C, GREEN, C2R itself
     PM_TRY(pm_k_gather_kick_drift(p, pos_d, vel_d, np, p->mesh2, a, f_a1, da, nullptr, st));
     pm_prof_mark(p, PM_STAGE_GATHER + 1, st);
@@ -581,12 +612,15 @@ int pm_plan_profile_read(pm_plan *p, float *ms, int *n_steps)
 }
 
 // ---- resident particle state -------------------------------------------------------------------
-static int resident_step(pm_plan *p, double mass, double a, double da, double f_a1,
-                         double omega_m0, float *rho_d, cudaStream_t st)
+// The two halves of a resident step.  Set rcur is stored in the cell order of the previous sort; the
+// first half orders it anew and deposits, the second solves for the potential and moves the particles
+// into the other set.  p->rsort_done: (keys_sorted, order_sorted, row_start) describe set rcur as it
+// is now -- a second deposit of the same state (the caller wants the density again) must not sort
+// again, because the incremental sort compares against the keys the list was LAST sorted by.
+static int resident_sort(pm_plan *p, cudaStream_t st)
 {
     const int64_t np = p->rnp;
-    float *rho = rho_d ? rho_d : p->mesh;
-    pm_prof_mark(p, 0, st);
+    if (p->rsort_done) return PM_OK;
     if (!p->rkeys_valid) {
         PM_TRY(pm_k_cell_keys(p, p->rpos[p->rcur], np, p->rstride, p->keys, nullptr, st));
         p->rsorted_n = 0;
@@ -596,8 +630,25 @@ static int resident_step(pm_plan *p, double mass, double a, double da, double f_
     pm_prof_mark(p, PM_STAGE_SORT + 1, st);
     PM_TRY(pm_k_row_offsets(p, np, st));
     pm_prof_mark(p, PM_STAGE_ROWS + 1, st);
+    p->rsort_done = true;
+    return PM_OK;
+}
+
+static int resident_deposit(pm_plan *p, double mass, float *rho, cudaStream_t st)
+{
+    pm_prof_mark(p, 0, st);
+    PM_TRY(resident_sort(p, st));
     PM_TRY(pm_k_deposit(p, p->rpos[p->rcur], p->rstride, mass, rho, st));
     pm_prof_mark(p, PM_STAGE_DEPOSIT + 1, st);
+    return PM_OK;
+}
+
+static int resident_advance(pm_plan *p, const float *rho, double rho_mean, double a, double da, double f_a1,
+                            double omega_m0, cudaStream_t st)
+{
+    const int64_t np = p->rnp;
+    PM_TRY(resident_sort(p, st));           // no-op after resident_deposit
+    p->rho_mean_hint = rho_mean;
     PM_TRY(pm_k_poisson(p, rho, a, omega_m0, p->mesh2, st));
     PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));
     pm_prof_mark(p, PM_STAGE_GATHER + 1, st);
@@ -605,7 +656,17 @@ static int resident_step(pm_plan *p, double mass, double a, double da, double f_
     p->rcur ^= 1;
     p->rkeys_valid = (np > 0);
     p->rsorted_n = np;   // set rcur is stored in the order of this step's sort
+    p->rsort_done = false;
     return PM_OK;
+}
+
+static int resident_step(pm_plan *p, double mass, double a, double da, double f_a1,
+                         double omega_m0, float *rho_d, cudaStream_t st)
+{
+    float *rho = rho_d ? rho_d : p->mesh;
+    PM_TRY(resident_deposit(p, mass, rho, st));
+    const double mean = (double)p->rnp * mass / ((double)p->nc * p->nc * p->nc);   // CIC weights sum to 1 (density.py:28-47)
+    return resident_advance(p, rho, mean, a, da, f_a1, omega_m0, st);
 }
 
 int pm_particles_load(pm_plan *p, const float *pos_d, const float *vel_d, int64_t np,
@@ -620,6 +681,7 @@ int pm_particles_load(pm_plan *p, const float *pos_d, const float *vel_d, int64_
     p->rnp = p->rtotal = np;
     p->rkeys_valid = false;
     p->rsorted_n = 0;
+    p->rsort_done = false;
     if (np == 0) return PM_OK;
     (void)b;
     const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
@@ -650,13 +712,155 @@ int pm_particles_order(pm_plan *p, uint32_t *ids_d, pm_stream_t stream)
     return PM_OK;
 }
 
+// ---- the resident step as a CUDA graph -----------------------------------------------------------
+// In steady state a resident step is a fixed sequence of ~20 launches whose only step-dependent inputs
+// are six scalars (the gather's kick/drift factors and the Green's factor): the sort decides between its
+// two ways on the device, the buffer sets alternate with period two.  So two graphs are captured (one
+// per buffer-set parity) from the very code path that runs eagerly, with the kernels told to read the
+// scalars from PmStepParams in device memory, and a replay only re-parameterises the one-thread kernel
+// node that writes that struct.  Reference: the loop body src/pmesh.py:56-63.
+__global__ void k_set_step_params(PmStepParams v, PmStepParams *dst) { *dst = v; }
+
+static void graph_drop(pm_plan *p, int k)
+{
+    if (p->graph_exec[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[k]);
+    p->graph_exec[k] = nullptr;
+    p->graph_node[k] = nullptr;
+}
+
+static PmStepParams step_params_for(const pm_plan *p, double a, double da, double f_a1, double omega_m0)
+{
+    PmStepParams v;
+    memset(&v, 0, sizeof(v));
+    pm_gather_step_scalars(a, f_a1, da, &v);
+    const double m = (double)p->nc * p->nc * p->nc;
+    v.green_scale = (float)(-3 * omega_m0 / 8 / a / m);
+    return v;
+}
+
+static bool graph_eligible(const pm_plan *p)
+{
+    // steady state only: keys and mover counts come from the previous gather, the state is not yet sorted,
+    // nothing is being profiled, own FFT, tiled gather
+    return p->use_graph && !p->slab && p->own_fft && !p->prof_ev && p->rnp > 0 && p->rkeys_valid && p->inc_counted &&
+           p->rsorted_n == p->rnp && !p->rsort_done && p->sort_mode == PM_SORT_AUTO && pm_gather_graphable(p);
+}
+
+static int resident_step_graphed(pm_plan *p, double mass, double a, double da, double f_a1, double omega_m0,
+                                 float *rho_d, cudaStream_t st)
+{
+    if (!graph_eligible(p) || !st) return resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, st);   // no capture on the legacy stream
+    const int k = p->rcur;
+    float *rho = rho_d ? rho_d : p->mesh;
+    PmStepParams v = step_params_for(p, a, da, f_a1, omega_m0);
+    if (p->graph_exec[k] && (p->graph_rho[k] != rho || p->graph_mass[k] != mass || p->graph_omega[k] != omega_m0 ||
+                             p->graph_np[k] != p->rnp || p->graph_stream[k] != st))
+        graph_drop(p, k);
+    if (!p->graph_exec[k]) {
+        // capture this step's own launch sequence
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, st);
+        }
+        k_set_step_params<<<1, 1, 0, st>>>(v, p->step_params_d);
+        ++g_pm_launches;
+        p->graph_params = p->step_params_d;
+        const bool s_keys = p->rkeys_valid, s_cnt = p->inc_counted, s_done = p->rsort_done;
+        const int s_cur = p->rcur;
+        const int64_t s_n = p->rsorted_n;
+        const int rc = resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, st);
+        p->graph_params = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        // the captured launches did not run: put the bookkeeping back to "before the step"
+        p->rkeys_valid = s_keys; p->inc_counted = s_cnt; p->rsort_done = s_done; p->rcur = s_cur; p->rsorted_n = s_n;
+        if (rc != PM_OK || ce != cudaSuccess || !graph) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            p->use_graph = false;            // this configuration cannot be captured: stay eager
+            return resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, st);
+        }
+        cudaGraphExec_t exec = nullptr;
+        cudaGraphNode_t node = nullptr;
+        {
+            size_t n = 0;
+            cudaGraphGetNodes(graph, nullptr, &n);
+            cudaGraphNode_t *nodes = (cudaGraphNode_t *)malloc(sizeof(cudaGraphNode_t) * (n ? n : 1));
+            if (nodes && cudaGraphGetNodes(graph, nodes, &n) == cudaSuccess)
+                for (size_t i = 0; i < n && !node; ++i) {
+                    cudaGraphNodeType t;
+                    cudaKernelNodeParams kp;
+                    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel &&
+                        cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == (void *)k_set_step_params)
+                        node = nodes[i];
+                }
+            free(nodes);
+        }
+        if (!node || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphDestroy(graph);
+            p->use_graph = false;
+            return resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, st);
+        }
+        cudaGraphDestroy(graph);
+        p->graph_exec[k] = exec; p->graph_node[k] = node;
+        p->graph_rho[k] = rho; p->graph_mass[k] = mass; p->graph_omega[k] = omega_m0; p->graph_np[k] = p->rnp;
+        p->graph_stream[k] = st;
+    } else {
+        PmStepParams *dst = p->step_params_d;
+        void *args[2] = {&v, &dst};
+        cudaKernelNodeParams kp;
+        memset(&kp, 0, sizeof(kp));
+        kp.func = (void *)k_set_step_params;
+        kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.sharedMemBytes = 0; kp.kernelParams = args; kp.extra = nullptr;
+        PM_CUDA(cudaGraphExecKernelNodeSetParams((cudaGraphExec_t)p->graph_exec[k], (cudaGraphNode_t)p->graph_node[k], &kp));
+    }
+    PM_CUDA(cudaGraphLaunch((cudaGraphExec_t)p->graph_exec[k], st));
+    ++p->graph_replays;
+    // what resident_step leaves behind on the host
+    p->inc_counted = true;      // the gather counted the movers of the next sort
+    p->rcur ^= 1;
+    p->rkeys_valid = true;
+    p->rsorted_n = p->rnp;
+    p->rsort_done = false;
+    p->rows_valid = true;
+    p->sort_last_n = p->rnp;
+    return PM_OK;
+}
+
+int pm_plan_graph_replays(const pm_plan *p) { return p ? p->graph_replays : PM_ERR_INVALID; }
+
+int pm_plan_set_graph(pm_plan *p, int on)
+{
+    if (!p) return PM_ERR_INVALID;
+    p->use_graph = (on != 0);
+    return PM_OK;
+}
+
 int pm_step_resident(pm_plan *p, double mass, double a, double da, double f_a1, double omega_m0,
                      float *rho_d, pm_stream_t stream)
 {
     PM_ARGS(p && a != 0.0);
     DeviceGuard guard;
     PM_TRY(guard.enter(p->device));
-    return resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, pm_cu(stream));
+    return resident_step_graphed(p, mass, a, da, f_a1, omega_m0, rho_d, pm_cu(stream));
+}
+
+int pm_resident_deposit(pm_plan *p, double mass, float *rho_d, pm_stream_t stream)
+{
+    PM_ARGS(p && rho_d && !p->slab);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return resident_deposit(p, mass, rho_d, pm_cu(stream));
+}
+
+int pm_resident_advance(pm_plan *p, const float *rho_d, double rho_mean, double a, double da, double f_a1,
+                        double omega_m0, pm_stream_t stream)
+{
+    PM_ARGS(p && rho_d && a != 0.0 && !p->slab);
+    DeviceGuard guard;
+    PM_TRY(guard.enter(p->device));
+    return resident_advance(p, rho_d, rho_mean, a, da, f_a1, omega_m0, pm_cu(stream));
 }
 
 int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass, double a,
@@ -675,6 +879,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     p->rnp = np;
     p->rkeys_valid = false;
     p->rsorted_n = 0;
+    p->rsort_done = false;
     const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
     (void)pbytes;
     if (np) {
@@ -693,6 +898,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
         PM_CUDA(cudaStreamWaitEvent(p->s_down, p->ev_b, 0));
         PM_CUDA(cudaMemcpyAsync(rho_h, p->mesh, mbytes, cudaMemcpyDeviceToHost, p->s_down));
     }
+    p->rho_mean_hint = (double)np * mass / ((double)p->nc * p->nc * p->nc);
     PM_TRY(pm_k_poisson(p, p->mesh, a, omega_m0, p->mesh2, st));
     PM_CUDA(cudaStreamWaitEvent(st, p->ev_a, 0));
     PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));

@@ -231,6 +231,7 @@ struct ColArgs {
     const float *sin2, *sin2rev;   // natural / digit-reversed sin^2(pi i/N)
     const float *sin2y;            // in the order the y pass left the y axis in (v1: sin2rev, v2: sin2)
     float scale;       // -3*Omega_m/(8a)/N^3
+    const float *scale_ptr;   // non-null: the factor is read from device memory instead (CUDA-graph replays, pm_api.cu)
     int axis;          // 1: along y (tiles = z x kx-tile), 0: along z (tiles = y x kx-tile, + side)
     // z pass geometry: the array is [N z][nyl][hw] holding y positions [y0, y0+nyl) -- the whole
     // y range on one GPU, this rank's share after the all-to-all transpose in slab mode
@@ -508,6 +509,7 @@ __device__ __forceinline__ void fft_cols_tile(const ColArgs &a, const int t, flo
 template <int N, int MODE>
 __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols(ColArgs a)
 {
+    if (MODE == COL_FUSED && a.scale_ptr) a.scale = __ldg(a.scale_ptr);
     extern __shared__ float2 s_dyn[];
     float2 *s_tile = s_dyn;
     float2 *s_x = s_tile + N * kColsCN<N>;   // extra column
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(kThrC<N>, PM_FFT_MINB) k_fft_cols_peer(ColArgs
 template <int N, bool FWD, bool CG>
 __device__ __forceinline__ void fft_rows_tile(const float2 *__restrict__ in, float2 *__restrict__ out,
                                               const float2 *__restrict__ tw, const size_t row0,
-                                              float2 *s_tile, const float2 *s_tw)
+                                              float2 *s_tile, const float2 *s_tw, const float mean = 0.f)
 {
     constexpr int H = N / 2;
     constexpr int S = fft_stages(H);
@@ -578,6 +580,8 @@ __device__ __forceinline__ void fft_rows_tile(const float2 *__restrict__ in, flo
             for (int it = 0; it < LD_IT; ++it) {
                 const int idx = it * kThr<N> + tid;
                 buf[it] = in[(row0 + idx / H) * H + idx % H];   // rho: written by an earlier launch
+                buf[it].x -= mean;   // rho - <rho>: the DC mode is zeroed by the Green's factor anyway, and
+                buf[it].y -= mean;   // without it no float32 rounding of the huge DC lineage leaks into low k
             }
 #pragma unroll
             for (int it = 0; it < LD_IT; ++it) {
@@ -689,12 +693,14 @@ __device__ __forceinline__ void fft_rows_tile(const float2 *__restrict__ in, flo
 template <int N, bool FWD>
 __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__ in,
                                                        float2 *__restrict__ out,
-                                                       const float2 *__restrict__ tw)
+                                                       const float2 *__restrict__ tw,
+                                                       const float *__restrict__ mean_ptr)
 {
     extern __shared__ float2 s_dyn[];
     float2 *s_tw = s_dyn + (N / 2) * kPitch;   // N-entry twiddle table (visible after the first barrier)
     for (int m = threadIdx.x; m < N; m += kThr<N>) s_tw[m] = tw[m];
-    fft_rows_tile<N, FWD, false>(in, out, tw, (size_t)blockIdx.x * kCols, s_dyn, s_tw);
+    const float mean = (FWD && mean_ptr) ? __ldg(mean_ptr) : 0.f;   // forward: transform rho - <rho>
+    fft_rows_tile<N, FWD, false>(in, out, tw, (size_t)blockIdx.x * kCols, s_dyn, s_tw, mean);
 }
 
 #include "pm_fft2.cuh"
@@ -703,6 +709,7 @@ __global__ void __launch_bounds__(kThr<N>) k_fft_rows(const float2 *__restrict__
 template <int N, int MODE>
 __global__ void __launch_bounds__(kThr2, 2) k_fft2_cols(ColArgs a)
 {
+    if (MODE == COL_FUSED && a.scale_ptr) a.scale = __ldg(a.scale_ptr);
     extern __shared__ float2 s_dyn[];
     float2 *s_tw = s_dyn, *s_tile = s_dyn + N;
     for (int m = threadIdx.x; m < N; m += kThr2) s_tw[m] = a.tw[m];
@@ -713,13 +720,15 @@ __global__ void __launch_bounds__(kThr2, 2) k_fft2_cols(ColArgs a)
 template <int N, bool FWD>
 __global__ void __launch_bounds__(kThr2, 2) k_fft2_rows(const float2 *__restrict__ in,
                                                         float2 *__restrict__ out,
-                                                        const float2 *__restrict__ tw)
+                                                        const float2 *__restrict__ tw,
+                                                        const float *__restrict__ mean_ptr)
 {
     extern __shared__ float2 s_dyn[];
     float2 *s_tw = s_dyn, *s_tile = s_dyn + N;
     for (int m = threadIdx.x; m < N; m += kThr2) s_tw[m] = tw[m];
     __syncthreads();
-    fft2_rows_tile<N, FWD, false>(in, out, (size_t)blockIdx.x * kRowsPT2<N>, s_tile, s_tw);
+    const float mean = (FWD && mean_ptr) ? __ldg(mean_ptr) : 0.f;   // forward: transform rho - <rho>
+    fft2_rows_tile<N, FWD, false>(in, out, (size_t)blockIdx.x * kRowsPT2<N>, s_tile, s_tw, mean);
 }
 
 // ---- x and y passes of one direction in ONE persistent launch ------------------------------------
@@ -741,6 +750,7 @@ struct PlaneArgs {
     unsigned *ticket;       // [0] ticket counter, [1 + z] finished producer items of plane z
     unsigned *err;          // set if a wait gave up (must never happen; checked by the tests)
     int nplanes, lag;
+    const float *mean_ptr;  // forward: <rho>, subtracted while the rows are loaded (nullptr: 0)
 };
 
 __device__ __forceinline__ unsigned pm_ld_acquire(const unsigned *p)
@@ -796,8 +806,9 @@ __global__ void __launch_bounds__(kThrC<N>, V2 ? 2 : PM_FFT_MINB) k_fft_plane(Pl
         }
         if (FWD == producer) {
             const size_t row0 = (size_t)z * N + (size_t)idx * RT;
-            if constexpr (V2) fft2_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, row0, s_tile, s_tw);
-            else fft_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, pa.ca.tw, row0, s_tile, s_tw);
+            const float mean = (FWD && pa.mean_ptr) ? __ldg(pa.mean_ptr) : 0.f;
+            if constexpr (V2) fft2_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, row0, s_tile, s_tw, mean);
+            else fft_rows_tile<N, FWD, !FWD>(pa.rows_in, pa.rows_out, pa.ca.tw, row0, s_tile, s_tw, mean);
         } else {
             if constexpr (V2) fft2_cols_tile<N, FWD ? COL_FWD : COL_INV, FWD>(pa.ca, z * TPP + idx, s_tile, s_tw);
             else fft_cols_tile<N, FWD ? COL_FWD : COL_INV, FWD>(pa.ca, z * TPP + idx, s_tile, s_x, s_tw);
@@ -876,6 +887,7 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
         ca.sin2y = p->sin2;
         const double m = (double)N * N * N;
         ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
+        ca.scale_ptr = p->graph_params ? &p->graph_params->green_scale : nullptr;
         ca.nyl = N;
         ca.y0 = 0;
         ca.tpr = H / C;
@@ -894,13 +906,14 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
             pa.err = p->fft_sync;
             pa.nplanes = N;
             pa.lag = p->fft_lag;
+            pa.mean_ptr = p->rho_mean_d;
             pa.rows_in = reinterpret_cast<const float2 *>(rho);
             pa.rows_out = ca.main;
             pa.ticket = p->fft_sync + 1;
             PM_LAUNCH(plane_fwd, plane_per_sm * p->sm_count, kThr2, smem_cols, st, pa);
         } else {
             PM_LAUNCH(rows_fwd, row_ctas, kThr2, smem_rows, st, reinterpret_cast<const float2 *>(rho), ca.main,
-                      (const float2 *)p->tw);
+                      (const float2 *)p->tw, (const float *)p->rho_mean_d);
             ca.axis = 1;
             if (p->fft_v3 == 3 && ring3_fits) PM_LAUNCH(cols3_fwd3, grid3, kThr2, smem3_3, st, ca, tiles);
             else if (p->fft_v3) PM_LAUNCH(cols3_fwd2, grid3, kThr2, smem3_2, st, ca, tiles);
@@ -930,7 +943,7 @@ int poisson_launch_v2(pm_plan *p, const float *rho, double a, double omega_m0, f
             else if (p->fft_v3) PM_LAUNCH(cols3_inv2, grid3, kThr2, smem3_2, st, ca, tiles);
             else PM_LAUNCH(cols_inv, tiles, kThr2, smem_cols, st, ca);
             PM_LAUNCH(rows_inv, row_ctas, kThr2, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
-                      reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
+                      reinterpret_cast<float2 *>(phi), (const float2 *)p->tw, (const float *)nullptr);
         }
         pm_prof_mark(p, PM_STAGE_C2R + 1, st);
         PM_CHECK_LAUNCH();
@@ -969,6 +982,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
     ca.sin2y = p->sin2rev;
     const double m = (double)N * N * N;
     ca.scale = (float)(-3 * omega_m0 / 8 / a / m);
+    ca.scale_ptr = p->graph_params ? &p->graph_params->green_scale : nullptr;
     ca.nyl = N;
     ca.y0 = 0;
     ca.tpr = H / kColsCN<N>;
@@ -1006,6 +1020,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
             pa.err = p->fft_sync;
             pa.nplanes = N;
             pa.lag = p->fft_lag;
+            pa.mean_ptr = p->rho_mean_d;
         }
     }
     if (fused) {
@@ -1018,7 +1033,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
         }
     } else {
         PM_LAUNCH(rows_fwd, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(rho),
-                  ca.main, (const float2 *)p->tw);
+                  ca.main, (const float2 *)p->tw, (const float *)p->rho_mean_d);
         ca.axis = 1;
         PM_LAUNCH(cols_fwd, tiles, kThrC<N>, smem_cols, st, ca);
     }
@@ -1038,7 +1053,7 @@ int poisson_launch(pm_plan *p, const float *rho, double a, double omega_m0, floa
         ca.axis = 1;
         PM_LAUNCH(cols_inv, tiles, kThrC<N>, smem_cols, st, ca);
         PM_LAUNCH(rows_inv, row_ctas, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(ca.main),
-                  reinterpret_cast<float2 *>(phi), (const float2 *)p->tw);
+                  reinterpret_cast<float2 *>(phi), (const float2 *)p->tw, (const float *)nullptr);
     }
     pm_prof_mark(p, PM_STAGE_C2R + 1, st);
     PM_CHECK_LAUNCH();
@@ -1077,7 +1092,7 @@ ColArgs slab_args(pm_plan *p)
     ca.main = p->spec;
     ca.side = p->spec + (size_t)p->nzl * N * (N / 2);
     ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev; ca.sin2y = p->sin2rev;
-    ca.scale = 0.f; ca.axis = 1;
+    ca.scale = 0.f; ca.scale_ptr = nullptr; ca.axis = 1;
     ca.nyl = N / p->nranks; ca.y0 = p->rank * ca.nyl;
     ca.tpr = (N / 2) / kColsCN<N>; ca.kt0 = 0; ca.hw = N / 2; ca.side_tiles = 1;
     return ca;
@@ -1090,7 +1105,7 @@ int slab_rows_fwd(pm_plan *p, const float *rho, cudaStream_t st)
     auto rows_fwd = k_fft_rows<N, true>;
     PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     PM_LAUNCH(rows_fwd, p->nzl * N / kCols, kThr<N>, smem_rows, st,
-              reinterpret_cast<const float2 *>(rho), p->spec, (const float2 *)p->tw);
+              reinterpret_cast<const float2 *>(rho), p->spec, (const float2 *)p->tw, (const float *)p->rho_mean_d);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -1170,7 +1185,7 @@ int slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
     PM_CUDA(cudaFuncSetAttribute(rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     PM_LAUNCH(rows_inv, p->nzl * N / kCols, kThr<N>, smem_rows, st,
               reinterpret_cast<const float2 *>(p->spec), reinterpret_cast<float2 *>(phi),
-              (const float2 *)p->tw);
+              (const float2 *)p->tw, (const float *)nullptr);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -1409,12 +1424,12 @@ int pk_launch(pm_plan *p, const float *rho, int nbins, double *psum, double *pcn
     ca.main = p->spec;
     ca.side = p->spec + (size_t)N * N * H;
     ca.tw = p->tw; ca.sin2 = p->sin2; ca.sin2rev = p->sin2rev; ca.sin2y = p->sin2rev;
-    ca.scale = 0.f; ca.nyl = N; ca.y0 = 0;
+    ca.scale = 0.f; ca.scale_ptr = nullptr; ca.nyl = N; ca.y0 = 0;
     ca.tpr = H / kColsCN<N>; ca.kt0 = 0; ca.hw = H; ca.side_tiles = 1;
     PM_CUDA(cudaMemsetAsync(psum, 0, sizeof(double) * nbins, st));
     PM_CUDA(cudaMemsetAsync(pcnt, 0, sizeof(double) * nbins, st));
     PM_LAUNCH(rows_fwd, N * N / kCols, kThr<N>, smem_rows, st, reinterpret_cast<const float2 *>(rho),
-              ca.main, (const float2 *)p->tw);
+              ca.main, (const float2 *)p->tw, (const float *)nullptr);   // P(k): the estimator wants the DC too
     ca.axis = 1;
     PM_LAUNCH(cols_fwd, N * ca.tpr, kThrC<N>, smem_cols, st, ca);
     ca.axis = 0;

@@ -271,7 +271,8 @@ __device__ __forceinline__ void fft2_cols_tile(const ColArgs &a, const int t, fl
 // Shared tile: [(row*RA + q)][RB + 1] float2 (the pad keeps stage B's stride-RB reads conflict-free).
 template <int N, bool FWD, bool CG>
 __device__ __forceinline__ void fft2_rows_tile(const float2 *__restrict__ in, float2 *__restrict__ out,
-                                               const size_t row0, float2 *s_tile, const float2 *s_tw)
+                                               const size_t row0, float2 *s_tile, const float2 *s_tw,
+                                               const float mean = 0.f)
 {
     constexpr int H = N / 2;
     constexpr int RA = RowFac<N>::RA, RB = RowFac<N>::RB, RT = kRowsPT2<N>, P = RB + 1;
@@ -288,7 +289,11 @@ __device__ __forceinline__ void fft2_rows_tile(const float2 *__restrict__ in, fl
             const float2 *src = in + (row0 + row) * H;
             float2 v[RA];
 #pragma unroll
-            for (int r = 0; r < RA; ++r) v[r] = src[i + RB * r];   // rho: written by an earlier launch
+            for (int r = 0; r < RA; ++r) {
+                v[r] = src[i + RB * r];   // rho: written by an earlier launch
+                v[r].x -= mean;           // rho - <rho> (see fft_rows_tile)
+                v[r].y -= mean;
+            }
             dftr<RA, -1>(v);
 #pragma unroll
             for (int qq = 1; qq < RA; ++qq) v[qq] = cmul(v[qq], s_tw[2 * i * qq]);   // W_H^(i q)

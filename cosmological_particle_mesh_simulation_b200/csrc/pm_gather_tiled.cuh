@@ -36,7 +36,15 @@ struct GatherTiledArgs {
     int64_t sout;
     int zc;                     // planes per CTA
     double k_kick, da, aa, raa, f_a1;
+    const PmStepParams *sp;     // non-null: the five scalars above are read from device memory (graph replays)
 };
+
+__device__ __forceinline__ void pm_gather_step_params(GatherTiledArgs &A)
+{
+    if (A.sp) {
+        A.k_kick = A.sp->k_kick; A.da = A.sp->da; A.aa = A.sp->aa; A.raa = A.sp->raa; A.f_a1 = A.sp->f_a1;
+    }
+}
 
 constexpr int kGtRing = 5;
 
@@ -49,6 +57,7 @@ constexpr size_t kGtSmem = ((size_t)kGtRing * (YB + 3) * NC + 3 * 7 * CAP + 4 * 
 template <int NC, int YB, int NT, int CAP, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_gather_tiled(GatherTiledArgs A)
 {
+    pm_gather_step_params(A);
     constexpr int SR = YB + 3;          // rows of a slab: y0-1 .. y0+YB+1
     constexpr int SLAB = SR * NC;       // floats
     constexpr int QUADS = NC / 4;

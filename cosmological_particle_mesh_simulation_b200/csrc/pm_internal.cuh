@@ -57,6 +57,18 @@ extern int g_pm_last_cufft;
 #define PM_SLOT_GHOST_RHO 16  // density ghost plane written into rank+1
 #define PM_SLOT_GHOST_PHI_UP 17   // my last phi plane written into rank+1
 #define PM_SLOT_GHOST_PHI_DN 18   // my first two phi planes written into rank-1
+#define PM_SLOT_MIG_COUNTS 19     // my row of the migration count matrix written into every rank (pm_migrate.cu)
+#define PM_SLOT_MIG_DATA 20       // my leavers' records written into their destinations
+#define PM_MIG_ROW (PM_PEER_MAX + 4)   // words per matrix row: counts per destination, timeouts, overflow, room, pad
+
+// Per-step scalars of a resident step as read from DEVICE memory by the kernels of a captured CUDA graph
+// (k_fft_cols<FUSED>: green_scale; the tiled gather kernels: the rest).  One small kernel node writes
+// them; its by-value argument is the only thing that changes between replays (pm_api.cu).
+struct PmStepParams {
+    double k_kick, da, aa, raa, f_a1;
+    float green_scale;
+    float pad;
+};
 
 struct pm_plan {
     int nc;           // N_CELLS
@@ -74,8 +86,9 @@ struct pm_plan {
 
     // deposit scratch
     uint32_t *keys, *iota, *keys_sorted, *order_sorted;  // iota[i] = i, written once
-    void *cub_tmp;
-    size_t cub_bytes;
+    uint64_t *sort_tmp;     // second ping-pong buffer of the full radix sort (the first is inc_a)
+    void *sort_ctl;         // SortCtl (pm_sort.cu): mover count, mode, error flag, barrier counter -- device resident
+    uint32_t *sort_hist;    // per-CTA digit histograms of k_radix_sort [PM_SORT_MAX_GRID][<=512], their column prefixes, column totals
     uint32_t *row_start;  // nzl*nc*dep_nseg + 1 offsets into the sorted particle list
 
     // incremental sort (pm_sort.cu): stayers / movers as (key << 32 | slot), tile tables
@@ -83,21 +96,29 @@ struct pm_plan {
     int64_t inc_bcap;       // capacity of inc_b / inc_bs in entries
     uint32_t *inc_tile;     // movers per 2048-entry tile -> exclusive offsets; [ntiles] = total
     uint32_t *inc_split;    // merge-path split of every output tile boundary
-    uint32_t *h_word;       // pinned host word the mover count is copied to
     int sort_mode;          // PM_SORT_AUTO / PM_SORT_FULL
     int64_t rsorted_n;      // the first rsorted_n entries of set rcur are stored in the order of
                             // the previous sort and keys_sorted[] still holds the keys they had
+    bool gather_ws;         // with gather_tiled: the warp-specialised mbarrier/bulk-copy kernel (pm_gather_ws.cuh); PM_GATHER_WS=0: k_gather_tiled
     bool gather_tiled;      // resident gather through shared-memory phi slabs (pm_gather_tiled.cuh) where supported
     bool inc_counted;       // inc_tile already holds this step's movers per tile (counted by the resident gather)
     bool rows_valid;        // row_start matches keys_sorted (set by the sort's merge or pm_k_row_offsets)
-    int sort_last_mode;     // what the last pm_k_sort did (pm_plan_sort_stats)
-    int64_t sort_last_n, sort_last_movers;
+    int64_t sort_last_n;    // entries of the last pm_k_sort (mode and mover count live in sort_ctl)
     int dep_nseg;         // segments per mesh row in the deposit (1 unless the mesh is wide)
 
     // Poisson scratch
     float *mesh;          // nc^3: rho when the caller does not keep it
     float *mesh2;         // nc^3: phi
     float2 *spec;         // nc*nc*(nc/2+1) half spectrum
+    // The forward transform runs on rho - <rho> (the DC mode is zeroed by the Green's factor, so the
+    // potential is the same in exact arithmetic; in float32 the 1e8-sized DC lineage otherwise leaks
+    // rounding noise into the lowest-k modes, which the 1/k^2 factor amplifies: measured 1.6e-5
+    // relative L2 in phi at 512^3 with it, < 3e-6 without).  rho_mean_d: the mean as a device float
+    // read by the row-pass kernels; rho_mean_hint: what the caller knows it to be (Np*mass/Nc^3 for a
+    // deposit of this library), NaN = unknown -> pm_k_poisson reduces the mesh (deterministic sum).
+    float *rho_mean_d;
+    double *mean_ws;      // [1024] block partial sums of that reduction
+    double rho_mean_hint;
     void *fft_work;
     size_t fft_work_bytes;
     float *sin2;          // sin^2(pi i / nc), i < nc
@@ -121,6 +142,7 @@ struct pm_plan {
     int64_t rnp;          // live particles in set rcur
     int64_t rstride;      // distance between the x, y, z rows of the resident sets (= np_cap)
     bool rkeys_valid;     // p->keys already holds the keys of set rcur (written by the last gather)
+    bool rsort_done;      // keys_sorted / order_sorted / row_start describe set rcur as it is now (pm_api.cu)
     cudaStream_t s_main, s_up, s_down;
     cudaEvent_t ev_a, ev_b, ev_c;
 
@@ -145,8 +167,30 @@ struct pm_plan {
     int peers_set;                          // how many of the nranks entries are filled in
     float *peer_mesh2[PM_PEER_MAX];         // rank s's phi buffer (ghost planes pushed through peer memory)
     int ghosts_set;
+    uint32_t *mig_matrix;                   // [PM_PEER_MAX][PM_MIG_ROW] in ws: every rank's leave counts etc. (pm_migrate.cu)
+    uint32_t *mig_matrix_h;                 // pinned host copy
+    uint32_t *peer_mig_matrix[PM_PEER_MAX]; // rank s's matrix / receive buffer as seen from this device
+    float *peer_mig_recv[PM_PEER_MAX];
+    int aux_set;
 
+    // tile deposit (pm_deposit_tiles.cuh): scratch slots, queue and counters of the heavy tiles
+    bool deposit_tiles;     // false: k_deposit_rows (PM_DEPOSIT=rows, meshes the tile kernel does not take)
+    unsigned long long *dep_scratch;
+    uint32_t *dep_ctl, *dep_slot_tile;
+    void *dep_items;
     void *diag;             // 64 bytes of device scratch for diagnostics (pm_plan_block_stats)
+
+    // CUDA-graph replay of the resident step (pm_step_resident; pm_api.cu)
+    PmStepParams *step_params_d;   // device copy of the per-step scalars (always allocated)
+    PmStepParams *graph_params;    // == step_params_d while a step is being CAPTURED (kernels then read it), else nullptr
+    bool use_graph;                // PM_GRAPH=0 turns replay off
+    void *graph_exec[2];           // cudaGraphExec_t per buffer-set parity
+    void *graph_node[2];           // the parameter kernel node of each
+    float *graph_rho[2];           // what each was captured for
+    double graph_mass[2], graph_omega[2];
+    int64_t graph_np[2];
+    cudaStream_t graph_stream[2];
+    int graph_replays;             // statistics
 
     // optional per-stage timing of pm_step (pm_plan_profile_begin/read)
     cudaEvent_t *prof_ev;   // prof_cap * (PM_NUM_STAGES + 1) events
@@ -166,7 +210,8 @@ static inline cudaStream_t pm_cu(pm_stream_t s) { return reinterpret_cast<cudaSt
 #ifndef PM_SORT_TILE
 #define PM_SORT_TILE 2048
 #endif
-size_t pm_sort_temp_bytes(int64_t np, int key_bits);
+#define PM_SORT_MAX_GRID 1024   /* sort_hist holds PM_SORT_MAX_GRID * 512 words */
+int pm_k_sort_stats(pm_plan *p, int64_t *entries, int64_t *movers, int *mode);
 int64_t pm_sort_tiles(int64_t np);
 int64_t pm_sort_mover_capacity(int64_t np);
 int pm_k_sort(pm_plan *p, int64_t np, int64_t n_old, cudaStream_t st);
@@ -183,6 +228,8 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
                                     double da, cudaStream_t st);
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
+void pm_gather_step_scalars(double a_val, double f_a1, double da, PmStepParams *out);
+bool pm_gather_graphable(const pm_plan *p);
 int pm_k_block_stats(pm_plan *p, int rows_per_block, int cap, int64_t *out4, cudaStream_t st);
 void pm_gather_tile_shape(int *rows_per_block, int *cap);
 // slab mode (pm_slab.cu / pm_particles.cu)
@@ -227,6 +274,7 @@ int pm_k_power_spectrum(pm_plan *p, const float *rho, int nbins, double *psum, d
 
 // pm_poisson.cu
 int pm_k_sin2_table(pm_plan *p);
+int pm_k_rho_mean(pm_plan *p, const float *rho, size_t n, double total_cells, cudaStream_t st);
 int pm_k_fourier_grid(pm_plan *p, float *fgrid, cudaStream_t st);
 int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                  cudaStream_t st);

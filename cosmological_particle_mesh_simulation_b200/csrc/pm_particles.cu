@@ -5,6 +5,7 @@
 // gather/kick/drift arithmetic below is written to be bit-identical to it given the same phi
 // (reference: src/integrate.py:27-97).  The explicit __f*_rn / __d*_rn intrinsics make the
 // rounding points visible (and keep them if the flag is ever lost).
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -281,9 +282,71 @@ static int pm_launch_deposit_ry(pm_plan *p, const float *pos, int64_t stride, do
     return PM_OK;
 }
 
+#include "pm_deposit_tiles.cuh"
+
+template <int ZB, int YB>
+static int pm_launch_deposit_tiles_zy(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
+                                      int nz_out, int slab, cudaStream_t st)
+{
+    const int nc = p->nc;
+    const size_t smem = (size_t)2 * ZB * YB * nc * sizeof(uint32_t);
+    auto k1 = k_deposit_tiles<ZB, YB>;
+    auto k2 = k_deposit_items<ZB, YB>;
+    auto k3 = k_deposit_slots<ZB, YB>;
+    PM_ONCE_PER_DEVICE_BEGIN(p->device)
+        // the largest tile any mesh gives this instantiation (8192 cells), not this call's
+        PM_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(uint32_t)));
+        PM_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(uint32_t)));
+        PM_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PM_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    PM_ONCE_PER_DEVICE_END()
+    DepositTileArgs A;
+    A.px = pos; A.py = pos + stride; A.pz = pos + 2 * stride;
+    A.order = p->order_sorted; A.row_start = p->row_start; A.rho = rho;
+    A.nc = nc; A.nseg = p->dep_nseg; A.nz_out = nz_out;
+    A.z0 = slab ? p->z0 : 0; A.nzl = p->nzl; A.slab = slab;
+    A.tiles_y = nc / YB; A.tiles_z = (nz_out + ZB - 1) / ZB;
+    // fixed-point unit 2^-k of a mass unit: k = 24 unless |mass| * Nc^3 (every axis at x == N_CELLS) would
+    // not leave 2^8 such terms of headroom in 63 bits
+    int k = 24;
+    {
+        const double big = fabs(mass) * (double)nc * nc * nc;
+        if (big > 0.0 && isfinite(big)) {
+            const int need = (int)ceil(log2(big));
+            if (55 - need < k) k = 55 - need;
+        }
+    }
+    A.smass = ldexp(mass, k); A.inv_scale = ldexp(1.0, -k);
+    A.fast_ok = (A.smass >= 0.0 && A.smass < 4294967296.0) ? 1 : 0;
+    A.scratch = p->dep_scratch; A.ctl = p->dep_ctl; A.slot_tile = p->dep_slot_tile; A.items = (DepItem *)p->dep_items;
+    PM_CUDA(cudaMemsetAsync(p->dep_ctl, 0, 4 * sizeof(uint32_t), st));
+    dim3 grid(A.tiles_y, A.tiles_z);
+    PM_LAUNCH(k1, grid, kDepThreads, smem, st, A);
+    PM_LAUNCH(k2, p->sm_count * 3, kDepThreads, smem, st, A);
+    PM_LAUNCH(k3, dim3(kDepMaxSlots, 4), kDepThreads, 0, st, A);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+// tile shape by mesh width: at most 8192 cells (64 KB of accumulators) per tile
+static int pm_launch_deposit_tiles(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
+                                   int nz_out, int slab, cudaStream_t st)
+{
+    const int nc = p->nc;
+    if (nc % 16 || nc < 16) return PM_ERR_UNSUPPORTED;
+    if (nc <= 512) return pm_launch_deposit_tiles_zy<2, 8>(p, pos, stride, mass, rho, nz_out, slab, st);
+    if (nc <= 1024) return pm_launch_deposit_tiles_zy<2, 4>(p, pos, stride, mass, rho, nz_out, slab, st);
+    if (nc <= 2048) return pm_launch_deposit_tiles_zy<2, 2>(p, pos, stride, mass, rho, nz_out, slab, st);
+    return PM_ERR_UNSUPPORTED;
+}
+
 static int pm_launch_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
                              int nz_out, int slab, cudaStream_t st)
 {
+    if (p->deposit_tiles) {
+        const int rc = pm_launch_deposit_tiles(p, pos, stride, mass, rho, nz_out, slab, st);
+        if (rc != PM_ERR_UNSUPPORTED) return rc;
+    }
     if (p->dep_nseg <= PM_DEPOSIT_RY && PM_DEPOSIT_RY % p->dep_nseg == 0)
         return pm_launch_deposit_ry<PM_DEPOSIT_RY>(p, pos, stride, mass, rho, nz_out, slab, st);
     return pm_launch_deposit_ry<8>(p, pos, stride, mass, rho, nz_out, slab, st);
@@ -525,6 +588,7 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 }
 
 #include "pm_gather_tiled.cuh"
+#include "pm_gather_ws.cuh"
 
 #ifndef PM_GT_YB
 #define PM_GT_YB 4      // particle rows per CTA
@@ -541,6 +605,17 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 
 // Tiled variant (pm_gather_tiled.cuh) when the mesh and the plan allow it; returns PM_ERR_UNSUPPORTED
 // otherwise so that the caller falls back to the one-thread-per-particle kernel.
+// warp-specialised variant (pm_gather_ws.cuh): consumer warps, phi ring depth, staging ring depth
+#ifndef PM_GW_CW
+#define PM_GW_CW 8
+#endif
+#ifndef PM_GW_R
+#define PM_GW_R 5
+#endif
+#ifndef PM_GW_S
+#define PM_GW_S 3
+#endif
+
 template <int NC>
 static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
                                   uint32_t *cnt, cudaStream_t st)
@@ -550,9 +625,14 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
     constexpr size_t smem = kGtSmem<NC, PM_GT_YB, PM_GT_CAP>;
     static_assert(smem <= 227 * 1024 / PM_GT_MINB, "PM_GT_MINB CTAs per SM");
     auto kern = k_gather_tiled<NC, PM_GT_YB, PM_GT_NT, PM_GT_CAP, PM_GT_MINB>;
+    using WsSmem = pmws::Smem<NC, PM_GT_YB, PM_GT_CAP, PM_GW_R, PM_GW_S>;
+    static_assert(WsSmem::total <= 227 * 1024 / PM_GT_MINB, "PM_GT_MINB CTAs per SM (warp-specialised gather)");
+    auto kern_ws = k_gather_ws<NC, PM_GT_YB, PM_GW_CW, PM_GT_CAP, PM_GW_R, PM_GW_S, PM_GT_MINB>;
     PM_ONCE_PER_DEVICE_BEGIN(p->device)
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        PM_CUDA(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem::total));
+        PM_CUDA(cudaFuncSetAttribute(kern_ws, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     PM_ONCE_PER_DEVICE_END()
     const int c = p->rcur, o = c ^ 1;
     GatherTiledArgs A;
@@ -565,10 +645,27 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
     A.sout = p->rstride;
     A.zc = zc;
     A.k_kick = k_kick; A.da = da; A.aa = aa; A.raa = pm_div_rcp(aa, da); A.f_a1 = f_a1;
+    A.sp = p->graph_params;
     dim3 grid(NC / PM_GT_YB, NC / zc);
-    PM_LAUNCH(kern, grid, PM_GT_NT, smem, st, A);
+    if (p->gather_ws) PM_LAUNCH(kern_ws, grid, (PM_GW_CW + 1) * 32, WsSmem::total, st, A, p->fft_sync + 0);
+    else PM_LAUNCH(kern, grid, PM_GT_NT, smem, st, A);
     PM_CHECK_LAUNCH();
     return PM_OK;
+}
+
+// the scalars the gather kernels take, as pm_k_gather_kick_drift_resident derives them from (a, da, f_a1)
+void pm_gather_step_scalars(double a_val, double f_a1, double da, PmStepParams *out)
+{
+    out->k_kick = da * f_a1;
+    out->aa = (a_val + da) * (a_val + da);
+    out->da = da;
+    out->raa = pm_div_rcp(out->aa, da);
+    out->f_a1 = f_a1;
+}
+
+bool pm_gather_graphable(const pm_plan *p)
+{
+    return p->gather_tiled && p->dep_nseg == 1 && (p->nc == 128 || p->nc == 256 || p->nc == 512);
 }
 
 static int pm_try_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,

@@ -76,14 +76,86 @@ __global__ void __launch_bounds__(256) k_green_multiply(float2 *__restrict__ spe
     }
 }
 
+// ---- <rho>: the constant the forward transform subtracts (pm_internal.cuh, rho_mean_d) -----------
+__global__ void k_set_mean(float *dst, float v) { *dst = v; }
+
+// Deterministic mean of an arbitrary mesh: 1024 fixed blocks write float64 partial sums, one block
+// adds them in index order (no atomics: the same input gives the same bits).
+__global__ void __launch_bounds__(256) k_mean_partial(const float *__restrict__ rho, size_t n,
+                                                      double *__restrict__ part)
+{
+    __shared__ double s_w[8];
+    const size_t per = (n + gridDim.x - 1) / gridDim.x;
+    const size_t lo = per * blockIdx.x, hi = lo + per < n ? lo + per : n;
+    double s = 0.0;
+    for (size_t i = lo + threadIdx.x; i < hi; i += 256) s += (double)rho[i];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_mean_final(const double *__restrict__ part, int nparts,
+                                                   double total_cells, float *__restrict__ mean)
+{
+    if (threadIdx.x != 0) return;
+    double t = 0.0;
+    for (int i = 0; i < nparts; ++i) t += part[i];
+    *mean = (float)(t / total_cells);
+}
+
+// Sets p->rho_mean_d from p->rho_mean_hint, or from the mesh itself when the hint is NaN.  `n` cells
+// of this rank, `total_cells` the divisor (a slab rank with an unknown mean would need an all-reduce:
+// slab callers always give the hint).
+int pm_k_rho_mean(pm_plan *p, const float *rho, size_t n, double total_cells, cudaStream_t st)
+{
+    if (!isnan(p->rho_mean_hint)) {
+        PM_LAUNCH(k_set_mean, 1, 1, 0, st, p->rho_mean_d, (float)p->rho_mean_hint);
+    } else {
+        PM_LAUNCH(k_mean_partial, 1024, 256, 0, st, rho, n, p->mean_ws);
+        PM_LAUNCH(k_mean_final, 1, 32, 0, st, (const double *)p->mean_ws, 1024, total_cells, p->rho_mean_d);
+    }
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
+__global__ void __launch_bounds__(256) k_sub_mean(const float4 *__restrict__ in, float4 *__restrict__ out,
+                                                  size_t n4, const float *__restrict__ mean_ptr)
+{
+    const float m = __ldg(mean_ptr);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = in[i];
+        v.x -= m; v.y -= m; v.z -= m; v.w -= m;
+        out[i] = v;
+    }
+}
+
 int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                  cudaStream_t st)
 {
+    const size_t cells = (size_t)p->nc * p->nc * p->nc;
+    {
+        const int rc = pm_k_rho_mean(p, rho, cells, (double)cells, st);
+        if (rc != PM_OK) return rc;
+    }
     if (p->own_fft) return pm_k_poisson_own(p, rho, a, omega_m0, phi, st);
     const int nc = p->nc, nxh = nc / 2 + 1;
     PM_CUFFT(cufftSetStream(p->r2c, st));
     PM_CUFFT(cufftSetStream(p->c2r, st));
-    PM_CUFFT(cufftExecR2C(p->r2c, const_cast<float *>(rho), reinterpret_cast<cufftComplex *>(p->spec)));
+    // library path (non-power-of-two meshes, A/B checks): rho - <rho> staged in the output mesh
+    const float *src = rho;
+    if (cells % 4 == 0 && (uintptr_t)rho % 16 == 0 && (uintptr_t)phi % 16 == 0) {
+        PM_LAUNCH(k_sub_mean, p->sm_count * 8, 256, 0, st, reinterpret_cast<const float4 *>(rho),
+                  reinterpret_cast<float4 *>(phi), cells / 4, (const float *)p->rho_mean_d);
+        src = phi;
+    }
+    PM_CUFFT(cufftExecR2C(p->r2c, const_cast<float *>(src), reinterpret_cast<cufftComplex *>(p->spec)));
     pm_prof_mark(p, PM_STAGE_R2C + 1, st);
     const double m = (double)nc * (double)nc * (double)nc;
     const double scale = -3 * omega_m0 / 8 / a / m;  // potential.py:15, plus the IFFT's 1/Nc^3

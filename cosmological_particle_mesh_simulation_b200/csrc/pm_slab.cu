@@ -139,9 +139,20 @@ static int chunk_ok(const pm_plan *p, int c, int C)
     return C >= 1 && c >= 0 && c < C && h % C == 0 && (h / C) % pm_fft_cols_per_tile(p->nc) == 0;
 }
 
+// <rho> of the WHOLE mesh (all ranks): total particles * mass / Nc^3, which only the caller knows.
+// The forward transform subtracts it (pm_internal.cuh, rho_mean_d); unset = 0 = plain transform.
+int pm_slab_set_rho_mean(pm_plan *p, double mean)
+{
+    if (!p || !p->slab || !(mean == mean)) return PM_ERR_INVALID;
+    p->rho_mean_hint = mean;
+    return PM_OK;
+}
+
 int pm_slab_fft_rows_forward(pm_plan *p, pm_stream_t stream)
 {
     PM_SLAB_ENTER(true);
+    if (p->rho_mean_hint != p->rho_mean_hint) p->rho_mean_hint = 0.0;   // NaN: never told
+    PM_TRY(pm_k_rho_mean(p, p->mesh, 0, 1.0, st));
     return pm_k_fft_slab_rows_fwd(p, p->mesh, st);
 }
 
@@ -263,9 +274,12 @@ int pm_slab_peer_release(pm_plan *p)
         p->peer_recv[s] = nullptr;
         p->peer_flag_of[s] = nullptr;
         p->peer_mesh2[s] = nullptr;
+        p->peer_mig_matrix[s] = nullptr;
+        p->peer_mig_recv[s] = nullptr;
     }
     p->peers_set = 0;
     p->ghosts_set = 0;
+    p->aux_set = 0;
     return PM_OK;
 }
 

@@ -6,8 +6,10 @@ reference: positions float32[3, Np] (row 0 = x), returns a fresh float32[Nc, Nc,
 [z, y, x]; N_CELLS comes from configure_me."""
 try:
     from . import _runtime as rt
+    from . import _session
 except ImportError:  # dropped into a flat source tree like the reference's
     import _runtime as rt
+    import _session
 import torch
 
 
@@ -17,12 +19,19 @@ def _density_device(positions, mass, n_cells, out=None):
         raise ValueError("positions must have shape (3, Np)")
     dev = positions.device.index
     npart = positions.shape[1]
-    plan = rt.get_plan(n_cells, npart, dev)
     rho = out if out is not None else torch.empty((n_cells,) * 3, dtype=torch.float32,
                                                   device=positions.device)
-    with torch.cuda.device(dev):
-        rt.check(rt.lib().pm_deposit_cic(plan.handle, positions.data_ptr(), npart, float(mass),
-                                         rho.data_ptr(), rt.stream_ptr(dev)), "pm_deposit_cic")
+    sess = _session.session_for_density(positions, n_cells)
+    if sess is not None:
+        # these are the positions advance_time wrote last step, untouched: the cell-ordered resident copy
+        # is deposited (incremental re-sort) instead of sorting the caller's array from scratch
+        sess.deposit(mass, rho)
+    else:
+        plan = rt.get_plan(n_cells, npart, dev)
+        with torch.cuda.device(dev):
+            rt.check(rt.lib().pm_deposit_cic(plan.handle, positions.data_ptr(), npart, float(mass),
+                                             rho.data_ptr(), rt.stream_ptr(dev)), "pm_deposit_cic")
+    _session.note_density(rho, float(mass) * npart / float(n_cells) ** 3)
     return rho
 
 

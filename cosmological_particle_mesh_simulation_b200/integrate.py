@@ -6,11 +6,13 @@ pre-step position, central-difference force at the 8 corners, kick, drift with p
 positions and velocities are updated IN PLACE and returned, like the reference."""
 try:
     from . import _runtime as rt
+    from . import _session
     from .cosmology import f
     from .potential import _potential_device
     from .fourier_utils import FourierGrid
 except ImportError:
     import _runtime as rt
+    import _session
     from cosmology import f
     from potential import _potential_device
     from fourier_utils import FourierGrid
@@ -68,5 +70,18 @@ def advance_time(density, positions, velocities, fgrid, a, da):
         rho = rt.to_device(density, dev) if rt.is_host(density) else density
         phi = _potential_device(rho, fgrid, a)
         return integrate(positions, velocities, a, fa1, da, phi)
+    if _session.enabled() and isinstance(fgrid, FourierGrid):
+        # the resident fast path behind the reference's signature (see _session.py): potential of `density`,
+        # gather + kick + drift of the cell-ordered resident copy, result written back in the caller's order
+        n = fgrid.n_cells
+        rt.check_dev_f32(density, (n, n, n), "density")
+        rt.check_dev_f32(positions, name="positions")
+        rt.check_dev_f32(velocities, tuple(positions.shape), "velocities")
+        if positions.dim() != 2 or positions.shape[0] != 3:
+            raise ValueError("positions must have shape (3, Np)")
+        sess = _session.session_for_advance(positions, velocities, n)
+        sess.advance(density, _session.known_mean(density), a, da, fa1, cfg.OMEGA_M0)
+        sess.state.store(positions, velocities)
+        return positions, velocities
     phi = _potential_device(density, fgrid, a)
     return _integrate_device(positions, velocities, a, fa1, da, phi)

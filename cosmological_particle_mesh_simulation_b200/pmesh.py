@@ -67,7 +67,8 @@ class ResidentParticles:
     pm_step_resident / pm_particles_store).  The caller's arrays are only read at construction and
     only written by store(), always in ORIGINAL particle order, so results are comparable
     particle for particle with the reference, which never permutes (src/save_data.py:19-24).
-    One resident state per (N_CELLS, device) at a time: it lives inside the cached plan."""
+    Every ResidentParticles owns its plan (workspace + state), so stateless calls on the same mesh
+    and device -- density(), step(), step_host(), which use the shared cached plan -- cannot disturb it."""
 
     def __init__(self, positions, velocities):
         cfg = rt.config()
@@ -76,11 +77,18 @@ class ResidentParticles:
         rt.check_dev_f32(velocities, tuple(positions.shape), "velocities")
         self.device = positions.device.index
         self.np = positions.shape[1]
-        self.plan = rt.get_plan(self.n_cells, self.np, self.device)
+        self.plan = rt.Plan(self.n_cells, max(self.np, 1), self.device)
         with torch.cuda.device(self.device):
             rt.check(rt.lib().pm_particles_load(self.plan.handle, positions.data_ptr(),
                                                 velocities.data_ptr(), self.np,
                                                 rt.stream_ptr(self.device)), "pm_particles_load")
+
+    def close(self):
+        """Free the plan (workspace and resident state)."""
+        if self.plan is not None:
+            torch.cuda.synchronize(self.device)
+            self.plan.close()
+            self.plan = None
 
     def step(self, a, da, mass=None, rho_out=None):
         cfg = rt.config()

@@ -67,6 +67,7 @@ class SlabRank:
                                                   self.device, self.rank, self.nranks),
                      f"pm_plan_create_slab(n_cells={n_cells}, np={np_capacity}, rank={rank}/{nranks})")
         self.handle = h
+        self.total_particles = None      # particles of ALL ranks (make_ranks / make_rank_from_local set it)
         self.buf = {}
         n, nzl, nyl, hh, P = self.n_cells, self.nzl, self.nzl, self.n_cells // 2, self.nranks
         shapes = dict(RHO=(torch.float32, (nzl, n, n)), RHO_GHOST_SEND=(torch.float32, (n, n)),
@@ -82,6 +83,7 @@ class SlabRank:
                       PEER_FLAGS=(torch.int32, (-1, 16)))
         self.peers_ready = False
         self.ghosts_ready = False
+        self.mig_ready = False
         for name, which in BUF.items():
             ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
             rt.check(rt.lib().pm_slab_buffer(self.handle, which, ctypes.byref(ptr), ctypes.byref(nbytes)),
@@ -172,6 +174,7 @@ class SlabRank:
 
     def peer_release(self):
         self.ghosts_ready = False
+        self.mig_ready = False
         if getattr(self, "handle", None):
             with torch.cuda.device(self.device):
                 torch.cuda.synchronize()
@@ -227,6 +230,30 @@ class SlabRank:
     def migrate_pack(self, counts):
         arr = (ctypes.c_int64 * self.nranks)(*[int(c) for c in counts])
         self._call("pm_slab_migrate_pack", arr)
+
+    # migration through peer memory (csrc/pm_migrate.cu)
+    def migrate_counts_push(self):
+        self._call("pm_slab_migrate_counts_push")
+
+    def migrate_counts_read(self):
+        """The count matrix every rank holds after the exchange: int64 array [P, P + 3]; row s = rank s's
+        leavers per destination, then its flag-wait timeouts, its leave-list overflow flag and its free
+        particle capacity.  Synchronises this rank's stream (the one host read of the step)."""
+        P = self.nranks
+        m = np.zeros((P, P + 3), dtype=np.uint32)
+        with torch.cuda.device(self.device):
+            rt.check(rt.lib().pm_slab_migrate_counts_read(self.handle, m.ctypes.data, rt.stream_ptr(self.device)),
+                     "pm_slab_migrate_counts_read")
+        return m.astype(np.int64)
+
+    def migrate_push(self, send_counts, dest_offsets):
+        P = self.nranks
+        a = (ctypes.c_int64 * P)(*[int(c) for c in send_counts])
+        b = (ctypes.c_int64 * P)(*[int(c) for c in dest_offsets])
+        self._call("pm_slab_migrate_push", a, b)
+
+    def migrate_wait(self):
+        self._call("pm_slab_migrate_wait")
 
     def migrate_unpack(self, n_arrive, n_leave):
         self._call("pm_slab_migrate_unpack", int(n_arrive), int(n_leave))
@@ -420,34 +447,41 @@ def setup_peers(ranks, comm):
 
 
 def setup_ghost_peers(ranks, comm):
-    """EXPERIMENTAL (not yet validated on hardware).  After setup_peers(): also publish where every
-    rank's phi buffer lives, so slab_step(ghosts="peer") can push the density and potential ghost
-    planes into the neighbours' memory instead of NCCL send/recv.  Returns True when usable."""
+    """After setup_peers(): also publish where every rank's phi buffer, migration receive buffer and
+    count matrix live, so that slab_step can push the density / potential ghost planes into the
+    neighbours' memory (ghosts="peer") and migrate particles through peer memory (migrate="peer",
+    csrc/pm_migrate.cu) instead of NCCL send/recv and all-to-all-v.  Returns True when usable."""
     if not all(r.peers_ready for r in ranks):
         return False
+    vp = ctypes.c_void_p
     if isinstance(comm, LocalComm):
+        ptrs = {}
+        for s in ranks:
+            a, b, c = vp(), vp(), vp()
+            rt.check(rt.lib().pm_slab_aux_buffers(s.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+                     "pm_slab_aux_buffers")
+            ptrs[s.rank] = (a, b, c)
         for r in ranks:
             for s in ranks:
-                rt.check(rt.lib().pm_slab_peer_ghost_set(r.handle, s.rank, ctypes.c_void_p(s.buf["PHI_LO_RECV"].data_ptr())),
-                         "pm_slab_peer_ghost_set")
+                rt.check(rt.lib().pm_slab_peer_aux_set(r.handle, s.rank, *ptrs[s.rank]), "pm_slab_peer_aux_set")
         for r in ranks:
-            r.ghosts_ready = True
+            r.ghosts_ready = r.mig_ready = True
         return True
     dist, r = comm.dist, ranks[0]
-    off = ctypes.c_uint64()
-    rt.check(rt.lib().pm_slab_peer_ghost_export(r.handle, ctypes.byref(off)), "pm_slab_peer_ghost_export")
+    off = (ctypes.c_uint64 * 3)()
+    rt.check(rt.lib().pm_slab_peer_aux_export(r.handle, off), "pm_slab_peer_aux_export")
     table = [None] * comm.nranks
-    dist.all_gather_object(table, int(off.value), group=comm.group)
+    dist.all_gather_object(table, [int(off[0]), int(off[1]), int(off[2])], group=comm.group)
     ok = 1
     try:
         for s, o in enumerate(table):
-            rt.check(rt.lib().pm_slab_peer_ghost_import(r.handle, s, int(o)), "pm_slab_peer_ghost_import")
+            rt.check(rt.lib().pm_slab_peer_aux_import(r.handle, s, (ctypes.c_uint64 * 3)(*o)), "pm_slab_peer_aux_import")
     except Exception:
         ok = 0
     dev = r.buf["RHO"].device if dist.get_backend(comm.group) == "nccl" else "cpu"
     flag = torch.tensor([ok], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=comm.group)
-    r.ghosts_ready = bool(int(flag.item()))
+    r.ghosts_ready = r.mig_ready = bool(int(flag.item()))
     return r.ghosts_ready
 
 
@@ -510,7 +544,13 @@ def default_chunks(n_cells, nranks=1, transport="nccl"):
     return 1
 
 
-def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, transport=None, ghosts="nccl"):
+class SlabExchangeError(RuntimeError):
+    """A peer-memory exchange failed on SOME rank (flag wait timed out, leave list or particle capacity
+    exceeded).  Every rank reads the same count matrix, so every rank raises this in the same step."""
+
+
+def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, transport=None, ghosts=None,
+              migrate=None):
     """One body of the loop src/pmesh.py:60-61 across the slabs.  `ranks`: the SlabRank objects
     of comm.local_ranks (one for DistComm, all P for LocalComm).  The distributed FFT runs as a
     pipeline of `chunks` kx chunks: with DistComm on GPUs the transposes go to a second stream
@@ -518,8 +558,10 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
     themselves store into / load from the other ranks' z-pass arrays over NVLink (one stream, no
     copy kernel; needs setup_peers), "peer" = separate push / pull copy kernels on the second
     stream, "nccl" = pack -> all-to-all -> unpack; default: "fused" when the ranks are set up for it.
-    ghosts: "nccl" = send/recv of the ghost planes (default), "peer" = EXPERIMENTAL pushes through the
-    peer mappings (needs setup_ghost_peers)."""
+    ghosts: "peer" = the ghost planes are stored into the neighbours' memory + one flag word (default once
+    setup_ghost_peers succeeded), "nccl" = send/recv.  migrate: "peer" = count matrix and particle records
+    through peer memory, one host read per step, errors agreed by all ranks (same default), "nccl" =
+    all-to-all of the counts + all-to-all-v of the records."""
     cfg = cfg or rt.config()
     if timer:
         timer.begin_step()
@@ -537,6 +579,10 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
     C = chunks or default_chunks(ranks[0].n_cells, ranks[0].nranks, transport)
     CH = lambda name, c: [r.chunk(name, c, C) for r in ranks]    # noqa: E731
 
+    if ghosts is None:
+        ghosts = "peer" if all(r.ghosts_ready for r in ranks) else "nccl"
+    if migrate is None:
+        migrate = "peer" if all(r.mig_ready for r in ranks) else "nccl"
     for r in ranks:
         r.deposit(mass)
     mark("deposit")
@@ -582,6 +628,9 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
         raise ValueError("at most %d chunks with the peer-memory transports" % (PEER_SLOTS_HALF - 1))
 
     for r in ranks:
+        if r.total_particles is not None:       # <rho> of the whole mesh: the transform runs on rho - <rho>
+            rt.check(rt.lib().pm_slab_set_rho_mean(r.handle, float(mass) * r.total_particles / float(r.n_cells) ** 3),
+                     "pm_slab_set_rho_mean")
         r.fft_rows_forward()
     if transport == "fused":
         # one stream: chunk c's stores drain over NVLink while chunk c+1 is transformed; the flag
@@ -714,14 +763,41 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
     for r in ranks:
         r.gather(a, f_a1, da)
     mark("gather")
-    # migration: the leave counts are exchanged on the device; one small device->host read per
-    # step brings both count vectors back (they size the messages)
-    send_counts, recv_counts = comm.exchange_count_tensors([r.buf["LEAVE_COUNTS"] for r in ranks])
-    for r, sc in zip(ranks, send_counts):
-        r.migrate_pack(sc)
-    comm.all_to_all_v(B("MIG_SEND"), send_counts, B("MIG_RECV"), recv_counts)
-    for r, sc, rc in zip(ranks, send_counts, recv_counts):
-        r.migrate_unpack(sum(rc), sum(sc))
+    if migrate not in ("nccl", "peer"):
+        raise ValueError(f"unknown migrate mode {migrate!r}")
+    if migrate == "peer":
+        if not all(r.mig_ready for r in ranks):
+            raise RuntimeError("migrate='peer' needs slab.setup_ghost_peers(ranks, comm) first")
+        # every rank stores its row of the count matrix into every rank, then ONE host read: all ranks
+        # hold the same matrix, which sizes the messages and carries every rank's error state
+        for r in ranks:
+            r.migrate_counts_push()
+        mats = [r.migrate_counts_read() for r in ranks]
+        P = ranks[0].nranks
+        m = mats[0]
+        cnt, tmo, over, room = m[:, :P], m[:, P], m[:, P + 1], m[:, P + 2]
+        arrive = cnt.sum(axis=0)
+        if tmo.any() or over.any() or (arrive > room).any():
+            raise SlabExchangeError(
+                "slab step failed on rank(s): flag-wait timeouts %s, leave-list overflow %s, particle capacity "
+                "exceeded %s (every rank raises this in the same step)"
+                % (np.nonzero(tmo)[0].tolist(), np.nonzero(over)[0].tolist(), np.nonzero(arrive > room)[0].tolist()))
+        offs = np.cumsum(cnt, axis=0) - cnt          # offs[s, d]: records of ranks below s towards d
+        for r in ranks:
+            r.migrate_push(cnt[r.rank], offs[r.rank])
+        for r in ranks:
+            r.migrate_wait()
+        for r in ranks:
+            r.migrate_unpack(int(arrive[r.rank]), int(cnt[r.rank].sum()))
+    else:
+        # the leave counts are exchanged on the device; one small device->host read per step brings both
+        # count vectors back (they size the messages)
+        send_counts, recv_counts = comm.exchange_count_tensors([r.buf["LEAVE_COUNTS"] for r in ranks])
+        for r, sc in zip(ranks, send_counts):
+            r.migrate_pack(sc)
+        comm.all_to_all_v(B("MIG_SEND"), send_counts, B("MIG_RECV"), recv_counts)
+        for r, sc, rc in zip(ranks, send_counts, recv_counts):
+            r.migrate_unpack(sum(rc), sum(sc))
     mark("migrate")
     if timer:
         timer.end_step()
@@ -743,18 +819,21 @@ def make_ranks(n_cells, pos, vel, comm, device=None, slack=1.25, ids=None):
         sel = owner == r
         sr = SlabRank(n_cells, max(cap, int(sel.sum().item()) + 4096), dev, r, P)
         sr.load(pos[:, sel].contiguous(), vel[:, sel].contiguous(), ids[sel].contiguous())
+        sr.total_particles = int(npart)
         out.append(sr)
     return out
 
 
-def make_rank_from_local(n_cells, pos_l, vel_l, ids_l, rank, nranks, device=None, capacity=None):
+def make_rank_from_local(n_cells, pos_l, vel_l, ids_l, rank, nranks, device=None, capacity=None, total_particles=None):
     """A SlabRank loaded with particles the caller already knows belong to `rank` (e.g. initial
-    conditions generated per slab)."""
+    conditions generated per slab).  total_particles: the particle count over ALL ranks (fixes the
+    mean density the transform subtracts); None = not subtracted."""
     dev = torch.cuda.current_device() if device is None else device
     n = pos_l.shape[1]
     cap = int(capacity) if capacity else int(n * 1.25) + 4096
     sr = SlabRank(n_cells, max(cap, n + 4096), dev, rank, nranks)
     sr.load(pos_l.contiguous(), vel_l.contiguous(), ids_l.contiguous())
+    sr.total_particles = None if total_particles is None else int(total_particles)
     return sr
 
 

@@ -115,14 +115,16 @@ PM_API int pm_plan_block_stats(pm_plan *plan, int rows_per_block, int cap, int64
  * reference scatters in particle-index order, src/density.py:17, and has no counterpart):
  *   PM_SORT_AUTO  re-sort only the entries whose cell key changed since the previous step and merge
  *                 them into the still-sorted rest; falls back to PM_SORT_FULL when there is no
- *                 previous order or more than 40 % of the entries moved.  One 4-byte device->host
- *                 read (the mover count) per step.
+ *                 previous order or more than 40 % of the entries moved.  The mover count and that
+ *                 decision stay on the device: no host synchronisation.
  *   PM_SORT_FULL  stable radix sort of every entry (also: environment variable PM_SORT=full).
- * Both give the same order bit for bit.  pm_plan_sort_stats reports what the last sort did
- * (mode: PM_SORT_FULL or PM_SORT_INCREMENTAL). */
+ * Both give the same order bit for bit (own stable radix sort, csrc/pm_sort.cu).  pm_plan_sort_stats
+ * reports what the last sort did (mode: PM_SORT_FULL or PM_SORT_INCREMENTAL); it reads the device and
+ * therefore synchronises. */
 #define PM_SORT_AUTO 0
 #define PM_SORT_FULL 1
 #define PM_SORT_INCREMENTAL 2
+#define PM_SORT_ERROR 3        /* pm_plan_sort_stats only: a grid barrier of the radix sort timed out */
 PM_API int pm_plan_set_sort_mode(pm_plan *plan, int mode);
 PM_API int pm_plan_sort_stats(const pm_plan *plan, int64_t *entries, int64_t *movers, int *mode);
 PM_API int64_t pm_plan_np_capacity(const pm_plan *plan);
@@ -255,6 +257,11 @@ PM_API int pm_slab_ghost_add(pm_plan *plan, pm_stream_t stream);
  * chunk overlaps the y and z passes of its neighbours.  (Nc/2)/C must be a multiple of the column
  * tile width (16; 8 for Nc >= 1024). */
 PM_API int pm_slab_fft_rows_forward(pm_plan *plan, pm_stream_t stream);
+/* Mean of the density over the WHOLE mesh (all ranks' particles * mass / Nc^3).  The forward
+ * transform runs on rho - mean: the Green's factor zeroes the DC mode anyway, and in
+ * float32 the DC's rounding noise would otherwise leak into the lowest-k modes that 1/k^2
+ * amplifies.  Single-GPU entry points know the mean themselves; a slab rank must be told. */
+PM_API int pm_slab_set_rho_mean(pm_plan *plan, double mean);
 PM_API int pm_slab_fft_y_forward(pm_plan *plan, int chunk, int nchunks, pm_stream_t stream);
 PM_API int pm_slab_fft_z(pm_plan *plan, int chunk, int nchunks, double a, double omega_m0,
                          pm_stream_t stream);
@@ -299,12 +306,52 @@ PM_API int pm_slab_ghost_wait_rho(pm_plan *plan, pm_stream_t stream);
 PM_API int pm_slab_ghost_push_phi(pm_plan *plan, pm_stream_t stream);
 PM_API int pm_slab_ghost_wait_phi(pm_plan *plan, pm_stream_t stream);
 PM_API int pm_slab_gather(pm_plan *plan, double a, double f_a1, double da, pm_stream_t stream);
+/* Ghost planes and particle migration through peer memory (csrc/pm_migrate.cu; no reference counterpart,
+ * SURVEY 8e).  After pm_slab_peer_import / pm_slab_peer_set, pm_slab_peer_aux_export / _import / _set publish
+ * three more buffers of every rank: its potential buffer (ghost planes), its migration receive buffer and
+ * its count matrix (offsets[3] inside the exported workspace, or plain pointers from pm_slab_aux_buffers for
+ * plans inside one process).  Then, per step and in this order on every rank:
+ *   pm_slab_migrate_counts_push   my leavers per destination + my error state -> every rank's matrix, flag
+ *   pm_slab_migrate_counts_read   wait for all rows; copies the matrix to the host (the step's one host read):
+ *                                 matrix_h[nranks][nranks + 3], row s = rank s's leavers per destination, its
+ *                                 flag-wait timeouts, its leave-list overflow flag, its free particle capacity
+ *   pm_slab_migrate_push          records of my leavers (ascending slot order) into the destinations' receive
+ *                                 buffers at dest_offsets[d] (= leavers of lower ranks towards d), flag
+ *   pm_slab_migrate_wait          wait for every sender; then pm_slab_migrate_unpack as with the NCCL route */
+PM_API int pm_slab_peer_aux_export(pm_plan *plan, uint64_t *offsets3);
+PM_API int pm_slab_peer_aux_import(pm_plan *plan, int peer, const uint64_t *offsets3);
+PM_API int pm_slab_peer_aux_set(pm_plan *plan, int peer, void *phi_buffer, void *mig_recv, void *count_matrix);
+PM_API int pm_slab_aux_buffers(pm_plan *plan, void **phi_buffer, void **mig_recv, void **count_matrix);
+PM_API int pm_slab_migrate_counts_push(pm_plan *plan, pm_stream_t stream);
+PM_API int pm_slab_migrate_counts_read(pm_plan *plan, uint32_t *matrix_h, pm_stream_t stream);
+PM_API int pm_slab_migrate_push(pm_plan *plan, const int64_t *send_counts, const int64_t *dest_offsets,
+                                pm_stream_t stream);
+PM_API int pm_slab_migrate_wait(pm_plan *plan, pm_stream_t stream);
 PM_API int pm_slab_migrate_pack(pm_plan *plan, const int64_t *counts_h, pm_stream_t stream);
 PM_API int pm_slab_migrate_unpack(pm_plan *plan, int64_t n_arrive, int64_t n_leave, pm_stream_t stream);
 /* live_d[s] = 0 for entries whose particle has left; rows are dense [3][pm_slab_entries()] */
 PM_API int pm_slab_export(pm_plan *plan, float *pos_d, float *vel_d, uint32_t *ids_d, uint32_t *live_d,
                           pm_stream_t stream);
 
+/* pm_step_resident replays its steady-state launch sequence as a CUDA graph (two graphs, one per buffer-set
+ * parity; only a one-thread parameter kernel is re-parameterised per step) when the step is graphable: own
+ * FFT, tiled gather (128/256/512 meshes), incremental sort, not being profiled, a non-default stream.
+ * pm_plan_set_graph(plan, 0) (or PM_GRAPH=0) keeps it eager; pm_plan_graph_replays counts the replays. */
+PM_API int pm_plan_set_graph(pm_plan *plan, int on);
+PM_API int pm_plan_graph_replays(const pm_plan *plan);
+/* The two halves of pm_step_resident as separate calls, for callers that drive the reference's loop
+ * body statement by statement (src/pmesh.py:60-61):
+ *     rho = density(positions, mass)                          -> pm_resident_deposit
+ *     positions, velocities = advance_time(rho, ..., a, da)   -> pm_resident_advance
+ * pm_resident_deposit orders the resident state by cell (incrementally) and deposits it into rho_d;
+ * calling it again before the state changes deposits again without re-sorting.  pm_resident_advance
+ * solves for the potential of rho_d (any density mesh; rho_mean = its mean if the caller knows it --
+ * total mass / Nc^3 for a density this library deposited -- or NaN to have it measured) and applies
+ * gather + kick + drift to the resident state.  pm_particles_store then writes the state back in the
+ * caller's original particle order.  Reference: src/density.py:7-48, src/integrate.py:9-13. */
+PM_API int pm_resident_deposit(pm_plan *plan, double mass, float *rho_d, pm_stream_t stream);
+PM_API int pm_resident_advance(pm_plan *plan, const float *rho_d, double rho_mean, double a, double da,
+                               double f_a1, double omega_m0, pm_stream_t stream);
 /*
  * The same loop body for a caller that keeps its state in host memory like the reference does
  * (NumPy arrays): uploads pos_h/vel_h, runs pm_step, downloads the updated pos_h/vel_h (and

@@ -142,11 +142,13 @@ pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
 comm = pm.slab.DistComm()
 ranks = pm.slab.make_ranks(n_cells, pos, vel, comm, device=0)
 assert pm.slab.setup_peers(ranks, comm), "CUDA IPC mapping / flag handshake failed"
+assert pm.slab.setup_ghost_peers(ranks, comm), "mapping of the ghost / migration buffers failed"
 ref_p, ref_v = pos.clone(), vel.clone()
 a, da = 0.3, 0.0099
 for s in range(3):
     pm.step(ref_p, ref_v, a, da, mass=8.0)
-    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2, 1)[s], transport=("fused", "peer", "fused")[s])
+    pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2, 1)[s], transport=("fused", "peer", "fused")[s],
+                      ghosts=("peer", "peer", "nccl")[s], migrate=("peer", "nccl", "peer")[s])
     a += da
 torch.cuda.synchronize()
 assert ranks[0].peer_timeouts() == 0
@@ -179,25 +181,32 @@ def test_peer_transport_through_cuda_ipc_two_processes_one_gpu(tmp_path):
     assert out.stdout.count("-ok") == 2, out.stdout
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PM_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental paths (ghost planes through peer memory, two-stream fused schedule): "
-                           "written without GPU time left in round 1 -- run with PM_TEST_EXPERIMENTAL=1 to validate them")
 @pytest.mark.parametrize("P", [1, 2, 4])
-def test_experimental_ghost_pushes_and_two_stream_schedule_are_bit_identical(pm, P):
+def test_ghost_planes_and_migration_through_peer_memory_are_bit_identical(pm, P):
+    """Ghost planes pushed into the neighbours' memory, particle migration through peer memory (count
+    matrix + records, csrc/pm_migrate.cu) and the two-stream fused schedule move the same numbers as
+    the NCCL send/recv and all-to-all-v routes: particles (by id) and potential bit for bit."""
     n_parts, n_cells = 64, 128
     cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
     pm.set_config(cfg)
     pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=5, vel_rms=0.5)
     outs = []
-    for transport, ghosts in (("fused", "nccl"), ("fused", "peer"), ("fused2", "peer"), ("nccl", "peer")):
+    for transport, ghosts, migrate in (("fused", "nccl", "nccl"), ("fused", "peer", "nccl"), ("fused", "peer", "peer"),
+                                       ("fused2", "peer", "peer"), ("nccl", "peer", "peer"), ("fused", None, None)):
         pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
         comm = pm.slab.LocalComm(P)
         ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
         assert pm.slab.setup_peers(ranks, comm) and pm.slab.setup_ghost_peers(ranks, comm)
+        moved = 0
         for s in range(4):
+            before = [r.count for r in ranks]
             pm.slab.slab_step(ranks, comm, 0.4 + 0.0099 * s, 0.0099, mass=8.0, cfg=cfg, chunks=(1, 2, 2, 1)[s],
-                              transport=transport, ghosts=ghosts)
+                              transport=transport, ghosts=ghosts, migrate=migrate)
+            moved += sum(abs(x - r.count) for x, r in zip(before, ranks))
         assert all(r.peer_timeouts() == 0 for r in ranks)
+        assert sum(r.count for r in ranks) == pos.shape[1]
+        if P > 1:
+            assert moved > 0                      # the migration route really carried particles
         phi = torch.cat([r.buf["PHI"] for r in ranks]).clone()
         outs.append(pm.slab.collect(ranks, comm, pos.shape[1]) + (phi,))
         for r in ranks:
@@ -205,6 +214,28 @@ def test_experimental_ghost_pushes_and_two_stream_schedule_are_bit_identical(pm,
     for other in outs[1:]:
         for x, y in zip(outs[0], other):
             assert torch.equal(x, y)
+
+
+def test_exchange_errors_are_raised_by_every_rank(pm):
+    """A leave list that overflows on ONE rank is seen in the count matrix by all of them: every rank
+    raises SlabExchangeError in the same step (nobody is left waiting in a collective)."""
+    n_parts, n_cells, P = 32, 64, 2
+    cfg = types.SimpleNamespace(**O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100).__dict__)
+    pm.set_config(cfg)
+    pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=5, vel_rms=0.1)
+    pos, vel = torch.from_numpy(pos_h).cuda(), torch.from_numpy(vel_h).cuda()
+    comm = pm.slab.LocalComm(P)
+    ranks = pm.slab.make_ranks(n_cells, pos, vel, comm)
+    assert pm.slab.setup_peers(ranks, comm) and pm.slab.setup_ghost_peers(ranks, comm)
+    pm.slab.slab_step(ranks, comm, 0.4, 0.0099, mass=8.0, cfg=cfg)
+    # fake an overflow on rank 1: its leave count towards rank 0 beyond the list capacity
+    ranks[1].buf["LEAVE_COUNTS"][0] = 2 ** 30
+    for r in ranks:
+        r.migrate_counts_push()
+    mats = [r.migrate_counts_read() for r in ranks]
+    assert all((m == mats[0]).all() for m in mats) and mats[0][1, P + 1] == 1 and mats[0][0, P + 1] == 0
+    for r in ranks:
+        r.close()
 
 
 def test_slab_run_is_deterministic(pm):

@@ -27,12 +27,14 @@ comm = pm.slab.DistComm()
 ranks = pm.slab.make_ranks(n_cells, pos, vel, comm, device=local)
 peer_ok = pm.slab.setup_peers(ranks, comm)     # CUDA IPC over NVLink; the NCCL path needs no set-up
 assert peer_ok, "peer-memory transport could not be set up on this box"
+assert pm.slab.setup_ghost_peers(ranks, comm), "mapping of the ghost / migration buffers failed"
 ref_p, ref_v = pos.clone(), vel.clone()
 a, da = 0.3, 0.0099
 for s in range(6):
     pm.step(ref_p, ref_v, a, da, mass=8.0)
     pm.slab.slab_step(ranks, comm, a, da, mass=8.0, cfg=cfg, chunks=(1, 2)[s %% 2],
-                      transport=("fused", "peer", "nccl")[s %% 3])
+                      transport=("fused", "peer", "nccl")[s %% 3], ghosts=("peer", "nccl")[s %% 2],
+                      migrate=("peer", "peer", "nccl", "nccl")[s %% 4])
     a += da
 torch.cuda.synchronize()
 assert ranks[0].peer_timeouts() == 0

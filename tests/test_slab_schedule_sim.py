@@ -26,6 +26,11 @@ and, with the ghost planes pushed through peer memory (ghosts="peer", experiment
       after that rank's gather of the previous step has read it;
   H7  rank-1's potential plane lands on phi plane 0 only after this step's ghost_add has read the density
       ghost from there.
+
+and, with the migration through peer memory (migrate="peer"):
+
+  H8  a rank unpacks step n's arrivals only after EVERY rank has stored its step-n records;
+  H9  no rank stores step n+1's records into a receive buffer before its owner unpacked step n's.
 """
 import contextlib
 import itertools
@@ -82,9 +87,12 @@ class RankRecorder:
                "fft_rows_inverse", "fft_y_forward_local", "fft_push", "fft_pull", "fft_y_inverse_local",
                "fft_y_forward_push", "fft_y_inverse_pull", "gather", "migrate_pack", "migrate_unpack",
                "ghost_push_rho", "ghost_wait_rho", "ghost_push_phi", "ghost_wait_phi", "signal", "wait"]
+    SLOT_MIG_COUNTS, SLOT_MIG_DATA = 19, 20          # PM_SLOT_MIG_* of csrc/pm_internal.cuh
 
     def __init__(self, rank, nranks, n_cells=512):
         self.rank, self.nranks, self.n_cells, self.peers_ready, self.ghosts_ready = rank, nranks, n_cells, True, True
+        self.mig_ready = True
+        self.total_particles = None
         self.buf = {k: (k, rank) for k in slab.BUF}
         self.main, self.side = Stream("main"), Stream("side")
         self.current = self.main
@@ -101,6 +109,24 @@ class RankRecorder:
 
     def chunk(self, name, c, C):
         return (name, self.rank, c)
+
+    # migration through peer memory: stores + flag word / flag wait (+ the host read), as pm_migrate.cu does
+    def migrate_counts_push(self):
+        self.current.ops.append(("signal", "signal", self.SLOT_MIG_COUNTS))
+
+    def migrate_counts_read(self):
+        import numpy as np
+        self.current.ops.append(("wait", "wait", self.SLOT_MIG_COUNTS))
+        m = np.zeros((self.nranks, self.nranks + 3), dtype=np.int64)
+        m[:, self.nranks + 2] = 1 << 30
+        return m
+
+    def migrate_push(self, counts, offsets):
+        self.current.ops.append(("kernel", "migrate_push", None))
+        self.current.ops.append(("signal", "signal", self.SLOT_MIG_DATA))
+
+    def migrate_wait(self):
+        self.current.ops.append(("wait", "wait", self.SLOT_MIG_DATA))
 
 
 class CommRecorder:
@@ -131,9 +157,10 @@ class CommRecorder:
         self._coll("a2av", range(self.nranks))
 
 
-def record_program(P, steps, transport, chunks, two_streams, monkeypatch, ghosts="nccl"):
+def record_program(P, steps, transport, chunks, two_streams, monkeypatch, ghosts="nccl", migrate="nccl"):
     """Run slab_step `steps` times for each rank against the recorders -> per-rank op queues."""
     monkeypatch.setattr(slab, "torch", types.SimpleNamespace(cuda=FakeCuda))
+    monkeypatch.setattr(slab.rt, "lib", lambda: types.SimpleNamespace(pm_slab_set_rho_mean=lambda *a: 0))
     cfg = types.SimpleNamespace(N_CELLS=512, N_PARTS=256, H0=0.68, OMEGA_LAMBDA0=0.69, OMEGA_K0=0.0, OMEGA_M0=0.31)
     ranks = []
     for r in range(P):
@@ -142,7 +169,7 @@ def record_program(P, steps, transport, chunks, two_streams, monkeypatch, ghosts
         comm = CommRecorder(rec, two_streams)
         for s in range(steps):
             slab.slab_step([rec], comm, 0.1 + 0.01 * s, 0.01, mass=8.0, cfg=cfg, chunks=chunks, transport=transport,
-                           ghosts=ghosts)
+                           ghosts=ghosts, migrate=migrate)
         ranks.append(rec)
     return ranks
 
@@ -158,10 +185,12 @@ def execute(ranks, transport, chunks, rng):
     P = len(ranks)
     pc = {(r.rank, s.name): 0 for r in ranks for s in (r.main, r.side)}
     queues = {(r.rank, s.name): s.ops for r in ranks for s in (r.main, r.side)}
-    flags = [[[0] * P for _ in range(2 * HALF)] for _ in range(P)]       # flags[owner][slot][writer]
-    sig_epoch = [[0] * (2 * HALF) for _ in range(P)]
+    NSLOT = 24
+    flags = [[[0] * P for _ in range(NSLOT)] for _ in range(P)]          # flags[owner][slot][writer]
+    sig_epoch = [[0] * NSLOT for _ in range(P)]
     wait_epoch = {}                                                       # (rank, stream, pc) -> epoch
-    wait_count = [[0] * (2 * HALF) for _ in range(P)]
+    wait_count = [[0] * NSLOT for _ in range(P)]
+    mig_pushed, unpacked = {}, [0] * P                                    # step -> ranks that stored their records
     arrived = {}                                                          # collective key -> set of ranks at it
     coll_done = [0] * P                                                   # collectives completed per rank (issue order)
     step = [0] * P                                                        # deposits executed
@@ -244,6 +273,14 @@ def execute(ranks, transport, chunks, rng):
                 if any(o[1] == "ghost_push_phi" for o in q) and min(gflag.get((r, "phi_up"), 0), gflag.get((r, "phi_dn"), 0)) < n:
                     raise Hazard(f"H5: rank {r} gathers step {n} before its potential ghost planes arrived")
                 gathered[r] += 1
+            elif name == "migrate_push":
+                if any(unpacked[d] < n - 1 for d in range(P)):
+                    raise Hazard(f"H9: rank {r} stores step {n}'s records before every owner unpacked step {n - 1}'s")
+                mark(mig_pushed, n, r)
+            elif name == "migrate_unpack":
+                if any(o[1] == "migrate_push" for o in q) and not full(mig_pushed, n):
+                    raise Hazard(f"H8: rank {r} unpacks step {n} before every rank stored its records")
+                unpacked[r] += 1
             elif name in ("fft_push", "fft_y_forward_push"):
                 if n > 1 and not full(fetched, (n - 1, c)):
                     raise Hazard(f"H3: rank {r} stores step {n} chunk {c} before everyone fetched step {n - 1}'s")
@@ -307,6 +344,38 @@ def test_ghost_planes_through_peer_memory_are_ordered(monkeypatch, P, transport,
                     if op[0] == "record":
                         op[1].done = False
         assert execute(ranks, transport, chunks, random.Random(seed)) == n_ops
+
+
+@pytest.mark.parametrize("transport,chunks,two_streams,ghosts", [("fused", 1, True, "peer"), ("fused2", 2, True, "peer"),
+                                                                 ("nccl", 2, True, "nccl"), ("peer", 2, False, "peer")])
+@pytest.mark.parametrize("P", [2, 3, 4])
+def test_migration_through_peer_memory_is_ordered(monkeypatch, P, transport, chunks, two_streams, ghosts):
+    ranks = record_program(P, steps=3, transport=transport, chunks=chunks, two_streams=two_streams,
+                           monkeypatch=monkeypatch, ghosts=ghosts, migrate="peer")
+    assert not any(op[0] == "collective" and op[1] in ("counts", "a2av") for r in ranks for op in r.main.ops)
+    n_ops = sum(len(s.ops) for r in ranks for s in (r.main, r.side))
+    for seed in range(25):
+        for r in ranks:
+            for s in (r.main, r.side):
+                for op in s.ops:
+                    if op[0] == "record":
+                        op[1].done = False
+        assert execute(ranks, transport, chunks, random.Random(seed)) == n_ops
+
+
+def test_the_model_catches_unordered_migration(monkeypatch):
+    """Drop the waits on the migration flags and H8 must fire for some interleaving."""
+    ranks = record_program(2, steps=2, transport="fused", chunks=1, two_streams=False, monkeypatch=monkeypatch,
+                           ghosts="peer", migrate="peer")
+    for r in ranks:
+        r.main.ops = [op for op in r.main.ops if not (op[0] == "wait" and op[2] == RankRecorder.SLOT_MIG_DATA)]
+    fired = set()
+    for seed in range(60):
+        try:
+            execute(ranks, "fused", 1, random.Random(seed))
+        except Hazard as e:
+            fired.add(str(e)[:2])
+    assert "H8" in fired
 
 
 def test_the_model_catches_an_unordered_ghost_push(monkeypatch):
