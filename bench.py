@@ -343,6 +343,115 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def weak_scaling_record(args, rank, world, dev, dist, pm, comm, transport, chunks):
+    """BASELINE configs[3] (1024^3 particles on a 2048^3 mesh over all `world` = 8 GPUs) against configs[2]
+    (512^3 on 1024^3) on ONE GPU: the same load per GPU, so parallel efficiency = t(1 GPU) / t(8 GPUs)
+    (north_star asks for >= 70 %).  A bounded sub-record of the --gpus 8 line: 3 warm-up + 3
+    timed steps each.  Every rank enters; rank 0 alone runs the one-GPU part."""
+    import torch
+    slab = pm.slab
+    K, W = 3, 3
+    rec = {"workload_1gpu": workload_label(512, 1024), "workload_all_gpus": workload_label(1024, 2048), "steps": K, "warmup": W}
+    ok = torch.ones(1, dtype=torch.int32, device=f"cuda:{dev}")
+    err = ""
+
+    def agree():
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(int(ok.item()))
+
+    # ---- one GPU: 512^3 on 1024^3, resident path, on rank 0 ----
+    ms1 = 0.0
+    try:
+        if rank == 0:
+            cfg1 = cfg_namespace(512, 1024)
+            pm.set_config(cfg1)
+            pl, vl, il = make_particles_slab_gpu(512, 1024, 0, 1, dev)
+            del il
+            st = pm.ResidentParticles(pl, vl)
+            del pl, vl
+            torch.cuda.empty_cache()
+            sched = pm.loop_scale_factors(cfg1)
+            side = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(side):
+                for i in range(W):
+                    st.step(*sched[i], mass=8.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(W, W + K):
+                    st.step(*sched[i], mass=8.0)
+                e1.record()
+                side.synchronize()
+                ms1 = e0.elapsed_time(e1) / K
+            st.close()
+            torch.cuda.empty_cache()
+    except Exception as e:      # noqa: BLE001 -- reported in the record, the main line must still be printed
+        ok.zero_()
+        err = "1-GPU part: " + repr(e)[:200]
+    if not agree():
+        return dict(rec, error=err or "failed on another rank")
+    t = torch.tensor([ms1], dtype=torch.float64, device=f"cuda:{dev}")
+    dist.broadcast(t, 0)
+    ms1 = float(t.item())
+    # ---- all GPUs: 1024^3 on 2048^3, slab path ----
+    n_parts, n_cells = 1024, 2048
+    cfg = cfg_namespace(n_parts, n_cells)
+    pm.set_config(cfg)
+    ranks = []
+    try:
+        pl, vl, il = make_particles_slab_gpu(n_parts, n_cells, rank, world, dev)
+        ranks = [slab.make_rank_from_local(n_cells, pl, vl, il, rank, world, device=dev, total_particles=n_parts ** 3)]
+        del pl, vl, il
+        torch.cuda.empty_cache()
+    except Exception as e:      # noqa: BLE001
+        ok.zero_()
+        err = "slab set-up: " + repr(e)[:200]
+    if not agree():
+        for r in ranks:
+            r.close()
+        return dict(rec, error=err or "failed on another rank")
+    tr = "nccl"
+    if transport != "nccl" and slab.setup_peers(ranks, comm):
+        tr = transport
+    aux = tr != "nccl" and slab.setup_ghost_peers(ranks, comm)
+    sched = pm.loop_scale_factors(cfg)
+    timer = slab.PhaseTimer()
+    kw = dict(mass=8.0, cfg=cfg, chunks=chunks or None, transport=tr, ghosts="peer" if aux else "nccl",
+              migrate="peer" if aux else "nccl")
+    for i in range(W):
+        slab.slab_step(ranks, comm, *sched[i], **kw)
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        slab.slab_step(ranks, comm, *sched[i], timer=timer, **kw)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / K], dtype=torch.float64, device=f"cuda:{dev}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms8 = float(t.item())
+    phases = timer.mean_ms()
+    tmo = torch.tensor([ranks[0].peer_timeouts() if tr != "nccl" else 0], dtype=torch.int64, device=f"cuda:{dev}")
+    dist.all_reduce(tmo, op=dist.ReduceOp.MAX)
+    slab.release_peers(ranks, comm)
+    for r in ranks:
+        r.close()
+    torch.cuda.empty_cache()
+    peak, _ = measured_hbm_peak()
+    bstep = b_step_bytes(n_parts ** 3, n_cells)
+    nvlink_bytes = 2 * (4 * n_cells ** 3 / world) * (world - 1) / world
+    t_roof = (bstep / world) / (peak * 1e9) + nvlink_bytes / 900e9
+    rec.update({"ms_per_step_1gpu": ms1, "ms_per_step_all_gpus": ms8, "n_gpus": world,
+                "parallel_efficiency": ms1 / ms8 if ms8 > 0 else None, "target": 0.70,
+                "value_all_gpus": n_parts ** 3 / (ms8 * 1e-3), "unit": UNIT,
+                "fft_transport": tr, "ghost_planes": kw["ghosts"], "migration": kw["migrate"],
+                "phases_ms_rank0": phases, "peer_flag_timeouts": int(tmo.item()),
+                "roofline_step": {"t_roof_ms": 1e3 * t_roof, "frac": 1e3 * t_roof / ms8,
+                                  "formula": "(60*Np+64*Nc^3)/P/hbm + 2*(4*Nc^3/P)*(P-1)/P/900e9 (SURVEY 8e, serial bound)"}})
+    return rec
+
+
 def run_slab(args, rank, world, local_rank):
     """N > 1: the 256^3/512^3 step slab-decomposed over the GPUs of the box (strong scaling)."""
     import torch
@@ -521,6 +630,16 @@ def run_slab(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         e2e_value = npart * ke / float(tmax[0].item())
 
+    weak = None
+    if world == 8 and (n_parts, n_cells) == (256, 512) and not args.no_weak_scaling:
+        # free the strong-scaling state first: configs[3] needs the memory
+        slab.release_peers(ranks, comm)
+        for r in ranks:
+            r.close()
+        ranks = []
+        torch.cuda.empty_cache()
+        weak = weak_scaling_record(args, rank, world, dev, dist, pm, comm, transport, args.chunks)
+        pm.set_config(cfg)
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         bstep = b_step_bytes(npart, n_cells)
@@ -561,6 +680,7 @@ def run_slab(args, rank, world, local_rank):
             "phases_ms_rank0": phases,
             "mass_conservation_rel_err": mass_err,
             "peer_flag_timeouts": peer_timeouts,
+            "weak_scaling": weak,
         }
         print(json.dumps(line), flush=True)
     slab.release_peers(ranks, comm)
@@ -623,27 +743,51 @@ def run_ours(args, rank, world, local_rank):
     barrier()
 
     # ---- timed region: K resident steps, CUDA events on the launching stream ----
+    # (a side stream: the legacy default stream cannot be captured, and the steady-state step replays as a
+    # CUDA graph -- include/pmstep.h, pm_plan_set_graph)
+    import ctypes
+    import numpy as np
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
     sampler = ClockSampler(dev)
     sampler.start()
     time.sleep(0.3)
-    rt.check(rt.lib().pm_plan_profile_begin(plan.handle, K), "profile_begin")
-    launches0 = pm.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(K):
-        a, da = sched[step_i % len(sched)]
-        state.step(a, da, mass=mass)
-        step_i += 1
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = pm.launch_count() - launches0
+    with torch.cuda.stream(side):
+        for _ in range(2):                       # the first steps on this stream capture the two graphs
+            a, da = sched[step_i % len(sched)]
+            state.step(a, da, mass=mass)
+            step_i += 1
+        barrier()
+        replays0 = int(rt.lib().pm_plan_graph_replays(plan.handle))
+        launches0 = pm.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(K):
+            a, da = sched[step_i % len(sched)]
+            state.step(a, da, mass=mass)
+            step_i += 1
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        launches_eager = pm.launch_count() - launches0
+        graph_replays = int(rt.lib().pm_plan_graph_replays(plan.handle)) - replays0
+        # ---- second pass, eager, with CUDA events between the stages: the per-stage breakdown ----
+        rt.check(rt.lib().pm_plan_profile_begin(plan.handle, K), "profile_begin")
+        launches0 = pm.launch_count()
+        evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evp0.record()
+        for _ in range(K):
+            a, da = sched[step_i % len(sched)]
+            state.step(a, da, mass=mass)
+            step_i += 1
+        evp1.record()
+        barrier()
+        ms_profiled = evp0.elapsed_time(evp1) / K
+        launches = pm.launch_count() - launches0          # kernels of one eager pass = kernels inside each replay
+    torch.cuda.current_stream(dev).wait_stream(side)
     sort_n, sort_movers, sort_mode = state.sort_stats()
     block_stats = state.block_stats()
     fft_sync_errors = int(rt.lib().pm_plan_fft_sync_errors(plan.handle))
-    import ctypes
-    import numpy as np
     nst = len(rt.STAGE_NAMES)
     buf = np.zeros((K, nst), dtype=np.float32)
     nrec = ctypes.c_int(0)
@@ -682,6 +826,57 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e_value = npart * world * ke / e2e_s
+
+    # ---- drop-in leg: the reference's own loop body (src/pmesh.py:60-61), statement for statement ----
+    dropin = None
+    if not args.no_e2e:
+        dropin = {}
+        state.store(pos, vel)
+        fgrid = pm.fourier_grid()
+        pd, vd = pos.clone(), vel.clone()
+
+        def loop_body(p_, v_, a_, da_):
+            rho_ = pm.density(p_, mass)                                          # pmesh.py:60
+            return pm.advance_time(rho_, p_, v_, fgrid, a_, da_)                  # pmesh.py:61
+
+        for _ in range(3):                      # first call: stateless + session set-up; then the resident session
+            a, da = sched[step_i % len(sched)]
+            loop_body(pd, vd, a, da)
+            step_i += 1
+        barrier()
+        kd = max(3, min(K, 20))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(kd):
+            a, da = sched[step_i % len(sched)]
+            loop_body(pd, vd, a, da)
+            step_i += 1
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / kd
+        dropin["cuda_tensors"] = {"value": npart / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": kd,
+                                  "api": "rho = density(pos, mass); pos, vel = advance_time(rho, pos, vel, fgrid, a, da) on CUDA "
+                                         "tensors: resident session behind the reference's signatures (_session.py)"}
+        pm.forget_resident()
+        del pd, vd
+        # NumPy in / NumPy out, as the reference's driver holds its state: every call crosses PCIe
+        pn, vn = pos.cpu().numpy().copy(), vel.cpu().numpy().copy()
+        kn = 3
+        a, da = sched[step_i % len(sched)]
+        loop_body(pn, vn, a, da)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(kn):
+            a, da = sched[step_i % len(sched)]
+            loop_body(pn, vn, a, da)
+            step_i += 1
+        torch.cuda.synchronize()
+        msn = 1e3 * (time.perf_counter() - t0) / kn
+        dropin["numpy"] = {"value": npart / (msn * 1e-3), "unit": UNIT, "ms_per_step": msn, "steps": kn,
+                           "h2d_bytes_per_step": 2 * 12 * npart + 12 * npart + 4 * n_cells ** 3,
+                           "d2h_bytes_per_step": 4 * n_cells ** 3 + 24 * npart,
+                           "api": "the same two calls on NumPy arrays (pageable host memory; the density mesh is returned to the host too)"}
+        del pn, vn
 
     if rank != 0:
         return
@@ -724,7 +919,12 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 24 * npart, "steps": ke,
                 "api": "pm_step_host (pinned host pos+vel in, pos+vel out; density stays on device, "
                        "as with the reference defaults SAVE_DENSITY=False, PLOT_*=False)"},
+        "e2e_dropin": dropin,
         "gpu_launches": int(launches),
+        "graph": {"replays_in_timed_region": graph_replays, "eager_launches_in_timed_region": int(launches_eager),
+                  "note": "steady-state steps replay as a CUDA graph; gpu_launches counts the kernels of the same K steps "
+                          "run eagerly in the profiled second pass (one replay launches the same kernels)"},
+        "ms_per_step_profiled_pass": ms_profiled,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg[dominant], "ms_per_launch": stage_ms[dominant]},
@@ -732,6 +932,7 @@ def run_ours(args, rank, world, local_rank):
                           "frac": ach_step / peak, "algorithmic_bytes_per_step": bstep,
                           "formula": "60*Np + 64*Nc^3 (SURVEY 8d)"},
         "stages_ms": stage_ms,
+        "stages_note": "CUDA events between the stages of a second, eager pass over the same K steps (the timed pass replays graphs)",
         "stage_frac_of_peak": {n: alg[n] / (stage_ms[n] * 1e-3) / 1e9 / peak for n in stage_ms if stage_ms[n] > 0.01},
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -761,6 +962,8 @@ def main():
     ap.add_argument("--evolve-steps", type=int, default=0, help="--particles evolved: steps to evolve (0 = the whole schedule)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="multi-GPU exploration runs: skip the host-buffer leg")
+    ap.add_argument("--no-weak-scaling", action="store_true",
+                    help="--gpus 8: skip the weak_scaling sub-record (configs[3] on 8 GPUs against configs[2] on one)")
     ap.add_argument("--chunks", type=int, default=0, help="kx chunks of the distributed FFT pipeline (0 = auto)")
     ap.add_argument("--transport", default="auto", choices=["auto", "fused", "fused2", "peer", "nccl"],
                     help="FFT transposes of the multi-GPU path: peer-memory copy kernels or NCCL all-to-all")

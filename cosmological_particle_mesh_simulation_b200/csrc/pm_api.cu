@@ -362,8 +362,10 @@ int pm_plan_destroy(pm_plan *p)
     if (p->s_down) cudaStreamDestroy(p->s_down);
     for (int s = 0; s < PM_PEER_MAX; ++s)
         if (p->peer_ipc[s]) cudaIpcCloseMemHandle(p->peer_ipc[s]);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 2; ++k) {
         if (p->graph_exec[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[k]);
+        if (p->graph_tpl[k]) cudaGraphDestroy((cudaGraph_t)p->graph_tpl[k]);
+    }
     if (p->mig_matrix_h) cudaFreeHost(p->mig_matrix_h);
     if (p->ws) cudaFree(p->ws);
     if (p->prof_ev) {
@@ -724,8 +726,10 @@ __global__ void k_set_step_params(PmStepParams v, PmStepParams *dst) { *dst = v;
 static void graph_drop(pm_plan *p, int k)
 {
     if (p->graph_exec[k]) cudaGraphExecDestroy((cudaGraphExec_t)p->graph_exec[k]);
+    if (p->graph_tpl[k]) cudaGraphDestroy((cudaGraph_t)p->graph_tpl[k]);
     p->graph_exec[k] = nullptr;
     p->graph_node[k] = nullptr;
+    p->graph_tpl[k] = nullptr;
 }
 
 static PmStepParams step_params_for(const pm_plan *p, double a, double da, double f_a1, double omega_m0)
@@ -802,8 +806,8 @@ static int resident_step_graphed(pm_plan *p, double mass, double a, double da, d
             p->use_graph = false;
             return resident_step(p, mass, a, da, f_a1, omega_m0, rho_d, st);
         }
-        cudaGraphDestroy(graph);
-        p->graph_exec[k] = exec; p->graph_node[k] = node;
+        // the node handle that cudaGraphExecKernelNodeSetParams takes belongs to this graph: keep it alive
+        p->graph_exec[k] = exec; p->graph_node[k] = node; p->graph_tpl[k] = graph;
         p->graph_rho[k] = rho; p->graph_mass[k] = mass; p->graph_omega[k] = omega_m0; p->graph_np[k] = p->rnp;
         p->graph_stream[k] = st;
     } else {

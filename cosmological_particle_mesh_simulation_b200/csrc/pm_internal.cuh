@@ -185,7 +185,8 @@ struct pm_plan {
     PmStepParams *graph_params;    // == step_params_d while a step is being CAPTURED (kernels then read it), else nullptr
     bool use_graph;                // PM_GRAPH=0 turns replay off
     void *graph_exec[2];           // cudaGraphExec_t per buffer-set parity
-    void *graph_node[2];           // the parameter kernel node of each
+    void *graph_node[2];           // the parameter kernel node of each (a handle into graph_tpl, which must outlive it)
+    void *graph_tpl[2];            // cudaGraph_t the executable was instantiated from
     float *graph_rho[2];           // what each was captured for
     double graph_mass[2], graph_omega[2];
     int64_t graph_np[2];

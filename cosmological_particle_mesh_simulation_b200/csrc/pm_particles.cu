@@ -621,6 +621,10 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
                                   uint32_t *cnt, cudaStream_t st)
 {
     int zc = 32;
+    if (const char *e = getenv("PM_GATHER_ZC")) {      // planes per CTA (tuning: shorter marches balance a clustered load)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) zc = v;
+    }
     while (zc > 1 && (NC % zc || (int64_t)(NC / PM_GT_YB) * (NC / zc) < 8LL * p->sm_count)) zc /= 2;
     constexpr size_t smem = kGtSmem<NC, PM_GT_YB, PM_GT_CAP>;
     static_assert(smem <= 227 * 1024 / PM_GT_MINB, "PM_GT_MINB CTAs per SM");

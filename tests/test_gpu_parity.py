@@ -477,6 +477,44 @@ def test_incremental_sort_equals_full_sort_bit_for_bit(pm, n_parts, n_cells, vsi
     assert sorted(out["auto"][0].tolist()) == list(range(npart))
 
 
+@pytest.mark.parametrize("n_parts,n_cells", [(64, 128), (96, 256)])
+def test_graph_replay_equals_eager_steps_bit_for_bit(pm, n_parts, n_cells):
+    """The steady-state resident step replays as a CUDA graph when it runs on a non-default stream
+    (pm_api.cu, resident_step_graphed): two graphs, one per buffer-set parity, re-parameterised through
+    one kernel node per step.  Eight steps (capture x2, then replays of both parities with NEW scalars
+    every step) must leave the same storage order, positions, velocities and density as eager steps."""
+    import ctypes
+    cfg = types.SimpleNamespace(N_CELLS=n_cells, N_PARTS=n_parts, OMEGA_M0=0.31, OMEGA_K0=0.0,
+                                OMEGA_LAMBDA0=0.69, H0=0.68, A_INIT=0.01, A_END=1.0, STEPS=1000)
+    pm.set_config(cfg)
+    rt = pm._runtime
+    rng = np.random.default_rng(11)
+    npart = n_parts ** 3 - 5
+    pos = rng.uniform(0, n_cells, (3, npart)).astype(np.float32)
+    vel = rng.normal(0, 0.05, (3, npart)).astype(np.float32)
+    sched = pm.loop_scale_factors(cfg)[:8]
+    out = {}
+    for mode in ("eager", "graph"):
+        st = pm.ResidentParticles(dev(pos), dev(vel))
+        rt.check(rt.lib().pm_plan_set_graph(st.plan.handle, 1 if mode == "graph" else 0), "pm_plan_set_graph")
+        rho = torch.zeros((n_cells,) * 3, device="cuda")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for a, da in sched:
+                st.step(a, da, rho_out=rho)
+        side.synchronize()
+        replays = int(rt.lib().pm_plan_graph_replays(st.plan.handle))
+        p, v = torch.empty(3, npart, device="cuda"), torch.empty(3, npart, device="cuda")
+        st.store(p, v)
+        out[mode] = (st.order().cpu().numpy(), p.cpu().numpy(), v.cpu().numpy(), rho.cpu().numpy(), replays, st.sort_stats())
+        st.close()
+    assert out["eager"][4] == 0
+    assert out["graph"][4] == len(sched) - 1, "every step after the first (full sort, not steady state) is a replay"
+    for k in range(4):
+        assert np.array_equal(out["eager"][k], out["graph"][k]), ("order", "positions", "velocities", "density")[k]
+
+
 @pytest.mark.parametrize("name", ["g16_free10", "clustered32"])
 def test_fused_step_and_host_step_equal_the_composed_calls(pm, golden_dir, name):
     g, cfg = load_case(golden_dir, name)
