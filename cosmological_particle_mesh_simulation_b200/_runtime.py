@@ -76,6 +76,7 @@ def lib():
             "pm_plan_n_cells": (i32, [vp]),
             "pm_plan_np_capacity": (i64, [vp]),
             "pm_plan_set_fft_backend": (i32, [vp, i32]),
+            "pm_plan_set_sin2_table": (i32, [vp, vp]),
             "pm_plan_fft_backend": (i32, [vp]),
             "pm_plan_set_fft_fuse": (i32, [vp, i32, i32]),
             "pm_plan_fft_sync_errors": (i32, [vp]),
@@ -170,7 +171,7 @@ EXPORTED_SYMBOLS = (
     "pm_plan_np_capacity", "pm_fourier_grid", "pm_cell_keys", "pm_sort_by_cell", "pm_deposit_cic",
     "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_plan_profile_begin",
     "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_resident_deposit", "pm_resident_advance", "pm_plan_set_graph", "pm_plan_graph_replays", "pm_particles_store",
-    "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend",
+    "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend", "pm_plan_set_sin2_table",
     "pm_plan_create_slab", "pm_slab_buffer", "pm_slab_load", "pm_slab_count", "pm_slab_entries",
     "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_rows_forward", "pm_slab_set_rho_mean", "pm_slab_fft_y_forward",
     "pm_slab_fft_z", "pm_slab_fft_y_inverse", "pm_slab_fft_rows_inverse", "pm_slab_gather",
@@ -230,6 +231,22 @@ def config():
 # ---------------------------------------------------------------------------------------------
 # plans
 # ---------------------------------------------------------------------------------------------
+def reference_sin2_table(n_cells: int):
+    """sin^2(k_i/2) for the Nc wavenumbers of one axis, evaluated with the reference's own NumPy
+    expressions (src/fourier_utils.py:8-15: k = float32(2*pi*fftfreq(Nc)), np.sin(k/2)**2 in float32).
+    The Green's table of fourier_grid() is 1/((s[i] + s[j]) + s[l]); with this s installed in a plan
+    (pm_plan_set_sin2_table) the kernels' G equals the reference's table bit for bit."""
+    import numpy as np
+    scale = 2 * np.pi
+    k = np.array(scale * np.fft.fftfreq(int(n_cells)), dtype="float32")
+    return np.ascontiguousarray(np.sin(k / 2) ** 2, dtype=np.float32)
+
+
+def install_reference_tables(handle, n_cells: int):
+    s2 = reference_sin2_table(n_cells)
+    check(lib().pm_plan_set_sin2_table(handle, s2.ctypes.data), "pm_plan_set_sin2_table")
+
+
 class Plan:
     """Owns one pm_plan* (cuFFT plans, Green's table, all per-step scratch) on one device."""
 
@@ -239,6 +256,7 @@ class Plan:
         check(lib().pm_plan_create(ctypes.byref(h), self.n_cells, self.np_capacity, self.device),
               f"pm_plan_create(n_cells={n_cells}, np={np_capacity}, device={device})")
         self.handle = h
+        install_reference_tables(h, self.n_cells)
 
     def close(self):
         if getattr(self, "handle", None):

@@ -18,6 +18,22 @@ torch bumps the tensor's version counter, which ends the session: the next call 
 caller's arrays again.  (A write that bypasses torch -- a raw pointer handed to another library --
 cannot be seen; call `forget()` after such a write, or disable the mechanism with
 `set_enabled(False)` / PM_DROPIN_RESIDENT=0.)  CUDA tensors only: NumPy arrays carry no version.
+
+Write-back.  By default every `advance_time` ends with pm_particles_store: the caller's tensors hold
+the new state in the caller's order when the call returns, exactly the in-place contract of the
+reference (src/integrate.py:15-25 updates its arguments).  That un-permute is a 4-byte scatter of
+24 bytes per particle -- 1.05 ms of a 3.35 ms step at 256^3 particles, for arrays the reference's
+loop never reads between two steps (src/pmesh.py:56-63 only hands them to the next call and, every
+N-th step, to save_file).  `set_enabled("lazy")` / PM_DROPIN_RESIDENT=lazy defers it: `advance_time`
+returns `ResidentView` handles -- torch.Tensor subclasses over the caller's own storage -- and the
+scatter runs the first time anybody USES one of them (any torch function or method that touches
+data: .cpu(), indexing, arithmetic, data_ptr(), __cuda_array_interface__, np.asarray ...; pure
+metadata such as .shape does not count), or at `sync()`.  `density` / `advance_time` accept the
+handles (and the original tensors) and continue from the resident state without any write-back.
+The one thing lazy mode cannot see is a READ of the original tensor objects through a name the
+caller kept instead of the returned handles (`advance_time(...)` with the result ignored, then
+`positions.cpu()`): those bytes are stale until `sync()`.  The reference's loop rebinds
+`positions, velocities = advance_time(...)`, so it only ever holds the handles.
 """
 import os
 import weakref
@@ -29,14 +45,22 @@ try:
 except ImportError:  # flat layout
     import _runtime as rt
 
-_enabled = os.environ.get("PM_DROPIN_RESIDENT", "1") != "0"
+_mode = os.environ.get("PM_DROPIN_RESIDENT", "1").strip().lower()
+_enabled = _mode != "0"
+_lazy = _mode == "lazy"
 _session = None          # at most one: the reference's loop drives one particle set
 _last_rho = None         # (weakref(rho), version, mean) of the last density() result
 
 
-def set_enabled(flag: bool):
-    global _enabled
+def set_enabled(flag):
+    """True: resident session, write-back at the end of every advance_time (default).  "lazy": write-back
+    deferred until the returned handles are used (module docstring).  False: stateless calls."""
+    global _enabled, _lazy
+    lazy = isinstance(flag, str) and flag.strip().lower() == "lazy"
+    if not lazy:
+        sync()
     _enabled = bool(flag)
+    _lazy = lazy
     if not _enabled:
         forget()
 
@@ -45,13 +69,55 @@ def enabled() -> bool:
     return _enabled
 
 
+def lazy() -> bool:
+    return _enabled and _lazy
+
+
+def sync():
+    """Bring the caller's tensors up to date with the resident state (no-op unless a lazy write-back
+    is pending)."""
+    if _session is not None:
+        _session.flush()
+
+
 def forget():
     """Drop the session (frees its plan); the next advance_time starts from the caller's arrays."""
     global _session, _last_rho
     if _session is not None:
+        _session.flush()
         _session.close()
     _session = None
     _last_rho = None
+
+
+def _getter(name):
+    return getattr(torch.Tensor, name).__get__
+
+
+# torch functions that read no tensor data: they do not trigger the deferred write-back
+_METADATA = frozenset(
+    [_getter(n) for n in ("shape", "device", "dtype", "ndim", "is_cuda", "layout", "requires_grad", "is_leaf",
+                          "grad_fn", "_version", "names", "is_sparse", "is_quantized", "is_meta")] +
+    [getattr(torch.Tensor, n) for n in ("size", "dim", "numel", "nelement", "stride", "is_contiguous", "storage_offset",
+                                        "element_size", "get_device", "is_floating_point", "is_complex", "__len__",
+                                        "is_pinned", "is_shared", "_is_view", "type")])
+
+
+class ResidentView(torch.Tensor):
+    """What advance_time returns in lazy mode: the caller's tensor (same storage, same version counter)
+    whose bytes may be one or more steps behind the resident state until somebody looks."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        if func not in _METADATA:
+            sync()
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **(kwargs or {}))
+
+
+def unwrap(t):
+    """The plain tensor behind a ResidentView (no torch function runs, so nothing is written back)."""
+    return t.__dict__["_pm_base"] if type(t) is ResidentView else t
 
 
 class Session:
@@ -63,7 +129,28 @@ class Session:
         self.n_cells = int(n_cells)
         self.state = ResidentParticles(positions, velocities)      # own plan; loads the caller's arrays
         self.device = positions.device.index
+        self.pending = False          # lazy mode: the caller's tensors are behind the resident state
+        self.views = None
         self.remember(positions, velocities)
+
+    def defer(self):
+        """Lazy mode, after an advance: no write-back now; hand out the handles."""
+        pos, vel = self.pos_ref(), self.vel_ref()
+        if self.views is None:
+            pv, vv = pos.as_subclass(ResidentView), vel.as_subclass(ResidentView)
+            pv.__dict__["_pm_base"], vv.__dict__["_pm_base"] = pos, vel      # the views keep the originals alive
+            self.views = (pv, vv)
+        self.pending = True
+        return self.views
+
+    def flush(self):
+        if not self.pending or self.state.plan is None:
+            return
+        self.pending = False
+        pos, vel = self.pos_ref(), self.vel_ref()
+        if pos is None or vel is None:
+            return                        # nobody can read them any more
+        self.state.store(pos, vel)        # raw-pointer write: the version counters (and the session) stay valid
 
     def remember(self, positions, velocities):
         self.pos_ref, self.vel_ref = weakref.ref(positions), weakref.ref(velocities)
@@ -109,6 +196,7 @@ def session_for_advance(positions, velocities, n_cells):
     if _session is not None and _session.matches(positions, velocities, n_cells):
         return _session
     if _session is not None:
+        _session.flush()          # lazy mode: the tensors of the old session get their last state first
         _session.close()
         _session = None
     _session = Session(positions, velocities, n_cells)

@@ -1,5 +1,6 @@
 // pm_api.cu -- the extern "C" surface declared in include/pmstep.h.
 #include <math.h>
+#include <stdio.h>
 #include <new>
 #include <stdlib.h>
 #include <string.h>
@@ -302,7 +303,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     rc = pm_k_sin2_table(p);
     {
         const char *be = getenv("PM_FFT_BACKEND");  // "cufft" forces the library path (A/B checks)
-        p->own_fft = pm_fft_supported(n_cells) && (g.slab || !(be && strcmp(be, "cufft") == 0));
+        p->own_fft = pm_fft_supported(n_cells) && (g.slab || !(be && (strcmp(be, "cufft") == 0 || strcmp(be, "f64") == 0)));
+        p->fft_f64 = !g.slab && be && strcmp(be, "f64") == 0 && n_cells <= 256;   // diagnostic float64 transforms (pm_poisson.cu)
     }
     if (rc == PM_OK && pm_fft_supported(n_cells)) rc = pm_k_fft_tables(p);
     if (rc == PM_OK) rc = (int)cudaMemset(p->fft_sync, 0, sizeof(unsigned));
@@ -324,6 +326,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_a, cudaEventDisableTiming);
     if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_b, cudaEventDisableTiming);
     if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_c, cudaEventDisableTiming);
+    for (int k = 0; k < PM_HOST_CHUNKS && rc == PM_OK; ++k) rc = (int)cudaEventCreateWithFlags(&p->ev_chunk[k], cudaEventDisableTiming);
     if (rc != PM_OK) {
         pm_plan_destroy(p);
         return rc;
@@ -354,9 +357,17 @@ int pm_plan_destroy(pm_plan *p)
         cufftDestroy(p->r2c);
         cufftDestroy(p->c2r);
     }
+    if (p->f64_ready) {
+        cufftDestroy(p->d2z);
+        cufftDestroy(p->z2d);
+    }
+    if (p->f64_mesh) cudaFree(p->f64_mesh);
+    if (p->f64_spec) cudaFree(p->f64_spec);
     if (p->ev_a) cudaEventDestroy(p->ev_a);
     if (p->ev_b) cudaEventDestroy(p->ev_b);
     if (p->ev_c) cudaEventDestroy(p->ev_c);
+    for (int k = 0; k < PM_HOST_CHUNKS; ++k)
+        if (p->ev_chunk[k]) cudaEventDestroy(p->ev_chunk[k]);
     if (p->s_main) cudaStreamDestroy(p->s_main);
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_down) cudaStreamDestroy(p->s_down);
@@ -380,11 +391,24 @@ int pm_plan_n_cells(const pm_plan *p) { return p ? p->nc : 0; }
 
 int pm_plan_set_fft_backend(pm_plan *p, int backend)
 {
-    if (!p || backend < 0 || backend > 1) return PM_ERR_INVALID;
+    if (!p || backend < 0 || backend > 2) return PM_ERR_INVALID;
     if (backend == 0 && !pm_fft_supported(p->nc)) return PM_ERR_UNSUPPORTED;
     if (backend == 1 && !p->have_fft) return PM_ERR_UNSUPPORTED;   // slab plans carry no cuFFT plan
+    if (backend == 2 && (p->slab || p->nc > 256)) return PM_ERR_UNSUPPORTED;   // diagnostic: small single-GPU meshes
     p->own_fft = (backend == 0);
+    p->fft_f64 = (backend == 2);
     return PM_OK;
+}
+
+int pm_plan_set_sin2_table(pm_plan *p, const float *sin2_h)
+{
+    if (!p || !sin2_h) return PM_ERR_INVALID;
+    DeviceGuard guard;
+    const int rc = guard.enter(p->device);
+    if (rc != PM_OK) return rc;
+    PM_CUDA(cudaDeviceSynchronize());          // no solve may be reading the tables
+    PM_CUDA(cudaMemcpy(p->sin2, sin2_h, sizeof(float) * p->nc, cudaMemcpyHostToDevice));
+    return pm_k_sin2rev_install(p, sin2_h);
 }
 
 int pm_plan_set_sort_mode(pm_plan *p, int mode)
@@ -403,7 +427,7 @@ int pm_plan_sort_stats(const pm_plan *p, int64_t *entries, int64_t *movers, int 
     return pm_k_sort_stats(const_cast<pm_plan *>(p), entries, movers, mode);
 }
 
-int pm_plan_fft_backend(const pm_plan *p) { return p ? (p->own_fft ? 0 : 1) : PM_ERR_INVALID; }
+int pm_plan_fft_backend(const pm_plan *p) { return p ? (p->own_fft ? 0 : (p->fft_f64 ? 2 : 1)) : PM_ERR_INVALID; }
 
 int pm_plan_set_fft_variant(pm_plan *p, int two_stage)
 {
@@ -886,12 +910,21 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     p->rsort_done = false;
     const size_t w = (size_t)np * sizeof(float), pitch = (size_t)p->rstride * sizeof(float);
     (void)pbytes;
+    // PM_HOST_TIMING=1: a timeline of this call on stderr (events on the three streams; diagnostic only)
+    static const bool timing = getenv("PM_HOST_TIMING") && atoi(getenv("PM_HOST_TIMING")) != 0;
+    cudaEvent_t tl[8] = {};
+    auto tmark = [&](int k, cudaStream_t s) {
+        if (timing && cudaEventCreate(&tl[k]) == cudaSuccess) cudaEventRecord(tl[k], s);
+    };
+    tmark(0, p->s_main);
     if (np) {
         PM_CUDA(cudaMemcpy2DAsync(p->rpos[0], pitch, pos_h, w, w, 3, cudaMemcpyHostToDevice, p->s_main));
         PM_CUDA(cudaMemcpy2DAsync(p->rvel[0], pitch, vel_h, w, w, 3, cudaMemcpyHostToDevice, p->s_up));
         PM_CUDA(cudaMemcpyAsync(p->rid[0], p->iota, (size_t)np * 4, cudaMemcpyDeviceToDevice, p->s_main));
     }
     PM_CUDA(cudaEventRecord(p->ev_a, p->s_up));
+    tmark(1, p->s_main);      // positions uploaded
+    tmark(2, p->s_up);        // velocities uploaded
     cudaStream_t st = p->s_main;
     PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->rstride, p->keys, nullptr, st));
     PM_TRY(pm_k_sort(p, np, 0, st));
@@ -904,20 +937,48 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     }
     p->rho_mean_hint = (double)np * mass / ((double)p->nc * p->nc * p->nc);
     PM_TRY(pm_k_poisson(p, p->mesh, a, omega_m0, p->mesh2, st));
+    tmark(3, st);             // potential ready
     PM_CUDA(cudaStreamWaitEvent(st, p->ev_a, 0));
     PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));
+    tmark(4, st);             // gather done
     p->rcur = 1;
-    // un-permute into set 0 as dense [3][np] arrays (the unpermute kernel writes stride np)
-    PM_TRY(pm_k_unpermute(p, p->rpos[0], p->rvel[0], st));
-    if (np) {
+    // un-permute into set 0 as dense [3][np] arrays (the unpermute kernels write stride np)
+    if (np && pm_unpermute_aos_ok(p, p->rpos[0], p->rvel[0])) {
+        // one sector-wide scatter of all particles into the idle half-spectrum buffer, then ranges of the
+        // caller's order are streamed into the six rows and downloaded while the next range is formed:
+        // the device-to-host link starts ~0.2 ms after the gather instead of after a full un-permute
+        PM_TRY(pm_k_unpermute_scatter_aos(p, st));
+        for (int k = 0; k < PM_HOST_CHUNKS; ++k) {
+            const int64_t i0 = (np * k / PM_HOST_CHUNKS) & ~(int64_t)63, i1 = k + 1 == PM_HOST_CHUNKS ? np : ((np * (k + 1) / PM_HOST_CHUNKS) & ~(int64_t)63);
+            if (i1 <= i0) continue;
+            PM_TRY(pm_k_aos_rows_range(p, i0, i1, p->rpos[0], p->rvel[0], st));
+            PM_CUDA(cudaEventRecord(p->ev_chunk[k], st));
+            PM_CUDA(cudaStreamWaitEvent(p->s_down, p->ev_chunk[k], 0));
+            const size_t cw = (size_t)(i1 - i0) * sizeof(float);
+            PM_CUDA(cudaMemcpy2DAsync(pos_h + i0, w, p->rpos[0] + i0, w, cw, 3, cudaMemcpyDeviceToHost, p->s_down));
+            PM_CUDA(cudaMemcpy2DAsync(vel_h + i0, w, p->rvel[0] + i0, w, cw, 3, cudaMemcpyDeviceToHost, p->s_down));
+        }
+    } else if (np) {
+        PM_TRY(pm_k_unpermute(p, p->rpos[0], p->rvel[0], st));
         PM_CUDA(cudaEventRecord(p->ev_c, st));
         PM_CUDA(cudaMemcpyAsync(pos_h, p->rpos[0], 3 * w, cudaMemcpyDeviceToHost, st));
         PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
         PM_CUDA(cudaMemcpyAsync(vel_h, p->rvel[0], 3 * w, cudaMemcpyDeviceToHost, p->s_up));
     }
+    tmark(5, st);             // un-permute kernels done
+    tmark(6, p->s_down);      // downloads done (chunked path)
     PM_CUDA(cudaStreamSynchronize(p->s_main));
     PM_CUDA(cudaStreamSynchronize(p->s_up));
     PM_CUDA(cudaStreamSynchronize(p->s_down));
+    if (timing && tl[0]) {
+        float t[8] = {};
+        for (int k = 1; k <= 6; ++k)
+            if (tl[k]) cudaEventElapsedTime(&t[k], tl[0], tl[k]);
+        fprintf(stderr, "pm_step_host timeline (ms): pos up %.2f | vel up %.2f | phi ready %.2f | gather done %.2f | un-permute done %.2f | download done %.2f\n",
+                t[1], t[2], t[3], t[4], t[5], t[6]);
+        for (int k = 0; k < 8; ++k)
+            if (tl[k]) cudaEventDestroy(tl[k]);
+    }
     p->rnp = 0;  // the resident buffers were scratch for this call
     p->rkeys_valid = false;
     return PM_OK;

@@ -209,16 +209,25 @@ struct NoMid {
 // G(k) of src/fourier_utils.py:15-16 in float32, summed as (s_axis0 + s_axis1) + s_axis2, 0 at DC
 __device__ __forceinline__ float green_f32(float sz, float sy, float sx)
 {
-    // 1/ksq by MUFU.RCP plus one Newton step (<= 1 ulp; the IEEE division sequence costs three
-    // times the instructions and this runs once per spectrum element inside the issue-bound z pass)
     const float ksq = (sz + sy) + sx;
 #ifdef PM_GREEN_IEEE_DIV
     return ksq != 0.0f ? 1.0f / ksq : 0.0f;
 #else
+#ifdef PM_GREEN_EXACT_RCP
+    // correctly rounded 1/ksq = np.divide(1, k_squared) of fourier_utils.py:16 bit for bit: measured +0.05 ms
+    // on the 0.31 ms fused z pass of the 512^3 mesh, and invisible in every parity figure
+    return ksq != 0.0f ? __frcp_rn(ksq) : 0.0f;
+#else
+    // 1/ksq by MUFU.RCP plus one Newton step: within 1 ulp of the reference's correctly rounded float32
+    // quotient.  That ulp is far below the float32 transform noise of this path -- the float64 diagnostic
+    // backend (pm_poisson.cu), which uses the exact quotient, shows which is which
+    // (tests/test_gpu_parity.py, spike fixtures): with float32 transforms the exact reciprocal changed no
+    // parity figure (profiles/r02_notes.md).
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ksq));
     r = fmaf(r, fmaf(-ksq, r, 1.0f), r);
     return ksq != 0.0f ? r : 0.0f;
+#endif
 #endif
 }
 
@@ -1476,6 +1485,31 @@ int pm_k_fft_tables(pm_plan *p)
     cudaError_t e = cudaMemcpy(p->tw, tw, sizeof(float2) * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->sin2rev, sr, sizeof(float) * n, cudaMemcpyHostToDevice);
     free(tw);
+    free(sr);
+    return (int)e;
+}
+
+// The digit-reversed copy of a caller-supplied sin^2 table (pm_plan_set_sin2_table).
+int pm_k_sin2rev_install(pm_plan *p, const float *sin2_h)
+{
+    const int n = p->nc;
+    if (!pm_fft_supported(n)) return PM_OK;
+    float *sr = (float *)malloc(sizeof(float) * n);
+    if (!sr) return PM_ERR_NOMEM;
+    for (int k = 0; k < n; ++k) {
+        int pos = 0;
+        switch (n) {
+            case 32: pos = digit_rev<32>(k); break;
+            case 64: pos = digit_rev<64>(k); break;
+            case 128: pos = digit_rev<128>(k); break;
+            case 256: pos = digit_rev<256>(k); break;
+            case 512: pos = digit_rev<512>(k); break;
+            case 1024: pos = digit_rev<1024>(k); break;
+            case 2048: pos = digit_rev<2048>(k); break;
+        }
+        sr[pos] = sin2_h[k];
+    }
+    const cudaError_t e = cudaMemcpy(p->sin2rev, sr, sizeof(float) * n, cudaMemcpyHostToDevice);
     free(sr);
     return (int)e;
 }

@@ -70,6 +70,7 @@ struct PmStepParams {
     float pad;
 };
 
+#define PM_HOST_CHUNKS 4
 struct pm_plan {
     int nc;           // N_CELLS
     int64_t np_cap;   // particle capacity
@@ -133,6 +134,12 @@ struct pm_plan {
     unsigned *fft_sync;   // [0] error flag, then per direction: ticket + per-plane counters
     cufftHandle r2c, c2r;
     bool have_fft;
+    // diagnostic backend 2 (pm_plan_set_fft_backend): the reference's own transform precision, float64
+    // D2Z/Z2D through cuFFT on buffers allocated on first use (pm_poisson.cu, pm_k_poisson_f64)
+    bool fft_f64, f64_ready;
+    cufftHandle d2z, z2d;
+    double *f64_mesh;     // [nc^3]
+    double *f64_spec;     // [nc^2 * (nc/2+1)] complex
 
     // resident particle state (pm_particles_load / pm_step_resident / pm_particles_store), two
     // buffer sets; set rcur holds the particles in the cell order of the previous step's sort.
@@ -145,6 +152,7 @@ struct pm_plan {
     bool rsort_done;      // keys_sorted / order_sorted / row_start describe set rcur as it is now (pm_api.cu)
     cudaStream_t s_main, s_up, s_down;
     cudaEvent_t ev_a, ev_b, ev_c;
+    cudaEvent_t ev_chunk[PM_HOST_CHUNKS];   // pm_step_host: un-permuted particle ranges ready for download
 
     // slab-mode scratch (nranks > 1, or a 1-rank slab plan used to test the slab kernels)
     float2 *tbuf[2];        // all-to-all staging: [nranks][nzl][nyl][nc/2] (+ side [nranks][nzl][nyl])
@@ -229,6 +237,9 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
                                     double da, cudaStream_t st);
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
+bool pm_unpermute_aos_ok(const pm_plan *p, const float *pos_out, const float *vel_out);
+int pm_k_unpermute_scatter_aos(pm_plan *p, cudaStream_t st);
+int pm_k_aos_rows_range(pm_plan *p, int64_t i0, int64_t i1, float *pos_out, float *vel_out, cudaStream_t st);
 void pm_gather_step_scalars(double a_val, double f_a1, double da, PmStepParams *out);
 bool pm_gather_graphable(const pm_plan *p);
 int pm_k_block_stats(pm_plan *p, int rows_per_block, int cap, int64_t *out4, cudaStream_t st);
@@ -243,6 +254,7 @@ int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st);
 // pm_fft.cu
 bool pm_fft_supported(int nc);
 int pm_k_fft_tables(pm_plan *p);
+int pm_k_sin2rev_install(pm_plan *p, const float *sin2_h);
 int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                      cudaStream_t st);
 // slab pieces of the same transform, cut into C chunks of kx columns so that the all-to-all of

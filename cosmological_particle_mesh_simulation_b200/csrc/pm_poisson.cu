@@ -136,10 +136,77 @@ __global__ void __launch_bounds__(256) k_sub_mean(const float4 *__restrict__ in,
     }
 }
 
+// ---- diagnostic backend 2: the reference's transform precision ------------------------------------
+// src/potential.py:12-29 transforms the float32 density in complex128, multiplies by
+// (-3*Omega_m/8/a) * fgrid (float64 scalar x float32 table) and keeps the real part as float32.  The same
+// here with cuFFT D2Z/Z2D: everything between the float32 density and the float32 potential is float64,
+// the Green's table is the float32 one of fourier_grid().  Not a production path (no fusion, 3x the
+// memory): it exists so that a test can change ONLY the transform precision and show which part of a
+// parity residue is float32 transform noise (tests/test_gpu_parity.py, the Q4 "spike" fixtures).
+__global__ void __launch_bounds__(256) k_f2d(const float *__restrict__ in, double *__restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (double)in[i];
+}
+
+__global__ void __launch_bounds__(256) k_d2f(const double *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i];
+}
+
+__global__ void __launch_bounds__(256) k_green_multiply_f64(double2 *__restrict__ spec, const float *__restrict__ sin2,
+                                                            int nc, int nxh, double c_pot, double inv_m)
+{
+    const int rows = nc * nc;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int z = r / nc, y = r - z * nc;
+        const float sz = sin2[z], sy = sin2[y];
+        double2 *row = spec + (size_t)r * nxh;
+        for (int x = threadIdx.x; x < nxh; x += blockDim.x) {
+            // (-3*Omega_m/8/a * fgrid) * density_k, then the inverse transform's 1/Nc^3 (pyFFTW normalises)
+            const double g = __dmul_rn(c_pot, (double)pm_green(sz, sy, sin2[x]));
+            double2 c = row[x];
+            c.x = __dmul_rn(__dmul_rn(g, c.x), inv_m);
+            c.y = __dmul_rn(__dmul_rn(g, c.y), inv_m);
+            row[x] = c;
+        }
+    }
+}
+
+static int pm_k_poisson_f64(pm_plan *p, const float *rho, double a, double omega_m0, float *phi, cudaStream_t st)
+{
+    const int nc = p->nc, nxh = nc / 2 + 1;
+    const size_t cells = (size_t)nc * nc * nc;
+    if (!p->f64_ready) {
+        PM_CUDA(cudaMalloc(&p->f64_mesh, cells * sizeof(double)));
+        PM_CUDA(cudaMalloc(&p->f64_spec, (size_t)nc * nc * nxh * 2 * sizeof(double)));
+        PM_CUFFT(cufftPlan3d(&p->d2z, nc, nc, nc, CUFFT_D2Z));
+        PM_CUFFT(cufftPlan3d(&p->z2d, nc, nc, nc, CUFFT_Z2D));
+        p->f64_ready = true;
+    }
+    PM_CUFFT(cufftSetStream(p->d2z, st));
+    PM_CUFFT(cufftSetStream(p->z2d, st));
+    PM_LAUNCH(k_f2d, p->sm_count * 8, 256, 0, st, rho, p->f64_mesh, cells);
+    PM_CUFFT(cufftExecD2Z(p->d2z, p->f64_mesh, reinterpret_cast<cufftDoubleComplex *>(p->f64_spec)));
+    pm_prof_mark(p, PM_STAGE_R2C + 1, st);
+    const int rows = nc * nc;
+    PM_LAUNCH(k_green_multiply_f64, rows < p->sm_count * 8 ? rows : p->sm_count * 8, 256, 0, st,
+              reinterpret_cast<double2 *>(p->f64_spec), p->sin2, nc, nxh, -3 * omega_m0 / 8 / a,
+              1.0 / ((double)nc * nc * nc));
+    pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
+    PM_CUFFT(cufftExecZ2D(p->z2d, reinterpret_cast<cufftDoubleComplex *>(p->f64_spec), p->f64_mesh));
+    PM_LAUNCH(k_d2f, p->sm_count * 8, 256, 0, st, (const double *)p->f64_mesh, phi, cells);
+    PM_CHECK_LAUNCH();
+    pm_prof_mark(p, PM_STAGE_C2R + 1, st);
+    return PM_OK;
+}
+
 int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,
                  cudaStream_t st)
 {
     const size_t cells = (size_t)p->nc * p->nc * p->nc;
+    if (p->fft_f64) return pm_k_poisson_f64(p, rho, a, omega_m0, phi, st);
     {
         const int rc = pm_k_rho_mean(p, rho, cells, (double)cells, st);
         if (rc != PM_OK) return rc;

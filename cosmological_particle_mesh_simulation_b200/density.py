@@ -37,6 +37,7 @@ def _density_device(positions, mass, n_cells, out=None):
 
 def density(positions, mass):
     n_cells = int(rt.config().N_CELLS)
+    positions = _session.unwrap(positions)      # lazy-mode handle of the resident session: no write-back needed
     if rt.is_host(positions):
         dev = rt.current_device()
         rho = _density_device(rt.to_device(positions, dev), mass, n_cells)

@@ -65,6 +65,7 @@ def advance_time(density, positions, velocities, fgrid, a, da):
     Omega_m slot of src/cosmology.py:23)."""
     cfg = rt.config()
     fa1 = f(a + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])
+    positions, velocities = _session.unwrap(positions), _session.unwrap(velocities)   # lazy-mode handles
     if rt.is_host(positions):
         dev = rt.current_device()
         rho = rt.to_device(density, dev) if rt.is_host(density) else density
@@ -81,6 +82,8 @@ def advance_time(density, positions, velocities, fgrid, a, da):
             raise ValueError("positions must have shape (3, Np)")
         sess = _session.session_for_advance(positions, velocities, n)
         sess.advance(density, _session.known_mean(density), a, da, fa1, cfg.OMEGA_M0)
+        if _session.lazy():
+            return sess.defer()           # handles over the caller's storage; written back on first use
         sess.state.store(positions, velocities)
         return positions, velocities
     phi = _potential_device(density, fgrid, a)

@@ -66,6 +66,7 @@ class SlabRank:
             rt.check(rt.lib().pm_plan_create_slab(ctypes.byref(h), self.n_cells, self.np_capacity,
                                                   self.device, self.rank, self.nranks),
                      f"pm_plan_create_slab(n_cells={n_cells}, np={np_capacity}, rank={rank}/{nranks})")
+            rt.install_reference_tables(h, self.n_cells)     # the reference's own sin^2 table: G bit for bit
         self.handle = h
         self.total_particles = None      # particles of ALL ranks (make_ranks / make_rank_from_local set it)
         self.buf = {}

@@ -72,8 +72,18 @@ PM_API int pm_plan_destroy(pm_plan *plan);
 PM_API int pm_plan_n_cells(const pm_plan *plan);
 /* Poisson backend: 0 = hand-written sm_100a FFT with the Green's function fused into the z pass
  * (default for power-of-two meshes 32..1024), 1 = cuFFT R2C/C2R around a separate Green's kernel
- * (any mesh size; also selectable with the environment variable PM_FFT_BACKEND=cufft). */
+ * (any mesh size; also selectable with the environment variable PM_FFT_BACKEND=cufft), 2 = DIAGNOSTIC:
+ * the reference's own transform precision -- float64 D2Z/Z2D through cuFFT between the float32 density
+ * and the float32 potential (src/potential.py:12-29 works in complex128); single-GPU meshes up to 256^3,
+ * buffers allocated on first use.  It lets a test change the transform precision and nothing else. */
 PM_API int pm_plan_set_fft_backend(pm_plan *plan, int backend);
+/* The Green's function of src/fourier_utils.py:5-16 is 1/((s[z] + s[y]) + s[x]) with the Nc-entry
+ * table s[i] = sin^2(k_i/2), k_i = float32(2*pi*fftfreq(Nc)[i]), all in float32.  A plan computes s in
+ * float64 and rounds once (within 2 ulp of the reference's NumPy float32 sine, which no C library
+ * reproduces bit for bit).  A caller that has the reference's own values -- the Python layer evaluates
+ * the reference's three NumPy expressions -- installs them here (sin2_h: n_cells floats, host memory);
+ * G is then the reference's table bit for bit (correctly rounded float32 sums and reciprocal). */
+PM_API int pm_plan_set_sin2_table(pm_plan *plan, const float *sin2_h);
 PM_API int pm_plan_fft_backend(const pm_plan *plan);
 /* Hand-written FFT, meshes 256..1024: fuse != 0 runs the row pass and the y pass of each
  * direction in one persistent launch that keeps the intermediate plane in L2 (pm_fft.cu,

@@ -109,6 +109,26 @@ def test_f_matches_oracle_bitwise_and_loop_predicate():
         assert sched[0] == (0.01, (1.00 - 0.01) / steps)
 
 
+def test_cosmology_keeps_float32_on_the_restart_path():
+    """save_data.from_file returns `a` as np.float32; the reference's f(a+da) (np.sqrt, src/cosmology.py:27)
+    then stays in float32 under NumPy 2.  Same here: dtype kept, bits equal to the float32 evaluation.
+    Also the names `from cosmology import *` gives the reference's modules (cosmo, np)."""
+    import numpy as np
+    from cosmological_particle_mesh_simulation_b200 import cosmology as C
+    a = np.float32(0.3) + np.float32(0.00099)
+    cosm = [0.68, 0.69, 0.0]
+    got = C.f(a, cosm)
+    assert isinstance(got, np.floating) and got.dtype == np.float32
+    want = 1 / np.sqrt((cosm[0] + cosm[2] * a + cosm[1] * a ** 3) / a)
+    assert want.dtype == np.float32 and got.tobytes() == want.tobytes()
+    assert float(got) != 1 / np.sqrt((cosm[0] + cosm[2] * float(a) + cosm[1] * float(a) ** 3) / float(a))  # float64 differs
+    assert C.H(a, 0.68, [0.31, 0.69, 0.0]).dtype == np.float32
+    # float64 / Python float input: float64 as before
+    assert np.asarray(C.f(0.3, cosm)).dtype == np.float64
+    c = C.cosmo()
+    assert c.f0 == C.f(0.01, [0.31, 0.69, 0.0]) and c.Dt == C.Dt(0.01, [0.31, 0.69, 0.0]) and C.np is np
+
+
 def test_cosmology_functions_equal_the_reference_bitwise(golden_dir):
     """tests/golden/cosmology.json: f (with the loop's argument order, SURVEY Q1, and the intended one),
     H and Dt evaluated by the reference's own cosmology.py (oracle/make_golden.py, main_driver)."""
@@ -173,3 +193,26 @@ def test_unmodified_reference_driver_resolves_every_import_to_the_package(tmp_pa
     assert "ModuleNotFoundError" not in out.stderr, out.stderr[-1500:]
     assert "no CPU fallback" in out.stderr and os.path.join(PKG, "gaussian_random_field.py") in out.stderr
     assert "Starting the simulation for 16^3 particles with 32^3 grid cells" in out.stdout     # pmesh.py:20, its own banner
+
+
+def test_lazy_drop_in_handle_mechanics(monkeypatch):
+    """_session.ResidentView (what advance_time returns with set_resident_dropin("lazy")): metadata access
+    leaves the deferred write-back pending, any access to data triggers it first, and the handle shares
+    storage and version counter with the caller's tensor."""
+    import numpy as np
+    import torch
+    from cosmological_particle_mesh_simulation_b200 import _session as S
+    calls = []
+    monkeypatch.setattr(S, "sync", lambda: calls.append(1))
+    t = torch.arange(6.0).reshape(3, 2)
+    v = t.as_subclass(S.ResidentView)
+    v.__dict__["_pm_base"] = t
+    assert S.unwrap(v) is t and S.unwrap(t) is t
+    assert (tuple(v.shape), v.dtype, v.device.type, v.dim(), v.size(1), len(v), v.is_contiguous(), v.numel()) == \
+        ((3, 2), torch.float32, "cpu", 2, 2, 3, True, 6)
+    assert calls == []                                   # nothing above read data
+    assert type(v + 1) is torch.Tensor and len(calls) == 1
+    assert np.asarray(v).shape == (3, 2) and len(calls) == 2
+    assert v.data_ptr() == t.data_ptr() and len(calls) == 3
+    v[0, 0] = 5.0                                        # in-place write through the handle: sync first, then one version bump
+    assert len(calls) == 4 and float(t[0, 0]) == 5.0 and t._version == 1

@@ -62,11 +62,14 @@ def load_case(golden_dir, name):
 
 CASES = ["g16_free10", "g32_step2", "g12_nonpow2", "clustered32", "free16", "free32"]
 # Stress fixtures: a particle with TWO coordinates == N_CELLS deposits ~Nc^2*m into single cells of
-# a tiny mesh (squared).  That spike carries >95 % of ||phi||, so the float32 transform
-# noise, which scales with ||phi||, is large relative to every other particle's force.  They stay
-# bit-exact where the arithmetic is shared (keys, sort, deposit, gather given phi) but the
-# free-running tolerance on them is the float32-FFT noise floor measured for these inputs, not the
-# north_star's 1e-5 (which the realistic fixtures free16/free32/clustered32 and the 64^3 run meet).
+# a tiny mesh (squared).  That spike carries >95 % of ||phi||, so anything that perturbs phi
+# RELATIVE TO ITS NORM is amplified ~1e3-fold in every other particle's force: the float32 transform
+# noise (cuFFT's or ours).  They stay bit-exact where the arithmetic is shared (keys, sort, gather given
+# phi), and the free-running tolerance on them with float32 transforms is that measured floor, not the
+# north_star's 1e-5 -- which the realistic fixtures free16/free32/clustered32 and the 64^3 run meet.
+# That this is transform precision and nothing else is a TEST, not a claim:
+# test_spike_fixtures_meet_1e_5_when_only_the_transform_precision_changes runs the same loop with the
+# float64 diagnostic transforms (pm_plan_set_fft_backend 2) and requires 1e-5 at every recorded step.
 SPIKE_CASES = {"g16_free10": 1e-3, "g32_step2": 1e-4, "g12_nonpow2": 1e-3}
 
 
@@ -190,7 +193,9 @@ def test_fourier_grid_and_potential(pm, golden_dir, name):
     table = fg.to_array().cpu().numpy()
     want = O.fourier_grid(cfg)
     assert table.shape == want.shape and table[0, 0, 0] == 0.0
-    assert np.abs(table - want).max() <= 1e-6 * np.abs(want).max()
+    # bit for bit: the plan holds the reference's own sin^2(k/2) values (NumPy float32, _runtime.reference_sin2_table)
+    # and the table kernel adds and divides in correctly rounded float32 (fourier_utils.py:15-16)
+    assert np.array_equal(table, want)
     for s in range(10):
         if f"phi_{s}" not in g:
             continue
@@ -398,6 +403,40 @@ def test_free_running_steps_against_golden(pm, golden_dir, name):
             assert rel_l2(vel.cpu().numpy(), g[f"vel_{s + 1}"]) <= tol, f"velocities step {s}"
 
 
+@pytest.mark.parametrize("name", sorted(SPIKE_CASES))
+def test_spike_fixtures_meet_1e_5_when_only_the_transform_precision_changes(pm, golden_dir, name, monkeypatch):
+    """The three fixtures whose float32-transform tolerance is relaxed (SPIKE_CASES) against the north_star bar,
+    ALL their steps, with one thing changed: the Poisson solve transforms in float64 (PM_FFT_BACKEND=f64 ->
+    cuFFT D2Z/Z2D, pm_poisson.cu), as the reference's complex128 pyFFTW does (src/potential.py:19-29).
+    Deposit, Green's table (the reference's own sin^2 values, exact float32 reciprocal), gather, kick and
+    drift are the production kernels.  Measured: positions <= 5e-8, velocities <= 8e-8, density <= 9e-7."""
+    monkeypatch.setenv("PM_FFT_BACKEND", "f64")
+    pm.release_plans()
+    try:
+        g, cfg = load_case(golden_dir, name)
+        pm.set_config(cfg_ns(cfg))
+        n = cfg.N_CELLS
+        pos, vel = dev(g["pos0"]), dev(g["vel0"])
+        fg = pm.fourier_grid()
+        da = float(g["da"])
+        checked = 0
+        for s, a in enumerate(g["a_list"]):
+            rho = pm.density(pos, float(g["mass"]))
+            if f"rho_{s}" in g:
+                assert rel_l2(rho.cpu().numpy(), g[f"rho_{s}"]) <= REL_L2, f"density step {s}"
+            pm.advance_time(rho, pos, vel, fg, float(a), da)
+            if f"pos_{s + 1}" in g:
+                assert rel_l2_periodic(pos.cpu().numpy(), g[f"pos_{s + 1}"], n) <= REL_L2, f"positions step {s}"
+                assert rel_l2(vel.cpu().numpy(), g[f"vel_{s + 1}"]) <= REL_L2, f"velocities step {s}"
+                checked += 1
+        assert checked >= 2
+        from cosmological_particle_mesh_simulation_b200 import _runtime as rt
+        plan = rt.get_plan(n, pos.shape[1], pos.device.index)
+        assert rt.lib().pm_plan_fft_backend(plan.handle) == 2
+    finally:
+        pm.release_plans()          # the next test builds its plans without the override
+
+
 @pytest.mark.parametrize("name", ["free16", "free32", "clustered32", "g12_nonpow2"])
 def test_resident_state_matches_stateless_steps_and_golden(pm, golden_dir, name):
     """load -> n x pm_step_resident -> store against n x pm_step and the golden particles; the
@@ -551,6 +590,48 @@ def test_numpy_drop_in_signatures(pm, golden_dir):
     assert p2 is pos and v2 is vel and isinstance(rho, np.ndarray)
     assert rel_l2_periodic(pos, g["pos_1"], cfg.N_CELLS) <= REL_L2
     assert rel_l2(vel, g["vel_1"]) <= REL_L2
+
+
+def test_lazy_drop_in_equals_eager_drop_in_bit_for_bit(pm, golden_dir):
+    """set_resident_dropin("lazy"): the reference's loop body (src/pmesh.py:60-61, names rebound to the
+    returned objects) runs on the resident state with NO per-step write-back; the caller-visible tensors
+    are brought up to date when the handles are first used.  Same bits as the default (eager) session."""
+    from cosmological_particle_mesh_simulation_b200 import _session as S
+    g, cfg = load_case(golden_dir, "free32")
+    pm.set_config(cfg_ns(cfg))
+    n, mass, da = cfg.N_CELLS, float(g["mass"]), float(g["da"])
+    fg = pm.fourier_grid()
+    out = {}
+    try:
+        for mode in (True, "lazy"):
+            pm.forget_resident()
+            pm.set_resident_dropin(mode)
+            positions, velocities = dev(g["pos0"]), dev(g["vel0"])
+            p0 = positions
+            rhos = []
+            for a in g["a_list"][:5]:
+                rho = pm.density(positions, mass)                                                  # pmesh.py:60
+                positions, velocities = pm.advance_time(rho, positions, velocities, fg, float(a), da)   # pmesh.py:61
+                rhos.append(rho)
+            if mode == "lazy":
+                assert type(positions) is S.ResidentView and S._session.pending
+                assert tuple(positions.shape) == (3, p0.shape[1]) and S._session.pending        # metadata: still deferred
+                stale = p0.cpu().numpy()                 # the ORIGINAL object, read behind the library's back
+                assert np.array_equal(stale, g["pos0"])  # never written so far (documented hazard)
+            out[mode] = (positions.cpu().numpy(), velocities.cpu().numpy(), rhos[-1].cpu().numpy())
+            if mode == "lazy":
+                assert not S._session.pending and np.array_equal(p0.cpu().numpy(), out[mode][0])   # same storage, now current
+                # the session goes on after a read; an in-place change through the handle ends it
+                rho = pm.density(positions, mass)
+                assert S._session.matches_positions(S.unwrap(positions), n)
+                positions += 0.0
+                assert not S._session.matches_positions(S.unwrap(positions), n)
+    finally:
+        pm.forget_resident()
+        pm.set_resident_dropin(True)
+    for k in range(3):
+        assert np.array_equal(out[True][k], out["lazy"][k])
+    assert rel_l2_periodic(out["lazy"][0], g["pos_5"], n) <= REL_L2 and rel_l2(out["lazy"][1], g["vel_5"]) <= REL_L2
 
 
 @pytest.mark.parametrize("n", [32, 64, 128])
