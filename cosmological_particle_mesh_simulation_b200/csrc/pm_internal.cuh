@@ -237,6 +237,7 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
                                     double da, cudaStream_t st);
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
+int pm_k_reorder_rows(pm_plan *p, const float *in, const uint32_t *order, int64_t np, float *out, cudaStream_t st);
 bool pm_unpermute_aos_ok(const pm_plan *p, const float *pos_out, const float *vel_out);
 int pm_k_unpermute_scatter_aos(pm_plan *p, cudaStream_t st);
 int pm_k_aos_rows_range(pm_plan *p, int64_t i0, int64_t i1, float *pos_out, float *vel_out, cudaStream_t st);

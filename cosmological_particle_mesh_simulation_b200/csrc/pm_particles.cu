@@ -823,6 +823,26 @@ __global__ void __launch_bounds__(256) k_aos_to_rows(const float4 *__restrict__ 
     vel_out[i] = a.w; vel_out[np + i] = b.x; vel_out[2 * np + i] = b.y;
 }
 
+// out[d][s] = in[d][order[s]] for the three rows of a particle array (both with the plan's row stride)
+__global__ void __launch_bounds__(256) k_reorder_rows(const float *__restrict__ in, const uint32_t *__restrict__ order,
+                                                      int64_t np, int64_t stride, float *__restrict__ out)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= np) return;
+    const int64_t j = order[s];
+    out[s] = in[j];
+    out[stride + s] = in[stride + j];
+    out[2 * stride + s] = in[2 * stride + j];
+}
+
+int pm_k_reorder_rows(pm_plan *p, const float *in, const uint32_t *order, int64_t np, float *out, cudaStream_t st)
+{
+    if (np == 0) return PM_OK;
+    PM_LAUNCH(k_reorder_rows, (unsigned)((np + 255) / 256), 256, 0, st, in, order, np, p->rstride, out);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
+}
+
 // the two passes separately (pm_step_host streams pass two in chunks, each followed by its download)
 bool pm_unpermute_aos_ok(const pm_plan *p, const float *pos_out, const float *vel_out)
 {
