@@ -790,6 +790,9 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.current_stream(dev).wait_stream(side)
     sort_n, sort_movers, sort_mode = state.sort_stats()
     block_stats = state.block_stats()
+    gi = state.gather_items()
+    gather_items = {"heavy": gi[0], "light": gi[1], "overflow": gi[2],
+                    "note": "work list of the tiled gather: columns above twice the mean load are cut into pieces and dispatched first"}
     fft_sync_errors = int(rt.lib().pm_plan_fft_sync_errors(plan.handle))
     nst = len(rt.STAGE_NAMES)
     buf = np.zeros((K, nst), dtype=np.float32)
@@ -938,6 +941,7 @@ def run_ours(args, rank, world, local_rank):
                    "particles": particles_desc,
                    "sort": {"mode": sort_mode, "mover_fraction_last_step": sort_movers / max(sort_n, 1)},
                    "gather_blocks": block_stats,
+                   "gather_items": gather_items,
                    "fft": {"fused_plane_passes": os.environ.get("PM_FFT_FUSE", "0") == "1",
                            "kernels": ("radix-8.8.8" if os.environ.get("PM_FFT_V2", "1") == "0" else
                                        "two-stage" if os.environ.get("PM_FFT_ZMIX", "1") == "0" else

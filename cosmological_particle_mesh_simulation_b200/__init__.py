@@ -21,7 +21,7 @@ include/pmstep.h.  CUDA tensors in -> CUDA tensors out (state stays in HBM); Num
 NumPy arrays out (uploaded, computed on the GPU, downloaded).  There is no CPU fallback.
 """
 from . import configure_me, cosmology  # noqa: F401
-from ._runtime import PMStepError, set_config, config, launch_count, release_plans  # noqa: F401
+from ._runtime import PMStepError, set_config, config, launch_count, release_plans, set_poisson_options, poisson_options  # noqa: F401
 from .density import density  # noqa: F401
 from .fourier_utils import fourier_grid, FourierGrid  # noqa: F401
 from .potential import potential  # noqa: F401

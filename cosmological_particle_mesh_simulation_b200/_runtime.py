@@ -77,6 +77,8 @@ def lib():
             "pm_plan_np_capacity": (i64, [vp]),
             "pm_plan_set_fft_backend": (i32, [vp, i32]),
             "pm_plan_set_sin2_table": (i32, [vp, vp]),
+            "pm_plan_set_poisson_options": (i32, [vp, i32, i32]),
+            "pm_plan_poisson_options": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
             "pm_plan_fft_backend": (i32, [vp]),
             "pm_plan_set_fft_fuse": (i32, [vp, i32, i32]),
             "pm_plan_fft_sync_errors": (i32, [vp]),
@@ -99,6 +101,7 @@ def lib():
             "pm_step_resident": (i32, [vp, f64, f64, f64, f64, f64, vp, vp]),
             "pm_plan_set_graph": (i32, [vp, i32]),
             "pm_plan_graph_replays": (i32, [vp]),
+            "pm_plan_gather_items": (i32, [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32)]),
             "pm_resident_deposit": (i32, [vp, f64, vp, vp]),
             "pm_resident_advance": (i32, [vp, vp, f64, f64, f64, f64, f64, vp]),
             "pm_particles_store": (i32, [vp, vp, vp, vp]),
@@ -170,8 +173,8 @@ EXPORTED_SYMBOLS = (
     "pm_plan_workspace_bytes", "pm_plan_create", "pm_plan_destroy", "pm_plan_n_cells",
     "pm_plan_np_capacity", "pm_fourier_grid", "pm_cell_keys", "pm_sort_by_cell", "pm_deposit_cic",
     "pm_poisson", "pm_gather_kick_drift", "pm_step", "pm_step_host", "pm_plan_profile_begin",
-    "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_resident_deposit", "pm_resident_advance", "pm_plan_set_graph", "pm_plan_graph_replays", "pm_particles_store",
-    "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend", "pm_plan_set_sin2_table",
+    "pm_plan_profile_read", "pm_particles_load", "pm_step_resident", "pm_resident_deposit", "pm_resident_advance", "pm_plan_set_graph", "pm_plan_graph_replays", "pm_plan_gather_items", "pm_particles_store",
+    "pm_particles_order", "pm_particles_count", "pm_plan_set_fft_backend", "pm_plan_fft_backend", "pm_plan_set_sin2_table", "pm_plan_set_poisson_options", "pm_plan_poisson_options",
     "pm_plan_create_slab", "pm_slab_buffer", "pm_slab_load", "pm_slab_count", "pm_slab_entries",
     "pm_slab_deposit", "pm_slab_ghost_add", "pm_slab_fft_rows_forward", "pm_slab_set_rho_mean", "pm_slab_fft_y_forward",
     "pm_slab_fft_z", "pm_slab_fft_y_inverse", "pm_slab_fft_rows_inverse", "pm_slab_gather",
@@ -247,6 +250,31 @@ def install_reference_tables(handle, n_cells: int):
     check(lib().pm_plan_set_sin2_table(handle, s2.ctypes.data), "pm_plan_set_sin2_table")
 
 
+# Options of the Poisson solve the reference does not have (include/pmstep.h, pm_plan_set_poisson_options):
+# (deconvolve, kspace_gradient); (0, 0) = the reference's scheme.  Applied to every single-GPU plan made
+# after set_poisson_options() and to the cached ones.
+_poisson_options = (0, 0)
+
+
+def set_poisson_options(deconvolve=0, kspace_gradient=False):
+    """deconvolve: 0, 1 or 2 = power of the CIC window divided out of phi_k; kspace_gradient: forces from
+    -i k phi_k on three force meshes instead of central differences of phi.  Defaults = the reference."""
+    global _poisson_options
+    _poisson_options = (int(deconvolve), 1 if kspace_gradient else 0)
+    try:
+        from . import _session
+    except ImportError:
+        import _session
+    _session.forget()         # a live drop-in session owns a plan made under the old options
+    for plan in _plans.values():
+        if plan.handle is not None:
+            check(lib().pm_plan_set_poisson_options(plan.handle, *_poisson_options), "pm_plan_set_poisson_options")
+
+
+def poisson_options():
+    return _poisson_options
+
+
 class Plan:
     """Owns one pm_plan* (cuFFT plans, Green's table, all per-step scratch) on one device."""
 
@@ -257,6 +285,8 @@ class Plan:
               f"pm_plan_create(n_cells={n_cells}, np={np_capacity}, device={device})")
         self.handle = h
         install_reference_tables(h, self.n_cells)
+        if _poisson_options != (0, 0):
+            check(lib().pm_plan_set_poisson_options(h, *_poisson_options), "pm_plan_set_poisson_options")
 
     def close(self):
         if getattr(self, "handle", None):

@@ -27,7 +27,8 @@ int key_bits_for(int nc)
 struct Layout {
     size_t keys, iota, keys_sorted, order_sorted, cub, row_start, mesh, mesh2, spec, fft, sin2, tw,
         rpos, rvel, rid, tbuf, leave_cnt, leave_slot, leave_sorted, mig, peer_flags, inc_a, inc_b, inc_tile, fft_sync,
-        total;
+        gat, total;
+    int gat_cap;
     int64_t leave_cap, inc_bcap;
 };
 
@@ -90,7 +91,10 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     L->inc_b = align_up((size_t)L->inc_bcap * 8);
     L->inc_tile = align_up(((size_t)pm_sort_tiles((int64_t)npad) + 2) * 4);
     L->fft_sync = align_up((size_t)(2 * (nc + 1) + 1) * 4);
-    L->total = align_up((size_t)512 * 8192 * 8) /* dep_scratch */ + align_up(64 + 512 * 4) /* dep ctl + slot_tile */ +
+    // gather work list: 2 per base chunk + the pieces of split chunks (pm_particles.cu, pm_gather_item_threshold)
+    L->gat_cap = pm_gather_item_capacity(nc, (int64_t)npad);
+    L->gat = align_up((size_t)L->gat_cap * 16) + kAlign;
+    L->total = L->gat + align_up((size_t)512 * 8192 * 8) /* dep_scratch */ + align_up(64 + 512 * 4) /* dep ctl + slot_tile */ +
                align_up((size_t)16384 * 16) /* dep_items */ + kAlign /* diag */ + align_up(1024 * sizeof(double) + 64) /* mean */ + L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
                L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw +
                2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot +
@@ -258,6 +262,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     p->dep_items = c;                 c += align_up((size_t)16384 * 16);
     p->mean_ws = (double *)c;         p->rho_mean_d = (float *)(c + 1024 * sizeof(double));
     c += align_up(1024 * sizeof(double) + 64);
+    p->gat_items = c;                 p->gat_ctl = (uint32_t *)(c + align_up((size_t)L.gat_cap * 16));  c += L.gat;
+    p->gat_cap = L.gat_cap;
     p->rho_mean_hint = NAN;
     {
         const char *fu = getenv("PM_FFT_FUSE");   // "0": separate row and y launches (A/B checks)
@@ -283,6 +289,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         p->gather_ws = !(gw && strcmp(gw, "0") == 0);
     }
     {
+        const char *gi = getenv("PM_GATHER_ITEMS");   // "0": the gather's fixed grid, no work list
+        p->gather_items = !(gi && strcmp(gi, "0") == 0);
         const char *gr = getenv("PM_GRAPH");     // "0": never replay the resident step as a CUDA graph
         p->use_graph = !(gr && strcmp(gr, "0") == 0);
     }
@@ -361,6 +369,9 @@ int pm_plan_destroy(pm_plan *p)
         cufftDestroy(p->d2z);
         cufftDestroy(p->z2d);
     }
+    if (p->dec_tab) cudaFree(p->dec_tab);
+    if (p->spec2) cudaFree(p->spec2);
+    if (p->fmesh) cudaFree(p->fmesh);
     if (p->f64_mesh) cudaFree(p->f64_mesh);
     if (p->f64_spec) cudaFree(p->f64_spec);
     if (p->ev_a) cudaEventDestroy(p->ev_a);
@@ -409,6 +420,56 @@ int pm_plan_set_sin2_table(pm_plan *p, const float *sin2_h)
     PM_CUDA(cudaDeviceSynchronize());          // no solve may be reading the tables
     PM_CUDA(cudaMemcpy(p->sin2, sin2_h, sizeof(float) * p->nc, cudaMemcpyHostToDevice));
     return pm_k_sin2rev_install(p, sin2_h);
+}
+
+int pm_plan_set_poisson_options(pm_plan *p, int deconvolve, int kspace_gradient)
+{
+    if (!p || deconvolve < 0 || deconvolve > 2 || kspace_gradient < 0 || kspace_gradient > 1) return PM_ERR_INVALID;
+    if ((deconvolve || kspace_gradient) && (p->slab || !p->have_fft)) return PM_ERR_UNSUPPORTED;
+    DeviceGuard guard;
+    int rc = guard.enter(p->device);
+    if (rc != PM_OK) return rc;
+    PM_CUDA(cudaDeviceSynchronize());
+    const size_t cells = (size_t)p->nc * p->nc * p->nc;
+    if ((deconvolve || kspace_gradient) && !p->dec_tab) {
+        PM_CUDA(cudaMalloc(&p->dec_tab, sizeof(float) * 2 * p->nc));
+        p->k_tab = p->dec_tab + p->nc;
+    }
+    if (kspace_gradient && !p->fmesh) {
+        // allocated when the option is first asked for, never during a step
+        if (cudaMalloc(&p->spec2, (size_t)p->nc * p->nc * (p->nc / 2 + 1) * sizeof(float2)) != cudaSuccess ||
+            cudaMalloc(&p->fmesh, 3 * cells * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            if (p->spec2) cudaFree(p->spec2);
+            p->spec2 = nullptr; p->fmesh = nullptr;
+            return PM_ERR_NOMEM;
+        }
+    }
+    p->deconv = deconvolve;
+    p->kgrad = kspace_gradient;
+    if (deconvolve || kspace_gradient) rc = pm_k_poisson_tables(p);
+    return rc;
+}
+
+int pm_plan_poisson_options(const pm_plan *p, int *deconvolve, int *kspace_gradient)
+{
+    if (!p || !deconvolve || !kspace_gradient) return PM_ERR_INVALID;
+    *deconvolve = p->deconv;
+    *kspace_gradient = p->kgrad;
+    return PM_OK;
+}
+
+int pm_plan_gather_items(pm_plan *p, int64_t *heavy, int64_t *light, int *overflow)
+{
+    if (!p || !heavy || !light || !overflow) return PM_ERR_INVALID;
+    DeviceGuard guard;
+    const int rc = guard.enter(p->device);
+    if (rc != PM_OK) return rc;
+    uint32_t h[4] = {0, 0, 0, 0};
+    PM_CUDA(cudaDeviceSynchronize());
+    PM_CUDA(cudaMemcpy(h, p->gat_ctl, sizeof(h), cudaMemcpyDeviceToHost));
+    *heavy = h[0]; *light = h[1]; *overflow = (int)h[2];
+    return PM_OK;
 }
 
 int pm_plan_set_sort_mode(pm_plan *p, int mode)
@@ -770,7 +831,7 @@ static bool graph_eligible(const pm_plan *p)
 {
     // steady state only: keys and mover counts come from the previous gather, the state is not yet sorted,
     // nothing is being profiled, own FFT, tiled gather
-    return p->use_graph && !p->slab && p->own_fft && !p->prof_ev && p->rnp > 0 && p->rkeys_valid && p->inc_counted &&
+    return p->use_graph && !p->slab && p->own_fft && !p->deconv && !p->kgrad && !p->prof_ev && p->rnp > 0 && p->rkeys_valid && p->inc_counted &&
            p->rsorted_n == p->rnp && !p->rsort_done && p->sort_mode == PM_SORT_AUTO && pm_gather_graphable(p);
 }
 

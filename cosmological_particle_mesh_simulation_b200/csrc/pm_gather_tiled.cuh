@@ -27,6 +27,14 @@
 __device__ __forceinline__ void pm_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void pm_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// One CTA's share of the gather: zc planes starting at plane zs of row block yb; a crowded single plane
+// (zc == 1) may be cut into particle ranges [beg, end) of the sorted list (end > beg), else beg = end = 0.
+struct GatherItem {
+    uint32_t yb_zs;             // yb | zs << 16
+    uint32_t zc;
+    uint32_t beg, end;
+};
+
 struct GatherTiledArgs {
     const float *px, *py, *pz, *vx, *vy, *vz;   // current buffer set, one pointer per SoA row
     const uint32_t *id_in, *perm, *row_start;
@@ -35,6 +43,12 @@ struct GatherTiledArgs {
     const float *phi;
     int64_t sout;
     int zc;                     // planes per CTA
+    // k_gather_ws only.  non-null: the CTAs work through a list instead of the (row block, z chunk) grid
+    // (k_gather_items, pm_particles.cu): item i < ctl[0] is items[i] (pieces of crowded chunks, taken
+    // first), the ctl[1] others are items[item_cap - 1 - (i - ctl[0])]
+    const struct GatherItem *items;
+    const uint32_t *item_ctl;
+    int item_cap;
     double k_kick, da, aa, raa, f_a1;
     const PmStepParams *sp;     // non-null: the five scalars above are read from device memory (graph replays)
 };

@@ -107,14 +107,30 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_gather_ws(GatherTiledAr
     uint64_t *full_p = bars, *empty_p = bars + S, *full_phi = bars + 2 * S, *empty_phi = bars + 2 * S + R;
     uint32_t *s_beg = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 * R), *s_end = s_beg + 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int y0 = blockIdx.x * YB;
-    const int zc = A.zc;
-    const int zs = blockIdx.y * zc;
+    int y0 = blockIdx.x * YB;
+    int zc = A.zc;
+    int zs = blockIdx.y * zc;
+    uint32_t ov_beg = 0, ov_end = 0;
+    if (A.items) {
+        // work list: the same march over zc planes, but (row block, first plane, planes) come from an item, and
+        // an item of one crowded plane covers only a range of that plane's particles.  One CTA per list slot:
+        // the grid is the list's worst-case length and CTAs beyond its end leave here.  (A variant whose CTAs
+        // loop over items drawn from a counter -- one CTA per base chunk, no empty CTAs -- measured slower:
+        // +5 registers and the per-item barrier re-initialisation cost more than the ~8000 empty CTAs.)
+        const uint32_t nh = A.item_ctl[0], nl = A.item_ctl[1], i = blockIdx.x;
+        if (i >= nh + nl) return;
+        const GatherItem it = A.items[i < nh ? i : (uint32_t)A.item_cap - 1u - (i - nh)];
+        y0 = (int)(it.yb_zs & 0xffffu) * YB;
+        zs = (int)(it.yb_zs >> 16);
+        zc = (int)it.zc;
+        ov_beg = it.beg;
+        ov_end = it.end;
+    }
 
     for (int i = tid; i < zc; i += (CW + 1) * 32) {
         const uint32_t r = (uint32_t)(zs + i) * NC + y0;
-        s_beg[i] = A.row_start[r];
-        s_end[i] = A.row_start[r + YB];
+        s_beg[i] = ov_end > ov_beg ? ov_beg : A.row_start[r];
+        s_end[i] = ov_end > ov_beg ? ov_end : A.row_start[r + YB];
     }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {

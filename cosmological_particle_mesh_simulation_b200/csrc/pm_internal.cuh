@@ -140,6 +140,13 @@ struct pm_plan {
     cufftHandle d2z, z2d;
     double *f64_mesh;     // [nc^3]
     double *f64_spec;     // [nc^2 * (nc/2+1)] complex
+    // Poisson options (pm_plan_set_poisson_options; north_star (2)): both 0 = the reference's scheme
+    int deconv;           // phi_k /= W(k)^deconv, W = CIC window
+    int kgrad;            // 1: accelerations from -i k phi_k (three force meshes), interpolated by the gather
+    float *dec_tab;       // [nc] per-axis 1/W_i^deconv
+    float *k_tab;         // [nc] wavenumbers 2*pi*fftfreq (0 at Nyquist)
+    float2 *spec2;        // second half spectrum (one force component at a time)
+    float *fmesh;         // [3][nc^3]: 2 * (-dphi/dx_d), the "s" of pm_push
 
     // resident particle state (pm_particles_load / pm_step_resident / pm_particles_store), two
     // buffer sets; set rcur holds the particles in the cell order of the previous step's sort.
@@ -186,6 +193,11 @@ struct pm_plan {
     unsigned long long *dep_scratch;
     uint32_t *dep_ctl, *dep_slot_tile;
     void *dep_items;
+    // work list of the tiled gather (pm_gather_ws.cuh, k_gather_items): heavy items from the front, light from the back
+    void *gat_items;
+    uint32_t *gat_ctl;      // [0] heavy items, [1] light items, [2] overflow flag
+    int gat_cap;
+    bool gather_items;      // PM_GATHER_ITEMS=0: fixed (row block, z chunk) grid as before
     void *diag;             // 64 bytes of device scratch for diagnostics (pm_plan_block_stats)
 
     // CUDA-graph replay of the resident step (pm_step_resident; pm_api.cu)
@@ -237,6 +249,8 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, double f_a1,
                                     double da, cudaStream_t st);
 int pm_k_unpermute(pm_plan *p, float *pos_out, float *vel_out, cudaStream_t st);
+int pm_k_poisson_tables(pm_plan *p);
+int pm_gather_item_capacity(int nc, int64_t np);
 int pm_k_reorder_rows(pm_plan *p, const float *in, const uint32_t *order, int64_t np, float *out, cudaStream_t st);
 bool pm_unpermute_aos_ok(const pm_plan *p, const float *pos_out, const float *vel_out);
 int pm_k_unpermute_scatter_aos(pm_plan *p, cudaStream_t st);

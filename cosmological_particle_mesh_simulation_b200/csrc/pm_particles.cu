@@ -467,7 +467,7 @@ struct SlabArgs {
 #ifndef PM_GATHER_MINB
 #define PM_GATHER_MINB 8
 #endif
-template <bool PERM, bool SLAB>
+template <bool PERM, bool SLAB, bool KGRAD = false>
 __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_kick_drift(
     const float *pos_in, const float *vel_in,   // may alias pos_out/vel_out when !PERM
     const uint32_t *__restrict__ id_in, const uint32_t *__restrict__ perm,
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
     uint32_t *__restrict__ keys_out, int64_t np, int64_t sin, int64_t sout,
     const float *__restrict__ phi, int nc, double k_kick, double da, double aa, double raa,
     double f_a1, float *__restrict__ acc, SlabArgs sl, uint32_t *__restrict__ mover_cnt,
-    const uint32_t *__restrict__ keys_old)
+    const uint32_t *__restrict__ keys_old, const float *__restrict__ fmesh = nullptr)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= np) return;
@@ -523,6 +523,24 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
             zo[k] *= (uint32_t)n * (uint32_t)n;
         }
     }
+    float sx, sy, sz;
+    if (KGRAD) {
+        // option kspace_gradient (pm_plan_set_poisson_options): fmesh[d] holds 2 * (-dphi/dx_d) from the
+        // spectral derivative; interpolate it with the same eight weights, in the order of integrate.py:92
+        const size_t cells = (size_t)nc * nc * nc;
+        const uint32_t cidx[8] = {zo[1] + yo[1] + xo[1], zo[1] + yo[1] + xo[2], zo[1] + yo[2] + xo[1], zo[2] + yo[1] + xo[1],
+                                  zo[1] + yo[2] + xo[2], zo[2] + yo[1] + xo[2], zo[2] + yo[2] + xo[1], zo[2] + yo[2] + xo[2]};
+        float s3[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float *fm = fmesh + d * cells;
+            float s = __fmul_rn(__ldg(fm + cidx[0]), t[0]);
+#pragma unroll
+            for (int c = 1; c < 8; ++c) s = __fadd_rn(s, __fmul_rn(__ldg(fm + cidx[c]), t[c]));
+            s3[d] = s;
+        }
+        sx = s3[0]; sy = s3[1]; sz = s3[2];
+    } else {
     // the 32 cells with at most one "outer" (0 or 3) coordinate
     float v[4][4][4];
 #pragma unroll
@@ -535,7 +553,8 @@ __global__ void __launch_bounds__(PM_GATHER_THREADS, PM_GATHER_MINB) k_gather_ki
                 v[a][b][c] = (outer <= 1) ? __ldg(phi + (zo[a] + yo[b] + xo[c])) : 0.0f;
             }
 
-    const float sx = pm_gp<0>(v, t), sy = pm_gp<1>(v, t), sz = pm_gp<2>(v, t);
+    sx = pm_gp<0>(v, t); sy = pm_gp<1>(v, t); sz = pm_gp<2>(v, t);
+    }
     pm_push(x, vx, sx, k_kick, da, aa, raa, f_a1, nc, acc ? acc + i : nullptr);
     pm_push(y, vy, sy, k_kick, da, aa, raa, f_a1, nc, acc ? acc + np + i : nullptr);
     pm_push(z, vz, sz, k_kick, da, aa, raa, f_a1, nc, acc ? acc + 2 * np + i : nullptr);
@@ -579,10 +598,11 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
     // host scalars evaluated exactly as integrate.py:94-95 does: da*f_a1, (a_val+da)**2
     const double k_kick = da * f_a1;
     const double aa = (a_val + da) * (a_val + da);
-    auto kern = k_gather_kick_drift<false, false>;
+    auto kern = p->kgrad ? k_gather_kick_drift<false, false, true> : k_gather_kick_drift<false, false, false>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, pos, vel,
               (const uint32_t *)nullptr, (const uint32_t *)nullptr, pos, vel, (uint32_t *)nullptr,
-              (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, acc, SlabArgs(), (uint32_t *)nullptr, (const uint32_t *)nullptr);
+              (uint32_t *)nullptr, np, np, np, phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, acc, SlabArgs(), (uint32_t *)nullptr, (const uint32_t *)nullptr,
+              (const float *)p->fmesh);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
@@ -615,6 +635,106 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 #ifndef PM_GW_S
 #define PM_GW_S 3
 #endif
+
+// ---- work list of the warp-specialised gather ------------------------------------------------------
+// With a fixed grid every CTA marches zc planes of one row block whatever they hold.  On an evolved
+// particle distribution (BASELINE configs[4]) a few (row block, chunk) columns inside haloes hold 10-100
+// times the mean and their CTAs finish long after the rest of the device has drained: 1.2 ms instead of
+// 0.53 ms on the z = 0 snapshot (profiles/r02_m_bench_main_evolved.json).  k_gather_items, one thread per
+// base chunk, reads the chunk's plane counts from the row table and files either the chunk as it is
+// ("light", taken from the back of the list) or -- when it holds more than T particles -- pieces of at
+// most ~T particles ("heavy", from the front, so that they are dispatched first): runs of planes, and
+// for a single plane above T, ranges of H = T/2 of its particles.  T = twice the mean chunk load (at
+// least 4096), so a near-uniform load files every chunk unchanged.  The list order depends on atomics;
+// the result does not (every particle belongs to exactly one item, all cross-item sums are integer).
+static uint32_t pm_gather_item_threshold(int nc, int64_t np, int zc0)
+{
+    const int64_t chunks = (int64_t)(nc / PM_GT_YB) * (nc / zc0);
+    const int64_t t = chunks > 0 ? 2 * (np / chunks) : np;
+    return (uint32_t)(t < 4096 ? 4096 : (t > 0x7fffffff ? 0x7fffffff : t));
+}
+
+static int pm_gather_base_zc(int nc, int sm_count)
+{
+    int zc = 32;
+    while (zc > 1 && (nc % zc || (int64_t)(nc / PM_GT_YB) * (nc / zc) < 8LL * sm_count)) zc /= 2;
+    return zc;
+}
+
+// List length bound for `chunks` base chunks and threshold T.  A chunk is filed whole (1 item) or in pieces:
+// run pieces cut by "acc + c > T" pair up with their successor to more than T particles, so a chunk holding n
+// particles yields at most 2n/T + 1 of them (the +1 is the closing piece); one flush in front of every plane
+// above T (<= n/T); range pieces of H = T/2 particles, the last of a plane shorter (<= 2n/T + n/T).  Per chunk
+// <= 1 + 6n/T, in total <= chunks + 6 np/T.
+static int64_t pm_gather_item_bound(int64_t chunks, int64_t np, uint32_t T) { return chunks + 6 * (np / T) + 64; }
+
+int pm_gather_item_capacity(int nc, int64_t np)
+{
+    if (nc % PM_GT_YB) return 64;
+    // room for any chunk size down to one plane and the smallest threshold
+    int64_t cap = pm_gather_item_bound((int64_t)(nc / PM_GT_YB) * nc, np, 4096);
+    if (cap > (1 << 22)) cap = 1 << 22;
+    return (int)cap;
+}
+
+template <int NC, int YB>
+__global__ void __launch_bounds__(128) k_gather_items(const uint32_t *__restrict__ row_start, int zc0, uint32_t T,
+                                                      GatherItem *__restrict__ items, int cap, uint32_t *__restrict__ ctl)
+{
+    constexpr int NYB = NC / YB;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= NYB * (NC / zc0)) return;
+    const int yb = idx % NYB, zs = (idx / NYB) * zc0, y0 = yb * YB;
+    const uint32_t H = T / 2;
+    auto emit = [&](bool heavy, int z, int nz, uint32_t b, uint32_t e) {
+        const uint32_t k = atomicAdd(ctl + (heavy ? 0 : 1), 1u);
+        const uint32_t other = ctl[heavy ? 1 : 0];
+        if (k + other + 1u >= (uint32_t)cap) {          // cannot happen with pm_gather_item_capacity; never write out of bounds
+            atomicExch(ctl + 2, 1u);
+            return;
+        }
+        GatherItem it;
+        it.yb_zs = (uint32_t)yb | ((uint32_t)z << 16);
+        it.zc = (uint32_t)nz;
+        it.beg = b;
+        it.end = e;
+        items[heavy ? k : (uint32_t)cap - 1u - k] = it;
+    };
+    const uint32_t cb = row_start[(uint32_t)zs * NC + y0];
+    const uint32_t ce = row_start[(uint32_t)(zs + zc0 - 1) * NC + y0 + YB];
+    // (the planes of a chunk are separate runs of the sorted list, so ce - cb is an upper bound that also counts
+    // the other row blocks in between -- it is only used to skip the per-plane scan of an obviously light chunk)
+    uint32_t total = 0;
+    if (ce - cb > T) {
+        for (int i = 0; i < zc0; ++i) {
+            const uint32_t r = (uint32_t)(zs + i) * NC + y0;
+            total += row_start[r + YB] - row_start[r];
+        }
+    }
+    if (total <= T) {
+        emit(false, zs, zc0, 0u, 0u);
+        return;
+    }
+    int z_first = zs;
+    uint32_t acc = 0;
+    for (int i = 0; i < zc0; ++i) {
+        const uint32_t r = (uint32_t)(zs + i) * NC + y0;
+        const uint32_t b = row_start[r], e = row_start[r + YB], c = e - b;
+        if (c > T) {
+            if (zs + i > z_first) emit(true, z_first, zs + i - z_first, 0u, 0u);
+            for (uint32_t q = b; q < e; q += H) emit(true, zs + i, 1, q, e - q < H ? e : q + H);
+            z_first = zs + i + 1;
+            acc = 0;
+        } else if (acc + c > T) {
+            emit(true, z_first, zs + i - z_first, 0u, 0u);
+            z_first = zs + i;
+            acc = c;
+        } else {
+            acc += c;
+        }
+    }
+    if (zs + zc0 > z_first) emit(true, z_first, zs + zc0 - z_first, 0u, 0u);
+}
 
 template <int NC>
 static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
@@ -650,7 +770,21 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
     A.zc = zc;
     A.k_kick = k_kick; A.da = da; A.aa = aa; A.raa = pm_div_rcp(aa, da); A.f_a1 = f_a1;
     A.sp = p->graph_params;
+    A.items = nullptr; A.item_ctl = nullptr; A.item_cap = 0;
     dim3 grid(NC / PM_GT_YB, NC / zc);
+    if (p->gather_ws && p->gather_items && p->gat_items && NC <= 65535) {
+        const int nchunks = (NC / PM_GT_YB) * (NC / zc);
+        const uint32_t T = pm_gather_item_threshold(NC, p->rnp, zc);
+        // worst-case grid for a fixed launch sequence (CUDA graph): CTAs beyond the list return at once
+        int64_t gmax = pm_gather_item_bound(nchunks, p->rnp, T);
+        if (gmax > p->gat_cap) gmax = p->gat_cap;
+        PM_CUDA(cudaMemsetAsync(p->gat_ctl, 0, 4 * sizeof(uint32_t), st));
+        auto kitems = k_gather_items<NC, PM_GT_YB>;
+        PM_LAUNCH(kitems, (nchunks + 127) / 128, 128, 0, st, (const uint32_t *)p->row_start, zc, T, (GatherItem *)p->gat_items,
+                  (int)gmax, p->gat_ctl);
+        A.items = (const GatherItem *)p->gat_items; A.item_ctl = p->gat_ctl; A.item_cap = (int)gmax;
+        grid = dim3((unsigned)gmax, 1);
+    }
     if (p->gather_ws) PM_LAUNCH(kern_ws, grid, (PM_GW_CW + 1) * 32, WsSmem::total, st, A, p->fft_sync + 0);
     else PM_LAUNCH(kern, grid, PM_GT_NT, smem, st, A);
     PM_CHECK_LAUNCH();
@@ -675,7 +809,7 @@ bool pm_gather_graphable(const pm_plan *p)
 static int pm_try_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
                                uint32_t *cnt, cudaStream_t st)
 {
-    if (!p->gather_tiled || p->dep_nseg != 1 || !p->rows_valid) return PM_ERR_UNSUPPORTED;
+    if (!p->gather_tiled || p->dep_nseg != 1 || !p->rows_valid || p->kgrad) return PM_ERR_UNSUPPORTED;
     switch (p->nc) {
     case 128: return pm_launch_gather_tiled<128>(p, phi, k_kick, da, aa, f_a1, cnt, st);
     case 256: return pm_launch_gather_tiled<256>(p, phi, k_kick, da, aa, f_a1, cnt, st);
@@ -746,10 +880,11 @@ int pm_k_gather_kick_drift_resident(pm_plan *p, const float *phi, double a_val, 
         }
         if (rc != PM_ERR_UNSUPPORTED) return rc;
     }
-    auto kern = k_gather_kick_drift<true, false>;
+    auto kern = p->kgrad ? k_gather_kick_drift<true, false, true> : k_gather_kick_drift<true, false, false>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c],
               p->rvel[c], p->rid[c], p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np,
-              p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, (float *)nullptr, SlabArgs(), cnt, (const uint32_t *)p->keys_sorted);
+              p->rstride, p->rstride, phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, (float *)nullptr, SlabArgs(), cnt, (const uint32_t *)p->keys_sorted,
+              (const float *)p->fmesh);
     PM_CHECK_LAUNCH();
     p->inc_counted = (cnt != nullptr);
     return PM_OK;
@@ -773,7 +908,8 @@ int pm_k_gather_kick_drift_slab(pm_plan *p, const float *phi, double a_val, doub
     auto kern = k_gather_kick_drift<true, true>;
     PM_LAUNCH(kern, (unsigned)((np + PM_GATHER_THREADS - 1) / PM_GATHER_THREADS), PM_GATHER_THREADS, 0, st, p->rpos[c], p->rvel[c], p->rid[c],
               p->order_sorted, p->rpos[o], p->rvel[o], p->rid[o], p->keys, np, p->rstride, p->rstride,
-              phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, (float *)nullptr, sl, (uint32_t *)nullptr, (const uint32_t *)nullptr);
+              phi, p->nc, k_kick, da, aa, pm_div_rcp(aa, da), f_a1, (float *)nullptr, sl, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+              (const float *)nullptr);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }

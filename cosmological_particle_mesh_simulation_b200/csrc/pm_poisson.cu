@@ -76,6 +76,74 @@ __global__ void __launch_bounds__(256) k_green_multiply(float2 *__restrict__ spe
     }
 }
 
+// ---- options: CIC-window deconvolution and spectral gradient (north_star (2)) -----------
+// The reference has neither: its potential is G(k) rho_k (src/potential.py:12-15) and its accelerations are
+// central differences of phi at the eight corners (src/integrate.py:84-91).  Both are options here, off by
+// default; with them on the solve runs the library transforms around ONE pass over the half spectrum that
+// applies Green's function, the constant and 1/W(k)^p together, and -- for the spectral gradient -- three
+// more passes that write 2 * (-i k_d) phi_k for one axis each into a second spectrum, transformed into the
+// plan's three force meshes.  W(k) = prod_i [sin(k_i/2) / (k_i/2)]^2 is the CIC assignment window: p = 1
+// undoes the deposit's smoothing, p = 2 the interpolation's as well.
+int pm_k_poisson_tables(pm_plan *p)
+{
+    const int nc = p->nc;
+    float *h = (float *)malloc(sizeof(float) * 2 * nc);
+    if (!h) return PM_ERR_NOMEM;
+    for (int i = 0; i < nc; ++i) {
+        const int fi = i <= (nc - 1) / 2 ? i : i - nc;                 // fftfreq numerator
+        const double k = 2.0 * M_PI * (double)fi / (double)nc;
+        const bool nyq = (nc % 2 == 0 && i == nc / 2);
+        double w = 1.0;
+        if (fi != 0) {
+            const double s = sin(0.5 * k) / (0.5 * k);
+            w = s * s;
+        }
+        h[i] = (float)pow(w, -(double)p->deconv);
+        h[nc + i] = nyq ? 0.0f : (float)k;                            // the derivative of the Nyquist mode is dropped
+    }
+    cudaError_t e = cudaMemcpy(p->dec_tab, h, sizeof(float) * nc, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(p->k_tab, h + nc, sizeof(float) * nc, cudaMemcpyHostToDevice);
+    free(h);
+    return (int)e;
+}
+
+__global__ void __launch_bounds__(256) k_green_multiply_dec(float2 *__restrict__ spec, const float *__restrict__ sin2,
+                                                            const float *__restrict__ dec, int nc, int nxh, double scale)
+{
+    const int rows = nc * nc;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int z = r / nc, y = r - z * nc;
+        const float sz = sin2[z], sy = sin2[y];
+        const double dzy = (double)dec[z] * (double)dec[y];
+        float2 *row = spec + (size_t)r * nxh;
+        for (int x = threadIdx.x; x < nxh; x += blockDim.x) {
+            const double g = scale * (double)pm_green(sz, sy, sin2[x]) * (dzy * (double)dec[x]);
+            float2 c = row[x];
+            c.x = (float)(g * (double)c.x);
+            c.y = (float)(g * (double)c.y);
+            row[x] = c;
+        }
+    }
+}
+
+// out = 2 * (-i k_axis) * in on the half spectrum [z][y][x <= nc/2]
+__global__ void __launch_bounds__(256) k_grad_spec(const float2 *__restrict__ in, float2 *__restrict__ out,
+                                                   const float *__restrict__ ktab, int nc, int nxh, int axis)
+{
+    const int rows = nc * nc;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int z = r / nc, y = r - z * nc;
+        const float2 *src = in + (size_t)r * nxh;
+        float2 *dst = out + (size_t)r * nxh;
+        const float kzy = axis == 2 ? ktab[z] : ktab[y];
+        for (int x = threadIdx.x; x < nxh; x += blockDim.x) {
+            const float k2 = 2.0f * (axis == 0 ? ktab[x] : kzy);
+            const float2 c = src[x];
+            dst[x] = make_float2(k2 * c.y, -k2 * c.x);                  // (a + ib)(-i k2) = k2 b - i k2 a
+        }
+    }
+}
+
 // ---- <rho>: the constant the forward transform subtracts (pm_internal.cuh, rho_mean_d) -----------
 __global__ void k_set_mean(float *dst, float v) { *dst = v; }
 
@@ -206,12 +274,13 @@ int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float 
                  cudaStream_t st)
 {
     const size_t cells = (size_t)p->nc * p->nc * p->nc;
-    if (p->fft_f64) return pm_k_poisson_f64(p, rho, a, omega_m0, phi, st);
+    if (p->fft_f64 && !(p->deconv || p->kgrad)) return pm_k_poisson_f64(p, rho, a, omega_m0, phi, st);
     {
         const int rc = pm_k_rho_mean(p, rho, cells, (double)cells, st);
         if (rc != PM_OK) return rc;
     }
-    if (p->own_fft) return pm_k_poisson_own(p, rho, a, omega_m0, phi, st);
+    if (p->own_fft && !(p->deconv || p->kgrad)) return pm_k_poisson_own(p, rho, a, omega_m0, phi, st);
+    if (!p->have_fft) return PM_ERR_UNSUPPORTED;      // (slab plans: options are refused at set time)
     const int nc = p->nc, nxh = nc / 2 + 1;
     PM_CUFFT(cufftSetStream(p->r2c, st));
     PM_CUFFT(cufftSetStream(p->c2r, st));
@@ -228,7 +297,18 @@ int pm_k_poisson(pm_plan *p, const float *rho, double a, double omega_m0, float 
     const double scale = -3 * omega_m0 / 8 / a / m;  // potential.py:15, plus the IFFT's 1/Nc^3
     int rows = nc * nc;
     int grid = rows < p->sm_count * 8 ? rows : p->sm_count * 8;
-    PM_LAUNCH(k_green_multiply, grid, 256, nxh * sizeof(float), st, p->spec, p->sin2, nc, nxh, scale);
+    if (p->deconv || p->kgrad) {
+        PM_LAUNCH(k_green_multiply_dec, grid, 256, 0, st, p->spec, p->sin2, p->dec_tab, nc, nxh, scale);
+        if (p->kgrad) {
+            // before the potential's own inverse transform: a multi-dimensional C2R may overwrite its input
+            for (int d = 0; d < 3; ++d) {
+                PM_LAUNCH(k_grad_spec, grid, 256, 0, st, (const float2 *)p->spec, p->spec2, (const float *)p->k_tab, nc, nxh, d);
+                PM_CUFFT(cufftExecC2R(p->c2r, reinterpret_cast<cufftComplex *>(p->spec2), p->fmesh + (size_t)d * cells));
+            }
+        }
+    } else {
+        PM_LAUNCH(k_green_multiply, grid, 256, nxh * sizeof(float), st, p->spec, p->sin2, nc, nxh, scale);
+    }
     PM_CHECK_LAUNCH();
     pm_prof_mark(p, PM_STAGE_GREEN + 1, st);
     PM_CUFFT(cufftExecC2R(p->c2r, reinterpret_cast<cufftComplex *>(p->spec), phi));

@@ -143,6 +143,14 @@ class ResidentParticles:
         return {"rows_per_block": rows_per_block, "cap": cap, "blocks": int(out[0]), "blocks_over_cap": int(out[1]),
                 "particles_over_cap": int(out[2]), "max_block_particles": int(out[3])}
 
+    def gather_items(self):
+        """(heavy, light, overflow) of the last tiled gather's work list (pm_plan_gather_items)."""
+        import ctypes
+        h, l, o = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int(0)
+        rt.check(rt.lib().pm_plan_gather_items(self.plan.handle, ctypes.byref(h), ctypes.byref(l), ctypes.byref(o)),
+                 "pm_plan_gather_items")
+        return h.value, l.value, o.value
+
     def order(self):
         """Original index of the particle in each storage slot (int32 CUDA tensor)."""
         ids = torch.empty(self.np, dtype=torch.int32, device=f"cuda:{self.device}")

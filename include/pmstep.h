@@ -84,6 +84,21 @@ PM_API int pm_plan_set_fft_backend(pm_plan *plan, int backend);
  * the reference's three NumPy expressions -- installs them here (sin2_h: n_cells floats, host memory);
  * G is then the reference's table bit for bit (correctly rounded float32 sums and reciprocal). */
 PM_API int pm_plan_set_sin2_table(pm_plan *plan, const float *sin2_h);
+/* Options of the Poisson solve that the reference does not have (BASELINE north_star (2)), both 0
+ * by default = the reference's scheme (src/potential.py:12-15, src/integrate.py:84-91) and the parity mode:
+ *   deconvolve       0, 1 or 2: phi_k is divided by W(k)^deconvolve, W(k) = prod_i [sin(k_i/2)/(k_i/2)]^2 the
+ *                    window of the cloud-in-cell assignment (1: the deposit's smoothing, 2: the force
+ *                    interpolation's too)
+ *   kspace_gradient  1: accelerations by spectral differentiation, -i k_d phi_k transformed into three force
+ *                    meshes that pm_gather_kick_drift / the step entry points interpolate with the CIC
+ *                    weights, instead of central differences of phi at the eight corners
+ * With an option on, the solve uses the library transforms around fused k-space kernels (one pass applies
+ * Green's function, the constants and the deconvolution; one pass per axis forms the gradient spectrum), the
+ * gather is the one-thread-per-particle kernel, and the step is not graph-replayed.  Single-GPU plans only
+ * (PM_ERR_UNSUPPORTED on slab plans); the force meshes (3 x 4 Nc^3 bytes + one spectrum) are allocated by this
+ * call, not during a step. */
+PM_API int pm_plan_set_poisson_options(pm_plan *plan, int deconvolve, int kspace_gradient);
+PM_API int pm_plan_poisson_options(const pm_plan *plan, int *deconvolve, int *kspace_gradient);
 PM_API int pm_plan_fft_backend(const pm_plan *plan);
 /* Hand-written FFT, meshes 256..1024: fuse != 0 runs the row pass and the y pass of each
  * direction in one persistent launch that keeps the intermediate plane in L2 (pm_fft.cu,
@@ -349,6 +364,11 @@ PM_API int pm_slab_export(pm_plan *plan, float *pos_d, float *vel_d, uint32_t *i
  * pm_plan_set_graph(plan, 0) (or PM_GRAPH=0) keeps it eager; pm_plan_graph_replays counts the replays. */
 PM_API int pm_plan_set_graph(pm_plan *plan, int on);
 PM_API int pm_plan_graph_replays(const pm_plan *plan);
+/* Work list of the last tiled gather (diagnostic; synchronises): the CTAs' shares are (row block, z chunk)
+ * columns filed whole ("light") or, where a column holds more than twice the mean, in pieces ("heavy",
+ * dispatched first) -- csrc/pm_particles.cu, k_gather_items.  overflow != 0 would mean the list outgrew its
+ * buffer (it cannot, by the bound it is sized with).  PM_GATHER_ITEMS=0 turns the list off. */
+PM_API int pm_plan_gather_items(pm_plan *plan, int64_t *heavy, int64_t *light, int *overflow);
 /* The two halves of pm_step_resident as separate calls, for callers that drive the reference's loop
  * body statement by statement (src/pmesh.py:60-61):
  *     rho = density(positions, mass)                          -> pm_resident_deposit

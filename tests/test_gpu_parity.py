@@ -634,6 +634,72 @@ def test_lazy_drop_in_equals_eager_drop_in_bit_for_bit(pm, golden_dir):
     assert rel_l2_periodic(out["lazy"][0], g["pos_5"], n) <= REL_L2 and rel_l2(out["lazy"][1], g["vel_5"]) <= REL_L2
 
 
+@pytest.mark.parametrize("n", [32, 20])
+def test_poisson_options_deconvolution_and_spectral_gradient(pm, n):
+    """pm_plan_set_poisson_options (BASELINE north_star (2); SURVEY Q6: options the reference does not have, off
+    in parity mode).  Off: the solve is the default one, bit for bit.  deconvolve = p: phi_k / W(k)^p against a
+    float64 NumPy evaluation.  kspace_gradient: the accelerations of the fused gather equal the CIC
+    interpolation of irfftn(-i k phi_k) evaluated in float64 (relative L2 <= 1e-5)."""
+    cfg = O.Config(N_CELLS=n, N_PARTS=n // 2, STEPS=100)
+    pm.set_config(cfg_ns(cfg))
+    rng = np.random.default_rng(7)
+    rho_h = (1.0 + 0.3 * rng.standard_normal((n, n, n))).astype(np.float32)
+    a = 0.3
+    fg = pm.fourier_grid()
+    G = O.fourier_grid(cfg).astype(np.float64)
+    G[0, 0, 0] = 0.0
+    k1 = 2 * np.pi * np.fft.fftfreq(n)
+    w1 = np.ones(n)
+    w1[1:] = (np.sin(k1[1:] / 2) / (k1[1:] / 2)) ** 2
+    W = w1[:, None, None] * w1[None, :, None] * w1[None, None, :]
+    rho_k = np.fft.fftn(rho_h.astype(np.float64))
+    try:
+        pm.release_plans()
+        assert pm.poisson_options() == (0, 0)
+        phi0 = pm.potential(dev(rho_h), fg, a).cpu().numpy()
+        # ---- deconvolution ----
+        for p in (1, 2):
+            pm.set_poisson_options(deconvolve=p)
+            phi = pm.potential(dev(rho_h), fg, a).cpu().numpy()
+            want = np.fft.ifftn(-3 * cfg.OMEGA_M0 / 8 / a * G * rho_k / W ** p).real
+            assert rel_l2(phi - phi.mean(dtype=np.float64), want - want.mean()) <= REL_L2, p
+        # ---- spectral gradient (with deconvolve = 2, the usual pairing) ----
+        pm.set_poisson_options(deconvolve=2, kspace_gradient=True)
+        phi = pm.potential(dev(rho_h), fg, a)             # also fills the plan's three force meshes
+        phi_k = -3 * cfg.OMEGA_M0 / 8 / a * G * rho_k / W ** 2
+        kk = k1.copy()
+        if n % 2 == 0:
+            kk[n // 2] = 0.0                              # the Nyquist mode has no derivative
+        F = [np.fft.ifftn(-1j * kk.reshape([-1 if ax == d else 1 for ax in range(3)]) * phi_k).real for d in (2, 1, 0)]  # x, y, z <-> axes 2, 1, 0
+        npart = 5000
+        pos_h = rng.uniform(0, n, (3, npart)).astype(np.float32)
+        vel_h = np.zeros((3, npart), np.float32)
+        acc = torch.zeros((3, npart), device="cuda")
+        pos, vel = dev(pos_h.copy()), dev(vel_h.copy())
+        da, fa1 = 0.0099, 1.3
+        from cosmological_particle_mesh_simulation_b200.integrate import _integrate_device
+        _integrate_device(pos, vel, a, fa1, da, phi, acc=acc)
+        c = np.floor(pos_h).astype(np.int64) % n
+        d = pos_h.astype(np.float64) - c
+        want_acc = np.zeros((3, npart))
+        for oz in (0, 1):
+            for oy in (0, 1):
+                for ox in (0, 1):
+                    wgt = (d[0] if ox else 1 - d[0]) * (d[1] if oy else 1 - d[1]) * (d[2] if oz else 1 - d[2])
+                    iz, iy, ix = (c[2] + oz) % n, (c[1] + oy) % n, (c[0] + ox) % n
+                    for k in range(3):
+                        want_acc[k] += wgt * F[k][iz, iy, ix]
+        got = acc.cpu().numpy()
+        assert rel_l2(got, want_acc) <= REL_L2
+        assert rel_l2(vel.cpu().numpy(), da * fa1 * want_acc) <= REL_L2           # the kick used them
+        # ---- and off again: the default solve, bit for bit ----
+        pm.set_poisson_options()
+        assert np.array_equal(pm.potential(dev(rho_h), fg, a).cpu().numpy(), phi0)
+    finally:
+        pm.set_poisson_options()
+        pm.release_plans()
+
+
 @pytest.mark.parametrize("n", [32, 64, 128])
 def test_device_power_spectrum_matches_estimator(pm, n):
     """pm_power_spectrum (forward half of the hand-written FFT + on-device binning) against the
@@ -890,8 +956,8 @@ def test_full_run_power_spectrum_64_on_128(pm):
     assert np.max(np.abs(p_gpu / p_cpu - 1.0)) <= 1e-3
 
 
-@pytest.mark.parametrize("n_cells,n_parts", [(128, 64), (256, 96)])
-def test_tiled_gather_equals_flat_gather_bit_for_bit(pm, n_cells, n_parts):
+@pytest.mark.parametrize("n_cells,n_parts,nblob", [(128, 64, 6000), (256, 96, 6000), (128, 64, 120000), (256, 96, 400000)])
+def test_tiled_gather_equals_flat_gather_bit_for_bit(pm, n_cells, n_parts, nblob):
     """pm_gather_tiled.cuh (phi staged through shared-memory slabs, particle inputs through cp.async
     rings) does the arithmetic of k_gather_kick_drift: positions, velocities and the mover counts
     the incremental sort consumes must agree bit for bit over several resident steps, including a
@@ -901,9 +967,10 @@ def test_tiled_gather_equals_flat_gather_bit_for_bit(pm, n_cells, n_parts):
     rt = pm._runtime
     pos_h, vel_h = O.lattice_ic(n_parts, n_cells, seed=5, vel_rms=0.3)
     rs = np.random.RandomState(3)
-    blob = rs.normal(n_cells / 2, 0.7, size=(3, 6000)).astype(np.float32) % n_cells
-    pos_h[:, :6000] = blob                      # > CAP particles in a few (z, y-block)s
-    pos_h[2, 6000:6100] = np.float32(n_cells)   # Q4: z == N_CELLS files under plane 0
+    blob = rs.normal(n_cells / 2, 0.7, size=(3, nblob)).astype(np.float32) % n_cells
+    pos_h[:, :nblob] = blob                     # > CAP particles in a few (z, y-block)s; the large blobs put tens of
+    #                                             thousands in ONE plane of a row block: heavy work items, cut into ranges
+    pos_h[2, nblob:nblob + 100] = np.float32(n_cells)   # Q4: z == N_CELLS files under plane 0
     out = {}
     for tiled in (0, 1):
         pm.release_plans()
@@ -911,9 +978,15 @@ def test_tiled_gather_equals_flat_gather_bit_for_bit(pm, n_cells, n_parts):
         st = pm.ResidentParticles(p, v)
         rt.check(rt.lib().pm_plan_set_gather_tiled(st.plan.handle, tiled), "tiled")
         a, da = 0.02, 0.0099
-        for _ in range(4):
+        for k in range(4):
             st.step(a, da)
             a += da
+            if tiled and k == 0:                    # (the blob flies apart within a few of these steps)
+                heavy, light, overflow = st.gather_items()
+                assert overflow == 0 and heavy + light > 0
+                if nblob > 100000:
+                    assert heavy > 8, (heavy, light)    # the work list really cut the blob's columns into pieces
+                # every particle in exactly one item <=> the results equal the flat kernel's (below)
         st.store(p, v)
         out[tiled] = (p.cpu().numpy(), v.cpu().numpy())
     pm.release_plans()
