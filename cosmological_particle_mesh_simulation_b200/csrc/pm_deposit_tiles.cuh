@@ -93,7 +93,11 @@ __device__ __forceinline__ float pm_fx_to_float(uint32_t lo, uint32_t hi, double
 // sign; or an unusual mass) the whole warp takes the general 64-bit route.
 // The entries are given as up to NR runs [rb[k], re[k]) of the sorted list, walked as ONE sequence: a
 // warp's batches stream through all of them with a single pipeline prologue and one ragged batch.
-template <int ZB, int YB, int NR>
+// NCT: the mesh width as a compile-time constant (0: read A.nc).  With the usual power-of-two meshes every row
+// offset, wrap test and tile-row product folds into immediates and shifts -- the runtime-nc version executed
+// 14 constant loads and ~60 integer multiply-adds per 32-particle batch on addressing alone (ncu source page,
+// profiles/r02_notes.md).
+template <int ZB, int YB, int NR, int NCT>
 __device__ __forceinline__ void pm_dep_accumulate(const DepositTileArgs &A, const uint32_t *rb, const uint32_t *re, int nruns,
                                                   int Z0, int y0, uint32_t *s_lo, uint32_t *s_hi)
 {
@@ -116,7 +120,7 @@ __device__ __forceinline__ void pm_dep_accumulate(const DepositTileArgs &A, cons
     };
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kDepThreads / 32;
-    const int nc = A.nc;
+    const int nc = NCT ? NCT : A.nc;
     const double magic = 6755399441055744.0;   // 1.5 * 2^52: low mantissa word = the integer part of the addend
     // two-deep software pipeline over a warp's batches: the permutation entry of batch b+2 and the position
     // of batch b+1 are in flight while batch b is computed (the order -> position chain of dependent loads
@@ -275,11 +279,11 @@ __device__ __forceinline__ void pm_dep_zero(uint32_t *s_lo, int words)
 }
 
 // Launch 1: one CTA per tile.
-template <int ZB, int YB>
+template <int ZB, int YB, int NCT>
 __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A)
 {
     extern __shared__ uint4 s_dep4[];
-    const int nc = A.nc, cells = ZB * YB * nc;
+    const int nc = NCT ? NCT : A.nc, cells = ZB * YB * nc;
     uint32_t *s_lo = reinterpret_cast<uint32_t *>(s_dep4), *s_hi = s_lo + cells;
     __shared__ uint32_t s_rb[2 * (ZB + 1)], s_re[2 * (ZB + 1)];
     __shared__ int s_mode;               // mode 0: accumulate here; 1: queued as work items
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A
     __syncthreads();
     if (s_mode == 1) return;                             // launches 2 and 3 produce this tile
 
-    pm_dep_accumulate<ZB, YB, NR>(A, s_rb, s_re, NR, Z0, y0, s_lo, s_hi);
+    pm_dep_accumulate<ZB, YB, NR, NCT>(A, s_rb, s_re, NR, Z0, y0, s_lo, s_hi);
     __syncthreads();
     // write-out: every cell of the tile once, 16-byte stores
     const int quads_row = nc / 4, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -388,11 +392,11 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A
 }
 
 // Launch 2: persistent CTAs drain the work-item queue of the heavy tiles.
-template <int ZB, int YB>
+template <int ZB, int YB, int NCT>
 __global__ void __launch_bounds__(kDepThreads) k_deposit_items(DepositTileArgs A)
 {
     extern __shared__ uint4 s_dep4[];
-    const int nc = A.nc, cells = ZB * YB * nc;
+    const int nc = NCT ? NCT : A.nc, cells = ZB * YB * nc;
     uint32_t *s_lo = reinterpret_cast<uint32_t *>(s_dep4), *s_hi = s_lo + cells;
     __shared__ uint32_t s_item;
     const uint32_t nitems = A.ctl[1];
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_items(DepositTileArgs A
         pm_dep_zero<ZB, YB>(s_lo, 2 * cells);
         __syncthreads();
         const uint32_t ib = it.beg, ie = it.beg + it.cnt;
-        pm_dep_accumulate<ZB, YB, 1>(A, &ib, &ie, 1, tz * ZB, ty * YB, s_lo, s_hi);
+        pm_dep_accumulate<ZB, YB, 1, NCT>(A, &ib, &ie, 1, tz * ZB, ty * YB, s_lo, s_hi);
         __syncthreads();
         unsigned long long *dst = A.scratch + (size_t)it.slot * cells;
         for (int c = threadIdx.x; c < cells; c += kDepThreads) {

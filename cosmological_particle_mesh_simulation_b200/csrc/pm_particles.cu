@@ -284,14 +284,14 @@ static int pm_launch_deposit_ry(pm_plan *p, const float *pos, int64_t stride, do
 
 #include "pm_deposit_tiles.cuh"
 
-template <int ZB, int YB>
+template <int ZB, int YB, int NCT>
 static int pm_launch_deposit_tiles_zy(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
                                       int nz_out, int slab, cudaStream_t st)
 {
     const int nc = p->nc;
     const size_t smem = (size_t)2 * ZB * YB * nc * sizeof(uint32_t);
-    auto k1 = k_deposit_tiles<ZB, YB>;
-    auto k2 = k_deposit_items<ZB, YB>;
+    auto k1 = k_deposit_tiles<ZB, YB, NCT>;
+    auto k2 = k_deposit_items<ZB, YB, NCT>;
     auto k3 = k_deposit_slots<ZB, YB>;
     PM_ONCE_PER_DEVICE_BEGIN(p->device)
         // the largest tile any mesh gives this instantiation (8192 cells), not this call's
@@ -334,9 +334,17 @@ static int pm_launch_deposit_tiles(pm_plan *p, const float *pos, int64_t stride,
 {
     const int nc = p->nc;
     if (nc % 16 || nc < 16) return PM_ERR_UNSUPPORTED;
-    if (nc <= 512) return pm_launch_deposit_tiles_zy<2, 8>(p, pos, stride, mass, rho, nz_out, slab, st);
-    if (nc <= 1024) return pm_launch_deposit_tiles_zy<2, 4>(p, pos, stride, mass, rho, nz_out, slab, st);
-    if (nc <= 2048) return pm_launch_deposit_tiles_zy<2, 2>(p, pos, stride, mass, rho, nz_out, slab, st);
+    switch (nc) {       // the usual meshes: width folded into the code (pm_deposit_tiles.cuh, NCT)
+    case 128: return pm_launch_deposit_tiles_zy<2, 8, 128>(p, pos, stride, mass, rho, nz_out, slab, st);
+    case 256: return pm_launch_deposit_tiles_zy<2, 8, 256>(p, pos, stride, mass, rho, nz_out, slab, st);
+    case 512: return pm_launch_deposit_tiles_zy<2, 8, 512>(p, pos, stride, mass, rho, nz_out, slab, st);
+    case 1024: return pm_launch_deposit_tiles_zy<2, 4, 1024>(p, pos, stride, mass, rho, nz_out, slab, st);
+    case 2048: return pm_launch_deposit_tiles_zy<2, 2, 2048>(p, pos, stride, mass, rho, nz_out, slab, st);
+    default: break;
+    }
+    if (nc <= 512) return pm_launch_deposit_tiles_zy<2, 8, 0>(p, pos, stride, mass, rho, nz_out, slab, st);
+    if (nc <= 1024) return pm_launch_deposit_tiles_zy<2, 4, 0>(p, pos, stride, mass, rho, nz_out, slab, st);
+    if (nc <= 2048) return pm_launch_deposit_tiles_zy<2, 2, 0>(p, pos, stride, mass, rho, nz_out, slab, st);
     return PM_ERR_UNSUPPORTED;
 }
 
