@@ -125,7 +125,7 @@ struct DeviceGuard {
 
 extern "C" {
 
-const char *pm_version(void) { return "pmstep 0.1 (sm_100a; cuFFT R2C/C2R + hand-written particle/Green kernels)"; }
+const char *pm_version(void) { return "pmstep 0.2 (sm_100a; hand-written sort, deposit, 5-pass real FFT with fused Green's function, gather; cuFFT only for non-power-of-two meshes and the diagnostic backends)"; }
 
 const char *pm_error_string(int code)
 {
