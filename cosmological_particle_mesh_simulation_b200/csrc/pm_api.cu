@@ -309,6 +309,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         return PM_ERR_CUFFT;
     }
     rc = pm_k_sin2_table(p);
+    if (rc == PM_OK && g.slab) rc = pm_peer_timeout_init();     // PM_PEER_TIMEOUT_MS (per device: a __device__ variable)
     {
         const char *be = getenv("PM_FFT_BACKEND");  // "cufft" forces the library path (A/B checks)
         p->own_fft = pm_fft_supported(n_cells) && (g.slab || !(be && (strcmp(be, "cufft") == 0 || strcmp(be, "f64") == 0)));

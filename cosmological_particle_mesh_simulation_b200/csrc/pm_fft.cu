@@ -1266,6 +1266,12 @@ struct PeerFlagPtrs {
     uint32_t *p[PM_PEER_MAX];
 };
 
+// How long a flag wait spins before it gives up, counts a timeout (reported by pm_slab_peer_timeouts and, with
+// the peer-memory migration, raised as an error by every rank in the same step) and lets the stream go on.
+// 10 s by default -- a peer whose host stalls (GC pause, synchronous snapshot I/O) must not turn into a
+// silently wrong step; PM_PEER_TIMEOUT_MS overrides it at plan creation (pm_peer_timeout_init).
+__device__ unsigned long long g_peer_timeout_ns = 10000000000ull;
+
 __global__ void k_peer_signal_impl(PeerFlagPtrs peers, int nranks, int rank, int slot, uint32_t epoch)
 {
     const int s = threadIdx.x;
@@ -1285,7 +1291,7 @@ __global__ void k_peer_wait_impl(uint32_t *flags, int nranks, int slot, uint32_t
         while ((int)(*w - epoch) < 0) {
             __nanosleep(100);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (now - t0 > 2000000000ull) {
+            if (now - t0 > g_peer_timeout_ns) {
                 atomicAdd(flags + (size_t)PM_PEER_SLOTS * PM_PEER_MAX, 1u);
                 break;
             }
@@ -1309,7 +1315,7 @@ __global__ void k_peer_wait_one(uint32_t *flags, int slot, int src, uint32_t epo
     while ((int)(*w - epoch) < 0) {
         __nanosleep(100);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (now - t0 > 2000000000ull) {
+        if (now - t0 > g_peer_timeout_ns) {
             atomicAdd(flags + (size_t)PM_PEER_SLOTS * PM_PEER_MAX, 1u);
             break;
         }
@@ -1451,6 +1457,16 @@ int pk_launch(pm_plan *p, const float *rho, int nbins, double *psum, double *pcn
 }
 
 }  // namespace
+
+int pm_peer_timeout_init()
+{
+    const char *e = getenv("PM_PEER_TIMEOUT_MS");
+    if (!e || !*e) return PM_OK;
+    const double ms = atof(e);
+    if (!(ms >= 1.0) || ms > 3.6e6) return PM_ERR_INVALID;
+    const unsigned long long ns = (unsigned long long)(ms * 1e6);
+    return (int)cudaMemcpyToSymbol(g_peer_timeout_ns, &ns, sizeof(ns));
+}
 
 bool pm_fft_supported(int nc)
 {

@@ -268,6 +268,7 @@ int pm_k_iota(uint32_t *out, int64_t n, cudaStream_t st);
 
 // pm_fft.cu
 bool pm_fft_supported(int nc);
+int pm_peer_timeout_init();
 int pm_k_fft_tables(pm_plan *p);
 int pm_k_sin2rev_install(pm_plan *p, const float *sin2_h);
 int pm_k_poisson_own(pm_plan *p, const float *rho, double a, double omega_m0, float *phi,

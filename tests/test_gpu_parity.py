@@ -634,6 +634,37 @@ def test_lazy_drop_in_equals_eager_drop_in_bit_for_bit(pm, golden_dir):
     assert rel_l2_periodic(out["lazy"][0], g["pos_5"], n) <= REL_L2 and rel_l2(out["lazy"][1], g["vel_5"]) <= REL_L2
 
 
+def test_plans_on_two_devices_in_one_process(pm):
+    """One process, two GPUs: the opt-ins for > 48 KB of dynamic shared memory (FFT passes, tile deposit, gather)
+    are per DEVICE; a process-wide "already set" flag would leave the second device without them and every
+    launch there would fail (round-1 advisor finding).  The same resident run on cuda:0 and cuda:1, bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg = types.SimpleNamespace(N_CELLS=128, N_PARTS=64, OMEGA_M0=0.31, OMEGA_K0=0.0,
+                                OMEGA_LAMBDA0=0.69, H0=0.68, A_INIT=0.01, A_END=1.0, STEPS=1000)
+    pm.set_config(cfg)
+    rng = np.random.default_rng(3)
+    npart = 64 ** 3
+    pos = rng.uniform(0, 128, (3, npart)).astype(np.float32)
+    vel = rng.normal(0, 0.05, (3, npart)).astype(np.float32)
+    sched = pm.loop_scale_factors(cfg)[:4]
+    out = []
+    for d in (0, 1):
+        p, v = torch.from_numpy(pos).to(f"cuda:{d}"), torch.from_numpy(vel).to(f"cuda:{d}")
+        st = pm.ResidentParticles(p, v)
+        rho = torch.zeros((128,) * 3, device=f"cuda:{d}")
+        for a, da in sched:
+            st.step(a, da, rho_out=rho)
+        st.store(p, v)
+        out.append((p.cpu().numpy(), v.cpu().numpy(), rho.cpu().numpy()))
+        st.close()
+        # the stateless entry points (shared cached plan of that device) as well
+        rho2 = pm.density(torch.from_numpy(pos).to(f"cuda:{d}"), 8.0)
+        assert rho2.device.index == d and np.isfinite(float(rho2.sum()))
+    for k in range(3):
+        assert np.array_equal(out[0][k], out[1][k])
+
+
 @pytest.mark.parametrize("n", [32, 20])
 def test_poisson_options_deconvolution_and_spectral_gradient(pm, n):
     """pm_plan_set_poisson_options (BASELINE north_star (2); SURVEY Q6: options the reference does not have, off
