@@ -94,7 +94,7 @@ int compute_layout(const Geometry &g, int64_t np, size_t fft_work, Layout *L)
     // gather work list: 2 per base chunk + the pieces of split chunks (pm_particles.cu, pm_gather_item_threshold)
     L->gat_cap = pm_gather_item_capacity(nc, (int64_t)npad);
     L->gat = align_up((size_t)L->gat_cap * 16) + kAlign;
-    L->total = L->gat + align_up((size_t)512 * 8192 * 8) /* dep_scratch */ + align_up(64 + 512 * 4) /* dep ctl + slot_tile */ +
+    L->total = L->gat + align_up((size_t)PM_DEP_MAX_SLOTS * 8192 * 8) /* dep_scratch */ + align_up(64 + 3 * PM_DEP_MAX_SLOTS * 4) /* dep ctl + slot tables */ +
                align_up((size_t)16384 * 16) /* dep_items */ + kAlign /* diag */ + align_up(1024 * sizeof(double) + 64) /* mean */ + L->fft_sync + L->keys + L->iota + L->keys_sorted + L->order_sorted + L->cub + L->row_start +
                L->mesh + L->mesh2 + L->spec + L->fft + 2 * L->sin2 + L->tw +
                2 * (L->rpos + L->rvel + L->rid) + 2 * L->tbuf + L->leave_cnt + L->leave_slot +
@@ -257,8 +257,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     p->inc_bcap = L.inc_bcap;
     p->fft_sync = (unsigned *)c;      c += L.fft_sync;
     p->diag = c;                      p->step_params_d = (PmStepParams *)(c + 256);  c += kAlign;
-    p->dep_scratch = (unsigned long long *)c;  c += align_up((size_t)512 * 8192 * 8);
-    p->dep_ctl = (uint32_t *)c;       p->dep_slot_tile = (uint32_t *)(c + 64);  c += align_up(64 + 512 * 4);
+    p->dep_scratch = (unsigned long long *)c;  c += align_up((size_t)PM_DEP_MAX_SLOTS * 8192 * 8);
+    p->dep_ctl = (uint32_t *)c;       p->dep_slot_tile = (uint32_t *)(c + 64 + PM_DEP_MAX_SLOTS * 4);  c += align_up(64 + 3 * PM_DEP_MAX_SLOTS * 4);
     p->dep_items = c;                 c += align_up((size_t)16384 * 16);
     p->mean_ws = (double *)c;         p->rho_mean_d = (float *)(c + 1024 * sizeof(double));
     c += align_up(1024 * sizeof(double) + 64);
@@ -318,7 +318,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     if (rc == PM_OK && pm_fft_supported(n_cells)) rc = pm_k_fft_tables(p);
     if (rc == PM_OK) rc = (int)cudaMemset(p->fft_sync, 0, sizeof(unsigned));
     if (rc == PM_OK) rc = (int)cudaMemset(p->sort_ctl, 0, 256);
-    if (rc == PM_OK) rc = (int)cudaMemset(p->dep_scratch, 0, (size_t)512 * 8192 * 8);   // all-zero between steps (k_deposit_slots)
+    if (rc == PM_OK) rc = (int)cudaMemset(p->dep_scratch, 0, (size_t)PM_DEP_MAX_SLOTS * 8192 * 8);   // all-zero between steps (k_deposit_items zeroes what it converts)
     if (rc == PM_OK && p->peer_flags)
         rc = (int)cudaMemset(p->peer_flags, 0, (size_t)(PM_PEER_SLOTS + 1) * PM_PEER_MAX * 4);
     if (rc == PM_OK && p->mig_matrix) rc = (int)cudaMemset(p->mig_matrix, 0, (size_t)PM_PEER_MAX * PM_MIG_ROW * 4);

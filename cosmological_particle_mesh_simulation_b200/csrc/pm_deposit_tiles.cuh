@@ -24,14 +24,14 @@
 // processed by its own CTA; the CTA cuts the runs into work items of at most kDepItem particles and
 // queues them.  A second, persistent launch drains the queue -- any CTA takes any item, accumulates it
 // in shared memory and adds the non-zero cells to the tile's 64-bit scratch slot in global memory
-// (REDG.ADD.64, exact again) -- and a third converts the scratch slots to float32 mesh rows and
-// zeroes them for the next step.  With a near-uniform load launches two and three find empty queues.
+// (REDG.ADD.64, exact again); the CTA that finishes a tile's last item converts its scratch slot to float32
+// mesh rows and zeroes it for the next step.  With a near-uniform load the second launch finds an empty queue.
 #pragma once
 
 constexpr uint32_t kDepHeavy = 8192;    // source particles above which a tile is split into work items
 constexpr uint32_t kDepItem = 8192;     // particles per work item
 constexpr int kDepThreads = 384;     // 12 warps share a tile: three CTAs of 64 KB (and 48 registers) per SM = 36 warps
-constexpr int kDepMaxSlots = 512;       // heavy tiles per step that get a scratch slot (the rest run unsplit)
+constexpr int kDepMaxSlots = PM_DEP_MAX_SLOTS;   // heavy tiles per step that get a scratch slot (the rest run unsplit)
 constexpr int kDepMaxItems = 16384;
 
 struct DepItem {
@@ -51,6 +51,8 @@ struct DepositTileArgs {
     unsigned long long *scratch;     // [kDepMaxSlots][ZB*YB*nc] int64 sums of the heavy tiles (all zero between steps)
     uint32_t *ctl;                   // [0] slots used, [1] items queued, [2] items taken, [3] tiles that ran unsplit for lack of slots
     uint32_t *slot_tile;             // [kDepMaxSlots] tile of each slot
+    uint32_t *slot_items;            // [kDepMaxSlots] work items queued for it
+    uint32_t *slot_done;             // [kDepMaxSlots] work items finished (zeroed with ctl); the CTA that finishes the last one converts the slot
     DepItem *items;                  // [kDepMaxItems]
 };
 
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A
             }
             if (ok) {
                 A.slot_tile[slot] = tile;
+                A.slot_items[slot] = nitems;
                 uint32_t w = first;
                 for (int k = 0; k < NR; ++k)
                     for (uint32_t b = s_rb[k]; b < s_re[k]; b += kDepItem) {
@@ -418,32 +421,39 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_items(DepositTileArgs A
             const uint32_t lo = s_lo[c], hi = s_hi[c];
             if (lo | hi) atomicAdd(dst + c, ((unsigned long long)hi << 32) | lo);
         }
-    }
-}
-
-// Launch 3: scratch slots -> mesh rows (and back to zero for the next step).  blockIdx.x = slot,
-// blockIdx.y = quarter of the tile.
-template <int ZB, int YB>
-__global__ void __launch_bounds__(kDepThreads) k_deposit_slots(DepositTileArgs A)
-{
-    const int nc = A.nc, cells = ZB * YB * nc;
-    const uint32_t nslots = A.ctl[0] < (uint32_t)kDepMaxSlots ? A.ctl[0] : (uint32_t)kDepMaxSlots;
-    const uint32_t s = blockIdx.x;
-    if (s >= nslots) return;
-    const uint32_t tile = A.slot_tile[s];
-    const int tz = tile / A.tiles_y, ty = tile - tz * A.tiles_y;
-    const int Z0 = tz * ZB, y0 = ty * YB;
-    unsigned long long *src = A.scratch + (size_t)s * cells;
-    const int rows_per = (ZB * YB + gridDim.y - 1) / gridDim.y;
-    const int r0 = blockIdx.y * rows_per, r1 = min(r0 + rows_per, ZB * YB);
-    for (int row = r0; row < r1; ++row) {
-        const int pz_ = row / YB, py_ = row % YB;
-        const bool out = Z0 + pz_ < A.nz_out;
-        float *dst = A.rho + ((size_t)(Z0 + pz_) * nc + (y0 + py_)) * nc;
-        for (int x = threadIdx.x; x < nc; x += kDepThreads) {
-            const unsigned long long v = src[(size_t)row * nc + x];
-            src[(size_t)row * nc + x] = 0ull;
-            if (out) dst[x] = pm_fx_to_float((uint32_t)v, (uint32_t)(v >> 32), A.inv_scale);
+        // The CTA that finishes a slot's LAST item turns the 64-bit sums into the tile's float32 mesh rows and
+        // zeroes the slot for the next step (a separate pass over all slots did this before: 146 us on the
+        // z = 0 snapshot).  Every CTA fences its adds before it counts itself done.
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (atomicAdd(A.slot_done + it.slot, 1u) + 1u == A.slot_items[it.slot]) ? 1u : 0u;
+        __syncthreads();
+        if (s_item) {
+            __threadfence();
+            const int Z0 = tz * ZB, y0 = ty * YB;
+            // eight independent loads in flight per thread (one load -> store chain per iteration made this
+            // latency-bound: ~30 us per slot)
+            constexpr int U = 8;
+            for (int c0 = threadIdx.x; c0 < cells; c0 += U * kDepThreads) {
+                unsigned long long v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u * kDepThreads;
+                    v[u] = c < cells ? __ldcg(dst + c) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u * kDepThreads;
+                    if (c < cells) {
+                        const int row = c / nc, x = c - row * nc;
+                        const int pz_ = row / YB, py_ = row % YB;
+                        dst[c] = 0ull;
+                        if (Z0 + pz_ < A.nz_out)
+                            A.rho[((size_t)(Z0 + pz_) * nc + (y0 + py_)) * nc + x] =
+                                pm_fx_to_float((uint32_t)v[u], (uint32_t)(v[u] >> 32), A.inv_scale);
+                    }
+                }
+            }
         }
     }
 }

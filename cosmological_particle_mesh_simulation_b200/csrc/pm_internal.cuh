@@ -71,6 +71,7 @@ struct PmStepParams {
 };
 
 #define PM_HOST_CHUNKS 4
+#define PM_DEP_MAX_SLOTS 1024     // crowded deposit tiles per step that get a scratch slot (pm_deposit_tiles.cuh)
 struct pm_plan {
     int nc;           // N_CELLS
     int64_t np_cap;   // particle capacity
@@ -191,7 +192,7 @@ struct pm_plan {
     // tile deposit (pm_deposit_tiles.cuh): scratch slots, queue and counters of the heavy tiles
     bool deposit_tiles;     // false: k_deposit_rows (PM_DEPOSIT=rows, meshes the tile kernel does not take)
     unsigned long long *dep_scratch;
-    uint32_t *dep_ctl, *dep_slot_tile;
+    uint32_t *dep_ctl, *dep_slot_tile;   // ctl: 16 words, then slot_done[S] (zeroed with ctl every step), slot_tile[S], slot_items[S]
     void *dep_items;
     // work list of the tiled gather (pm_gather_ws.cuh, k_gather_items): heavy items from the front, light from the back
     void *gat_items;

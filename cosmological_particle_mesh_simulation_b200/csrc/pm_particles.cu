@@ -292,7 +292,6 @@ static int pm_launch_deposit_tiles_zy(pm_plan *p, const float *pos, int64_t stri
     const size_t smem = (size_t)2 * ZB * YB * nc * sizeof(uint32_t);
     auto k1 = k_deposit_tiles<ZB, YB, NCT>;
     auto k2 = k_deposit_items<ZB, YB, NCT>;
-    auto k3 = k_deposit_slots<ZB, YB>;
     PM_ONCE_PER_DEVICE_BEGIN(p->device)
         // the largest tile any mesh gives this instantiation (8192 cells), not this call's
         PM_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(uint32_t)));
@@ -318,12 +317,12 @@ static int pm_launch_deposit_tiles_zy(pm_plan *p, const float *pos, int64_t stri
     }
     A.smass = ldexp(mass, k); A.inv_scale = ldexp(1.0, -k);
     A.fast_ok = (A.smass >= 0.0 && A.smass < 4294967296.0) ? 1 : 0;
-    A.scratch = p->dep_scratch; A.ctl = p->dep_ctl; A.slot_tile = p->dep_slot_tile; A.items = (DepItem *)p->dep_items;
-    PM_CUDA(cudaMemsetAsync(p->dep_ctl, 0, 4 * sizeof(uint32_t), st));
+    A.scratch = p->dep_scratch; A.ctl = p->dep_ctl; A.items = (DepItem *)p->dep_items;
+    A.slot_done = p->dep_ctl + 16; A.slot_tile = p->dep_slot_tile; A.slot_items = p->dep_slot_tile + PM_DEP_MAX_SLOTS;
+    PM_CUDA(cudaMemsetAsync(p->dep_ctl, 0, (16 + PM_DEP_MAX_SLOTS) * sizeof(uint32_t), st));   // counters + slot_done
     dim3 grid(A.tiles_y, A.tiles_z);
     PM_LAUNCH(k1, grid, kDepThreads, smem, st, A);
     PM_LAUNCH(k2, p->sm_count * 3, kDepThreads, smem, st, A);
-    PM_LAUNCH(k3, dim3(kDepMaxSlots, 4), kDepThreads, 0, st, A);
     PM_CHECK_LAUNCH();
     return PM_OK;
 }
