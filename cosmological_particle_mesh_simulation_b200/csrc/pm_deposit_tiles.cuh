@@ -28,7 +28,8 @@
 // mesh rows and zeroes it for the next step.  With a near-uniform load the second launch finds an empty queue.
 #pragma once
 
-constexpr uint32_t kDepHeavy = 8192;    // source particles above which a tile is split into work items
+constexpr uint32_t kDepHeavy = 16384;   // source particles above which a tile is split into work items (sweep on the z = 0
+                                        // snapshot, profiles/r02_notes.md: 8192 -> 0.70 ms, 16384 -> 0.63, 32768 -> 0.69, never -> 0.84)
 constexpr uint32_t kDepItem = 8192;     // particles per work item
 constexpr int kDepThreads = 384;     // 12 warps share a tile: three CTAs of 64 KB (and 48 registers) per SM = 36 warps
 constexpr int kDepMaxSlots = PM_DEP_MAX_SLOTS;   // heavy tiles per step that get a scratch slot (the rest run unsplit)
@@ -54,6 +55,7 @@ struct DepositTileArgs {
     uint32_t *slot_items;            // [kDepMaxSlots] work items queued for it
     uint32_t *slot_done;             // [kDepMaxSlots] work items finished (zeroed with ctl); the CTA that finishes the last one converts the slot
     DepItem *items;                  // [kDepMaxItems]
+    uint32_t heavy, item;            // thresholds (kDepHeavy, kDepItem unless PM_DEP_HEAVY / PM_DEP_ITEM say otherwise)
 };
 
 // (hi:lo) += v, v a signed 64-bit fixed-point value.  Exact whatever the interleaving: the low words
@@ -331,10 +333,10 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A
         uint32_t total = 0, nitems = 0;
         for (int k = 0; k < NR; ++k) {
             total += s_re[k] - s_rb[k];
-            nitems += (s_re[k] - s_rb[k] + kDepItem - 1) / kDepItem;
+            nitems += (s_re[k] - s_rb[k] + A.item - 1) / A.item;
         }
         int mode = 0;
-        if (total > kDepHeavy && A.scratch) {
+        if (total > A.heavy && A.scratch) {
             const uint32_t slot = atomicAdd(A.ctl + 0, 1u);
             uint32_t first = 0;
             bool ok = slot < (uint32_t)kDepMaxSlots;
@@ -348,10 +350,10 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A
                 A.slot_items[slot] = nitems;
                 uint32_t w = first;
                 for (int k = 0; k < NR; ++k)
-                    for (uint32_t b = s_rb[k]; b < s_re[k]; b += kDepItem) {
+                    for (uint32_t b = s_rb[k]; b < s_re[k]; b += A.item) {
                         DepItem it;
                         it.slot = slot; it.tile = tile; it.beg = b;
-                        it.cnt = s_re[k] - b < kDepItem ? s_re[k] - b : kDepItem;
+                        it.cnt = s_re[k] - b < A.item ? s_re[k] - b : A.item;
                         A.items[w++] = it;
                     }
                 mode = 1;

@@ -318,6 +318,12 @@ static int pm_launch_deposit_tiles_zy(pm_plan *p, const float *pos, int64_t stri
     A.smass = ldexp(mass, k); A.inv_scale = ldexp(1.0, -k);
     A.fast_ok = (A.smass >= 0.0 && A.smass < 4294967296.0) ? 1 : 0;
     A.scratch = p->dep_scratch; A.ctl = p->dep_ctl; A.items = (DepItem *)p->dep_items;
+    {
+        static const uint32_t heavy = getenv("PM_DEP_HEAVY") ? (uint32_t)atoi(getenv("PM_DEP_HEAVY")) : kDepHeavy;
+        static const uint32_t item = getenv("PM_DEP_ITEM") ? (uint32_t)atoi(getenv("PM_DEP_ITEM")) : kDepItem;
+        A.heavy = heavy < 256 ? 256 : heavy;
+        A.item = item < 256 ? 256 : item;
+    }
     A.slot_done = p->dep_ctl + 16; A.slot_tile = p->dep_slot_tile; A.slot_items = p->dep_slot_tile + PM_DEP_MAX_SLOTS;
     PM_CUDA(cudaMemsetAsync(p->dep_ctl, 0, (16 + PM_DEP_MAX_SLOTS) * sizeof(uint32_t), st));   // counters + slot_done
     dim3 grid(A.tiles_y, A.tiles_z);
