@@ -21,8 +21,8 @@
 //     rounded to 2^-24, rounded ONCE to float32; the reference rounds every partial sum).
 //   * every mesh cell is written exactly once, zeros included (no memset pass).
 // Skew (BASELINE configs[4]): a tile whose source runs hold more than kDepHeavy particles is not
-// processed by its own CTA; the CTA cuts the runs into work items of at most kDepItem particles and
-// queues them.  A second, persistent launch drains the queue -- any CTA takes any item, accumulates it
+// processed by its own CTA; the CTA cuts the concatenated runs into work items of at most kDepItem particles
+// and queues them.  A second, persistent launch drains the queue -- any CTA takes any item, accumulates it
 // in shared memory and adds the non-zero cells to the tile's 64-bit scratch slot in global memory
 // (REDG.ADD.64, exact again); the CTA that finishes a tile's last item converts its scratch slot to float32
 // mesh rows and zeroes it for the next step.  With a near-uniform load the second launch finds an empty queue.
@@ -103,7 +103,8 @@ __device__ __forceinline__ float pm_fx_to_float(uint32_t lo, uint32_t hi, double
 // profiles/r02_notes.md).
 template <int ZB, int YB, int NR, int NCT>
 __device__ __forceinline__ void pm_dep_accumulate(const DepositTileArgs &A, const uint32_t *rb, const uint32_t *re, int nruns,
-                                                  int Z0, int y0, uint32_t *s_lo, uint32_t *s_hi)
+                                                  int Z0, int y0, uint32_t *s_lo, uint32_t *s_hi,
+                                                  uint32_t vbeg = 0u, uint32_t vcnt = 0xffffffffu)
 {
     // cumulative run lengths in registers; virtual index v -> sorted-list index
     uint32_t cum[NR + 1], rbeg[NR];
@@ -114,7 +115,10 @@ __device__ __forceinline__ void pm_dep_accumulate(const DepositTileArgs &A, cons
         rbeg[k] = k < nruns ? rb[k] : 0u;
         cum[k + 1] = cum[k] + len;
     }
-    const uint32_t beg = 0, end = cum[NR];
+    // [vbeg, vbeg + vcnt) of the concatenated runs: the whole sequence for a tile's own CTA, a slice of it for a
+    // work item of a crowded tile
+    const uint32_t beg = vbeg < cum[NR] ? vbeg : cum[NR];
+    const uint32_t end = vcnt < cum[NR] - beg ? beg + vcnt : cum[NR];
     auto list_index = [&](uint32_t v) -> uint32_t {
         uint32_t j = rbeg[0] + v;
 #pragma unroll
@@ -333,8 +337,8 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A
         uint32_t total = 0, nitems = 0;
         for (int k = 0; k < NR; ++k) {
             total += s_re[k] - s_rb[k];
-            nitems += (s_re[k] - s_rb[k] + A.item - 1) / A.item;
         }
+        nitems = (total + A.item - 1) / A.item;             // slices of the concatenated runs, not of each run
         int mode = 0;
         if (total > A.heavy && A.scratch) {
             const uint32_t slot = atomicAdd(A.ctl + 0, 1u);
@@ -349,13 +353,12 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_tiles(DepositTileArgs A
                 A.slot_tile[slot] = tile;
                 A.slot_items[slot] = nitems;
                 uint32_t w = first;
-                for (int k = 0; k < NR; ++k)
-                    for (uint32_t b = s_rb[k]; b < s_re[k]; b += A.item) {
-                        DepItem it;
-                        it.slot = slot; it.tile = tile; it.beg = b;
-                        it.cnt = s_re[k] - b < A.item ? s_re[k] - b : A.item;
-                        A.items[w++] = it;
-                    }
+                for (uint32_t b = 0; b < total; b += A.item) {
+                    DepItem it;
+                    it.slot = slot; it.tile = tile; it.beg = b;          // virtual index into the tile's runs
+                    it.cnt = total - b < A.item ? total - b : A.item;
+                    A.items[w++] = it;
+                }
                 mode = 1;
             } else {
                 atomicAdd(A.ctl + 3, 1u);                // statistics: ran unsplit
@@ -415,8 +418,11 @@ __global__ void __launch_bounds__(kDepThreads) k_deposit_items(DepositTileArgs A
         const int tz = it.tile / A.tiles_y, ty = it.tile - tz * A.tiles_y;
         pm_dep_zero<ZB, YB>(s_lo, 2 * cells);
         __syncthreads();
-        const uint32_t ib = it.beg, ie = it.beg + it.cnt;
-        pm_dep_accumulate<ZB, YB, 1, NCT>(A, &ib, &ie, 1, tz * ZB, ty * YB, s_lo, s_hi);
+        {
+            uint32_t rb[2 * (ZB + 1)], re[2 * (ZB + 1)];
+            const int nr = pm_dep_runs<ZB, YB>(A, tz * ZB, ty * YB, rb, re);     // the order the tile's own CTA queued them in
+            pm_dep_accumulate<ZB, YB, 2 * (ZB + 1), NCT>(A, rb, re, nr, tz * ZB, ty * YB, s_lo, s_hi, it.beg, it.cnt);
+        }
         __syncthreads();
         unsigned long long *dst = A.scratch + (size_t)it.slot * cells;
         for (int c = threadIdx.x; c < cells; c += kDepThreads) {

@@ -663,7 +663,8 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 static uint32_t pm_gather_item_threshold(int nc, int64_t np, int zc0)
 {
     const int64_t chunks = (int64_t)(nc / PM_GT_YB) * (nc / zc0);
-    const int64_t t = chunks > 0 ? 2 * (np / chunks) : np;
+    static const double factor = getenv("PM_GATHER_T_FACTOR") ? atof(getenv("PM_GATHER_T_FACTOR")) : 2.0;
+    const int64_t t = chunks > 0 ? (int64_t)((factor < 1.0 ? 1.0 : factor) * (double)(np / chunks)) : np;
     return (uint32_t)(t < 4096 ? 4096 : (t > 0x7fffffff ? 0x7fffffff : t));
 }
 
