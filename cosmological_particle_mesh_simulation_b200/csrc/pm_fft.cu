@@ -1107,9 +1107,24 @@ ColArgs slab_args(pm_plan *p)
     return ca;
 }
 
+// Row passes of a slab: the two-stage register-resident kernels (pm_fft2.cuh) where they exist (256..1024
+// points; same input, output layout and packing of the Nyquist term as k_fft_rows: natural kx), else the
+// radix-8 kernels.  At 1024 points the former stream at 5 TB/s, the latter at 2.7.
 template <int N>
 int slab_rows_fwd(pm_plan *p, const float *rho, cudaStream_t st)
 {
+    if constexpr (kHasV2<N>) {
+        if (p->fft_v2) {
+            constexpr int RT = kRowsPT2<N>;
+            const size_t smem2 = ((size_t)N + (size_t)RT * RowFac<N>::RA * (RowFac<N>::RB + 1)) * sizeof(float2);
+            auto rows2 = k_fft2_rows<N, true>;
+            PM_CUDA(cudaFuncSetAttribute(rows2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PM_LAUNCH(rows2, p->nzl * N / RT, kThr2, smem2, st, reinterpret_cast<const float2 *>(rho), p->spec,
+                      (const float2 *)p->tw, (const float *)p->rho_mean_d);
+            PM_CHECK_LAUNCH();
+            return PM_OK;
+        }
+    }
     const size_t smem_rows = ((size_t)(N / 2) * kPitch + N) * sizeof(float2);
     auto rows_fwd = k_fft_rows<N, true>;
     PM_CUDA(cudaFuncSetAttribute(rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
@@ -1189,6 +1204,18 @@ int slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main_c, const
 template <int N>
 int slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
 {
+    if constexpr (kHasV2<N>) {
+        if (p->fft_v2) {
+            constexpr int RT = kRowsPT2<N>;
+            const size_t smem2 = ((size_t)N + (size_t)RT * RowFac<N>::RA * (RowFac<N>::RB + 1)) * sizeof(float2);
+            auto rows2 = k_fft2_rows<N, false>;
+            PM_CUDA(cudaFuncSetAttribute(rows2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PM_LAUNCH(rows2, p->nzl * N / RT, kThr2, smem2, st, reinterpret_cast<const float2 *>(p->spec),
+                      reinterpret_cast<float2 *>(phi), (const float2 *)p->tw, (const float *)nullptr);
+            PM_CHECK_LAUNCH();
+            return PM_OK;
+        }
+    }
     const size_t smem_rows = ((size_t)(N / 2) * kPitch + N) * sizeof(float2);
     auto rows_inv = k_fft_rows<N, false>;
     PM_CUDA(cudaFuncSetAttribute(rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));

@@ -1,9 +1,13 @@
 """potential(density, fgrid, a) -- FFT Poisson solve (reference: src/potential.py:7-29).
 
-B200 path: pm_poisson = cuFFT R2C -> one fused pass over the half spectrum applying
--3*Omega_m/(8a) * G(k) / Nc^3 with the DC mode zeroed -> cuFFT C2R, all float32
-(csrc/pm_poisson.cu).  The reference transforms the real density as complex128 c2c; the results
-agree to ~1e-6 relative L2 (tests/test_gpu_parity.py)."""
+B200 path: pm_poisson.  Power-of-two meshes (32..2048): the hand-written five-pass real transform of
+csrc/pm_fft*.cu(h) -- rows and y forward, ONE fused z pass (forward z, times -3*Omega_m/(8a) * G(k) / Nc^3
+with the DC mode zeroed, inverse z), y and rows inverse -- all float32, the density mean subtracted on the
+way in.  Other mesh sizes, and the deconvolution / spectral-gradient options: cuFFT R2C/C2R around one
+fused pass over the half spectrum (csrc/pm_poisson.cu).  G(k) is the reference's table bit for bit
+(_runtime.reference_sin2_table).  The reference transforms the real density as complex128 c2c; the
+results agree to ~1e-6 relative L2 (tests/test_gpu_parity.py); `pm_plan_set_fft_backend(plan, 2)`
+switches to float64 transforms for diagnosis."""
 try:
     from . import _runtime as rt
     from .fourier_utils import FourierGrid
