@@ -92,7 +92,11 @@ struct Smem {
 }  // namespace pmws
 
 // CW consumer warps + 1 producer warp.  Grid: (NC / YB, NC / zc), zc <= 32 planes per CTA.
-template <int NC, int YB, int CW, int CAP, int R, int S, int MINB>
+// PP: particles per consumer lane and batch.  PP = 2 runs two particles' dependent chains (shared-memory phi
+// reads -> float32 differences -> float64 kick and drift) side by side in one thread, phase by phase, so that
+// the instruction scheduler can interleave them: the kernel is bound by latency at ~18 warps per SM, not by
+// issue slots (43 %) or DRAM (46 %).
+template <int NC, int YB, int CW, int CAP, int R, int S, int MINB, int PP = 1>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_gather_ws(GatherTiledArgs A, unsigned *err)
 {
     pm_gather_step_params(A);
@@ -315,6 +319,84 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_gather_ws(GatherTiledAr
         }
     };
 
+    // PP particles of one lane, phase by phase (same arithmetic and rounding points as `update`)
+    auto update_n = [&](int s0, uint32_t pbase, const uint32_t (&ii)[PP], const bool (&ok)[PP], const float *sp) {
+        float x[PP], y[PP], z[PP], vx[PP], vy[PP], vz[PP], sx[PP], sy[PP], sz[PP];
+        uint32_t id[PP], kold[PP];
+#pragma unroll
+        for (int j = 0; j < PP; ++j) {
+            const uint32_t i = ok[j] ? ii[j] : 0u;
+            x[j] = ok[j] ? sp[i] : 0.f; y[j] = ok[j] ? sp[CAP + i] : 0.f; z[j] = ok[j] ? sp[2 * CAP + i] : 0.f;
+            vx[j] = sp[3 * CAP + i]; vy[j] = sp[4 * CAP + i]; vz[j] = sp[5 * CAP + i];
+            id[j] = __float_as_uint(sp[6 * CAP + i]);
+        }
+#pragma unroll
+        for (int j = 0; j < PP; ++j) {
+            const int xc = pm_cell(x[j], NC), yc = pm_cell(y[j], NC), zcell = pm_cell(z[j], NC);
+            kold[j] = ((uint32_t)zcell * NC + yc) * NC + xc;
+            const double d_x = (double)x[j] - (double)xc, d_y = (double)y[j] - (double)yc, d_z = (double)z[j] - (double)zcell;
+            const double t_x = 1.0 - d_x, t_y = 1.0 - d_y, t_z = 1.0 - d_z;
+            float t[8];
+            t[0] = (float)__dmul_rn(__dmul_rn(t_x, t_y), t_z);
+            t[1] = (float)__dmul_rn(__dmul_rn(d_x, t_y), t_z);
+            t[2] = (float)__dmul_rn(__dmul_rn(t_x, d_y), t_z);
+            t[3] = (float)__dmul_rn(__dmul_rn(t_x, t_y), d_z);
+            t[4] = (float)__dmul_rn(__dmul_rn(d_x, d_y), t_z);
+            t[5] = (float)__dmul_rn(__dmul_rn(d_x, t_y), d_z);
+            t[6] = (float)__dmul_rn(__dmul_rn(t_x, d_y), d_z);
+            t[7] = (float)__dmul_rn(__dmul_rn(d_x, d_y), d_z);
+            int xo[4];
+            {
+                const int a1 = xc + 1 == NC ? 0 : xc + 1;
+                xo[0] = xc == 0 ? NC - 1 : xc - 1; xo[1] = xc; xo[2] = a1; xo[3] = a1 + 1 == NC ? 0 : a1 + 1;
+            }
+            int ry = yc - y0;
+            ry = ry < 0 ? 0 : (ry > YB - 1 ? YB - 1 : ry);
+            const float *row0 = ring + ry * NC;
+            float v[4][4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                int slot = s0 + a;
+                slot = slot >= R ? slot - R : slot;
+                const float *pl = row0 + slot * SLAB;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float *pc = pl + xo[c];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int outer = (a == 0 || a == 3) + (b == 0 || b == 3) + (c == 0 || c == 3);
+                        v[a][b][c] = (outer <= 1) ? pc[b * NC] : 0.0f;
+                    }
+                }
+            }
+            sx[j] = pm_gp<0>(v, t); sy[j] = pm_gp<1>(v, t); sz[j] = pm_gp<2>(v, t);
+        }
+#pragma unroll
+        for (int j = 0; j < PP; ++j) {
+            pm_push(x[j], vx[j], sx[j], A.k_kick, A.da, A.aa, A.raa, A.f_a1, NC, nullptr);
+            pm_push(y[j], vy[j], sy[j], A.k_kick, A.da, A.aa, A.raa, A.f_a1, NC, nullptr);
+            pm_push(z[j], vz[j], sz[j], A.k_kick, A.da, A.aa, A.raa, A.f_a1, NC, nullptr);
+        }
+#pragma unroll
+        for (int j = 0; j < PP; ++j) {
+            if (ok[j]) {
+                const uint32_t p = pbase + ii[j];
+                A.pos_out[p] = x[j]; A.pos_out[A.sout + p] = y[j]; A.pos_out[2 * A.sout + p] = z[j];
+                A.vel_out[p] = vx[j]; A.vel_out[A.sout + p] = vy[j]; A.vel_out[2 * A.sout + p] = vz[j];
+                A.id_out[p] = id[j];
+                const uint32_t knew = pm_key(x[j], y[j], z[j], NC, 0, NC);
+                A.keys_out[p] = knew;
+                if (A.mover_cnt) {
+                    const unsigned act = __activemask();
+                    const uint32_t tile = p / PM_SORT_TILE;
+                    const unsigned same = __match_any_sync(act, tile);
+                    const unsigned mv = __ballot_sync(act, knew != kold[j]) & same;
+                    if (mv && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(A.mover_cnt + tile, __popc(mv));
+                }
+            }
+        }
+    };
+
     int s = 0;
     for (int k = 0; k < zc; ++k) {
         // phi planes pi = k .. k+3 (k = 0: all four; afterwards only the newest)
@@ -328,13 +410,24 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_gather_ws(GatherTiledAr
             const int st = s % S;
             if (!mbar_wait(full_p + st, (unsigned)((s / S) & 1), err)) return;
             const float *sp = stage + st * 7 * CAP;
-            const uint32_t nb = (cnt + 31) / 32;
+            const uint32_t nb = (cnt + 32 * PP - 1) / (32 * PP);
             // rotate the first batch with the sub-step so the odd batch does not always hit warp 0
             for (uint32_t b = (uint32_t)((warp + CW - s % CW) % CW); b < nb; b += CW) {
-                const uint32_t i = b * 32 + lane;
-                if (i < cnt)
-                    update(s0, beg + off + i, sp[i], sp[CAP + i], sp[2 * CAP + i], sp[3 * CAP + i], sp[4 * CAP + i],
-                           sp[5 * CAP + i], __float_as_uint(sp[6 * CAP + i]));
+                if constexpr (PP == 1) {
+                    const uint32_t i = b * 32 + lane;
+                    if (i < cnt)
+                        update(s0, beg + off + i, sp[i], sp[CAP + i], sp[2 * CAP + i], sp[3 * CAP + i], sp[4 * CAP + i],
+                               sp[5 * CAP + i], __float_as_uint(sp[6 * CAP + i]));
+                } else {
+                    uint32_t ii[PP];
+                    bool ok[PP];
+#pragma unroll
+                    for (int j = 0; j < PP; ++j) {
+                        ii[j] = (b * PP + j) * 32 + lane;
+                        ok[j] = ii[j] < cnt;
+                    }
+                    if (ok[0]) update_n(s0, beg + off, ii, ok, sp);       // (ok[j] implies ok[0])
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_p + st);

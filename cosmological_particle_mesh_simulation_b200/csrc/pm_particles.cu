@@ -648,6 +648,9 @@ int pm_k_gather_kick_drift(pm_plan *p, float *pos, float *vel, int64_t np, const
 #ifndef PM_GW_S
 #define PM_GW_S 3
 #endif
+#ifndef PM_GW_PP
+#define PM_GW_PP 1      // particles per consumer lane and batch (pm_gather_ws.cuh)
+#endif
 
 // ---- work list of the warp-specialised gather ------------------------------------------------------
 // With a fixed grid every CTA marches zc planes of one row block whatever they hold.  On an evolved
@@ -765,7 +768,7 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
     auto kern = k_gather_tiled<NC, PM_GT_YB, PM_GT_NT, PM_GT_CAP, PM_GT_MINB>;
     using WsSmem = pmws::Smem<NC, PM_GT_YB, PM_GT_CAP, PM_GW_R, PM_GW_S>;
     static_assert(WsSmem::total <= 227 * 1024 / PM_GT_MINB, "PM_GT_MINB CTAs per SM (warp-specialised gather)");
-    auto kern_ws = k_gather_ws<NC, PM_GT_YB, PM_GW_CW, PM_GT_CAP, PM_GW_R, PM_GW_S, PM_GT_MINB>;
+    auto kern_ws = k_gather_ws<NC, PM_GT_YB, PM_GW_CW, PM_GT_CAP, PM_GW_R, PM_GW_S, PM_GT_MINB, PM_GW_PP>;
     PM_ONCE_PER_DEVICE_BEGIN(p->device)
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
