@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(kThr2, 2) k_fft2_cols(ColArgs a)
 }
 
 template <int N, bool FWD>
-__global__ void __launch_bounds__(kThr2, 2) k_fft2_rows(const float2 *__restrict__ in,
+__global__ void __launch_bounds__(kThr2, N >= 2048 ? 1 : 2) k_fft2_rows(const float2 *__restrict__ in,
                                                         float2 *__restrict__ out,
                                                         const float2 *__restrict__ tw,
                                                         const float *__restrict__ mean_ptr)
@@ -1107,13 +1107,13 @@ ColArgs slab_args(pm_plan *p)
     return ca;
 }
 
-// Row passes of a slab: the two-stage register-resident kernels (pm_fft2.cuh) where they exist (256..1024
+// Row passes of a slab: the two-stage register-resident kernels (pm_fft2.cuh) where they exist (256..2048
 // points; same input, output layout and packing of the Nyquist term as k_fft_rows: natural kx), else the
 // radix-8 kernels.  At 1024 points the former stream at 5 TB/s, the latter at 2.7.
 template <int N>
 int slab_rows_fwd(pm_plan *p, const float *rho, cudaStream_t st)
 {
-    if constexpr (kHasV2<N>) {
+    if constexpr (kHasRows2<N>) {
         if (p->fft_v2) {
             constexpr int RT = kRowsPT2<N>;
             const size_t smem2 = ((size_t)N + (size_t)RT * RowFac<N>::RA * (RowFac<N>::RB + 1)) * sizeof(float2);
@@ -1204,7 +1204,7 @@ int slab_unpack_y_inv(pm_plan *p, int c, int C, const float2 *back_main_c, const
 template <int N>
 int slab_rows_inv(pm_plan *p, float *phi, cudaStream_t st)
 {
-    if constexpr (kHasV2<N>) {
+    if constexpr (kHasRows2<N>) {
         if (p->fft_v2) {
             constexpr int RT = kRowsPT2<N>;
             const size_t smem2 = ((size_t)N + (size_t)RT * RowFac<N>::RA * (RowFac<N>::RB + 1)) * sizeof(float2);

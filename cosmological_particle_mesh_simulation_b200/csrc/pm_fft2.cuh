@@ -100,10 +100,15 @@ template <int N> struct RowFac;
 template <> struct RowFac<256>  { static constexpr int RA = 16, RB = 8; };
 template <> struct RowFac<512>  { static constexpr int RA = 16, RB = 16; };
 template <> struct RowFac<1024> { static constexpr int RA = 32, RB = 16; };
+template <> struct RowFac<2048> { static constexpr int RA = 32, RB = 32; };   // rows only (slab path): 32 x 32 = 1024 complex points
 template <int N>
 constexpr int kRowsPT2 = kThr2 / RowFac<N>::RA;
 template <int N>
 constexpr bool kHasV2 = (N == 256 || N == 512 || N == 1024);
+// the row kernel alone also exists for 2048 points (two 32-point register DFTs; one CTA of 256 threads per SM
+// pair of row tiles would need > 128 registers in the inverse, so it runs at one CTA per 255-register budget)
+template <int N>
+constexpr bool kHasRows2 = kHasV2<N> || N == 2048;
 
 // ---- column transform of a tile: N points x CC columns ----------------------------------------
 // ld(pos, c) / st(pos, c, v) address the global tile; green(k, c) is the real factor applied to

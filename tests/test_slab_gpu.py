@@ -254,3 +254,37 @@ def test_slab_run_is_deterministic(pm):
         for r in ranks:
             r.close()
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("n_cells,nranks", [(512, 2), (1024, 8), (2048, 8)])
+def test_slab_row_passes_two_stage_equal_radix8(pm, n_cells, nranks, monkeypatch):
+    """The slab's row passes run the two-stage register-resident kernels (pm_fft2.cuh; 2048 points: rows only)
+    where they exist and the radix-8 kernels otherwise (PM_FFT_V2=0 forces them).  Same layout and Nyquist
+    packing, so forward + inverse over one rank's planes must agree to float32 rounding, and both must return
+    2 * Nc/2 ... i.e. Nc times the (mean-free) input.  One rank of an `nranks` geometry is enough: the row
+    passes are local.  (2048: 256 planes of 2048^2 = 4.3 GB per array.)"""
+    slab = pm.slab
+    rng = torch.Generator(device="cuda").manual_seed(5)
+    out = {}
+    x = None
+    for v2 in ("1", "0"):
+        monkeypatch.setenv("PM_FFT_V2", v2)
+        r = slab.SlabRank(n_cells, 4096, torch.cuda.current_device(), 0, nranks)
+        try:
+            if x is None:
+                x = torch.rand(r.buf["RHO"].shape, generator=rng, device="cuda", dtype=torch.float32)
+            r.buf["RHO"].copy_(x)
+            pm._runtime.check(pm._runtime.lib().pm_slab_set_rho_mean(r.handle, 0.5), "pm_slab_set_rho_mean")
+            r.fft_rows_forward()
+            r.fft_rows_inverse()
+            torch.cuda.synchronize()
+            out[v2] = r.buf["PHI"].clone()
+        finally:
+            r.close()
+    a, b = out["1"], out["0"]
+    want = (x - 0.5) * float(n_cells)
+    scale = float(want.double().norm())
+    assert float((a.double() - b.double()).norm()) / scale <= 2e-6
+    assert float((a.double() - want.double()).norm()) / scale <= 2e-6
+    del out, a, b, want, x
+    torch.cuda.empty_cache()
