@@ -289,6 +289,8 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
         p->gather_ws = !(gw && strcmp(gw, "0") == 0);
     }
     {
+        const char *pd = getenv("PM_PEER_DMA");       // "1": copy engines for the "peer" transport's transposes
+        p->peer_dma = pd && strcmp(pd, "0") != 0;
         const char *gi = getenv("PM_GATHER_ITEMS");   // "0": the gather's fixed grid, no work list
         p->gather_items = !(gi && strcmp(gi, "0") == 0);
         const char *gr = getenv("PM_GRAPH");     // "0": never replay the resident step as a CUDA graph

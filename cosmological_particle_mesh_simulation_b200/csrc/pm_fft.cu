@@ -1263,11 +1263,54 @@ __global__ void __launch_bounds__(256) k_slab_peer_copy(float2 *__restrict__ ful
     }
 }
 
+// The same transposes by the COPY ENGINES (transport "peer", PM_PEER_DMA != 0): per destination rank one
+// strided 3-D copy (rows of hc*8 bytes, nyl rows per plane, nzl planes) and, with chunk 0, one 2-D copy of
+// the Nyquist plane.  The copy kernels above need SMs and shared nothing with the one-CTA-per-SM column
+// kernels of the wide meshes, so "overlapping" them only interleaved them; DMA transfers run beside the y
+// and z passes of the neighbouring chunks for real (NVSwitch gives one GPU its full 900 GB/s towards any
+// single peer, so the per-peer copies simply follow each other on the stream).
+template <bool PULL>
+int slab_peer_copy_dma(pm_plan *p, int c, int C, cudaStream_t st)
+{
+    const int N = p->nc, H = N / 2;
+    const int nzl = p->nzl, nyl = N / p->nranks, hc = H / C;
+    const size_t main_n = (size_t)nzl * N * H;
+    float2 *spec_main = p->spec, *spec_side = p->spec + main_n;
+    for (int k = 0; k < p->nranks; ++k) {
+        const int s = (p->rank + k) % p->nranks;          // start with the own block, then round the ring
+        float2 *rem_main = p->peer_recv[s] + main_n / C * c;      // [P*nzl][nyl][hc] on rank s
+        cudaMemcpy3DParms q;
+        memset(&q, 0, sizeof(q));
+        cudaPitchedPtr loc = make_cudaPitchedPtr(spec_main, (size_t)H * sizeof(float2), (size_t)H * sizeof(float2), (size_t)N);
+        cudaPitchedPtr rem = make_cudaPitchedPtr(rem_main, (size_t)hc * sizeof(float2), (size_t)hc * sizeof(float2), (size_t)nyl);
+        const cudaPos loc_pos = make_cudaPos((size_t)c * hc * sizeof(float2), (size_t)s * nyl, 0);
+        const cudaPos rem_pos = make_cudaPos(0, 0, (size_t)p->rank * nzl);
+        q.srcPtr = PULL ? rem : loc; q.srcPos = PULL ? rem_pos : loc_pos;
+        q.dstPtr = PULL ? loc : rem; q.dstPos = PULL ? loc_pos : rem_pos;
+        q.extent = make_cudaExtent((size_t)hc * sizeof(float2), (size_t)nyl, (size_t)nzl);
+        q.kind = cudaMemcpyDefault;
+        PM_CUDA(cudaMemcpy3DAsync(&q, st));
+        if (c == 0) {
+            // Nyquist plane: local [nzl][N], remote [P*nzl][nyl] behind the main array
+            float2 *l2 = spec_side + (size_t)s * nyl;
+            float2 *r2 = p->peer_recv[s] + main_n + (size_t)p->rank * nzl * nyl;
+            if (PULL)
+                PM_CUDA(cudaMemcpy2DAsync(l2, (size_t)N * sizeof(float2), r2, (size_t)nyl * sizeof(float2),
+                                          (size_t)nyl * sizeof(float2), (size_t)nzl, cudaMemcpyDefault, st));
+            else
+                PM_CUDA(cudaMemcpy2DAsync(r2, (size_t)nyl * sizeof(float2), l2, (size_t)N * sizeof(float2),
+                                          (size_t)nyl * sizeof(float2), (size_t)nzl, cudaMemcpyDefault, st));
+        }
+    }
+    return PM_OK;
+}
+
 template <bool PULL>
 int slab_peer_copy(pm_plan *p, int c, int C, cudaStream_t st)
 {
     const int N = p->nc, H = N / 2;
     const int nzl = p->nzl, nyl = N / p->nranks, hc = H / C;
+    if (p->peer_dma) return slab_peer_copy_dma<PULL>(p, c, C, st);
     if (hc % 2) return PM_ERR_UNSUPPORTED;
     PeerPtrs pp;
     for (int s = 0; s < PM_PEER_MAX; ++s) pp.p[s] = s < p->nranks ? p->peer_recv[s] : nullptr;

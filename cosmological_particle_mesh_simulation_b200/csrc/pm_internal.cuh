@@ -198,6 +198,7 @@ struct pm_plan {
     void *gat_items;
     uint32_t *gat_ctl;      // [0] heavy items, [1] light items, [2] overflow flag
     int gat_cap;
+    bool peer_dma;          // transport "peer": the transposes by cudaMemcpy3DAsync (copy engines) instead of copy kernels
     bool gather_items;      // PM_GATHER_ITEMS=0: fixed (row block, z chunk) grid as before
     void *diag;             // 64 bytes of device scratch for diagnostics (pm_plan_block_stats)
 
