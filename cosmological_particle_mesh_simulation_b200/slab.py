@@ -114,6 +114,10 @@ class SlabRank:
     def count(self):
         return int(rt.lib().pm_slab_count(self.handle))
 
+    def entries(self):
+        """Slots in use (live particles + entries that left and are dropped by the next sort)."""
+        return int(rt.lib().pm_slab_entries(self.handle))
+
     def export(self):
         """(pos[3,n], vel[3,n], ids[n]) of the live particles, storage order."""
         n = int(rt.lib().pm_slab_entries(self.handle))
@@ -228,6 +232,11 @@ class SlabRank:
     def gather(self, a, f_a1, da):
         self._call("pm_slab_gather", float(a), float(f_a1), float(da))
 
+    def leave_capacity(self):
+        """Records per destination rank and step the leave lists hold (csrc/pm_api.cu, compute_layout)."""
+        npad = (self.np_capacity + 3) // 4 * 4
+        return max(npad // 32, 65536)
+
     def migrate_pack(self, counts):
         arr = (ctypes.c_int64 * self.nranks)(*[int(c) for c in counts])
         self._call("pm_slab_migrate_pack", arr)
@@ -291,6 +300,10 @@ class LocalComm:
         (send_counts, recv_counts) as lists of Python ints per local rank."""
         send = [c.tolist() for c in counts]
         return send, self.exchange_counts(send)
+
+    def agree_any(self, flag):
+        """True on every rank if `flag` is true on any (all ranks live here: nothing to exchange)."""
+        return bool(flag)
 
     def all_to_all_v(self, send, send_counts, recv, recv_counts):
         P = self.nranks
@@ -362,6 +375,14 @@ class DistComm:
         return [out.tolist()]
 
     _count_device = "cpu"
+
+    def agree_any(self, flag):
+        """True on every rank if `flag` is true on any rank (one small all-reduce)."""
+        if self.nranks == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self._count_device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return bool(int(t.item()))
 
     def exchange_count_tensors(self, counts):
         """As LocalComm.exchange_count_tensors, with ONE device->host read per step: the counts
@@ -794,6 +815,13 @@ def slab_step(ranks, comm, a, da, mass=None, cfg=None, timer=None, chunks=None, 
         # the leave counts are exchanged on the device; one small device->host read per step brings both
         # count vectors back (they size the messages)
         send_counts, recv_counts = comm.exchange_count_tensors([r.buf["LEAVE_COUNTS"] for r in ranks])
+        # An overflow is local knowledge (a leave list beyond its capacity, arrivals beyond the free room); a rank
+        # that raised alone would leave the others inside the all-to-all-v.  One flag all-reduce makes it common.
+        bad = [r.rank for r, sc, rc in zip(ranks, send_counts, recv_counts)
+               if max(sc) > r.leave_capacity() or r.entries() + sum(rc) > r.np_capacity]
+        if comm.agree_any(bool(bad)):
+            raise SlabExchangeError("slab step failed: leave-list or particle capacity exceeded on some rank "
+                                    "(here: %s); every rank raises this in the same step" % (bad or "none"))
         for r, sc in zip(ranks, send_counts):
             r.migrate_pack(sc)
         comm.all_to_all_v(B("MIG_SEND"), send_counts, B("MIG_RECV"), recv_counts)

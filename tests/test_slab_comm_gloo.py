@@ -40,6 +40,8 @@ assert sc2[0] == list(counts[r]) and rc2[0] == rc[r], (sc2, rc2)
 ls, lr = loc.exchange_count_tensors([torch.tensor(c_, dtype=torch.int32) for c_ in counts])
 assert ls == [list(c_) for c_ in counts] and lr == rc
 z = torch.zeros(16, 7); comm.all_to_all_v([recs[r]], [counts[r]], [z], c); assert torch.equal(z, rv[r])
+# an error seen by one rank becomes every rank's (the NCCL migration path agrees on overflows this way)
+assert comm.agree_any(r == 1) is True and comm.agree_any(False) is False and loc.agree_any(True) is True
 assert slab.slab_of_particles(torch.tensor([0.0, 15.9, 16.0, 32.0]), 32, 2).tolist() == [0, 0, 1, 0]
 dist.barrier(); dist.destroy_process_group()
 sys.stdout.write("rank" + str(r) + "-ok\n"); sys.stdout.flush()

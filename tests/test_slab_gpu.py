@@ -234,6 +234,20 @@ def test_exchange_errors_are_raised_by_every_rank(pm):
         r.migrate_counts_push()
     mats = [r.migrate_counts_read() for r in ranks]
     assert all((m == mats[0]).all() for m in mats) and mats[0][1, P + 1] == 1 and mats[0][0, P + 1] == 0
+    # the NCCL migration path: the same overflow, agreed on by a flag all-reduce before the all-to-all-v
+    pm.slab.slab_step(ranks, comm, 0.41, 0.0099, mass=8.0, cfg=cfg, migrate="nccl")
+    real_gather = pm.slab.SlabRank.gather
+
+    def gather_then_overflow(self, *args):
+        real_gather(self, *args)
+        if self.rank == 1:
+            self.buf["LEAVE_COUNTS"][0] = 2 ** 30
+    pm.slab.SlabRank.gather = gather_then_overflow
+    try:
+        with pytest.raises(pm.slab.SlabExchangeError):
+            pm.slab.slab_step(ranks, comm, 0.42, 0.0099, mass=8.0, cfg=cfg, migrate="nccl")
+    finally:
+        pm.slab.SlabRank.gather = real_gather
     for r in ranks:
         r.close()
 

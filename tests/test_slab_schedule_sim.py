@@ -128,6 +128,15 @@ class RankRecorder:
     def migrate_wait(self):
         self.current.ops.append(("wait", "wait", self.SLOT_MIG_DATA))
 
+    # capacity bookkeeping the NCCL migration path consults before its all-to-all-v
+    np_capacity = 1 << 30
+
+    def leave_capacity(self):
+        return 1 << 30
+
+    def entries(self):
+        return 0
+
 
 class CommRecorder:
     """Stands in for slab.DistComm (one rank per process, collectives on the current stream)."""
@@ -155,6 +164,10 @@ class CommRecorder:
 
     def all_to_all_v(self, send, sc, recv, rc):
         self._coll("a2av", range(self.nranks))
+
+    def agree_any(self, flag):
+        self._coll("agree", range(self.nranks))      # one more collective every rank enters
+        return bool(flag)
 
 
 def record_program(P, steps, transport, chunks, two_streams, monkeypatch, ghosts="nccl", migrate="nccl"):
