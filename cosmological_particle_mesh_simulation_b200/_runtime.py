@@ -158,6 +158,14 @@ def lib():
             "pm_ic_power_spectrum": (i32, [ctypes.POINTER(ICParams), vp, vp, sz, vp]),
             "pm_ic_gaussian_random_field": (i32, [ctypes.POINTER(ICParams), vp, vp, vp, vp, sz, vp]),
             "pm_ic_zeldovich": (i32, [ctypes.POINTER(ICParams), vp, vp, vp, vp, vp, sz, vp]),
+            "pm_ic_slab_workspace_bytes": (sz, []),
+            "pm_ic_noise_range": (i32, [vp, vp, i64, i64, ctypes.c_uint64, vp]),
+            "pm_ic_slab_rho_k": (i32, [ctypes.POINTER(ICParams), vp, vp, i32, i32, vp, vp, sz, vp]),
+            "pm_ic_slab_fft": (i32, [vp, i32, i32, i32, i32, i32, vp]),
+            "pm_ic_slab_real_f32": (i32, [vp, i64, f64, vp, vp]),
+            "pm_ic_slab_from_f32": (i32, [vp, i64, vp, vp]),
+            "pm_ic_slab_displacement_k": (i32, [ctypes.POINTER(ICParams), i32, vp, i32, i32, vp, vp]),
+            "pm_ic_slab_particles": (i32, [ctypes.POINTER(ICParams), i32, vp, i32, i32, ctypes.c_uint64, vp, vp, vp, vp, vp]),
             "pm_plan_profile_begin": (i32, [vp, i32]),
             "pm_plan_profile_read": (i32, [vp, vp, ctypes.POINTER(i32)]),
         }
@@ -189,6 +197,8 @@ EXPORTED_SYMBOLS = (
     "pm_plan_set_sort_mode", "pm_plan_sort_stats", "pm_plan_set_fft_fuse", "pm_plan_fft_sync_errors",
     "pm_plan_set_fft_variant", "pm_plan_set_gather_tiled", "pm_plan_gather_tile", "pm_plan_block_stats", "pm_ic_workspace_bytes", "pm_ic_noise",
     "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",
+    "pm_ic_slab_workspace_bytes", "pm_ic_noise_range", "pm_ic_slab_rho_k", "pm_ic_slab_fft", "pm_ic_slab_real_f32",
+    "pm_ic_slab_from_f32", "pm_ic_slab_displacement_k", "pm_ic_slab_particles",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

@@ -444,6 +444,47 @@ PM_API int pm_ic_gaussian_random_field(const pm_ic_params *prm, const float *f1_
 PM_API int pm_ic_zeldovich(const pm_ic_params *prm, const float *density_d, const double *jitter_d,
                            float *pos_d, float *vel_d, void *work_d, size_t work_bytes, pm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Initial conditions, one slab per rank (configs[2]-[3]: the 1024^3 lattice does not have to exist on
+ * any one GPU).  The same generator as above, cut into the pieces a slab-decomposed run needs; the
+ * host side (slab_ic.py) strings them together with two kinds of all-to-all transposes.  Replaces the
+ * same reference functions (src/gaussian_random_field.py:9-29, src/zeldovich.py:10-100).
+ *
+ * Decomposition: k-space fields are held as planes [i0_lo, i0_lo + n0l) of the slowest array axis
+ * ([n0l][n][n] complex128); real-space fields as columns [i2_lo, i2_lo + n2l) of the fastest axis
+ * ([n][n][n2l]) -- the lattice coordinate that becomes positions[2], the axis the mesh slabs are cut
+ * along (slab.py), so nearly every particle is generated on the rank that owns it.  A 3-D transform is
+ * PM_IC_AXES_12 on k-space planes, transpose, PM_IC_AXIS_0 on real-space columns (inverse), or
+ * PM_IC_AXES_01, transpose, PM_IC_AXIS_2 (forward).  Noise and jitter are functions of the GLOBAL
+ * element / particle index, the power-spectrum normalisation is summed over the whole grid in the
+ * single-GPU generator's order on every rank: the union of the slabs is the single-GPU particle set
+ * up to the rounding of the differently ordered transforms.
+ * ---------------------------------------------------------------------------------------------- */
+#define PM_IC_AXES_12 0   /* 2-D transform over the two fastest axes, one per index of the slowest   */
+#define PM_IC_AXIS_0 1    /* 1-D transform along the slowest axis (stride d1*d2)                     */
+#define PM_IC_AXES_01 2   /* 2-D transform over the two slowest axes (stride d2), one per fastest    */
+#define PM_IC_AXIS_2 3    /* 1-D transform along the fastest axis                                    */
+PM_API size_t pm_ic_slab_workspace_bytes(void);
+/* f1, f2: the elements [e0, e0 + n) of the fields pm_ic_noise(seed) fills */
+PM_API int pm_ic_noise_range(float *f1_d, float *f2_d, int64_t e0, int64_t n, uint64_t seed, pm_stream_t stream);
+/* zk_d: complex128 [n0l][n][n] = sqrt(p D^2) (f1 + i f2) on planes i0_lo .. i0_lo + n0l - 1; f1/f2: those planes */
+PM_API int pm_ic_slab_rho_k(const pm_ic_params *prm, const float *f1_d, const float *f2_d, int i0_lo, int n0l,
+                            void *zk_d, void *work_d, size_t work_bytes, pm_stream_t stream);
+/* in-place complex128 transform of a contiguous [d0][d1][d2] array over `axes` (cuFFT Z2Z, unnormalised) */
+PM_API int pm_ic_slab_fft(void *z_d, int d0, int d1, int d2, int axes, int inverse, pm_stream_t stream);
+/* out[i] = float32(re(z[i]) * scale);   z[i] = in[i] + 0i */
+PM_API int pm_ic_slab_real_f32(const void *z_d, int64_t count, double scale, float *out_d, pm_stream_t stream);
+PM_API int pm_ic_slab_from_f32(const float *in_d, int64_t count, void *z_d, pm_stream_t stream);
+/* out = (-i l_dir) (rho_k / -k^2) (N_CELLS / N_PARTS) on planes i0_lo .. (zeldovich.py:24-38, 56-69) */
+PM_API int pm_ic_slab_displacement_k(const pm_ic_params *prm, int dir, const void *rho_k_d, int i0_lo, int n0l,
+                                     void *out_d, pm_stream_t stream);
+/* z_d: complex128 [n][n][n2l], the unnormalised inverse transform of the above on columns i2_lo ..;
+ * pos_d, vel_d: float32[n*n*n2l] (row `dir` of the caller's [3][..] arrays), ids_d (optional): the
+ * single-GPU particle index (i0 n + i1) n + i2; jitter_d (optional): float64[n*n*n2l] in local order,
+ * default the pm_ic_jitter(seed) stream of the particle's global index */
+PM_API int pm_ic_slab_particles(const pm_ic_params *prm, int dir, const void *z_d, int i2_lo, int n2l, uint64_t seed,
+                                const double *jitter_d, float *pos_d, float *vel_d, int32_t *ids_d, pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
