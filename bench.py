@@ -472,7 +472,14 @@ def run_slab(args, rank, world, local_rank):
     mass = (n_cells / n_parts) ** 3
     comm = slab.DistComm()
     def build_ranks():
-        if n_parts > 256:
+        if args.particles == "zeldovich":
+            # the package's own initial conditions, generated slab by slab (slab_ic.py): no rank holds the lattice
+            out = pm.slab_ic.make_ranks_from_ic(comm, cfg=cfg, device=dev)
+            cnt = torch.tensor([out[0].count], dtype=torch.int64, device=f"cuda:{dev}")
+            dist.all_reduce(cnt)
+            assert int(cnt.item()) == npart, (int(cnt.item()), npart)
+            desc = "gaussian_random_field + zeldovich generated per slab on the GPUs (Philox, RANDOM_SEED 38)"
+        elif n_parts > 256:
             # large configurations: every rank generates its own slab on its GPU
             pl, vl, il = make_particles_slab_gpu(n_parts, n_cells, rank, world, dev)
             out = [slab.make_rank_from_local(n_cells, pl, vl, il, rank, world, device=dev, total_particles=npart)]
@@ -722,6 +729,11 @@ def run_ours(args, rank, world, local_rank):
         pos_h, vel_h = pos.cpu(), vel.cpu()
         particles_desc = ("z=0-like snapshot (BASELINE configs[4]): own Zel'dovich ICs (RANDOM_SEED 38) evolved by "
                           "%d resident steps of the reference schedule to a = %.4f" % (n_ev, a_last + da_last))
+    elif args.particles == "zeldovich":
+        with torch.cuda.device(dev):
+            pos, vel = pm.zeldovich(pm.gaussian_random_field(device=dev))
+        pos_h, vel_h = pos.cpu(), vel.cpu()
+        particles_desc = "the package's own initial conditions (gaussian_random_field + zeldovich on the GPU, RANDOM_SEED 38)"
     else:
         pos_h, vel_h = make_particles_torch(n_parts, n_cells, "cpu")
         particles_desc = "lattice + uniform(-2,2) jitter, Gaussian velocities rms %g, seed 38" % VEL_SIGMA
@@ -992,7 +1004,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-parts", type=int, default=256)
     ap.add_argument("--n-cells", type=int, default=512)
-    ap.add_argument("--particles", default="ic", choices=["ic", "clustered", "evolved"],
+    ap.add_argument("--particles", default="ic", choices=["ic", "clustered", "evolved", "zeldovich"],
                     help="N=1 workload: IC-like lattice+jitter (default, the metric's configuration); the synthetic clustered "
                          "microbench load of BASELINE configs[4]; or `evolved`, the z=0 snapshot obtained by running the "
                          "package's own ICs through the whole schedule (per-stage times show deposit/sort/gather under skew)")
