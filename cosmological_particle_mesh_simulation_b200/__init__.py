@@ -27,7 +27,7 @@ from .fourier_utils import fourier_grid, FourierGrid  # noqa: F401
 from .potential import potential  # noqa: F401
 from .integrate import advance_time, integrate  # noqa: F401
 from .cosmology import f  # noqa: F401
-from .pmesh import step, step_host, simulator, run, loop_scale_factors, ResidentParticles  # noqa: F401
+from .pmesh import step, step_host, simulator, run, run_slabs, loop_scale_factors, ResidentParticles  # noqa: F401
 from . import slab, slab_ic, analysis, _session  # noqa: F401,E402
 from ._session import forget as forget_resident, set_enabled as set_resident_dropin, sync as sync_particles  # noqa: F401,E402
 from .gaussian_random_field import gaussian_random_field  # noqa: F401,E402

@@ -289,6 +289,121 @@ def run(max_steps=None, device=None):
     return positions, velocities, a_current
 
 
+def run_slabs(comm=None, max_steps=None, device=None, peers=True):
+    """`run` for a slab-decomposed box: the same driver (src/pmesh.py:18-79 -- initial conditions or
+    restart, loop predicate, snapshot / plot cadences, status line) with the mesh cut into z slabs
+    over the ranks of `comm` (slab.DistComm(): one process per GPU under torchrun, the default;
+    slab.LocalComm(P): all ranks in this process on one GPU).
+
+    Initial conditions are generated slab by slab (slab_ic.py: no rank holds the N_PARTS^3 lattice);
+    a restart reads the snapshot on every rank and keeps the rank's share.  The FFT transposes,
+    ghost planes and migration go through peer memory when it can be set up (`peers`), NCCL
+    otherwise.  On a cadence step the particles are collected in original order and the density
+    slabs concatenated; the rank that holds slab 0 writes the snapshot and the images, so the
+    files are those of the single-GPU run.  Returns (ranks, a_current); the caller closes the ranks
+    (slab.release_peers first when peers were set up)."""
+    from time import time
+    try:
+        from . import slab, slab_ic
+        from .save_data import save_file, from_file, wait
+        from .plot_helper import plot_step, plot_projection
+    except ImportError:
+        import slab
+        import slab_ic
+        from save_data import save_file, from_file, wait
+        from plot_helper import plot_step, plot_projection
+    cfg = rt.config()
+    dev = rt.current_device() if device is None else int(device)
+    comm = comm if comm is not None else slab.DistComm()
+    N_CELLS, N_PARTS = int(cfg.N_CELLS), int(cfg.N_PARTS)
+    A_INIT, A_END = cfg.A_INIT, cfg.A_END
+    flag = lambda name: bool(getattr(cfg, name, False))    # noqa: E731
+    writer = 0 in comm.local_ranks                          # the process that holds slab 0 does the I/O
+    npart = N_PARTS ** 3
+    dens_contrast = (N_CELLS / N_PARTS) ** 3
+    da = (A_END - A_INIT) / cfg.STEPS
+    da_save = (A_END - A_INIT) / cfg.N_SAVE_FILES
+    da_plot = (A_END - A_INIT) / cfg.N_PLOTS
+    a_current = A_INIT
+    n_file = 0
+    n_plot = 0
+    if writer:
+        print('Starting the simulation for {}^3 particles'.format(N_PARTS), 'with {}^3 grid cells'.format(N_CELLS),
+              'on {} slabs'.format(comm.nranks))
+
+    def gather_slabs(pieces, dim):
+        """The whole mesh from the ranks' slabs along `dim` (every process gets it)."""
+        if isinstance(comm, slab.LocalComm) or comm.nranks == 1:
+            return torch.cat(list(pieces), dim=dim)
+        mine = pieces[0].contiguous()
+        parts = [torch.empty_like(mine) for _ in range(comm.nranks)]
+        comm.dist.all_gather(parts, mine, group=comm.group)
+        return torch.cat(parts, dim=dim)
+
+    def full_density(ranks):
+        """[Nc, Nc, Nc] density of the last deposit."""
+        return gather_slabs([r.buf["RHO"] for r in ranks], 0)
+
+    with torch.cuda.device(dev):
+        if flag("RESTART"):
+            n_file = cfg.RESTART_FROM_N
+            n_plot = (cfg.RESTART_FROM_N) / cfg.N_SAVE_FILES * cfg.N_PLOTS
+            positions, velocities, a_current = from_file(n_file, device=dev)
+            ranks = slab.make_ranks(N_CELLS, positions, velocities, comm, device=dev)
+            del positions, velocities
+        else:
+            ranks, grf = slab_ic.make_ranks_from_ic(comm, cfg=cfg, device=dev, return_density=True)
+            if flag("SAVE_DATA"):
+                # the t = 0 snapshot holds the initial Gaussian field (src/pmesh.py:44): assembled from the
+                # ranks' columns only here, and only when it is written
+                rho0 = gather_slabs(grf, 2) if flag("SAVE_DENSITY") else None
+                positions, velocities = slab.collect(ranks, comm, npart)
+                if writer:
+                    save_file(rho0, positions, velocities, 0, a_current)
+                del positions, velocities, rho0
+                n_file += 1
+            del grf
+        if peers and comm.nranks > 1 and slab.setup_peers(ranks, comm):
+            slab.setup_ghost_peers(ranks, comm)
+        n_steps = 0
+        while a_current < A_END - da:
+            if max_steps is not None and n_steps >= max_steps:
+                break
+            start_time = time()
+            a_next = a_current + da
+            saving = a_next >= A_INIT + n_file * da_save
+            plotting = a_next >= A_INIT + n_plot * da_plot
+            want_save = saving and flag("SAVE_DATA")
+            want_plot = plotting and (flag("PLOT_STEPS") or flag("PLOT_PROJECTIONS"))
+            need_rho = want_plot or (want_save and flag("SAVE_DENSITY"))
+
+            slab.slab_step(ranks, comm, a_current, da, mass=dens_contrast, cfg=cfg)
+            a_current += da
+
+            rho = full_density(ranks) if need_rho else None          # the PRE-step density (SURVEY Q11)
+            if saving:
+                if want_save:
+                    positions, velocities = slab.collect(ranks, comm, npart)
+                    if writer:
+                        save_file(rho if flag("SAVE_DENSITY") else None, positions, velocities, n_file, a_current)
+                    del positions, velocities
+                n_file += 1
+            if plotting:
+                if writer and flag("PLOT_STEPS"):
+                    plot_step(rho, n_plot)
+                if writer and flag("PLOT_PROJECTIONS"):
+                    plot_projection(rho, n_plot, 15)
+                n_plot += 1
+            del rho
+            if writer and flag("PRINT_STATUS"):
+                torch.cuda.synchronize(dev)
+                print_status(a_current, start_time, cfg)
+            n_steps += 1
+        torch.cuda.synchronize(dev)
+    wait()
+    return ranks, a_current
+
+
 def print_status(a_current, start_time, cfg=None):
     """src/pmesh.py:81-84."""
     from time import time
@@ -298,8 +413,28 @@ def print_status(a_current, start_time, cfg=None):
 
 
 if __name__ == "__main__":      # src/pmesh.py:86-93 (`python pmesh.py` from the package directory)
+    import os
     from time import time
     _t0 = time()
-    simulator()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # under torchrun: one process per GPU, the box cut into slabs
+        import torch.distributed as _dist
+        _local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(_local)
+        _dist.init_process_group("nccl", device_id=torch.device(f"cuda:{_local}"))
+        try:
+            from . import slab as _slab
+        except ImportError:
+            import slab as _slab
+        _comm = _slab.DistComm()
+        _ranks, _ = run_slabs(_comm, device=_local)
+        _slab.release_peers(_ranks, _comm)
+        for _r in _ranks:
+            _r.close()
+        _dist.barrier()
+        _dist.destroy_process_group()
+        if _comm.rank != 0:
+            raise SystemExit(0)
+    else:
+        simulator()
     print("Finished in")
     print("--- %.2f seconds ---" % (time() - _t0))

@@ -214,10 +214,11 @@ def route_to_owners(parts, comm, n_cells):
     return out
 
 
-def slab_initial_conditions(comm, cfg=None, device=None, seed=None, route=True, ops=None):
+def slab_initial_conditions(comm, cfg=None, device=None, seed=None, route=True, ops=None, return_density=False):
     """The package's gaussian_random_field() + zeldovich() for a slab-decomposed run.
     Returns per local rank (positions [3, k], velocities [3, k], ids int32 [k]); with `route`
-    (default) every particle is on the rank that owns its z cell."""
+    (default) every particle is on the rank that owns its z cell.  return_density: also the
+    float32 Gaussian field, per local rank its columns [n][n][n/P] (the mesh the t = 0 snapshot holds)."""
     cfg = cfg if cfg is not None else rt.config()
     if ops is None:
         dev = rt.current_device() if device is None else int(device)
@@ -225,17 +226,19 @@ def slab_initial_conditions(comm, cfg=None, device=None, seed=None, route=True, 
         ops = [DeviceOps(cfg, dev, seed) for _ in comm.local_ranks]
     density = slab_gaussian_random_field(comm, ops)
     parts = slab_zeldovich(density, comm, ops)
-    del density
-    return route_to_owners(parts, comm, int(cfg.N_CELLS)) if route else parts
+    if route:
+        parts = route_to_owners(parts, comm, int(cfg.N_CELLS))
+    return (parts, density) if return_density else parts
 
 
-def make_ranks_from_ic(comm, cfg=None, device=None, seed=None, slack=1.25):
+def make_ranks_from_ic(comm, cfg=None, device=None, seed=None, slack=1.25, return_density=False):
     """slab.SlabRank(s) of this process loaded with slab-generated initial conditions."""
     cfg = cfg if cfg is not None else rt.config()
     dev = rt.current_device() if device is None else int(device)
     total = int(cfg.N_PARTS) ** 3
     cap = int(total / comm.nranks * slack) + 4096
-    parts = slab_initial_conditions(comm, cfg=cfg, device=dev, seed=seed)
-    return [make_rank_from_local(int(cfg.N_CELLS), p, v, i, r, comm.nranks, device=dev, capacity=cap,
-                                 total_particles=total)
-            for (p, v, i), r in zip(parts, comm.local_ranks)]
+    parts, density = slab_initial_conditions(comm, cfg=cfg, device=dev, seed=seed, return_density=True)
+    ranks = [make_rank_from_local(int(cfg.N_CELLS), p, v, i, r, comm.nranks, device=dev, capacity=cap,
+                                  total_particles=total)
+             for (p, v, i), r in zip(parts, comm.local_ranks)]
+    return (ranks, density) if return_density else ranks

@@ -130,3 +130,56 @@ def test_restart_continues_from_a_snapshot(pm, tmp_path, monkeypatch):
     d = (pos_r.cpu().numpy().astype(np.float64) - pos.cpu().numpy() + 16) % 32 - 16
     assert np.linalg.norm(d) / np.linalg.norm(pos.cpu().numpy().astype(np.float64)) < 1e-5
     assert _rel(vel_r.cpu().numpy(), vel.cpu().numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("P", [1, 2])
+def test_slab_driver_writes_the_snapshots_of_the_single_gpu_driver(pm, tmp_path, monkeypatch, P):
+    """pmesh.run_slabs (initial conditions per slab, slab steps, cadence, snapshots assembled from the
+    slabs) against pmesh.run on the same configuration: same files, same contents to the tolerance
+    the slab step is held to, then a restart of the slab driver from one of them."""
+    cfg = _cfg(PLOT_STEPS=True)
+    pm.set_config(cfg)
+    one, many = tmp_path / "one", tmp_path / "many"
+    one.mkdir(), many.mkdir()
+    monkeypatch.chdir(one)
+    _, _, a_one = pm.run()
+    pm.save_data.wait()
+    monkeypatch.chdir(many)
+    comm = pm.slab.LocalComm(P)
+    ranks, a_many = pm.run_slabs(comm, peers=(P > 1))
+    pm.save_data.wait()
+    assert a_many == a_one
+    assert sum(r.count for r in ranks) == cfg.N_PARTS ** 3
+    files = sorted(f for f in os.listdir(one / "Data"))
+    assert files == sorted(f for f in os.listdir(many / "Data")) and "data.0.hdf5" in files
+    for f in files:
+        if not f.endswith(".hdf5"):
+            continue
+        h1, h2 = H.Reader(str(one / "Data" / f)), H.Reader(str(many / "Data" / f))
+        assert float(h1["a"]) == float(h2["a"])
+        assert _rel(h2["density"], h1["density"]) < 1e-5, f
+        box = cfg.N_CELLS * O.snapshot_units(float(h1["a"]), cfg)[0]
+        for n in ("x1", "x2", "x3"):
+            a1, a2 = h1[n].astype(np.float64), h2[n].astype(np.float64)
+            d = np.minimum(np.abs(a1 - a2), box - np.abs(a1 - a2))     # a particle may sit on either side of the wrap
+            assert np.linalg.norm(d) / np.linalg.norm(a1) < 1e-4, (f, n)
+        for n in ("vx1", "vx2", "vx3"):
+            assert _rel(h2[n], h1[n]) < 1e-3, (f, n)
+    if P > 1:
+        pm.slab.release_peers(ranks, comm)
+    for r in ranks:
+        r.close()
+    # restart of the slab driver from snapshot 2: three more steps == the single-GPU restart
+    cfg.RESTART, cfg.RESTART_FROM_N, cfg.SAVE_DATA, cfg.PLOT_STEPS = True, 2, False, False
+    monkeypatch.chdir(one)
+    pos_r, vel_r, a_r = pm.run(max_steps=3)
+    monkeypatch.chdir(many)
+    comm = pm.slab.LocalComm(P)
+    ranks, a_s = pm.run_slabs(comm, max_steps=3, peers=False)
+    assert a_s == a_r and type(a_s) is type(a_r)
+    pos_s, vel_s = pm.slab.collect(ranks, comm, cfg.N_PARTS ** 3)
+    d = (pos_s.double() - pos_r.double() + 16) % 32 - 16
+    assert float(d.norm() / pos_r.double().norm()) < 1e-4
+    assert _rel(vel_s.cpu().numpy(), vel_r.cpu().numpy()) < 1e-3
+    for r in ranks:
+        r.close()
