@@ -15,9 +15,11 @@ remembered together with the identity and the version counters of those tensors.
 resident state (pm_resident_deposit / pm_resident_advance) and only write the result back in the
 caller's original particle order (pm_particles_store).  Any in-place change the caller makes through
 torch bumps the tensor's version counter, which ends the session: the next call starts from the
-caller's arrays again.  (A write that bypasses torch -- a raw pointer handed to another library --
-cannot be seen; call `forget()` after such a write, or disable the mechanism with
-`set_enabled(False)` / PM_DROPIN_RESIDENT=0.)  CUDA tensors only: NumPy arrays carry no version.
+caller's arrays again.  The package's own entry points that write into caller tensors through raw
+pointers (step, integrate, ResidentParticles.store, rho_out=) bump those counters themselves
+(`after_raw_write`), so mixing them with the two calls above is safe.  (A write by ANOTHER library
+through a raw pointer cannot be seen; call `forget()` after such a write, or disable the mechanism
+with `set_enabled(False)` / PM_DROPIN_RESIDENT=0.)  CUDA tensors only: NumPy arrays carry no version.
 
 Write-back.  By default every `advance_time` ends with pm_particles_store: the caller's tensors hold
 the new state in the caller's order when the call returns, exactly the in-place contract of the
@@ -33,7 +35,9 @@ handles (and the original tensors) and continue from the resident state without 
 The one thing lazy mode cannot see is a READ of the original tensor objects through a name the
 caller kept instead of the returned handles (`advance_time(...)` with the result ignored, then
 `positions.cpu()`): those bytes are stale until `sync()`.  The reference's loop rebinds
-`positions, velocities = advance_time(...)`, so it only ever holds the handles.
+`positions, velocities = advance_time(...)`, so it only ever holds the handles.  The package's own
+entry points are covered either way: they call `before_raw_access` on their arguments, which runs
+the pending write-back when the session mirrors one of them.
 """
 import os
 import weakref
@@ -88,6 +92,44 @@ def forget():
         _session.close()
     _session = None
     _last_rho = None
+
+
+def _same_storage(a, b):
+    try:
+        return a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr()
+    except Exception:      # a tensor without storage
+        return False
+
+
+def before_raw_access(*tensors):
+    """One of the package's C-ABI calls is about to read or write these caller tensors through raw
+    pointers.  If the live session mirrors one of them (the same object or another view of its
+    storage) and a lazy write-back is pending, the caller's bytes are brought up to date first."""
+    s = _session
+    if s is None or not s.pending:
+        return
+    mine = [r() for r in (s.pos_ref, s.vel_ref)]
+    for t in tensors:
+        t = unwrap(t) if t is not None else None
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            continue
+        if any(m is not None and (m is t or _same_storage(m, t)) for m in mine):
+            s.flush()
+            return
+
+
+def after_raw_write(*tensors):
+    """One of the package's C-ABI calls wrote into these caller tensors through raw pointers, which
+    torch's version counters do not see: bump them, as an in-place torch op would have, so that a
+    session (or a remembered density mean) that mirrors one of the tensors ends instead of
+    continuing from a resident state the caller has just overwritten."""
+    for t in tensors:
+        t = unwrap(t) if t is not None else None
+        if isinstance(t, torch.Tensor):
+            try:
+                torch._C._increment_version([t])
+            except TypeError:                      # signature that takes one tensor
+                torch._C._increment_version(t)
 
 
 def _getter(name):
@@ -150,7 +192,7 @@ class Session:
         pos, vel = self.pos_ref(), self.vel_ref()
         if pos is None or vel is None:
             return                        # nobody can read them any more
-        self.state.store(pos, vel)        # raw-pointer write: the version counters (and the session) stay valid
+        self.state._store(pos, vel)       # the session's own write: the version counters (and the session) stay valid
 
     def remember(self, positions, velocities):
         self.pos_ref, self.vel_ref = weakref.ref(positions), weakref.ref(velocities)

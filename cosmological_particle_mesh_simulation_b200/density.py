@@ -28,6 +28,7 @@ def _density_device(positions, mass, n_cells, out=None):
         sess.deposit(mass, rho)
     else:
         plan = rt.get_plan(n_cells, npart, dev)
+        _session.before_raw_access(positions)
         with torch.cuda.device(dev):
             rt.check(rt.lib().pm_deposit_cic(plan.handle, positions.data_ptr(), npart, float(mass),
                                              rho.data_ptr(), rt.stream_ptr(dev)), "pm_deposit_cic")

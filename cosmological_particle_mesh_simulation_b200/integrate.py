@@ -32,11 +32,13 @@ def _integrate_device(positions, velocities, a_val, f_a1, da, potentials, acc=No
     plan = rt.get_plan(n, 1, dev)
     if acc is not None:
         rt.check_dev_f32(acc, (3, npart), "acc")
+    _session.before_raw_access(positions, velocities)
     with torch.cuda.device(dev):
         rt.check(rt.lib().pm_gather_kick_drift(
             plan.handle, positions.data_ptr(), velocities.data_ptr(), npart, potentials.data_ptr(),
             float(a_val), float(f_a1), float(da), acc.data_ptr() if acc is not None else None,
             rt.stream_ptr(dev)), "pm_gather_kick_drift")
+    _session.after_raw_write(positions, velocities, acc)          # ends a drop-in session that mirrors them
     return positions, velocities
 
 
@@ -84,7 +86,7 @@ def advance_time(density, positions, velocities, fgrid, a, da):
         sess.advance(density, _session.known_mean(density), a, da, fa1, cfg.OMEGA_M0)
         if _session.lazy():
             return sess.defer()           # handles over the caller's storage; written back on first use
-        sess.state.store(positions, velocities)
+        sess.state._store(positions, velocities)      # the session's own write-back: it stays valid
         return positions, velocities
     phi = _potential_device(density, fgrid, a)
     return _integrate_device(positions, velocities, a, fa1, da, phi)

@@ -9,9 +9,11 @@ the reference's whole driver, src/pmesh.py:18-79: initial conditions or restart,
 snapshot/plot cadences and the status line, with the state resident in HBM throughout."""
 try:
     from . import _runtime as rt
+    from . import _session
     from .cosmology import f
 except ImportError:
     import _runtime as rt
+    import _session
     from cosmology import f
 import torch
 
@@ -34,12 +36,14 @@ def step(positions, velocities, a, da, mass=None, rho_out=None):
     if rho_out is not None:
         rt.check_dev_f32(rho_out, (n, n, n), "rho_out")
     plan = rt.get_plan(n, npart, dev)
+    _session.before_raw_access(positions, velocities)
     with torch.cuda.device(dev):
         rt.check(rt.lib().pm_step(plan.handle, positions.data_ptr(), velocities.data_ptr(), npart,
                                   float(mass), float(a), float(da), float(_fa1(a, da, cfg)),
                                   float(cfg.OMEGA_M0),
                                   rho_out.data_ptr() if rho_out is not None else None,
                                   rt.stream_ptr(dev)), "pm_step")
+    _session.after_raw_write(positions, velocities, rho_out)     # ends a drop-in session that mirrors them
     return positions, velocities
 
 
@@ -78,6 +82,7 @@ class ResidentParticles:
         self.device = positions.device.index
         self.np = positions.shape[1]
         self.plan = rt.Plan(self.n_cells, max(self.np, 1), self.device)
+        _session.before_raw_access(positions, velocities)
         with torch.cuda.device(self.device):
             rt.check(rt.lib().pm_particles_load(self.plan.handle, positions.data_ptr(),
                                                 velocities.data_ptr(), self.np,
@@ -101,9 +106,16 @@ class ResidentParticles:
                 self.plan.handle, float(mass), float(a), float(da), float(_fa1(a, da, cfg)),
                 float(cfg.OMEGA_M0), rho_out.data_ptr() if rho_out is not None else None,
                 rt.stream_ptr(self.device)), "pm_step_resident")
+        _session.after_raw_write(rho_out)
 
     def store(self, positions, velocities):
         """Write the state into the caller's (3, Np) CUDA tensors in original particle order."""
+        _session.before_raw_access(positions, velocities)
+        self._store(positions, velocities)
+        _session.after_raw_write(positions, velocities)
+        return positions, velocities
+
+    def _store(self, positions, velocities):
         rt.check_dev_f32(positions, (3, self.np), "positions")
         rt.check_dev_f32(velocities, (3, self.np), "velocities")
         with torch.cuda.device(self.device):

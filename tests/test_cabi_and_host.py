@@ -216,3 +216,23 @@ def test_lazy_drop_in_handle_mechanics(monkeypatch):
     assert v.data_ptr() == t.data_ptr() and len(calls) == 3
     v[0, 0] = 5.0                                        # in-place write through the handle: sync first, then one version bump
     assert len(calls) == 4 and float(t[0, 0]) == 5.0 and t._version == 1
+
+
+def test_raw_writes_of_the_package_are_made_visible_to_torch():
+    """_session.after_raw_write: what the package's C-ABI wrappers call after writing into a caller's tensor
+    through data_ptr() -- the version counter moves (views share it), None and handles are accepted;
+    before_raw_access without a session is a no-op."""
+    import torch
+    from cosmological_particle_mesh_simulation_b200 import _session as S
+    t = torch.zeros(3, 4)
+    row = t[1]
+    v0 = t._version
+    S.after_raw_write(t, None)
+    assert t._version > v0 and row._version == t._version
+    v1 = t._version
+    h = t.as_subclass(S.ResidentView)
+    h.__dict__["_pm_base"] = t
+    S.after_raw_write(h)
+    assert t._version > v1
+    assert S._session is None
+    S.before_raw_access(t, None, h)          # nothing to flush

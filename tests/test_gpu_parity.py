@@ -634,6 +634,57 @@ def test_lazy_drop_in_equals_eager_drop_in_bit_for_bit(pm, golden_dir):
     assert rel_l2_periodic(out["lazy"][0], g["pos_5"], n) <= REL_L2 and rel_l2(out["lazy"][1], g["vel_5"]) <= REL_L2
 
 
+@pytest.mark.parametrize("mode", [True, "lazy"])
+def test_drop_in_session_ends_when_the_package_itself_overwrites_the_tensors(pm, golden_dir, mode):
+    """The package's own entry points write through raw pointers, which torch's version counters do not see
+    by themselves: pm.step / integrate / ResidentParticles.store on the tensors a drop-in session mirrors must
+    end that session (and, in lazy mode, first bring the caller's bytes up to date), or the next density() /
+    advance_time() would continue from a resident state the caller has just overwritten.  Checked against the
+    stateless calls."""
+    from cosmological_particle_mesh_simulation_b200 import _session as S
+    g, cfg = load_case(golden_dir, "free32")
+    pm.set_config(cfg_ns(cfg))
+    n, mass, da = cfg.N_CELLS, float(g["mass"]), float(g["da"])
+    a0, a1, a2, a3 = (float(x) for x in g["a_list"][:4])
+    fg = pm.fourier_grid()
+
+    def sequence():
+        positions, velocities = dev(g["pos0"]), dev(g["vel0"])
+        rho = pm.density(positions, mass)
+        positions, velocities = pm.advance_time(rho, positions, velocities, fg, a0, da)        # a session is born here
+        pm.step(positions, velocities, a1, da, mass=mass)                                      # raw write no. 1
+        rho = pm.density(positions, mass)
+        positions, velocities = pm.advance_time(rho, positions, velocities, fg, a2, da)
+        phi = pm.potential(pm.density(positions, mass), fg, a3)
+        pm.integrate(positions, velocities, a3, float(pm.f(a3 + da, [cfg.H0, cfg.OMEGA_LAMBDA0, cfg.OMEGA_K0])), da, phi)   # no. 2
+        rho = pm.density(positions, mass)
+        other = pm.ResidentParticles(dev(g["pos0"]), dev(g["vel0"]))
+        positions, velocities = pm.advance_time(rho, positions, velocities, fg, a3, da)
+        other.store(positions, velocities)                                                     # no. 3: back to the start
+        other.close()
+        rho_end = pm.density(positions, mass)
+        return positions.cpu().numpy(), velocities.cpu().numpy(), rho.cpu().numpy(), rho_end.cpu().numpy()
+
+    try:
+        pm.forget_resident()
+        pm.set_resident_dropin(False)
+        want = sequence()
+        pm.set_resident_dropin(mode)
+        got = sequence()
+        assert S._session is not None
+    finally:
+        pm.forget_resident()
+        pm.set_resident_dropin(True)
+    # writes no. 1 and 2: the density after step / advance / integrate.  (Not bitwise: the stateless Poisson call
+    # measures the mesh mean, the session knows it analytically -- float32 transform noise apart.  A session that
+    # had gone on from its stale state would be off by a whole step, ~1e-3.)
+    assert rel_l2(got[2], want[2]) <= 5e-6
+    # write no. 3 put the initial state back: everything after it is exact
+    for k, name in ((0, "positions"), (1, "velocities"), (3, "final density")):
+        assert np.array_equal(got[k], want[k]), name
+    assert np.array_equal(got[0], g["pos0"]) and np.array_equal(got[1], g["vel0"])
+
+
 def test_plans_on_two_devices_in_one_process(pm):
     """One process, two GPUs: the opt-ins for > 48 KB of dynamic shared memory (FFT passes, tile deposit, gather)
     are per DEVICE; a process-wide "already set" flag would leave the second device without them and every
