@@ -338,6 +338,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_b, cudaEventDisableTiming);
     if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_c, cudaEventDisableTiming);
     for (int k = 0; k < PM_HOST_CHUNKS && rc == PM_OK; ++k) rc = (int)cudaEventCreateWithFlags(&p->ev_chunk[k], cudaEventDisableTiming);
+    for (int k = 0; k < PM_HOST_CHUNKS && rc == PM_OK; ++k) rc = (int)cudaEventCreateWithFlags(&p->ev_upchunk[k], cudaEventDisableTiming);
     if (rc != PM_OK) {
         pm_plan_destroy(p);
         return rc;
@@ -382,6 +383,8 @@ int pm_plan_destroy(pm_plan *p)
     if (p->ev_c) cudaEventDestroy(p->ev_c);
     for (int k = 0; k < PM_HOST_CHUNKS; ++k)
         if (p->ev_chunk[k]) cudaEventDestroy(p->ev_chunk[k]);
+    for (int k = 0; k < PM_HOST_CHUNKS; ++k)
+        if (p->ev_upchunk[k]) cudaEventDestroy(p->ev_upchunk[k]);
     if (p->s_main) cudaStreamDestroy(p->s_main);
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_down) cudaStreamDestroy(p->s_down);
@@ -955,6 +958,12 @@ int pm_resident_advance(pm_plan *p, const float *rho_d, double rho_mean, double 
     return resident_advance(p, rho_d, rho_mean, a, da, f_a1, omega_m0, pm_cu(stream));
 }
 
+// first particle of range k of a host-buffer step's PM_HOST_CHUNKS ranges (multiples of 64 particles)
+static inline int64_t host_chunk_begin(int64_t np, int k)
+{
+    return k >= PM_HOST_CHUNKS ? np : ((np * k / PM_HOST_CHUNKS) & ~(int64_t)63);
+}
+
 int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass, double a,
                  double da, double f_a1, double omega_m0, float *rho_h)
 {
@@ -964,11 +973,16 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     const size_t pbytes = (size_t)np * 3 * sizeof(float);
     const size_t mbytes = (size_t)p->nc * p->nc * p->nc * sizeof(float);
     // The host owns the state, so every call starts from the caller's particle order: upload into
-    // set 0, sort, put the particles in cell order into set 1, one resident step (set 1 -> set 0),
-    // un-permute into set 1, download.  Velocities are not needed before the gather, so their upload
-    // (s_up, after the positions) overlaps the sort, the deposit and the Poisson solve; the density
-    // download (s_down) overlaps the Poisson solve; the particle download runs in ranges behind the
-    // un-permute.
+    // set 0, sort, put the POSITIONS in cell order into set 1, deposit, Poisson solve.  The velocity upload
+    // (s_up, after the positions, in ranges) overlaps all of that; the density download (s_down) overlaps
+    // the Poisson solve.  Then the step is split where the velocities enter it: the gather proper -- the
+    // stencil sums of every particle, positions and phi only -- runs on the cell-ordered set as soon as phi is
+    // there and stores its three floats per particle at the particle's ORIGINAL index; kick and drift
+    // (pm_push, the function the fused kernels call: same bits) then run in the caller's order, range by range
+    // behind the velocity upload, each range downloaded while the next is pushed.  No velocity re-ordering, no
+    // un-permute of the results, and the device-to-host link starts right after the last velocity range has
+    // arrived (PM_HOST_SPLIT=0, or a plan without the warp-specialised gather: the fused resident step
+    // followed by an un-permute, as before).
     p->rcur = 0;
     p->rnp = np;
     p->rkeys_valid = false;
@@ -991,7 +1005,13 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
         PM_CUDA(cudaMemcpy2DAsync(p->rpos[0], pitch, pos_h, w, w, 3, cudaMemcpyHostToDevice, st));
         PM_CUDA(cudaEventRecord(p->ev_c, st));
         PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
-        PM_CUDA(cudaMemcpy2DAsync(p->rvel[0], pitch, vel_h, w, w, 3, cudaMemcpyHostToDevice, p->s_up));
+        for (int k = 0; k < PM_HOST_CHUNKS; ++k) {
+            const int64_t i0 = host_chunk_begin(np, k), i1 = host_chunk_begin(np, k + 1);
+            if (i1 > i0)
+                PM_CUDA(cudaMemcpy2DAsync(p->rvel[0] + i0, pitch, vel_h + i0, w, (size_t)(i1 - i0) * sizeof(float), 3,
+                                          cudaMemcpyHostToDevice, p->s_up));
+            PM_CUDA(cudaEventRecord(p->ev_upchunk[k], p->s_up));
+        }
     }
     PM_CUDA(cudaEventRecord(p->ev_a, p->s_up));
     tmark(1, st);             // positions uploaded
@@ -1018,6 +1038,29 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     p->rho_mean_hint = (double)np * mass / ((double)p->nc * p->nc * p->nc);
     PM_TRY(pm_k_poisson(p, p->mesh, a, omega_m0, p->mesh2, st));
     tmark(3, st);             // potential ready
+    static const bool split_off = getenv("PM_HOST_SPLIT") && atoi(getenv("PM_HOST_SPLIT")) == 0;
+    bool split = np && !split_off && pm_gather_sums_ok(p);
+    if (split) {
+        const int rc = pm_k_gather_sums(p, p->mesh2, st);   // set 1 (cell order) -> sums at the original index
+        if (rc == PM_ERR_UNSUPPORTED) split = false;        // nothing was launched: the fused route below
+        else if (rc != PM_OK) return rc;
+    }
+    if (split) {
+        tmark(4, st);         // gather done
+        p->inc_counted = false;
+        for (int k = 0; k < PM_HOST_CHUNKS; ++k) {
+            const int64_t i0 = host_chunk_begin(np, k), i1 = host_chunk_begin(np, k + 1);
+            if (i1 <= i0) continue;
+            PM_CUDA(cudaStreamWaitEvent(st, p->ev_upchunk[k], 0));
+            // caller's order: uploaded positions / velocities of set 0 -> dense [3][np] rows in set 1
+            PM_TRY(pm_k_push_rows(p, p->rpos[0], p->rvel[0], i0, i1, a, f_a1, da, p->rpos[1], p->rvel[1], st));
+            PM_CUDA(cudaEventRecord(p->ev_chunk[k], st));
+            PM_CUDA(cudaStreamWaitEvent(p->s_down, p->ev_chunk[k], 0));
+            const size_t cw = (size_t)(i1 - i0) * sizeof(float);
+            PM_CUDA(cudaMemcpy2DAsync(pos_h + i0, w, p->rpos[1] + i0, w, cw, 3, cudaMemcpyDeviceToHost, p->s_down));
+            PM_CUDA(cudaMemcpy2DAsync(vel_h + i0, w, p->rvel[1] + i0, w, cw, 3, cudaMemcpyDeviceToHost, p->s_down));
+        }
+    } else {
     PM_CUDA(cudaStreamWaitEvent(st, p->ev_a, 0));
     if (np) PM_TRY(pm_k_reorder_rows(p, p->rvel[0], p->rid[1], np, p->rvel[1], st));
     PM_TRY(pm_k_gather_kick_drift_resident(p, p->mesh2, a, f_a1, da, st));     // set 1 -> set 0
@@ -1030,7 +1073,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
         // the device-to-host link starts ~0.2 ms after the gather instead of after a full un-permute
         PM_TRY(pm_k_unpermute_scatter_aos(p, st));
         for (int k = 0; k < PM_HOST_CHUNKS; ++k) {
-            const int64_t i0 = (np * k / PM_HOST_CHUNKS) & ~(int64_t)63, i1 = k + 1 == PM_HOST_CHUNKS ? np : ((np * (k + 1) / PM_HOST_CHUNKS) & ~(int64_t)63);
+            const int64_t i0 = host_chunk_begin(np, k), i1 = host_chunk_begin(np, k + 1);
             if (i1 <= i0) continue;
             PM_TRY(pm_k_aos_rows_range(p, i0, i1, p->rpos[1], p->rvel[1], st));
             PM_CUDA(cudaEventRecord(p->ev_chunk[k], st));
@@ -1045,6 +1088,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
         PM_CUDA(cudaMemcpyAsync(pos_h, p->rpos[1], 3 * w, cudaMemcpyDeviceToHost, st));
         PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
         PM_CUDA(cudaMemcpyAsync(vel_h, p->rvel[1], 3 * w, cudaMemcpyDeviceToHost, p->s_up));
+    }
     }
     tmark(5, st);             // un-permute kernels done
     tmark(6, p->s_down);      // downloads done (chunked path)

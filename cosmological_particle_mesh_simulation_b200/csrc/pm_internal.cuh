@@ -161,6 +161,7 @@ struct pm_plan {
     cudaStream_t s_main, s_up, s_down;
     cudaEvent_t ev_a, ev_b, ev_c;
     cudaEvent_t ev_chunk[PM_HOST_CHUNKS];   // pm_step_host: un-permuted particle ranges ready for download
+    cudaEvent_t ev_upchunk[PM_HOST_CHUNKS]; // pm_step_host: velocity ranges uploaded
 
     // slab-mode scratch (nranks > 1, or a 1-rank slab plan used to test the slab kernels)
     float2 *tbuf[2];        // all-to-all staging: [nranks][nzl][nyl][nc/2] (+ side [nranks][nzl][nyl])
@@ -258,6 +259,10 @@ bool pm_unpermute_aos_ok(const pm_plan *p, const float *pos_out, const float *ve
 int pm_k_unpermute_scatter_aos(pm_plan *p, cudaStream_t st);
 int pm_k_aos_rows_range(pm_plan *p, int64_t i0, int64_t i1, float *pos_out, float *vel_out, cudaStream_t st);
 void pm_gather_step_scalars(double a_val, double f_a1, double da, PmStepParams *out);
+bool pm_gather_sums_ok(const pm_plan *p);
+int pm_k_gather_sums(pm_plan *p, const float *phi, cudaStream_t st);
+int pm_k_push_rows(pm_plan *p, const float *pos_in, const float *vel_in, int64_t i0, int64_t i1, double a_val, double f_a1,
+                   double da, float *pos_out, float *vel_out, cudaStream_t st);
 bool pm_gather_graphable(const pm_plan *p);
 int pm_k_block_stats(pm_plan *p, int rows_per_block, int cap, int64_t *out4, cudaStream_t st);
 void pm_gather_tile_shape(int *rows_per_block, int *cap);

@@ -753,10 +753,13 @@ __global__ void __launch_bounds__(128) k_gather_items(const uint32_t *__restrict
     if (zs + zc0 > z_first) emit(true, z_first, zs + zc0 - z_first, 0u, 0u);
 }
 
+// s_out != nullptr: the sums-only variant of the warp-specialised kernel (see k_gather_ws, SONLY): s_out is
+// [3][s_stride], indexed by the particle's original index.
 template <int NC>
 static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
-                                  uint32_t *cnt, cudaStream_t st)
+                                  uint32_t *cnt, cudaStream_t st, float *s_out = nullptr, int64_t s_stride = 0)
 {
+    if (s_out && !p->gather_ws) return PM_ERR_UNSUPPORTED;
     int zc = 32;
     if (const char *e = getenv("PM_GATHER_ZC")) {      // planes per CTA (tuning: shorter marches balance a clustered load)
         const int v = atoi(e);
@@ -769,7 +772,10 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
     using WsSmem = pmws::Smem<NC, PM_GT_YB, PM_GT_CAP, PM_GW_R, PM_GW_S>;
     static_assert(WsSmem::total <= 227 * 1024 / PM_GT_MINB, "PM_GT_MINB CTAs per SM (warp-specialised gather)");
     auto kern_ws = k_gather_ws<NC, PM_GT_YB, PM_GW_CW, PM_GT_CAP, PM_GW_R, PM_GW_S, PM_GT_MINB, PM_GW_PP>;
+    auto kern_ws_s = k_gather_ws<NC, PM_GT_YB, PM_GW_CW, PM_GT_CAP, PM_GW_R, PM_GW_S, PM_GT_MINB, 1, true>;
     PM_ONCE_PER_DEVICE_BEGIN(p->device)
+        PM_CUDA(cudaFuncSetAttribute(kern_ws_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem::total));
+        PM_CUDA(cudaFuncSetAttribute(kern_ws_s, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         PM_CUDA(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WsSmem::total));
@@ -788,6 +794,10 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
     A.k_kick = k_kick; A.da = da; A.aa = aa; A.raa = pm_div_rcp(aa, da); A.f_a1 = f_a1;
     A.sp = p->graph_params;
     A.items = nullptr; A.item_ctl = nullptr; A.item_cap = 0;
+    if (s_out) {
+        A.pos_out = s_out; A.sout = s_stride;
+        A.vel_out = nullptr; A.id_out = nullptr; A.keys_out = nullptr; A.mover_cnt = nullptr;
+    }
     dim3 grid(NC / PM_GT_YB, NC / zc);
     if (p->gather_ws && p->gather_items && p->gat_items && NC <= 65535) {
         const int nchunks = (NC / PM_GT_YB) * (NC / zc);
@@ -802,7 +812,8 @@ static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, d
         A.items = (const GatherItem *)p->gat_items; A.item_ctl = p->gat_ctl; A.item_cap = (int)gmax;
         grid = dim3((unsigned)gmax, 1);
     }
-    if (p->gather_ws) PM_LAUNCH(kern_ws, grid, (PM_GW_CW + 1) * 32, WsSmem::total, st, A, p->fft_sync + 0);
+    if (s_out) PM_LAUNCH(kern_ws_s, grid, (PM_GW_CW + 1) * 32, WsSmem::total, st, A, p->fft_sync + 0);
+    else if (p->gather_ws) PM_LAUNCH(kern_ws, grid, (PM_GW_CW + 1) * 32, WsSmem::total, st, A, p->fft_sync + 0);
     else PM_LAUNCH(kern, grid, PM_GT_NT, smem, st, A);
     PM_CHECK_LAUNCH();
     return PM_OK;
@@ -824,15 +835,65 @@ bool pm_gather_graphable(const pm_plan *p)
 }
 
 static int pm_try_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
-                               uint32_t *cnt, cudaStream_t st)
+                               uint32_t *cnt, cudaStream_t st, float *s_out = nullptr, int64_t s_stride = 0)
 {
     if (!p->gather_tiled || p->dep_nseg != 1 || !p->rows_valid || p->kgrad) return PM_ERR_UNSUPPORTED;
     switch (p->nc) {
-    case 128: return pm_launch_gather_tiled<128>(p, phi, k_kick, da, aa, f_a1, cnt, st);
-    case 256: return pm_launch_gather_tiled<256>(p, phi, k_kick, da, aa, f_a1, cnt, st);
-    case 512: return pm_launch_gather_tiled<512>(p, phi, k_kick, da, aa, f_a1, cnt, st);
+    case 128: return pm_launch_gather_tiled<128>(p, phi, k_kick, da, aa, f_a1, cnt, st, s_out, s_stride);
+    case 256: return pm_launch_gather_tiled<256>(p, phi, k_kick, da, aa, f_a1, cnt, st, s_out, s_stride);
+    case 512: return pm_launch_gather_tiled<512>(p, phi, k_kick, da, aa, f_a1, cnt, st, s_out, s_stride);
     default: return PM_ERR_UNSUPPORTED;
     }
+}
+
+// ---- the host-buffer step's split gather (pm_step_host) ------------------------------------------------
+// The stencil sums of every particle of the resident (cell-ordered) set rcur, stored at the particle's original
+// index in the idle half-spectrum buffer as [3][np].  PM_ERR_UNSUPPORTED when this plan has no warp-specialised
+// gather (mesh sizes other than 128/256/512, spectral-gradient option) or the buffer is too small: the caller
+// then takes the fused route.
+bool pm_gather_sums_ok(const pm_plan *p)
+{
+    const size_t spec_bytes = (size_t)p->nc * p->nc * (p->nc / 2 + 1) * sizeof(float2);
+    return !p->slab && p->spec && p->gather_tiled && p->gather_ws && p->dep_nseg == 1 && !p->kgrad &&
+           (p->nc == 128 || p->nc == 256 || p->nc == 512) && p->rnp > 0 && (size_t)p->rnp * 12 <= spec_bytes;
+}
+
+int pm_k_gather_sums(pm_plan *p, const float *phi, cudaStream_t st)
+{
+    if (!pm_gather_sums_ok(p)) return PM_ERR_UNSUPPORTED;
+    return pm_try_gather_tiled(p, phi, 0.0, 0.0, 1.0, 0.0, nullptr, st, reinterpret_cast<float *>(p->spec), p->rnp);
+}
+
+// Particles [i0, i1) of the CALLER's order: kick and drift (pm_push, the very function the fused kernels call)
+// from the uploaded positions / velocities (stride sin) and the stencil sums (stride np), into dense [3][np] rows.
+__global__ void __launch_bounds__(256) k_push_rows(const float *__restrict__ pos_in, const float *__restrict__ vel_in,
+                                                   int64_t sin, const float *__restrict__ sums, int64_t i0, int64_t i1,
+                                                   int64_t np, int nc, double k_kick, double da, double aa, double raa,
+                                                   double f_a1, float *__restrict__ pos_out, float *__restrict__ vel_out)
+{
+    const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
+    float x = pos_in[i], y = pos_in[sin + i], z = pos_in[2 * sin + i];
+    float vx = vel_in[i], vy = vel_in[sin + i], vz = vel_in[2 * sin + i];
+    const float sx = sums[i], sy = sums[np + i], sz = sums[2 * np + i];
+    pm_push(x, vx, sx, k_kick, da, aa, raa, f_a1, nc, nullptr);
+    pm_push(y, vy, sy, k_kick, da, aa, raa, f_a1, nc, nullptr);
+    pm_push(z, vz, sz, k_kick, da, aa, raa, f_a1, nc, nullptr);
+    pos_out[i] = x; pos_out[np + i] = y; pos_out[2 * np + i] = z;
+    vel_out[i] = vx; vel_out[np + i] = vy; vel_out[2 * np + i] = vz;
+}
+
+int pm_k_push_rows(pm_plan *p, const float *pos_in, const float *vel_in, int64_t i0, int64_t i1, double a_val, double f_a1,
+                   double da, float *pos_out, float *vel_out, cudaStream_t st)
+{
+    if (i1 <= i0) return PM_OK;
+    PmStepParams v;
+    pm_gather_step_scalars(a_val, f_a1, da, &v);
+    PM_LAUNCH(k_push_rows, (unsigned)((i1 - i0 + 255) / 256), 256, 0, st, pos_in, vel_in, (int64_t)p->rstride,
+              reinterpret_cast<const float *>(p->spec), i0, i1, p->rnp, p->nc, v.k_kick, v.da, v.aa, v.raa, v.f_a1, pos_out,
+              vel_out);
+    PM_CHECK_LAUNCH();
+    return PM_OK;
 }
 
 // ---- diagnostics: particles per block of mesh rows, from the row table of the last sort ----------

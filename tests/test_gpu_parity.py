@@ -579,6 +579,42 @@ def test_fused_step_and_host_step_equal_the_composed_calls(pm, golden_dir, name)
     assert np.array_equal(pn, pos.cpu().numpy()) and np.array_equal(vn, vel.cpu().numpy())
 
 
+@pytest.mark.parametrize("n_cells,n_parts,blob", [(128, 64, 0), (256, 96, 0), (128, 50, 40000), (512, 128, 0)])
+def test_host_step_split_gather_equals_the_device_step_bit_for_bit(pm, n_cells, n_parts, blob):
+    """pm_step_host on meshes that have the warp-specialised gather (128 / 256 / 512) splits the step where the
+    velocities enter it: stencil sums of the cell-ordered particles stored at the original index (k_gather_ws,
+    SONLY), then kick + drift in the caller's order behind the chunked velocity upload (k_push_rows).  Same
+    pm_push, so the results must equal pm.step's on the same arrays bit for bit -- incl. a crowded blob (work
+    list), particle counts that are not multiples of the chunk granularity, and positions == N_CELLS (Q4)."""
+    cfg = O.Config(N_CELLS=n_cells, N_PARTS=n_parts, STEPS=100)
+    pm.set_config(cfg_ns(cfg))
+    rng = np.random.default_rng(n_cells + n_parts)
+    npart = n_parts ** 3
+    pos_h = rng.uniform(0, n_cells, (3, npart)).astype(np.float32)
+    if blob:
+        pos_h[:, :blob] = (n_cells / 2 + rng.normal(0, 1.0, (3, blob))).astype(np.float32) % n_cells
+    pos_h[:, -1] = [float(n_cells), 0.0, n_cells - 1e-3]
+    pos_h[:, -2] = [3.5, float(n_cells), float(n_cells)]
+    vel_h = rng.normal(0, 0.5, (3, npart)).astype(np.float32)
+    mass = (n_cells / n_parts) ** 3
+    a, da = 0.3, 0.0099
+    pd, vd = dev(pos_h), dev(vel_h)
+    rho_d = torch.empty((n_cells,) * 3, dtype=torch.float32, device="cuda")
+    ph, vh = torch.from_numpy(pos_h.copy()).pin_memory(), torch.from_numpy(vel_h.copy()).pin_memory()
+    rh = torch.empty((n_cells,) * 3, dtype=torch.float32).pin_memory()
+    for k in range(3):                       # three consecutive steps: the output of one is the input of the next
+        pm.step(pd, vd, a + k * da, da, mass=mass, rho_out=rho_d)
+        pm.step_host(ph, vh, a + k * da, da, mass=mass, rho_out=rh)
+        assert torch.equal(ph, pd.cpu()), f"positions, step {k}"
+        assert torch.equal(vh, vd.cpu()), f"velocities, step {k}"
+        assert torch.equal(rh, rho_d.cpu()), f"density, step {k}"
+    pn, vn = pos_h.copy(), vel_h.copy()      # pageable NumPy buffers, no density
+    pm.step_host(pn, vn, a, da, mass=mass)
+    p1, v1 = dev(pos_h), dev(vel_h)
+    pm.step(p1, v1, a, da, mass=mass)
+    assert np.array_equal(pn, p1.cpu().numpy()) and np.array_equal(vn, v1.cpu().numpy())
+
+
 def test_numpy_drop_in_signatures(pm, golden_dir):
     """The reference's loop body (pmesh.py:60-61) on NumPy arrays, unchanged call shapes."""
     g, cfg = load_case(golden_dir, "free16")
