@@ -98,7 +98,7 @@ struct Smem {
 // issue slots (43 %) or DRAM (46 %).
 // SONLY (the host-buffer step, pm_step_host): the kernel stops after the gather proper -- the three stencil
 // sums s_x, s_y, s_z of a particle, which is everything pm_push needs from the mesh -- and stores them at the
-// particle's ORIGINAL index (pos_out[d * sout + id]); velocities are neither read for arithmetic nor written,
+// particle's ORIGINAL index (one float4 record: ((float4 *)pos_out)[id]); velocities are neither read for arithmetic nor written,
 // so the kernel can run while they are still on their way over PCIe, and the push itself is done in the
 // caller's order afterwards (k_push_rows, same pm_push).
 template <int NC, int YB, int CW, int CAP, int R, int S, int MINB, int PP = 1, bool SONLY = false>
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) k_gather_ws(GatherTiledAr
         }
         const float sx = pm_gp<0>(v, t), sy = pm_gp<1>(v, t), sz = pm_gp<2>(v, t);
         if constexpr (SONLY) {
-            A.pos_out[id] = sx; A.pos_out[A.sout + id] = sy; A.pos_out[2 * A.sout + id] = sz;
+            reinterpret_cast<float4 *>(A.pos_out)[id] = make_float4(sx, sy, sz, 0.0f);   // one 16-byte store, not three 4-byte ones
             return;
         }
         pm_push(x, vx, sx, A.k_kick, A.da, A.aa, A.raa, A.f_a1, NC, nullptr);

@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(128) k_gather_items(const uint32_t *__restrict
 }
 
 // s_out != nullptr: the sums-only variant of the warp-specialised kernel (see k_gather_ws, SONLY): s_out is
-// [3][s_stride], indexed by the particle's original index.
+// an array of float4 records indexed by the particle's original index.
 template <int NC>
 static int pm_launch_gather_tiled(pm_plan *p, const float *phi, double k_kick, double da, double aa, double f_a1,
                                   uint32_t *cnt, cudaStream_t st, float *s_out = nullptr, int64_t s_stride = 0)
@@ -848,14 +848,14 @@ static int pm_try_gather_tiled(pm_plan *p, const float *phi, double k_kick, doub
 
 // ---- the host-buffer step's split gather (pm_step_host) ------------------------------------------------
 // The stencil sums of every particle of the resident (cell-ordered) set rcur, stored at the particle's original
-// index in the idle half-spectrum buffer as [3][np].  PM_ERR_UNSUPPORTED when this plan has no warp-specialised
+// index in the idle half-spectrum buffer as one (s_x, s_y, s_z, -) record per particle.  PM_ERR_UNSUPPORTED when this plan has no warp-specialised
 // gather (mesh sizes other than 128/256/512, spectral-gradient option) or the buffer is too small: the caller
 // then takes the fused route.
 bool pm_gather_sums_ok(const pm_plan *p)
 {
     const size_t spec_bytes = (size_t)p->nc * p->nc * (p->nc / 2 + 1) * sizeof(float2);
     return !p->slab && p->spec && p->gather_tiled && p->gather_ws && p->dep_nseg == 1 && !p->kgrad &&
-           (p->nc == 128 || p->nc == 256 || p->nc == 512) && p->rnp > 0 && (size_t)p->rnp * 12 <= spec_bytes;
+           (p->nc == 128 || p->nc == 256 || p->nc == 512) && p->rnp > 0 && (size_t)p->rnp * 16 <= spec_bytes;
 }
 
 int pm_k_gather_sums(pm_plan *p, const float *phi, cudaStream_t st)
@@ -865,9 +865,9 @@ int pm_k_gather_sums(pm_plan *p, const float *phi, cudaStream_t st)
 }
 
 // Particles [i0, i1) of the CALLER's order: kick and drift (pm_push, the very function the fused kernels call)
-// from the uploaded positions / velocities (stride sin) and the stencil sums (stride np), into dense [3][np] rows.
+// from the uploaded positions / velocities (stride sin) and the stencil-sum records, into dense [3][np] rows.
 __global__ void __launch_bounds__(256) k_push_rows(const float *__restrict__ pos_in, const float *__restrict__ vel_in,
-                                                   int64_t sin, const float *__restrict__ sums, int64_t i0, int64_t i1,
+                                                   int64_t sin, const float4 *__restrict__ sums, int64_t i0, int64_t i1,
                                                    int64_t np, int nc, double k_kick, double da, double aa, double raa,
                                                    double f_a1, float *__restrict__ pos_out, float *__restrict__ vel_out)
 {
@@ -875,7 +875,8 @@ __global__ void __launch_bounds__(256) k_push_rows(const float *__restrict__ pos
     if (i >= i1) return;
     float x = pos_in[i], y = pos_in[sin + i], z = pos_in[2 * sin + i];
     float vx = vel_in[i], vy = vel_in[sin + i], vz = vel_in[2 * sin + i];
-    const float sx = sums[i], sy = sums[np + i], sz = sums[2 * np + i];
+    const float4 s4 = sums[i];
+    const float sx = s4.x, sy = s4.y, sz = s4.z;
     pm_push(x, vx, sx, k_kick, da, aa, raa, f_a1, nc, nullptr);
     pm_push(y, vy, sy, k_kick, da, aa, raa, f_a1, nc, nullptr);
     pm_push(z, vz, sz, k_kick, da, aa, raa, f_a1, nc, nullptr);
@@ -890,7 +891,7 @@ int pm_k_push_rows(pm_plan *p, const float *pos_in, const float *vel_in, int64_t
     PmStepParams v;
     pm_gather_step_scalars(a_val, f_a1, da, &v);
     PM_LAUNCH(k_push_rows, (unsigned)((i1 - i0 + 255) / 256), 256, 0, st, pos_in, vel_in, (int64_t)p->rstride,
-              reinterpret_cast<const float *>(p->spec), i0, i1, p->rnp, p->nc, v.k_kick, v.da, v.aa, v.raa, v.f_a1, pos_out,
+              reinterpret_cast<const float4 *>(p->spec), i0, i1, p->rnp, p->nc, v.k_kick, v.da, v.aa, v.raa, v.f_a1, pos_out,
               vel_out);
     PM_CHECK_LAUNCH();
     return PM_OK;

@@ -467,18 +467,35 @@ __global__ void __launch_bounds__(kThreads, 3) k_radix_sort(RadixArgs A)
 #pragma unroll
         for (int q = 0; q < DPT; ++q) s_scan[tid + q * kThreads] = 0u;
         __syncthreads();
-        for (uint32_t t = t0; t < t1; ++t) {
-            const uint32_t base = t * kTile;
+        // All loads of a tile first, then the digits, and no branch around a load (the index is clamped instead):
+        // with `i < n ? load(i) : ...` inside the digit loop every load sat in its own reconvergence region, one
+        // DRAM latency after the other (ncu source page of the 16.7 M-entry sort, call LL: the shift behind each
+        // load held 27 % of the kernel's samples).  Measured effect (call MM): none to speak of -- full sort 1.11 ->
+        // 1.10 ms, movers' sort unchanged -- so the kernel is bound elsewhere (24 warps per SM, issue 20 %: the
+        // match -> shared-memory read-modify-write -> shuffle chain of the ranking phase); kept because it is the
+        // better code, recorded because it was not the fix.
+        auto hist_tiles = [&](auto ld) {
+            for (uint32_t t = t0; t < t1; ++t) {
+                const uint32_t base = t * kTile;
+                uint64_t v[kRadixItems];
 #pragma unroll
-            for (int k = 0; k < kRadixItems; ++k) {
-                const uint32_t i = base + k * kThreads + tid;
-                // one shared-memory atomic per distinct digit of the warp: the high digits of a nearly
-                // sorted list are all the same, which would serialise 32 ways otherwise
-                const uint32_t d = i < n ? ((uint32_t)(load(i) >> shift) & mask) : (uint32_t)NB + lane;
-                const unsigned peers = __match_any_sync(full, d);
-                if (i < n && lane == __ffs(peers) - 1) atomicAdd(&s_scan[d], (uint32_t)__popc(peers));
+                for (int k = 0; k < kRadixItems; ++k) {
+                    const uint32_t i = base + k * kThreads + tid;
+                    v[k] = ld(i < n ? i : n - 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < kRadixItems; ++k) {
+                    const uint32_t i = base + k * kThreads + tid;
+                    const uint32_t d = i < n ? ((uint32_t)(v[k] >> shift) & mask) : (uint32_t)NB + lane;   // idle lanes match nobody
+                    // one shared-memory atomic per distinct digit of the warp: the high digits of a nearly
+                    // sorted list are all the same, which would serialise 32 ways otherwise
+                    const unsigned peers = __match_any_sync(full, d);
+                    if (i < n && lane == __ffs(peers) - 1) atomicAdd(&s_scan[d], (uint32_t)__popc(peers));
+                }
             }
-        }
+        };
+        if (synth) hist_tiles([&](uint32_t i) -> uint64_t { return ((uint64_t)J.in_keys32[i] << 32) | (uint64_t)i; });
+        else hist_tiles([&](uint32_t i) -> uint64_t { return __ldcg(src + i); });
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < DPT; ++q) A.hist[(size_t)c * NB + tid + q * kThreads] = s_scan[tid + q * kThreads];
