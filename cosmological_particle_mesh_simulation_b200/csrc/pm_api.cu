@@ -1017,7 +1017,14 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     tmark(1, st);             // positions uploaded
     tmark(2, p->s_up);        // velocities uploaded
     PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->rstride, p->keys, nullptr, st));
-    PM_TRY(pm_k_sort(p, np, 0, st));
+    static const bool split_off = getenv("PM_HOST_SPLIT") && atoi(getenv("PM_HOST_SPLIT")) == 0;
+    const bool want_split = np && !split_off && pm_gather_sums_ok(p);
+    p->sort_rows_only = want_split;      // grouped by mesh row is all the split route needs (pm_k_sort)
+    {
+        const int rc = pm_k_sort(p, np, 0, st);
+        p->sort_rows_only = false;
+        if (rc != PM_OK) return rc;
+    }
     PM_TRY(pm_k_row_offsets(p, np, st));
     if (np) {
         // The caller's order is arbitrary, and reading it through the sort permutation costs the deposit and
@@ -1038,8 +1045,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     p->rho_mean_hint = (double)np * mass / ((double)p->nc * p->nc * p->nc);
     PM_TRY(pm_k_poisson(p, p->mesh, a, omega_m0, p->mesh2, st));
     tmark(3, st);             // potential ready
-    static const bool split_off = getenv("PM_HOST_SPLIT") && atoi(getenv("PM_HOST_SPLIT")) == 0;
-    bool split = np && !split_off && pm_gather_sums_ok(p);
+    bool split = want_split;
     if (split) {
         const int rc = pm_k_gather_sums(p, p->mesh2, st);   // set 1 (cell order) -> sums at the original index
         if (rc == PM_ERR_UNSUPPORTED) split = false;        // nothing was launched: the fused route below

@@ -162,6 +162,7 @@ struct pm_plan {
     cudaEvent_t ev_a, ev_b, ev_c;
     cudaEvent_t ev_chunk[PM_HOST_CHUNKS];   // pm_step_host: un-permuted particle ranges ready for download
     cudaEvent_t ev_upchunk[PM_HOST_CHUNKS]; // pm_step_host: velocity ranges uploaded
+    bool sort_rows_only;      // pm_step_host (split route): the next full sort orders by mesh ROW only (see pm_k_sort)
 
     // slab-mode scratch (nranks > 1, or a 1-rank slab plan used to test the slab kernels)
     float2 *tbuf[2];        // all-to-all staging: [nranks][nzl][nyl][nc/2] (+ side [nranks][nzl][nyl])

@@ -731,8 +731,24 @@ int pm_k_sort(pm_plan *p, int64_t np, int64_t n_old, cudaStream_t st)
     A.job[1].n_ptr = nullptr; A.job[1].n_fixed = (uint32_t)np;
     A.job[1].bit0 = 32; A.job[1].passes = passes;
     A.select = &ctl->full;
+    int dig_launch = dig;
+    if (p->sort_rows_only && force_full) {
+        // The host-buffer step (pm_step_host, split route) sorts particles it will never see again: the tile deposit
+        // and the row-block gather only need them grouped by mesh ROW (the row table), and their results do not
+        // depend on the order inside a row (exact integer accumulation; per-particle gather).  Sorting on the row
+        // bits alone -- stable, so a row keeps the caller's order -- saves one pass of three on 128^3..512^3 meshes.
+        const RowArgs ra = row_args(p);
+        int xbits = 0;
+        while ((1 << xbits) < p->nc) ++xbits;
+        if ((1 << xbits) == p->nc && ra.xseg == p->nc && p->key_bits > xbits) {
+            const int rbits = p->key_bits - xbits;
+            dig_launch = radix_digit(rbits);
+            A.job[1].bit0 = 32 + xbits;
+            A.job[1].passes = radix_passes(rbits, dig_launch);
+        }
+    }
     {
-        const int rc = launch_radix(p, A, dig, st);
+        const int rc = launch_radix(p, A, dig_launch, st);
         if (rc != PM_OK) return rc;
     }
     if (!force_full) {
