@@ -384,9 +384,16 @@ PM_API int pm_resident_advance(pm_plan *plan, const float *rho_d, double rho_mea
                                double f_a1, double omega_m0, pm_stream_t stream);
 /*
  * The same loop body for a caller that keeps its state in host memory like the reference does
- * (NumPy arrays): uploads pos_h/vel_h, runs pm_step, downloads the updated pos_h/vel_h (and
+ * (NumPy arrays): uploads pos_h/vel_h, runs the step, downloads the updated pos_h/vel_h IN PLACE (and
  * rho_h when not NULL).  Pinned host buffers make the copies asynchronous and overlapped;
  * pageable ones work but are slower.  Returns after the results are in host memory.
+ * The results are those of pm_step bit for bit.  Inside, the step is arranged around the two PCIe
+ * directions: positions are uploaded first; sort, deposit and Poisson solve run
+ * under the velocity upload; on 128^3 / 256^3 / 512^3 meshes the gather proper then stores every
+ * particle's three stencil sums at its original index and kick + drift run in the caller's order,
+ * range by range behind the arriving velocities, each range downloaded while the next is pushed --
+ * so parts of vel_h are overwritten with results while later parts are still being read.
+ * PM_HOST_SPLIT=0 (environment) selects the older route: fused gather, un-permute, download.
  */
 PM_API int pm_step_host(pm_plan *plan, float *pos_h, float *vel_h, int64_t np, double mass, double a,
                  double da, double f_a1, double omega_m0, float *rho_h);
