@@ -339,6 +339,7 @@ static int plan_create(pm_plan **out, const Geometry &g, int64_t np_capacity, in
     if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_c, cudaEventDisableTiming);
     for (int k = 0; k < PM_HOST_CHUNKS && rc == PM_OK; ++k) rc = (int)cudaEventCreateWithFlags(&p->ev_chunk[k], cudaEventDisableTiming);
     for (int k = 0; k < PM_HOST_CHUNKS && rc == PM_OK; ++k) rc = (int)cudaEventCreateWithFlags(&p->ev_upchunk[k], cudaEventDisableTiming);
+    if (rc == PM_OK) rc = (int)cudaEventCreateWithFlags(&p->ev_x, cudaEventDisableTiming);
     if (rc != PM_OK) {
         pm_plan_destroy(p);
         return rc;
@@ -385,6 +386,7 @@ int pm_plan_destroy(pm_plan *p)
         if (p->ev_chunk[k]) cudaEventDestroy(p->ev_chunk[k]);
     for (int k = 0; k < PM_HOST_CHUNKS; ++k)
         if (p->ev_upchunk[k]) cudaEventDestroy(p->ev_upchunk[k]);
+    if (p->ev_x) cudaEventDestroy(p->ev_x);
     if (p->s_main) cudaStreamDestroy(p->s_main);
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_down) cudaStreamDestroy(p->s_down);
@@ -972,6 +974,12 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     PM_TRY(guard.enter(p->device));
     const size_t pbytes = (size_t)np * 3 * sizeof(float);
     const size_t mbytes = (size_t)p->nc * p->nc * p->nc * sizeof(float);
+    // This call works on the plan's own streams, and it returns only when its results are in host memory: wait
+    // first for whatever the caller still has in flight on this device.  A pm_step / density() enqueued on the
+    // caller's stream a moment ago uses the same workspace (keys, permutation, meshes), and nothing else orders
+    // the plan's streams behind it -- with the sort now starting 2.4 ms into the call, such a step's gather was
+    // still reading the permutation this call's sort overwrites (tests/test_gpu_parity.py, the 512^3 case).
+    PM_CUDA(cudaDeviceSynchronize());
     // The host owns the state, so every call starts from the caller's particle order: upload into
     // set 0, sort, put the POSITIONS in cell order into set 1, deposit, Poisson solve.  The velocity upload
     // (s_up, after the positions, in ranges) overlaps all of that; the density download (s_down) overlaps
@@ -998,13 +1006,24 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
     };
     tmark(0, p->s_main);
     cudaStream_t st = p->s_main;
+    static const bool split_off = getenv("PM_HOST_SPLIT") && atoi(getenv("PM_HOST_SPLIT")) == 0;
+    const bool want_split = np && !split_off && pm_gather_sums_ok(p);
     if (np) {
         // positions first and alone on the link: everything up to the gather needs only them.  (Issued
         // together, the two uploads share the link and the positions arrive last: measured 7.3 ms instead
-        // of 3.6 ms before the first kernel could start.)
-        PM_CUDA(cudaMemcpy2DAsync(p->rpos[0], pitch, pos_h, w, w, 3, cudaMemcpyHostToDevice, st));
-        PM_CUDA(cudaEventRecord(p->ev_c, st));
-        PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
+        // of 3.6 ms before the first kernel could start.)  On the split route the sort is by mesh ROW, which
+        // needs y and z only: those two rows go first and the keys and the sort run under the upload of x.
+        if (want_split) {
+            PM_CUDA(cudaMemcpy2DAsync(p->rpos[0] + p->rstride, pitch, pos_h + np, w, w, 2, cudaMemcpyHostToDevice, st));
+            PM_CUDA(cudaEventRecord(p->ev_c, st));
+            PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
+            PM_CUDA(cudaMemcpyAsync(p->rpos[0], pos_h, w, cudaMemcpyHostToDevice, p->s_up));
+            PM_CUDA(cudaEventRecord(p->ev_x, p->s_up));
+        } else {
+            PM_CUDA(cudaMemcpy2DAsync(p->rpos[0], pitch, pos_h, w, w, 3, cudaMemcpyHostToDevice, st));
+            PM_CUDA(cudaEventRecord(p->ev_c, st));
+            PM_CUDA(cudaStreamWaitEvent(p->s_up, p->ev_c, 0));
+        }
         for (int k = 0; k < PM_HOST_CHUNKS; ++k) {
             const int64_t i0 = host_chunk_begin(np, k), i1 = host_chunk_begin(np, k + 1);
             if (i1 > i0)
@@ -1014,11 +1033,9 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
         }
     }
     PM_CUDA(cudaEventRecord(p->ev_a, p->s_up));
-    tmark(1, st);             // positions uploaded
+    tmark(1, st);             // positions uploaded (split route: y and z)
     tmark(2, p->s_up);        // velocities uploaded
-    PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->rstride, p->keys, nullptr, st));
-    static const bool split_off = getenv("PM_HOST_SPLIT") && atoi(getenv("PM_HOST_SPLIT")) == 0;
-    const bool want_split = np && !split_off && pm_gather_sums_ok(p);
+    PM_TRY(pm_k_cell_keys(p, p->rpos[0], np, p->rstride, p->keys, nullptr, st, want_split));
     p->sort_rows_only = want_split;      // grouped by mesh row is all the split route needs (pm_k_sort)
     {
         const int rc = pm_k_sort(p, np, 0, st);
@@ -1026,6 +1043,7 @@ int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass
         if (rc != PM_OK) return rc;
     }
     PM_TRY(pm_k_row_offsets(p, np, st));
+    if (want_split) PM_CUDA(cudaStreamWaitEvent(st, p->ev_x, 0));     // from here on x is needed
     if (np) {
         // The caller's order is arbitrary, and reading it through the sort permutation costs the deposit and
         // above all the gather a random 4-byte access per value (gather: 2.8 ms instead of 0.5 ms).  So the

@@ -162,6 +162,7 @@ struct pm_plan {
     cudaEvent_t ev_a, ev_b, ev_c;
     cudaEvent_t ev_chunk[PM_HOST_CHUNKS];   // pm_step_host: un-permuted particle ranges ready for download
     cudaEvent_t ev_upchunk[PM_HOST_CHUNKS]; // pm_step_host: velocity ranges uploaded
+    cudaEvent_t ev_x;                       // pm_step_host (split route): x coordinates uploaded
     bool sort_rows_only;      // pm_step_host (split route): the next full sort orders by mesh ROW only (see pm_k_sort)
 
     // slab-mode scratch (nranks > 1, or a 1-rank slab plan used to test the slab kernels)
@@ -244,7 +245,7 @@ int pm_k_sort_u32(pm_plan *p, const uint32_t *in, uint32_t *out, int64_t count, 
 
 // pm_particles.cu
 int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uint32_t *keys,
-                   uint32_t *order, cudaStream_t st);
+                   uint32_t *order, cudaStream_t st, bool rows_only = false);
 int pm_k_row_offsets(pm_plan *p, int64_t np, cudaStream_t st);
 int pm_k_deposit(pm_plan *p, const float *pos, int64_t stride, double mass, float *rho,
                  cudaStream_t st);

@@ -51,11 +51,13 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float *__restrict__ px,
                                                    int z0, int nzl, uint32_t *__restrict__ keys,
                                                    uint32_t *__restrict__ order)
 {
+    // px == nullptr: keys of the mesh ROW only (x cell 0) -- the host-buffer step sorts by row and computes them
+    // while the x coordinates are still on their way over PCIe
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (VEC) {
         int64_t i = t * 4;
         if (i >= np) return;
-        float4 x = *reinterpret_cast<const float4 *>(px + i);
+        float4 x = px ? *reinterpret_cast<const float4 *>(px + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 y = *reinterpret_cast<const float4 *>(py + i);
         float4 z = *reinterpret_cast<const float4 *>(pz + i);
         uint4 k;
@@ -70,16 +72,16 @@ __global__ void __launch_bounds__(256) k_cell_keys(const float *__restrict__ px,
         }
     } else {
         if (t >= np) return;
-        keys[t] = pm_key(px[t], py[t], pz[t], nc, z0, nzl);
+        keys[t] = pm_key(px ? px[t] : 0.f, py[t], pz[t], nc, z0, nzl);
         if (order) order[t] = (uint32_t)t;
     }
 }
 
 int pm_k_cell_keys(pm_plan *p, const float *pos, int64_t np, int64_t stride, uint32_t *keys,
-                   uint32_t *order, cudaStream_t st)
+                   uint32_t *order, cudaStream_t st, bool rows_only)
 {
     if (np == 0) return PM_OK;
-    const float *px = pos, *py = pos + stride, *pz = pos + 2 * stride;
+    const float *px = rows_only ? nullptr : pos, *py = pos + stride, *pz = pos + 2 * stride;
     bool vec = (np % 4 == 0) && (stride % 4 == 0) && ((uintptr_t)pos % 16 == 0) && ((uintptr_t)keys % 16 == 0) &&
                (!order || (uintptr_t)order % 16 == 0);
     if (vec) {

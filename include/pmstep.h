@@ -394,6 +394,9 @@ PM_API int pm_resident_advance(pm_plan *plan, const float *rho_d, double rho_mea
  * range by range behind the arriving velocities, each range downloaded while the next is pushed --
  * so parts of vel_h are overwritten with results while later parts are still being read.
  * PM_HOST_SPLIT=0 (environment) selects the older route: fused gather, un-permute, download.
+ * The call runs on the plan's own streams: it starts with a device synchronisation (work the caller
+ * enqueued on other streams with this plan must be finished before the workspace is reused) and ends
+ * with the results in host memory.
  */
 PM_API int pm_step_host(pm_plan *plan, float *pos_h, float *vel_h, int64_t np, double mass, double a,
                  double da, double f_a1, double omega_m0, float *rho_h);
