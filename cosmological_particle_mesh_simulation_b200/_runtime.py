@@ -11,6 +11,7 @@ import importlib
 import os
 import sys
 import threading
+import weakref
 
 import numpy as np
 import torch
@@ -166,6 +167,8 @@ def lib():
             "pm_ic_slab_from_f32": (i32, [vp, i64, vp, vp]),
             "pm_ic_slab_displacement_k": (i32, [ctypes.POINTER(ICParams), i32, vp, i32, i32, vp, vp]),
             "pm_ic_slab_particles": (i32, [ctypes.POINTER(ICParams), i32, vp, i32, i32, ctypes.c_uint64, vp, vp, vp, vp, vp]),
+            "pm_host_register": (i32, [vp, sz]),
+            "pm_host_unregister": (i32, [vp]),
             "pm_plan_profile_begin": (i32, [vp, i32]),
             "pm_plan_profile_read": (i32, [vp, vp, ctypes.POINTER(i32)]),
         }
@@ -199,6 +202,7 @@ EXPORTED_SYMBOLS = (
     "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",
     "pm_ic_slab_workspace_bytes", "pm_ic_noise_range", "pm_ic_slab_rho_k", "pm_ic_slab_fft", "pm_ic_slab_real_f32",
     "pm_ic_slab_from_f32", "pm_ic_slab_displacement_k", "pm_ic_slab_particles",
+    "pm_host_register", "pm_host_unregister",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")
@@ -378,6 +382,100 @@ def check_dev_f32(t: torch.Tensor, shape=None, name="tensor"):
     return t
 
 
+# ---------------------------------------------------------------------------------------------
+# host arrays of the drop-in calls (NumPy in -> NumPy out, like the reference)
+# ---------------------------------------------------------------------------------------------
+# The reference's driver keeps positions and velocities in two NumPy arrays for the whole run and hands
+# them to density() / advance_time() every step (src/pmesh.py:56-63).  Copied as pageable memory, with a
+# fresh host array for every result, that loop spent 0.57 s per step at 256^3 particles on a 512^3 mesh,
+# almost all of it in staged copies and first-touch page faults.  So: a large array that keeps coming back
+# is page-locked in place once (pm_host_register; un-registered when the array dies), after which torch
+# sees it as pinned memory and copies by DMA; results that the reference returns as fresh arrays (the
+# density mesh) come from a small pool of pinned buffers that are handed out again once the previous
+# array -- and every view of it -- is gone; in-place results are copied straight into the caller's array.
+# PM_PIN_HOST_ARRAYS=0 turns both off.
+_PIN_MIN_BYTES = 1 << 20
+_pin_enabled = os.environ.get("PM_PIN_HOST_ARRAYS", "1").strip() != "0"
+_pinned_ranges = {}        # (address, bytes) -> weakref.finalize of the array that was registered
+_pin_refused = set()       # ranges the driver would not register (kept so that we ask only once)
+_host_pool = []            # [pinned tensor, weakref to the holder of the array handed out]
+_HOST_POOL_MAX = 4
+
+
+def _unpin(key):
+    _pinned_ranges.pop(key, None)
+    if _lib is not None:
+        _lib.pm_host_unregister(key[0])
+
+
+def pin_host_array(a) -> bool:
+    """Page-lock the memory of NumPy array `a` in place (once; released when `a` is garbage-collected)."""
+    if not _pin_enabled or not isinstance(a, np.ndarray) or a.nbytes < _PIN_MIN_BYTES or not a.flags.c_contiguous:
+        return False
+    key = (int(a.ctypes.data), int(a.nbytes))
+    if key in _pinned_ranges:
+        return True
+    if key in _pin_refused:
+        return False
+    if lib().pm_host_register(key[0], key[1]) != 0:
+        _pin_refused.add(key)
+        return False
+    try:
+        fin = weakref.finalize(a, _unpin, key)
+        fin.atexit = False         # at interpreter exit the driver releases everything itself
+        _pinned_ranges[key] = fin
+    except TypeError:          # an ndarray subclass without weak references
+        lib().pm_host_unregister(key[0])
+        _pin_refused.add(key)
+        return False
+    return True
+
+
+class _PinnedHolder:
+    """Owner of a pooled pinned buffer as NumPy sees it: every array (and view) made from it keeps it alive."""
+
+    def __init__(self, tensor):
+        self._tensor = tensor
+        self.__array_interface__ = {"shape": tuple(tensor.shape), "typestr": "<f4", "data": (tensor.data_ptr(), False),
+                                    "version": 3, "strides": None}
+
+
+def to_host_array(t: torch.Tensor):
+    """A fresh float32 NumPy array with the contents of CUDA tensor `t`, from the pinned pool when possible."""
+    if not _pin_enabled or t.dtype != torch.float32 or t.numel() * 4 < _PIN_MIN_BYTES:
+        return t.cpu().numpy()
+    slot = None
+    for entry in _host_pool:
+        if entry[1]() is None and tuple(entry[0].shape) == tuple(t.shape):
+            slot = entry
+            break
+    if slot is None:
+        if len(_host_pool) >= _HOST_POOL_MAX:
+            free = [e for e in _host_pool if e[1]() is None]
+            if not free:
+                return t.cpu().numpy()
+            _host_pool.remove(free[0])
+        try:
+            slot = [torch.empty(tuple(t.shape), dtype=torch.float32, pin_memory=True), lambda: None]
+        except RuntimeError:
+            return t.cpu().numpy()
+        _host_pool.append(slot)
+    slot[0].copy_(t)                       # synchronous device-to-host DMA
+    holder = _PinnedHolder(slot[0])
+    slot[1] = weakref.ref(holder)
+    return np.asarray(holder)
+
+
+def copy_to_host(dst, src_dev: torch.Tensor):
+    """src_dev (CUDA) into the caller's NumPy array or CPU tensor `dst`, without an intermediate host array."""
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src_dev)
+        return
+    pin_host_array(dst)
+    torch.from_numpy(dst).copy_(src_dev)
+
+
 def to_device(x, device: int) -> torch.Tensor:
     a = as_host_f32(x)
+    pin_host_array(a)
     return torch.from_numpy(a).to(f"cuda:{device}", non_blocking=False)

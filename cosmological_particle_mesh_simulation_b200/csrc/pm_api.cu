@@ -966,6 +966,26 @@ static inline int64_t host_chunk_begin(int64_t np, int k)
     return k >= PM_HOST_CHUNKS ? np : ((np * k / PM_HOST_CHUNKS) & ~(int64_t)63);
 }
 
+int pm_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return PM_ERR_INVALID;
+    if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();      // not an error of this library's work: leave no state behind
+        return PM_ERR_UNSUPPORTED;
+    }
+    return PM_OK;
+}
+
+int pm_host_unregister(void *ptr)
+{
+    if (!ptr) return PM_ERR_INVALID;
+    if (cudaHostUnregister(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return PM_ERR_UNSUPPORTED;
+    }
+    return PM_OK;
+}
+
 int pm_step_host(pm_plan *p, float *pos_h, float *vel_h, int64_t np, double mass, double a,
                  double da, double f_a1, double omega_m0, float *rho_h)
 {

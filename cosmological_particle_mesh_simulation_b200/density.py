@@ -42,6 +42,5 @@ def density(positions, mass):
     if rt.is_host(positions):
         dev = rt.current_device()
         rho = _density_device(rt.to_device(positions, dev), mass, n_cells)
-        host = rho.cpu()
-        return host if isinstance(positions, torch.Tensor) else host.numpy()
+        return rho.cpu() if isinstance(positions, torch.Tensor) else rt.to_host_array(rho)
     return _density_device(positions, mass, n_cells)

@@ -43,10 +43,7 @@ def _integrate_device(positions, velocities, a_val, f_a1, da, potentials, acc=No
 
 
 def _copy_back(dst, src_dev):
-    if isinstance(dst, torch.Tensor):
-        dst.copy_(src_dev)
-    else:
-        np.copyto(dst, src_dev.cpu().numpy())
+    rt.copy_to_host(dst, src_dev)      # straight into the caller's array (page-locked in place when it is large)
 
 
 def integrate(positions, velocities, a_val, f_a1, da, potentials):

@@ -35,6 +35,6 @@ def _potential_device(rho, fgrid, a, out=None):
 def potential(density, fgrid, a):
     if rt.is_host(density):
         dev = rt.current_device()
-        phi = _potential_device(rt.to_device(density, dev), fgrid, a).cpu()
-        return phi if isinstance(density, torch.Tensor) else phi.numpy()
+        phi = _potential_device(rt.to_device(density, dev), fgrid, a)
+        return phi.cpu() if isinstance(density, torch.Tensor) else rt.to_host_array(phi)
     return _potential_device(density, fgrid, a)

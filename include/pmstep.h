@@ -402,6 +402,17 @@ PM_API int pm_step_host(pm_plan *plan, float *pos_h, float *vel_h, int64_t np, d
                  double da, double f_a1, double omega_m0, float *rho_h);
 
 /*
+ * Page-locking of caller-owned host arrays (the reference keeps its state in NumPy arrays that live for
+ * the whole run, src/pmesh.py:39-52: registering them once makes every later copy a direct DMA at the
+ * PCIe rate instead of a staged pageable copy).  pm_host_register returns PM_OK, or PM_ERR_UNSUPPORTED
+ * when the range cannot be registered (overlaps a registered range, unsupported memory ...) -- the
+ * caller then simply uses the array as pageable memory; no CUDA error state is left behind.  The range
+ * must be unregistered before the memory is freed.
+ */
+PM_API int pm_host_register(void *ptr, size_t bytes);
+PM_API int pm_host_unregister(void *ptr);
+
+/*
  * Per-stage device timing of pm_step (bench.py's live roofline).  pm_plan_profile_begin arms a
  * ring of CUDA events for up to max_steps calls of pm_step (0 disarms it); each armed call records
  * an event on the caller's stream between stages -- no synchronisation, no extra kernels.

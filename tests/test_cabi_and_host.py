@@ -236,3 +236,35 @@ def test_raw_writes_of_the_package_are_made_visible_to_torch():
     assert t._version > v1
     assert S._session is None
     S.before_raw_access(t, None, h)          # nothing to flush
+
+
+def test_pooled_host_arrays_stay_busy_while_any_view_lives():
+    """_runtime._PinnedHolder: what NumPy sees as the owner of a pooled result buffer (density() on NumPy input
+    returns such arrays) -- it must stay alive, i.e. the buffer must not be handed out again, as long as the array
+    OR ANY VIEW of it exists; small arrays are never page-locked."""
+    import gc
+    import weakref
+    import numpy as np
+    import torch
+    from cosmological_particle_mesh_simulation_b200 import _runtime as rt
+    t = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    h = rt._PinnedHolder(t)
+    alive = weakref.ref(h)
+    a = np.asarray(h)
+    assert a.shape == (3, 4) and a.dtype == np.float32 and a[2, 3] == 11.0
+    a[0, 0] = 7.0
+    assert float(t[0, 0]) == 7.0                      # the array IS the buffer, not a copy
+    del h
+    row = a[1]
+    flat = a.reshape(-1)[2:5]
+    del a
+    gc.collect()
+    assert alive() is not None                        # two views left
+    del row
+    gc.collect()
+    assert alive() is not None
+    del flat
+    gc.collect()
+    assert alive() is None                            # now the pool may reuse the buffer
+    assert rt.pin_host_array(np.zeros(16, dtype=np.float32)) is False          # too small: no library call
+    assert rt.pin_host_array(np.zeros((1 << 19, 2), dtype=np.float32)[:, 0]) is False   # not contiguous

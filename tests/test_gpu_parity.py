@@ -628,6 +628,44 @@ def test_numpy_drop_in_signatures(pm, golden_dir):
     assert rel_l2(vel, g["vel_1"]) <= REL_L2
 
 
+def test_numpy_drop_in_loop_pins_the_callers_arrays_and_pools_the_results(pm):
+    """The reference's loop body on NumPy arrays (src/pmesh.py:60-61), several steps: the two particle arrays are
+    page-locked in place once, density() hands out pooled pinned result arrays and never one that is still
+    referenced (directly or through a view), and the numbers are those of the same calls on CUDA tensors."""
+    from cosmological_particle_mesh_simulation_b200 import _runtime as rt
+    cfg = O.Config(N_CELLS=128, N_PARTS=64, STEPS=100)
+    pm.set_config(cfg_ns(cfg))
+    pos_h, vel_h = O.lattice_ic(64, 128, seed=5, vel_rms=0.3)
+    pos, vel = pos_h.copy(), vel_h.copy()
+    pd, vd = dev(pos_h), dev(vel_h)
+    fg = pm.fourier_grid()
+    pm.set_resident_dropin(False)              # the CUDA-tensor side runs the same stateless kernels
+    try:
+        kept, a, da = [], 0.3, 0.0099
+        for k in range(4):
+            rho = pm.density(pos, 8.0)                                  # pmesh.py:60
+            rho_d = pm.density(pd, 8.0)
+            assert isinstance(rho, np.ndarray) and rho.dtype == np.float32 and rho.shape == (128,) * 3
+            assert np.array_equal(rho, rho_d.cpu().numpy())
+            kept.append((rho[3], rho[3].copy()))                         # a VIEW kept by the caller, and its contents
+            pos, vel = pm.advance_time(rho, pos, vel, fg, a, da)        # pmesh.py:61
+            pd, vd = pm.advance_time(rho_d, pd, vd, fg, a, da)
+            assert np.array_equal(pos, pd.cpu().numpy()) and np.array_equal(vel, vd.cpu().numpy())
+            a += da
+        for view, want in kept:                                          # no pooled buffer was reused under a live view
+            assert np.array_equal(view, want)
+        key = (pos.ctypes.data, pos.nbytes)
+        if rt._pin_enabled:
+            assert key in rt._pinned_ranges and (vel.ctypes.data, vel.nbytes) in rt._pinned_ranges
+            assert 1 <= len(rt._host_pool) <= rt._HOST_POOL_MAX
+        del pos, vel, kept, rho, view
+        import gc
+        gc.collect()
+        assert key not in rt._pinned_ranges                              # un-registered with the array
+    finally:
+        pm.set_resident_dropin(True)
+
+
 def test_lazy_drop_in_equals_eager_drop_in_bit_for_bit(pm, golden_dir):
     """set_resident_dropin("lazy"): the reference's loop body (src/pmesh.py:60-61, names rebound to the
     returned objects) runs on the resident state with NO per-step write-back; the caller-visible tensors
