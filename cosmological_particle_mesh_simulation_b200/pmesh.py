@@ -15,6 +15,7 @@ except ImportError:
     import _runtime as rt
     import _session
     from cosmology import f
+import numpy as np
 import torch
 
 
@@ -57,6 +58,11 @@ def step_host(positions, velocities, a, da, mass=None, rho_out=None, device=None
     p = rt.as_host_f32(positions)
     v = rt.as_host_f32(velocities, p.shape)
     r = rt.as_host_f32(rho_out, (n, n, n)) if rho_out is not None else None
+    # NumPy arrays that the caller keeps for the run (src/pmesh.py:39-52) are page-locked in place the first time
+    # they are seen, so that the copies of this call are asynchronous DMA like those from pinned tensors
+    for arr, src in ((p, positions), (v, velocities), (r, rho_out)):
+        if isinstance(src, np.ndarray):
+            rt.pin_host_array(arr)
     dev = rt.current_device() if device is None else int(device)
     plan = rt.get_plan(n, p.shape[1], dev)
     rt.check(rt.lib().pm_step_host(plan.handle, p.ctypes.data, v.ctypes.data, p.shape[1],
