@@ -477,5 +477,6 @@ def copy_to_host(dst, src_dev: torch.Tensor):
 
 def to_device(x, device: int) -> torch.Tensor:
     a = as_host_f32(x)
-    pin_host_array(a)
+    if isinstance(x, np.ndarray):      # the caller's own array object (a CPU tensor can be pinned by its owner)
+        pin_host_array(a)
     return torch.from_numpy(a).to(f"cuda:{device}", non_blocking=False)
