@@ -167,6 +167,7 @@ def lib():
             "pm_ic_slab_from_f32": (i32, [vp, i64, vp, vp]),
             "pm_ic_slab_displacement_k": (i32, [ctypes.POINTER(ICParams), i32, vp, i32, i32, vp, vp]),
             "pm_ic_slab_particles": (i32, [ctypes.POINTER(ICParams), i32, vp, i32, i32, ctypes.c_uint64, vp, vp, vp, vp, vp]),
+            "pm_step_host_range": (i32, [i64, i32, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i32)]),
             "pm_host_register": (i32, [vp, sz]),
             "pm_host_unregister": (i32, [vp]),
             "pm_plan_profile_begin": (i32, [vp, i32]),
@@ -202,7 +203,7 @@ EXPORTED_SYMBOLS = (
     "pm_ic_jitter", "pm_ic_power_spectrum", "pm_ic_gaussian_random_field", "pm_ic_zeldovich",
     "pm_ic_slab_workspace_bytes", "pm_ic_noise_range", "pm_ic_slab_rho_k", "pm_ic_slab_fft", "pm_ic_slab_real_f32",
     "pm_ic_slab_from_f32", "pm_ic_slab_displacement_k", "pm_ic_slab_particles",
-    "pm_host_register", "pm_host_unregister",
+    "pm_host_register", "pm_host_unregister", "pm_step_host_range",
 )
 
 STAGE_NAMES = ("keys", "sort", "rows", "deposit", "fft_r2c", "green", "fft_c2r", "gather_kick_drift")

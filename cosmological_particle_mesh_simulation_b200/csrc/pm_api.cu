@@ -966,6 +966,15 @@ static inline int64_t host_chunk_begin(int64_t np, int k)
     return k >= PM_HOST_CHUNKS ? np : ((np * k / PM_HOST_CHUNKS) & ~(int64_t)63);
 }
 
+int pm_step_host_range(int64_t np, int k, int64_t *i0, int64_t *i1, int *n_ranges)
+{
+    if (np < 0 || k < 0 || k >= PM_HOST_CHUNKS || !i0 || !i1) return PM_ERR_INVALID;
+    *i0 = host_chunk_begin(np, k);
+    *i1 = host_chunk_begin(np, k + 1);
+    if (n_ranges) *n_ranges = PM_HOST_CHUNKS;
+    return PM_OK;
+}
+
 int pm_host_register(void *ptr, size_t bytes)
 {
     if (!ptr || bytes == 0) return PM_ERR_INVALID;

@@ -400,6 +400,9 @@ PM_API int pm_resident_advance(pm_plan *plan, const float *rho_d, double rho_mea
  */
 PM_API int pm_step_host(pm_plan *plan, float *pos_h, float *vel_h, int64_t np, double mass, double a,
                  double da, double f_a1, double omega_m0, float *rho_h);
+/* Diagnostic (host arithmetic only, no device needed): the particle range [*i0, *i1) that pm_step_host
+ * uploads, pushes and downloads as range k of its *n_ranges ranges for np particles. */
+PM_API int pm_step_host_range(int64_t np, int k, int64_t *i0, int64_t *i1, int *n_ranges);
 
 /*
  * Page-locking of caller-owned host arrays (the reference keeps its state in NumPy arrays that live for

@@ -268,3 +268,26 @@ def test_pooled_host_arrays_stay_busy_while_any_view_lives():
     assert alive() is None                            # now the pool may reuse the buffer
     assert rt.pin_host_array(np.zeros(16, dtype=np.float32)) is False          # too small: no library call
     assert rt.pin_host_array(np.zeros((1 << 19, 2), dtype=np.float32)[:, 0]) is False   # not contiguous
+
+
+def test_host_step_ranges_cover_every_particle_once():
+    """pm_step_host_range: the ranges pm_step_host uploads velocities in, pushes and downloads (host arithmetic of
+    the library itself, no device): consecutive, disjoint, together [0, np), and every boundary except the last a
+    multiple of 64 particles (256-byte aligned rows for the 2-D copies)."""
+    import ctypes
+    from cosmological_particle_mesh_simulation_b200 import _runtime as rt
+    L = rt.lib()
+    for np_ in [0, 1, 63, 64, 65, 100, 255, 256, 257, 4096, 125000, 262144, 884736, 16777216, 16777215, (1 << 31) + 12345]:
+        i0, i1, n = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int(0)
+        assert L.pm_step_host_range(np_, 0, ctypes.byref(i0), ctypes.byref(i1), ctypes.byref(n)) == 0
+        assert n.value >= 1
+        end = 0
+        for k in range(n.value):
+            assert L.pm_step_host_range(np_, k, ctypes.byref(i0), ctypes.byref(i1), None) == 0
+            assert i0.value == end and i1.value >= i0.value
+            if k + 1 < n.value:
+                assert i1.value % 64 == 0
+            end = i1.value
+        assert end == np_
+        assert L.pm_step_host_range(np_, n.value, ctypes.byref(i0), ctypes.byref(i1), None) != 0
+    assert L.pm_step_host_range(-1, 0, ctypes.byref(i0), ctypes.byref(i1), None) != 0
